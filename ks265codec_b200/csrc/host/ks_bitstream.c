@@ -1,0 +1,751 @@
+/*
+ * ks_bitstream.c -- HEVC Main-profile bitstream writer for the ks265 B200 encoder (host side).
+ * See ks_bitstream.h for the reference counterparts.  Section numbers refer to ITU-T H.265 (v3+).
+ */
+#include "ks_bitstream.h"
+#include <stdlib.h>
+#include <string.h>
+
+/* =========================================================== raw bit writer ======================== */
+typedef struct { uint8_t *buf; size_t cap, pos; uint32_t cur; int nbits; int overflow; } bitw;
+
+static void bw_init(bitw *b, uint8_t *buf, size_t cap) { b->buf = buf; b->cap = cap; b->pos = 0; b->cur = 0; b->nbits = 0; b->overflow = 0; }
+static void bw_byte(bitw *b, uint8_t v) { if (b->pos < b->cap) b->buf[b->pos++] = v; else b->overflow = 1; }
+static void bw_put(bitw *b, uint32_t v, int n)
+{
+    while (n > 0) {
+        int take = 8 - b->nbits; if (take > n) take = n;
+        b->cur = (b->cur << take) | ((v >> (n - take)) & ((1u << take) - 1));
+        b->nbits += take; n -= take;
+        if (b->nbits == 8) { bw_byte(b, (uint8_t)b->cur); b->cur = 0; b->nbits = 0; }
+    }
+}
+static void bw_ue(bitw *b, uint32_t v)
+{
+    uint32_t x = v + 1; int len = 0;
+    while ((x >> len) > 1) len++;
+    bw_put(b, 0, len); bw_put(b, x, len + 1);
+}
+static void bw_se(bitw *b, int v) { bw_ue(b, v > 0 ? (uint32_t)(2 * v - 1) : (uint32_t)(-2 * v)); }
+static void bw_trailing(bitw *b) { bw_put(b, 1, 1); if (b->nbits) bw_put(b, 0, 8 - b->nbits); }
+
+/* Annex-B NAL: start code + 2-byte header + emulation-prevented payload (7.4.2 / Annex B) */
+static long nal_emit(uint8_t *out, size_t cap, int nal_type, int tid, const uint8_t *rbsp, size_t n)
+{
+    size_t o = 0; int zeros = 0;
+    if (cap < 6) return -1;
+    out[o++] = 0; out[o++] = 0; out[o++] = 0; out[o++] = 1;
+    out[o++] = (uint8_t)(nal_type << 1); out[o++] = (uint8_t)(tid + 1);
+    for (size_t i = 0; i < n; i++) {
+        if (o + 2 > cap) return -1;
+        if (zeros >= 2 && rbsp[i] <= 3) { out[o++] = 3; zeros = 0; }
+        out[o++] = rbsp[i];
+        zeros = rbsp[i] == 0 ? zeros + 1 : 0;
+    }
+    return (long)o;
+}
+
+/* =========================================================== parameter sets ======================== */
+static int level_idc(const ks_stream_params *sp)
+{   /* Table A.8 by luma picture size (reference emits 93/120/150 for 720p/1080p/2160p) */
+    long ps = (long)sp->width * sp->height;
+    if (ps <= 552960) return 90; if (ps <= 983040) return 93; if (ps <= 2228224) return 120;
+    if (ps <= 8912896) return 150; return 180;
+}
+static void write_ptl(bitw *b, const ks_stream_params *sp)
+{   /* 7.3.3 profile_tier_level(1, 0): Main profile, main tier */
+    bw_put(b, 0, 2); bw_put(b, 0, 1); bw_put(b, 1, 5);
+    bw_put(b, 0x60000000u, 32);            /* compatibility flags: profiles 1 and 2 */
+    bw_put(b, 1, 1); bw_put(b, 0, 1); bw_put(b, 0, 1); bw_put(b, 1, 1);   /* progressive, !interlaced, !non-packed, frame-only */
+    bw_put(b, 0, 32); bw_put(b, 0, 12);    /* 43 reserved zero bits + inbld/reserved */
+    bw_put(b, (uint32_t)level_idc(sp), 8);
+}
+long ks_write_vps(const ks_stream_params *sp, uint8_t *out, size_t cap)
+{
+    uint8_t tmp[128]; bitw b; bw_init(&b, tmp, sizeof(tmp));
+    bw_put(&b, 0, 4); bw_put(&b, 3, 2); bw_put(&b, 0, 6); bw_put(&b, 0, 3); bw_put(&b, 1, 1); bw_put(&b, 0xffff, 16);
+    write_ptl(&b, sp);
+    bw_put(&b, 1, 1); bw_ue(&b, 1); bw_ue(&b, 0); bw_ue(&b, 0);      /* sub_layer_ordering_info: dpb 2, no reorder */
+    bw_put(&b, 0, 6); bw_ue(&b, 0); bw_put(&b, 0, 1); bw_put(&b, 0, 1);
+    bw_trailing(&b);
+    return nal_emit(out, cap, 32, 0, tmp, b.pos);
+}
+long ks_write_sps(const ks_stream_params *sp, uint8_t *out, size_t cap)
+{
+    uint8_t tmp[256]; bitw b; bw_init(&b, tmp, sizeof(tmp));
+    bw_put(&b, 0, 4); bw_put(&b, 0, 3); bw_put(&b, 1, 1);
+    write_ptl(&b, sp);
+    bw_ue(&b, 0); bw_ue(&b, 1);
+    bw_ue(&b, (uint32_t)sp->width); bw_ue(&b, (uint32_t)sp->height);
+    if (sp->width != sp->disp_width || sp->height != sp->disp_height) {
+        bw_put(&b, 1, 1); bw_ue(&b, 0); bw_ue(&b, (uint32_t)(sp->width - sp->disp_width) / 2);
+        bw_ue(&b, 0); bw_ue(&b, (uint32_t)(sp->height - sp->disp_height) / 2);
+    } else bw_put(&b, 0, 1);
+    bw_ue(&b, 0); bw_ue(&b, 0);
+    bw_ue(&b, (uint32_t)sp->log2_max_poc_lsb - 4);
+    bw_put(&b, 1, 1); bw_ue(&b, 1); bw_ue(&b, 0); bw_ue(&b, 0);
+    bw_ue(&b, KS_CELL_LOG2 - 3);                 /* log2_min_luma_coding_block_size_minus3 */
+    bw_ue(&b, KS_CTU_LOG2 - KS_CELL_LOG2);       /* log2_diff_max_min_luma_coding_block_size */
+    bw_ue(&b, 0); bw_ue(&b, KS_MAX_TB_LOG2 - 2); /* TB 4..32 */
+    bw_ue(&b, 0); bw_ue(&b, 0);                  /* max_transform_hierarchy_depth inter/intra = 0 (reference: 0/0) */
+    bw_put(&b, 0, 1); bw_put(&b, 0, 1);          /* scaling lists off, AMP off */
+    bw_put(&b, (uint32_t)sp->sao, 1); bw_put(&b, 0, 1);
+    bw_ue(&b, 0); bw_put(&b, 0, 1);              /* no SPS RPS candidates, no long-term */
+    bw_put(&b, 0, 1);                            /* sps_temporal_mvp_enabled_flag = 0 */
+    bw_put(&b, (uint32_t)sp->strong_intra_smoothing, 1);
+    bw_put(&b, 0, 1); bw_put(&b, 0, 1);          /* no VUI, no extension */
+    bw_trailing(&b);
+    return nal_emit(out, cap, 33, 0, tmp, b.pos);
+}
+long ks_write_pps(const ks_stream_params *sp, uint8_t *out, size_t cap)
+{
+    uint8_t tmp[128]; bitw b; bw_init(&b, tmp, sizeof(tmp));
+    bw_ue(&b, 0); bw_ue(&b, 0); bw_put(&b, 0, 1); bw_put(&b, 0, 1); bw_put(&b, 0, 3);
+    bw_put(&b, (uint32_t)sp->sign_hiding, 1); bw_put(&b, 0, 1);
+    bw_ue(&b, 0); bw_ue(&b, 0); bw_se(&b, 0);
+    bw_put(&b, 0, 1); bw_put(&b, 0, 1); bw_put(&b, 0, 1);    /* constrained intra, transform skip, cu_qp_delta */
+    bw_se(&b, 0); bw_se(&b, 0); bw_put(&b, 0, 1);
+    bw_put(&b, 0, 1); bw_put(&b, 0, 1); bw_put(&b, 0, 1);    /* weighted pred / bipred, transquant bypass */
+    bw_put(&b, 0, 1); bw_put(&b, 0, 1);                      /* tiles, entropy_coding_sync */
+    bw_put(&b, 1, 1);                                        /* loop filter across slices */
+    bw_put(&b, 1, 1); bw_put(&b, 1, 1); bw_put(&b, 0, 1);    /* deblocking control present, override enabled, not disabled */
+    bw_se(&b, sp->pps_beta_offset_div2); bw_se(&b, sp->pps_tc_offset_div2);
+    bw_put(&b, 0, 1); bw_put(&b, 0, 1); bw_ue(&b, 0); bw_put(&b, 0, 1); bw_put(&b, 0, 1);
+    bw_trailing(&b);
+    return nal_emit(out, cap, 34, 0, tmp, b.pos);
+}
+
+/* =========================================================== CABAC engine (9.3.4) ================== */
+static const uint8_t range_lps[64][4] = {
+    {128,176,208,240},{128,167,197,227},{128,158,187,216},{123,150,178,205},{116,142,169,195},{111,135,160,185},{105,128,152,175},{100,122,144,166},
+    {95,116,137,158},{90,110,130,150},{85,104,123,142},{81,99,117,135},{77,94,111,128},{73,89,105,122},{69,85,100,116},{66,80,95,110},
+    {62,76,90,104},{59,72,86,99},{56,69,81,94},{53,65,77,89},{51,62,73,85},{48,59,69,80},{46,56,66,76},{43,53,63,72},
+    {41,50,59,69},{39,48,56,65},{37,45,54,62},{35,43,51,59},{33,41,48,56},{32,39,46,53},{30,37,43,50},{29,35,41,48},
+    {27,33,39,45},{26,31,37,43},{24,30,35,41},{23,28,33,39},{22,27,32,37},{21,26,30,35},{20,24,29,33},{19,23,27,31},
+    {18,22,26,30},{17,21,25,28},{16,20,23,27},{15,19,22,25},{14,18,21,24},{14,17,20,23},{13,16,19,22},{12,15,18,21},
+    {12,14,17,20},{11,14,16,19},{11,13,15,18},{10,12,15,17},{10,12,14,16},{9,11,13,15},{9,11,12,14},{8,10,12,14},
+    {8,9,11,13},{7,9,11,12},{7,9,10,12},{7,8,10,11},{6,8,9,11},{6,7,9,10},{6,7,8,9},{2,2,2,2}};
+static const uint8_t next_lps[64] = {0,0,1,2,2,4,4,5,6,7,8,9,9,11,11,12,13,13,15,15,16,16,18,18,19,19,21,21,22,22,23,24,
+    24,25,26,26,27,27,28,29,29,30,30,30,31,32,32,33,33,33,34,34,35,35,35,36,36,36,37,37,37,38,38,63};
+static const uint8_t renorm_tab[32] = {6,5,4,4,3,3,3,3,2,2,2,2,2,2,2,2,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1};
+
+/* context layout */
+enum {
+    CX_SPLIT_CU = 0, CX_SKIP = 3, CX_MERGE_FLAG = 6, CX_MERGE_IDX = 7, CX_PART_MODE = 8, CX_PRED_MODE = 12,
+    CX_PREV_INTRA = 13, CX_CHROMA_PRED = 14, CX_MVD = 15, CX_CBF_LUMA = 17, CX_CBF_CHROMA = 19, CX_ROOT_CBF = 24,
+    CX_LAST_X = 25, CX_LAST_Y = 43, CX_CSBF = 61, CX_SIG = 65, CX_GT1 = 107, CX_GT2 = 131, CX_MVP_IDX = 137,
+    CX_SAO_MERGE = 138, CX_SAO_TYPE = 139, CX_COUNT = 140
+};
+#define CNU 154
+/* init values (Tables 9-5..9-37), rows: initType 0 (I), 1 (P), 2 (B) */
+static const uint8_t init_values[3][CX_COUNT] = {
+ { /* I */
+   139,141,157, CNU,CNU,CNU, CNU, CNU, 184,CNU,CNU,CNU, CNU, 184, 63, CNU,CNU, 111,141, 94,138,182,154,154, CNU,
+   110,110,124,125,140,153,125,127,140,109,111,143,127,111,79,108,123,63,
+   110,110,124,125,140,153,125,127,140,109,111,143,127,111,79,108,123,63,
+   91,171,134,141,
+   111,111,125,110,110,94,124,108,124,107,125,141,179,153,125,107,125,141,179,153,125,107,125,141,179,153,125,
+   140,139,182,182,152,136,152,136,153,136,139,111,136,139,111,
+   140,92,137,138,140,152,138,139,153,74,149,92,139,107,122,152,140,179,166,182,140,227,122,197,
+   138,153,136,167,152,152, CNU, 153, 200 },
+ { /* P */
+   107,139,126, 197,185,201, 110, 122, 154,139,154,154, 149, 154, 152, 140,198, 153,111, 149,107,167,154,154, 79,
+   125,110,94,110,95,79,125,111,110,78,110,111,111,95,94,108,123,108,
+   125,110,94,110,95,79,125,111,110,78,110,111,111,95,94,108,123,108,
+   121,140,61,154,
+   155,154,139,153,139,123,123,63,153,166,183,140,136,153,154,166,183,140,136,153,154,166,183,140,136,153,154,
+   170,153,123,123,107,121,107,121,167,151,183,140,151,183,140,
+   154,196,196,167,154,152,167,182,182,134,149,136,153,121,136,137,169,194,166,167,154,167,137,182,
+   107,167,91,122,107,167, 168, 153, 185 },
+ { /* B */
+   107,139,126, 197,185,201, 154, 137, 154,139,154,154, 134, 183, 152, 169,198, 153,111, 149,92,167,154,154, 79,
+   125,110,124,110,95,94,125,111,111,79,125,126,111,111,79,108,123,93,
+   125,110,124,110,95,94,125,111,111,79,125,126,111,111,79,108,123,93,
+   121,140,61,154,
+   170,154,139,153,139,123,123,63,124,166,183,140,136,153,154,166,183,140,136,153,154,166,183,140,136,153,154,
+   170,153,138,138,122,121,122,121,167,151,183,140,151,183,140,
+   154,196,167,167,154,152,167,182,182,134,149,136,153,121,136,122,169,208,166,167,154,152,167,182,
+   107,167,91,107,107,167, 168, 153, 160 },
+};
+
+typedef struct {
+    uint32_t low, range; int bits_left, buffered, num_buffered;
+    uint8_t *buf; size_t pos, cap; int overflow;
+    uint8_t ctx[CX_COUNT];         /* (pStateIdx<<1)|valMps */
+} cabac;
+
+static void cb_byte(cabac *c, int v) { if (c->pos < c->cap) c->buf[c->pos++] = (uint8_t)v; else c->overflow = 1; }
+static void cb_init(cabac *c, uint8_t *buf, size_t cap, int init_type, int qp)
+{
+    c->low = 0; c->range = 510; c->bits_left = 23; c->buffered = 0xff; c->num_buffered = 0;
+    c->buf = buf; c->cap = cap; c->pos = 0; c->overflow = 0;
+    if (qp < 0) qp = 0; if (qp > 51) qp = 51;
+    for (int i = 0; i < CX_COUNT; i++) {      /* 9.3.2.2 */
+        int v = init_values[init_type][i];
+        int m = (v >> 4) * 5 - 45, n = ((v & 15) << 3) - 16;
+        int pre = ((m * qp) >> 4) + n;
+        if (pre < 1) pre = 1; if (pre > 126) pre = 126;
+        int mps = pre > 63;
+        c->ctx[i] = (uint8_t)(((mps ? pre - 64 : 63 - pre) << 1) | mps);
+    }
+}
+static void cb_write_out(cabac *c)
+{
+    uint32_t lead = c->low >> (24 - c->bits_left);
+    c->bits_left += 8;
+    c->low &= 0xffffffffu >> c->bits_left;
+    if (lead == 0xff) c->num_buffered++;
+    else if (c->num_buffered > 0) {
+        uint32_t carry = lead >> 8;
+        cb_byte(c, (int)(c->buffered + carry));
+        c->buffered = (int)(lead & 0xff);
+        int byte = (int)((0xff + carry) & 0xff);
+        while (c->num_buffered > 1) { cb_byte(c, byte); c->num_buffered--; }
+    } else { c->num_buffered = 1; c->buffered = (int)lead; }
+}
+static inline void cb_bin(cabac *c, int ctx, int bin)
+{
+    uint8_t s = c->ctx[ctx];
+    uint32_t state = s >> 1, mps = s & 1;
+    uint32_t lps = range_lps[state][(c->range >> 6) & 3];
+    c->range -= lps;
+    if ((uint32_t)bin != mps) {
+        int nb = renorm_tab[lps >> 3];
+        c->low = (c->low + c->range) << nb; c->range = lps << nb;
+        if (state == 0) mps ^= 1;
+        c->ctx[ctx] = (uint8_t)((next_lps[state] << 1) | mps);
+        c->bits_left -= nb;
+    } else {
+        c->ctx[ctx] = (uint8_t)(((state < 62 ? state + 1 : state) << 1) | mps);
+        if (c->range >= 256) return;
+        c->low <<= 1; c->range <<= 1; c->bits_left--;
+    }
+    if (c->bits_left < 12) cb_write_out(c);
+}
+static inline void cb_bypass(cabac *c, int bin)
+{
+    c->low <<= 1; if (bin) c->low += c->range;
+    if (--c->bits_left < 12) cb_write_out(c);
+}
+static void cb_bypass_bins(cabac *c, uint32_t bins, int n)
+{
+    while (n > 8) {
+        n -= 8; uint32_t pat = bins >> n;
+        c->low <<= 8; c->low += c->range * pat; bins -= pat << n;
+        c->bits_left -= 8; if (c->bits_left < 12) cb_write_out(c);
+    }
+    c->low <<= n; c->low += c->range * bins; c->bits_left -= n;
+    if (c->bits_left < 12) cb_write_out(c);
+}
+static void cb_terminate(cabac *c, int bin)
+{
+    c->range -= 2;
+    if (bin) { c->low += c->range; c->low <<= 7; c->range = 2 << 7; c->bits_left -= 7; }
+    else if (c->range >= 256) return;
+    else { c->low <<= 1; c->range <<= 1; c->bits_left--; }
+    if (c->bits_left < 12) cb_write_out(c);
+}
+static void cb_finish(cabac *c)
+{   /* flush (9.3.4.5) then rbsp_slice_segment_trailing_bits */
+    if (c->low >> (32 - c->bits_left)) {
+        cb_byte(c, c->buffered + 1);
+        while (c->num_buffered > 1) { cb_byte(c, 0x00); c->num_buffered--; }
+        c->low -= 1u << (32 - c->bits_left);
+    } else {
+        if (c->num_buffered > 0) cb_byte(c, c->buffered);
+        while (c->num_buffered > 1) { cb_byte(c, 0xff); c->num_buffered--; }
+    }
+    /* write (low >> 8) using 24 - bits_left bits, then stop bit + alignment */
+    int n = 24 - c->bits_left;
+    uint64_t v = ((uint64_t)(c->low >> 8) & ((1ull << n) - 1));
+    v = (v << 1) | 1; n += 1;
+    int pad = (8 - (n & 7)) & 7;
+    v <<= pad; n += pad;
+    for (int i = n - 8; i >= 0; i -= 8) cb_byte(c, (int)((v >> i) & 0xff));
+}
+
+/* =========================================================== slice data ============================ */
+typedef struct {
+    const ks_stream_params *sp; const ks_slice_params *sl; const ks_frame_syn *syn;
+    cabac cb;
+    uint8_t *skip;       /* per cell: coded as skip */
+    uint8_t *scan4;      /* diag scan of a 4x4: pos -> (y<<2)|x */
+    uint8_t scan_cg[4][64]; /* diag scan of CG grid for log2 tb 2..5: idx -> (y<<3)|x */
+    uint16_t cg_prefix[KS_CTU / 4 + 2 * KS_CTU / 8 + 1]; /* per-CTU prefix popcounts of CG rows */
+    int cur_ctu;
+} slice_enc;
+
+static uint8_t g_scan4[16];
+static uint8_t g_scan_cg[4][64];
+static int g_scan_ready;
+static void build_diag(uint8_t *dst, int n, int shift)
+{   /* 6.5.3 up-right diagonal scan */
+    int i = 0, x = 0, y = 0;
+    for (;;) {
+        while (y >= 0) { if (x < n && y < n) dst[i++] = (uint8_t)((y << shift) | x); y--; x++; }
+        y = x; x = 0;
+        if (i >= n * n) break;
+    }
+}
+static void scans_init(void)
+{
+    if (g_scan_ready) return;
+    build_diag(g_scan4, 4, 2);
+    for (int l = 2; l <= 5; l++) build_diag(g_scan_cg[l - 2], 1 << (l - 2), 3);
+    g_scan_ready = 1;
+}
+
+static inline const ks_cell *cell_at(const ks_frame_syn *s, int x, int y) { return &s->cells[(y >> KS_CELL_LOG2) * s->cells_w + (x >> KS_CELL_LOG2)]; }
+static inline int zidx(int x, int y)
+{
+    int cx = (x >> KS_CELL_LOG2) & 3, cy = (y >> KS_CELL_LOG2) & 3;
+    return (cx & 1) | ((cy & 1) << 1) | ((cx & 2) << 1) | ((cy & 2) << 2);
+}
+/* 6.4.1 z-scan availability of the block containing (xn,yn) for a block whose origin is (xc,yc) */
+static int avail(const ks_frame_syn *s, int xc, int yc, int xn, int yn)
+{
+    if (xn < 0 || yn < 0 || xn >= s->width || yn >= s->height) return 0;
+    int ac = (yc >> KS_CTU_LOG2) * s->ctus_w + (xc >> KS_CTU_LOG2), an = (yn >> KS_CTU_LOG2) * s->ctus_w + (xn >> KS_CTU_LOG2);
+    if (an != ac) return an < ac;
+    return zidx(xn, yn) < zidx(xc, yc);
+}
+
+/* ---- coefficient access: CG (cgx,cgy in 4x4 units of the component plane) -> 16 levels or NULL ---- */
+static void ctu_prefix(slice_enc *e, int ctu)
+{
+    const ks_ctu_syn *c = &e->syn->ctus[ctu];
+    int acc = 0, k = 0;
+    for (int i = 0; i < 16; i++) { e->cg_prefix[k++] = (uint16_t)acc; acc += __builtin_popcount(c->cg_y[i]); }
+    for (int i = 0; i < 8; i++) { e->cg_prefix[k++] = (uint16_t)acc; acc += __builtin_popcount(c->cg_cb[i]); }
+    for (int i = 0; i < 8; i++) { e->cg_prefix[k++] = (uint16_t)acc; acc += __builtin_popcount(c->cg_cr[i]); }
+    e->cg_prefix[k] = (uint16_t)acc;
+    e->cur_ctu = ctu;
+}
+static const int16_t *cg_levels(slice_enc *e, int comp, int cgx, int cgy)
+{   /* (cgx,cgy) relative to the current CTU, in CG units of that component */
+    const ks_ctu_syn *c = &e->syn->ctus[e->cur_ctu];
+    uint32_t bits; int row;
+    if (comp == 0) { bits = c->cg_y[cgy]; row = cgy; }
+    else if (comp == 1) { bits = c->cg_cb[cgy]; row = 16 + cgy; }
+    else { bits = c->cg_cr[cgy]; row = 24 + cgy; }
+    if (!((bits >> cgx) & 1)) return NULL;
+    uint32_t idx = c->cg_base + e->cg_prefix[row] + (uint32_t)__builtin_popcount(bits & ((1u << cgx) - 1));
+    return e->syn->levels + (size_t)idx * 16;
+}
+
+/* ---- 7.3.8.11 residual_coding for one transform block (diagonal scan only: TB >= 8 or inter) ---- */
+static void code_residual(slice_enc *e, int comp, int x0c, int y0c, int log2)
+{   /* x0c,y0c: TB origin inside the CTU in component samples */
+    cabac *c = &e->cb;
+    int ncg = 1 << (log2 - 2);           /* CGs per side */
+    const uint8_t *scg = g_scan_cg[log2 - 2];
+    const int16_t *cgp[64];
+    int last_cg = -1;
+    for (int i = 0; i < ncg * ncg; i++) {
+        int cx = scg[i] & 7, cy = scg[i] >> 3;
+        cgp[i] = cg_levels(e, comp, (x0c >> 2) + cx, (y0c >> 2) + cy);
+        if (cgp[i]) last_cg = i;
+    }
+    if (last_cg < 0) return;             /* caller guarantees cbf=1 */
+    int last_pos = 15;
+    while (!cgp[last_cg][g_scan4[last_pos]]) last_pos--;
+    int lx = ((scg[last_cg] & 7) << 2) + (g_scan4[last_pos] & 3), ly = ((scg[last_cg] >> 3) << 2) + (g_scan4[last_pos] >> 2);
+    /* last_sig_coeff_{x,y}_prefix / suffix (9.3.4.2.3) */
+    static const uint8_t group_idx[32] = {0,1,2,3,4,4,5,5,6,6,6,6,7,7,7,7,8,8,8,8,8,8,8,8,9,9,9,9,9,9,9,9};
+    static const uint8_t min_in_group[10] = {0,1,2,3,4,6,8,12,16,24};
+    int off, shift;
+    if (comp == 0) { off = 3 * (log2 - 2) + ((log2 - 1) >> 2); shift = (log2 + 1) >> 2; }
+    else { off = 15; shift = log2 - 2; }
+    int gx = group_idx[lx], gy = group_idx[ly], cmax = (log2 << 1) - 1, i;
+    for (i = 0; i < gx; i++) cb_bin(c, CX_LAST_X + off + (i >> shift), 1);
+    if (gx < cmax) cb_bin(c, CX_LAST_X + off + (i >> shift), 0);
+    for (i = 0; i < gy; i++) cb_bin(c, CX_LAST_Y + off + (i >> shift), 1);
+    if (gy < cmax) cb_bin(c, CX_LAST_Y + off + (i >> shift), 0);
+    if (gx > 3) cb_bypass_bins(c, (uint32_t)(lx - min_in_group[gx]), (gx - 2) >> 1);
+    if (gy > 3) cb_bypass_bins(c, (uint32_t)(ly - min_in_group[gy]), (gy - 2) >> 1);
+
+    uint8_t csbf[8][8]; memset(csbf, 0, sizeof(csbf));
+    int c1 = 1;
+    for (int i2 = last_cg; i2 >= 0; i2--) {
+        int cx = scg[i2] & 7, cy = scg[i2] >> 3;
+        int right = cx + 1 < ncg ? csbf[cy][cx + 1] : 0, below = cy + 1 < ncg ? csbf[cy + 1][cx] : 0;
+        int coded = cgp[i2] != NULL, infer_dc = 0;
+        if (i2 < last_cg && i2 > 0) {
+            cb_bin(c, CX_CSBF + ((right | below) ? 1 : 0) + (comp ? 2 : 0), coded);
+            infer_dc = 1;
+        } else coded = 1;                 /* last and DC CGs are inferred coded */
+        csbf[cy][cx] = (uint8_t)coded;
+        if (!coded) continue;
+        static const int16_t zero16[16] = {0};
+        const int16_t *lv = cgp[i2] ? cgp[i2] : zero16;
+        int prev = right | (below << 1);
+        int start = i2 == last_cg ? last_pos - 1 : 15;
+        uint16_t sig_mask = i2 == last_cg ? (uint16_t)(1u << last_pos) : 0;
+        for (int n = start; n >= 0; n--) {
+            int p = g_scan4[n], xp = p & 3, yp = p >> 2, sig = lv[p] != 0;
+            if (n > 0 || !infer_dc) {
+                int sc;
+                if (cx == 0 && cy == 0 && p == 0) sc = 0;
+                else {
+                    if (prev == 0) sc = (xp + yp == 0) ? 2 : (xp + yp < 3) ? 1 : 0;
+                    else if (prev == 1) sc = yp == 0 ? 2 : yp == 1 ? 1 : 0;
+                    else if (prev == 2) sc = xp == 0 ? 2 : xp == 1 ? 1 : 0;
+                    else sc = 2;
+                    if (comp == 0) { if (cx | cy) sc += 3; sc += log2 == 3 ? 9 : 21; }
+                    else sc += log2 == 3 ? 9 : 12;
+                }
+                cb_bin(c, CX_SIG + (comp ? 27 : 0) + sc, sig);
+                if (sig) infer_dc = 0;
+            } else sig = 1;               /* inferred DC significance */
+            if (sig) sig_mask |= (uint16_t)(1u << n);
+        }
+        /* greater1 / greater2 / signs / remaining */
+        int ctx_set = (i2 > 0 && comp == 0) ? 2 : 0;
+        if (c1 == 0) ctx_set++;
+        c1 = 1;
+        int nsig = 0, first_sig = 16, last_sig = -1, first_g1 = -1;
+        int absv[16], pos[16];
+        for (int n = 15; n >= 0; n--) if (sig_mask & (1u << n)) {
+            int v = lv[g_scan4[n]];
+            absv[nsig] = v < 0 ? -v : v; pos[nsig] = n; nsig++;
+            if (last_sig < 0) last_sig = n;
+            first_sig = n;
+        }
+        uint32_t signs = 0;
+        for (int k = 0; k < nsig; k++) signs = (signs << 1) | (uint32_t)(lv[g_scan4[pos[k]]] < 0);
+        int ng1 = nsig < 8 ? nsig : 8;
+        for (int k = 0; k < ng1; k++) {
+            int g1 = absv[k] > 1;
+            cb_bin(c, CX_GT1 + (comp ? 16 : 0) + 4 * ctx_set + c1, g1);
+            if (g1) { c1 = 0; if (first_g1 < 0) first_g1 = k; }
+            else if (c1 < 3 && c1 > 0) c1++;
+        }
+        if (c1 == 0 && first_g1 >= 0) cb_bin(c, CX_GT2 + (comp ? 4 : 0) + ctx_set, absv[first_g1] > 2);
+        int hidden = e->sp->sign_hiding && (last_sig - first_sig > 3);
+        if (hidden) cb_bypass_bins(c, signs >> 1, nsig - 1); else cb_bypass_bins(c, signs, nsig);
+        int rice = 0;
+        for (int k = 0; k < nsig; k++) {
+            /* baseLevel the flags can express: 3 for the coefficient that carried greater2, 2 for the other
+             * greater1-coded ones (first 8), 1 beyond */
+            int base = k < 8 ? (k == first_g1 ? 3 : 2) : 1;
+            if (absv[k] >= base) {
+                int rem = absv[k] - base;
+                /* 9.3.3.11 coeff_abs_level_remaining: TR prefix (cMax 4<<rice) + EGk suffix */
+                if (rem < (3 << rice)) {
+                    int len = rem >> rice;
+                    cb_bypass_bins(c, (1u << (len + 1)) - 2, len + 1);
+                    cb_bypass_bins(c, (uint32_t)rem & ((1u << rice) - 1), rice);
+                } else {
+                    int len = rice, code = rem - (3 << rice);
+                    while (code >= (1 << len)) { code -= 1 << len; len++; }
+                    cb_bypass_bins(c, (1u << (3 + len + 1 - rice)) - 2, 3 + len + 1 - rice);
+                    cb_bypass_bins(c, (uint32_t)code, len);
+                }
+                if (absv[k] > 3 * (1 << rice) && rice < 4) rice++;
+            }
+        }
+    }
+}
+
+/* ---- merge / AMVP candidates (8.5.3.2.2-.7 specialised: P slices, one reference picture, no TMVP) ---- */
+typedef struct { int16_t x, y; } mv_t;
+static int inter_nb(const ks_frame_syn *s, int xc, int yc, int xn, int yn, mv_t *mv)
+{
+    if (!avail(s, xc, yc, xn, yn)) return 0;
+    const ks_cell *n = cell_at(s, xn, yn);
+    if (n->flags & KS_F_INTRA) return 0;
+    mv->x = n->mvx; mv->y = n->mvy;
+    return 1;
+}
+static int merge_list(const ks_frame_syn *s, int x, int y, int size, int maxc, mv_t *list)
+{
+    mv_t a1, b1, b0, a0, b2; int n = 0;
+    int fa1 = inter_nb(s, x, y, x - 1, y + size - 1, &a1);
+    int fb1 = inter_nb(s, x, y, x + size - 1, y - 1, &b1);
+    if (fb1 && fa1 && a1.x == b1.x && a1.y == b1.y) fb1 = 0;
+    int fb0 = inter_nb(s, x, y, x + size, y - 1, &b0);
+    int ab1 = avail(s, x, y, x + size - 1, y - 1) && !(cell_at(s, x + size - 1, y - 1)->flags & KS_F_INTRA);
+    if (fb0 && ab1) { const ks_cell *t = cell_at(s, x + size - 1, y - 1); if (t->mvx == b0.x && t->mvy == b0.y) fb0 = 0; }
+    int fa0 = inter_nb(s, x, y, x - 1, y + size, &a0);
+    if (fa0 && fa1 && a1.x == a0.x && a1.y == a0.y) fa0 = 0;
+    int fb2 = inter_nb(s, x, y, x - 1, y - 1, &b2);
+    if (fb2 && fa1 && a1.x == b2.x && a1.y == b2.y) fb2 = 0;
+    if (fb2 && ab1) { const ks_cell *t = cell_at(s, x + size - 1, y - 1); if (t->mvx == b2.x && t->mvy == b2.y) fb2 = 0; }
+    if (fa0 + fa1 + fb0 + fb1 == 4) fb2 = 0;
+    if (fa1 && n < maxc) list[n++] = a1;
+    if (fb1 && n < maxc) list[n++] = b1;
+    if (fb0 && n < maxc) list[n++] = b0;
+    if (fa0 && n < maxc) list[n++] = a0;
+    if (fb2 && n < maxc) list[n++] = b2;
+    while (n < maxc) { list[n].x = 0; list[n].y = 0; n++; }
+    return n;
+}
+static void amvp_list(const ks_frame_syn *s, int x, int y, int size, mv_t list[2])
+{
+    mv_t a, b, t; int fa = 0, fb = 0, n = 0;
+    int sa0 = inter_nb(s, x, y, x - 1, y + size, &t); if (sa0) { a = t; fa = 1; }
+    int sa1 = inter_nb(s, x, y, x - 1, y + size - 1, &t); if (sa1 && !fa) { a = t; fa = 1; }
+    if (inter_nb(s, x, y, x + size, y - 1, &t)) { b = t; fb = 1; }
+    if (!fb && inter_nb(s, x, y, x + size - 1, y - 1, &t)) { b = t; fb = 1; }
+    if (!fb && inter_nb(s, x, y, x - 1, y - 1, &t)) { b = t; fb = 1; }
+    if (!(sa0 || sa1) && fb) { a = b; fa = 1; }       /* isScaledFlag == 0: A takes B (B re-derived identically) */
+    if (fa) list[n++] = a;
+    if (fb && !(fa && a.x == b.x && a.y == b.y)) list[n++] = b;
+    while (n < 2) { list[n].x = 0; list[n].y = 0; n++; }
+}
+static int mvd_bits(int d) { int a = d < 0 ? -d : d; if (a == 0) return 1; if (a == 1) return 3; int v = a - 2, k = 1, b = 3; while (v >= (1 << k)) { v -= 1 << k; k++; b++; } return b + k + 1; }
+
+static void code_mvd(cabac *c, int dx, int dy)
+{   /* 7.3.8.9 */
+    int ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy;
+    cb_bin(c, CX_MVD, ax > 0); cb_bin(c, CX_MVD, ay > 0);
+    if (ax > 0) cb_bin(c, CX_MVD + 1, ax > 1);
+    if (ay > 0) cb_bin(c, CX_MVD + 1, ay > 1);
+    for (int k = 0; k < 2; k++) {
+        int a = k ? ay : ax, d = k ? dy : dx;
+        if (a > 0) {
+            if (a > 1) {  /* abs_mvd_minus2: EG1 */
+                int v = a - 2, kk = 1;
+                while (v >= (1 << kk)) { cb_bypass(c, 1); v -= 1 << kk; kk++; }
+                cb_bypass(c, 0);
+                cb_bypass_bins(c, (uint32_t)v, kk);
+            }
+            cb_bypass(c, d < 0);
+        }
+    }
+}
+
+/* ---- transform tree for one CU (max_transform_hierarchy_depth 0: TU = min(CU,32)) ---- */
+static void code_tu(slice_enc *e, int x, int y, int log2, int f)
+{
+    int xc = x & (KS_CTU - 1), yc = y & (KS_CTU - 1);
+    if (f & KS_F_CBF_Y) code_residual(e, 0, xc, yc, log2);
+    if (f & KS_F_CBF_CB) code_residual(e, 1, xc >> 1, yc >> 1, log2 - 1);
+    if (f & KS_F_CBF_CR) code_residual(e, 2, xc >> 1, yc >> 1, log2 - 1);
+}
+static void code_transform_tree(slice_enc *e, int x, int y, int cu_log2, int intra)
+{
+    cabac *c = &e->cb; const ks_frame_syn *s = e->syn;
+    if (cu_log2 <= KS_MAX_TB_LOG2) {
+        int f = cell_at(s, x, y)->flags;
+        cb_bin(c, CX_CBF_CHROMA + 0, (f & KS_F_CBF_CB) != 0);
+        cb_bin(c, CX_CBF_CHROMA + 0, (f & KS_F_CBF_CR) != 0);
+        if (intra || (f & (KS_F_CBF_CB | KS_F_CBF_CR))) cb_bin(c, CX_CBF_LUMA + 1, (f & KS_F_CBF_Y) != 0);
+        code_tu(e, x, y, cu_log2, f);
+    } else {                                  /* 64x64 CU: split inferred, four 32x32 TUs */
+        int fq[4], cb_any = 0, cr_any = 0;
+        for (int k = 0; k < 4; k++) {
+            fq[k] = cell_at(s, x + (k & 1) * 32, y + (k >> 1) * 32)->flags;
+            cb_any |= fq[k] & KS_F_CBF_CB; cr_any |= fq[k] & KS_F_CBF_CR;
+        }
+        cb_bin(c, CX_CBF_CHROMA + 0, cb_any != 0);
+        cb_bin(c, CX_CBF_CHROMA + 0, cr_any != 0);
+        for (int k = 0; k < 4; k++) {
+            int xx = x + (k & 1) * 32, yy = y + (k >> 1) * 32;
+            if (xx >= s->width || yy >= s->height) continue;   /* cannot happen for a 64 CU inside the picture */
+            if (cb_any) cb_bin(c, CX_CBF_CHROMA + 1, (fq[k] & KS_F_CBF_CB) != 0);
+            if (cr_any) cb_bin(c, CX_CBF_CHROMA + 1, (fq[k] & KS_F_CBF_CR) != 0);
+            cb_bin(c, CX_CBF_LUMA + 0, (fq[k] & KS_F_CBF_Y) != 0);
+            code_tu(e, xx, yy, 5, fq[k]);
+        }
+    }
+}
+
+static int cu_cbf_any(const ks_frame_syn *s, int x, int y, int size)
+{
+    int any = 0;
+    for (int yy = y; yy < y + size; yy += KS_CELL) for (int xx = x; xx < x + size; xx += KS_CELL)
+        any |= cell_at(s, xx, yy)->flags & (KS_F_CBF_Y | KS_F_CBF_CB | KS_F_CBF_CR);
+    return any != 0;
+}
+
+/* ---- 7.3.8.5 coding_unit ---- */
+static void code_cu(slice_enc *e, int x, int y, int log2)
+{
+    cabac *c = &e->cb; const ks_frame_syn *s = e->syn;
+    const ks_cell *cu = cell_at(s, x, y);
+    int size = 1 << log2, intra = cu->flags & KS_F_INTRA;
+    if (s->slice_type != KS_SLICE_I) {
+        mv_t ml[5]; int merge_idx = -1;
+        if (!intra) {
+            int n = merge_list(s, x, y, size, e->sp->max_merge_cand, ml);
+            for (int k = 0; k < n; k++) if (ml[k].x == cu->mvx && ml[k].y == cu->mvy) { merge_idx = k; break; }
+        }
+        int any = intra ? 1 : cu_cbf_any(s, x, y, size);
+        int skip = !intra && merge_idx >= 0 && !any;
+        int ctx = 0;
+        if (avail(s, x, y, x - 1, y)) ctx += e->skip[(y >> KS_CELL_LOG2) * s->cells_w + ((x - 1) >> KS_CELL_LOG2)];
+        if (avail(s, x, y, x, y - 1)) ctx += e->skip[((y - 1) >> KS_CELL_LOG2) * s->cells_w + (x >> KS_CELL_LOG2)];
+        cb_bin(c, CX_SKIP + ctx, skip);
+        for (int yy = y; yy < y + size; yy += KS_CELL) for (int xx = x; xx < x + size; xx += KS_CELL)
+            e->skip[(yy >> KS_CELL_LOG2) * s->cells_w + (xx >> KS_CELL_LOG2)] = (uint8_t)skip;
+        if (skip || (!intra && merge_idx >= 0)) {
+            if (!skip) { cb_bin(c, CX_PRED_MODE, 0); cb_bin(c, CX_PART_MODE, 1); cb_bin(c, CX_MERGE_FLAG, 1); }
+            if (e->sp->max_merge_cand > 1) {         /* merge_idx: TR, first bin context coded */
+                cb_bin(c, CX_MERGE_IDX, merge_idx != 0);
+                if (merge_idx != 0) for (int k = 1; k < e->sp->max_merge_cand - 1; k++) { int b = merge_idx != k; cb_bypass(c, b); if (!b) break; }
+            }
+            if (skip) return;
+            code_transform_tree(e, x, y, log2, 0);   /* merge 2Nx2N: rqt_root_cbf inferred 1 */
+            return;
+        }
+        cb_bin(c, CX_PRED_MODE, intra != 0);
+        if (!intra) {
+            cb_bin(c, CX_PART_MODE, 1);              /* PART_2Nx2N */
+            cb_bin(c, CX_MERGE_FLAG, 0);
+            mv_t pl[2]; amvp_list(s, x, y, size, pl);
+            int c0 = mvd_bits(cu->mvx - pl[0].x) + mvd_bits(cu->mvy - pl[0].y);
+            int c1 = mvd_bits(cu->mvx - pl[1].x) + mvd_bits(cu->mvy - pl[1].y);
+            int idx = c1 < c0;
+            code_mvd(c, cu->mvx - pl[idx].x, cu->mvy - pl[idx].y);
+            cb_bin(c, CX_MVP_IDX, idx);
+            cb_bin(c, CX_ROOT_CBF, any);
+            if (any) code_transform_tree(e, x, y, log2, 0);
+            return;
+        }
+    }
+    /* intra 2Nx2N */
+    if (log2 == KS_CELL_LOG2) cb_bin(c, CX_PART_MODE, 1);
+    int cand_a = 1, cand_b = 1;                       /* 8.4.2 */
+    if (avail(s, x, y, x - 1, y)) { const ks_cell *n = cell_at(s, x - 1, y); if (n->flags & KS_F_INTRA) cand_a = n->intra_mode; }
+    if (avail(s, x, y, x, y - 1) && ((y - 1) >> KS_CTU_LOG2) == (y >> KS_CTU_LOG2)) { const ks_cell *n = cell_at(s, x, y - 1); if (n->flags & KS_F_INTRA) cand_b = n->intra_mode; }
+    int mpm[3];
+    if (cand_a == cand_b) {
+        if (cand_a < 2) { mpm[0] = 0; mpm[1] = 1; mpm[2] = 26; }
+        else { mpm[0] = cand_a; mpm[1] = 2 + ((cand_a + 29) & 31); mpm[2] = 2 + ((cand_a - 2 + 1) & 31); }
+    } else {
+        mpm[0] = cand_a; mpm[1] = cand_b;
+        mpm[2] = (cand_a != 0 && cand_b != 0) ? 0 : (cand_a != 1 && cand_b != 1) ? 1 : 26;
+    }
+    int mode = cu->intra_mode, mi = -1;
+    for (int k = 0; k < 3; k++) if (mpm[k] == mode) mi = k;
+    cb_bin(c, CX_PREV_INTRA, mi >= 0);
+    if (mi >= 0) { cb_bypass(c, mi > 0); if (mi > 0) cb_bypass(c, mi > 1); }
+    else {
+        if (mpm[0] > mpm[1]) { int t = mpm[0]; mpm[0] = mpm[1]; mpm[1] = t; }
+        if (mpm[0] > mpm[2]) { int t = mpm[0]; mpm[0] = mpm[2]; mpm[2] = t; }
+        if (mpm[1] > mpm[2]) { int t = mpm[1]; mpm[1] = mpm[2]; mpm[2] = t; }
+        int rem = mode;
+        for (int k = 2; k >= 0; k--) if (rem > mpm[k]) rem--;
+        cb_bypass_bins(c, (uint32_t)rem, 5);
+    }
+    cb_bin(c, CX_CHROMA_PRED, 0);                     /* intra_chroma_pred_mode = 4 (DM) */
+    code_transform_tree(e, x, y, log2, 1);
+}
+
+/* ---- 7.3.8.4 coding_quadtree ---- */
+static void code_quadtree(slice_enc *e, int x, int y, int log2)
+{
+    const ks_frame_syn *s = e->syn; cabac *c = &e->cb;
+    int size = 1 << log2, split;
+    if (x + size <= s->width && y + size <= s->height && log2 > KS_CELL_LOG2) {
+        split = cell_at(s, x, y)->cu_log2 < log2;
+        int depth = KS_CTU_LOG2 - log2, ctx = 0;
+        if (avail(s, x, y, x - 1, y)) ctx += (KS_CTU_LOG2 - cell_at(s, x - 1, y)->cu_log2) > depth;
+        if (avail(s, x, y, x, y - 1)) ctx += (KS_CTU_LOG2 - cell_at(s, x, y - 1)->cu_log2) > depth;
+        cb_bin(c, CX_SPLIT_CU + ctx, split);
+    } else split = log2 > KS_CELL_LOG2;
+    if (split) {
+        int h = size >> 1;
+        for (int k = 0; k < 4; k++) {
+            int xx = x + (k & 1) * h, yy = y + (k >> 1) * h;
+            if (xx < s->width && yy < s->height) code_quadtree(e, xx, yy, log2 - 1);
+        }
+    } else code_cu(e, x, y, log2);
+}
+
+/* ---- 7.3.8.3 sao ---- */
+static int sao_equal(const ks_ctu_syn *a, const ks_ctu_syn *b) { return memcmp(a->sao, b->sao, sizeof(a->sao)) == 0; }
+static void code_sao(slice_enc *e, int rx, int ry)
+{
+    cabac *c = &e->cb; const ks_frame_syn *s = e->syn; const ks_slice_params *sl = e->sl;
+    const ks_ctu_syn *ct = &s->ctus[ry * s->ctus_w + rx];
+    if (!sl->sao_luma && !sl->sao_chroma) return;
+    if (rx > 0) { int m = sao_equal(ct, ct - 1); cb_bin(c, CX_SAO_MERGE, m); if (m) return; }
+    if (ry > 0) { int m = sao_equal(ct, ct - s->ctus_w); cb_bin(c, CX_SAO_MERGE, m); if (m) return; }
+    for (int ci = 0; ci < 3; ci++) {
+        if ((ci == 0 && !sl->sao_luma) || (ci > 0 && !sl->sao_chroma)) continue;
+        const ks_sao_param *p = &ct->sao[ci];
+        int type = ci == 2 ? ct->sao[1].type : p->type;
+        if (ci < 2) { cb_bin(c, CX_SAO_TYPE, type != 0); if (type) cb_bypass(c, type == 2); }
+        if (!type) continue;
+        for (int k = 0; k < 4; k++) {     /* sao_offset_abs: TR cMax 7 */
+            int a = p->off[k] < 0 ? -p->off[k] : p->off[k];
+            for (int j = 0; j < a; j++) cb_bypass(c, 1);
+            if (a < 7) cb_bypass(c, 0);
+        }
+        if (type == 1) {
+            for (int k = 0; k < 4; k++) if (p->off[k]) cb_bypass(c, p->off[k] < 0);
+            cb_bypass_bins(c, p->band_or_class, 5);
+        } else if (ci < 2) cb_bypass_bins(c, ci == 0 ? p->band_or_class : ct->sao[1].band_or_class, 2);
+    }
+}
+
+size_t ks_slice_scratch_bytes(const ks_stream_params *sp)
+{
+    size_t cells = (size_t)(sp->width >> KS_CELL_LOG2) * (sp->height >> KS_CELL_LOG2);
+    return sizeof(slice_enc) + cells + (size_t)sp->width * sp->height * 2 + 65536;
+}
+
+long ks_write_slice(const ks_stream_params *sp, const ks_slice_params *sl, const ks_frame_syn *syn,
+                    void *scratch, uint8_t *out, size_t cap)
+{
+    scans_init();
+    slice_enc *e = (slice_enc *)scratch;
+    memset(e, 0, sizeof(*e));
+    e->sp = sp; e->sl = sl; e->syn = syn;
+    size_t cells = (size_t)syn->cells_w * syn->cells_h;
+    e->skip = (uint8_t *)(e + 1);
+    memset(e->skip, 0, cells);
+    uint8_t *rbsp = e->skip + cells;
+    size_t rcap = (size_t)sp->width * sp->height * 2 + 65536 - 1024;
+
+    /* ---- 7.3.6.1 slice_segment_header ---- */
+    bitw b; bw_init(&b, rbsp, 512);
+    int idr = sl->nal_type == 19 || sl->nal_type == 20;
+    bw_put(&b, 1, 1);
+    if (sl->nal_type >= 16 && sl->nal_type <= 23) bw_put(&b, 0, 1);
+    bw_ue(&b, 0);
+    bw_ue(&b, (uint32_t)sl->slice_type);
+    if (!idr) {
+        bw_put(&b, (uint32_t)sl->poc & ((1u << sp->log2_max_poc_lsb) - 1), sp->log2_max_poc_lsb);
+        bw_put(&b, 0, 1);                        /* short_term_ref_pic_set_sps_flag = 0: explicit RPS (like the reference) */
+        bw_ue(&b, (uint32_t)sl->num_neg_refs); bw_ue(&b, 0);
+        int prev = 0;
+        for (int i = 0; i < sl->num_neg_refs; i++) { bw_ue(&b, (uint32_t)(prev - sl->neg_delta_poc[i] - 1)); bw_put(&b, 1, 1); prev = sl->neg_delta_poc[i]; }
+    }
+    if (sp->sao) { bw_put(&b, (uint32_t)sl->sao_luma, 1); bw_put(&b, (uint32_t)sl->sao_chroma, 1); }
+    if (sl->slice_type != KS_SLICE_I) {
+        bw_put(&b, 1, 1); bw_ue(&b, 0);          /* num_ref_idx_active_override: 1 active ref (reference does the same) */
+        bw_ue(&b, (uint32_t)(5 - sp->max_merge_cand));
+    }
+    bw_se(&b, sl->qp - 26);
+    bw_put(&b, (uint32_t)sl->deblock_override, 1);
+    if (sl->deblock_override) { bw_put(&b, 0, 1); bw_se(&b, sl->beta_offset_div2); bw_se(&b, sl->tc_offset_div2); }
+    bw_put(&b, 1, 1);                            /* slice_loop_filter_across_slices_enabled_flag */
+    bw_trailing(&b);                             /* byte_alignment() has the same form */
+    size_t hdr = b.pos;
+
+    /* ---- slice_segment_data ---- */
+    int init_type = sl->slice_type == KS_SLICE_I ? 0 : (sl->slice_type == KS_SLICE_P ? 1 : 2);
+    cb_init(&e->cb, rbsp + hdr, rcap - hdr, init_type, sl->qp);
+    int nctu = syn->ctus_w * syn->ctus_h;
+    for (int a = 0; a < nctu; a++) {
+        int rx = a % syn->ctus_w, ry = a / syn->ctus_w;
+        ctu_prefix(e, a);
+        code_sao(e, rx, ry);
+        code_quadtree(e, rx << KS_CTU_LOG2, ry << KS_CTU_LOG2, KS_CTU_LOG2);
+        cb_terminate(&e->cb, a == nctu - 1);
+    }
+    cb_finish(&e->cb);
+    if (e->cb.overflow) return -1;
+    return nal_emit(out, cap, sl->nal_type, sl->temporal_id, rbsp, hdr + e->cb.pos);
+}
+
+uint64_t ks_plane_sse(const uint8_t *a, int sa, const uint8_t *b, int sb, int w, int h)
+{
+    uint64_t s = 0;
+    for (int y = 0; y < h; y++, a += sa, b += sb)
+        for (int x = 0; x < w; x++) { int d = (int)a[x] - (int)b[x]; s += (uint64_t)(d * d); }
+    return s;
+}

@@ -1,0 +1,416 @@
+/* ora_frame.c -- CPU model of the picture-level hot path (TEST INFRASTRUCTURE; see ora_frame.h). */
+#include "ora_frame.h"
+#include "ks_oracle.h"
+#include <stdlib.h>
+#include <string.h>
+
+const int ora_lambda_sad_q4[52] = {4,4,5,5,6,7,7,8,9,10,12,13,15,17,19,21,23,26,30,33,37,42,47,53,59,66,74,83,94,105,118,132,149,167,187,210,236,265,297,334,375,421,472,530,595,668,749,841,944,1060,1189,1335};
+const int ora_lambda_sse_q4[52] = {1,1,1,2,2,3,3,4,5,7,9,11,14,17,22,27,34,43,54,69,86,109,137,173,218,274,345,435,548,691,870,1097,1382,1741,2193,2763,3482,4387,5527,6963,8773,11053,13926,17546,22107,27853,35092,44214,55706,70185,88427,111411};
+
+static inline int iabs(int v) { return v < 0 ? -v : v; }
+static inline int imin(int a, int b) { return a < b ? a : b; }
+static inline int imax(int a, int b) { return a > b ? a : b; }
+static inline int clip3(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* ------------------------------------------------------------------ pictures --------------------- */
+int ora_pic_alloc(ora_pic *pic, int w, int h)
+{
+    for (int i = 0; i < 3; i++) {
+        int pw = i ? w / 2 : w, ph = i ? h / 2 : h;
+        ora_plane *p = &pic->c[i];
+        p->w = pw; p->h = ph; p->stride = pw + 2 * ORA_PAD;
+        p->base = (uint8_t *)calloc((size_t)p->stride * (ph + 2 * ORA_PAD), 1);
+        if (!p->base) return -1;
+        p->p = p->base + (size_t)ORA_PAD * p->stride + ORA_PAD;
+    }
+    return 0;
+}
+void ora_pic_free(ora_pic *pic) { for (int i = 0; i < 3; i++) { free(pic->c[i].base); pic->c[i].base = NULL; } }
+void ora_pic_extend(ora_pic *pic)
+{
+    for (int i = 0; i < 3; i++) {
+        ora_plane *p = &pic->c[i];
+        for (int y = 0; y < p->h; y++) {
+            uint8_t *r = p->p + (size_t)y * p->stride;
+            memset(r - ORA_PAD, r[0], ORA_PAD); memset(r + p->w, r[p->w - 1], ORA_PAD);
+        }
+        for (int y = 1; y <= ORA_PAD; y++) {
+            memcpy(p->p - (size_t)y * p->stride - ORA_PAD, p->p - ORA_PAD, (size_t)p->stride);
+            memcpy(p->p + (size_t)(p->h - 1 + y) * p->stride - ORA_PAD, p->p + (size_t)(p->h - 1) * p->stride - ORA_PAD, (size_t)p->stride);
+        }
+    }
+}
+void ora_pic_load(ora_pic *pic, const uint8_t *i420, int sw, int sh)
+{
+    const uint8_t *s = i420;
+    for (int i = 0; i < 3; i++) {
+        ora_plane *p = &pic->c[i];
+        int w = i ? sw / 2 : sw, h = i ? sh / 2 : sh;
+        for (int y = 0; y < p->h; y++) {
+            const uint8_t *sr = s + (size_t)imin(y, h - 1) * w;
+            uint8_t *d = p->p + (size_t)y * p->stride;
+            memcpy(d, sr, (size_t)w);
+            for (int x = w; x < p->w; x++) d[x] = sr[w - 1];
+        }
+        s += (size_t)w * h;
+    }
+    ora_pic_extend(pic);
+}
+
+/* ------------------------------------------------------------------ helpers ---------------------- */
+static uint16_t scan_tb[4][1024];    /* per log2 (2..5): scan position -> (y<<8)|x, diag CG order x diag 4x4 */
+static int scan_ready;
+static void build_scans(void)
+{
+    if (scan_ready) return;
+    uint8_t d4[16], dcg[64];
+    for (int l = 2; l <= 5; l++) {
+        int ncg = 1 << (l - 2);
+        for (int pass = 0; pass < 2; pass++) {
+            int n = pass ? ncg : 4, i = 0, x = 0, y = 0; uint8_t *dst = pass ? dcg : d4;
+            for (;;) { while (y >= 0) { if (x < n && y < n) dst[i++] = (uint8_t)((y << 3) | x); y--; x++; } y = x; x = 0; if (i >= n * n) break; }
+        }
+        for (int c = 0; c < ncg * ncg; c++)
+            for (int k = 0; k < 16; k++) {
+                int xx = ((dcg[c] & 7) << 2) + (d4[k] & 7), yy = ((dcg[c] >> 3) << 2) + (d4[k] >> 3);
+                scan_tb[l - 2][c * 16 + k] = (uint16_t)((yy << 8) | xx);
+            }
+    }
+    scan_ready = 1;
+}
+static inline int zidx(int x, int y)
+{
+    int cx = (x >> 4) & 3, cy = (y >> 4) & 3;
+    return (cx & 1) | ((cy & 1) << 1) | ((cx & 2) << 1) | ((cy & 2) << 2);
+}
+static int avail(const ora_cfg *cfg, int xc, int yc, int xn, int yn)
+{   /* H.265 6.4.1, one slice, CTB 64, 16x16 granularity */
+    if (xn < 0 || yn < 0 || xn >= cfg->width || yn >= cfg->height) return 0;
+    int cw = (cfg->width + 63) >> 6;
+    int ac = (yc >> 6) * cw + (xc >> 6), an = (yn >> 6) * cw + (xn >> 6);
+    if (an != ac) return an < ac;
+    return zidx(xn, yn) < zidx(xc, yc);
+}
+static inline int mvbits(int d) { int a = iabs(d); return a ? 2 * (32 - __builtin_clz((unsigned)a)) + 1 : 1; }
+
+/* one transform block: residual -> fdct -> quant (-> sign hiding) -> dequant -> idct+pred.  returns cbf */
+static int code_tb(const ora_cfg *cfg, int qp, int intra_slice, int log2, int is_dst,
+                   const uint8_t *src, int ss, const uint8_t *pred, int ps, uint8_t *rec, int rs, int16_t *lev, int ls)
+{
+    int n = 1 << log2;
+    int16_t res[1024], coef[1024], q[1024], du[1024], deq[1024];
+    ora_residual(res, src, pred, ss, ps, n);
+    ora_fdct(res, coef, n, n, log2, is_dst);
+    int nnz = ora_quant(coef, q, n, qp, log2, intra_slice, du);
+    if (nnz && cfg->sign_hiding) nnz = ora_sign_hide(coef, q, du, n, log2, scan_tb[log2 - 2]);
+    for (int y = 0; y < n; y++) memcpy(lev + (size_t)y * ls, q + y * n, (size_t)n * 2);
+    if (!nnz) { for (int y = 0; y < n; y++) memcpy(rec + (size_t)y * rs, pred + (size_t)y * ps, (size_t)n); return 0; }
+    ora_dequant(q, deq, n, qp, log2);
+    ora_idct_add(deq, rec, pred, n, rs, ps, log2, is_dst);
+    return 1;
+}
+
+/* ------------------------------------------------------------------ intra picture ---------------- */
+static void build_nb(const ora_cfg *cfg, const ora_plane *rec, int comp, int x0, int y0, int n, uint8_t *nb)
+{   /* 8.4.4.2.2 reference sample availability + substitution; (x0,y0) in component samples */
+    int sh = comp ? 1 : 0, lx = x0 << sh, ly = y0 << sh, tot = 4 * n + 1;
+    uint8_t av[129];
+    int any = 0;
+    for (int i = 0; i < tot; i++) {
+        int xn, yn;
+        if (i < 2 * n) { xn = x0 - 1; yn = y0 + 2 * n - 1 - i; }
+        else if (i == 2 * n) { xn = x0 - 1; yn = y0 - 1; }
+        else { xn = x0 + i - 2 * n - 1; yn = y0 - 1; }
+        av[i] = (uint8_t)avail(cfg, lx, ly, xn * (1 << sh), yn * (1 << sh));
+        if (av[i]) { nb[i] = rec->p[(size_t)yn * rec->stride + xn]; any = 1; }
+    }
+    if (!any) { memset(nb, 128, (size_t)tot); return; }
+    if (!av[0]) { int i = 1; while (!av[i]) i++; nb[0] = nb[i]; }
+    for (int i = 1; i < tot; i++) if (!av[i]) nb[i] = nb[i - 1];
+}
+void ora_intra_picture(const ora_cfg *cfg, int qp, const ora_pic *src, ora_pic *rec, ks_cell *cells, ora_levels *lv)
+{
+    build_scans();
+    int cw = cfg->width >> 4, W = cfg->width, H = cfg->height;
+    int ctus_w = (W + 63) >> 6, ctus_h = (H + 63) >> 6;
+    int lam = ora_lambda_sad_q4[qp], qpc = ora_chroma_qp[qp];
+    for (int cty = 0; cty < ctus_h; cty++) for (int ctx = 0; ctx < ctus_w; ctx++)
+        for (int z = 0; z < 16; z++) {
+            int cx = (z & 1) | ((z >> 1) & 2), cy = ((z >> 1) & 1) | ((z >> 2) & 2);
+            int x0 = (ctx << 6) + (cx << 4), y0 = (cty << 6) + (cy << 4);
+            if (x0 >= W || y0 >= H) continue;
+            uint8_t nb[65], pred[256];
+            const uint8_t *s = src->c[0].p + (size_t)y0 * src->c[0].stride + x0;
+            build_nb(cfg, &rec->c[0], 0, x0, y0, 16, nb);
+            int best = 0, best_cost = 0x7fffffff;
+            for (int m = 0; m < 35; m++) {
+                ora_intra_pred(pred, 16, nb, 4, m, 1, cfg->strong_intra);
+                int bits = (m == 0 || m == 1 || m == 10 || m == 26) ? 3 : 6;
+                int cost = (int)ora_sad(s, pred, src->c[0].stride, 16, 16, 16) + ((lam * bits) >> 4);
+                if (cost < best_cost) { best_cost = cost; best = m; }
+            }
+            ora_intra_pred(pred, 16, nb, 4, best, 1, cfg->strong_intra);
+            ks_cell *c = &cells[(y0 >> 4) * cw + (x0 >> 4)];
+            memset(c, 0, sizeof(*c));
+            c->cu_log2 = 4; c->flags = KS_F_INTRA; c->intra_mode = (uint8_t)best;
+            uint8_t *r = rec->c[0].p + (size_t)y0 * rec->c[0].stride + x0;
+            if (code_tb(cfg, qp, 1, 4, 0, s, src->c[0].stride, pred, 16, r, rec->c[0].stride, lv->c[0] + (size_t)y0 * W + x0, W)) c->flags |= KS_F_CBF_Y;
+            for (int ci = 1; ci < 3; ci++) {
+                int xc = x0 >> 1, yc = y0 >> 1;
+                uint8_t nbc[33], pc[64];
+                build_nb(cfg, &rec->c[ci], ci, xc, yc, 8, nbc);
+                ora_intra_pred(pc, 8, nbc, 3, best, 0, 0);
+                const uint8_t *sc = src->c[ci].p + (size_t)yc * src->c[ci].stride + xc;
+                uint8_t *rc = rec->c[ci].p + (size_t)yc * rec->c[ci].stride + xc;
+                if (code_tb(cfg, qpc, 1, 3, 0, sc, src->c[ci].stride, pc, 8, rc, rec->c[ci].stride, lv->c[ci] + (size_t)yc * (W / 2) + xc, W / 2))
+                    c->flags |= ci == 1 ? KS_F_CBF_CB : KS_F_CBF_CR;
+            }
+        }
+}
+
+/* ------------------------------------------------------------------ inter picture ---------------- */
+static const int8_t dia_dx[4] = {0, 0, -1, 1}, dia_dy[4] = {-1, 1, 0, 0};
+static const int8_t sq_dx[8] = {-1, 0, 1, -1, 1, -1, 0, 1}, sq_dy[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+
+static void me_cell(const ora_cfg *cfg, int lam, const ora_plane *src, const ora_plane *ref, int x0, int y0, int tpx, int tpy, int *omx, int *omy)
+{   /* a5 (start point) + a3 (small diamond, x264 DIA) + a6 (half/quarter refinement with real interpolation, SAD cost) */
+    const uint8_t *s = src->p + (size_t)y0 * src->stride + x0;
+    const uint8_t *r0 = ref->p + (size_t)y0 * ref->stride + x0;
+    int rs = ref->stride, ss = src->stride, R = cfg->me_range;
+#define MVCOST(qx, qy) ((lam * (mvbits((qx) - tpx) + mvbits((qy) - tpy))) >> 4)
+#define ICOST(ix, iy) ((int)ora_sad(s, r0 + (iy) * rs + (ix), ss, rs, 16, 16) + MVCOST((ix) * 4, (iy) * 4))
+    int bx = 0, by = 0, bc = ICOST(0, 0);
+    int cx = clip3(-R, R, (tpx + 2) >> 2), cy = clip3(-R, R, (tpy + 2) >> 2);
+    if (cx || cy) { int c = ICOST(cx, cy); if (c < bc) { bc = c; bx = cx; by = cy; } }
+    for (int it = 0; it < cfg->me_iters; it++) {
+        int bk = -1, lc = bc;
+        for (int k = 0; k < 4; k++) {
+            int nx = bx + dia_dx[k], ny = by + dia_dy[k];
+            if (iabs(nx) > R || iabs(ny) > R) continue;
+            int c = ICOST(nx, ny);
+            if (c < lc) { lc = c; bk = k; }
+        }
+        if (bk < 0) break;
+        bx += dia_dx[bk]; by += dia_dy[bk]; bc = lc;
+    }
+    int mx = bx * 4, my = by * 4;
+    for (int step = 2; step >= 1; step--) {
+        if (cfg->subpel < (step == 2 ? 1 : 2)) break;
+        int bk = -1, lc = bc;
+        for (int k = 0; k < 8; k++) {
+            int qx = mx + sq_dx[k] * step, qy = my + sq_dy[k] * step;
+            uint8_t pred[256];
+            ora_mc_luma(pred, 16, r0, rs, 16, 16, qx, qy);
+            int c = (int)ora_sad(s, pred, ss, 16, 16, 16) + MVCOST(qx, qy);
+            if (c < lc) { lc = c; bk = k; }
+        }
+        if (bk >= 0) { mx += sq_dx[bk] * step; my += sq_dy[bk] * step; bc = lc; }
+    }
+    *omx = mx; *omy = my;
+#undef ICOST
+#undef MVCOST
+}
+
+static void recon_inter_cu(const ora_cfg *cfg, int qp, int qpc, const ora_pic *src, const ora_pic *ref, ora_pic *rec,
+                           ks_cell *cells, ora_levels *lv, int x0, int y0, int log2, int mvx, int mvy)
+{
+    int S = 1 << log2, W = cfg->width, cw = W >> 4;
+    static uint8_t pred[3][64 * 64];
+    ora_mc_luma(pred[0], 64, ref->c[0].p + (size_t)y0 * ref->c[0].stride + x0, ref->c[0].stride, S, S, mvx, mvy);
+    for (int ci = 1; ci < 3; ci++)
+        ora_mc_chroma(pred[ci], 64, ref->c[ci].p + (size_t)(y0 / 2) * ref->c[ci].stride + x0 / 2, ref->c[ci].stride, S / 2, S / 2, mvx, mvy);
+    int T = imin(S, 32), tl = log2 > 5 ? 5 : log2;
+    for (int ty = 0; ty < S; ty += T) for (int tx = 0; tx < S; tx += T) {
+        int x = x0 + tx, y = y0 + ty, f = 0;
+        if (code_tb(cfg, qp, 0, tl, 0, src->c[0].p + (size_t)y * src->c[0].stride + x, src->c[0].stride, pred[0] + ty * 64 + tx, 64,
+                    rec->c[0].p + (size_t)y * rec->c[0].stride + x, rec->c[0].stride, lv->c[0] + (size_t)y * W + x, W)) f |= KS_F_CBF_Y;
+        for (int ci = 1; ci < 3; ci++) {
+            int xc = x / 2, yc = y / 2;
+            if (code_tb(cfg, qpc, 0, tl - 1, 0, src->c[ci].p + (size_t)yc * src->c[ci].stride + xc, src->c[ci].stride,
+                        pred[ci] + (ty / 2) * 64 + tx / 2, 64, rec->c[ci].p + (size_t)yc * rec->c[ci].stride + xc, rec->c[ci].stride,
+                        lv->c[ci] + (size_t)yc * (W / 2) + xc, W / 2)) f |= ci == 1 ? KS_F_CBF_CB : KS_F_CBF_CR;
+        }
+        for (int yy = y; yy < y + T; yy += 16) for (int xx = x; xx < x + T; xx += 16) {
+            ks_cell *c = &cells[(yy >> 4) * cw + (xx >> 4)];
+            c->mvx = (int16_t)mvx; c->mvy = (int16_t)mvy; c->cu_log2 = (uint8_t)log2; c->flags = (uint8_t)f; c->intra_mode = 0; c->rsv = 0;
+        }
+    }
+}
+
+void ora_inter_picture(const ora_cfg *cfg, int qp, const ora_pic *src, const ora_pic *ref, const ks_cell *prev_cells,
+                       ora_pic *rec, ks_cell *cells, ora_levels *lv)
+{
+    build_scans();
+    int W = cfg->width, H = cfg->height, cw = W >> 4, ch = H >> 4;
+    int lam = ora_lambda_sad_q4[qp], qpc = ora_chroma_qp[qp];
+    /* 1. motion search per 16x16 cell (independent of neighbours: predictor = co-located MV of the previous picture) */
+    for (int cy = 0; cy < ch; cy++) for (int cx = 0; cx < cw; cx++) {
+        int tpx = 0, tpy = 0, mx, my;
+        if (prev_cells && !(prev_cells[cy * cw + cx].flags & KS_F_INTRA)) { tpx = prev_cells[cy * cw + cx].mvx; tpy = prev_cells[cy * cw + cx].mvy; }
+        me_cell(cfg, lam, &src->c[0], &ref->c[0], cx << 4, cy << 4, tpx, tpy, &mx, &my);
+        ks_cell *c = &cells[cy * cw + cx];
+        memset(c, 0, sizeof(*c)); c->mvx = (int16_t)mx; c->mvy = (int16_t)my; c->cu_log2 = 4;
+    }
+    /* 2. CU size: merge four equal-MV siblings upward (16 -> 32 -> 64) when the larger CU lies inside the picture */
+    for (int y = 0; y + 32 <= H; y += 32) for (int x = 0; x + 32 <= W; x += 32) {
+        ks_cell *a = &cells[(y >> 4) * cw + (x >> 4)], *b = a + 1, *c = a + cw, *d = c + 1;
+        if (a->mvx == b->mvx && a->mvx == c->mvx && a->mvx == d->mvx && a->mvy == b->mvy && a->mvy == c->mvy && a->mvy == d->mvy)
+            a->cu_log2 = b->cu_log2 = c->cu_log2 = d->cu_log2 = 5;
+    }
+    for (int y = 0; y + 64 <= H; y += 64) for (int x = 0; x + 64 <= W; x += 64) {
+        ks_cell *a = &cells[(y >> 4) * cw + (x >> 4)];
+        int ok = 1;
+        for (int j = 0; j < 4 && ok; j++) for (int i = 0; i < 4; i++) { ks_cell *t = a + j * cw + i; if (t->cu_log2 != 5 || t->mvx != a->mvx || t->mvy != a->mvy) { ok = 0; break; } }
+        if (ok) for (int j = 0; j < 4; j++) for (int i = 0; i < 4; i++) a[j * cw + i].cu_log2 = 6;
+    }
+    /* 3. prediction + residual coding + reconstruction per CU */
+    for (int y = 0; y < H; y += 16) for (int x = 0; x < W; x += 16) {
+        ks_cell c = cells[(y >> 4) * cw + (x >> 4)];
+        int S = 1 << c.cu_log2;
+        if ((x & (S - 1)) || (y & (S - 1))) continue;
+        recon_inter_cu(cfg, qp, qpc, src, ref, rec, cells, lv, x, y, c.cu_log2, c.mvx, c.mvy);
+    }
+}
+
+/* ------------------------------------------------------------------ deblocking (a16) ------------- */
+static int is_tu_edge(const ks_cell *p, const ks_cell *q, int xp, int yp, int xq, int yq, int pos)
+{   /* pos = coordinate (x for vertical edges, y for horizontal) of the edge, a multiple of 16 */
+    int sp = 1 << p->cu_log2, sq = 1 << q->cu_log2;
+    int same = p->cu_log2 == q->cu_log2 && (xp & ~(sp - 1)) == (xq & ~(sq - 1)) && (yp & ~(sp - 1)) == (yq & ~(sq - 1));
+    if (!same) return 1;
+    return p->cu_log2 == 6 && (pos & 31) == 0;
+}
+static int edge_bs(const ks_cell *p, const ks_cell *q)
+{
+    if ((p->flags | q->flags) & KS_F_INTRA) return 2;
+    if ((p->flags | q->flags) & KS_F_CBF_Y) return 1;
+    if (iabs(p->mvx - q->mvx) >= 4 || iabs(p->mvy - q->mvy) >= 4) return 1;
+    return 0;
+}
+void ora_deblock_picture(const ora_cfg *cfg, int qp, int beta_off, int tc_off, ora_pic *rec, const ks_cell *cells)
+{
+    int W = cfg->width, H = cfg->height, cw = W >> 4;
+    int beta = ora_beta_table[clip3(0, 51, qp + (beta_off << 1))];
+    int qpc = ora_chroma_qp[qp];
+    for (int dir = 0; dir < 2; dir++)
+        for (int e = 16; e < (dir ? H : W); e += 16)
+            for (int t = 0; t < (dir ? W : H); t += 4) {
+                int xq = dir ? t : e, yq = dir ? e : t, xp = dir ? t : e - 1, yp = dir ? e - 1 : t;
+                const ks_cell *p = &cells[(yp >> 4) * cw + (xp >> 4)], *q = &cells[(yq >> 4) * cw + (xq >> 4)];
+                if (!is_tu_edge(p, q, xp, yp, xq, yq, e)) continue;
+                int bs = edge_bs(p, q);
+                if (!bs) continue;
+                int tc = ora_tc_table[clip3(0, 53, qp + 2 * (bs - 1) + (tc_off << 1))];
+                ora_plane *pl = &rec->c[0];
+                ora_deblock_luma_seg(pl->p + (size_t)yq * pl->stride + xq, dir ? pl->stride : 1, dir ? 1 : pl->stride, beta, tc);
+                if (bs == 2) {
+                    int tcc = ora_tc_table[clip3(0, 53, qpc + 2 + (tc_off << 1))];
+                    for (int ci = 1; ci < 3; ci++) {
+                        ora_plane *pc = &rec->c[ci];
+                        ora_deblock_chroma_seg(pc->p + (size_t)(yq >> 1) * pc->stride + (xq >> 1), dir ? pc->stride : 1, dir ? 1 : pc->stride, tcc, 2);
+                    }
+                }
+            }
+}
+
+/* ------------------------------------------------------------------ SAO (a17..a19) --------------- */
+static int sao_offset_rd(int sum, int cnt, int signc, int lam, int is_bo, int *best_o)
+{   /* signc: +1 offsets must be >=0, -1 must be <=0, 0 free.  returns cost (delta SSE + lambda*bits), Q0 */
+    *best_o = 0;
+    if (!cnt) return 0;
+    int o = sum >= 0 ? (sum + cnt / 2) / cnt : -((-sum + cnt / 2) / cnt);
+    o = clip3(-7, 7, o);
+    if ((signc > 0 && o < 0) || (signc < 0 && o > 0)) o = 0;
+    int best = (lam * 1) >> 4;                 /* offset 0: one bin */
+    int step = o > 0 ? -1 : 1;
+    for (int v = o; v != 0; v += step) {
+        int bits = iabs(v) + 1 + (is_bo ? 1 : 0);
+        int c = cnt * v * v - 2 * v * sum + ((lam * bits) >> 4);
+        if (c < best || (c == best && iabs(v) < iabs(*best_o))) { best = c; *best_o = v; }
+    }
+    return best;
+}
+void ora_sao_picture(const ora_cfg *cfg, int qp, const ora_pic *src, const ora_pic *deb, ora_pic *out, ks_ctu_syn *ctus)
+{
+    int W = cfg->width, H = cfg->height, ctus_w = (W + 63) >> 6, ctus_h = (H + 63) >> 6;
+    int lam = ora_lambda_sse_q4[qp];
+    for (int ry = 0; ry < ctus_h; ry++) for (int rx = 0; rx < ctus_w; rx++) {
+        ks_ctu_syn *ct = &ctus[ry * ctus_w + rx];
+        memset(ct->sao, 0, sizeof(ct->sao));
+        ora_sao_stats st[3];
+        for (int ci = 0; ci < 3; ci++) {
+            int sh = ci ? 1 : 0, x0 = (rx << 6) >> sh, y0 = (ry << 6) >> sh, pw = W >> sh, ph = H >> sh;
+            int w = imin(64 >> sh, pw - x0), h = imin(64 >> sh, ph - y0);
+            ora_sao_stats_ctb(&st[ci], src->c[ci].p, src->c[ci].stride, deb->c[ci].p, deb->c[ci].stride, x0, y0, w, h, pw, ph);
+        }
+        for (int grp = 0; grp < 2; grp++) {
+            int c0 = grp ? 1 : 0, c1 = grp ? 2 : 0;
+            int best_cost = 0, best_type = 0, best_class = 0, best_off[3][4], best_band[3];
+            memset(best_off, 0, sizeof(best_off)); memset(best_band, 0, sizeof(best_band));
+            if (cfg->sao) {
+                for (int k = 0; k < 4; k++) {           /* edge classes */
+                    int total = (lam * 4) >> 4, off[3][4];
+                    for (int ci = c0; ci <= c1; ci++)
+                        for (int cat = 1; cat <= 4; cat++)
+                            total += sao_offset_rd(st[ci].eo_sum[k][cat], st[ci].eo_cnt[k][cat], cat <= 2 ? 1 : -1, lam, 0, &off[ci][cat - 1]);
+                    if (total < best_cost) { best_cost = total; best_type = 2; best_class = k; for (int ci = c0; ci <= c1; ci++) memcpy(best_off[ci], off[ci], sizeof(off[ci])); }
+                }
+                {                                       /* band offset: best 4 consecutive bands per component */
+                    int total = (lam * 7) >> 4, off[3][4], band[3];
+                    for (int ci = c0; ci <= c1; ci++) {
+                        int bc[32], bo[32], bestc = 0x7fffffff, bs = 0;
+                        for (int b = 0; b < 32; b++) bc[b] = sao_offset_rd(st[ci].bo_sum[b], st[ci].bo_cnt[b], 0, lam, 1, &bo[b]);
+                        for (int s = 0; s <= 28; s++) { int c = bc[s] + bc[s + 1] + bc[s + 2] + bc[s + 3]; if (c < bestc) { bestc = c; bs = s; } }
+                        total += bestc; band[ci] = bs;
+                        for (int j = 0; j < 4; j++) off[ci][j] = bo[bs + j];
+                    }
+                    if (total < best_cost) { best_cost = total; best_type = 1; for (int ci = c0; ci <= c1; ci++) { memcpy(best_off[ci], off[ci], sizeof(off[ci])); best_band[ci] = band[ci]; } }
+                }
+                int nz = 0;
+                for (int ci = c0; ci <= c1; ci++) for (int j = 0; j < 4; j++) nz |= best_off[ci][j];
+                if (!nz) best_type = 0;
+            }
+            for (int ci = c0; ci <= c1; ci++) {
+                ks_sao_param *p = &ct->sao[ci];
+                p->type = (uint8_t)best_type;
+                if (best_type) {
+                    p->band_or_class = (uint8_t)(best_type == 2 ? best_class : best_band[ci]);
+                    for (int j = 0; j < 4; j++) p->off[j] = (int8_t)best_off[ci][j];
+                }
+            }
+        }
+        for (int ci = 0; ci < 3; ci++) {
+            int sh = ci ? 1 : 0, x0 = (rx << 6) >> sh, y0 = (ry << 6) >> sh, pw = W >> sh, ph = H >> sh;
+            int w = imin(64 >> sh, pw - x0), h = imin(64 >> sh, ph - y0);
+            const ks_sao_param *p = &ct->sao[ci];
+            ora_sao_apply_ctb(out->c[ci].p, out->c[ci].stride, deb->c[ci].p, deb->c[ci].stride, x0, y0, w, h, pw, ph, p->type, p->band_or_class, p->off);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ level packing ---------------- */
+uint32_t ora_pack_levels(const ora_cfg *cfg, const ora_levels *lv, ks_ctu_syn *ctus, int16_t *pool)
+{
+    int W = cfg->width, H = cfg->height, ctus_w = (W + 63) >> 6, ctus_h = (H + 63) >> 6;
+    uint32_t n = 0;
+    for (int ry = 0; ry < ctus_h; ry++) for (int rx = 0; rx < ctus_w; rx++) {
+        ks_ctu_syn *ct = &ctus[ry * ctus_w + rx];
+        memset(ct->cg_y, 0, sizeof(ct->cg_y)); memset(ct->cg_cb, 0, 8); memset(ct->cg_cr, 0, 8);
+        ct->cg_base = n; ct->rsv[0] = ct->rsv[1] = 0;
+        for (int ci = 0; ci < 3; ci++) {
+            int sh = ci ? 1 : 0, pw = W >> sh, ph = H >> sh, ng = 16 >> sh;
+            for (int gy = 0; gy < ng; gy++) for (int gx = 0; gx < ng; gx++) {
+                int x = ((rx << 6) >> sh) + gx * 4, y = ((ry << 6) >> sh) + gy * 4;
+                if (x >= pw || y >= ph) continue;
+                const int16_t *s = lv->c[ci] + (size_t)y * pw + x;
+                int nz = 0;
+                for (int j = 0; j < 4; j++) for (int i = 0; i < 4; i++) nz |= s[j * pw + i];
+                if (!nz) continue;
+                if (ci == 0) ct->cg_y[gy] |= (uint16_t)(1u << gx); else if (ci == 1) ct->cg_cb[gy] |= (uint8_t)(1u << gx); else ct->cg_cr[gy] |= (uint8_t)(1u << gx);
+                for (int j = 0; j < 4; j++) for (int i = 0; i < 4; i++) pool[(size_t)n * 16 + j * 4 + i] = s[j * pw + i];
+                n++;
+            }
+        }
+    }
+    return n;
+}
