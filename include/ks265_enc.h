@@ -1,0 +1,58 @@
+/*
+ * ks265_enc.h -- host-side encoder API of the ks265 B200 encoder (libks265gpu.so).
+ *
+ * Mirrors the reference's public C API in Android_demo/prebuilt/include/qy265enc.h: QY265ConfigDefaultPreset (:226)
+ * -> ks265_config_default_preset, QY265EncoderOpen (:196) -> ks265_encoder_open, QY265EncoderEncodeFrame (:215) ->
+ * ks265_encoder_encode_gop (the unit of work here is a closed GOP shard: the device pipeline is picture-serial
+ * inside a GOP and GOP shards are what spread over streams / GPUs), QY265EncoderClose (:198) -> ks265_encoder_close.
+ * Error codes follow qy265def.h:7-22 in spirit: 0 = OK, negative = failure.
+ */
+#ifndef KS265_ENC_H
+#define KS265_ENC_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ks265_config {
+    int width, height;          /* -wdt / -hgt */
+    double fps;                 /* -fr */
+    int preset;                 /* 0 ultrafast .. 8 placebo (README.md:20-24) */
+    int rc;                     /* -rc: only 0 (fixed QP) runs on the device path */
+    int qp;                     /* -qp */
+    int iper;                   /* -iper: intra period = GOP shard length */
+    int fixqp;                  /* -fixqp: 1 = same QP for I and P (default: P = QP+1 like the reference) */
+    int sao;                    /* -sao */
+    int sign_hiding;
+    int me_range, me_iters, subpel;
+    int device;                 /* CUDA device ordinal */
+    int psnr;                   /* compute per-plane SSE on the device */
+} ks265_config;
+
+typedef struct ks265_gop_stats {
+    int frames;
+    uint64_t sse[3];            /* summed over the shard (coded area) */
+    uint64_t bytes;
+    uint64_t gpu_launches;
+} ks265_gop_stats;
+
+typedef struct ks265_encoder ks265_encoder;
+
+int  ks265_config_default_preset(ks265_config *cfg, const char *preset);     /* fills everything but width/height */
+int  ks265_preset_index(const char *name);
+ks265_encoder *ks265_encoder_open(const ks265_config *cfg, int *err);
+void ks265_encoder_close(ks265_encoder *enc);
+/* Encode `nframes` display-size I420 pictures (host memory, tightly packed) as one closed GOP: IDR + P...
+ * Writes Annex-B NAL units (VPS/SPS/PPS first) to `bs`; optionally the reconstruction (display size I420) to `recon`.
+ * `frames_dev` != NULL means the pictures already live in DEVICE memory (same layout) and `frames` is ignored.
+ * Returns bytes written or a negative error. */
+long ks265_encoder_encode_gop(ks265_encoder *enc, const uint8_t *frames, const void *frames_dev, int nframes,
+                              uint8_t *bs, size_t bs_cap, uint8_t *recon, ks265_gop_stats *stats);
+/* device-only variant for measurement: runs the device pipeline of a GOP without entropy coding */
+long ks265_encoder_run_gop_device(ks265_encoder *enc, const void *frames_dev, int nframes, ks265_gop_stats *stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

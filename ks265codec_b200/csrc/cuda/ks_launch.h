@@ -1,0 +1,34 @@
+/*
+ * ks_launch.h -- host-visible launch interface of the CUDA hot path (internal to libks265gpu.so).
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "ks265_syntax.h"
+
+/* one picture's planes: Y (pitch = W), U, V (pitch = W/2); tightly packed, W and H multiples of 16 */
+struct KsPlanes { uint8_t *p[3]; };
+struct KsLevels { int16_t *p[3]; };
+
+/* per-picture launch parameters (passed by value to kernels) */
+struct KsPicParams {
+    int W, H;               /* coded luma size */
+    int cw, ch;             /* 16x16 cells */
+    int ctw, cth;           /* 64x64 CTUs */
+    int slice_type, qp, qpc;
+    int lambda_sad_q4, lambda_sse_q4;
+    int me_range, me_iters, subpel;
+    int sign_hiding, sao, strong_intra;
+    int beta_offset_div2, tc_offset_div2;
+};
+
+/* all launches are asynchronous on `st` */
+void ks_upload_tables();
+void ks_launch_me(const KsPicParams &pp, const uint8_t *srcY, const uint8_t *refY, const ks_cell *prev_cells, ks_cell *cells, cudaStream_t st);
+void ks_launch_recon_inter(const KsPicParams &pp, KsPlanes src, KsPlanes ref, KsPlanes rec, KsLevels lv, ks_cell *cells, cudaStream_t st);
+void ks_launch_recon_intra(const KsPicParams &pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *cells, int *sync_ws, cudaStream_t st);
+void ks_launch_deblock(const KsPicParams &pp, KsPlanes rec, const ks_cell *cells, cudaStream_t st);
+void ks_launch_sao(const KsPicParams &pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_syn *ctus, unsigned long long *sse_out, cudaStream_t st);
+void ks_launch_pack(const KsPicParams &pp, KsLevels lv, ks_ctu_syn *ctus, int16_t *pool, uint32_t *n_cg, uint32_t *scan_ws, cudaStream_t st);
+/* number of kernel launches each stage issues (for bench.py's gpu_launches accounting) */
+enum { KS_LAUNCHES_ME = 1, KS_LAUNCHES_RECON = 1, KS_LAUNCHES_DEBLOCK = 2, KS_LAUNCHES_SAO = 2, KS_LAUNCHES_PACK = 3 };

@@ -1,0 +1,320 @@
+/*
+ * ks_loopfilter.cuh -- in-loop filters of the ks265 B200 hot path.
+ *
+ *  deblocking (spec 8.7.2; reference ctuDeblockFilterVer E@0x4144a0, CtuDeblockFilterHorT<> E@0x471d40, leaf
+ *  EdgeFilterLuma{Ver,Hor}_c E@0x413100/0x4133f0, PixelFilterChroma*_c E@0x4137d0, Bs from CalcBsInterP E@0x413990):
+ *  HEVC deblocking is picture-parallel by design -- all vertical edges first, then all horizontal edges on the
+ *  result -- so it is two flat launches, one thread per 4-sample edge segment, in place.  All edges lie on the
+ *  16-sample grid (minimum CU/TU is 16x16 here).
+ *
+ *  SAO (spec 8.7.3; reference statSao*_c E@0x4a6370.., CEncSao::modeDecisionCtu E@0x4a9870, SaoApplyOffset*_c
+ *  E@0x43dba0..): ONE launch, one CTA per CTU: the deblocked 64x64(+1 halo) tile is staged in shared memory once,
+ *  statistics (per-warp packed histograms, the reference's (d<<12)|1 accumulator trick) -> offset RD decision ->
+ *  apply -> write the final picture, plus the per-plane SSE for the PSNR line.  SAO of a CTU needs only its own
+ *  parameters and deblocked neighbours, so stats/decide/apply need no global pass in between (the reference's
+ *  1-CTU lag in CLoopFilterCtu::Execute E@0x492b40 disappears).
+ * Bit-exact mirror of oracle/ora_frame.c (ora_deblock_picture, ora_sao_picture).
+ */
+#pragma once
+#include "ks_common.cuh"
+
+/* ------------------------------------------------------------------ deblocking ------------------- */
+__device__ __forceinline__ bool ks_is_tu_edge(ks_cell p, ks_cell q, int xp, int yp, int xq, int yq, int pos)
+{
+    int sp = 1 << p.cu_log2, sq = 1 << q.cu_log2;
+    bool same = p.cu_log2 == q.cu_log2 && (xp & ~(sp - 1)) == (xq & ~(sq - 1)) && (yp & ~(sp - 1)) == (yq & ~(sq - 1));
+    if (!same) return true;
+    return p.cu_log2 == 6 && (pos & 31) == 0;
+}
+__device__ __forceinline__ int ks_edge_bs(ks_cell p, ks_cell q)
+{
+    if ((p.flags | q.flags) & KS_F_INTRA) return 2;
+    if ((p.flags | q.flags) & KS_F_CBF_Y) return 1;
+    if (abs(p.mvx - q.mvx) >= 4 || abs(p.mvy - q.mvy) >= 4) return 1;
+    return 0;
+}
+/* filter one 4-line segment held in registers: px[l][0..3] = p3..p0, px[l][4..7] = q0..q3 */
+__device__ __forceinline__ bool ks_deblock_luma_regs(int (&px)[4][8], int beta, int tc)
+{
+#define P_(i, l) px[l][3 - (i)]
+#define Q_(i, l) px[l][4 + (i)]
+    int dp0 = abs(P_(2,0) - 2 * P_(1,0) + P_(0,0)), dp3 = abs(P_(2,3) - 2 * P_(1,3) + P_(0,3));
+    int dq0 = abs(Q_(2,0) - 2 * Q_(1,0) + Q_(0,0)), dq3 = abs(Q_(2,3) - 2 * Q_(1,3) + Q_(0,3));
+    int dpq0 = dp0 + dq0, dpq3 = dp3 + dq3, dp = dp0 + dp3, dq = dq0 + dq3, d = dpq0 + dpq3;
+    if (d >= beta) return false;
+    bool s0 = 2 * dpq0 < (beta >> 2) && abs(P_(3,0) - P_(0,0)) + abs(Q_(0,0) - Q_(3,0)) < (beta >> 3) && abs(P_(0,0) - Q_(0,0)) < ((5 * tc + 1) >> 1);
+    bool s3 = 2 * dpq3 < (beta >> 2) && abs(P_(3,3) - P_(0,3)) + abs(Q_(0,3) - Q_(3,3)) < (beta >> 3) && abs(P_(0,3) - Q_(0,3)) < ((5 * tc + 1) >> 1);
+    bool strong = s0 && s3;
+    bool dep = dp < ((beta + (beta >> 1)) >> 3), deq = dq < ((beta + (beta >> 1)) >> 3);
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+        int p0 = P_(0,l), p1 = P_(1,l), p2 = P_(2,l), p3 = P_(3,l), q0 = Q_(0,l), q1 = Q_(1,l), q2 = Q_(2,l), q3 = Q_(3,l);
+        if (strong) {
+            P_(0,l) = ks_clip3(p0 - 2 * tc, p0 + 2 * tc, (p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
+            P_(1,l) = ks_clip3(p1 - 2 * tc, p1 + 2 * tc, (p2 + p1 + p0 + q0 + 2) >> 2);
+            P_(2,l) = ks_clip3(p2 - 2 * tc, p2 + 2 * tc, (2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
+            Q_(0,l) = ks_clip3(q0 - 2 * tc, q0 + 2 * tc, (p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
+            Q_(1,l) = ks_clip3(q1 - 2 * tc, q1 + 2 * tc, (p0 + q0 + q1 + q2 + 2) >> 2);
+            Q_(2,l) = ks_clip3(q2 - 2 * tc, q2 + 2 * tc, (p0 + q0 + q1 + 3 * q2 + 2 * q3 + 4) >> 3);
+        } else {
+            int delta = (9 * (q0 - p0) - 3 * (q1 - p1) + 8) >> 4;
+            if (abs(delta) < tc * 10) {
+                delta = ks_clip3(-tc, tc, delta);
+                P_(0,l) = ks_clip8(p0 + delta); Q_(0,l) = ks_clip8(q0 - delta);
+                if (dep) P_(1,l) = ks_clip8(p1 + ks_clip3(-(tc >> 1), tc >> 1, (((p2 + p0 + 1) >> 1) - p1 + delta) >> 1));
+                if (deq) Q_(1,l) = ks_clip8(q1 + ks_clip3(-(tc >> 1), tc >> 1, (((q2 + q0 + 1) >> 1) - q1 - delta) >> 1));
+            }
+        }
+    }
+#undef P_
+#undef Q_
+    return true;
+}
+
+/* dir 0: vertical edges (x = 16,32,..), thread per (edge, 4-row segment); dir 1: horizontal edges */
+template <int DIR>
+__global__ void __launch_bounds__(256)
+ks_deblock_kernel(KsPicParams pp, KsPlanes rec, const ks_cell *__restrict__ cells)
+{
+    const int W = pp.W, H = pp.H;
+    const int nedge = ((DIR ? H : W) >> 4) - 1, nseg = (DIR ? W : H) >> 2;
+    int ei, si;
+    if (DIR == 0) { ei = blockIdx.x * 32 + (threadIdx.x & 31); si = blockIdx.y * 8 + (threadIdx.x >> 5); }   /* lanes across edges of one row band */
+    else { si = blockIdx.x * 32 + (threadIdx.x & 31); ei = blockIdx.y * 8 + (threadIdx.x >> 5); }           /* lanes across columns (coalesced) */
+    if (ei >= nedge || si >= nseg) return;
+    const int e = (ei + 1) << 4, t = si << 2;
+    const int xq = DIR ? t : e, yq = DIR ? e : t, xp = DIR ? t : e - 1, yp = DIR ? e - 1 : t;
+    const ks_cell cp = cells[(yp >> 4) * pp.cw + (xp >> 4)], cq = cells[(yq >> 4) * pp.cw + (xq >> 4)];
+    if (!ks_is_tu_edge(cp, cq, xp, yp, xq, yq, e)) return;
+    const int bs = ks_edge_bs(cp, cq);
+    if (!bs) return;
+    const int beta = c_beta_table[ks_clip3(0, 51, pp.qp + (pp.beta_offset_div2 << 1))];
+    const int tc = c_tc_table[ks_clip3(0, 53, pp.qp + 2 * (bs - 1) + (pp.tc_offset_div2 << 1))];
+    uint8_t *Y = rec.p[0];
+    int px[4][8];
+    if (DIR == 0) {
+#pragma unroll
+        for (int l = 0; l < 4; l++) {
+            const uint32_t *r = reinterpret_cast<const uint32_t *>(Y + (size_t)(yq + l) * W + xq - 4);
+            uint32_t a = r[0], b = r[1];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { px[l][i] = (a >> (8 * i)) & 255; px[l][4 + i] = (b >> (8 * i)) & 255; }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            uint32_t a = *reinterpret_cast<const uint32_t *>(Y + (size_t)(yq - 4 + i) * W + xq);
+#pragma unroll
+            for (int l = 0; l < 4; l++) px[l][i] = (a >> (8 * l)) & 255;
+        }
+    }
+    if (ks_deblock_luma_regs(px, beta, tc)) {
+        if (DIR == 0) {
+#pragma unroll
+            for (int l = 0; l < 4; l++) {
+                uint32_t *r = reinterpret_cast<uint32_t *>(Y + (size_t)(yq + l) * W + xq - 4);
+                r[0] = (uint32_t)px[l][0] | ((uint32_t)px[l][1] << 8) | ((uint32_t)px[l][2] << 16) | ((uint32_t)px[l][3] << 24);
+                r[1] = (uint32_t)px[l][4] | ((uint32_t)px[l][5] << 8) | ((uint32_t)px[l][6] << 16) | ((uint32_t)px[l][7] << 24);
+            }
+        } else {
+#pragma unroll
+            for (int i = 1; i < 7; i++)
+                *reinterpret_cast<uint32_t *>(Y + (size_t)(yq - 4 + i) * W + xq) =
+                    (uint32_t)px[0][i] | ((uint32_t)px[1][i] << 8) | ((uint32_t)px[2][i] << 16) | ((uint32_t)px[3][i] << 24);
+        }
+    }
+    if (bs == 2) {      /* chroma: only intra edges, 2 chroma lines per 4 luma lines (spec 8.7.2.5.5/.8) */
+        const int tcc = c_tc_table[ks_clip3(0, 53, pp.qpc + 2 + (pp.tc_offset_div2 << 1))];
+        const int CW = W >> 1, xs = DIR ? CW : 1, ys = DIR ? 1 : CW;
+#pragma unroll
+        for (int ci = 1; ci < 3; ci++) {
+            uint8_t *q = rec.p[ci] + (size_t)(yq >> 1) * CW + (xq >> 1);
+#pragma unroll
+            for (int l = 0; l < 2; l++) {
+                uint8_t *c = q + l * ys;
+                int p0 = c[-xs], p1 = c[-2 * xs], q0 = c[0], q1 = c[xs];
+                int delta = ks_clip3(-tcc, tcc, ((((q0 - p0) << 2) + p1 - q1 + 4) >> 3));
+                c[-xs] = (uint8_t)ks_clip8(p0 + delta); c[0] = (uint8_t)ks_clip8(q0 - delta);
+            }
+        }
+    }
+}
+
+void ks_launch_deblock(const KsPicParams &pp, KsPlanes rec, const ks_cell *cells, cudaStream_t st)
+{
+    int nev = (pp.W >> 4) - 1, nsv = pp.H >> 2, neh = (pp.H >> 4) - 1, nsh = pp.W >> 2;
+    if (nev > 0) ks_deblock_kernel<0><<<dim3((nev + 31) / 32, (nsv + 7) / 8), 256, 0, st>>>(pp, rec, cells);
+    if (neh > 0) ks_deblock_kernel<1><<<dim3((nsh + 31) / 32, (neh + 7) / 8), 256, 0, st>>>(pp, rec, cells);
+}
+
+/* ------------------------------------------------------------------ SAO -------------------------- */
+#define KS_SAO_WARPS 8
+struct KsSaoSmem {
+    uint8_t tile[3][66 * 68];              /* deblocked samples incl. 1-sample halo; chroma uses 34 x 36 */
+    int hist[KS_SAO_WARPS][3][52];         /* packed (sum<<12)|count: [0..19] EO class*5+cat, [20..51] BO band */
+    int sum[3][52], cnt[3][52];
+    int cost[3][48], off[3][48];           /* [0..15] EO class*4+(cat-1), [16..47] BO band */
+    ks_sao_param par[3];
+    unsigned long long sse[3];
+};
+__device__ __forceinline__ int ks_sgn(int v) { return (v > 0) - (v < 0); }
+__device__ __forceinline__ int ks_sao_offset_rd(int sum, int cnt, int signc, int lam, int is_bo, int *best_o)
+{   /* == oracle sao_offset_rd */
+    *best_o = 0;
+    if (!cnt) return 0;
+    int o = sum >= 0 ? (sum + cnt / 2) / cnt : -((-sum + cnt / 2) / cnt);
+    o = ks_clip3(-7, 7, o);
+    if ((signc > 0 && o < 0) || (signc < 0 && o > 0)) o = 0;
+    int best = lam >> 4;
+    int step = o > 0 ? -1 : 1;
+    for (int v = o; v != 0; v += step) {
+        int bits = abs(v) + 1 + (is_bo ? 1 : 0);
+        int c = cnt * v * v - 2 * v * sum + ((lam * bits) >> 4);
+        if (c < best || (c == best && abs(v) < abs(*best_o))) { best = c; *best_o = v; }
+    }
+    return best;
+}
+
+__global__ void __launch_bounds__(KS_SAO_WARPS * KS_WARP)
+ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_syn *__restrict__ ctus, unsigned long long *sse_out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    KsSaoSmem *sm = reinterpret_cast<KsSaoSmem *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rx = blockIdx.x, ry = blockIdx.y;
+    const int dxa[4] = {-1, 0, -1, 1}, dya[4] = {0, -1, -1, -1};      /* neighbour a of class k; b = -a */
+    const int cat_of[5] = {1, 2, 0, 3, 4};
+    for (int i = tid; i < KS_SAO_WARPS * 3 * 52; i += blockDim.x) (&sm->hist[0][0][0])[i] = 0;
+    if (tid < 3) sm->sse[tid] = 0;
+    /* ---- stage the deblocked tile (+halo, coordinates clamped; out-of-picture neighbours are masked later) ---- */
+    for (int ci = 0; ci < 3; ci++) {
+        const int sh = ci ? 1 : 0, PW = pp.W >> sh, PH = pp.H >> sh, x0 = (rx << 6) >> sh, y0 = (ry << 6) >> sh;
+        const int tw = (64 >> sh) + 2, pitch = ci ? 36 : 68;
+        for (int i = tid; i < tw * tw; i += blockDim.x) {
+            int r = i / tw, c = i - r * tw;
+            int gy = min(max(y0 - 1 + r, 0), PH - 1), gx = min(max(x0 - 1 + c, 0), PW - 1);
+            sm->tile[ci][r * pitch + c] = deb.p[ci][(size_t)gy * PW + gx];
+        }
+    }
+    __syncthreads();
+    /* ---- statistics ---- */
+    if (pp.sao) {
+        for (int ci = 0; ci < 3; ci++) {
+            const int sh = ci ? 1 : 0, PW = pp.W >> sh, PH = pp.H >> sh, x0 = (rx << 6) >> sh, y0 = (ry << 6) >> sh;
+            const int bw = min(64 >> sh, PW - x0), bh = min(64 >> sh, PH - y0), pitch = ci ? 36 : 68, bwl = 6 - sh;
+            int *h = sm->hist[warp][ci];
+            for (int i = tid; i < (bh << bwl); i += blockDim.x) {
+                int y = i >> bwl, x = i & ((1 << bwl) - 1);
+                if (x >= bw) continue;
+                const uint8_t *t = &sm->tile[ci][(y + 1) * pitch + x + 1];
+                int c = t[0], d = (int)src.p[ci][(size_t)(y0 + y) * PW + x0 + x] - c;
+                int v = d * 4096 + 1;
+                atomicAdd(&h[20 + (c >> 3)], v);
+                int gx = x0 + x, gy = y0 + y;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    int xa = gx + dxa[k], ya = gy + dya[k], xb = gx - dxa[k], yb = gy - dya[k];
+                    if (xa < 0 || xb < 0 || ya < 0 || yb < 0 || xa >= PW || xb >= PW || ya >= PH || yb >= PH) continue;
+                    int cat = cat_of[2 + ks_sgn(c - t[dya[k] * pitch + dxa[k]]) + ks_sgn(c - t[-dya[k] * pitch - dxa[k]])];
+                    if (cat) atomicAdd(&h[k * 5 + cat], v);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < 3 * 52) {
+            int ci = tid / 52, b = tid - ci * 52, s = 0, n = 0;
+            for (int w = 0; w < KS_SAO_WARPS; w++) { int v = sm->hist[w][ci][b]; int c = v & 4095; n += c; s += (v - c) >> 12; }
+            sm->sum[ci][b] = s; sm->cnt[ci][b] = n;
+        }
+        __syncthreads();
+        /* ---- per-bin offset RD (144 independent little problems) ---- */
+        if (tid < 3 * 48) {
+            int ci = tid / 48, j = tid - ci * 48, o, c;
+            if (j < 16) { int k = j >> 2, cat = (j & 3) + 1; c = ks_sao_offset_rd(sm->sum[ci][k * 5 + cat], sm->cnt[ci][k * 5 + cat], cat <= 2 ? 1 : -1, pp.lambda_sse_q4, 0, &o); }
+            else c = ks_sao_offset_rd(sm->sum[ci][20 + j - 16], sm->cnt[ci][20 + j - 16], 0, pp.lambda_sse_q4, 1, &o);
+            sm->cost[ci][j] = c; sm->off[ci][j] = o;
+        }
+    }
+    __syncthreads();
+    /* ---- type decision: thread 0 luma, thread 32 chroma (Cb and Cr share type / class) ---- */
+    if (tid == 0 || tid == 32) {
+        const int c0 = tid ? 1 : 0, c1 = tid ? 2 : 0, lam = pp.lambda_sse_q4;
+        int best_cost = 0, best_type = 0, best_class = 0, best_band[3] = {0, 0, 0};
+        if (pp.sao) {
+            for (int k = 0; k < 4; k++) {
+                int total = (lam * 4) >> 4;
+                for (int ci = c0; ci <= c1; ci++) for (int j = 0; j < 4; j++) total += sm->cost[ci][k * 4 + j];
+                if (total < best_cost) { best_cost = total; best_type = 2; best_class = k; }
+            }
+            int total = (lam * 7) >> 4, band[3] = {0, 0, 0};
+            for (int ci = c0; ci <= c1; ci++) {
+                int bestc = 0x7fffffff, bs = 0;
+                for (int s = 0; s <= 28; s++) { int c = sm->cost[ci][16 + s] + sm->cost[ci][17 + s] + sm->cost[ci][18 + s] + sm->cost[ci][19 + s]; if (c < bestc) { bestc = c; bs = s; } }
+                total += bestc; band[ci] = bs;
+            }
+            if (total < best_cost) { best_cost = total; best_type = 1; for (int ci = c0; ci <= c1; ci++) best_band[ci] = band[ci]; }
+            int nz = 0;
+            for (int ci = c0; ci <= c1; ci++) for (int j = 0; j < 4; j++)
+                nz |= best_type == 2 ? sm->off[ci][best_class * 4 + j] : (best_type == 1 ? sm->off[ci][16 + best_band[ci] + j] : 0);
+            if (!nz) best_type = 0;
+        }
+        for (int ci = c0; ci <= c1; ci++) {
+            ks_sao_param p; p.type = (uint8_t)best_type; p.band_or_class = 0; p.off[0] = p.off[1] = p.off[2] = p.off[3] = 0;
+            if (best_type) {
+                p.band_or_class = (uint8_t)(best_type == 2 ? best_class : best_band[ci]);
+                for (int j = 0; j < 4; j++) p.off[j] = (int8_t)(best_type == 2 ? sm->off[ci][best_class * 4 + j] : sm->off[ci][16 + best_band[ci] + j]);
+            }
+            sm->par[ci] = p;
+            ctus[ry * pp.ctw + rx].sao[ci] = p;
+        }
+        if (tid == 0) { ctus[ry * pp.ctw + rx].rsv[0] = 0; ctus[ry * pp.ctw + rx].rsv[1] = 0; }
+    }
+    __syncthreads();
+    /* ---- apply + write the final picture + SSE against the source ---- */
+    for (int ci = 0; ci < 3; ci++) {
+        const int sh = ci ? 1 : 0, PW = pp.W >> sh, PH = pp.H >> sh, x0 = (rx << 6) >> sh, y0 = (ry << 6) >> sh;
+        const int bw = min(64 >> sh, PW - x0), bh = min(64 >> sh, PH - y0), pitch = ci ? 36 : 68, bwl = 4 - sh;   /* 4 samples per thread */
+        const ks_sao_param p = sm->par[ci];
+        const int k = p.band_or_class;
+        unsigned long long sse = 0;
+        for (int i = tid; i < (bh << bwl); i += blockDim.x) {
+            int y = i >> bwl, x = (i & ((1 << bwl) - 1)) << 2;
+            if (x >= bw) continue;
+            const uint8_t *t = &sm->tile[ci][(y + 1) * pitch + x + 1];
+            uint32_t s4 = *reinterpret_cast<const uint32_t *>(src.p[ci] + (size_t)(y0 + y) * PW + x0 + x), o4 = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int c = t[j], v = c;
+                if (p.type == 1) { int b = ((c >> 3) - k) & 31; if (b < 4) v = c + p.off[b]; }
+                else if (p.type == 2) {
+                    int gx = x0 + x + j, gy = y0 + y;
+                    int xa = gx + dxa[k], ya = gy + dya[k], xb = gx - dxa[k], yb = gy - dya[k];
+                    if (!(xa < 0 || xb < 0 || ya < 0 || yb < 0 || xa >= PW || xb >= PW || ya >= PH || yb >= PH)) {
+                        int cat = cat_of[2 + ks_sgn(c - t[j + dya[k] * pitch + dxa[k]]) + ks_sgn(c - t[j - dya[k] * pitch - dxa[k]])];
+                        if (cat) v = c + p.off[cat - 1];
+                    }
+                }
+                v = ks_clip8(v);
+                o4 |= (uint32_t)v << (8 * j);
+                int e = (int)((s4 >> (8 * j)) & 255) - v;
+                sse += (unsigned)(e * e);
+            }
+            *reinterpret_cast<uint32_t *>(out.p[ci] + (size_t)(y0 + y) * PW + x0 + x) = o4;
+        }
+        if (sse_out) {
+            unsigned lo = ks_warp_sum((unsigned)sse);       /* per-thread SSE < 2^32: <= 64 samples * 65025 */
+            if (lane == 0) atomicAdd(&sm->sse[ci], (unsigned long long)lo);
+        }
+    }
+    if (sse_out) {
+        __syncthreads();
+        if (tid < 3) atomicAdd(&sse_out[tid], sm->sse[tid]);
+    }
+}
+
+void ks_launch_sao(const KsPicParams &pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_syn *ctus, unsigned long long *sse_out, cudaStream_t st)
+{
+    static bool attr_done = false;
+    if (!attr_done) { cudaFuncSetAttribute(ks_sao_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsSaoSmem)); attr_done = true; }
+    ks_sao_kernel<<<dim3(pp.ctw, pp.cth), KS_SAO_WARPS * KS_WARP, sizeof(KsSaoSmem), st>>>(pp, src, deb, out, ctus, sse_out);
+}

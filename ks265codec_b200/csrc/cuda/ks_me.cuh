@@ -1,0 +1,246 @@
+/*
+ * ks_me.cuh -- motion estimation + interpolation for the ks265 B200 hot path.
+ *
+ * One warp owns one 16x16 cell.  The reference window (40 rows x 52 bytes) is staged in shared memory once
+ * and re-centred only when the search walks out of it; every SAD is 2 x VABSDIFF4-accumulate per lane
+ * (8 pixels per lane) and a packed butterfly shuffle reduction for 2 candidates at a time.
+ * Sub-pel candidates use the real 8-tap interpolation (reference: subMeHpel_RealInterp E@0x4ac3b0 /
+ * subMeQpel_8Sad_* E@0x4acb90.., kernels interpLuma{Hor,Ver}* E@0x417600..): horizontal taps run on
+ * dp4a (u8 x s8), the 2-D case keeps the raw 14-bit row sums (no offset, like interpLumaHor8to16_c) in
+ * shared memory and finishes with (sum+2048)>>12 like interpLumaVer16to8_c.
+ * Search order / tie-breaking mirror oracle/ora_frame.c:me_cell bit for bit.
+ */
+#pragma once
+#include "ks_common.cuh"
+
+#define KS_WIN_H 40
+#define KS_WIN_WW 13          /* words per window row (52 bytes; odd word pitch -> conflict-free rows) */
+#define KS_WIN_MARGIN 12
+
+struct KsWarpScratch {
+    uint32_t win[KS_WIN_H][KS_WIN_WW];
+    int16_t  tmp[24][16];     /* raw horizontal 8-tap sums, rows -3..+19 */
+};
+
+/* stage the window whose top-left luma sample is (wx0, wy0); wx0 % 4 == 0; coordinates clamp to the picture
+ * (equivalent to the reference's padded reference planes, expandPicture_*) */
+__device__ __forceinline__ void ks_load_window(uint32_t (*win)[KS_WIN_WW], const uint8_t *__restrict__ ref, int W, int H,
+                                               int wx0, int wy0, int lane)
+{
+    for (int idx = lane; idx < KS_WIN_H * KS_WIN_WW; idx += KS_WARP) {
+        int r = idx / KS_WIN_WW, c = idx - r * KS_WIN_WW;
+        int gy = min(max(wy0 + r, 0), H - 1), gx = wx0 + 4 * c;
+        const uint8_t *row = ref + (size_t)gy * W;
+        uint32_t v;
+        if (gx >= 0 && gx + 3 < W) v = *reinterpret_cast<const uint32_t *>(row + gx);
+        else {
+            v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) v |= (uint32_t)row[min(max(gx + b, 0), W - 1)] << (8 * b);
+        }
+        win[r][c] = v;
+    }
+    __syncwarp();
+}
+
+/* lane's 8 reference pixels of the 16x16 block whose origin is (bxw, byw) in window coordinates */
+__device__ __forceinline__ void ks_win_px8(const uint32_t (*win)[KS_WIN_WW], int bxw, int byw, int lane, uint32_t &a, uint32_t &b)
+{
+    int wx = bxw + 8 * (lane & 1);
+    const uint32_t *r = win[byw + (lane >> 1)] + (wx >> 2);
+    unsigned sh = (wx & 3) * 8;
+    a = __funnelshift_r(r[0], r[1], sh);
+    b = __funnelshift_r(r[1], r[2], sh);
+}
+__device__ __forceinline__ unsigned ks_sad_partial(const uint32_t (*win)[KS_WIN_WW], int bxw, int byw, int lane, uint32_t s0, uint32_t s1)
+{
+    uint32_t a, b;
+    ks_win_px8(win, bxw, byw, lane, a, b);
+    return __vsadu4(a, s0) + __vsadu4(b, s1);
+}
+
+/* 16 bytes starting at window byte column p of row `row`, as 4 words */
+__device__ __forceinline__ void ks_row16(const uint32_t (*win)[KS_WIN_WW], int row, int p, uint32_t n[4])
+{
+    const uint32_t *r = win[row] + (p >> 2);
+    unsigned sh = (p & 3) * 8;
+#pragma unroll
+    for (int i = 0; i < 4; i++) n[i] = __funnelshift_r(r[i], r[i + 1], sh);
+}
+/* raw 8-tap horizontal sums for 8 consecutive outputs; n = 16 bytes starting 3 left of the first output */
+__device__ __forceinline__ void ks_htaps8(const uint32_t n[4], int tlo, int thi, int out[8])
+{
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        unsigned sh = (j & 3) * 8;
+        uint32_t lo = __funnelshift_r(n[j >> 2], n[(j >> 2) + 1], sh);
+        uint32_t hi = (j < 4) ? __funnelshift_r(n[1 + (j >> 2)], n[2 + (j >> 2)], sh)
+                              : ((j == 4) ? n[2] : __funnelshift_r(n[2], n[3], sh));
+        out[j] = ks_dp4a_us(hi, thi, ks_dp4a_us(lo, tlo, 0));
+    }
+}
+
+/* quarter-sample prediction of the 16x16 block at integer window origin (bxw, byw) with fractions (fx, fy):
+ * returns the lane's 8 predicted pixels (row lane>>1, columns 8*(lane&1)..+7) packed in (o0, o1).
+ * Matches ora_mc_luma (spec 8.5.3.3.3.1) exactly. Warp-collective (uses scratch->tmp for the 2-D case). */
+__device__ __forceinline__ void ks_interp16(KsWarpScratch *sc, int bxw, int byw, int fx, int fy, int lane, uint32_t &o0, uint32_t &o1)
+{
+    const int row = lane >> 1, half = lane & 1;
+    if (fx == 0 && fy == 0) { ks_win_px8(sc->win, bxw, byw, lane, o0, o1); return; }
+    int v[8];
+    if (fy == 0) {
+        uint32_t n[4];
+        ks_row16(sc->win, byw + row, bxw + 8 * half - 3, n);
+        ks_htaps8(n, c_luma_taps_packed[fx][0], c_luma_taps_packed[fx][1], v);
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = ks_clip8((v[j] + 32) >> 6);
+    } else if (fx == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            uint32_t a, b; int c = c_luma_taps[fy][t];
+            int wx = bxw + 8 * half;
+            const uint32_t *r = sc->win[byw + row - 3 + t] + (wx >> 2);
+            unsigned sh = (wx & 3) * 8;
+            a = __funnelshift_r(r[0], r[1], sh); b = __funnelshift_r(r[1], r[2], sh);
+#pragma unroll
+            for (int j = 0; j < 4; j++) { v[j] += c * (int)((a >> (8 * j)) & 255); v[4 + j] += c * (int)((b >> (8 * j)) & 255); }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = ks_clip8((v[j] + 32) >> 6);
+    } else {
+        const int tlo = c_luma_taps_packed[fx][0], thi = c_luma_taps_packed[fx][1];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            int rr = row + 16 * k;
+            if (rr < 23) {
+                uint32_t n[4]; int h[8];
+                ks_row16(sc->win, byw - 3 + rr, bxw + 8 * half - 3, n);
+                ks_htaps8(n, tlo, thi, h);
+                uint32_t *d = reinterpret_cast<uint32_t *>(&sc->tmp[rr][8 * half]);
+#pragma unroll
+                for (int j = 0; j < 4; j++) d[j] = ((uint32_t)h[2 * j] & 0xffffu) | ((uint32_t)h[2 * j + 1] << 16);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            int c = c_luma_taps[fy][t];
+            uint4 q = *reinterpret_cast<const uint4 *>(&sc->tmp[row + t][8 * half]);
+            uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) { v[2 * j] += c * (int)(short)(w[j] & 0xffffu); v[2 * j + 1] += c * ((int)w[j] >> 16); }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = ks_clip8((v[j] + 2048) >> 12);
+        __syncwarp();
+    }
+    o0 = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+    o1 = (uint32_t)v[4] | ((uint32_t)v[5] << 8) | ((uint32_t)v[6] << 16) | ((uint32_t)v[7] << 24);
+}
+
+/* window origin that centres integer offset (cx, cy) of the cell at (x0, y0) */
+__device__ __forceinline__ void ks_center_window(int x0, int y0, int cx, int cy, int &wx0, int &wy0)
+{
+    wx0 = (x0 + cx - KS_WIN_MARGIN) & ~3;
+    wy0 = y0 + cy - KS_WIN_MARGIN;
+}
+
+#define KS_ME_WARPS 8
+__global__ void __launch_bounds__(KS_ME_WARPS * KS_WARP)
+ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, const uint8_t *__restrict__ refY,
+             const ks_cell *__restrict__ prev_cells, ks_cell *__restrict__ cells)
+{
+    __shared__ __align__(16) KsWarpScratch scratch[KS_ME_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cell = blockIdx.x * KS_ME_WARPS + warp;
+    if (cell >= pp.cw * pp.ch) return;
+    KsWarpScratch *sc = &scratch[warp];
+    const int cyc = cell / pp.cw, cxc = cell - cyc * pp.cw, x0 = cxc << 4, y0 = cyc << 4;
+    const int W = pp.W, H = pp.H, R = pp.me_range, lam = pp.lambda_sad_q4;
+    /* source pixels of this lane: row lane>>1, 8 bytes */
+    const uint2 s = *reinterpret_cast<const uint2 *>(srcY + (size_t)(y0 + (lane >> 1)) * W + x0 + 8 * (lane & 1));
+    int tpx = 0, tpy = 0;
+    if (prev_cells) { ks_cell pc = prev_cells[cell]; if (!(pc.flags & KS_F_INTRA)) { tpx = pc.mvx; tpy = pc.mvy; } }
+#define MVCOST(qx, qy) ((lam * (ks_mvbits((qx) - tpx) + ks_mvbits((qy) - tpy))) >> 4)
+
+    /* ---- start point: zero vs rounded temporal predictor (reference: meInitPoint E@0x4818b0) ---- */
+    int wx0, wy0;
+    ks_center_window(x0, y0, 0, 0, wx0, wy0);
+    ks_load_window(sc->win, refY, W, H, wx0, wy0, lane);
+    int bx = 0, by = 0;
+    int bc = (int)ks_warp_sum(ks_sad_partial(sc->win, x0 - wx0, y0 - wy0, lane, s.x, s.y)) + MVCOST(0, 0);
+    {
+        int cx = ks_clip3(-R, R, (tpx + 2) >> 2), cy = ks_clip3(-R, R, (tpy + 2) >> 2);
+        if (cx | cy) {
+            int bxw = x0 + cx - wx0, byw = y0 + cy - wy0;
+            if (bxw < 0 || bxw > 35 || byw < 0 || byw > 24) {
+                ks_center_window(x0, y0, cx, cy, wx0, wy0);
+                ks_load_window(sc->win, refY, W, H, wx0, wy0, lane);
+                bxw = x0 + cx - wx0; byw = y0 + cy - wy0;
+            }
+            int c = (int)ks_warp_sum(ks_sad_partial(sc->win, bxw, byw, lane, s.x, s.y)) + MVCOST(cx * 4, cy * 4);
+            if (c < bc) { bc = c; bx = cx; by = cy; }
+        }
+    }
+    /* ---- small diamond (reference: interMeDia E@0x4849d0, x264 DIA with sad4 order up,down,left,right) ---- */
+    for (int it = 0; it < pp.me_iters; it++) {
+        int bxw = x0 + bx - wx0, byw = y0 + by - wy0;
+        if (bxw < 1 || bxw > 34 || byw < 1 || byw > 23) {
+            ks_center_window(x0, y0, bx, by, wx0, wy0);
+            ks_load_window(sc->win, refY, W, H, wx0, wy0, lane);
+            bxw = x0 + bx - wx0; byw = y0 + by - wy0;
+        }
+        unsigned p01 = ks_sad_partial(sc->win, bxw, byw - 1, lane, s.x, s.y) | (ks_sad_partial(sc->win, bxw, byw + 1, lane, s.x, s.y) << 16);
+        unsigned p23 = ks_sad_partial(sc->win, bxw - 1, byw, lane, s.x, s.y) | (ks_sad_partial(sc->win, bxw + 1, byw, lane, s.x, s.y) << 16);
+        p01 = ks_warp_sum(p01); p23 = ks_warp_sum(p23);
+        int sad[4] = {(int)(p01 & 0xffffu), (int)(p01 >> 16), (int)(p23 & 0xffffu), (int)(p23 >> 16)};
+        const int dx[4] = {0, 0, -1, 1}, dy[4] = {-1, 1, 0, 0};
+        int bk = -1, lc = bc;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int nx = bx + dx[k], ny = by + dy[k];
+            if (abs(nx) > R || abs(ny) > R) continue;
+            int c = sad[k] + MVCOST(nx * 4, ny * 4);
+            if (c < lc) { lc = c; bk = k; }
+        }
+        if (bk < 0) break;
+        bx += dx[bk]; by += dy[bk]; bc = lc;
+    }
+    /* ---- half then quarter refinement, 8 neighbours each (reference: subMeSquare E@0x4aee80) ---- */
+    int mx = bx * 4, my = by * 4;
+    if (pp.subpel > 0) {
+        int bxw = x0 + bx - wx0, byw = y0 + by - wy0;
+        if (bxw < 4 || bxw > 27 || byw < 4 || byw > 20) {
+            ks_center_window(x0, y0, bx, by, wx0, wy0);
+            ks_load_window(sc->win, refY, W, H, wx0, wy0, lane);
+        }
+        const int sqx[8] = {-1, 0, 1, -1, 1, -1, 0, 1}, sqy[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+        for (int step = 2; step >= 1; step--) {
+            if (pp.subpel < (step == 2 ? 1 : 2)) break;
+            int bk = -1, lc = bc;
+            for (int k = 0; k < 8; k++) {
+                int qx = mx + sqx[k] * step, qy = my + sqy[k] * step;
+                uint32_t o0, o1;
+                ks_interp16(sc, x0 + (qx >> 2) - wx0, y0 + (qy >> 2) - wy0, qx & 3, qy & 3, lane, o0, o1);
+                int c = (int)ks_warp_sum(__vsadu4(o0, s.x) + __vsadu4(o1, s.y)) + MVCOST(qx, qy);
+                if (c < lc) { lc = c; bk = k; }
+            }
+            if (bk >= 0) { mx += sqx[bk] * step; my += sqy[bk] * step; bc = lc; }
+        }
+    }
+#undef MVCOST
+    if (lane == 0) {
+        ks_cell c; c.mvx = (int16_t)mx; c.mvy = (int16_t)my; c.cu_log2 = 4; c.flags = 0; c.intra_mode = 0; c.rsv = 0;
+        cells[cell] = c;
+    }
+}
+
+void ks_launch_me(const KsPicParams &pp, const uint8_t *srcY, const uint8_t *refY, const ks_cell *prev_cells, ks_cell *cells, cudaStream_t st)
+{
+    int ncell = pp.cw * pp.ch;
+    ks_me_kernel<<<(ncell + KS_ME_WARPS - 1) / KS_ME_WARPS, KS_ME_WARPS * KS_WARP, 0, st>>>(pp, srcY, refY, prev_cells, cells);
+}

@@ -1,0 +1,578 @@
+/*
+ * ks_recon.cuh -- prediction + residual path of the ks265 B200 hot path (SURVEY.md 8a rows a7-a14 + intra, f1).
+ *
+ *  ks_tb_code<N>   one warp codes 32/N transform blocks at once: residual -> forward DCT (reference
+ *                  H265_2dDct*_c E@0x4b7600.., stage shifts 2*log2N-2 and 7) -> quantiser (H265QuantBlock_c
+ *                  E@0x4a2580) -> sign-data hiding (signBitHidingHDQ E@0x4a29c0) -> dequantiser
+ *                  (H265DeQuantBlock_c E@0x439540) -> inverse DCT + prediction add (H265_2dIDct*_c E@0x4417f0..).
+ *                  int16/int32 butterfly work on the CUDA cores: lane = one row/column, the transform matrix is
+ *                  an immediate-offset constant-bank operand, one even/odd butterfly level halves the MACs,
+ *                  transposes go through padded shared memory.  No tensor cores (north star).
+ *  ks_recon_inter_kernel   one CTA per 64x64 CTU: CU-size decision, motion compensation of the 16 cells into
+ *                  shared memory (the reference's `reconstruct` E@0x47d600 driver + interpolatePuLx E@0x487260),
+ *                  then the transform tasks.
+ *  ks_recon_intra_kernel   I pictures: CTU rows run as a wavefront (reference: WPP, CCtuEncWpp::waitForTopRightCtu
+ *                  E@0x468d40) inside ONE launch, rows handed out by a ticket counter, progress flags in HBM.
+ * Bit-exact mirror of oracle/ora_frame.c.
+ */
+#pragma once
+#include "ks_me.cuh"
+
+/* ------------------------------------------------------------------ transform-block coder -------- */
+struct KsTbScratch {
+    int16_t S[32 * 40];        /* transpose buffer, rows padded by 8 (conflict-free 128-bit reads) */
+    int16_t C[32 * 32];        /* coefficients  [v][u] (per TB group: G blocks of N x N, consecutive) */
+    int16_t L[32 * 32];        /* levels */
+    int16_t D[32 * 32];        /* deltaU */
+};
+
+template <int N> struct KsLog2 { static const int v = N == 32 ? 5 : (N == 16 ? 4 : 3); };
+
+/* forward: out[u] = sum_x M[u][x] in[x] with one even/odd split */
+template <int N>
+__device__ __forceinline__ void ks_fwd_pass(const int (&in)[N], int (&out)[N], int shift)
+{
+    constexpr int STEP = 32 / N, HN = N / 2;
+    int e[HN], o[HN];
+#pragma unroll
+    for (int x = 0; x < HN; x++) { e[x] = in[x] + in[N - 1 - x]; o[x] = in[x] - in[N - 1 - x]; }
+    const int rnd = 1 << (shift - 1);
+#pragma unroll
+    for (int u = 0; u < N; u++) {
+        int acc = rnd;
+#pragma unroll
+        for (int x = 0; x < HN; x++) acc += c_dct[u * STEP][x] * ((u & 1) ? o[x] : e[x]);
+        out[u] = acc >> shift;
+    }
+}
+/* inverse: out[y] = sum_k M[k][y] in[k] with one even/odd split */
+template <int N>
+__device__ __forceinline__ void ks_inv_pass(const int (&in)[N], int (&out)[N], int shift, bool clip16)
+{
+    constexpr int STEP = 32 / N, HN = N / 2;
+    const int rnd = 1 << (shift - 1);
+#pragma unroll
+    for (int y = 0; y < HN; y++) {
+        int e = 0, o = 0;
+#pragma unroll
+        for (int k = 0; k < N; k += 2) e += c_dct[k * STEP][y] * in[k];
+#pragma unroll
+        for (int k = 1; k < N; k += 2) o += c_dct[k * STEP][y] * in[k];
+        int a = (e + o + rnd) >> shift, b = (e - o + rnd) >> shift;
+        if (clip16) { a = ks_clip3(-32768, 32767, a); b = ks_clip3(-32768, 32767, b); }
+        out[y] = a; out[N - 1 - y] = b;
+    }
+}
+
+/* sign-data hiding for one coefficient group (16 scan positions starting at scan index sp) of a TB whose
+ * coefficient/level/deltaU arrays are N x N row-major.  Mirrors ora_sign_hide's per-CG body. */
+template <int N>
+__device__ __forceinline__ void ks_sbh_cg(const int16_t *C, int16_t *L, const int16_t *D, const uint16_t *scan, int sp, bool is_last_cg)
+{
+    int first = 16, last = -1, sum = 0;
+    int pos[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) { int s = scan[sp + i]; pos[i] = (s >> 8) * N + (s & 255); }
+#pragma unroll
+    for (int i = 0; i < 16; i++) { int l = L[pos[i]]; if (l) { if (first == 16) first = i; last = i; } }
+    if (last - first < 4) return;
+#pragma unroll
+    for (int i = 0; i < 16; i++) if (i >= first && i <= last) sum += L[pos[i]];
+    int lf = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) if (i == first) lf = L[pos[i]];
+    const int signbit = lf > 0 ? 0 : 1;
+    if (signbit == (sum & 1)) return;
+    int min_cost = 0x7fffffff, min_pos = -1, final_change = 0;
+    int start = is_last_cg ? last : 15;
+#pragma unroll
+    for (int i = 15; i >= 0; i--) {
+        if (i > start) continue;
+        int p = pos[i], lv = L[p], du = D[p], cost, change = 0;
+        if (lv != 0) {
+            if (du > 0) { cost = -du; change = 1; }
+            else if (i == first && abs(lv) == 1) cost = 0x7fffffff;
+            else { cost = du; change = -1; }
+        } else if (i < first) {
+            int this_sign = C[p] >= 0 ? 0 : 1;
+            if (this_sign != signbit) cost = 0x7fffffff;
+            else { cost = -du; change = 1; }
+        } else { cost = -du; change = 1; }
+        if (cost < min_cost) { min_cost = cost; final_change = change; min_pos = p; }
+    }
+    int lv = L[min_pos];
+    if (lv == 32767 || lv == -32768) final_change = -1;
+    L[min_pos] = (int16_t)(C[min_pos] >= 0 ? lv + final_change : lv - final_change);
+}
+
+/*
+ * One warp, G = 32/N transform blocks: lane -> (g = lane / N, r = lane % N).
+ *   src_row : global pointer to row r of the lane's source block      (N bytes, valid lanes only)
+ *   pred_row: shared  pointer to row r of the lane's prediction block (N bytes)
+ *   rec_row : global pointer to row r of the lane's reconstruction
+ *   lev_row : global pointer to row r of the lane's level block (dense int16 plane)
+ * returns, per lane, whether the lane's block has any non-zero level (cbf).
+ */
+template <int N>
+__device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, bool valid,
+                                        const uint8_t *__restrict__ src_row, const uint8_t *pred_row,
+                                        uint8_t *__restrict__ rec_row, int16_t *__restrict__ lev_row,
+                                        int qp, int intra_slice, int sign_hiding, int lane)
+{
+    constexpr int LOG2 = KsLog2<N>::v, G = 32 / N, SP = N + 8;
+    const int g = lane / N, r = lane % N;
+    const unsigned gmask = (N == 32) ? 0xffffffffu : (((1u << N) - 1u) << (g * N));
+    int16_t *S = sc->S + g * N * SP, *C = sc->C + g * N * N, *L = sc->L + g * N * N, *D = sc->D + g * N * N;
+    int res[N], t[N];
+    uint8_t pred[N];
+    /* a. residual row */
+#pragma unroll
+    for (int x = 0; x < N; x += 4) {
+        uint32_t p4 = *reinterpret_cast<const uint32_t *>(pred_row + x);
+        uint32_t s4 = valid ? *reinterpret_cast<const uint32_t *>(src_row + x) : p4;
+#pragma unroll
+        for (int b = 0; b < 4; b++) { pred[x + b] = (uint8_t)(p4 >> (8 * b)); res[x + b] = (int)((s4 >> (8 * b)) & 255) - (int)pred[x + b]; }
+    }
+    /* b. forward pass 1 (rows), stage shift 2*log2N-2; store transposed S[u][r] */
+    ks_fwd_pass<N>(res, t, 2 * LOG2 - 2);
+#pragma unroll
+    for (int u = 0; u < N; u++) S[u * SP + r] = (int16_t)t[u];
+    __syncwarp();
+    /* c. forward pass 2 (columns): lane = horizontal frequency u = r */
+#pragma unroll
+    for (int y = 0; y < N; y += 8) {
+        uint4 q = *reinterpret_cast<const uint4 *>(&S[r * SP + y]);
+        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) { res[y + 2 * j] = (int)(short)(w[j] & 0xffffu); res[y + 2 * j + 1] = (int)w[j] >> 16; }
+    }
+    ks_fwd_pass<N>(res, t, 7);
+    /* d. quantise: t[v] = coefficient (v, u=r) */
+    const int qbits = 21 + qp / 6 - LOG2, scale = c_quant_scales[qp % 6];
+    const int add = (intra_slice ? 171 : 85) << (qbits - 9);
+    bool nz = false;
+#pragma unroll
+    for (int v = 0; v < N; v++) {
+        int c = (int)(short)t[v], a = abs(c), m = a * scale, lv = (m + add) >> qbits;
+        int du = (m - (lv << qbits)) >> (qbits - 8);
+        lv = min(lv, 32767);
+        nz |= lv != 0;
+        C[v * N + r] = (int16_t)c; L[v * N + r] = (int16_t)(c < 0 ? -lv : lv); D[v * N + r] = (int16_t)du;
+    }
+    unsigned nzb = __ballot_sync(0xffffffffu, nz && valid);
+    bool cbf = (nzb & gmask) != 0;
+    /* e. sign-data hiding, one coefficient group per lane (uniform ballots first, then the per-CG pass) */
+    if (sign_hiding && nzb) {
+        constexpr int NCG = (N / 4) * (N / 4);
+        constexpr int REPS = (G * NCG + 31) / 32;
+        unsigned ball[REPS];
+#pragma unroll
+        for (int rep = 0; rep < REPS; rep++) {
+            int id = lane + 32 * rep, tb = id / NCG, cg = id % NCG;
+            bool cgnz = false;
+            if (id < G * NCG) {
+                const int16_t *Lt = sc->L + tb * N * N;
+#pragma unroll
+                for (int i = 0; i < 16; i++) { int s = scan[cg * 16 + i]; cgnz |= Lt[(s >> 8) * N + (s & 255)] != 0; }
+            }
+            ball[rep] = __ballot_sync(0xffffffffu, cgnz);
+        }
+#pragma unroll
+        for (int rep = 0; rep < REPS; rep++) {
+            int id = lane + 32 * rep, tb = id / NCG, cg = id % NCG;
+            if (id < G * NCG && ((ball[rep] >> lane) & 1)) {
+                unsigned long long m;
+                if (REPS == 2) m = ((unsigned long long)ball[1] << 32) | ball[0];
+                else m = ball[0];
+                constexpr unsigned long long TBMASK = NCG == 64 ? ~0ull : ((1ull << (NCG & 63)) - 1ull);
+                unsigned long long tbm = (m >> ((tb * NCG) & 63)) & TBMASK;
+                int top = 63 - __clzll((long long)tbm);
+                ks_sbh_cg<N>(sc->C + tb * N * N, sc->L + tb * N * N, sc->D + tb * N * N, scan, cg * 16, cg == top);
+            }
+        }
+    }
+    __syncwarp();
+    /* f. store the level row (dense plane) */
+    if (valid) {
+#pragma unroll
+        for (int x = 0; x < N; x += 8) *reinterpret_cast<uint4 *>(lev_row + x) = *reinterpret_cast<const uint4 *>(&L[r * N + x]);
+    }
+    /* g. reconstruction */
+    if (nzb) {
+        const int shift = LOG2 - 1, dq = c_inv_quant_scales[qp % 6] << (qp / 6), rnd = 1 << (shift - 1);
+#pragma unroll
+        for (int k = 0; k < N; k++) res[k] = ks_clip3(-32768, 32767, ((int)L[k * N + r] * dq + rnd) >> shift);   /* column x = r */
+        ks_inv_pass<N>(res, t, 7, true);
+        __syncwarp();
+#pragma unroll
+        for (int y = 0; y < N; y++) S[y * SP + r] = (int16_t)t[y];
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < N; k += 8) {
+            uint4 q = *reinterpret_cast<const uint4 *>(&S[r * SP + k]);
+            uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) { res[k + 2 * j] = (int)(short)(w[j] & 0xffffu); res[k + 2 * j + 1] = (int)w[j] >> 16; }
+        }
+        ks_inv_pass<N>(res, t, 12, false);
+#pragma unroll
+        for (int x = 0; x < N; x++) pred[x] = (uint8_t)ks_clip8((int)pred[x] + t[x]);
+    }
+    if (valid) {
+#pragma unroll
+        for (int x = 0; x < N; x += 4)
+            *reinterpret_cast<uint32_t *>(rec_row + x) = (uint32_t)pred[x] | ((uint32_t)pred[x + 1] << 8) | ((uint32_t)pred[x + 2] << 16) | ((uint32_t)pred[x + 3] << 24);
+    }
+    __syncwarp();
+    return cbf;
+}
+
+/* ------------------------------------------------------------------ chroma motion compensation --- */
+/* 8x8 chroma block, 4-tap filters, eighth-sample mv (spec 8.5.3.3.3.2 == ora_mc_chroma).  Warp-collective.
+ * cwin: 12x12 byte window (rows/cols -1..+10 of the integer position), tmp: >= 11x8 int16. */
+__device__ __forceinline__ void ks_mc_chroma8(uint8_t *cwin, int16_t *tmp, const uint8_t *__restrict__ ref, int PW, int PH,
+                                              int xc, int yc, int mvx, int mvy, uint8_t *dst, int dpitch, int lane)
+{
+    const int ix = xc + (mvx >> 3) - 1, iy = yc + (mvy >> 3) - 1, fx = mvx & 7, fy = mvy & 7;
+    for (int idx = lane; idx < 144; idx += KS_WARP) {
+        int r = idx / 12, c = idx - r * 12;
+        cwin[idx] = ref[(size_t)min(max(iy + r, 0), PH - 1) * PW + min(max(ix + c, 0), PW - 1)];
+    }
+    __syncwarp();
+    const int row = lane >> 2, col = (lane & 3) * 2;
+    int v0, v1;
+    if (fx == 0 && fy == 0) { v0 = cwin[(row + 1) * 12 + col + 1]; v1 = cwin[(row + 1) * 12 + col + 2]; }
+    else if (fy == 0) {
+        const uint8_t *p = cwin + (row + 1) * 12 + col;
+        int a = 0, b = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) { int c = c_chroma_taps[fx][t]; a += c * p[t]; b += c * p[t + 1]; }
+        v0 = ks_clip8((a + 32) >> 6); v1 = ks_clip8((b + 32) >> 6);
+    } else if (fx == 0) {
+        const uint8_t *p = cwin + row * 12 + col + 1;
+        int a = 0, b = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) { int c = c_chroma_taps[fy][t]; a += c * p[t * 12]; b += c * p[t * 12 + 1]; }
+        v0 = ks_clip8((a + 32) >> 6); v1 = ks_clip8((b + 32) >> 6);
+    } else {
+        for (int idx = lane; idx < 88; idx += KS_WARP) {      /* raw horizontal sums, rows -1..+9 */
+            int r = idx >> 3, c = idx & 7;
+            const uint8_t *p = cwin + r * 12 + c;
+            int a = 0;
+#pragma unroll
+            for (int t = 0; t < 4; t++) a += c_chroma_taps[fx][t] * p[t];
+            tmp[idx] = (int16_t)a;
+        }
+        __syncwarp();
+        int a = 0, b = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) { int c = c_chroma_taps[fy][t]; a += c * tmp[(row + t) * 8 + col]; b += c * tmp[(row + t) * 8 + col + 1]; }
+        v0 = ks_clip8((a + 2048) >> 12); v1 = ks_clip8((b + 2048) >> 12);
+    }
+    dst[row * dpitch + col] = (uint8_t)v0; dst[row * dpitch + col + 1] = (uint8_t)v1;
+    __syncwarp();
+}
+
+/* ------------------------------------------------------------------ inter picture: one CTA per CTU - */
+#define KS_RECON_WARPS 8
+struct KsReconSmem {
+    union { KsWarpScratch mc[KS_RECON_WARPS]; KsTbScratch tb[KS_RECON_WARPS]; } u;
+    uint16_t scan[64 + 256 + 1024];            /* scan tables for 8x8, 16x16, 32x32 */
+    uint8_t  predY[64 * 64];
+    uint8_t  predC[2][32 * 32];
+    uint8_t  cwin[KS_RECON_WARPS][144];
+    int16_t  mvx[16], mvy[16];
+    uint8_t  valid[16], culog2[16];
+    unsigned cbf[16];                          /* KS_F_CBF_* bits per cell, OR-ed by the transform tasks */
+    uint8_t  task_n[16], task_q[16], task_sub[16];
+    int      ntasks;
+};
+__device__ __forceinline__ const uint16_t *ks_scan_ptr(const KsReconSmem *sm, int n) { return sm->scan + (n == 8 ? 0 : (n == 16 ? 64 : 320)); }
+__device__ __forceinline__ void ks_load_scans(uint16_t *scan, int tid, int nthreads)
+{
+    for (int i = tid; i < 64 + 256 + 1024; i += nthreads) scan[i] = i < 64 ? c_scan_tb[1][i] : (i < 320 ? c_scan_tb[2][i - 64] : c_scan_tb[3][i - 320]);
+}
+
+__global__ void __launch_bounds__(KS_RECON_WARPS * KS_WARP)
+ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes ref, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    KsReconSmem *sm = reinterpret_cast<KsReconSmem *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ctx = blockIdx.x, cty = blockIdx.y, X0 = ctx << 6, Y0 = cty << 6;
+    const int W = pp.W, H = pp.H, CW = W >> 1, CH = H >> 1;
+    ks_load_scans(sm->scan, tid, blockDim.x);
+    if (tid < 16) {
+        int cx = tid & 3, cy = tid >> 2, x = X0 + (cx << 4), y = Y0 + (cy << 4);
+        bool v = x < W && y < H;
+        sm->valid[tid] = v; sm->cbf[tid] = 0;
+        if (v) { ks_cell c = cells[(y >> 4) * pp.cw + (x >> 4)]; sm->mvx[tid] = c.mvx; sm->mvy[tid] = c.mvy; }
+        else { sm->mvx[tid] = 0; sm->mvy[tid] = 0; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        /* CU size: four equal-MV siblings merge upward (16 -> 32 -> 64), mirror of ora_inter_picture step 2 */
+        bool q32[4]; int nt = 0;
+        for (int q = 0; q < 4; q++) {
+            int b = (q & 1) * 2 + (q >> 1) * 8, i0 = b, i1 = b + 1, i2 = b + 4, i3 = b + 5;
+            bool ok = sm->valid[i0] && sm->valid[i1] && sm->valid[i2] && sm->valid[i3];
+            ok = ok && sm->mvx[i0] == sm->mvx[i1] && sm->mvx[i0] == sm->mvx[i2] && sm->mvx[i0] == sm->mvx[i3]
+                    && sm->mvy[i0] == sm->mvy[i1] && sm->mvy[i0] == sm->mvy[i2] && sm->mvy[i0] == sm->mvy[i3];
+            q32[q] = ok;
+            int l = ok ? 5 : 4;
+            sm->culog2[i0] = sm->culog2[i1] = sm->culog2[i2] = sm->culog2[i3] = (uint8_t)l;
+        }
+        bool c64 = q32[0] && q32[1] && q32[2] && q32[3];
+        for (int q = 1; q < 4 && c64; q++) { int b = (q & 1) * 2 + (q >> 1) * 8; c64 = sm->mvx[b] == sm->mvx[0] && sm->mvy[b] == sm->mvy[0]; }
+        if (c64) for (int i = 0; i < 16; i++) sm->culog2[i] = 6;
+        for (int q = 0; q < 4; q++) {
+            int b = (q & 1) * 2 + (q >> 1) * 8;
+            if (!sm->valid[b]) continue;
+            if (q32[q]) {
+                sm->task_n[nt] = 32; sm->task_q[nt] = (uint8_t)q; sm->task_sub[nt++] = 0;
+                sm->task_n[nt] = 16; sm->task_q[nt] = (uint8_t)q; sm->task_sub[nt++] = 2;     /* chroma 16x16 Cb+Cr */
+            } else {
+                sm->task_n[nt] = 16; sm->task_q[nt] = (uint8_t)q; sm->task_sub[nt++] = 0;     /* luma cells 0,1 */
+                sm->task_n[nt] = 16; sm->task_q[nt] = (uint8_t)q; sm->task_sub[nt++] = 1;     /* luma cells 2,3 */
+                sm->task_n[nt] = 8;  sm->task_q[nt] = (uint8_t)q; sm->task_sub[nt++] = 0;     /* Cb of 4 cells */
+                sm->task_n[nt] = 8;  sm->task_q[nt] = (uint8_t)q; sm->task_sub[nt++] = 1;     /* Cr of 4 cells */
+            }
+        }
+        sm->ntasks = nt;
+    }
+    /* ---- motion compensation of the 16 cells into shared memory ---- */
+    for (int k = warp; k < 16; k += KS_RECON_WARPS) {
+        if (!sm->valid[k]) continue;
+        const int cx = k & 3, cy = k >> 2, x0 = X0 + (cx << 4), y0 = Y0 + (cy << 4);
+        const int mvx = sm->mvx[k], mvy = sm->mvy[k];
+        KsWarpScratch *sc = &sm->u.mc[warp];
+        int wx0, wy0;
+        ks_center_window(x0, y0, mvx >> 2, mvy >> 2, wx0, wy0);
+        ks_load_window(sc->win, ref.p[0], W, H, wx0, wy0, lane);
+        uint32_t o0, o1;
+        ks_interp16(sc, x0 + (mvx >> 2) - wx0, y0 + (mvy >> 2) - wy0, mvx & 3, mvy & 3, lane, o0, o1);
+        *reinterpret_cast<uint2 *>(&sm->predY[((cy << 4) + (lane >> 1)) * 64 + (cx << 4) + 8 * (lane & 1)]) = make_uint2(o0, o1);
+        for (int ci = 0; ci < 2; ci++)
+            ks_mc_chroma8(sm->cwin[warp], &sc->tmp[0][0], ref.p[1 + ci], CW, CH, x0 >> 1, y0 >> 1, mvx, mvy,
+                          &sm->predC[ci][(cy << 3) * 32 + (cx << 3)], 32, lane);
+    }
+    __syncthreads();
+    /* ---- transform tasks ---- */
+    const int ntasks = sm->ntasks;
+    for (int t = warp; t < ntasks; t += KS_RECON_WARPS) {
+        const int n = sm->task_n[t], q = sm->task_q[t], sub = sm->task_sub[t];
+        const int qx = (q & 1) * 32, qy = (q >> 1) * 32;             /* quadrant origin inside the CTU (luma) */
+        KsTbScratch *ts = &sm->u.tb[warp];
+        if (n == 32) {
+            int r = lane, x = X0 + qx, y = Y0 + qy + r;
+            bool cbf = ks_tb_code<32>(ts, ks_scan_ptr(sm, 32), true, src.p[0] + (size_t)y * W + x, &sm->predY[(qy + r) * 64 + qx],
+                                      rec.p[0] + (size_t)y * W + x, lv.p[0] + (size_t)y * W + x, pp.qp, 0, pp.sign_hiding, lane);
+            if (lane == 0 && cbf) { int b = (q & 1) * 2 + (q >> 1) * 8; atomicOr(&sm->cbf[b], KS_F_CBF_Y); atomicOr(&sm->cbf[b + 1], KS_F_CBF_Y); atomicOr(&sm->cbf[b + 4], KS_F_CBF_Y); atomicOr(&sm->cbf[b + 5], KS_F_CBF_Y); }
+        } else if (n == 16 && sub == 2) {
+            int g = lane >> 4, r = lane & 15, x = (X0 + qx) >> 1, y = ((Y0 + qy) >> 1) + r;
+            bool cbf = ks_tb_code<16>(ts, ks_scan_ptr(sm, 16), true, src.p[1 + g] + (size_t)y * CW + x, &sm->predC[g][((qy >> 1) + r) * 32 + (qx >> 1)],
+                                      rec.p[1 + g] + (size_t)y * CW + x, lv.p[1 + g] + (size_t)y * CW + x, pp.qpc, 0, pp.sign_hiding, lane);
+            if (r == 0 && cbf) { int b = (q & 1) * 2 + (q >> 1) * 8, f = g ? KS_F_CBF_CR : KS_F_CBF_CB; atomicOr(&sm->cbf[b], f), atomicOr(&sm->cbf[b + 1], f), atomicOr(&sm->cbf[b + 4], f), atomicOr(&sm->cbf[b + 5], f); }
+        } else if (n == 16) {
+            int g = lane >> 4, r = lane & 15, kc = sub * 2 + g;               /* cell inside the quadrant */
+            int cidx = (q & 1) * 2 + (q >> 1) * 8 + (kc & 1) + (kc >> 1) * 4;
+            bool v = sm->valid[cidx];
+            int lx = qx + (kc & 1) * 16, ly = qy + (kc >> 1) * 16 + r, x = X0 + lx, y = Y0 + ly;
+            bool cbf = ks_tb_code<16>(ts, ks_scan_ptr(sm, 16), v, src.p[0] + (size_t)y * W + x, &sm->predY[ly * 64 + lx],
+                                      rec.p[0] + (size_t)y * W + x, lv.p[0] + (size_t)y * W + x, pp.qp, 0, pp.sign_hiding, lane);
+            if (r == 0 && cbf) atomicOr(&sm->cbf[cidx], KS_F_CBF_Y);
+        } else {
+            int g = lane >> 3, r = lane & 7, kc = g, ci = sub;
+            int cidx = (q & 1) * 2 + (q >> 1) * 8 + (kc & 1) + (kc >> 1) * 4;
+            bool v = sm->valid[cidx];
+            int lx = (qx >> 1) + (kc & 1) * 8, ly = (qy >> 1) + (kc >> 1) * 8 + r, x = (X0 >> 1) + lx, y = (Y0 >> 1) + ly;
+            bool cbf = ks_tb_code<8>(ts, ks_scan_ptr(sm, 8), v, src.p[1 + ci] + (size_t)y * CW + x, &sm->predC[ci][ly * 32 + lx],
+                                     rec.p[1 + ci] + (size_t)y * CW + x, lv.p[1 + ci] + (size_t)y * CW + x, pp.qpc, 0, pp.sign_hiding, lane);
+            if (r == 0 && cbf) atomicOr(&sm->cbf[cidx], ci ? KS_F_CBF_CR : KS_F_CBF_CB);
+        }
+    }
+    __syncthreads();
+    if (tid < 16 && sm->valid[tid]) {
+        int cx = tid & 3, cy = tid >> 2;
+        ks_cell c; c.mvx = sm->mvx[tid]; c.mvy = sm->mvy[tid]; c.cu_log2 = sm->culog2[tid]; c.flags = (uint8_t)sm->cbf[tid]; c.intra_mode = 0; c.rsv = 0;
+        cells[((Y0 >> 4) + cy) * pp.cw + (X0 >> 4) + cx] = c;
+    }
+}
+
+void ks_launch_recon_inter(const KsPicParams &pp, KsPlanes src, KsPlanes ref, KsPlanes rec, KsLevels lv, ks_cell *cells, cudaStream_t st)
+{
+    static bool attr_done = false;
+    if (!attr_done) { cudaFuncSetAttribute(ks_recon_inter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsReconSmem)); attr_done = true; }
+    dim3 grid(pp.ctw, pp.cth);
+    ks_recon_inter_kernel<<<grid, KS_RECON_WARPS * KS_WARP, sizeof(KsReconSmem), st>>>(pp, src, ref, rec, lv, cells);
+}
+
+/* ------------------------------------------------------------------ intra picture (wavefront) ---- */
+/* predicted sample (x,y) of an n x n block for `mode` (spec 8.4.4.2.4-.6 == ora_intra_pred); p = reference
+ * array (already filtered if the mode asks for it): p[2n-1-i] = left[i], p[2n] = corner, p[2n+1+i] = top[i] */
+__device__ __forceinline__ int ks_intra_sample(const uint8_t *p, int n, int log2n, int mode, int x, int y, int dc, bool edge)
+{
+    const int n2 = 2 * n;
+    if (mode == 0)
+        return ((n - 1 - x) * p[n2 - 1 - y] + (x + 1) * p[n2 + 1 + n] + (n - 1 - y) * p[n2 + 1 + x] + (y + 1) * p[n2 - 1 - n] + n) >> (log2n + 1);
+    if (mode == 1) {
+        if (edge) {
+            if (x == 0 && y == 0) return (p[n2 - 1] + 2 * dc + p[n2 + 1] + 2) >> 2;
+            if (y == 0) return (p[n2 + 1 + x] + 3 * dc + 2) >> 2;
+            if (x == 0) return (p[n2 - 1 - y] + 3 * dc + 2) >> 2;
+        }
+        return dc;
+    }
+    const int ang = c_intra_angle[mode], inv = c_intra_inv_angle[mode];
+    const bool vert = mode >= 18;
+    const int i = vert ? x : y, j = vert ? y : x;
+    if (ang == 0 && edge && i == 0) {
+        /* mode 26: pred[0][y] = top[0] + ((left[y]-corner)>>1); mode 10: pred[x][0] = left[0] + ((top[x]-corner)>>1) */
+        return vert ? ks_clip8(p[n2 + 1] + ((p[n2 - 1 - j] - p[n2]) >> 1)) : ks_clip8(p[n2 - 1] + ((p[n2 + 1 + j] - p[n2]) >> 1));
+    }
+    const int idx = ((j + 1) * ang) >> 5, f = ((j + 1) * ang) & 31;
+    int k0 = i + idx + 1, k1 = k0 + 1;
+    auto refv = [&](int k) -> int {
+        if (k >= 0) return vert ? p[n2 + k] : p[n2 - k];
+        int i2 = -1 + ((k * inv + 128) >> 8);
+        return vert ? p[n2 - 1 - i2] : p[n2 + 1 + i2];
+    };
+    int a = refv(k0);
+    if (!f) return a;
+    return ((32 - f) * a + f * refv(k1) + 16) >> 5;
+}
+
+struct KsIntraSmem {
+    KsTbScratch tb[2];
+    uint16_t scan[64 + 256 + 1024];
+    uint8_t  nb[3][72];          /* substituted reference samples: luma 65, chroma 33 */
+    uint8_t  fb[72];             /* [1 2 1]-filtered luma references */
+    uint8_t  av[3][72];
+    uint8_t  predY[16 * 16];
+    uint8_t  predC[2][8 * 8];
+    unsigned best_key[KS_RECON_WARPS];
+    int      dc[3];
+    int      best_mode;
+    int      row;
+    unsigned cbf;
+};
+
+__global__ void __launch_bounds__(KS_RECON_WARPS * KS_WARP)
+ks_recon_intra_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells, int *sync_ws)
+{
+    __shared__ __align__(16) KsIntraSmem sm;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int W = pp.W, H = pp.H, CW = W >> 1;
+    int *ticket = sync_ws, *progress = sync_ws + 1;
+    ks_load_scans(sm.scan, tid, blockDim.x);
+    if (tid == 0) sm.row = atomicAdd(ticket, 1);         /* rows are taken in start order: a row only ever waits on rows already running */
+    __syncthreads();
+    const int cty = sm.row;
+    if (cty >= pp.cth) return;
+    for (int ctx = 0; ctx < pp.ctw; ctx++) {
+        if (cty > 0) {
+            if (tid == 0) {
+                int need = min(ctx + 2, pp.ctw);
+                while (atomicAdd(&progress[cty - 1], 0) < need) __nanosleep(200);
+                __threadfence();
+            }
+            __syncthreads();
+        }
+        for (int z = 0; z < 16; z++) {
+            const int cx = (z & 1) | ((z >> 1) & 2), cy = ((z >> 1) & 1) | ((z >> 2) & 2);
+            const int x0 = (ctx << 6) + (cx << 4), y0 = (cty << 6) + (cy << 4);
+            if (x0 >= W || y0 >= H) continue;
+            /* 1. reference samples with availability (8.4.4.2.2); neighbours come from the pre-filter reconstruction.
+             *    __ldcg: other CTAs wrote these lines, bypass the (non-coherent) L1 */
+            for (int idx = tid; idx < 65 + 33 + 33; idx += blockDim.x) {
+                int ci = idx < 65 ? 0 : (idx < 98 ? 1 : 2), i = idx - (ci == 0 ? 0 : (ci == 1 ? 65 : 98));
+                int n = ci ? 8 : 16, sh = ci ? 1 : 0, bx = x0 >> sh, by = y0 >> sh, xn, yn;
+                if (i < 2 * n) { xn = bx - 1; yn = by + 2 * n - 1 - i; }
+                else if (i == 2 * n) { xn = bx - 1; yn = by - 1; }
+                else { xn = bx + i - 2 * n - 1; yn = by - 1; }
+                bool a = ks_avail(W, H, pp.ctw, x0, y0, xn << sh, yn << sh);
+                sm.av[ci][i] = a;
+                sm.nb[ci][i] = a ? __ldcg(rec.p[ci] + (size_t)yn * (W >> sh) + xn) : 0;
+            }
+            __syncthreads();
+            if (lane == 0 && warp < 3) {                 /* substitution: one thread per component */
+                int ci = warp, tot = ci ? 33 : 65; uint8_t *nb = sm.nb[ci]; const uint8_t *av = sm.av[ci];
+                int any = 0;
+                for (int i = 0; i < tot; i++) any |= av[i];
+                if (!any) for (int i = 0; i < tot; i++) nb[i] = 128;
+                else {
+                    if (!av[0]) { int i = 1; while (!av[i]) i++; nb[0] = nb[i]; }
+                    for (int i = 1; i < tot; i++) if (!av[i]) nb[i] = nb[i - 1];
+                }
+                int n = ci ? 8 : 16, s = n;
+                for (int i = 0; i < n; i++) s += nb[2 * n + 1 + i] + nb[2 * n - 1 - i];
+                sm.dc[ci] = s >> (ci ? 4 : 5);
+            }
+            __syncthreads();
+            if (tid < 65) sm.fb[tid] = (tid == 0 || tid == 64) ? sm.nb[0][tid] : (uint8_t)((sm.nb[0][tid - 1] + 2 * sm.nb[0][tid] + sm.nb[0][tid + 1] + 2) >> 2);
+            __syncthreads();
+            /* 2. mode decision by SAD + lambda*bits: warp w evaluates modes w, w+8, ... on all 256 samples */
+            {
+                unsigned best = 0xffffffffu;
+                const int px = lane & 15, py0 = lane >> 4;
+                uint8_t s[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) s[j] = src.p[0][(size_t)(y0 + py0 + 2 * j) * W + x0 + px];
+                for (int m = warp; m < 35; m += KS_RECON_WARPS) {
+                    int d1 = abs(m - 26), d2 = abs(m - 10);
+                    bool filt = m != 1 && min(d1, d2) > 1;            /* intraHorVerDistThres[16] = 1 */
+                    const uint8_t *p = filt ? sm.fb : sm.nb[0];
+                    unsigned sad = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) sad += abs(ks_intra_sample(p, 16, 4, m, px, py0 + 2 * j, sm.dc[0], true) - (int)s[j]);
+                    sad = ks_warp_sum(sad);
+                    int bits = (m == 0 || m == 1 || m == 10 || m == 26) ? 3 : 6;
+                    unsigned key = ((sad + ((pp.lambda_sad_q4 * bits) >> 4)) << 6) | (unsigned)m;
+                    best = min(best, key);
+                }
+                if (lane == 0) sm.best_key[warp] = best;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned b = sm.best_key[0];
+                for (int w = 1; w < KS_RECON_WARPS; w++) b = min(b, sm.best_key[w]);
+                sm.best_mode = (int)(b & 63); sm.cbf = 0;
+            }
+            __syncthreads();
+            const int mode = sm.best_mode;
+            /* 3. prediction blocks */
+            {
+                int d1 = abs(mode - 26), d2 = abs(mode - 10);
+                bool filt = mode != 1 && min(d1, d2) > 1;
+                sm.predY[tid] = (uint8_t)ks_intra_sample(filt ? sm.fb : sm.nb[0], 16, 4, mode, tid & 15, tid >> 4, sm.dc[0], true);
+                if (tid < 128) { int ci = tid >> 6, k = tid & 63; sm.predC[ci][k] = (uint8_t)ks_intra_sample(sm.nb[1 + ci], 8, 3, mode, k & 7, k >> 3, sm.dc[1 + ci], false); }
+            }
+            __syncthreads();
+            /* 4. residual coding: warp 0 luma 16x16 (lanes 0..15), warp 1 Cb+Cr 8x8 (lanes 0..15) */
+            if (warp == 0) {
+                int g = lane >> 4, r = lane & 15, y = y0 + r;
+                bool cbf = ks_tb_code<16>(&sm.tb[0], sm.scan + 64, g == 0, src.p[0] + (size_t)y * W + x0, &sm.predY[r * 16],
+                                          rec.p[0] + (size_t)y * W + x0, lv.p[0] + (size_t)y * W + x0, pp.qp, 1, pp.sign_hiding, lane);
+                if (lane == 0 && cbf) atomicOr(&sm.cbf, KS_F_CBF_Y);
+            } else if (warp == 1) {
+                int g = lane >> 3, r = lane & 7, ci = g & 1, x = x0 >> 1, y = (y0 >> 1) + r;
+                bool cbf = ks_tb_code<8>(&sm.tb[1], sm.scan, g < 2, src.p[1 + ci] + (size_t)y * CW + x, &sm.predC[ci][r * 8],
+                                         rec.p[1 + ci] + (size_t)y * CW + x, lv.p[1 + ci] + (size_t)y * CW + x, pp.qpc, 1, pp.sign_hiding, lane);
+                if (r == 0 && g < 2 && cbf) atomicOr(&sm.cbf, ci ? KS_F_CBF_CR : KS_F_CBF_CB);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                ks_cell c; c.mvx = 0; c.mvy = 0; c.cu_log2 = 4; c.flags = (uint8_t)(KS_F_INTRA | sm.cbf); c.intra_mode = (uint8_t)mode; c.rsv = 0;
+                cells[(y0 >> 4) * pp.cw + (x0 >> 4)] = c;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) { __threadfence(); atomicExch(&progress[cty], ctx + 1); }
+    }
+}
+
+void ks_launch_recon_intra(const KsPicParams &pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *cells, int *sync_ws, cudaStream_t st)
+{
+    cudaMemsetAsync(sync_ws, 0, sizeof(int) * (size_t)(1 + pp.cth), st);
+    ks_recon_intra_kernel<<<pp.cth, KS_RECON_WARPS * KS_WARP, 0, st>>>(pp, src, rec, lv, cells, sync_ws);
+}
