@@ -1,0 +1,286 @@
+#!/usr/bin/env python3
+"""bench.py -- BASELINE.json metric: 4K YUV420 encode fps @ fixed QP (-preset veryfast -rc 0 -qp 27 -iper 128).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's B200 hot path (one rank per GPU under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's own CPU encoder (oracle/_ref/appencoder)
+
+A step = every stream of the rank encodes one 128-picture GOP shard (1 IDR + 127 P) of synthetic 3840x2160 I420.
+  value : device hot path only (ME + sub-pel, MC + DCT/quant/IDCT, deblock, SAO, level packing, syntax D2H) with the
+          pictures already resident in HBM -- whole-job pictures/s over all ranks.
+  e2e   : the same GOP shards through the public encoder API with HOST buffers: H2D of every picture, the device hot
+          path, D2H of the frame syntax, host CABAC -> Annex-B bytes (and, for N>1, the NCCL gather of the NAL units).
+Timing: CUDA events after a device-wide synchronize on both sides (all streams idle), barrier before, max over ranks.
+Working set per step (streams x 128 x 12.4 MB) is far larger than the 126 MB L2: no flush needed.
+"""
+import argparse
+import json
+import os
+import re
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+W, H, QP, IPER, PRESET = 3840, 2160, 27, 128, "veryfast"
+DISTINCT = 16                      # distinct synthetic pictures; a shard plays them forward/backward (smooth motion)
+FSZ = W * H * 3 // 2
+METRIC = "4K YUV420 encode fps @ fixed QP (3840x2160 -preset veryfast -rc 0 -qp 27 -iper 128)"
+
+
+def shard_order(n=IPER, distinct=DISTINCT):
+    """ping-pong index sequence 0..d-1,d-1..0,... of length n: consecutive pictures always differ by one motion step"""
+    seq, i, d = [], 0, 1
+    for _ in range(n):
+        seq.append(i)
+        if i + d < 0 or i + d >= distinct:
+            d = -d
+        else:
+            i += d
+    return seq
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs"""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def run_reference(sample_frames, yuv_path, threads):
+    """reference encoder on host cores; returns fps from its own 'test time' line"""
+    enc = os.path.join(ROOT, "oracle", "_ref", "appencoder")
+    out = "/dev/shm/ks265_ref_%d.265" % os.getpid()
+    cmd = [enc, "-i", yuv_path, "-wdt", str(W), "-hgt", str(H), "-fr", "30", "-preset", PRESET, "-rc", "0", "-qp", str(QP),
+           "-iper", str(IPER), "-frms", str(sample_frames), "-threads", str(threads), "-b", out]
+    t0 = time.time()
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1800)
+    wall = time.time() - t0
+    if os.path.exists(out):
+        os.remove(out)
+    m = re.search(r"Total Frames:\s*(\d+),\s*test time:\s*([\d.]+)\s*ms,\s*FPS:\s*([\d.]+)", r.stdout)
+    if not m:
+        raise RuntimeError("reference encoder gave no timing line: " + r.stdout[-400:] + r.stderr[-400:])
+    return float(m.group(3)), wall
+
+
+def write_sample_yuv(frames_u8, order, n, path):
+    with open(path, "wb") as f:
+        for i in order[:n]:
+            f.write(frames_u8[i].tobytes())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=0, help="concurrent GOP shards per GPU (0 = auto)")
+    ap.add_argument("--cpu-sample-frames", type=int, default=32)
+    a = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+
+    import numpy as np
+    import gen_yuv
+    order = shard_order()
+
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        frames = [np.frombuffer(fr, np.uint8) for fr in gen_yuv.frames(W, H, DISTINCT, seed=1234)]
+        path = "/dev/shm/ks265_bench_%d.yuv" % os.getpid()
+        n = a.cpu_sample_frames
+        write_sample_yuv(frames, order, n, path)
+        try:
+            vals = []
+            for i in range(a.warmup + a.steps):
+                fps, wall = run_reference(n, path, 0)
+                if i >= a.warmup:
+                    vals.append((fps, wall))
+        finally:
+            os.remove(path)
+        fps = sum(v[0] for v in vals) / len(vals)
+        ms = 1000.0 * sum(v[1] for v in vals) / len(vals)
+        sample = "%d pictures of the same synthetic 4K sequence per step, centos_x64/appencoder -threads 0 (all host cores), fps from its own 'test time' line" % n
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                          "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                          "config": {"workload": "3840x2160 I420 -preset veryfast -rc 0 -qp 27 -iper 128", "sample_frames": n},
+                          "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": sample},
+                          "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import ks265codec_b200 as ks
+    from ks265codec_b200 import shard as ksh
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    streams = a.streams or max(2, min(12, (cores // max(1, a.gpus)) - 1))
+
+    # ---- synthetic input: DISTINCT pictures, shard = 128-picture ping-pong sequence; device copy + pinned host copy ----
+    frames = [np.frombuffer(fr, np.uint8) for fr in gen_yuv.frames(W, H, DISTINCT, seed=1234)]
+    host_seq = torch.empty(IPER * FSZ, dtype=torch.uint8).pin_memory()
+    hv = host_seq.numpy()
+    for k, i in enumerate(order):
+        hv[k * FSZ:(k + 1) * FSZ] = frames[i]
+    dev_seq = host_seq.cuda(non_blocking=False)
+    cfg = ks.default_config(W, H, preset=PRESET, qp=QP, iper=IPER, device=local_rank, psnr=0)
+    encs = [ks.Encoder(cfg) for _ in range(streams)]
+    outs = [np.empty(96 << 20, np.uint8) for _ in range(streams)]      # Annex-B output buffers (a 4K GOP is a few MB)
+    results = [None] * streams
+
+    def step_device():
+        def work(i):
+            results[i] = encs[i].run_gop_device(dev_seq.data_ptr(), IPER)
+        th = [threading.Thread(target=work, args=(i,)) for i in range(streams)]
+        [t.start() for t in th]; [t.join() for t in th]
+
+    def step_e2e():
+        def work(i):
+            results[i] = encs[i].encode_gop(hv, want_recon=False, nframes=IPER, out=outs[i])
+        th = [threading.Thread(target=work, args=(i,)) for i in range(streams)]
+        [t.start() for t in th]; [t.join() for t in th]
+        if world > 1:       # the only exchange of the job: NAL units of every shard to rank 0 over NCCL
+            local = {rank + world * i: results[i][0] for i in range(streams)}
+            ksh.gather_bitstreams(local, world * streams)
+
+    def timed(fn, steps, warmup, sampler=None):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        e1.record(); e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        clk = sampler.stop() if sampler else None
+        if world > 1:
+            t = torch.tensor([ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        return ms, clk
+
+    # ---- value: device hot path, inputs resident in HBM ----
+    for e in encs:
+        e.set_profiling(True)
+    ms_dev, clocks = timed(step_device, a.steps, a.warmup, ClockSampler(local_rank) if rank == 0 else None)
+    launches = sum(int(r.gpu_launches) for r in results) * a.steps      # every step issues the same launches
+    stage = {}
+    for e in encs:
+        for k, (ms, n) in e.stage_times().items():
+            t = stage.setdefault(k, [0.0, 0]); t[0] += ms; t[1] += n
+        e.set_profiling(False)
+    frames_per_step = streams * IPER * world
+    value = frames_per_step * a.steps / (ms_dev / 1000.0)
+
+    # ---- e2e: host buffers -> Annex-B bytes through the public API ----
+    ms_e2e, _ = timed(step_e2e, a.steps, max(1, min(a.warmup, 1)))
+    e2e = frames_per_step * a.steps / (ms_e2e / 1000.0)
+    h2d = sum(int(r[2].h2d_bytes) for r in results)
+    d2h = sum(int(r[2].d2h_bytes) for r in results)
+    bs_bytes = sum(int(r[2].bytes) for r in results)
+
+    # ---- roofline of the dominant stage (SURVEY.md 8d per-kernel algorithmic bytes; S = 1.5*W*H per picture) ----
+    S = 1.5 * W * H
+    alg = {"me": 2.0 * W * H + 8.0 * W * H / 256, "recon_inter": 5.0 * S + 8.0 * W * H / 256, "recon_intra": 4.0 * S,
+           "deblock": 2.0 * W * H, "sao": 3.0 * S, "pack": 2.0 * S + 0.1 * S}
+    dom = max((k for k in stage if stage[k][1] > 0), key=lambda k: stage[k][0])
+    # the dominant stage timed ALONE (one stream, nothing else on the GPU): that is the launch duration the roofline uses
+    solo = encs[0]
+    solo.set_profiling(True)
+    torch.cuda.synchronize()
+    solo.run_gop_device(dev_seq.data_ptr(), 24)
+    torch.cuda.synchronize()
+    solo_t = solo.stage_times()
+    solo.set_profiling(False)
+    avg_ms = solo_t[dom][0] / max(1, solo_t[dom][1])
+    peak, peak_src = peaks()
+    achieved = alg[dom] / (avg_ms / 1000.0) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg[dom],
+                "stage_ms_share": {k: v[0] / max(1e-9, sum(x[0] for x in stage.values())) for k, v in stage.items()},
+                "solo_stage_ms": {k: (v[0] / v[1] if v[1] else None) for k, v in solo_t.items()},
+                "note": "dominant stage = largest share of the timed region (CUDA-event intervals on each encoder stream, %d streams sharing the GPU); avg_launch_ms = the same stage timed alone on an idle GPU (24 pictures, one stream), peak = burst copy bandwidth" % streams}
+
+    # ---- cpu baseline (rank 0, N=1 only): the reference encoder on a bounded sample ----
+    cpu = None
+    if rank == 0 and world == 1:
+        path = "/dev/shm/ks265_bench_%d.yuv" % os.getpid()
+        n = a.cpu_sample_frames
+        try:
+            write_sample_yuv(frames, order, n, path)
+            fps, wall = run_reference(n, path, 0)
+            cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference",
+                   "sample": "%d pictures of the same synthetic 4K sequence, oracle/_ref/appencoder (centos_x64) -threads 0, fps from its 'test time' line (wall %.1f s)" % (n, wall)}
+        except Exception as ex:          # the baseline is reported, never required for the GPU numbers
+            cpu = {"value": None, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": "failed: %s" % str(ex)[:200]}
+        finally:
+            if os.path.exists(path):
+                os.remove(path)
+    for e in encs:
+        e.close()
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "3840x2160 I420 -preset veryfast -rc 0 -qp 27 -iper 128 (BASELINE configs[2])", "gop_shard": "1 IDR + 127 P, closed GOP",
+                       "streams_per_gpu": streams, "pictures_per_step": frames_per_step, "parallelism": "gop-shard x%d" % world,
+                       "l2": "inputs larger than L2 (%.1f GB of pictures per step per GPU)" % (streams * IPER * FSZ / 1e9),
+                       "value_scope": "device hot path (ME, MC+transform+quant, deblock, SAO, level pack, syntax D2H), pictures resident in HBM; host CABAC excluded",
+                       "e2e_scope": "host I420 -> H2D -> device hot path -> syntax D2H -> host CABAC -> Annex-B (+NCCL NAL gather if N>1)"},
+            "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e / a.steps,
+                    "bitstream_bytes_per_step": bs_bytes * world},
+            "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -35,6 +35,8 @@ typedef struct ks265_gop_stats {
     uint64_t sse[3];            /* summed over the shard (coded area) */
     uint64_t bytes;
     uint64_t gpu_launches;
+    uint64_t d2h_bytes;         /* syntax bytes copied device->host */
+    uint64_t h2d_bytes;         /* picture bytes copied host->device */
 } ks265_gop_stats;
 
 typedef struct ks265_encoder ks265_encoder;
@@ -49,6 +51,9 @@ void ks265_encoder_close(ks265_encoder *enc);
  * Returns bytes written or a negative error. */
 long ks265_encoder_encode_gop(ks265_encoder *enc, const uint8_t *frames, const void *frames_dev, int nframes,
                               uint8_t *bs, size_t bs_cap, uint8_t *recon, ks265_gop_stats *stats);
+/* per-stage device times accumulated since `on` (see ks_gpu_get_stage_times) */
+int  ks265_encoder_set_profiling(ks265_encoder *enc, int on);
+int  ks265_encoder_get_stage_times(ks265_encoder *enc, double ms[6], uint64_t launches[6]);
 /* device-only variant for measurement: runs the device pipeline of a GOP without entropy coding */
 long ks265_encoder_run_gop_device(ks265_encoder *enc, const void *frames_dev, int nframes, ks265_gop_stats *stats);
 

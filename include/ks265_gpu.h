@@ -82,6 +82,13 @@ uint64_t ks_gpu_launch_count(const ks_gpu_ctx *ctx);
 /* raw CUDA stream of the context (cudaStream_t) so callers can time with events on the launching stream */
 void *ks_gpu_stream(ks_gpu_ctx *ctx);
 
+/* per-stage device timing (CUDA events on the context's stream, accumulated at finish): stage order
+ * 0 motion search, 1 inter prediction+residual, 2 intra picture, 3 deblock, 4 SAO, 5 level packing */
+int  ks_gpu_set_profiling(ks_gpu_ctx *ctx, int on);
+int  ks_gpu_get_stage_times(const ks_gpu_ctx *ctx, double ms[6], uint64_t launches[6]);
+/* bytes copied device->host so far (syntax blocks) */
+uint64_t ks_gpu_d2h_bytes(const ks_gpu_ctx *ctx);
+
 /* ---- stage-level debug/test access (tests compare every stage with the oracle) ---- */
 enum { KS_DBG_PRE_RECON = 0, KS_DBG_LEVELS = 1, KS_DBG_SRC = 2 };
 /* copies coded-size planes (Y, U, V back to back; levels as int16) of the LAST submitted picture to `dst` */

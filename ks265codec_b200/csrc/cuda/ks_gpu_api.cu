@@ -15,10 +15,12 @@ static const int k_lambda_sad_q4[52] = {4,4,5,5,6,7,7,8,9,10,12,13,15,17,19,21,2
 static const int k_lambda_sse_q4[52] = {1,1,1,2,2,3,3,4,5,7,9,11,14,17,22,27,34,43,54,69,86,109,137,173,218,274,345,435,548,691,870,1097,1382,1741,2193,2763,3482,4387,5527,6963,8773,11053,13926,17546,22107,27853,35092,44214,55706,70185,88427,111411};
 static const uint8_t k_chroma_qp[58] = {0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,25,26,27,28,29,29,30,31,32,33,33,34,34,35,35,36,36,37,37,38,39,40,41,42,43,44,45,46,47,48,49,50,51};
 
+#define KS_NSTAGE 6   /* me, recon_inter, recon_intra, deblock, sao, pack */
 struct ks_syn_slot {
     ks_cell *d_cells; ks_ctu_syn *d_ctus; int16_t *d_pool; uint32_t *d_ncg; unsigned long long *d_sse;
     ks_cell *h_cells; ks_ctu_syn *h_ctus; int16_t *h_pool; uint32_t *h_ncg; unsigned long long *h_sse;
     cudaEvent_t done; int pending;
+    cudaEvent_t ev[KS_NSTAGE + 1]; int stage_of[KS_NSTAGE + 1]; int nev; size_t d2h_bytes;
 };
 struct ks_gpu_ctx {
     int device, dw, dh, W, H, cw, ch, ctw, cth;
@@ -35,6 +37,7 @@ struct ks_gpu_ctx {
     cudaEvent_t ev_stage[2]; int stage_idx;
     ks_syn_slot *syn;
     uint64_t launches;
+    int profiling; double stage_ms[KS_NSTAGE]; uint64_t stage_n[KS_NSTAGE]; uint64_t d2h_total;
 };
 
 static KsPlanes planes_of(const ks_gpu_ctx *c, uint8_t *base) { KsPlanes p; p.p[0] = base; p.p[1] = base + (size_t)c->W * c->H; p.p[2] = p.p[1] + (size_t)c->W * c->H / 4; return p; }
@@ -97,6 +100,7 @@ extern "C" ks_gpu_ctx *ks_gpu_open(int device, int width, int height, const ks_g
             ok = ok && cudaHostAlloc(&s->h_ncg, sizeof(uint32_t), cudaHostAllocDefault) == cudaSuccess;
             ok = ok && cudaHostAlloc(&s->h_sse, 3 * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
             ok = ok && cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming) == cudaSuccess;
+            for (int k = 0; k <= KS_NSTAGE; k++) ok = ok && cudaEventCreate(&s->ev[k]) == cudaSuccess;
             if (ok) cudaMemset(s->d_ctus, 0, nctu * sizeof(ks_ctu_syn));
         }
         if (!ok) { e = KS_ENOMEM; fprintf(stderr, "ks265gpu: allocation failed: %s\n", cudaGetErrorString(cudaGetLastError())); goto fail; }
@@ -123,6 +127,7 @@ extern "C" void ks_gpu_close(ks_gpu_ctx *c)
         if (s->h_cells) cudaFreeHost(s->h_cells); if (s->h_ctus) cudaFreeHost(s->h_ctus); if (s->h_pool) cudaFreeHost(s->h_pool);
         if (s->h_ncg) cudaFreeHost(s->h_ncg); if (s->h_sse) cudaFreeHost(s->h_sse);
         if (s->done) cudaEventDestroy(s->done);
+        for (int k = 0; k <= KS_NSTAGE; k++) if (s->ev[k]) cudaEventDestroy(s->ev[k]);
     }
     if (c->st) cudaStreamDestroy(c->st);
     free(c->d_src); free(c->d_rec); free(c->syn); free(c);
@@ -131,6 +136,20 @@ extern "C" void ks_gpu_close(ks_gpu_ctx *c)
 extern "C" int ks_gpu_coded_size(const ks_gpu_ctx *c, int *w, int *h) { if (!c) return KS_EINVAL; if (w) *w = c->W; if (h) *h = c->H; return 0; }
 extern "C" uint64_t ks_gpu_launch_count(const ks_gpu_ctx *c) { return c ? c->launches : 0; }
 extern "C" void *ks_gpu_stream(ks_gpu_ctx *c) { return c ? (void *)c->st : NULL; }
+extern "C" int ks_gpu_set_profiling(ks_gpu_ctx *c, int on)
+{
+    if (!c) return KS_EINVAL;
+    c->profiling = on != 0;
+    for (int k = 0; k < KS_NSTAGE; k++) { c->stage_ms[k] = 0; c->stage_n[k] = 0; }
+    return 0;
+}
+extern "C" int ks_gpu_get_stage_times(const ks_gpu_ctx *c, double ms[6], uint64_t n[6])
+{
+    if (!c) return KS_EINVAL;
+    for (int k = 0; k < KS_NSTAGE; k++) { ms[k] = c->stage_ms[k]; n[k] = c->stage_n[k]; }
+    return 0;
+}
+extern "C" uint64_t ks_gpu_d2h_bytes(const ks_gpu_ctx *c) { return c ? c->d2h_total : 0; }
 
 static int extend_into_slot(ks_gpu_ctx *c, const uint8_t *dev_i420, int slot)
 {
@@ -190,18 +209,28 @@ extern "C" int ks_gpu_encode_picture_submit(ks_gpu_ctx *c, const ks_pic_params *
     if (s->pending) return KS_EINVAL;
     KsPlanes src = planes_of(c, c->d_src[p->src_slot]), pre = planes_of(c, c->d_pre), out = planes_of(c, c->d_rec[p->out_slot]);
     KsLevels lv; lv.p[0] = c->d_lev; lv.p[1] = c->d_lev + (size_t)c->W * c->H; lv.p[2] = lv.p[1] + (size_t)c->W * c->H / 4;
+    s->nev = 0;
+#define MARK(stage) do { if (c->profiling) { cudaEventRecord(s->ev[s->nev], c->st); s->stage_of[s->nev++] = (stage); } } while (0)
     if (p->slice_type == KS_SLICE_I) {
+        MARK(2);
         ks_launch_recon_intra(pp, src, pre, lv, s->d_cells, c->d_sync, c->st); c->launches += KS_LAUNCHES_RECON;
     } else {
         KsPlanes ref = planes_of(c, c->d_rec[p->ref_slot]);
         const ks_cell *prev = p->prev_syn_slot >= 0 ? c->syn[p->prev_syn_slot].d_cells : NULL;
+        MARK(0);
         ks_launch_me(pp, src.p[0], ref.p[0], prev, s->d_cells, c->st); c->launches += KS_LAUNCHES_ME;
+        MARK(1);
         ks_launch_recon_inter(pp, src, ref, pre, lv, s->d_cells, c->st); c->launches += KS_LAUNCHES_RECON;
     }
+    MARK(3);
     ks_launch_deblock(pp, pre, s->d_cells, c->st); c->launches += KS_LAUNCHES_DEBLOCK;
     if (p->want_sse) CK(cudaMemsetAsync(s->d_sse, 0, 3 * sizeof(unsigned long long), c->st));
+    MARK(4);
     ks_launch_sao(pp, src, pre, out, s->d_ctus, p->want_sse ? s->d_sse : NULL, c->st); c->launches += KS_LAUNCHES_SAO - 1;
+    MARK(5);
     ks_launch_pack(pp, lv, s->d_ctus, s->d_pool, s->d_ncg, c->d_counts, c->st); c->launches += KS_LAUNCHES_PACK;
+    MARK(-1);
+#undef MARK
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(s->h_cells, s->d_cells, (size_t)c->cw * c->ch * sizeof(ks_cell), cudaMemcpyDeviceToHost, c->st));
     CK(cudaMemcpyAsync(s->h_ctus, s->d_ctus, (size_t)c->ctw * c->cth * sizeof(ks_ctu_syn), cudaMemcpyDeviceToHost, c->st));
@@ -228,6 +257,12 @@ extern "C" int ks_gpu_encode_picture_finish(ks_gpu_ctx *c, int syn_slot, ks_pic_
         CK(cudaEventRecord(s->done, c->st));
         CK(cudaEventSynchronize(s->done));
     }
+    if (c->profiling)
+        for (int k = 0; k + 1 < s->nev; k++) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, s->ev[k], s->ev[k + 1]) == cudaSuccess) { c->stage_ms[s->stage_of[k]] += ms; c->stage_n[s->stage_of[k]]++; }
+        }
+    c->d2h_total += (size_t)c->cw * c->ch * sizeof(ks_cell) + (size_t)c->ctw * c->cth * sizeof(ks_ctu_syn) + 4 + (size_t)n * 32;
     s->pending = 0;
     out->cells = s->h_cells; out->ctus = s->h_ctus; out->levels = s->h_pool; out->n_cg = n;
     out->sse[0] = s->h_sse[0]; out->sse[1] = s->h_sse[1]; out->sse[2] = s->h_sse[2];

@@ -97,7 +97,7 @@ long ks265_encoder_encode_gop(ks265_encoder *enc, const uint8_t *frames, const v
     size_t fsz = (size_t)enc->cfg.width * enc->cfg.height * 3 / 2;
     int w = enc->cfg.width, h = enc->cfg.height, r;
     long pos = 0, n;
-    uint64_t l0 = ks_gpu_launch_count(enc->gpu);
+    uint64_t l0 = ks_gpu_launch_count(enc->gpu), d0 = ks_gpu_d2h_bytes(enc->gpu);
     if (stats) memset(stats, 0, sizeof(*stats));
     if ((n = ks_write_vps(sp, bs + pos, cap - pos)) < 0) return -28; pos += n;
     if ((n = ks_write_sps(sp, bs + pos, cap - pos)) < 0) return -28; pos += n;
@@ -134,7 +134,8 @@ long ks265_encoder_encode_gop(ks265_encoder *enc, const uint8_t *frames, const v
         pos += n;
         if (stats) { stats->sse[0] += out.sse[0]; stats->sse[1] += out.sse[1]; stats->sse[2] += out.sse[2]; }
     }
-    if (stats) { stats->frames = nframes; stats->bytes = (uint64_t)pos; stats->gpu_launches = ks_gpu_launch_count(enc->gpu) - l0; }
+    if (stats) { stats->frames = nframes; stats->bytes = (uint64_t)pos; stats->gpu_launches = ks_gpu_launch_count(enc->gpu) - l0;
+                 stats->d2h_bytes = ks_gpu_d2h_bytes(enc->gpu) - d0; stats->h2d_bytes = frames_dev ? 0 : (uint64_t)fsz * nframes; }
     return pos;
 }
 
@@ -142,7 +143,7 @@ long ks265_encoder_run_gop_device(ks265_encoder *enc, const void *frames_dev, in
 {
     if (!enc || !frames_dev || nframes < 1) return -22;
     int r;
-    uint64_t l0 = ks_gpu_launch_count(enc->gpu);
+    uint64_t l0 = ks_gpu_launch_count(enc->gpu), d0 = ks_gpu_d2h_bytes(enc->gpu);
     ks_pic_params pp;
     ks_pic_out out;
     uint64_t cg = 0;
@@ -154,6 +155,9 @@ long ks265_encoder_run_gop_device(ks265_encoder *enc, const void *frames_dev, in
     }
     if ((r = ks_gpu_encode_picture_finish(enc->gpu, (nframes - 1) & 1, &out))) return r;
     cg += out.n_cg;
-    if (stats) { memset(stats, 0, sizeof(*stats)); stats->frames = nframes; stats->bytes = cg * 32; stats->gpu_launches = ks_gpu_launch_count(enc->gpu) - l0; }
+    if (stats) { memset(stats, 0, sizeof(*stats)); stats->frames = nframes; stats->bytes = cg * 32; stats->gpu_launches = ks_gpu_launch_count(enc->gpu) - l0; stats->d2h_bytes = ks_gpu_d2h_bytes(enc->gpu) - d0; }
     return (long)nframes;
 }
+
+int ks265_encoder_set_profiling(ks265_encoder *enc, int on) { return enc ? ks_gpu_set_profiling(enc->gpu, on) : -22; }
+int ks265_encoder_get_stage_times(ks265_encoder *enc, double ms[6], uint64_t launches[6]) { return enc ? ks_gpu_get_stage_times(enc->gpu, ms, launches) : -22; }
