@@ -99,6 +99,8 @@ int  ks_gpu_debug_me(ks_gpu_ctx *ctx, const ks_pic_params *pp, ks_cell *cells_ou
 /* ---- known-answer entry points: the reference's leaf signatures replayed on the device ---- */
 /* sad_c E@0x473db0 (a,b,strideA,strideB,h,w), w,h in {16} -- the ME kernel's VABSDIFF4 + shuffle path */
 int  ks_gpu_kat_sad16(const uint8_t *a, const uint8_t *b, long stride_a, long stride_b, uint32_t *out);
+/* had_c E@0x474500 (SATD, 8x8 Hadamard tiles) on a 16x16 block -- register butterflies + shuffle stages */
+int  ks_gpu_kat_satd16(const uint8_t *a, const uint8_t *b, long stride_a, long stride_b, uint32_t *out);
 /* interpLuma{Hor,Ver}8to8 / Hor8to16+Ver16to8 composition for a 16x16 block at quarter-sample (fx,fy);
  * `ref` points at integer sample (0,0) of a plane of size w x h (coordinates clamp at the borders) */
 int  ks_gpu_kat_interp_luma16(const uint8_t *ref_plane, int w, int h, int x, int y, int mvx, int mvy, uint8_t *dst16x16);

@@ -163,22 +163,38 @@ extern "C" int ks_gpu_upload_frame(ks_gpu_ctx *c, int slot, const uint8_t *y, co
 {
     if (!c || slot < 0 || slot >= c->cfg.n_src_slots || !y || !u || !v) return KS_EINVAL;
     CK(cudaSetDevice(c->device));
-    const int si = c->stage_idx; c->stage_idx ^= 1;
-    CK(cudaEventSynchronize(c->ev_stage[si]));  /* this pinned staging buffer's previous H2D must be done */
-    uint8_t *d = c->h_stage[si];
-    for (int r = 0; r < c->dh; r++) memcpy(d + (size_t)r * c->dw, y + (size_t)r * sy, c->dw);
-    d += (size_t)c->dw * c->dh;
-    for (int r = 0; r < c->dh / 2; r++) memcpy(d + (size_t)r * (c->dw / 2), u + (size_t)r * suv, c->dw / 2);
-    d += (size_t)c->dw * c->dh / 4;
-    for (int r = 0; r < c->dh / 2; r++) memcpy(d + (size_t)r * (c->dw / 2), v + (size_t)r * suv, c->dw / 2);
-    CK(cudaMemcpyAsync(c->d_stage, c->h_stage[si], (size_t)c->dw * c->dh * 3 / 2, cudaMemcpyHostToDevice, c->st));
-    CK(cudaEventRecord(c->ev_stage[si], c->st));
-    return extend_into_slot(c, c->d_stage, slot);
+    const size_t dsz = (size_t)c->dw * c->dh * 3 / 2;
+    const bool tight = sy == c->dw && suv == c->dw / 2 && u == y + (size_t)c->dw * c->dh && v == u + (size_t)c->dw * c->dh / 4;
+    const bool same = c->dw == c->W && c->dh == c->H;
+    uint8_t *dst = same ? c->d_src[slot] : c->d_stage;          /* no padding needed: land directly in the slot */
+    cudaPointerAttributes at;
+    if (tight && cudaPointerGetAttributes(&at, y) == cudaSuccess && at.type == cudaMemoryTypeHost) {
+        /* caller's buffer is page-locked: DMA straight out of it (caller keeps it alive until the picture is finished,
+         * the same ownership rule as QY265Picture, qy265enc.h:153-157) */
+        CK(cudaMemcpyAsync(dst, y, dsz, cudaMemcpyHostToDevice, c->st));
+    } else {
+        (void)cudaGetLastError();
+        const int si = c->stage_idx; c->stage_idx ^= 1;
+        CK(cudaEventSynchronize(c->ev_stage[si]));  /* this pinned staging buffer's previous H2D must be done */
+        uint8_t *d = c->h_stage[si];
+        for (int r = 0; r < c->dh; r++) memcpy(d + (size_t)r * c->dw, y + (size_t)r * sy, c->dw);
+        d += (size_t)c->dw * c->dh;
+        for (int r = 0; r < c->dh / 2; r++) memcpy(d + (size_t)r * (c->dw / 2), u + (size_t)r * suv, c->dw / 2);
+        d += (size_t)c->dw * c->dh / 4;
+        for (int r = 0; r < c->dh / 2; r++) memcpy(d + (size_t)r * (c->dw / 2), v + (size_t)r * suv, c->dw / 2);
+        CK(cudaMemcpyAsync(dst, c->h_stage[si], dsz, cudaMemcpyHostToDevice, c->st));
+        CK(cudaEventRecord(c->ev_stage[si], c->st));
+    }
+    return same ? 0 : extend_into_slot(c, c->d_stage, slot);
 }
 extern "C" int ks_gpu_upload_frame_device(ks_gpu_ctx *c, int slot, const void *dev_i420)
 {
     if (!c || slot < 0 || slot >= c->cfg.n_src_slots || !dev_i420) return KS_EINVAL;
     CK(cudaSetDevice(c->device));
+    if (c->dw == c->W && c->dh == c->H) {
+        CK(cudaMemcpyAsync(c->d_src[slot], dev_i420, c->fsz, cudaMemcpyDeviceToDevice, c->st));
+        return 0;
+    }
     return extend_into_slot(c, (const uint8_t *)dev_i420, slot);
 }
 
@@ -332,6 +348,18 @@ extern "C" int ks_gpu_kat_sad16(const uint8_t *a, const uint8_t *b, long sa, lon
     if (!da.p || !db.p || !dout.p) return KS_ENOMEM;
     CK(cudaMemcpy(da.p, ha, 256, cudaMemcpyHostToDevice)); CK(cudaMemcpy(db.p, hb, 256, cudaMemcpyHostToDevice));
     if (ks_kat_sad16_dev(da.p, db.p, dout.p)) return KS_ECUDA;
+    CK(cudaMemcpy(out, dout.p, 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+extern "C" int ks_gpu_kat_satd16(const uint8_t *a, const uint8_t *b, long sa, long sb, uint32_t *out)
+{
+    int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return KS_ENODEV;
+    uint8_t ha[256], hb[256];
+    for (int y = 0; y < 16; y++) { memcpy(ha + 16 * y, a + y * sa, 16); memcpy(hb + 16 * y, b + y * sb, 16); }
+    dev_buf<uint8_t> da(256), db(256); dev_buf<uint32_t> dout(1);
+    if (!da.p || !db.p || !dout.p) return KS_ENOMEM;
+    CK(cudaMemcpy(da.p, ha, 256, cudaMemcpyHostToDevice)); CK(cudaMemcpy(db.p, hb, 256, cudaMemcpyHostToDevice));
+    if (ks_kat_satd16_dev(da.p, db.p, dout.p)) return KS_ECUDA;
     CK(cudaMemcpy(out, dout.p, 4, cudaMemcpyDeviceToHost));
     return 0;
 }

@@ -23,6 +23,14 @@ __global__ void ks_kat_sad16_kernel(const uint8_t *a, const uint8_t *b16, uint32
     unsigned v = ks_warp_sum(ks_sad_partial(sc.win, -wx0, -wy0, lane, s.x, s.y));
     if (lane == 0) *out = v;
 }
+__global__ void ks_kat_satd16_kernel(const uint8_t *a, const uint8_t *b16, uint32_t *out)
+{
+    const int lane = threadIdx.x;
+    const uint2 s = *reinterpret_cast<const uint2 *>(a + (lane >> 1) * 16 + 8 * (lane & 1));
+    const uint2 r = *reinterpret_cast<const uint2 *>(b16 + (lane >> 1) * 16 + 8 * (lane & 1));
+    unsigned v = ks_satd16(r.x, r.y, s.x, s.y, lane);
+    if (lane == 0) *out = v;
+}
 __global__ void ks_kat_interp_kernel(const uint8_t *plane, int w, int h, int x, int y, int mvx, int mvy, uint8_t *dst)
 {
     __shared__ __align__(16) KsWarpScratch sc;
@@ -50,6 +58,7 @@ __global__ void ks_kat_tb_kernel(const uint8_t *src, const uint8_t *pred, int qp
 }
 
 int ks_kat_sad16_dev(const uint8_t *a, const uint8_t *b16, uint32_t *out) { ks_kat_sad16_kernel<<<1, 32>>>(a, b16, out); return cudaGetLastError() == cudaSuccess ? 0 : -1; }
+int ks_kat_satd16_dev(const uint8_t *a, const uint8_t *b16, uint32_t *out) { ks_kat_satd16_kernel<<<1, 32>>>(a, b16, out); return cudaGetLastError() == cudaSuccess ? 0 : -1; }
 int ks_kat_interp_dev(const uint8_t *plane, int w, int h, int x, int y, int mvx, int mvy, uint8_t *dst)
 { ks_kat_interp_kernel<<<1, 32>>>(plane, w, h, x, y, mvx, mvy, dst); return cudaGetLastError() == cudaSuccess ? 0 : -1; }
 int ks_kat_tb_dev(int log2n, const uint8_t *src, const uint8_t *pred, int qp, int intra_slice, int sign_hiding, int16_t *levels, uint8_t *recon, int *cbf)

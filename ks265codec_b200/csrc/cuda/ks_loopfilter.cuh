@@ -149,8 +149,10 @@ void ks_launch_deblock(const KsPicParams &pp, KsPlanes rec, const ks_cell *cells
 
 /* ------------------------------------------------------------------ SAO -------------------------- */
 #define KS_SAO_WARPS 8
+#define KS_SAO_PITCH_Y 72      /* tile row: [3] left halo, [4..67] samples, [68] right halo (word-aligned interior) */
+#define KS_SAO_PITCH_C 40
 struct KsSaoSmem {
-    uint8_t tile[3][66 * 68];              /* deblocked samples incl. 1-sample halo; chroma uses 34 x 36 */
+    uint8_t tile[3][66 * KS_SAO_PITCH_Y];  /* deblocked samples incl. 1-sample halo; chroma uses 34 x 40 */
     int hist[KS_SAO_WARPS][3][52];         /* packed (sum<<12)|count: [0..19] EO class*5+cat, [20..51] BO band */
     int sum[3][52], cnt[3][52];
     int cost[3][48], off[3][48];           /* [0..15] EO class*4+(cat-1), [16..47] BO band */
@@ -174,6 +176,32 @@ __device__ __forceinline__ int ks_sao_offset_rd(int sum, int cnt, int signc, int
     }
     return best;
 }
+/* the 3x6 neighbourhood of a run of 4 samples starting at tile pointer t (row pitch `pitch`) */
+struct KsSaoNb { uint32_t up, ce, dn; int ul, ur, cl, cr, dl, dr; };
+__device__ __forceinline__ KsSaoNb ks_sao_load_nb(const uint8_t *t, int pitch)
+{
+    KsSaoNb n;
+    const uint32_t *u = reinterpret_cast<const uint32_t *>(t - pitch), *c = reinterpret_cast<const uint32_t *>(t), *d = reinterpret_cast<const uint32_t *>(t + pitch);
+    n.up = u[0]; n.ce = c[0]; n.dn = d[0];
+    n.ul = u[-1] >> 24; n.cl = c[-1] >> 24; n.dl = d[-1] >> 24;
+    n.ur = u[1] & 255; n.cr = c[1] & 255; n.dr = d[1] & 255;
+    return n;
+}
+/* edge categories (0 none, 1..4) of sample j of the run for the four EO classes; out-of-picture neighbours -> 0 */
+__device__ __forceinline__ void ks_sao_cats(const KsSaoNb &n, int j, bool lft, bool rgt, bool top, bool bot, int cat[4])
+{
+    const int lut = 0x43021;                       /* cat_of[0..4] = {1,2,0,3,4} as nibbles */
+    int c = (n.ce >> (8 * j)) & 255;
+    int l = j ? (n.ce >> (8 * j - 8)) & 255 : n.cl, r = j < 3 ? (n.ce >> (8 * j + 8)) & 255 : n.cr;
+    int u = (n.up >> (8 * j)) & 255, d = (n.dn >> (8 * j)) & 255;
+    int ul = j ? (n.up >> (8 * j - 8)) & 255 : n.ul, ur = j < 3 ? (n.up >> (8 * j + 8)) & 255 : n.ur;
+    int dl = j ? (n.dn >> (8 * j - 8)) & 255 : n.dl, dr = j < 3 ? (n.dn >> (8 * j + 8)) & 255 : n.dr;
+    bool h = !(lft || rgt), v = !(top || bot), hv = h && v;
+    cat[0] = h ? (lut >> (4 * (2 + ks_sgn(c - l) + ks_sgn(c - r)))) & 15 : 0;
+    cat[1] = v ? (lut >> (4 * (2 + ks_sgn(c - u) + ks_sgn(c - d)))) & 15 : 0;
+    cat[2] = hv ? (lut >> (4 * (2 + ks_sgn(c - ul) + ks_sgn(c - dr)))) & 15 : 0;
+    cat[3] = hv ? (lut >> (4 * (2 + ks_sgn(c - ur) + ks_sgn(c - dl)))) & 15 : 0;
+}
 
 __global__ void __launch_bounds__(KS_SAO_WARPS * KS_WARP)
 ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_syn *__restrict__ ctus, unsigned long long *sse_out)
@@ -182,42 +210,65 @@ ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_s
     KsSaoSmem *sm = reinterpret_cast<KsSaoSmem *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rx = blockIdx.x, ry = blockIdx.y;
-    const int dxa[4] = {-1, 0, -1, 1}, dya[4] = {0, -1, -1, -1};      /* neighbour a of class k; b = -a */
-    const int cat_of[5] = {1, 2, 0, 3, 4};
     for (int i = tid; i < KS_SAO_WARPS * 3 * 52; i += blockDim.x) (&sm->hist[0][0][0])[i] = 0;
     if (tid < 3) sm->sse[tid] = 0;
-    /* ---- stage the deblocked tile (+halo, coordinates clamped; out-of-picture neighbours are masked later) ---- */
+    /* ---- stage the deblocked tile: interior rows as 32-bit words, halo columns as bytes (coordinates clamped;
+     *      neighbours outside the picture are masked out in the statistics/apply passes) ---- */
     for (int ci = 0; ci < 3; ci++) {
         const int sh = ci ? 1 : 0, PW = pp.W >> sh, PH = pp.H >> sh, x0 = (rx << 6) >> sh, y0 = (ry << 6) >> sh;
-        const int tw = (64 >> sh) + 2, pitch = ci ? 36 : 68;
-        for (int i = tid; i < tw * tw; i += blockDim.x) {
-            int r = i / tw, c = i - r * tw;
-            int gy = min(max(y0 - 1 + r, 0), PH - 1), gx = min(max(x0 - 1 + c, 0), PW - 1);
-            sm->tile[ci][r * pitch + c] = deb.p[ci][(size_t)gy * PW + gx];
+        const int tw = 64 >> sh, pitch = ci ? KS_SAO_PITCH_C : KS_SAO_PITCH_Y, wpr = tw >> 2, bw = min(tw, PW - x0);
+        const uint8_t *plane = deb.p[ci];
+        for (int i = tid; i < (tw + 2) * wpr; i += blockDim.x) {
+            int r = i / wpr, c = i - r * wpr;
+            int gy = min(max(y0 - 1 + r, 0), PH - 1);
+            uint32_t w = (4 * c < bw) ? __ldg(reinterpret_cast<const uint32_t *>(plane + (size_t)gy * PW + x0 + 4 * c)) : 0u;
+            *reinterpret_cast<uint32_t *>(&sm->tile[ci][r * pitch + 4 + 4 * c]) = w;
+        }
+        for (int i = tid; i < (tw + 2) * 2; i += blockDim.x) {
+            int r = i >> 1, side = i & 1;
+            int gy = min(max(y0 - 1 + r, 0), PH - 1), gx = side ? min(x0 + bw, PW - 1) : max(x0 - 1, 0);
+            sm->tile[ci][r * pitch + (side ? 4 + bw : 3)] = __ldg(plane + (size_t)gy * PW + gx);
         }
     }
     __syncthreads();
-    /* ---- statistics ---- */
+    /* ---- statistics: runs of 4 samples per thread; EO categories accumulate in registers (16 packed counters),
+     *      BO bands in per-warp shared histograms with run aggregation ---- */
     if (pp.sao) {
         for (int ci = 0; ci < 3; ci++) {
             const int sh = ci ? 1 : 0, PW = pp.W >> sh, PH = pp.H >> sh, x0 = (rx << 6) >> sh, y0 = (ry << 6) >> sh;
-            const int bw = min(64 >> sh, PW - x0), bh = min(64 >> sh, PH - y0), pitch = ci ? 36 : 68, bwl = 6 - sh;
+            const int bw = min(64 >> sh, PW - x0), bh = min(64 >> sh, PH - y0), pitch = ci ? KS_SAO_PITCH_C : KS_SAO_PITCH_Y, rl = 4 - sh;
             int *h = sm->hist[warp][ci];
-            for (int i = tid; i < (bh << bwl); i += blockDim.x) {
-                int y = i >> bwl, x = i & ((1 << bwl) - 1);
-                if (x >= bw) continue;
-                const uint8_t *t = &sm->tile[ci][(y + 1) * pitch + x + 1];
-                int c = t[0], d = (int)src.p[ci][(size_t)(y0 + y) * PW + x0 + x] - c;
-                int v = d * 4096 + 1;
-                atomicAdd(&h[20 + (c >> 3)], v);
-                int gx = x0 + x, gy = y0 + y;
+            int acc[16];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    int xa = gx + dxa[k], ya = gy + dya[k], xb = gx - dxa[k], yb = gy - dya[k];
-                    if (xa < 0 || xb < 0 || ya < 0 || yb < 0 || xa >= PW || xb >= PW || ya >= PH || yb >= PH) continue;
-                    int cat = cat_of[2 + ks_sgn(c - t[dya[k] * pitch + dxa[k]]) + ks_sgn(c - t[-dya[k] * pitch - dxa[k]])];
-                    if (cat) atomicAdd(&h[k * 5 + cat], v);
+            for (int k = 0; k < 16; k++) acc[k] = 0;
+            for (int i = tid; i < (bh << rl); i += blockDim.x) {
+                const int y = i >> rl, x = (i & ((1 << rl) - 1)) << 2;
+                if (x >= bw) continue;
+                const KsSaoNb n = ks_sao_load_nb(&sm->tile[ci][(y + 1) * pitch + 4 + x], pitch);
+                const uint32_t s4 = __ldg(reinterpret_cast<const uint32_t *>(src.p[ci] + (size_t)(y0 + y) * PW + x0 + x));
+                const bool top = y0 + y == 0, bot = y0 + y == PH - 1;
+                int cur_band = -1, band_acc = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int c = (n.ce >> (8 * j)) & 255, d = (int)((s4 >> (8 * j)) & 255) - c, v = d * 4096 + 1;
+                    const int band = c >> 3;
+                    if (band != cur_band) { if (cur_band >= 0) atomicAdd(&h[20 + cur_band], band_acc); cur_band = band; band_acc = 0; }
+                    band_acc += v;
+                    int cat[4];
+                    ks_sao_cats(n, j, x0 + x + j == 0, x0 + x + j == PW - 1, top, bot, cat);
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+#pragma unroll
+                        for (int cc = 1; cc <= 4; cc++) acc[k * 4 + cc - 1] += cat[k] == cc ? v : 0;
                 }
+                atomicAdd(&h[20 + cur_band], band_acc);
+            }
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                int t = acc[k];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                if (lane == 0) h[(k >> 2) * 5 + (k & 3) + 1] = t;         /* this warp's private slot: plain store */
             }
         }
         __syncthreads();
@@ -273,26 +324,27 @@ ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_s
     /* ---- apply + write the final picture + SSE against the source ---- */
     for (int ci = 0; ci < 3; ci++) {
         const int sh = ci ? 1 : 0, PW = pp.W >> sh, PH = pp.H >> sh, x0 = (rx << 6) >> sh, y0 = (ry << 6) >> sh;
-        const int bw = min(64 >> sh, PW - x0), bh = min(64 >> sh, PH - y0), pitch = ci ? 36 : 68, bwl = 4 - sh;   /* 4 samples per thread */
+        const int bw = min(64 >> sh, PW - x0), bh = min(64 >> sh, PH - y0), pitch = ci ? KS_SAO_PITCH_C : KS_SAO_PITCH_Y, rl = 4 - sh;
         const ks_sao_param p = sm->par[ci];
         const int k = p.band_or_class;
-        unsigned long long sse = 0;
-        for (int i = tid; i < (bh << bwl); i += blockDim.x) {
-            int y = i >> bwl, x = (i & ((1 << bwl) - 1)) << 2;
+        const int o0 = p.off[0], o1 = p.off[1], o2 = p.off[2], o3 = p.off[3];
+        unsigned sse = 0;
+        for (int i = tid; i < (bh << rl); i += blockDim.x) {
+            const int y = i >> rl, x = (i & ((1 << rl) - 1)) << 2;
             if (x >= bw) continue;
-            const uint8_t *t = &sm->tile[ci][(y + 1) * pitch + x + 1];
-            uint32_t s4 = *reinterpret_cast<const uint32_t *>(src.p[ci] + (size_t)(y0 + y) * PW + x0 + x), o4 = 0;
+            const KsSaoNb n = ks_sao_load_nb(&sm->tile[ci][(y + 1) * pitch + 4 + x], pitch);
+            const uint32_t s4 = __ldg(reinterpret_cast<const uint32_t *>(src.p[ci] + (size_t)(y0 + y) * PW + x0 + x));
+            const bool top = y0 + y == 0, bot = y0 + y == PH - 1;
+            uint32_t o4 = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                int c = t[j], v = c;
-                if (p.type == 1) { int b = ((c >> 3) - k) & 31; if (b < 4) v = c + p.off[b]; }
+                int c = (n.ce >> (8 * j)) & 255, v = c;
+                if (p.type == 1) { int b = ((c >> 3) - k) & 31; if (b < 4) v = c + (b == 0 ? o0 : b == 1 ? o1 : b == 2 ? o2 : o3); }
                 else if (p.type == 2) {
-                    int gx = x0 + x + j, gy = y0 + y;
-                    int xa = gx + dxa[k], ya = gy + dya[k], xb = gx - dxa[k], yb = gy - dya[k];
-                    if (!(xa < 0 || xb < 0 || ya < 0 || yb < 0 || xa >= PW || xb >= PW || ya >= PH || yb >= PH)) {
-                        int cat = cat_of[2 + ks_sgn(c - t[j + dya[k] * pitch + dxa[k]]) + ks_sgn(c - t[j - dya[k] * pitch - dxa[k]])];
-                        if (cat) v = c + p.off[cat - 1];
-                    }
+                    int cat[4];
+                    ks_sao_cats(n, j, x0 + x + j == 0, x0 + x + j == PW - 1, top, bot, cat);
+                    int ct = k == 0 ? cat[0] : k == 1 ? cat[1] : k == 2 ? cat[2] : cat[3];
+                    if (ct) v = c + (ct == 1 ? o0 : ct == 2 ? o1 : ct == 3 ? o2 : o3);
                 }
                 v = ks_clip8(v);
                 o4 |= (uint32_t)v << (8 * j);
@@ -302,7 +354,7 @@ ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_s
             *reinterpret_cast<uint32_t *>(out.p[ci] + (size_t)(y0 + y) * PW + x0 + x) = o4;
         }
         if (sse_out) {
-            unsigned lo = ks_warp_sum((unsigned)sse);       /* per-thread SSE < 2^32: <= 64 samples * 65025 */
+            unsigned lo = ks_warp_sum(sse);                  /* per-thread SSE <= 16 samples * 65025 */
             if (lane == 0) atomicAdd(&sm->sse[ci], (unsigned long long)lo);
         }
     }

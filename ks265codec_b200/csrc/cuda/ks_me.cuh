@@ -27,18 +27,38 @@ struct KsWarpScratch {
 __device__ __forceinline__ void ks_load_window(uint32_t (*win)[KS_WIN_WW], const uint8_t *__restrict__ ref, int W, int H,
                                                int wx0, int wy0, int lane)
 {
-    for (int idx = lane; idx < KS_WIN_H * KS_WIN_WW; idx += KS_WARP) {
+    /* all 17 loads of a lane are issued before the first store (memory-level parallelism: one L2 round trip per window,
+     * not 17); words that straddle the picture border are patched afterwards with clamped byte loads (rare) */
+    constexpr int NW = KS_WIN_H * KS_WIN_WW, PER = (NW + KS_WARP - 1) / KS_WARP;
+    uint32_t v[PER];
+    unsigned border = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        int idx = lane + k * KS_WARP;
         int r = idx / KS_WIN_WW, c = idx - r * KS_WIN_WW;
         int gy = min(max(wy0 + r, 0), H - 1), gx = wx0 + 4 * c;
-        const uint8_t *row = ref + (size_t)gy * W;
-        uint32_t v;
-        if (gx >= 0 && gx + 3 < W) v = *reinterpret_cast<const uint32_t *>(row + gx);
-        else {
-            v = 0;
+        bool in = idx < NW && gx >= 0 && gx + 3 < W;
+        v[k] = in ? __ldg(reinterpret_cast<const uint32_t *>(ref + (size_t)gy * W + gx)) : 0u;
+        if (idx < NW && !in) border |= 1u << k;
+    }
 #pragma unroll
-            for (int b = 0; b < 4; b++) v |= (uint32_t)row[min(max(gx + b, 0), W - 1)] << (8 * b);
+    for (int k = 0; k < PER; k++) {
+        int idx = lane + k * KS_WARP;
+        if (idx < NW) (&win[0][0])[idx] = v[k];
+    }
+    if (__any_sync(0xffffffffu, border != 0)) {
+#pragma unroll 1
+        for (int k = 0; k < PER; k++) {
+            if (!((border >> k) & 1)) continue;
+            int idx = lane + k * KS_WARP;
+            int r = idx / KS_WIN_WW, c = idx - r * KS_WIN_WW;
+            int gy = min(max(wy0 + r, 0), H - 1), gx = wx0 + 4 * c;
+            const uint8_t *row = ref + (size_t)gy * W;
+            uint32_t w = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) w |= (uint32_t)row[min(max(gx + b, 0), W - 1)] << (8 * b);
+            (&win[0][0])[idx] = w;
         }
-        win[r][c] = v;
     }
     __syncwarp();
 }
@@ -57,6 +77,41 @@ __device__ __forceinline__ unsigned ks_sad_partial(const uint32_t (*win)[KS_WIN_
     uint32_t a, b;
     ks_win_px8(win, bxw, byw, lane, a, b);
     return __vsadu4(a, s0) + __vsadu4(b, s1);
+}
+
+/* SATD of a 16x16 block (reference had_c E@0x474500 -> xCalcHADs8x8 E@0x474200): four 8x8 Hadamard tiles, each
+ * (sum|coef| + 2) >> 2.  Lane holds 8 differences of row lane>>1, columns 8*(lane&1)..+7 (a = ref/pred, s = source).
+ * Horizontal butterflies stay in registers, vertical ones are 3 shuffle stages across the 8 rows of a tile.
+ * Warp-collective; every lane returns the block SATD.  Used as the sub-pel cost when the preset asks for SATD
+ * (reference `satdInter`, qy265enc.h:138: fast..placebo), SAD otherwise (ultrafast..veryfast). */
+__device__ __forceinline__ unsigned ks_satd16(uint32_t a0, uint32_t a1, uint32_t s0, uint32_t s1, int lane)
+{
+    int d[8];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        d[j] = (int)((s0 >> (8 * j)) & 255) - (int)((a0 >> (8 * j)) & 255);
+        d[4 + j] = (int)((s1 >> (8 * j)) & 255) - (int)((a1 >> (8 * j)) & 255);
+    }
+#pragma unroll
+    for (int len = 1; len < 8; len <<= 1)
+#pragma unroll
+        for (int i = 0; i < 8; i += 2 * len)
+#pragma unroll
+            for (int j = i; j < i + len; j++) { int u = d[j], v = d[j + len]; d[j] = u + v; d[j + len] = u - v; }
+    /* rows of one 8x8 tile are lanes {2r + half}: row bit k of the tile <-> lane bit k+1 */
+#pragma unroll
+    for (int bit = 2; bit <= 8; bit <<= 1) {
+        const bool hi = (lane & bit) != 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { int o = __shfl_xor_sync(0xffffffffu, d[j], bit); d[j] = hi ? o - d[j] : d[j] + o; }
+    }
+    unsigned t = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) t += (unsigned)abs(d[j]);
+    t += __shfl_xor_sync(0xffffffffu, t, 2); t += __shfl_xor_sync(0xffffffffu, t, 4); t += __shfl_xor_sync(0xffffffffu, t, 8);
+    t = (t + 2) >> 2;                                   /* per 8x8 tile; tiles: lane bit 0 (left/right), lane bit 4 (top/bottom) */
+    t += __shfl_xor_sync(0xffffffffu, t, 1); t += __shfl_xor_sync(0xffffffffu, t, 16);
+    return t;
 }
 
 /* 16 bytes starting at window byte column p of row `row`, as 4 words */

@@ -234,9 +234,15 @@ __device__ __forceinline__ void ks_mc_chroma8(uint8_t *cwin, int16_t *tmp, const
                                               int xc, int yc, int mvx, int mvy, uint8_t *dst, int dpitch, int lane)
 {
     const int ix = xc + (mvx >> 3) - 1, iy = yc + (mvy >> 3) - 1, fx = mvx & 7, fy = mvy & 7;
-    for (int idx = lane; idx < 144; idx += KS_WARP) {
-        int r = idx / 12, c = idx - r * 12;
-        cwin[idx] = ref[(size_t)min(max(iy + r, 0), PH - 1) * PW + min(max(ix + c, 0), PW - 1)];
+    {
+        uint8_t b[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) {                          /* 5 independent loads in flight per lane */
+            int idx = min(lane + k * KS_WARP, 143), r = idx / 12, c = idx - r * 12;
+            b[k] = __ldg(ref + (size_t)min(max(iy + r, 0), PH - 1) * PW + min(max(ix + c, 0), PW - 1));
+        }
+#pragma unroll
+        for (int k = 0; k < 5; k++) if (lane + k * KS_WARP < 144) cwin[lane + k * KS_WARP] = b[k];
     }
     __syncwarp();
     const int row = lane >> 2, col = (lane & 3) * 2;
@@ -293,7 +299,7 @@ __device__ __forceinline__ void ks_load_scans(uint16_t *scan, int tid, int nthre
     for (int i = tid; i < 64 + 256 + 1024; i += nthreads) scan[i] = i < 64 ? c_scan_tb[1][i] : (i < 320 ? c_scan_tb[2][i - 64] : c_scan_tb[3][i - 320]);
 }
 
-__global__ void __launch_bounds__(KS_RECON_WARPS * KS_WARP)
+__global__ void __launch_bounds__(KS_RECON_WARPS * KS_WARP, 2)
 ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes ref, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -58,6 +58,17 @@ def test_kat_sad16():
         assert int(out[0]) == O.ora_sad(ptr(a), ptr(b), 24, 40, 16, 16)
 
 
+def test_kat_satd16():
+    L, O = ks.lib(), oracle()
+    rng = np.random.default_rng(3)
+    for amp in (255, 40, 6, 1):
+        a = rng.integers(0, 256, (16, 16), dtype=np.uint8)
+        b = np.clip(a.astype(int) + rng.integers(-amp, amp + 1, (16, 16)), 0, 255).astype(np.uint8)
+        out = np.zeros(1, np.uint32)
+        assert L.ks_gpu_kat_satd16(ptr(a), ptr(b), 16, 16, ptr(out)) == 0
+        assert int(out[0]) == O.ora_satd(ptr(a), ptr(b), 16, 16, 16, 16)
+
+
 def test_kat_interp_luma16_all_phases_and_borders():
     L, O = ks.lib(), oracle()
     rng = np.random.default_rng(2)
