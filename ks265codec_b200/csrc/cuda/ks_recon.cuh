@@ -6,7 +6,8 @@
  *                  E@0x4a2580) -> sign-data hiding (signBitHidingHDQ E@0x4a29c0) -> dequantiser
  *                  (H265DeQuantBlock_c E@0x439540) -> inverse DCT + prediction add (H265_2dIDct*_c E@0x4417f0..).
  *                  int16/int32 butterfly work on the CUDA cores: lane = one row/column, the transform matrix is
- *                  an immediate-offset constant-bank operand, one even/odd butterfly level halves the MACs,
+ *                  fully unrolled partial butterflies with IMMEDIATE coefficients (ks_dct_gen.cuh; constant-bank
+ *                  operands thrashed the immediate-constant cache),
  *                  transposes go through padded shared memory.  No tensor cores (north star).
  *  ks_recon_inter_kernel   one CTA per 64x64 CTU: CU-size decision, motion compensation of the 16 cells into
  *                  shared memory (the reference's `reconstruct` E@0x47d600 driver + interpolatePuLx E@0x487260),
@@ -28,41 +29,8 @@ struct KsTbScratch {
 
 template <int N> struct KsLog2 { static const int v = N == 32 ? 5 : (N == 16 ? 4 : 3); };
 
-/* forward: out[u] = sum_x M[u][x] in[x] with one even/odd split */
-template <int N>
-__device__ __forceinline__ void ks_fwd_pass(const int (&in)[N], int (&out)[N], int shift)
-{
-    constexpr int STEP = 32 / N, HN = N / 2;
-    int e[HN], o[HN];
-#pragma unroll
-    for (int x = 0; x < HN; x++) { e[x] = in[x] + in[N - 1 - x]; o[x] = in[x] - in[N - 1 - x]; }
-    const int rnd = 1 << (shift - 1);
-#pragma unroll
-    for (int u = 0; u < N; u++) {
-        int acc = rnd;
-#pragma unroll
-        for (int x = 0; x < HN; x++) acc += c_dct[u * STEP][x] * ((u & 1) ? o[x] : e[x]);
-        out[u] = acc >> shift;
-    }
-}
-/* inverse: out[y] = sum_k M[k][y] in[k] with one even/odd split */
-template <int N>
-__device__ __forceinline__ void ks_inv_pass(const int (&in)[N], int (&out)[N], int shift, bool clip16)
-{
-    constexpr int STEP = 32 / N, HN = N / 2;
-    const int rnd = 1 << (shift - 1);
-#pragma unroll
-    for (int y = 0; y < HN; y++) {
-        int e = 0, o = 0;
-#pragma unroll
-        for (int k = 0; k < N; k += 2) e += c_dct[k * STEP][y] * in[k];
-#pragma unroll
-        for (int k = 1; k < N; k += 2) o += c_dct[k * STEP][y] * in[k];
-        int a = (e + o + rnd) >> shift, b = (e - o + rnd) >> shift;
-        if (clip16) { a = ks_clip3(-32768, 32767, a); b = ks_clip3(-32768, 32767, b); }
-        out[y] = a; out[N - 1 - y] = b;
-    }
-}
+/* transform passes: generated partial butterflies with immediate coefficients (tools/gen_dct.py) */
+#include "ks_dct_gen.cuh"
 
 /* sign-data hiding for one coefficient group (16 scan positions starting at scan index sp) of a TB whose
  * coefficient/level/deltaU arrays are N x N row-major.  Mirrors ora_sign_hide's per-CG body. */
