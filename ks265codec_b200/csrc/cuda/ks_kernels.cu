@@ -49,11 +49,13 @@ __global__ void ks_kat_tb_kernel(const uint8_t *src, const uint8_t *pred, int qp
     __shared__ __align__(16) KsTbScratch ts;
     __shared__ __align__(16) uint8_t sp[32 * 32];
     __shared__ uint16_t scan[1024];
+    __shared__ __align__(16) int t0[256];
     const int lane = threadIdx.x;
+    ks_load_t0(t0, lane, 32);
     for (int i = lane; i < N * N; i += 32) { sp[i] = pred[i]; scan[i] = c_scan_tb[KsLog2<N>::v - 2][i]; }
     __syncwarp();
     const int g = lane / N, r = lane % N;
-    bool c = ks_tb_code<N>(&ts, scan, g == 0, src + r * N, sp + r * N, recon + r * N, levels + r * N, qp, intra_slice, sign_hiding, lane);
+    bool c = ks_tb_code<N>(&ts, scan, t0, g == 0, src + r * N, sp + r * N, recon + r * N, levels + r * N, qp, intra_slice, sign_hiding, lane);
     if (lane == 0) *cbf = c;
 }
 

@@ -152,7 +152,7 @@ __device__ __forceinline__ void ks_interp16(KsWarpScratch *sc, int bxw, int byw,
     } else if (fx == 0) {
 #pragma unroll
         for (int j = 0; j < 8; j++) v[j] = 0;
-#pragma unroll
+#pragma unroll 2
         for (int t = 0; t < 8; t++) {
             uint32_t a, b; int c = c_luma_taps[fy][t];
             int wx = bxw + 8 * half;
@@ -181,7 +181,7 @@ __device__ __forceinline__ void ks_interp16(KsWarpScratch *sc, int bxw, int byw,
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 8; j++) v[j] = 0;
-#pragma unroll
+#pragma unroll 2
         for (int t = 0; t < 8; t++) {
             int c = c_luma_taps[fy][t];
             uint4 q = *reinterpret_cast<const uint4 *>(&sc->tmp[row + t][8 * half]);

@@ -33,30 +33,23 @@ template <int N> struct KsLog2 { static const int v = N == 32 ? 5 : (N == 16 ? 4
 #include "ks_dct_gen.cuh"
 
 /* sign-data hiding for one coefficient group (16 scan positions starting at scan index sp) of a TB whose
- * coefficient/level/deltaU arrays are N x N row-major.  Mirrors ora_sign_hide's per-CG body. */
-template <int N>
-__device__ __forceinline__ void ks_sbh_cg(const int16_t *C, int16_t *L, const int16_t *D, const uint16_t *scan, int sp, bool is_last_cg)
+ * coefficient/level/deltaU arrays are N x N row-major.  Mirrors ora_sign_hide's per-CG body.  Deliberately NOT
+ * unrolled / not inlined: it runs for few groups and the kernel's instruction footprint matters more. */
+__device__ __noinline__ void ks_sbh_cg(const int16_t *C, int16_t *L, const int16_t *D, const uint16_t *scan, int sp, bool is_last_cg, int n)
 {
-    int first = 16, last = -1, sum = 0;
-    int pos[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) { int s = scan[sp + i]; pos[i] = (s >> 8) * N + (s & 255); }
-#pragma unroll
-    for (int i = 0; i < 16; i++) { int l = L[pos[i]]; if (l) { if (first == 16) first = i; last = i; } }
+#define KS_POS(i) (((int)scan[sp + (i)] >> 8) * n + ((int)scan[sp + (i)] & 255))
+    int first = 16, last = -1, sum = 0, lf = 0;
+#pragma unroll 1
+    for (int i = 0; i < 16; i++) { int l = L[KS_POS(i)]; if (l) { if (first == 16) { first = i; lf = l; } last = i; } }
     if (last - first < 4) return;
-#pragma unroll
-    for (int i = 0; i < 16; i++) if (i >= first && i <= last) sum += L[pos[i]];
-    int lf = 0;
-#pragma unroll
-    for (int i = 0; i < 16; i++) if (i == first) lf = L[pos[i]];
+#pragma unroll 1
+    for (int i = first; i <= last; i++) sum += L[KS_POS(i)];
     const int signbit = lf > 0 ? 0 : 1;
     if (signbit == (sum & 1)) return;
     int min_cost = 0x7fffffff, min_pos = -1, final_change = 0;
-    int start = is_last_cg ? last : 15;
-#pragma unroll
-    for (int i = 15; i >= 0; i--) {
-        if (i > start) continue;
-        int p = pos[i], lv = L[p], du = D[p], cost, change = 0;
+#pragma unroll 1
+    for (int i = is_last_cg ? last : 15; i >= 0; i--) {
+        int p = KS_POS(i), lv = L[p], du = D[p], cost, change = 0;
         if (lv != 0) {
             if (du > 0) { cost = -du; change = 1; }
             else if (i == first && abs(lv) == 1) cost = 0x7fffffff;
@@ -68,6 +61,7 @@ __device__ __forceinline__ void ks_sbh_cg(const int16_t *C, int16_t *L, const in
         } else { cost = -du; change = 1; }
         if (cost < min_cost) { min_cost = cost; final_change = change; min_pos = p; }
     }
+#undef KS_POS
     int lv = L[min_pos];
     if (lv == 32767 || lv == -32768) final_change = -1;
     L[min_pos] = (int16_t)(C[min_pos] >= 0 ? lv + final_change : lv - final_change);
@@ -79,10 +73,11 @@ __device__ __forceinline__ void ks_sbh_cg(const int16_t *C, int16_t *L, const in
  *   pred_row: shared  pointer to row r of the lane's prediction block (N bytes)
  *   rec_row : global pointer to row r of the lane's reconstruction
  *   lev_row : global pointer to row r of the lane's level block (dense int16 plane)
+ *   t0      : shared 16x16 int table, t0[j][x] = M32[2j+1][x] (level-0 odd part of the 32-point butterflies)
  * returns, per lane, whether the lane's block has any non-zero level (cbf).
  */
 template <int N>
-__device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, bool valid,
+__device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, const int *t0, bool valid,
                                         const uint8_t *__restrict__ src_row, const uint8_t *pred_row,
                                         uint8_t *__restrict__ rec_row, int16_t *__restrict__ lev_row,
                                         int qp, int intra_slice, int sign_hiding, int lane)
@@ -91,22 +86,20 @@ __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, b
     const int g = lane / N, r = lane % N;
     const unsigned gmask = (N == 32) ? 0xffffffffu : (((1u << N) - 1u) << (g * N));
     int16_t *S = sc->S + g * N * SP, *C = sc->C + g * N * N, *L = sc->L + g * N * N, *D = sc->D + g * N * N;
-    int res[N], t[N];
+    int res[N];
     uint8_t pred[N];
     /* a. residual row */
 #pragma unroll
     for (int x = 0; x < N; x += 4) {
         uint32_t p4 = *reinterpret_cast<const uint32_t *>(pred_row + x);
-        uint32_t s4 = valid ? *reinterpret_cast<const uint32_t *>(src_row + x) : p4;
+        uint32_t s4 = valid ? __ldg(reinterpret_cast<const uint32_t *>(src_row + x)) : p4;
 #pragma unroll
         for (int b = 0; b < 4; b++) { pred[x + b] = (uint8_t)(p4 >> (8 * b)); res[x + b] = (int)((s4 >> (8 * b)) & 255) - (int)pred[x + b]; }
     }
-    /* b. forward pass 1 (rows), stage shift 2*log2N-2; store transposed S[u][r] */
-    ks_fwd_pass<N>(res, t, 2 * LOG2 - 2);
-#pragma unroll
-    for (int u = 0; u < N; u++) S[u * SP + r] = (int16_t)t[u];
+    /* b. forward pass 1 (rows), stage shift 2*log2N-2; results stored transposed: S[u][r] */
+    ks_fwd_pass<N>(res, 2 * LOG2 - 2, t0, [&](int u, int v) { S[u * SP + r] = (int16_t)v; });
     __syncwarp();
-    /* c. forward pass 2 (columns): lane = horizontal frequency u = r */
+    /* c. forward pass 2 (columns): lane = horizontal frequency u = r; d. quantise each coefficient (v, u=r) as it appears */
 #pragma unroll
     for (int y = 0; y < N; y += 8) {
         uint4 q = *reinterpret_cast<const uint4 *>(&S[r * SP + y]);
@@ -114,19 +107,16 @@ __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, b
 #pragma unroll
         for (int j = 0; j < 4; j++) { res[y + 2 * j] = (int)(short)(w[j] & 0xffffu); res[y + 2 * j + 1] = (int)w[j] >> 16; }
     }
-    ks_fwd_pass<N>(res, t, 7);
-    /* d. quantise: t[v] = coefficient (v, u=r) */
     const int qbits = 21 + qp / 6 - LOG2, scale = c_quant_scales[qp % 6];
     const int add = (intra_slice ? 171 : 85) << (qbits - 9);
     bool nz = false;
-#pragma unroll
-    for (int v = 0; v < N; v++) {
-        int c = (int)(short)t[v], a = abs(c), m = a * scale, lv = (m + add) >> qbits;
+    ks_fwd_pass<N>(res, 7, t0, [&](int v, int coef) {
+        int c = (int)(short)coef, a = abs(c), m = a * scale, lv = (m + add) >> qbits;
         int du = (m - (lv << qbits)) >> (qbits - 8);
         lv = min(lv, 32767);
         nz |= lv != 0;
         C[v * N + r] = (int16_t)c; L[v * N + r] = (int16_t)(c < 0 ? -lv : lv); D[v * N + r] = (int16_t)du;
-    }
+    });
     unsigned nzb = __ballot_sync(0xffffffffu, nz && valid);
     bool cbf = (nzb & gmask) != 0;
     /* e. sign-data hiding, one coefficient group per lane (uniform ballots first, then the per-CG pass) */
@@ -140,7 +130,7 @@ __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, b
             bool cgnz = false;
             if (id < G * NCG) {
                 const int16_t *Lt = sc->L + tb * N * N;
-#pragma unroll
+#pragma unroll 4
                 for (int i = 0; i < 16; i++) { int s = scan[cg * 16 + i]; cgnz |= Lt[(s >> 8) * N + (s & 255)] != 0; }
             }
             ball[rep] = __ballot_sync(0xffffffffu, cgnz);
@@ -150,12 +140,12 @@ __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, b
             int id = lane + 32 * rep, tb = id / NCG, cg = id % NCG;
             if (id < G * NCG && ((ball[rep] >> lane) & 1)) {
                 unsigned long long m;
-                if (REPS == 2) m = ((unsigned long long)ball[1] << 32) | ball[0];
+                if (REPS == 2) m = ((unsigned long long)ball[REPS - 1] << 32) | ball[0];
                 else m = ball[0];
                 constexpr unsigned long long TBMASK = NCG == 64 ? ~0ull : ((1ull << (NCG & 63)) - 1ull);
                 unsigned long long tbm = (m >> ((tb * NCG) & 63)) & TBMASK;
                 int top = 63 - __clzll((long long)tbm);
-                ks_sbh_cg<N>(sc->C + tb * N * N, sc->L + tb * N * N, sc->D + tb * N * N, scan, cg * 16, cg == top);
+                ks_sbh_cg(sc->C + tb * N * N, sc->L + tb * N * N, sc->D + tb * N * N, scan, cg * 16, cg == top, N);
             }
         }
     }
@@ -168,21 +158,15 @@ __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, b
     /* g. reconstruction */
     if (nzb) {
         const int shift = LOG2 - 1, dq = c_inv_quant_scales[qp % 6] << (qp / 6), rnd = 1 << (shift - 1);
-#pragma unroll
-        for (int k = 0; k < N; k++) res[k] = ks_clip3(-32768, 32767, ((int)L[k * N + r] * dq + rnd) >> shift);   /* column x = r */
-        ks_inv_pass<N>(res, t, 7, true);
+        int t[N];
+        /* inverse pass 1 (columns, lane = column x = r): inputs are dequantised on the fly */
+        ks_inv_pass<N>([&](int k) { return ks_clip3(-32768, 32767, ((int)L[k * N + r] * dq + rnd) >> shift); }, t, 7, true, t0);
         __syncwarp();
 #pragma unroll
         for (int y = 0; y < N; y++) S[y * SP + r] = (int16_t)t[y];
         __syncwarp();
-#pragma unroll
-        for (int k = 0; k < N; k += 8) {
-            uint4 q = *reinterpret_cast<const uint4 *>(&S[r * SP + k]);
-            uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-            for (int j = 0; j < 4; j++) { res[k + 2 * j] = (int)(short)(w[j] & 0xffffu); res[k + 2 * j + 1] = (int)w[j] >> 16; }
-        }
-        ks_inv_pass<N>(res, t, 12, false);
+        /* inverse pass 2 (rows, lane = row y = r) */
+        ks_inv_pass<N>([&](int k) { return (int)S[r * SP + k]; }, t, 12, false, t0);
 #pragma unroll
         for (int x = 0; x < N; x++) pred[x] = (uint8_t)ks_clip8((int)pred[x] + t[x]);
     }
@@ -252,16 +236,19 @@ __device__ __forceinline__ void ks_mc_chroma8(uint8_t *cwin, int16_t *tmp, const
 struct KsReconSmem {
     union { KsWarpScratch mc[KS_RECON_WARPS]; KsTbScratch tb[KS_RECON_WARPS]; } u;
     uint16_t scan[64 + 256 + 1024];            /* scan tables for 8x8, 16x16, 32x32 */
+    int      t0[256];                          /* M32[2j+1][x], j,x < 16: level-0 odd part of the 32-point butterflies */
     uint8_t  predY[64 * 64];
     uint8_t  predC[2][32 * 32];
     uint8_t  cwin[KS_RECON_WARPS][144];
     int16_t  mvx[16], mvy[16];
-    uint8_t  valid[16], culog2[16];
+    uint8_t  valid[16];
     unsigned cbf[16];                          /* KS_F_CBF_* bits per cell, OR-ed by the transform tasks */
-    uint8_t  task_n[16], task_q[16], task_sub[16];
-    int      ntasks;
 };
 __device__ __forceinline__ const uint16_t *ks_scan_ptr(const KsReconSmem *sm, int n) { return sm->scan + (n == 8 ? 0 : (n == 16 ? 64 : 320)); }
+__device__ __forceinline__ void ks_load_t0(int *t0, int tid, int nthreads)
+{
+    for (int i = tid; i < 256; i += nthreads) t0[i] = c_dct[2 * (i >> 4) + 1][i & 15];
+}
 __device__ __forceinline__ void ks_load_scans(uint16_t *scan, int tid, int nthreads)
 {
     for (int i = tid; i < 64 + 256 + 1024; i += nthreads) scan[i] = i < 64 ? c_scan_tb[1][i] : (i < 320 ? c_scan_tb[2][i - 64] : c_scan_tb[3][i - 320]);
@@ -276,6 +263,7 @@ ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes ref, KsPlanes rec, 
     const int ctx = blockIdx.x, cty = blockIdx.y, X0 = ctx << 6, Y0 = cty << 6;
     const int W = pp.W, H = pp.H, CW = W >> 1, CH = H >> 1;
     ks_load_scans(sm->scan, tid, blockDim.x);
+    ks_load_t0(sm->t0, tid, blockDim.x);
     if (tid < 16) {
         int cx = tid & 3, cy = tid >> 2, x = X0 + (cx << 4), y = Y0 + (cy << 4);
         bool v = x < W && y < H;
@@ -284,37 +272,21 @@ ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes ref, KsPlanes rec, 
         else { sm->mvx[tid] = 0; sm->mvy[tid] = 0; }
     }
     __syncthreads();
-    if (tid == 0) {
-        /* CU size: four equal-MV siblings merge upward (16 -> 32 -> 64), mirror of ora_inter_picture step 2 */
-        bool q32[4]; int nt = 0;
-        for (int q = 0; q < 4; q++) {
-            int b = (q & 1) * 2 + (q >> 1) * 8, i0 = b, i1 = b + 1, i2 = b + 4, i3 = b + 5;
-            bool ok = sm->valid[i0] && sm->valid[i1] && sm->valid[i2] && sm->valid[i3];
-            ok = ok && sm->mvx[i0] == sm->mvx[i1] && sm->mvx[i0] == sm->mvx[i2] && sm->mvx[i0] == sm->mvx[i3]
-                    && sm->mvy[i0] == sm->mvy[i1] && sm->mvy[i0] == sm->mvy[i2] && sm->mvy[i0] == sm->mvy[i3];
-            q32[q] = ok;
-            int l = ok ? 5 : 4;
-            sm->culog2[i0] = sm->culog2[i1] = sm->culog2[i2] = sm->culog2[i3] = (uint8_t)l;
-        }
-        bool c64 = q32[0] && q32[1] && q32[2] && q32[3];
-        for (int q = 1; q < 4 && c64; q++) { int b = (q & 1) * 2 + (q >> 1) * 8; c64 = sm->mvx[b] == sm->mvx[0] && sm->mvy[b] == sm->mvy[0]; }
-        if (c64) for (int i = 0; i < 16; i++) sm->culog2[i] = 6;
-        for (int q = 0; q < 4; q++) {
-            int b = (q & 1) * 2 + (q >> 1) * 8;
-            if (!sm->valid[b]) continue;
-            if (q32[q]) {
-                sm->task_n[nt] = 32; sm->task_q[nt] = (uint8_t)q; sm->task_sub[nt++] = 0;
-                sm->task_n[nt] = 16; sm->task_q[nt] = (uint8_t)q; sm->task_sub[nt++] = 2;     /* chroma 16x16 Cb+Cr */
-            } else {
-                sm->task_n[nt] = 16; sm->task_q[nt] = (uint8_t)q; sm->task_sub[nt++] = 0;     /* luma cells 0,1 */
-                sm->task_n[nt] = 16; sm->task_q[nt] = (uint8_t)q; sm->task_sub[nt++] = 1;     /* luma cells 2,3 */
-                sm->task_n[nt] = 8;  sm->task_q[nt] = (uint8_t)q; sm->task_sub[nt++] = 0;     /* Cb of 4 cells */
-                sm->task_n[nt] = 8;  sm->task_q[nt] = (uint8_t)q; sm->task_sub[nt++] = 1;     /* Cr of 4 cells */
-            }
-        }
-        sm->ntasks = nt;
+    /* CU size: four equal-MV siblings merge upward (16 -> 32 -> 64), mirror of ora_inter_picture step 2.
+     * Every thread derives the same flags from shared memory: no serial section, no task list. */
+    bool q32[4], c64 = true;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int b0 = (q & 1) * 2 + (q >> 1) * 8;
+        bool ok = sm->valid[b0] && sm->valid[b0 + 1] && sm->valid[b0 + 4] && sm->valid[b0 + 5];
+        const int mx = sm->mvx[b0], my = sm->mvy[b0];
+        ok = ok && sm->mvx[b0 + 1] == mx && sm->mvx[b0 + 4] == mx && sm->mvx[b0 + 5] == mx
+                && sm->mvy[b0 + 1] == my && sm->mvy[b0 + 4] == my && sm->mvy[b0 + 5] == my;
+        q32[q] = ok;
+        c64 = c64 && ok && mx == sm->mvx[0] && my == sm->mvy[0];
     }
     /* ---- motion compensation of the 16 cells into shared memory ---- */
+#pragma unroll 1
     for (int k = warp; k < 16; k += KS_RECON_WARPS) {
         if (!sm->valid[k]) continue;
         const int cx = k & 3, cy = k >> 2, x0 = X0 + (cx << 4), y0 = Y0 + (cy << 4);
@@ -326,41 +298,48 @@ ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes ref, KsPlanes rec, 
         uint32_t o0, o1;
         ks_interp16(sc, x0 + (mvx >> 2) - wx0, y0 + (mvy >> 2) - wy0, mvx & 3, mvy & 3, lane, o0, o1);
         *reinterpret_cast<uint2 *>(&sm->predY[((cy << 4) + (lane >> 1)) * 64 + (cx << 4) + 8 * (lane & 1)]) = make_uint2(o0, o1);
+#pragma unroll 1
         for (int ci = 0; ci < 2; ci++)
             ks_mc_chroma8(sm->cwin[warp], &sc->tmp[0][0], ref.p[1 + ci], CW, CH, x0 >> 1, y0 >> 1, mvx, mvy,
                           &sm->predC[ci][(cy << 3) * 32 + (cx << 3)], 32, lane);
     }
     __syncthreads();
-    /* ---- transform tasks ---- */
-    const int ntasks = sm->ntasks;
-    for (int t = warp; t < ntasks; t += KS_RECON_WARPS) {
-        const int n = sm->task_n[t], q = sm->task_q[t], sub = sm->task_sub[t];
+    /* ---- transform tasks: 16 slots (k, q) = (kind 0..3, quadrant); a quadrant coded with one 32x32 TU uses kinds
+     *      0 (luma 32) and 1 (Cb+Cr 16), otherwise kinds 0,1 (two luma 16 pairs) and 2,3 (four Cb 8 / four Cr 8).
+     *      Slot order k*4+q gives every warp one heavy and one light task. ---- */
+#pragma unroll 1
+    for (int sl = warp; sl < 16; sl += KS_RECON_WARPS) {
+        const int k = sl >> 2, q = sl & 3;
         const int qx = (q & 1) * 32, qy = (q >> 1) * 32;             /* quadrant origin inside the CTU (luma) */
+        const int b0 = (q & 1) * 2 + (q >> 1) * 8;
+        if (!sm->valid[b0]) continue;
         KsTbScratch *ts = &sm->u.tb[warp];
-        if (n == 32) {
-            int r = lane, x = X0 + qx, y = Y0 + qy + r;
-            bool cbf = ks_tb_code<32>(ts, ks_scan_ptr(sm, 32), true, src.p[0] + (size_t)y * W + x, &sm->predY[(qy + r) * 64 + qx],
-                                      rec.p[0] + (size_t)y * W + x, lv.p[0] + (size_t)y * W + x, pp.qp, 0, pp.sign_hiding, lane);
-            if (lane == 0 && cbf) { int b = (q & 1) * 2 + (q >> 1) * 8; atomicOr(&sm->cbf[b], KS_F_CBF_Y); atomicOr(&sm->cbf[b + 1], KS_F_CBF_Y); atomicOr(&sm->cbf[b + 4], KS_F_CBF_Y); atomicOr(&sm->cbf[b + 5], KS_F_CBF_Y); }
-        } else if (n == 16 && sub == 2) {
-            int g = lane >> 4, r = lane & 15, x = (X0 + qx) >> 1, y = ((Y0 + qy) >> 1) + r;
-            bool cbf = ks_tb_code<16>(ts, ks_scan_ptr(sm, 16), true, src.p[1 + g] + (size_t)y * CW + x, &sm->predC[g][((qy >> 1) + r) * 32 + (qx >> 1)],
-                                      rec.p[1 + g] + (size_t)y * CW + x, lv.p[1 + g] + (size_t)y * CW + x, pp.qpc, 0, pp.sign_hiding, lane);
-            if (r == 0 && cbf) { int b = (q & 1) * 2 + (q >> 1) * 8, f = g ? KS_F_CBF_CR : KS_F_CBF_CB; atomicOr(&sm->cbf[b], f), atomicOr(&sm->cbf[b + 1], f), atomicOr(&sm->cbf[b + 4], f), atomicOr(&sm->cbf[b + 5], f); }
-        } else if (n == 16) {
-            int g = lane >> 4, r = lane & 15, kc = sub * 2 + g;               /* cell inside the quadrant */
-            int cidx = (q & 1) * 2 + (q >> 1) * 8 + (kc & 1) + (kc >> 1) * 4;
+        if (q32[q]) {
+            if (k == 0) {
+                int r = lane, x = X0 + qx, y = Y0 + qy + r;
+                bool cbf = ks_tb_code<32>(ts, ks_scan_ptr(sm, 32), sm->t0, true, src.p[0] + (size_t)y * W + x, &sm->predY[(qy + r) * 64 + qx],
+                                          rec.p[0] + (size_t)y * W + x, lv.p[0] + (size_t)y * W + x, pp.qp, 0, pp.sign_hiding, lane);
+                if (lane == 0 && cbf) { atomicOr(&sm->cbf[b0], KS_F_CBF_Y); atomicOr(&sm->cbf[b0 + 1], KS_F_CBF_Y); atomicOr(&sm->cbf[b0 + 4], KS_F_CBF_Y); atomicOr(&sm->cbf[b0 + 5], KS_F_CBF_Y); }
+            } else if (k == 1) {
+                int g = lane >> 4, r = lane & 15, x = (X0 + qx) >> 1, y = ((Y0 + qy) >> 1) + r;
+                bool cbf = ks_tb_code<16>(ts, ks_scan_ptr(sm, 16), sm->t0, true, src.p[1 + g] + (size_t)y * CW + x, &sm->predC[g][((qy >> 1) + r) * 32 + (qx >> 1)],
+                                          rec.p[1 + g] + (size_t)y * CW + x, lv.p[1 + g] + (size_t)y * CW + x, pp.qpc, 0, pp.sign_hiding, lane);
+                if (r == 0 && cbf) { unsigned f = g ? KS_F_CBF_CR : KS_F_CBF_CB; atomicOr(&sm->cbf[b0], f); atomicOr(&sm->cbf[b0 + 1], f); atomicOr(&sm->cbf[b0 + 4], f); atomicOr(&sm->cbf[b0 + 5], f); }
+            }
+        } else if (k < 2) {
+            int g = lane >> 4, r = lane & 15, kc = k * 2 + g;                 /* cell inside the quadrant */
+            int cidx = b0 + (kc & 1) + (kc >> 1) * 4;
             bool v = sm->valid[cidx];
             int lx = qx + (kc & 1) * 16, ly = qy + (kc >> 1) * 16 + r, x = X0 + lx, y = Y0 + ly;
-            bool cbf = ks_tb_code<16>(ts, ks_scan_ptr(sm, 16), v, src.p[0] + (size_t)y * W + x, &sm->predY[ly * 64 + lx],
+            bool cbf = ks_tb_code<16>(ts, ks_scan_ptr(sm, 16), sm->t0, v, src.p[0] + (size_t)y * W + x, &sm->predY[ly * 64 + lx],
                                       rec.p[0] + (size_t)y * W + x, lv.p[0] + (size_t)y * W + x, pp.qp, 0, pp.sign_hiding, lane);
             if (r == 0 && cbf) atomicOr(&sm->cbf[cidx], KS_F_CBF_Y);
         } else {
-            int g = lane >> 3, r = lane & 7, kc = g, ci = sub;
-            int cidx = (q & 1) * 2 + (q >> 1) * 8 + (kc & 1) + (kc >> 1) * 4;
+            int g = lane >> 3, r = lane & 7, kc = g, ci = k - 2;
+            int cidx = b0 + (kc & 1) + (kc >> 1) * 4;
             bool v = sm->valid[cidx];
             int lx = (qx >> 1) + (kc & 1) * 8, ly = (qy >> 1) + (kc >> 1) * 8 + r, x = (X0 >> 1) + lx, y = (Y0 >> 1) + ly;
-            bool cbf = ks_tb_code<8>(ts, ks_scan_ptr(sm, 8), v, src.p[1 + ci] + (size_t)y * CW + x, &sm->predC[ci][ly * 32 + lx],
+            bool cbf = ks_tb_code<8>(ts, ks_scan_ptr(sm, 8), sm->t0, v, src.p[1 + ci] + (size_t)y * CW + x, &sm->predC[ci][ly * 32 + lx],
                                      rec.p[1 + ci] + (size_t)y * CW + x, lv.p[1 + ci] + (size_t)y * CW + x, pp.qpc, 0, pp.sign_hiding, lane);
             if (r == 0 && cbf) atomicOr(&sm->cbf[cidx], ci ? KS_F_CBF_CR : KS_F_CBF_CB);
         }
@@ -368,7 +347,7 @@ ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes ref, KsPlanes rec, 
     __syncthreads();
     if (tid < 16 && sm->valid[tid]) {
         int cx = tid & 3, cy = tid >> 2;
-        ks_cell c; c.mvx = sm->mvx[tid]; c.mvy = sm->mvy[tid]; c.cu_log2 = sm->culog2[tid]; c.flags = (uint8_t)sm->cbf[tid]; c.intra_mode = 0; c.rsv = 0;
+        ks_cell c; c.mvx = sm->mvx[tid]; c.mvy = sm->mvy[tid]; c.cu_log2 = (uint8_t)(c64 ? 6 : (q32[(cx >> 1) + (cy >> 1) * 2] ? 5 : 4)); c.flags = (uint8_t)sm->cbf[tid]; c.intra_mode = 0; c.rsv = 0;
         cells[((Y0 >> 4) + cy) * pp.cw + (X0 >> 4) + cx] = c;
     }
 }
@@ -525,12 +504,12 @@ ks_recon_intra_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, k
             /* 4. residual coding: warp 0 luma 16x16 (lanes 0..15), warp 1 Cb+Cr 8x8 (lanes 0..15) */
             if (warp == 0) {
                 int g = lane >> 4, r = lane & 15, y = y0 + r;
-                bool cbf = ks_tb_code<16>(&sm.tb[0], sm.scan + 64, g == 0, src.p[0] + (size_t)y * W + x0, &sm.predY[r * 16],
+                bool cbf = ks_tb_code<16>(&sm.tb[0], sm.scan + 64, nullptr, g == 0, src.p[0] + (size_t)y * W + x0, &sm.predY[r * 16],
                                           rec.p[0] + (size_t)y * W + x0, lv.p[0] + (size_t)y * W + x0, pp.qp, 1, pp.sign_hiding, lane);
                 if (lane == 0 && cbf) atomicOr(&sm.cbf, KS_F_CBF_Y);
             } else if (warp == 1) {
                 int g = lane >> 3, r = lane & 7, ci = g & 1, x = x0 >> 1, y = (y0 >> 1) + r;
-                bool cbf = ks_tb_code<8>(&sm.tb[1], sm.scan, g < 2, src.p[1 + ci] + (size_t)y * CW + x, &sm.predC[ci][r * 8],
+                bool cbf = ks_tb_code<8>(&sm.tb[1], sm.scan, nullptr, g < 2, src.p[1 + ci] + (size_t)y * CW + x, &sm.predC[ci][r * 8],
                                          rec.p[1 + ci] + (size_t)y * CW + x, lv.p[1 + ci] + (size_t)y * CW + x, pp.qpc, 1, pp.sign_hiding, lane);
                 if (r == 0 && g < 2 && cbf) atomicOr(&sm.cbf, ci ? KS_F_CBF_CR : KS_F_CBF_CB);
             }
