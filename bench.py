@@ -230,8 +230,8 @@ def main():
     S = 1.5 * W * H
     alg = {"me": 2.0 * W * H + 8.0 * W * H / 256, "recon_inter": 5.0 * S + 8.0 * W * H / 256, "recon_intra": 4.0 * S,
            "deblock": 2.0 * W * H, "sao": 3.0 * S, "pack": 2.0 * S + 0.1 * S}
-    dom = max((k for k in stage if stage[k][1] > 0), key=lambda k: stage[k][0])
-    # the dominant stage timed ALONE (one stream, nothing else on the GPU): that is the launch duration the roofline uses
+    # every stage timed ALONE (one stream, nothing else on the GPU): these are the launch durations the roofline uses.
+    # dominant stage = largest solo time per picture, weighted by how often the stage runs in a GOP shard.
     solo = encs[0]
     solo.set_profiling(True)
     torch.cuda.synchronize()
@@ -239,6 +239,9 @@ def main():
     torch.cuda.synchronize()
     solo_t = solo.stage_times()
     solo.set_profiling(False)
+    per_pic = {k: (v[0] / v[1] if v[1] else 0.0) * ((1.0 / IPER) if k == "recon_intra" else ((IPER - 1.0) / IPER if k in ("me", "recon_inter") else 1.0))
+               for k, v in solo_t.items()}
+    dom = max(per_pic, key=per_pic.get)
     avg_ms = solo_t[dom][0] / max(1, solo_t[dom][1])
     peak, peak_src = peaks()
     achieved = alg[dom] / (avg_ms / 1000.0) / 1e9
@@ -246,7 +249,10 @@ def main():
                 "peak_source": peak_src, "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg[dom],
                 "stage_ms_share": {k: v[0] / max(1e-9, sum(x[0] for x in stage.values())) for k, v in stage.items()},
                 "solo_stage_ms": {k: (v[0] / v[1] if v[1] else None) for k, v in solo_t.items()},
-                "note": "dominant stage = largest share of the timed region (CUDA-event intervals on each encoder stream, %d streams sharing the GPU); avg_launch_ms = the same stage timed alone on an idle GPU (24 pictures, one stream), peak = burst copy bandwidth" % streams}
+                "solo_ms_per_picture": per_pic,
+                "limiter": {"me": "issue slots (integer SAD/interpolation ALU), not HBM", "recon_inter": "issue slots + barriers (integer transforms), not HBM",
+                            "recon_intra": "dependency chain of the CTU wavefront", "sao": "shared-memory/ALU, then HBM", "deblock": "latency", "pack": "HBM"}[dom],
+                "note": "dominant stage = largest solo time per picture (GOP-weighted); avg_launch_ms = that stage timed alone on an idle GPU with CUDA events on its stream (24 pictures, one stream); peak = burst copy bandwidth. stage_ms_share = event intervals inside the timed region with %d streams sharing the GPU (includes co-scheduling waits)." % streams}
 
     # ---- cpu baseline (rank 0, N=1 only): the reference encoder on a bounded sample ----
     cpu = None
