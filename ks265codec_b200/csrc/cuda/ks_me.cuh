@@ -19,7 +19,8 @@
 
 struct KsWarpScratch {
     uint32_t win[KS_WIN_H][KS_WIN_WW];
-    int16_t  tmp[24][16];     /* raw horizontal 8-tap sums, rows -3..+19 */
+    int16_t  tmp[24][16];     /* raw horizontal 8-tap sums, rows -3..+19 (single-block interpolation, ks_interp16) */
+    int16_t  pl[2][24][16];   /* + two more planes of raw row sums shared by the sub-pel candidates of one cell (with tmp = plane 0) */
 };
 
 /* stage the window whose top-left luma sample is (wx0, wy0); wx0 % 4 == 0; coordinates clamp to the picture
@@ -197,6 +198,66 @@ __device__ __forceinline__ void ks_interp16(KsWarpScratch *sc, int bxw, int byw,
     o1 = (uint32_t)v[4] | ((uint32_t)v[5] << 8) | ((uint32_t)v[6] << 16) | ((uint32_t)v[7] << 24);
 }
 
+/* ---- shared intermediates for the sub-pel search (reference: subMeQpel_8Sad_* pick a variant "so H/V intermediate
+ * rows are shared").  A plane holds, for 24 window rows x 16 columns starting at (wxb, wyb), the raw
+ * horizontal 8-tap sums for fraction fx (14-bit, like interpLumaHor8to16_c) or sample<<6 for fx == 0
+ * (InterpolateCopy8to16_c).  Every candidate of the stage is then one vertical pass over a plane. ---- */
+__device__ __forceinline__ void ks_make_plane(int16_t (*pl)[16], const uint32_t (*win)[KS_WIN_WW], int wxb, int wyb, int fx, int lane)
+{
+    const int tlo = c_luma_taps_packed[fx][0], thi = c_luma_taps_packed[fx][1];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int u = lane + 32 * k;               /* 48 units: (row, 8-column group) */
+        if (u < 48) {
+            const int r = u >> 1, g = u & 1;
+            uint32_t n[4]; int h[8];
+            if (fx) {
+                ks_row16(win, wyb + r, wxb + 8 * g - 3, n);
+                ks_htaps8(n, tlo, thi, h);
+            } else {
+                const int wx = wxb + 8 * g;
+                const uint32_t *rr = win[wyb + r] + (wx >> 2);
+                const unsigned sh = (wx & 3) * 8;
+                const uint32_t a = __funnelshift_r(rr[0], rr[1], sh), b = __funnelshift_r(rr[1], rr[2], sh);
+#pragma unroll
+                for (int j = 0; j < 4; j++) { h[j] = (int)((a >> (8 * j)) & 255) << 6; h[4 + j] = (int)((b >> (8 * j)) & 255) << 6; }
+            }
+            uint32_t *d = reinterpret_cast<uint32_t *>(&pl[r][8 * g]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) d[j] = ((uint32_t)h[2 * j] & 0xffffu) | ((uint32_t)h[2 * j + 1] << 16);
+        }
+    }
+    __syncwarp();
+}
+/* lane's 8 predicted samples (row lane>>1, columns 8*(lane&1)..+7) from a plane: vertical 8-tap with fraction fy over
+ * plane rows roff+row .. roff+row+7 ((sum+2048)>>12, == interpLumaVer16to8_c), or the centre row rounded ((v+32)>>6) for fy == 0 */
+__device__ __forceinline__ void ks_plane_pred(const int16_t (*pl)[16], int roff, int fy, int lane, uint32_t &o0, uint32_t &o1)
+{
+    const int row = lane >> 1, half = lane & 1;
+    int v[8];
+    if (fy == 0) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(&pl[roff + 3 + row][8 * half]);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) { v[2 * j] = ks_clip8(((int)(short)(w[j] & 0xffffu) + 32) >> 6); v[2 * j + 1] = ks_clip8((((int)w[j] >> 16) + 32) >> 6); }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = 0;
+#pragma unroll 2
+        for (int t = 0; t < 8; t++) {
+            const int c = c_luma_taps[fy][t];
+            const uint4 q = *reinterpret_cast<const uint4 *>(&pl[roff + row + t][8 * half]);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) { v[2 * j] += c * (int)(short)(w[j] & 0xffffu); v[2 * j + 1] += c * ((int)w[j] >> 16); }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = ks_clip8((v[j] + 2048) >> 12);
+    }
+    o0 = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+    o1 = (uint32_t)v[4] | ((uint32_t)v[5] << 8) | ((uint32_t)v[6] << 16) | ((uint32_t)v[7] << 24);
+}
+
 /* window origin that centres integer offset (cx, cy) of the cell at (x0, y0) */
 __device__ __forceinline__ void ks_center_window(int x0, int y0, int cx, int cy, int &wx0, int &wy0)
 {
@@ -265,26 +326,50 @@ ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, const uint8_t *__
         if (bk < 0) break;
         bx += dx[bk]; by += dy[bk]; bc = lc;
     }
-    /* ---- half then quarter refinement, 8 neighbours each (reference: subMeSquare E@0x4aee80) ---- */
+    /* ---- half then quarter refinement, 8 neighbours each (reference: subMeSquare E@0x4aee80).  The candidates of a
+     *      stage share planes of raw horizontal sums: 2 planes + 2 vertical-only blocks for the half stage, 3 planes (one
+     *      per x offset) for the quarter stage; each candidate is then a single vertical pass + SAD. ---- */
     int mx = bx * 4, my = by * 4;
     if (pp.subpel > 0) {
         int bxw = x0 + bx - wx0, byw = y0 + by - wy0;
-        if (bxw < 4 || bxw > 27 || byw < 4 || byw > 20) {
+        if (bxw < 4 || bxw > 27 || byw < 4 || byw > 19) {
             ks_center_window(x0, y0, bx, by, wx0, wy0);
             ks_load_window(sc->win, refY, W, H, wx0, wy0, lane);
+            bxw = x0 + bx - wx0; byw = y0 + by - wy0;
         }
         const int sqx[8] = {-1, 0, 1, -1, 1, -1, 0, 1}, sqy[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
-        for (int step = 2; step >= 1; step--) {
-            if (pp.subpel < (step == 2 ? 1 : 2)) break;
+        int16_t (*P0)[16] = sc->tmp, (*P1)[16] = sc->pl[0], (*P2)[16] = sc->pl[1];
+        {   /* half-sample stage: planes for x-1/2 (P0) and x+1/2 (P2), rows -4..+19 of the integer position */
+            const int wyb = byw - 4;
+            ks_make_plane(P0, sc->win, bxw - 1, wyb, 2, lane);
+            ks_make_plane(P2, sc->win, bxw, wyb, 2, lane);
             int bk = -1, lc = bc;
+#pragma unroll 1
             for (int k = 0; k < 8; k++) {
-                int qx = mx + sqx[k] * step, qy = my + sqy[k] * step;
+                const int dx = sqx[k], dy = sqy[k], qx = mx + 2 * dx, qy = my + 2 * dy;
                 uint32_t o0, o1;
-                ks_interp16(sc, x0 + (qx >> 2) - wx0, y0 + (qy >> 2) - wy0, qx & 3, qy & 3, lane, o0, o1);
+                if (dx == 0) ks_interp16(sc, bxw, byw + (dy < 0 ? -1 : 0), 0, 2, lane, o0, o1);      /* vertical-only, straight from the samples */
+                else ks_plane_pred(dx < 0 ? P0 : P2, dy < 0 ? 0 : 1, dy ? 2 : 0, lane, o0, o1);
                 int c = (int)ks_warp_sum(__vsadu4(o0, s.x) + __vsadu4(o1, s.y)) + MVCOST(qx, qy);
                 if (c < lc) { lc = c; bk = k; }
             }
-            if (bk >= 0) { mx += sqx[bk] * step; my += sqy[bk] * step; bc = lc; }
+            if (bk >= 0) { mx += sqx[bk] * 2; my += sqy[bk] * 2; bc = lc; }
+        }
+        if (pp.subpel > 1) {   /* quarter-sample stage around (mx, my): one plane per x offset */
+            const int iym = (my - 1) >> 2, wyb = y0 + iym - wy0 - 3;
+            ks_make_plane(P0, sc->win, x0 + ((mx - 1) >> 2) - wx0, wyb, (mx - 1) & 3, lane);
+            ks_make_plane(P1, sc->win, x0 + (mx >> 2) - wx0, wyb, mx & 3, lane);
+            ks_make_plane(P2, sc->win, x0 + ((mx + 1) >> 2) - wx0, wyb, (mx + 1) & 3, lane);
+            int bk = -1, lc = bc;
+#pragma unroll 1
+            for (int k = 0; k < 8; k++) {
+                const int dx = sqx[k], dy = sqy[k], qx = mx + dx, qy = my + dy;
+                uint32_t o0, o1;
+                ks_plane_pred(dx < 0 ? P0 : (dx == 0 ? P1 : P2), (qy >> 2) - iym, qy & 3, lane, o0, o1);
+                int c = (int)ks_warp_sum(__vsadu4(o0, s.x) + __vsadu4(o1, s.y)) + MVCOST(qx, qy);
+                if (c < lc) { lc = c; bk = k; }
+            }
+            if (bk >= 0) { mx += sqx[bk]; my += sqy[bk]; bc = lc; }
         }
     }
 #undef MVCOST
