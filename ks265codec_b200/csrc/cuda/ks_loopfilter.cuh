@@ -153,7 +153,8 @@ void ks_launch_deblock(const KsPicParams &pp, KsPlanes rec, const ks_cell *cells
 #define KS_SAO_PITCH_C 40
 struct KsSaoSmem {
     uint8_t tile[3][66 * KS_SAO_PITCH_Y];  /* deblocked samples incl. 1-sample halo; chroma uses 34 x 40 */
-    int hist[KS_SAO_WARPS][3][52];         /* packed (sum<<12)|count: [0..19] EO class*5+cat, [20..51] BO band */
+    int hist[KS_SAO_WARPS][3][52];         /* packed (sum<<12)|count per warp: [20..51] BO band ([0..19] unused) */
+    int ph[20][KS_SAO_WARPS * KS_WARP];    /* per-THREAD EO histograms (bin-major: conflict-free, no atomics), packed the same way */
     int sum[3][52], cnt[3][52];
     int cost[3][48], off[3][48];           /* [0..15] EO class*4+(cat-1), [16..47] BO band */
     ks_sao_param par[3];
@@ -231,16 +232,16 @@ ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_s
         }
     }
     __syncthreads();
-    /* ---- statistics: runs of 4 samples per thread; EO categories accumulate in registers (16 packed counters),
-     *      BO bands in per-warp shared histograms with run aggregation ---- */
+    /* ---- statistics: runs of 4 samples per thread.  EO: every thread owns a private column of a bin-major shared
+     *      histogram (plain read-modify-write, conflict-free, no atomics; the reference's packed (d<<12)|1 accumulator);
+     *      BO: per-warp shared histograms with run aggregation. ---- */
     if (pp.sao) {
         for (int ci = 0; ci < 3; ci++) {
             const int sh = ci ? 1 : 0, PW = pp.W >> sh, PH = pp.H >> sh, x0 = (rx << 6) >> sh, y0 = (ry << 6) >> sh;
             const int bw = min(64 >> sh, PW - x0), bh = min(64 >> sh, PH - y0), pitch = ci ? KS_SAO_PITCH_C : KS_SAO_PITCH_Y, rl = 4 - sh;
             int *h = sm->hist[warp][ci];
-            int acc[16];
 #pragma unroll
-            for (int k = 0; k < 16; k++) acc[k] = 0;
+            for (int b = 0; b < 20; b++) sm->ph[b][tid] = 0;
             for (int i = tid; i < (bh << rl); i += blockDim.x) {
                 const int y = i >> rl, x = (i & ((1 << rl) - 1)) << 2;
                 if (x >= bw) continue;
@@ -257,25 +258,26 @@ ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_s
                     int cat[4];
                     ks_sao_cats(n, j, x0 + x + j == 0, x0 + x + j == PW - 1, top, bot, cat);
 #pragma unroll
-                    for (int k = 0; k < 4; k++)
-#pragma unroll
-                        for (int cc = 1; cc <= 4; cc++) acc[k * 4 + cc - 1] += cat[k] == cc ? v : 0;
+                    for (int k = 0; k < 4; k++) sm->ph[k * 5 + cat[k]][tid] += v;      /* bin cat 0 collects the rest and is ignored */
                 }
                 atomicAdd(&h[20 + cur_band], band_acc);
             }
+            __syncthreads();
+            /* reduce the 256 private columns: warp w owns bins w, w+8, w+16; decode before the cross-lane sum (count <= 4096) */
+            for (int b = warp; b < 20; b += KS_SAO_WARPS) {
+                int s_ = 0, n_ = 0;
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                int t = acc[k];
+                for (int i = 0; i < KS_SAO_WARPS; i++) { int v = sm->ph[b][lane + 32 * i]; int c = v & 4095; n_ += c; s_ += (v - c) >> 12; }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-                if (lane == 0) h[(k >> 2) * 5 + (k & 3) + 1] = t;         /* this warp's private slot: plain store */
+                for (int o = 16; o > 0; o >>= 1) { s_ += __shfl_xor_sync(0xffffffffu, s_, o); n_ += __shfl_xor_sync(0xffffffffu, n_, o); }
+                if (lane == 0) { sm->sum[ci][b] = s_; sm->cnt[ci][b] = n_; }
             }
+            __syncthreads();
         }
-        __syncthreads();
-        if (tid < 3 * 52) {
-            int ci = tid / 52, b = tid - ci * 52, s = 0, n = 0;
-            for (int w = 0; w < KS_SAO_WARPS; w++) { int v = sm->hist[w][ci][b]; int c = v & 4095; n += c; s += (v - c) >> 12; }
-            sm->sum[ci][b] = s; sm->cnt[ci][b] = n;
+        if (tid < 3 * 32) {
+            int ci = tid >> 5, b = 20 + (tid & 31), s_ = 0, n_ = 0;
+            for (int w = 0; w < KS_SAO_WARPS; w++) { int v = sm->hist[w][ci][b]; int c = v & 4095; n_ += c; s_ += (v - c) >> 12; }
+            sm->sum[ci][b] = s_; sm->cnt[ci][b] = n_;
         }
         __syncthreads();
         /* ---- per-bin offset RD (144 independent little problems) ---- */

@@ -404,6 +404,7 @@ struct KsIntraSmem {
     uint8_t  predY[16 * 16];
     uint8_t  predC[2][8 * 8];
     unsigned best_key[KS_RECON_WARPS];
+    uint8_t  mref[KS_RECON_WARPS][64];  /* per-warp extended main reference of the mode under test: index k+16, k = -16..32 */
     int      dc[3];
     int      best_mode;
     int      row;
@@ -464,20 +465,50 @@ ks_recon_intra_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, k
             __syncthreads();
             if (tid < 65) sm.fb[tid] = (tid == 0 || tid == 64) ? sm.nb[0][tid] : (uint8_t)((sm.nb[0][tid - 1] + 2 * sm.nb[0][tid] + sm.nb[0][tid + 1] + 2) >> 2);
             __syncthreads();
-            /* 2. mode decision by SAD + lambda*bits: warp w evaluates modes w, w+8, ... on all 256 samples */
+            /* 2. mode decision by SAD + lambda*bits: warp w evaluates modes w, w+8, ... on all 256 samples.
+             *    Angular modes first project the (possibly filtered) references onto one extended main-reference array
+             *    per mode (spec 8.4.4.2.6 ref[]), so a sample costs two shared loads + one interpolation. */
             {
                 unsigned best = 0xffffffffu;
                 const int px = lane & 15, py0 = lane >> 4;
                 uint8_t s[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++) s[j] = src.p[0][(size_t)(y0 + py0 + 2 * j) * W + x0 + px];
+                uint8_t *mref = sm.mref[warp];
+#pragma unroll 1
                 for (int m = warp; m < 35; m += KS_RECON_WARPS) {
                     int d1 = abs(m - 26), d2 = abs(m - 10);
                     bool filt = m != 1 && min(d1, d2) > 1;            /* intraHorVerDistThres[16] = 1 */
                     const uint8_t *p = filt ? sm.fb : sm.nb[0];
                     unsigned sad = 0;
+                    if (m < 2) {
 #pragma unroll
-                    for (int j = 0; j < 8; j++) sad += abs(ks_intra_sample(p, 16, 4, m, px, py0 + 2 * j, sm.dc[0], true) - (int)s[j]);
+                        for (int j = 0; j < 8; j++) sad += abs(ks_intra_sample(p, 16, 4, m, px, py0 + 2 * j, sm.dc[0], true) - (int)s[j]);
+                    } else {
+                        const int ang = c_intra_angle[m], inv = c_intra_inv_angle[m];
+                        const bool vert = m >= 18;
+                        __syncwarp();
+                        for (int e = lane; e < 49; e += 32) {           /* k = e - 16 in -16..32 */
+                            int k = e - 16, v;
+                            if (k >= 0) v = vert ? p[32 + k] : p[32 - k];
+                            else { int i2 = -1 + ((k * inv + 128) >> 8); i2 = min(max(i2, -1), 31); v = vert ? p[31 - i2] : p[33 + i2]; }
+                            mref[e] = (uint8_t)v;
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const int x = px, y = py0 + 2 * j, ii = vert ? x : y, jj = vert ? y : x;
+                            int v;
+                            if (ang == 0 && ii == 0)
+                                v = vert ? ks_clip8(p[33] + ((p[31 - jj] - p[32]) >> 1)) : ks_clip8(p[31] + ((p[33 + jj] - p[32]) >> 1));
+                            else {
+                                const int idx = ((jj + 1) * ang) >> 5, f = ((jj + 1) * ang) & 31;
+                                const int a = mref[16 + ii + idx + 1], b2 = mref[16 + ii + idx + 2];
+                                v = f ? ((32 - f) * a + f * b2 + 16) >> 5 : a;
+                            }
+                            sad += abs(v - (int)s[j]);
+                        }
+                    }
                     sad = ks_warp_sum(sad);
                     int bits = (m == 0 || m == 1 || m == 10 || m == 26) ? 3 : 6;
                     unsigned key = ((sad + ((pp.lambda_sad_q4 * bits) >> 4)) << 6) | (unsigned)m;
