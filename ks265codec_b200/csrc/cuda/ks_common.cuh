@@ -14,6 +14,7 @@ __constant__ int      c_luma_taps[4][8];
 __constant__ int      c_chroma_taps[8][4];
 __constant__ int      c_luma_taps_packed[4][2];   /* taps 0..3 / 4..7 as 4 x s8 (dp4a operand) */
 __constant__ int      c_chroma_taps_packed[8];
+__constant__ int      c_vtaps_pk[4][2][3];        /* vertical luma taps as s8 pairs for dp2a over row-pair planes: [fy][first-row parity][word] */
 __constant__ uint8_t  c_tc_table[54];
 __constant__ uint8_t  c_beta_table[52];
 __constant__ uint8_t  c_chroma_qp[58];
@@ -73,6 +74,19 @@ static void ks_upload_tables_impl()
         unsigned v = 0; for (int i = 0; i < 4; i++) v |= (unsigned)(lt[f][4 * h + i] & 255) << (8 * i); ltp[f][h] = (int)v; }
     for (int f = 0; f < 8; f++) { unsigned v = 0; for (int i = 0; i < 4; i++) v |= (unsigned)(ct[f][i] & 255) << (8 * i); ctp[f] = (int)v; }
     cudaMemcpyToSymbol(c_luma_taps_packed, ltp, sizeof(ltp));
+    {   /* even first row: pairs (c0,c1)(c2,c3)(c4,c5)(c6,c7)(0,0); odd: (0,c0)(c1,c2)(c3,c4)(c5,c6)(c7,0) */
+        int vt[4][2][3];
+        for (int f = 0; f < 4; f++) for (int par = 0; par < 2; par++) {
+            int seq[10];
+            for (int i = 0; i < 10; i++) { int t = par ? i - 1 : i; seq[i] = (t >= 0 && t < 8) ? lt[f][t] : 0; }
+            for (int w = 0; w < 3; w++) {
+                unsigned v = 0;
+                for (int b = 0; b < 4; b++) { int i = 4 * w + b; v |= (unsigned)((i < 10 ? seq[i] : 0) & 255) << (8 * b); }
+                vt[f][par][w] = (int)v;
+            }
+        }
+        cudaMemcpyToSymbol(c_vtaps_pk, vt, sizeof(vt));
+    }
     cudaMemcpyToSymbol(c_chroma_taps_packed, ctp, sizeof(ctp));
     static const uint8_t tc[54] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,1,1,1,1,1,1,1,1,1,2,2,2,2,3,3,3,3,4,4,4,5,5,6,6,7,8,9,10,11,13,14,16,18,20,22,24};
     static const uint8_t bt[52] = {0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,0,6,7,8,9,10,11,12,13,14,15,16,17,18,20,22,24,26,28,30,32,34,36,38,40,42,44,46,48,50,52,54,56,58,60,62,64};

@@ -20,7 +20,8 @@
 struct KsWarpScratch {
     uint32_t win[KS_WIN_H][KS_WIN_WW];
     int16_t  tmp[24][16];     /* raw horizontal 8-tap sums, rows -3..+19 (single-block interpolation, ks_interp16) */
-    int16_t  pl[2][24][16];   /* + two more planes of raw row sums shared by the sub-pel candidates of one cell (with tmp = plane 0) */
+    uint32_t pl[2][12][16];   /* + two more planes shared by the sub-pel candidates of one cell (tmp doubles as plane 0); plane layout:
+                                 [row pair][column] = rows (2k, 2k+1) packed lo/hi, so a vertical tap pair is ONE dp2a */
 };
 
 /* stage the window whose top-left luma sample is (wx0, wy0); wx0 % 4 == 0; coordinates clamp to the picture
@@ -59,6 +60,48 @@ __device__ __forceinline__ void ks_load_window(uint32_t (*win)[KS_WIN_WW], const
 #pragma unroll
             for (int b = 0; b < 4; b++) w |= (uint32_t)row[min(max(gx + b, 0), W - 1)] << (8 * b);
             (&win[0][0])[idx] = w;
+        }
+    }
+    __syncwarp();
+}
+
+/* compact window for motion COMPENSATION of one 16x16 block with a known vector: 23 rows x 7 words (28 bytes) starting at
+ * (wx0 % 4 == 0, wy0); the block's integer origin then sits at window (3..6, 3).  Same storage as the search window. */
+#define KS_MCWIN_ROWS 23
+#define KS_MCWIN_WORDS 7
+__device__ __forceinline__ void ks_load_window_mc(uint32_t (*win)[KS_WIN_WW], const uint8_t *__restrict__ ref, int W, int H,
+                                                  int wx0, int wy0, int lane)
+{
+    constexpr int NW = KS_MCWIN_ROWS * KS_MCWIN_WORDS, PER = (NW + KS_WARP - 1) / KS_WARP;
+    uint32_t v[PER];
+    unsigned border = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        int idx = lane + k * KS_WARP;
+        int r = idx / KS_MCWIN_WORDS, c = idx - r * KS_MCWIN_WORDS;
+        int gy = min(max(wy0 + r, 0), H - 1), gx = wx0 + 4 * c;
+        bool in = idx < NW && gx >= 0 && gx + 3 < W;
+        v[k] = in ? __ldg(reinterpret_cast<const uint32_t *>(ref + (size_t)gy * W + gx)) : 0u;
+        if (idx < NW && !in) border |= 1u << k;
+    }
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        int idx = lane + k * KS_WARP;
+        int r = idx / KS_MCWIN_WORDS, c = idx - r * KS_MCWIN_WORDS;
+        if (idx < NW) win[r][c] = v[k];
+    }
+    if (__any_sync(0xffffffffu, border != 0)) {
+#pragma unroll 1
+        for (int k = 0; k < PER; k++) {
+            if (!((border >> k) & 1)) continue;
+            int idx = lane + k * KS_WARP;
+            int r = idx / KS_MCWIN_WORDS, c = idx - r * KS_MCWIN_WORDS;
+            int gy = min(max(wy0 + r, 0), H - 1), gx = wx0 + 4 * c;
+            const uint8_t *row = ref + (size_t)gy * W;
+            uint32_t w = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) w |= (uint32_t)row[min(max(gx + b, 0), W - 1)] << (8 * b);
+            win[r][c] = w;
         }
     }
     __syncwarp();
@@ -201,8 +244,10 @@ __device__ __forceinline__ void ks_interp16(KsWarpScratch *sc, int bxw, int byw,
 /* ---- shared intermediates for the sub-pel search (reference: subMeQpel_8Sad_* pick a variant "so H/V intermediate
  * rows are shared").  A plane holds, for 24 window rows x 16 columns starting at (wxb, wyb), the raw
  * horizontal 8-tap sums for fraction fx (14-bit, like interpLumaHor8to16_c) or sample<<6 for fx == 0
- * (InterpolateCopy8to16_c).  Every candidate of the stage is then one vertical pass over a plane. ---- */
-__device__ __forceinline__ void ks_make_plane(int16_t (*pl)[16], const uint32_t (*win)[KS_WIN_WW], int wxb, int wyb, int fx, int lane)
+ * (InterpolateCopy8to16_c), rows interleaved in pairs: word [r>>1][c] = (row r even | row r odd << 16).
+ * Every candidate of the stage is then one vertical pass over a plane: 5 dp2a (s16 x s8 pairs) per sample. ---- */
+typedef uint32_t (*KsPlane)[16];
+__device__ __forceinline__ void ks_make_plane(KsPlane pl, const uint32_t (*win)[KS_WIN_WW], int wxb, int wyb, int fx, int lane)
 {
     const int tlo = c_luma_taps_packed[fx][0], thi = c_luma_taps_packed[fx][1];
 #pragma unroll
@@ -222,37 +267,43 @@ __device__ __forceinline__ void ks_make_plane(int16_t (*pl)[16], const uint32_t 
 #pragma unroll
                 for (int j = 0; j < 4; j++) { h[j] = (int)((a >> (8 * j)) & 255) << 6; h[4 + j] = (int)((b >> (8 * j)) & 255) << 6; }
             }
-            uint32_t *d = reinterpret_cast<uint32_t *>(&pl[r][8 * g]);
+            int16_t *d = reinterpret_cast<int16_t *>(&pl[r >> 1][8 * g]) + (r & 1);
 #pragma unroll
-            for (int j = 0; j < 4; j++) d[j] = ((uint32_t)h[2 * j] & 0xffffu) | ((uint32_t)h[2 * j + 1] << 16);
+            for (int j = 0; j < 8; j++) d[2 * j] = (int16_t)h[j];
         }
     }
     __syncwarp();
 }
+__device__ __forceinline__ int ks_dp2a_lo(int a, int b, int c) { int d; asm("dp2a.lo.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
+__device__ __forceinline__ int ks_dp2a_hi(int a, int b, int c) { int d; asm("dp2a.hi.s32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d; }
 /* lane's 8 predicted samples (row lane>>1, columns 8*(lane&1)..+7) from a plane: vertical 8-tap with fraction fy over
  * plane rows roff+row .. roff+row+7 ((sum+2048)>>12, == interpLumaVer16to8_c), or the centre row rounded ((v+32)>>6) for fy == 0 */
-__device__ __forceinline__ void ks_plane_pred(const int16_t (*pl)[16], int roff, int fy, int lane, uint32_t &o0, uint32_t &o1)
+__device__ __forceinline__ void ks_plane_pred(const KsPlane pl, int roff, int fy, int lane, uint32_t &o0, uint32_t &o1)
 {
     const int row = lane >> 1, half = lane & 1;
     int v[8];
     if (fy == 0) {
-        const uint4 q = *reinterpret_cast<const uint4 *>(&pl[roff + 3 + row][8 * half]);
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        const int R = roff + 3 + row;
+        const uint4 qa = *reinterpret_cast<const uint4 *>(&pl[R >> 1][8 * half]), qb = *reinterpret_cast<const uint4 *>(&pl[R >> 1][8 * half + 4]);
+        const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
-        for (int j = 0; j < 4; j++) { v[2 * j] = ks_clip8(((int)(short)(w[j] & 0xffffu) + 32) >> 6); v[2 * j + 1] = ks_clip8((((int)w[j] >> 16) + 32) >> 6); }
+        for (int j = 0; j < 8; j++) { int t = (R & 1) ? ((int)w[j] >> 16) : (int)(short)(w[j] & 0xffffu); v[j] = ks_clip8((t + 32) >> 6); }
     } else {
+        const int R0 = roff + row, par = R0 & 1;
+        const int k0 = c_vtaps_pk[fy][par][0], k1 = c_vtaps_pk[fy][par][1], k2 = c_vtaps_pk[fy][par][2];
 #pragma unroll
-        for (int j = 0; j < 8; j++) v[j] = 0;
-#pragma unroll 2
-        for (int t = 0; t < 8; t++) {
-            const int c = c_luma_taps[fy][t];
-            const uint4 q = *reinterpret_cast<const uint4 *>(&pl[roff + row + t][8 * half]);
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        for (int j = 0; j < 8; j++) v[j] = 2048;
 #pragma unroll
-            for (int j = 0; j < 4; j++) { v[2 * j] += c * (int)(short)(w[j] & 0xffffu); v[2 * j + 1] += c * ((int)w[j] >> 16); }
+        for (int i = 0; i < 5; i++) {
+            const int pr = min((R0 >> 1) + i, 11);      /* the 5th pair only matters for odd R0; clamp keeps the even case in bounds (its taps are 0) */
+            const uint4 qa = *reinterpret_cast<const uint4 *>(&pl[pr][8 * half]), qb = *reinterpret_cast<const uint4 *>(&pl[pr][8 * half + 4]);
+            const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+            const int kk = i < 2 ? k0 : (i < 4 ? k1 : k2);
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[j] = (i & 1) ? ks_dp2a_hi((int)w[j], kk, v[j]) : ks_dp2a_lo((int)w[j], kk, v[j]);
         }
 #pragma unroll
-        for (int j = 0; j < 8; j++) v[j] = ks_clip8((v[j] + 2048) >> 12);
+        for (int j = 0; j < 8; j++) v[j] = ks_clip8(v[j] >> 12);
     }
     o0 = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
     o1 = (uint32_t)v[4] | ((uint32_t)v[5] << 8) | ((uint32_t)v[6] << 16) | ((uint32_t)v[7] << 24);
@@ -338,7 +389,7 @@ ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, const uint8_t *__
             bxw = x0 + bx - wx0; byw = y0 + by - wy0;
         }
         const int sqx[8] = {-1, 0, 1, -1, 1, -1, 0, 1}, sqy[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
-        int16_t (*P0)[16] = sc->tmp, (*P1)[16] = sc->pl[0], (*P2)[16] = sc->pl[1];
+        KsPlane P0 = reinterpret_cast<KsPlane>(sc->tmp), P1 = sc->pl[0], P2 = sc->pl[1];
         {   /* half-sample stage: planes for x-1/2 (P0) and x+1/2 (P2), rows -4..+19 of the integer position */
             const int wyb = byw - 4;
             ks_make_plane(P0, sc->win, bxw - 1, wyb, 2, lane);

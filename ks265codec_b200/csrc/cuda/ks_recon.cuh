@@ -292,11 +292,10 @@ ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes ref, KsPlanes rec, 
         const int cx = k & 3, cy = k >> 2, x0 = X0 + (cx << 4), y0 = Y0 + (cy << 4);
         const int mvx = sm->mvx[k], mvy = sm->mvy[k];
         KsWarpScratch *sc = &sm->u.mc[warp];
-        int wx0, wy0;
-        ks_center_window(x0, y0, mvx >> 2, mvy >> 2, wx0, wy0);
-        ks_load_window(sc->win, ref.p[0], W, H, wx0, wy0, lane);
+        const int wx0 = (x0 + (mvx >> 2) - 3) & ~3, wy0 = y0 + (mvy >> 2) - 3;      /* only the 23 x 28 samples this block can touch */
+        ks_load_window_mc(sc->win, ref.p[0], W, H, wx0, wy0, lane);
         uint32_t o0, o1;
-        ks_interp16(sc, x0 + (mvx >> 2) - wx0, y0 + (mvy >> 2) - wy0, mvx & 3, mvy & 3, lane, o0, o1);
+        ks_interp16(sc, x0 + (mvx >> 2) - wx0, 3, mvx & 3, mvy & 3, lane, o0, o1);
         *reinterpret_cast<uint2 *>(&sm->predY[((cy << 4) + (lane >> 1)) * 64 + (cx << 4) + 8 * (lane & 1)]) = make_uint2(o0, o1);
 #pragma unroll 1
         for (int ci = 0; ci < 2; ci++)
