@@ -26,6 +26,7 @@ typedef struct ks265_config {
     int sao;                    /* -sao */
     int sign_hiding;
     int me_range, me_iters, subpel;
+    int satd;                   /* sub-pel cost metric: 0 SAD (ultrafast..veryfast), 1 SATD (fast..placebo), like the reference */
     int device;                 /* CUDA device ordinal */
     int psnr;                   /* compute per-plane SSE on the device */
 } ks265_config;

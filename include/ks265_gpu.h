@@ -37,6 +37,7 @@ typedef struct ks_gpu_cfg {
     int n_src_slots;    /* source pictures resident on the device (>= 2) */
     int n_rec_slots;    /* reconstructed/reference pictures resident on the device (>= 2) */
     int n_syn_slots;    /* pictures in flight between submit and finish (>= 2) */
+    int satd;           /* sub-pel cost = SATD (had_c) instead of SAD: reference `satdInter`, presets fast..placebo */
 } ks_gpu_cfg;
 
 typedef struct ks_pic_params {

@@ -32,7 +32,7 @@ class KsCtuSyn(C.Structure):
 
 class KsGpuCfg(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("me_range", "me_iters", "subpel", "sign_hiding", "sao", "strong_intra",
-                                       "n_src_slots", "n_rec_slots", "n_syn_slots")]
+                                       "n_src_slots", "n_rec_slots", "n_syn_slots", "satd")]
 
 
 class KsPicParams(C.Structure):
@@ -48,7 +48,7 @@ class KsPicOut(C.Structure):
 class Ks265Config(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("fps", C.c_double), ("preset", C.c_int), ("rc", C.c_int),
                 ("qp", C.c_int), ("iper", C.c_int), ("fixqp", C.c_int), ("sao", C.c_int), ("sign_hiding", C.c_int),
-                ("me_range", C.c_int), ("me_iters", C.c_int), ("subpel", C.c_int), ("device", C.c_int), ("psnr", C.c_int)]
+                ("me_range", C.c_int), ("me_iters", C.c_int), ("subpel", C.c_int), ("satd", C.c_int), ("device", C.c_int), ("psnr", C.c_int)]
 
 
 class Ks265GopStats(C.Structure):

@@ -208,7 +208,7 @@ static int fill_params(const ks_gpu_ctx *c, const ks_pic_params *p, KsPicParams 
     pp->W = c->W; pp->H = c->H; pp->cw = c->cw; pp->ch = c->ch; pp->ctw = c->ctw; pp->cth = c->cth;
     pp->slice_type = p->slice_type; pp->qp = p->qp; pp->qpc = k_chroma_qp[p->qp];
     pp->lambda_sad_q4 = k_lambda_sad_q4[p->qp]; pp->lambda_sse_q4 = k_lambda_sse_q4[p->qp];
-    pp->me_range = c->cfg.me_range; pp->me_iters = c->cfg.me_iters; pp->subpel = c->cfg.subpel;
+    pp->me_range = c->cfg.me_range; pp->me_iters = c->cfg.me_iters; pp->subpel = c->cfg.subpel; pp->satd = c->cfg.satd;
     pp->sign_hiding = c->cfg.sign_hiding; pp->sao = c->cfg.sao; pp->strong_intra = c->cfg.strong_intra;
     pp->beta_offset_div2 = p->beta_offset_div2; pp->tc_offset_div2 = p->tc_offset_div2;
     return 0;

@@ -17,7 +17,7 @@ struct KsPicParams {
     int ctw, cth;           /* 64x64 CTUs */
     int slice_type, qp, qpc;
     int lambda_sad_q4, lambda_sse_q4;
-    int me_range, me_iters, subpel;
+    int me_range, me_iters, subpel, satd;
     int sign_hiding, sao, strong_intra;
     int beta_offset_div2, tc_offset_div2;
 };

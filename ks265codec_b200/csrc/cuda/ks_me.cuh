@@ -389,6 +389,13 @@ ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, const uint8_t *__
             bxw = x0 + bx - wx0; byw = y0 + by - wy0;
         }
         const int sqx[8] = {-1, 0, 1, -1, 1, -1, 0, 1}, sqy[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+        const bool satd = pp.satd != 0;
+#define KS_SUBCOST(o0, o1) (satd ? ks_satd16(o0, o1, s.x, s.y, lane) : ks_warp_sum(__vsadu4(o0, s.x) + __vsadu4(o1, s.y)))
+        if (satd) {     /* the metric changes for the sub-pel stages: re-cost the integer winner with SATD (x264 does the same) */
+            uint32_t c0, c1;
+            ks_win_px8(sc->win, bxw, byw, lane, c0, c1);
+            bc = (int)ks_satd16(c0, c1, s.x, s.y, lane) + MVCOST(mx, my);
+        }
         KsPlane P0 = reinterpret_cast<KsPlane>(sc->tmp), P1 = sc->pl[0], P2 = sc->pl[1];
         {   /* half-sample stage: planes for x-1/2 (P0) and x+1/2 (P2), rows -4..+19 of the integer position */
             const int wyb = byw - 4;
@@ -401,7 +408,7 @@ ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, const uint8_t *__
                 uint32_t o0, o1;
                 if (dx == 0) ks_interp16(sc, bxw, byw + (dy < 0 ? -1 : 0), 0, 2, lane, o0, o1);      /* vertical-only, straight from the samples */
                 else ks_plane_pred(dx < 0 ? P0 : P2, dy < 0 ? 0 : 1, dy ? 2 : 0, lane, o0, o1);
-                int c = (int)ks_warp_sum(__vsadu4(o0, s.x) + __vsadu4(o1, s.y)) + MVCOST(qx, qy);
+                int c = (int)KS_SUBCOST(o0, o1) + MVCOST(qx, qy);
                 if (c < lc) { lc = c; bk = k; }
             }
             if (bk >= 0) { mx += sqx[bk] * 2; my += sqy[bk] * 2; bc = lc; }
@@ -417,11 +424,12 @@ ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, const uint8_t *__
                 const int dx = sqx[k], dy = sqy[k], qx = mx + dx, qy = my + dy;
                 uint32_t o0, o1;
                 ks_plane_pred(dx < 0 ? P0 : (dx == 0 ? P1 : P2), (qy >> 2) - iym, qy & 3, lane, o0, o1);
-                int c = (int)ks_warp_sum(__vsadu4(o0, s.x) + __vsadu4(o1, s.y)) + MVCOST(qx, qy);
+                int c = (int)KS_SUBCOST(o0, o1) + MVCOST(qx, qy);
                 if (c < lc) { lc = c; bk = k; }
             }
             if (bk >= 0) { mx += sqx[bk]; my += sqy[bk]; bc = lc; }
         }
+#undef KS_SUBCOST
     }
 #undef MVCOST
     if (lane == 0) {

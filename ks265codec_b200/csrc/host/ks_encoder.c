@@ -35,6 +35,7 @@ int ks265_config_default_preset(ks265_config *cfg, const char *preset)
     cfg->sao = 1; cfg->sign_hiding = 1; cfg->me_range = 64;
     cfg->me_iters = p == 0 ? 8 : (p == 1 ? 12 : (p == 2 ? 16 : 32));
     cfg->subpel = p == 0 ? 1 : 2;
+    cfg->satd = p >= 3;
     return 0;
 }
 
@@ -46,7 +47,7 @@ ks265_encoder *ks265_encoder_open(const ks265_config *cfg, int *err)
     enc->cfg = *cfg;
     if (cfg->rc != 0) { fprintf(stderr, "ks265: only -rc 0 (fixed QP) is implemented on the device path\n"); if (err) *err = -22; free(enc); return NULL; }
     ks_gpu_cfg g; memset(&g, 0, sizeof(g));
-    g.me_range = cfg->me_range; g.me_iters = cfg->me_iters; g.subpel = cfg->subpel; g.sign_hiding = cfg->sign_hiding; g.sao = cfg->sao;
+    g.me_range = cfg->me_range; g.me_iters = cfg->me_iters; g.subpel = cfg->subpel; g.sign_hiding = cfg->sign_hiding; g.sao = cfg->sao; g.satd = cfg->satd;
     g.strong_intra = 1; g.n_src_slots = 3; g.n_rec_slots = 2; g.n_syn_slots = 2;
     enc->gpu = ks_gpu_open(cfg->device, cfg->width, cfg->height, &g, &e);
     if (!enc->gpu) { if (err) *err = e; free(enc); return NULL; }

@@ -10,7 +10,7 @@
 typedef struct ora_seq_cfg {
     int width, height;        /* display size */
     int nframes, qp, iper, fixqp;
-    int me_range, me_iters, subpel, sign_hiding, sao, max_merge_cand;
+    int me_range, me_iters, subpel, sign_hiding, sao, max_merge_cand, satd;
 } ora_seq_cfg;
 
 static void store_cropped(const ora_pic *p, int w, int h, uint8_t *dst)
@@ -26,7 +26,7 @@ static void store_cropped(const ora_pic *p, int w, int h, uint8_t *dst)
 long ora_encode_sequence(const ora_seq_cfg *sc, const uint8_t *yuv, uint8_t *bs, size_t bs_cap, uint8_t *recon_out)
 {
     int W = (sc->width + 15) & ~15, H = (sc->height + 15) & ~15;
-    ora_cfg cfg = {W, H, sc->me_range, sc->me_iters, sc->subpel, sc->sign_hiding, sc->sao, 1};
+    ora_cfg cfg = {W, H, sc->me_range, sc->me_iters, sc->subpel, sc->sign_hiding, sc->sao, 1, sc->satd};
     ks_stream_params sp; memset(&sp, 0, sizeof(sp));
     sp.disp_width = sc->width; sp.disp_height = sc->height; sp.width = W; sp.height = H; sp.fps_num = 30; sp.fps_den = 1;
     sp.sign_hiding = sc->sign_hiding; sp.sao = sc->sao; sp.max_merge_cand = sc->max_merge_cand;

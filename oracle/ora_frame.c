@@ -194,6 +194,7 @@ static void me_cell(const ora_cfg *cfg, int lam, const ora_plane *src, const ora
         bx += dia_dx[bk]; by += dia_dy[bk]; bc = lc;
     }
     int mx = bx * 4, my = by * 4;
+    if (cfg->satd && cfg->subpel > 0) bc = (int)ora_satd(s, r0 + by * rs + bx, ss, rs, 16, 16) + MVCOST(mx, my);
     for (int step = 2; step >= 1; step--) {
         if (cfg->subpel < (step == 2 ? 1 : 2)) break;
         int bk = -1, lc = bc;
@@ -201,7 +202,7 @@ static void me_cell(const ora_cfg *cfg, int lam, const ora_plane *src, const ora
             int qx = mx + sq_dx[k] * step, qy = my + sq_dy[k] * step;
             uint8_t pred[256];
             ora_mc_luma(pred, 16, r0, rs, 16, 16, qx, qy);
-            int c = (int)ora_sad(s, pred, ss, 16, 16, 16) + MVCOST(qx, qy);
+            int c = (int)(cfg->satd ? ora_satd(s, pred, ss, 16, 16, 16) : ora_sad(s, pred, ss, 16, 16, 16)) + MVCOST(qx, qy);
             if (c < lc) { lc = c; bk = k; }
         }
         if (bk >= 0) { mx += sq_dx[bk] * step; my += sq_dy[bk] * step; bc = lc; }

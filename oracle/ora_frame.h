@@ -26,6 +26,7 @@ typedef struct ora_cfg {
     int sign_hiding;
     int sao;
     int strong_intra;
+    int satd;               /* sub-pel cost: SATD (had_c) instead of SAD */
 } ora_cfg;
 
 typedef struct ora_plane { uint8_t *base, *p; int stride, w, h; } ora_plane;

@@ -23,11 +23,11 @@ DEC = os.path.join(ROOT, "oracle", "_ref", "appdecoder")
 
 
 class OraCfg(C.Structure):
-    _fields_ = [(n, C.c_int) for n in ("width", "height", "me_range", "me_iters", "subpel", "sign_hiding", "sao", "strong_intra")]
+    _fields_ = [(n, C.c_int) for n in ("width", "height", "me_range", "me_iters", "subpel", "sign_hiding", "sao", "strong_intra", "satd")]
 
 
 class SeqCfg(C.Structure):
-    _fields_ = [(n, C.c_int) for n in "width height nframes qp iper fixqp me_range me_iters subpel sign_hiding sao max_merge_cand".split()]
+    _fields_ = [(n, C.c_int) for n in "width height nframes qp iper fixqp me_range me_iters subpel sign_hiding sao max_merge_cand satd".split()]
 
 
 def first_diff(a, b, what, shape=None):
@@ -40,10 +40,10 @@ def first_diff(a, b, what, shape=None):
         pytest.fail("%s: %d mismatches, first at %s: gpu=%s oracle=%s" % (what, d.size, where, a[loc], b[loc]))
 
 
-def gpu_cfg(subpel=2, sbh=1, sao=1, iters=16):
+def gpu_cfg(subpel=2, sbh=1, sao=1, iters=16, satd=0):
     g = ks.KsGpuCfg()
     g.me_range, g.me_iters, g.subpel, g.sign_hiding, g.sao, g.strong_intra = 64, iters, subpel, sbh, sao, 1
-    g.n_src_slots, g.n_rec_slots, g.n_syn_slots = 3, 2, 2
+    g.n_src_slots, g.n_rec_slots, g.n_syn_slots, g.satd = 3, 2, 2, satd
     return g
 
 
@@ -146,14 +146,14 @@ def run_oracle_picture(cfg, slice_type, qp, boff, toff, src, ref, prev_cells):
     return o
 
 
-@pytest.mark.parametrize("w,h,qp,sbh,sao,subpel", [(192, 112, 32, 1, 1, 2), (200, 120, 27, 1, 1, 2), (320, 240, 24, 0, 0, 1), (256, 128, 37, 1, 1, 0)])
-def test_picture_stages_match_oracle(w, h, qp, sbh, sao, subpel):
+@pytest.mark.parametrize("w,h,qp,sbh,sao,subpel,satd", [(192, 112, 32, 1, 1, 2, 0), (200, 120, 27, 1, 1, 2, 0), (320, 240, 24, 0, 0, 1, 0), (256, 128, 37, 1, 1, 0, 0), (272, 144, 29, 1, 1, 2, 1)])
+def test_picture_stages_match_oracle(w, h, qp, sbh, sao, subpel, satd):
     """I picture then 3 P pictures: every stage output of the device (ME field, pre-filter recon, dense levels, final
     recon after deblock+SAO, SAO parameters, CG bitmaps, packed level pool) equals the CPU model."""
     L = ks.lib()
     nfr = 4
     yuv = np.frombuffer(gen_yuv.make(w, h, nfr, seed=7), np.uint8)
-    g = gpu_cfg(subpel, sbh, sao)
+    g = gpu_cfg(subpel, sbh, sao, satd=satd)
     err = C.c_int(0)
     ctx = L.ks_gpu_open(0, w, h, C.byref(g), C.byref(err))
     assert ctx, "ks_gpu_open failed: %d" % err.value
@@ -162,7 +162,7 @@ def test_picture_stages_match_oracle(w, h, qp, sbh, sao, subpel):
         L.ks_gpu_coded_size(ctx, C.byref(cw_), C.byref(ch_))
         W, H = cw_.value, ch_.value
         assert (W, H) == ((w + 15) & ~15, (h + 15) & ~15)
-        cfg = OraCfg(W, H, 64, 16, subpel, sbh, sao, 1)
+        cfg = OraCfg(W, H, 64, 16, subpel, sbh, sao, 1, satd)
         fsz, dsz = W * H * 3 // 2, w * h * 3 // 2
         ncell, nctu = (W >> 4) * (H >> 4), ((W + 63) >> 6) * ((H + 63) >> 6)
         ref_fin = None; prev_cells = None
@@ -217,10 +217,10 @@ def test_picture_stages_match_oracle(w, h, qp, sbh, sao, subpel):
 
 
 # ---------------------------------------------------------------------------------------- whole encoder
-def oracle_encode(yuv, w, h, n, qp, iper, subpel=2, sbh=1, sao=1, iters=16):
+def oracle_encode(yuv, w, h, n, qp, iper, subpel=2, sbh=1, sao=1, iters=16, satd=0):
     O = oracle()
     O.ora_encode_sequence.restype = C.c_long
-    cfg = SeqCfg(w, h, n, qp, iper, 0, 64, iters, subpel, sbh, sao, 3)
+    cfg = SeqCfg(w, h, n, qp, iper, 0, 64, iters, subpel, sbh, sao, 3, satd)
     bs = np.zeros(w * h * 3 * n + 100000, np.uint8); rec = np.zeros(w * h * 3 // 2 * n, np.uint8)
     nb = O.ora_encode_sequence(C.byref(cfg), ptr(yuv), ptr(bs), C.c_size_t(bs.size), ptr(rec))
     assert nb > 0
@@ -238,7 +238,7 @@ def decode_with_reference(bs, nbytes_expected):
         return np.fromfile(o, np.uint8)
 
 
-@pytest.mark.parametrize("w,h,n,qp,preset", [(192, 112, 5, 32, "veryfast"), (416, 240, 6, 27, "veryfast"), (200, 120, 4, 30, "superfast"), (1280, 720, 5, 32, "superfast")])
+@pytest.mark.parametrize("w,h,n,qp,preset", [(192, 112, 5, 32, "veryfast"), (416, 240, 6, 27, "veryfast"), (200, 120, 4, 30, "superfast"), (1280, 720, 5, 32, "superfast"), (352, 288, 5, 28, "fast"), (1920, 1080, 3, 27, "veryfast")])
 def test_encoder_bitstream_equals_oracle_and_decodes(w, h, n, qp, preset):
     """ks265_encoder_encode_gop: (1) Annex-B bytes == CPU model's bytes, (2) recon == model recon,
     (3) the reference decoder's output of OUR stream == our recon (the vendor's own -hm style self-test)."""
@@ -246,7 +246,7 @@ def test_encoder_bitstream_equals_oracle_and_decodes(w, h, n, qp, preset):
     cfg = ks.default_config(w, h, preset=preset, qp=qp, iper=n, psnr=1)
     with ks.Encoder(cfg) as e:
         bs, rec, st = e.encode_gop(yuv, want_recon=True)
-    obs, orec = oracle_encode(yuv, w, h, n, qp, n, subpel=cfg.subpel, sbh=cfg.sign_hiding, sao=cfg.sao, iters=cfg.me_iters)
+    obs, orec = oracle_encode(yuv, w, h, n, qp, n, subpel=cfg.subpel, sbh=cfg.sign_hiding, sao=cfg.sao, iters=cfg.me_iters, satd=cfg.satd)
     first_diff(rec, orec, "recon vs oracle")
     assert bytes(bs) == bytes(obs), "bitstream differs from the CPU model (%d vs %d bytes)" % (bs.size, obs.size)
     dec = decode_with_reference(bs, rec.size)
