@@ -394,168 +394,195 @@ __device__ __forceinline__ int ks_intra_sample(const uint8_t *p, int n, int log2
     return ((32 - f) * a + f * refv(k1) + 16) >> 5;
 }
 
+#define KS_INTRA_WARPS 16
 struct KsIntraSmem {
     KsTbScratch tb[2];
     uint16_t scan[64 + 256 + 1024];
     uint8_t  nb[3][72];          /* substituted reference samples: luma 65, chroma 33 */
+    uint8_t  raw[3][72];         /* as loaded (before substitution) */
     uint8_t  fb[72];             /* [1 2 1]-filtered luma references */
     uint8_t  av[3][72];
     uint8_t  predY[16 * 16];
     uint8_t  predC[2][8 * 8];
-    unsigned best_key[KS_RECON_WARPS];
-    uint8_t  mref[KS_RECON_WARPS][64];  /* per-warp extended main reference of the mode under test: index k+16, k = -16..32 */
+    uint8_t  mref[KS_INTRA_WARPS][64];  /* per-warp extended main reference of the mode under test: index k+16, k = -16..32 */
+    unsigned best_key;
     int      dc[3];
-    int      best_mode;
-    int      row;
+    int      ticket;
     unsigned cbf;
 };
 
-__global__ void __launch_bounds__(KS_RECON_WARPS * KS_WARP)
+/* reference-sample substitution (spec 8.4.4.2.2) for one component by one warp: every entry takes the nearest available
+ * entry at or before it in scan order (bottom-left -> corner -> top-right), leading unavailable entries take the first
+ * available one, 128 if nothing is available.  Also the DC value.  tot = 65 (luma 16x16) or 33 (chroma 8x8). */
+__device__ __forceinline__ void ks_intra_substitute(const uint8_t *raw, const uint8_t *av, uint8_t *nb, int tot, int n, int *dc_out, int lane)
+{
+    const unsigned m0 = __ballot_sync(0xffffffffu, lane < tot && av[lane]);
+    const unsigned m1 = __ballot_sync(0xffffffffu, 32 + lane < tot && av[32 + lane]);
+    const unsigned m2 = __ballot_sync(0xffffffffu, 64 + lane < tot && av[64 + lane]);
+    const int first = m0 ? __ffs(m0) - 1 : (m1 ? 32 + __ffs(m1) - 1 : (m2 ? 64 + __ffs(m2) - 1 : -1));
+    int dc = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int i = lane + 32 * k;
+        if (i < tot) {
+            const unsigned own = k == 0 ? m0 : (k == 1 ? m1 : m2), cand = own & (0xffffffffu >> (31 - lane));
+            int j;
+            if (cand) j = 32 * k + 31 - __clz(cand);
+            else if (k >= 1 && (k == 2 ? m1 : m0)) { unsigned w = k == 2 ? m1 : m0; j = 32 * (k - 1) + 31 - __clz(w); }
+            else if (k == 2 && m0) j = 31 - __clz(m0);
+            else j = first;
+            const int v = j < 0 ? 128 : raw[j];
+            nb[i] = (uint8_t)v;
+            if ((i >= n && i < 2 * n) || (i > 2 * n && i <= 3 * n)) dc += v;       /* left[0..n) and top[0..n) */
+        }
+    }
+    dc = (int)ks_warp_sum((unsigned)dc);
+    if (lane == 0) *dc_out = (dc + n) >> (n == 16 ? 5 : 4);
+    __syncwarp();
+}
+
+/* I pictures.  The block order inside a CTU (z-scan) and the availability rules are normative, so the parallelism is the
+ * dependency DAG itself: two CTAs per CTU row take alternate CTUs (CTU c+1 may start once CTU c finished its first 8 blocks),
+ * rows follow each other with a one-CTU lag, all inside ONE launch.  Progress = blocks finished per CTU, published in HBM;
+ * CTAs take (row, parity) tickets in start order so a CTA only ever waits on work that is already running or done. */
+__global__ void __launch_bounds__(KS_INTRA_WARPS * KS_WARP, 1)
 ks_recon_intra_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells, int *sync_ws)
 {
     __shared__ __align__(16) KsIntraSmem sm;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int W = pp.W, H = pp.H, CW = W >> 1;
-    int *ticket = sync_ws, *progress = sync_ws + 1;
+    int *ticket = sync_ws, *progress = sync_ws + 1;              /* progress[cty * ctw + ctx] = blocks done (0..16) */
     ks_load_scans(sm.scan, tid, blockDim.x);
-    if (tid == 0) sm.row = atomicAdd(ticket, 1);         /* rows are taken in start order: a row only ever waits on rows already running */
+    if (tid == 0) sm.ticket = atomicAdd(ticket, 1);
     __syncthreads();
-    const int cty = sm.row;
+    const int cty = sm.ticket >> 1, par = sm.ticket & 1;
     if (cty >= pp.cth) return;
-    for (int ctx = 0; ctx < pp.ctw; ctx++) {
-        if (cty > 0) {
-            if (tid == 0) {
-                int need = min(ctx + 2, pp.ctw);
-                while (atomicAdd(&progress[cty - 1], 0) < need) __nanosleep(200);
-                __threadfence();
-            }
-            __syncthreads();
-        }
+    for (int ctx = par; ctx < pp.ctw; ctx += 2) {
         for (int z = 0; z < 16; z++) {
             const int cx = (z & 1) | ((z >> 1) & 2), cy = ((z >> 1) & 1) | ((z >> 2) & 2);
             const int x0 = (ctx << 6) + (cx << 4), y0 = (cty << 6) + (cy << 4);
-            if (x0 >= W || y0 >= H) continue;
-            /* 1. reference samples with availability (8.4.4.2.2); neighbours come from the pre-filter reconstruction.
-             *    __ldcg: other CTAs wrote these lines, bypass the (non-coherent) L1 */
-            for (int idx = tid; idx < 65 + 33 + 33; idx += blockDim.x) {
-                int ci = idx < 65 ? 0 : (idx < 98 ? 1 : 2), i = idx - (ci == 0 ? 0 : (ci == 1 ? 65 : 98));
-                int n = ci ? 8 : 16, sh = ci ? 1 : 0, bx = x0 >> sh, by = y0 >> sh, xn, yn;
-                if (i < 2 * n) { xn = bx - 1; yn = by + 2 * n - 1 - i; }
-                else if (i == 2 * n) { xn = bx - 1; yn = by - 1; }
-                else { xn = bx + i - 2 * n - 1; yn = by - 1; }
-                bool a = ks_avail(W, H, pp.ctw, x0, y0, xn << sh, yn << sh);
-                sm.av[ci][i] = a;
-                sm.nb[ci][i] = a ? __ldcg(rec.p[ci] + (size_t)yn * (W >> sh) + xn) : 0;
+            const bool inside = x0 < W && y0 < H;
+            /* 0. wait for the blocks this one reads (see the kernel comment); skipped (outside) blocks still publish progress */
+            if (tid == 0 && inside) {
+                const int need_left = z == 0 ? 8 : (z == 2 ? 14 : ((z == 8 || z == 10) ? 16 : 0));
+                const int need_up = (cy == 0) ? 16 : 0, need_ur = (z == 5) ? 11 : 0;
+                if (need_left && ctx > 0) while (atomicAdd(&progress[cty * pp.ctw + ctx - 1], 0) < need_left) __nanosleep(100);
+                if (need_up && cty > 0) while (atomicAdd(&progress[(cty - 1) * pp.ctw + ctx], 0) < need_up) __nanosleep(100);
+                if (need_ur && cty > 0 && ctx + 1 < pp.ctw) while (atomicAdd(&progress[(cty - 1) * pp.ctw + ctx + 1], 0) < need_ur) __nanosleep(100);
+                __threadfence();
             }
             __syncthreads();
-            if (lane == 0 && warp < 3) {                 /* substitution: one thread per component */
-                int ci = warp, tot = ci ? 33 : 65; uint8_t *nb = sm.nb[ci]; const uint8_t *av = sm.av[ci];
-                int any = 0;
-                for (int i = 0; i < tot; i++) any |= av[i];
-                if (!any) for (int i = 0; i < tot; i++) nb[i] = 128;
-                else {
-                    if (!av[0]) { int i = 1; while (!av[i]) i++; nb[0] = nb[i]; }
-                    for (int i = 1; i < tot; i++) if (!av[i]) nb[i] = nb[i - 1];
+            if (inside) {
+                /* 1. reference samples with availability (8.4.4.2.2); neighbours come from the pre-filter reconstruction.
+                 *    __ldcg: other CTAs wrote these lines, bypass the (non-coherent) L1 */
+                if (tid < 65 + 33 + 33) {
+                    int idx = tid;
+                    int ci = idx < 65 ? 0 : (idx < 98 ? 1 : 2), i = idx - (ci == 0 ? 0 : (ci == 1 ? 65 : 98));
+                    int n = ci ? 8 : 16, sh = ci ? 1 : 0, bx = x0 >> sh, by = y0 >> sh, xn, yn;
+                    if (i < 2 * n) { xn = bx - 1; yn = by + 2 * n - 1 - i; }
+                    else if (i == 2 * n) { xn = bx - 1; yn = by - 1; }
+                    else { xn = bx + i - 2 * n - 1; yn = by - 1; }
+                    bool a = ks_avail(W, H, pp.ctw, x0, y0, xn << sh, yn << sh);
+                    sm.av[ci][i] = a;
+                    sm.raw[ci][i] = a ? __ldcg(rec.p[ci] + (size_t)yn * (W >> sh) + xn) : 0;
                 }
-                int n = ci ? 8 : 16, s = n;
-                for (int i = 0; i < n; i++) s += nb[2 * n + 1 + i] + nb[2 * n - 1 - i];
-                sm.dc[ci] = s >> (ci ? 4 : 5);
-            }
-            __syncthreads();
-            if (tid < 65) sm.fb[tid] = (tid == 0 || tid == 64) ? sm.nb[0][tid] : (uint8_t)((sm.nb[0][tid - 1] + 2 * sm.nb[0][tid] + sm.nb[0][tid + 1] + 2) >> 2);
-            __syncthreads();
-            /* 2. mode decision by SAD + lambda*bits: warp w evaluates modes w, w+8, ... on all 256 samples.
-             *    Angular modes first project the (possibly filtered) references onto one extended main-reference array
-             *    per mode (spec 8.4.4.2.6 ref[]), so a sample costs two shared loads + one interpolation. */
-            {
-                unsigned best = 0xffffffffu;
-                const int px = lane & 15, py0 = lane >> 4;
-                uint8_t s[8];
+                if (tid == 255) { sm.best_key = 0xffffffffu; sm.cbf = 0; }
+                __syncthreads();
+                if (warp < 3) {
+                    ks_intra_substitute(sm.raw[warp], sm.av[warp], sm.nb[warp], warp ? 33 : 65, warp ? 8 : 16, &sm.dc[warp], lane);
+                    if (warp == 0)
+                        for (int i = lane; i < 65; i += 32)
+                            sm.fb[i] = (i == 0 || i == 64) ? sm.nb[0][i] : (uint8_t)((sm.nb[0][i - 1] + 2 * sm.nb[0][i] + sm.nb[0][i + 1] + 2) >> 2);
+                }
+                __syncthreads();
+                /* 2. mode decision by SAD + lambda*bits: warp w evaluates modes w, w+16, w+32 on all 256 samples.
+                 *    Angular modes first project the (possibly filtered) references onto one extended main-reference array
+                 *    per mode (spec 8.4.4.2.6 ref[]), so a sample costs two shared loads + one interpolation. */
+                {
+                    unsigned best = 0xffffffffu;
+                    const int px = lane & 15, py0 = lane >> 4;
+                    uint8_t s[8];
 #pragma unroll
-                for (int j = 0; j < 8; j++) s[j] = src.p[0][(size_t)(y0 + py0 + 2 * j) * W + x0 + px];
-                uint8_t *mref = sm.mref[warp];
+                    for (int j = 0; j < 8; j++) s[j] = src.p[0][(size_t)(y0 + py0 + 2 * j) * W + x0 + px];
+                    uint8_t *mref = sm.mref[warp];
 #pragma unroll 1
-                for (int m = warp; m < 35; m += KS_RECON_WARPS) {
-                    int d1 = abs(m - 26), d2 = abs(m - 10);
-                    bool filt = m != 1 && min(d1, d2) > 1;            /* intraHorVerDistThres[16] = 1 */
-                    const uint8_t *p = filt ? sm.fb : sm.nb[0];
-                    unsigned sad = 0;
-                    if (m < 2) {
+                    for (int m = warp; m < 35; m += KS_INTRA_WARPS) {
+                        int d1 = abs(m - 26), d2 = abs(m - 10);
+                        bool filt = m != 1 && min(d1, d2) > 1;            /* intraHorVerDistThres[16] = 1 */
+                        const uint8_t *p = filt ? sm.fb : sm.nb[0];
+                        unsigned sad = 0;
+                        if (m < 2) {
 #pragma unroll
-                        for (int j = 0; j < 8; j++) sad += abs(ks_intra_sample(p, 16, 4, m, px, py0 + 2 * j, sm.dc[0], true) - (int)s[j]);
-                    } else {
-                        const int ang = c_intra_angle[m], inv = c_intra_inv_angle[m];
-                        const bool vert = m >= 18;
-                        __syncwarp();
-                        for (int e = lane; e < 49; e += 32) {           /* k = e - 16 in -16..32 */
-                            int k = e - 16, v;
-                            if (k >= 0) v = vert ? p[32 + k] : p[32 - k];
-                            else { int i2 = -1 + ((k * inv + 128) >> 8); i2 = min(max(i2, -1), 31); v = vert ? p[31 - i2] : p[33 + i2]; }
-                            mref[e] = (uint8_t)v;
-                        }
-                        __syncwarp();
-#pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            const int x = px, y = py0 + 2 * j, ii = vert ? x : y, jj = vert ? y : x;
-                            int v;
-                            if (ang == 0 && ii == 0)
-                                v = vert ? ks_clip8(p[33] + ((p[31 - jj] - p[32]) >> 1)) : ks_clip8(p[31] + ((p[33 + jj] - p[32]) >> 1));
-                            else {
-                                const int idx = ((jj + 1) * ang) >> 5, f = ((jj + 1) * ang) & 31;
-                                const int a = mref[16 + ii + idx + 1], b2 = mref[16 + ii + idx + 2];
-                                v = f ? ((32 - f) * a + f * b2 + 16) >> 5 : a;
+                            for (int j = 0; j < 8; j++) sad += abs(ks_intra_sample(p, 16, 4, m, px, py0 + 2 * j, sm.dc[0], true) - (int)s[j]);
+                        } else {
+                            const int ang = c_intra_angle[m], inv = c_intra_inv_angle[m];
+                            const bool vert = m >= 18;
+                            __syncwarp();
+                            for (int e = lane; e < 49; e += 32) {           /* k = e - 16 in -16..32 */
+                                int k = e - 16, v;
+                                if (k >= 0) v = vert ? p[32 + k] : p[32 - k];
+                                else { int i2 = -1 + ((k * inv + 128) >> 8); i2 = min(max(i2, -1), 31); v = vert ? p[31 - i2] : p[33 + i2]; }
+                                mref[e] = (uint8_t)v;
                             }
-                            sad += abs(v - (int)s[j]);
+                            __syncwarp();
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const int x = px, y = py0 + 2 * j, ii = vert ? x : y, jj = vert ? y : x;
+                                int v;
+                                if (ang == 0 && ii == 0)
+                                    v = vert ? ks_clip8(p[33] + ((p[31 - jj] - p[32]) >> 1)) : ks_clip8(p[31] + ((p[33 + jj] - p[32]) >> 1));
+                                else {
+                                    const int idx = ((jj + 1) * ang) >> 5, f = ((jj + 1) * ang) & 31;
+                                    const int a = mref[16 + ii + idx + 1], b2 = mref[16 + ii + idx + 2];
+                                    v = f ? ((32 - f) * a + f * b2 + 16) >> 5 : a;
+                                }
+                                sad += abs(v - (int)s[j]);
+                            }
                         }
+                        sad = ks_warp_sum(sad);
+                        int bits = (m == 0 || m == 1 || m == 10 || m == 26) ? 3 : 6;
+                        unsigned key = ((sad + ((pp.lambda_sad_q4 * bits) >> 4)) << 6) | (unsigned)m;
+                        best = min(best, key);
                     }
-                    sad = ks_warp_sum(sad);
-                    int bits = (m == 0 || m == 1 || m == 10 || m == 26) ? 3 : 6;
-                    unsigned key = ((sad + ((pp.lambda_sad_q4 * bits) >> 4)) << 6) | (unsigned)m;
-                    best = min(best, key);
+                    if (lane == 0) atomicMin(&sm.best_key, best);
                 }
-                if (lane == 0) sm.best_key[warp] = best;
+                __syncthreads();
+                const int mode = (int)(sm.best_key & 63);
+                /* 3. prediction blocks: threads 0..255 luma, 256..383 chroma */
+                if (tid < 256) {
+                    int d1 = abs(mode - 26), d2 = abs(mode - 10);
+                    bool filt = mode != 1 && min(d1, d2) > 1;
+                    sm.predY[tid] = (uint8_t)ks_intra_sample(filt ? sm.fb : sm.nb[0], 16, 4, mode, tid & 15, tid >> 4, sm.dc[0], true);
+                } else if (tid < 384) {
+                    int t = tid - 256, ci = t >> 6, k = t & 63;
+                    sm.predC[ci][k] = (uint8_t)ks_intra_sample(sm.nb[1 + ci], 8, 3, mode, k & 7, k >> 3, sm.dc[1 + ci], false);
+                }
+                __syncthreads();
+                /* 4. residual coding: warp 0 luma 16x16 (lanes 0..15), warp 1 Cb+Cr 8x8 (lanes 0..15) */
+                if (warp == 0) {
+                    int g = lane >> 4, r = lane & 15, y = y0 + r;
+                    bool cbf = ks_tb_code<16>(&sm.tb[0], sm.scan + 64, nullptr, g == 0, src.p[0] + (size_t)y * W + x0, &sm.predY[r * 16],
+                                              rec.p[0] + (size_t)y * W + x0, lv.p[0] + (size_t)y * W + x0, pp.qp, 1, pp.sign_hiding, lane);
+                    if (lane == 0 && cbf) atomicOr(&sm.cbf, KS_F_CBF_Y);
+                } else if (warp == 1) {
+                    int g = lane >> 3, r = lane & 7, ci = g & 1, x = x0 >> 1, y = (y0 >> 1) + r;
+                    bool cbf = ks_tb_code<8>(&sm.tb[1], sm.scan, nullptr, g < 2, src.p[1 + ci] + (size_t)y * CW + x, &sm.predC[ci][r * 8],
+                                             rec.p[1 + ci] + (size_t)y * CW + x, lv.p[1 + ci] + (size_t)y * CW + x, pp.qpc, 1, pp.sign_hiding, lane);
+                    if (r == 0 && g < 2 && cbf) atomicOr(&sm.cbf, ci ? KS_F_CBF_CR : KS_F_CBF_CB);
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    ks_cell c; c.mvx = 0; c.mvy = 0; c.cu_log2 = 4; c.flags = (uint8_t)(KS_F_INTRA | sm.cbf); c.intra_mode = (uint8_t)mode; c.rsv = 0;
+                    cells[(y0 >> 4) * pp.cw + (x0 >> 4)] = c;
+                }
             }
-            __syncthreads();
-            if (tid == 0) {
-                unsigned b = sm.best_key[0];
-                for (int w = 1; w < KS_RECON_WARPS; w++) b = min(b, sm.best_key[w]);
-                sm.best_mode = (int)(b & 63); sm.cbf = 0;
-            }
-            __syncthreads();
-            const int mode = sm.best_mode;
-            /* 3. prediction blocks */
-            {
-                int d1 = abs(mode - 26), d2 = abs(mode - 10);
-                bool filt = mode != 1 && min(d1, d2) > 1;
-                sm.predY[tid] = (uint8_t)ks_intra_sample(filt ? sm.fb : sm.nb[0], 16, 4, mode, tid & 15, tid >> 4, sm.dc[0], true);
-                if (tid < 128) { int ci = tid >> 6, k = tid & 63; sm.predC[ci][k] = (uint8_t)ks_intra_sample(sm.nb[1 + ci], 8, 3, mode, k & 7, k >> 3, sm.dc[1 + ci], false); }
-            }
-            __syncthreads();
-            /* 4. residual coding: warp 0 luma 16x16 (lanes 0..15), warp 1 Cb+Cr 8x8 (lanes 0..15) */
-            if (warp == 0) {
-                int g = lane >> 4, r = lane & 15, y = y0 + r;
-                bool cbf = ks_tb_code<16>(&sm.tb[0], sm.scan + 64, nullptr, g == 0, src.p[0] + (size_t)y * W + x0, &sm.predY[r * 16],
-                                          rec.p[0] + (size_t)y * W + x0, lv.p[0] + (size_t)y * W + x0, pp.qp, 1, pp.sign_hiding, lane);
-                if (lane == 0 && cbf) atomicOr(&sm.cbf, KS_F_CBF_Y);
-            } else if (warp == 1) {
-                int g = lane >> 3, r = lane & 7, ci = g & 1, x = x0 >> 1, y = (y0 >> 1) + r;
-                bool cbf = ks_tb_code<8>(&sm.tb[1], sm.scan, nullptr, g < 2, src.p[1 + ci] + (size_t)y * CW + x, &sm.predC[ci][r * 8],
-                                         rec.p[1 + ci] + (size_t)y * CW + x, lv.p[1 + ci] + (size_t)y * CW + x, pp.qpc, 1, pp.sign_hiding, lane);
-                if (r == 0 && g < 2 && cbf) atomicOr(&sm.cbf, ci ? KS_F_CBF_CR : KS_F_CBF_CB);
-            }
-            __syncthreads();
-            if (tid == 0) {
-                ks_cell c; c.mvx = 0; c.mvy = 0; c.cu_log2 = 4; c.flags = (uint8_t)(KS_F_INTRA | sm.cbf); c.intra_mode = (uint8_t)mode; c.rsv = 0;
-                cells[(y0 >> 4) * pp.cw + (x0 >> 4)] = c;
-            }
+            if (tid == 0) { __threadfence(); atomicExch(&progress[cty * pp.ctw + ctx], z + 1); }
         }
-        __syncthreads();
-        if (tid == 0) { __threadfence(); atomicExch(&progress[cty], ctx + 1); }
     }
 }
 
 void ks_launch_recon_intra(const KsPicParams &pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *cells, int *sync_ws, cudaStream_t st)
 {
-    cudaMemsetAsync(sync_ws, 0, sizeof(int) * (size_t)(1 + pp.cth), st);
-    ks_recon_intra_kernel<<<pp.cth, KS_RECON_WARPS * KS_WARP, 0, st>>>(pp, src, rec, lv, cells, sync_ws);
+    cudaMemsetAsync(sync_ws, 0, sizeof(int) * (size_t)(1 + pp.ctw * pp.cth), st);
+    ks_recon_intra_kernel<<<2 * pp.cth, KS_INTRA_WARPS * KS_WARP, 0, st>>>(pp, src, rec, lv, cells, sync_ws);
 }
