@@ -29,6 +29,7 @@ struct ks_gpu_ctx {
     size_t fsz;                 /* bytes of one coded picture (W*H*3/2) */
     uint8_t **d_src, **d_rec;   /* slots */
     uint8_t *d_pre;             /* pre-filter reconstruction / deblocked in place */
+    uint8_t *d_pred;            /* inter prediction planes written by the motion search */
     int16_t *d_lev;
     uint32_t *d_counts;
     int *d_sync;
@@ -80,6 +81,7 @@ extern "C" ks_gpu_ctx *ks_gpu_open(int device, int width, int height, const ks_g
         for (int i = 0; i < c->cfg.n_src_slots; i++) ok = ok && cudaMalloc(&c->d_src[i], c->fsz) == cudaSuccess;
         for (int i = 0; i < c->cfg.n_rec_slots; i++) ok = ok && cudaMalloc(&c->d_rec[i], c->fsz) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_pre, c->fsz) == cudaSuccess;
+        ok = ok && cudaMalloc(&c->d_pred, c->fsz) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_lev, c->fsz * 2) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_counts, sizeof(uint32_t) * c->ctw * c->cth) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_sync, sizeof(int) * ((size_t)c->ctw * c->cth + 1)) == cudaSuccess;
@@ -119,7 +121,7 @@ extern "C" void ks_gpu_close(ks_gpu_ctx *c)
     if (c->st) cudaStreamSynchronize(c->st);
     if (c->d_src) for (int i = 0; i < c->cfg.n_src_slots; i++) cudaFree(c->d_src[i]);
     if (c->d_rec) for (int i = 0; i < c->cfg.n_rec_slots; i++) cudaFree(c->d_rec[i]);
-    cudaFree(c->d_pre); cudaFree(c->d_lev); cudaFree(c->d_counts); cudaFree(c->d_sync); cudaFree(c->d_stage);
+    cudaFree(c->d_pre); cudaFree(c->d_pred); cudaFree(c->d_lev); cudaFree(c->d_counts); cudaFree(c->d_sync); cudaFree(c->d_stage);
     for (int i = 0; i < 2; i++) { if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]); if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]); }
     if (c->syn) for (int i = 0; i < c->cfg.n_syn_slots; i++) {
         ks_syn_slot *s = &c->syn[i];
@@ -234,9 +236,10 @@ extern "C" int ks_gpu_encode_picture_submit(ks_gpu_ctx *c, const ks_pic_params *
         KsPlanes ref = planes_of(c, c->d_rec[p->ref_slot]);
         const ks_cell *prev = p->prev_syn_slot >= 0 ? c->syn[p->prev_syn_slot].d_cells : NULL;
         MARK(0);
-        ks_launch_me(pp, src.p[0], ref.p[0], prev, s->d_cells, c->st); c->launches += KS_LAUNCHES_ME;
+        KsPlanes pred = planes_of(c, c->d_pred);
+        ks_launch_me(pp, src.p[0], ref, prev, s->d_cells, pred, c->st); c->launches += KS_LAUNCHES_ME;
         MARK(1);
-        ks_launch_recon_inter(pp, src, ref, pre, lv, s->d_cells, c->st); c->launches += KS_LAUNCHES_RECON;
+        ks_launch_recon_inter(pp, src, pred, pre, lv, s->d_cells, c->st); c->launches += KS_LAUNCHES_RECON;
     }
     MARK(3);
     ks_launch_deblock(pp, pre, s->d_cells, c->st); c->launches += KS_LAUNCHES_DEBLOCK;
@@ -327,7 +330,8 @@ extern "C" int ks_gpu_debug_me(ks_gpu_ctx *c, const ks_pic_params *p, ks_cell *c
     ks_syn_slot *s = &c->syn[p->syn_slot];
     KsPlanes src = planes_of(c, c->d_src[p->src_slot]), ref = planes_of(c, c->d_rec[p->ref_slot]);
     const ks_cell *prev = p->prev_syn_slot >= 0 ? c->syn[p->prev_syn_slot].d_cells : NULL;
-    ks_launch_me(pp, src.p[0], ref.p[0], prev, s->d_cells, c->st); c->launches += KS_LAUNCHES_ME;
+    KsPlanes nopred; nopred.p[0] = nopred.p[1] = nopred.p[2] = NULL;
+    ks_launch_me(pp, src.p[0], ref, prev, s->d_cells, nopred, c->st); c->launches += KS_LAUNCHES_ME;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(cells_out, s->d_cells, (size_t)c->cw * c->ch * sizeof(ks_cell), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));

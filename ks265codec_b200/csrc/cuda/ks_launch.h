@@ -24,8 +24,8 @@ struct KsPicParams {
 
 /* all launches are asynchronous on `st` */
 void ks_upload_tables();
-void ks_launch_me(const KsPicParams &pp, const uint8_t *srcY, const uint8_t *refY, const ks_cell *prev_cells, ks_cell *cells, cudaStream_t st);
-void ks_launch_recon_inter(const KsPicParams &pp, KsPlanes src, KsPlanes ref, KsPlanes rec, KsLevels lv, ks_cell *cells, cudaStream_t st);
+void ks_launch_me(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref, const ks_cell *prev_cells, ks_cell *cells, KsPlanes pred, cudaStream_t st);
+void ks_launch_recon_inter(const KsPicParams &pp, KsPlanes src, KsPlanes pred, KsPlanes rec, KsLevels lv, ks_cell *cells, cudaStream_t st);
 void ks_launch_recon_intra(const KsPicParams &pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *cells, int *sync_ws, cudaStream_t st);
 void ks_launch_deblock(const KsPicParams &pp, KsPlanes rec, const ks_cell *cells, cudaStream_t st);
 void ks_launch_sao(const KsPicParams &pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_syn *ctus, unsigned long long *sse_out, cudaStream_t st);

@@ -316,12 +316,66 @@ __device__ __forceinline__ void ks_center_window(int x0, int y0, int cx, int cy,
     wy0 = y0 + cy - KS_WIN_MARGIN;
 }
 
+/* ------------------------------------------------------------------ chroma motion compensation --- */
+/* 8x8 chroma block, 4-tap filters, eighth-sample mv (spec 8.5.3.3.3.2 == ora_mc_chroma).  Warp-collective.
+ * cwin: 12x12 byte window (rows/cols -1..+10 of the integer position), tmp: >= 11x8 int16. */
+__device__ __forceinline__ void ks_mc_chroma8(uint8_t *cwin, int16_t *tmp, const uint8_t *__restrict__ ref, int PW, int PH,
+                                              int xc, int yc, int mvx, int mvy, uint8_t *dst, int dpitch, int lane)
+{
+    const int ix = xc + (mvx >> 3) - 1, iy = yc + (mvy >> 3) - 1, fx = mvx & 7, fy = mvy & 7;
+    {
+        uint8_t b[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) {                          /* 5 independent loads in flight per lane */
+            int idx = min(lane + k * KS_WARP, 143), r = idx / 12, c = idx - r * 12;
+            b[k] = __ldg(ref + (size_t)min(max(iy + r, 0), PH - 1) * PW + min(max(ix + c, 0), PW - 1));
+        }
+#pragma unroll
+        for (int k = 0; k < 5; k++) if (lane + k * KS_WARP < 144) cwin[lane + k * KS_WARP] = b[k];
+    }
+    __syncwarp();
+    const int row = lane >> 2, col = (lane & 3) * 2;
+    int v0, v1;
+    if (fx == 0 && fy == 0) { v0 = cwin[(row + 1) * 12 + col + 1]; v1 = cwin[(row + 1) * 12 + col + 2]; }
+    else if (fy == 0) {
+        const uint8_t *p = cwin + (row + 1) * 12 + col;
+        int a = 0, b = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) { int c = c_chroma_taps[fx][t]; a += c * p[t]; b += c * p[t + 1]; }
+        v0 = ks_clip8((a + 32) >> 6); v1 = ks_clip8((b + 32) >> 6);
+    } else if (fx == 0) {
+        const uint8_t *p = cwin + row * 12 + col + 1;
+        int a = 0, b = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) { int c = c_chroma_taps[fy][t]; a += c * p[t * 12]; b += c * p[t * 12 + 1]; }
+        v0 = ks_clip8((a + 32) >> 6); v1 = ks_clip8((b + 32) >> 6);
+    } else {
+        for (int idx = lane; idx < 88; idx += KS_WARP) {      /* raw horizontal sums, rows -1..+9 */
+            int r = idx >> 3, c = idx & 7;
+            const uint8_t *p = cwin + r * 12 + c;
+            int a = 0;
+#pragma unroll
+            for (int t = 0; t < 4; t++) a += c_chroma_taps[fx][t] * p[t];
+            tmp[idx] = (int16_t)a;
+        }
+        __syncwarp();
+        int a = 0, b = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) { int c = c_chroma_taps[fy][t]; a += c * tmp[(row + t) * 8 + col]; b += c * tmp[(row + t) * 8 + col + 1]; }
+        v0 = ks_clip8((a + 2048) >> 12); v1 = ks_clip8((b + 2048) >> 12);
+    }
+    dst[row * dpitch + col] = (uint8_t)v0; dst[row * dpitch + col + 1] = (uint8_t)v1;
+    __syncwarp();
+}
+
 #define KS_ME_WARPS 8
 __global__ void __launch_bounds__(KS_ME_WARPS * KS_WARP)
-ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, const uint8_t *__restrict__ refY,
-             const ks_cell *__restrict__ prev_cells, ks_cell *__restrict__ cells)
+ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref, const ks_cell *__restrict__ prev_cells,
+             ks_cell *__restrict__ cells, KsPlanes pred)
 {
     __shared__ __align__(16) KsWarpScratch scratch[KS_ME_WARPS];
+    __shared__ uint8_t cwins[KS_ME_WARPS][144];
+    const uint8_t *__restrict__ refY = ref.p[0];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cell = blockIdx.x * KS_ME_WARPS + warp;
     if (cell >= pp.cw * pp.ch) return;
@@ -381,6 +435,8 @@ ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, const uint8_t *__
      *      stage share planes of raw horizontal sums: 2 planes + 2 vertical-only blocks for the half stage, 3 planes (one
      *      per x offset) for the quarter stage; each candidate is then a single vertical pass + SAD. ---- */
     int mx = bx * 4, my = by * 4;
+    uint32_t best0, best1;                      /* the winning candidate's prediction (this lane's 8 samples) */
+    ks_win_px8(sc->win, x0 + bx - wx0, y0 + by - wy0, lane, best0, best1);
     if (pp.subpel > 0) {
         int bxw = x0 + bx - wx0, byw = y0 + by - wy0;
         if (bxw < 4 || bxw > 27 || byw < 4 || byw > 19) {
@@ -409,7 +465,7 @@ ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, const uint8_t *__
                 if (dx == 0) ks_interp16(sc, bxw, byw + (dy < 0 ? -1 : 0), 0, 2, lane, o0, o1);      /* vertical-only, straight from the samples */
                 else ks_plane_pred(dx < 0 ? P0 : P2, dy < 0 ? 0 : 1, dy ? 2 : 0, lane, o0, o1);
                 int c = (int)KS_SUBCOST(o0, o1) + MVCOST(qx, qy);
-                if (c < lc) { lc = c; bk = k; }
+                if (c < lc) { lc = c; bk = k; best0 = o0; best1 = o1; }
             }
             if (bk >= 0) { mx += sqx[bk] * 2; my += sqy[bk] * 2; bc = lc; }
         }
@@ -425,7 +481,7 @@ ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, const uint8_t *__
                 uint32_t o0, o1;
                 ks_plane_pred(dx < 0 ? P0 : (dx == 0 ? P1 : P2), (qy >> 2) - iym, qy & 3, lane, o0, o1);
                 int c = (int)KS_SUBCOST(o0, o1) + MVCOST(qx, qy);
-                if (c < lc) { lc = c; bk = k; }
+                if (c < lc) { lc = c; bk = k; best0 = o0; best1 = o1; }
             }
             if (bk >= 0) { mx += sqx[bk]; my += sqy[bk]; bc = lc; }
         }
@@ -436,10 +492,21 @@ ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, const uint8_t *__
         ks_cell c; c.mvx = (int16_t)mx; c.mvy = (int16_t)my; c.cu_log2 = 4; c.flags = 0; c.intra_mode = 0; c.rsv = 0;
         cells[cell] = c;
     }
+    /* ---- the search already holds the winner's luma prediction: emit it (and the chroma prediction for the same vector) so
+     *      the residual kernel needs no motion compensation pass of its own (reference: getReusSubMePred E@0x486770 re-uses the
+     *      sub-ME interpolation as the final prediction) ---- */
+    if (pred.p[0]) {
+        *reinterpret_cast<uint2 *>(pred.p[0] + (size_t)(y0 + (lane >> 1)) * W + x0 + 8 * (lane & 1)) = make_uint2(best0, best1);
+        const int CW = W >> 1, CH = H >> 1;
+#pragma unroll 1
+        for (int ci = 0; ci < 2; ci++)
+            ks_mc_chroma8(cwins[warp], &sc->tmp[0][0], ref.p[1 + ci], CW, CH, x0 >> 1, y0 >> 1, mx, my,
+                          pred.p[1 + ci] + (size_t)(y0 >> 1) * CW + (x0 >> 1), CW, lane);
+    }
 }
 
-void ks_launch_me(const KsPicParams &pp, const uint8_t *srcY, const uint8_t *refY, const ks_cell *prev_cells, ks_cell *cells, cudaStream_t st)
+void ks_launch_me(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref, const ks_cell *prev_cells, ks_cell *cells, KsPlanes pred, cudaStream_t st)
 {
     int ncell = pp.cw * pp.ch;
-    ks_me_kernel<<<(ncell + KS_ME_WARPS - 1) / KS_ME_WARPS, KS_ME_WARPS * KS_WARP, 0, st>>>(pp, srcY, refY, prev_cells, cells);
+    ks_me_kernel<<<(ncell + KS_ME_WARPS - 1) / KS_ME_WARPS, KS_ME_WARPS * KS_WARP, 0, st>>>(pp, srcY, ref, prev_cells, cells, pred);
 }

@@ -9,9 +9,9 @@
  *                  fully unrolled partial butterflies with IMMEDIATE coefficients (ks_dct_gen.cuh; constant-bank
  *                  operands thrashed the immediate-constant cache),
  *                  transposes go through padded shared memory.  No tensor cores (north star).
- *  ks_recon_inter_kernel   one CTA per 64x64 CTU: CU-size decision, motion compensation of the 16 cells into
- *                  shared memory (the reference's `reconstruct` E@0x47d600 driver + interpolatePuLx E@0x487260),
- *                  then the transform tasks.
+ *  ks_recon_inter_kernel   one CTA per 64x64 CTU: CU-size decision, then the transform tasks (the reference's `reconstruct`
+ *                  E@0x47d600 driver).  The prediction comes from the motion-search kernel, which already holds the winner's
+ *                  interpolated block (reference: getReusSubMePred E@0x486770).
  *  ks_recon_intra_kernel   I pictures: CTU rows run as a wavefront (reference: WPP, CCtuEncWpp::waitForTopRightCtu
  *                  E@0x468d40) inside ONE launch, rows handed out by a ticket counter, progress flags in HBM.
  * Bit-exact mirror of oracle/ora_frame.c.
@@ -179,67 +179,12 @@ __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, c
     return cbf;
 }
 
-/* ------------------------------------------------------------------ chroma motion compensation --- */
-/* 8x8 chroma block, 4-tap filters, eighth-sample mv (spec 8.5.3.3.3.2 == ora_mc_chroma).  Warp-collective.
- * cwin: 12x12 byte window (rows/cols -1..+10 of the integer position), tmp: >= 11x8 int16. */
-__device__ __forceinline__ void ks_mc_chroma8(uint8_t *cwin, int16_t *tmp, const uint8_t *__restrict__ ref, int PW, int PH,
-                                              int xc, int yc, int mvx, int mvy, uint8_t *dst, int dpitch, int lane)
-{
-    const int ix = xc + (mvx >> 3) - 1, iy = yc + (mvy >> 3) - 1, fx = mvx & 7, fy = mvy & 7;
-    {
-        uint8_t b[5];
-#pragma unroll
-        for (int k = 0; k < 5; k++) {                          /* 5 independent loads in flight per lane */
-            int idx = min(lane + k * KS_WARP, 143), r = idx / 12, c = idx - r * 12;
-            b[k] = __ldg(ref + (size_t)min(max(iy + r, 0), PH - 1) * PW + min(max(ix + c, 0), PW - 1));
-        }
-#pragma unroll
-        for (int k = 0; k < 5; k++) if (lane + k * KS_WARP < 144) cwin[lane + k * KS_WARP] = b[k];
-    }
-    __syncwarp();
-    const int row = lane >> 2, col = (lane & 3) * 2;
-    int v0, v1;
-    if (fx == 0 && fy == 0) { v0 = cwin[(row + 1) * 12 + col + 1]; v1 = cwin[(row + 1) * 12 + col + 2]; }
-    else if (fy == 0) {
-        const uint8_t *p = cwin + (row + 1) * 12 + col;
-        int a = 0, b = 0;
-#pragma unroll
-        for (int t = 0; t < 4; t++) { int c = c_chroma_taps[fx][t]; a += c * p[t]; b += c * p[t + 1]; }
-        v0 = ks_clip8((a + 32) >> 6); v1 = ks_clip8((b + 32) >> 6);
-    } else if (fx == 0) {
-        const uint8_t *p = cwin + row * 12 + col + 1;
-        int a = 0, b = 0;
-#pragma unroll
-        for (int t = 0; t < 4; t++) { int c = c_chroma_taps[fy][t]; a += c * p[t * 12]; b += c * p[t * 12 + 1]; }
-        v0 = ks_clip8((a + 32) >> 6); v1 = ks_clip8((b + 32) >> 6);
-    } else {
-        for (int idx = lane; idx < 88; idx += KS_WARP) {      /* raw horizontal sums, rows -1..+9 */
-            int r = idx >> 3, c = idx & 7;
-            const uint8_t *p = cwin + r * 12 + c;
-            int a = 0;
-#pragma unroll
-            for (int t = 0; t < 4; t++) a += c_chroma_taps[fx][t] * p[t];
-            tmp[idx] = (int16_t)a;
-        }
-        __syncwarp();
-        int a = 0, b = 0;
-#pragma unroll
-        for (int t = 0; t < 4; t++) { int c = c_chroma_taps[fy][t]; a += c * tmp[(row + t) * 8 + col]; b += c * tmp[(row + t) * 8 + col + 1]; }
-        v0 = ks_clip8((a + 2048) >> 12); v1 = ks_clip8((b + 2048) >> 12);
-    }
-    dst[row * dpitch + col] = (uint8_t)v0; dst[row * dpitch + col + 1] = (uint8_t)v1;
-    __syncwarp();
-}
-
 /* ------------------------------------------------------------------ inter picture: one CTA per CTU - */
 #define KS_RECON_WARPS 8
 struct KsReconSmem {
-    union { KsWarpScratch mc[KS_RECON_WARPS]; KsTbScratch tb[KS_RECON_WARPS]; } u;
+    KsTbScratch tb[KS_RECON_WARPS];
     uint16_t scan[64 + 256 + 1024];            /* scan tables for 8x8, 16x16, 32x32 */
     int      t0[256];                          /* M32[2j+1][x], j,x < 16: level-0 odd part of the 32-point butterflies */
-    uint8_t  predY[64 * 64];
-    uint8_t  predC[2][32 * 32];
-    uint8_t  cwin[KS_RECON_WARPS][144];
     int16_t  mvx[16], mvy[16];
     uint8_t  valid[16];
     unsigned cbf[16];                          /* KS_F_CBF_* bits per cell, OR-ed by the transform tasks */
@@ -255,7 +200,7 @@ __device__ __forceinline__ void ks_load_scans(uint16_t *scan, int tid, int nthre
 }
 
 __global__ void __launch_bounds__(KS_RECON_WARPS * KS_WARP, 2)
-ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes ref, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells)
+ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes pred, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     KsReconSmem *sm = reinterpret_cast<KsReconSmem *>(smem_raw);
@@ -285,24 +230,6 @@ ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes ref, KsPlanes rec, 
         q32[q] = ok;
         c64 = c64 && ok && mx == sm->mvx[0] && my == sm->mvy[0];
     }
-    /* ---- motion compensation of the 16 cells into shared memory ---- */
-#pragma unroll 1
-    for (int k = warp; k < 16; k += KS_RECON_WARPS) {
-        if (!sm->valid[k]) continue;
-        const int cx = k & 3, cy = k >> 2, x0 = X0 + (cx << 4), y0 = Y0 + (cy << 4);
-        const int mvx = sm->mvx[k], mvy = sm->mvy[k];
-        KsWarpScratch *sc = &sm->u.mc[warp];
-        const int wx0 = (x0 + (mvx >> 2) - 3) & ~3, wy0 = y0 + (mvy >> 2) - 3;      /* only the 23 x 28 samples this block can touch */
-        ks_load_window_mc(sc->win, ref.p[0], W, H, wx0, wy0, lane);
-        uint32_t o0, o1;
-        ks_interp16(sc, x0 + (mvx >> 2) - wx0, 3, mvx & 3, mvy & 3, lane, o0, o1);
-        *reinterpret_cast<uint2 *>(&sm->predY[((cy << 4) + (lane >> 1)) * 64 + (cx << 4) + 8 * (lane & 1)]) = make_uint2(o0, o1);
-#pragma unroll 1
-        for (int ci = 0; ci < 2; ci++)
-            ks_mc_chroma8(sm->cwin[warp], &sc->tmp[0][0], ref.p[1 + ci], CW, CH, x0 >> 1, y0 >> 1, mvx, mvy,
-                          &sm->predC[ci][(cy << 3) * 32 + (cx << 3)], 32, lane);
-    }
-    __syncthreads();
     /* ---- transform tasks: 16 slots (k, q) = (kind 0..3, quadrant); a quadrant coded with one 32x32 TU uses kinds
      *      0 (luma 32) and 1 (Cb+Cr 16), otherwise kinds 0,1 (two luma 16 pairs) and 2,3 (four Cb 8 / four Cr 8).
      *      Slot order k*4+q gives every warp one heavy and one light task. ---- */
@@ -312,16 +239,16 @@ ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes ref, KsPlanes rec, 
         const int qx = (q & 1) * 32, qy = (q >> 1) * 32;             /* quadrant origin inside the CTU (luma) */
         const int b0 = (q & 1) * 2 + (q >> 1) * 8;
         if (!sm->valid[b0]) continue;
-        KsTbScratch *ts = &sm->u.tb[warp];
+        KsTbScratch *ts = &sm->tb[warp];
         if (q32[q]) {
             if (k == 0) {
                 int r = lane, x = X0 + qx, y = Y0 + qy + r;
-                bool cbf = ks_tb_code<32>(ts, ks_scan_ptr(sm, 32), sm->t0, true, src.p[0] + (size_t)y * W + x, &sm->predY[(qy + r) * 64 + qx],
+                bool cbf = ks_tb_code<32>(ts, ks_scan_ptr(sm, 32), sm->t0, true, src.p[0] + (size_t)y * W + x, pred.p[0] + (size_t)y * W + x,
                                           rec.p[0] + (size_t)y * W + x, lv.p[0] + (size_t)y * W + x, pp.qp, 0, pp.sign_hiding, lane);
                 if (lane == 0 && cbf) { atomicOr(&sm->cbf[b0], KS_F_CBF_Y); atomicOr(&sm->cbf[b0 + 1], KS_F_CBF_Y); atomicOr(&sm->cbf[b0 + 4], KS_F_CBF_Y); atomicOr(&sm->cbf[b0 + 5], KS_F_CBF_Y); }
             } else if (k == 1) {
                 int g = lane >> 4, r = lane & 15, x = (X0 + qx) >> 1, y = ((Y0 + qy) >> 1) + r;
-                bool cbf = ks_tb_code<16>(ts, ks_scan_ptr(sm, 16), sm->t0, true, src.p[1 + g] + (size_t)y * CW + x, &sm->predC[g][((qy >> 1) + r) * 32 + (qx >> 1)],
+                bool cbf = ks_tb_code<16>(ts, ks_scan_ptr(sm, 16), sm->t0, true, src.p[1 + g] + (size_t)y * CW + x, pred.p[1 + g] + (size_t)y * CW + x,
                                           rec.p[1 + g] + (size_t)y * CW + x, lv.p[1 + g] + (size_t)y * CW + x, pp.qpc, 0, pp.sign_hiding, lane);
                 if (r == 0 && cbf) { unsigned f = g ? KS_F_CBF_CR : KS_F_CBF_CB; atomicOr(&sm->cbf[b0], f); atomicOr(&sm->cbf[b0 + 1], f); atomicOr(&sm->cbf[b0 + 4], f); atomicOr(&sm->cbf[b0 + 5], f); }
             }
@@ -330,7 +257,7 @@ ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes ref, KsPlanes rec, 
             int cidx = b0 + (kc & 1) + (kc >> 1) * 4;
             bool v = sm->valid[cidx];
             int lx = qx + (kc & 1) * 16, ly = qy + (kc >> 1) * 16 + r, x = X0 + lx, y = Y0 + ly;
-            bool cbf = ks_tb_code<16>(ts, ks_scan_ptr(sm, 16), sm->t0, v, src.p[0] + (size_t)y * W + x, &sm->predY[ly * 64 + lx],
+            bool cbf = ks_tb_code<16>(ts, ks_scan_ptr(sm, 16), sm->t0, v, src.p[0] + (size_t)y * W + x, pred.p[0] + (size_t)(v ? y : Y0) * W + (v ? x : X0),
                                       rec.p[0] + (size_t)y * W + x, lv.p[0] + (size_t)y * W + x, pp.qp, 0, pp.sign_hiding, lane);
             if (r == 0 && cbf) atomicOr(&sm->cbf[cidx], KS_F_CBF_Y);
         } else {
@@ -338,7 +265,7 @@ ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes ref, KsPlanes rec, 
             int cidx = b0 + (kc & 1) + (kc >> 1) * 4;
             bool v = sm->valid[cidx];
             int lx = (qx >> 1) + (kc & 1) * 8, ly = (qy >> 1) + (kc >> 1) * 8 + r, x = (X0 >> 1) + lx, y = (Y0 >> 1) + ly;
-            bool cbf = ks_tb_code<8>(ts, ks_scan_ptr(sm, 8), sm->t0, v, src.p[1 + ci] + (size_t)y * CW + x, &sm->predC[ci][ly * 32 + lx],
+            bool cbf = ks_tb_code<8>(ts, ks_scan_ptr(sm, 8), sm->t0, v, src.p[1 + ci] + (size_t)y * CW + x, pred.p[1 + ci] + (size_t)(v ? y : (Y0 >> 1)) * CW + (v ? x : (X0 >> 1)),
                                      rec.p[1 + ci] + (size_t)y * CW + x, lv.p[1 + ci] + (size_t)y * CW + x, pp.qpc, 0, pp.sign_hiding, lane);
             if (r == 0 && cbf) atomicOr(&sm->cbf[cidx], ci ? KS_F_CBF_CR : KS_F_CBF_CB);
         }
@@ -351,12 +278,12 @@ ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes ref, KsPlanes rec, 
     }
 }
 
-void ks_launch_recon_inter(const KsPicParams &pp, KsPlanes src, KsPlanes ref, KsPlanes rec, KsLevels lv, ks_cell *cells, cudaStream_t st)
+void ks_launch_recon_inter(const KsPicParams &pp, KsPlanes src, KsPlanes pred, KsPlanes rec, KsLevels lv, ks_cell *cells, cudaStream_t st)
 {
     static bool attr_done = false;
     if (!attr_done) { cudaFuncSetAttribute(ks_recon_inter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsReconSmem)); attr_done = true; }
     dim3 grid(pp.ctw, pp.cth);
-    ks_recon_inter_kernel<<<grid, KS_RECON_WARPS * KS_WARP, sizeof(KsReconSmem), st>>>(pp, src, ref, rec, lv, cells);
+    ks_recon_inter_kernel<<<grid, KS_RECON_WARPS * KS_WARP, sizeof(KsReconSmem), st>>>(pp, src, pred, rec, lv, cells);
 }
 
 /* ------------------------------------------------------------------ intra picture (wavefront) ---- */
