@@ -369,7 +369,7 @@ __device__ __forceinline__ void ks_mc_chroma8(uint8_t *cwin, int16_t *tmp, const
 }
 
 #define KS_ME_WARPS 8
-__global__ void __launch_bounds__(KS_ME_WARPS * KS_WARP)
+__global__ void __launch_bounds__(KS_ME_WARPS * KS_WARP, 4)
 ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref, const ks_cell *__restrict__ prev_cells,
              ks_cell *__restrict__ cells, KsPlanes pred)
 {

@@ -199,7 +199,7 @@ __device__ __forceinline__ void ks_load_scans(uint16_t *scan, int tid, int nthre
     for (int i = tid; i < 64 + 256 + 1024; i += nthreads) scan[i] = i < 64 ? c_scan_tb[1][i] : (i < 320 ? c_scan_tb[2][i - 64] : c_scan_tb[3][i - 320]);
 }
 
-__global__ void __launch_bounds__(KS_RECON_WARPS * KS_WARP, 3)
+__global__ void __launch_bounds__(KS_RECON_WARPS * KS_WARP, 2)
 ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes pred, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];

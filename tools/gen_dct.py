@@ -31,7 +31,7 @@ def fwd(N):
         for i in range(h):
             L.append("    const int %s = %s + %s, %s = %s - %s;" % (e[i], cur[i], cur[n - 1 - i], o[i], cur[i], cur[n - 1 - i]))
         if N == 32 and lvl == 0:
-            L.append("#pragma unroll 1")
+            L.append("#pragma unroll 2")
             L.append("    for (int j = 0; j < 16; j++) {")
             L.append("        const int4 *t = reinterpret_cast<const int4 *>(t0 + 16 * j);")
             L.append("        const int4 a = t[0], b = t[1], c = t[2], d = t[3];")
@@ -75,7 +75,7 @@ def inv(N):
         if N == 32 and kstep == 1:
             for y in range(16):
                 L.append("    int oL0_%d = 0;" % y); od.append("oL0_%d" % y)
-            L.append("#pragma unroll 1")
+            L.append("#pragma unroll 2")
             L.append("    for (int j = 0; j < 16; j++) {")
             L.append("        const int xi = ld(2 * j + 1);")
             L.append("        const int4 *t = reinterpret_cast<const int4 *>(t0 + 16 * j);")
