@@ -228,8 +228,13 @@ def main():
 
     # ---- roofline of the dominant stage (SURVEY.md 8d per-kernel algorithmic bytes; S = 1.5*W*H per picture) ----
     S = 1.5 * W * H
-    alg = {"me": 2.0 * W * H + 8.0 * W * H / 256, "recon_inter": 5.0 * S + 8.0 * W * H / 256, "recon_intra": 4.0 * S,
-           "deblock": 2.0 * W * H, "sao": 3.0 * S, "pack": 2.0 * S + 0.1 * S}
+    # algorithmic bytes per launch: compulsory HBM traffic with perfect on-chip reuse
+    alg = {"me": S + S + S + 8.0 * W * H / 256,                 # source luma+ (S_luma) + reference picture -> MV field + prediction planes
+           "recon_inter": S + S + S + 2.0 * S + 8.0 * W * H / 256,    # source + prediction in, reconstruction + int16 levels out
+           "recon_intra": S + S + 2.0 * S, "deblock": 2.0 * W * H, "sao": 3.0 * S, "pack": 2.0 * S + 0.1 * S}
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/ncu_full_r1.md);
+    # ncu flushes L2 before each replay, writes mostly stay in the 126 MB L2, so traffic can be BELOW the algorithmic bytes
+    ncu_traffic = {"me": 16.9e6, "recon_inter": 31.4e6, "sao": 25.1e6, "deblock": 12.9e6, "pack": 31.6e6, "recon_intra": None}
     # every stage timed ALONE (one stream, nothing else on the GPU): these are the launch durations the roofline uses.
     # dominant stage = largest solo time per picture, weighted by how often the stage runs in a GOP shard.
     solo = encs[0]
@@ -245,7 +250,7 @@ def main():
     avg_ms = solo_t[dom][0] / max(1, solo_t[dom][1])
     peak, peak_src = peaks()
     achieved = alg[dom] / (avg_ms / 1000.0) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic.get(dom),
                 "peak_source": peak_src, "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg[dom],
                 "stage_ms_share": {k: v[0] / max(1e-9, sum(x[0] for x in stage.values())) for k, v in stage.items()},
                 "solo_stage_ms": {k: (v[0] / v[1] if v[1] else None) for k, v in solo_t.items()},

@@ -287,3 +287,35 @@ def test_4k_roundtrip_property():
     assert 10 * np.log10(255 * 255 / mse) > 33.0
     sse_y = int(((rec.reshape(n, -1)[:, :w * h].astype(np.int64) - yuv.reshape(n, -1)[:, :w * h]) ** 2).sum())
     assert st.sse[0] == sse_y          # device-side SSE (PSNR line) agrees with the host recomputation
+
+
+def test_8k_roundtrip_property():
+    """BASELINE configs[4] size (7680x4320): one IDR + one P picture decode with the reference decoder to exactly our recon"""
+    w, h, n = 7680, 4320, 2
+    yuv = np.frombuffer(gen_yuv.make(w, h, n, seed=8), np.uint8)
+    cfg = ks.default_config(w, h, preset="veryfast", qp=27, iper=128, psnr=1)
+    with ks.Encoder(cfg) as e:
+        bs, rec, st = e.encode_gop(yuv, want_recon=True)
+    dec = decode_with_reference(bs, rec.size)
+    first_diff(dec, rec, "8K: reference decoder output vs our recon")
+    mse = ((rec[:w * h].astype(np.float64) - yuv[:w * h]) ** 2).mean()
+    assert 10 * np.log10(255 * 255 / mse) > 33.0
+
+
+def test_cli_matches_library_and_reference_decoder(tmp_path):
+    """the appencoder-compatible CLI: flags, summary lines, -b stream decodable by the reference decoder == its own -o"""
+    w, h, n = 416, 240, 9
+    yuv = gen_yuv.make(w, h, n, seed=4)
+    src, bs, rec = tmp_path / "in.yuv", tmp_path / "o.265", tmp_path / "o.yuv"
+    src.write_bytes(yuv)
+    r = subprocess.run([ks.CLI_PATH, "-i", str(src), "-wdt", str(w), "-hgt", str(h), "-fr", "30", "-preset", "veryfast", "-rc", "0", "-qp", "30",
+                        "-iper", "4", "-b", str(bs), "-o", str(rec), "-psnr", "1", "-md5", "1", "-threads", "1", "-streams", "2"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+    assert "Total Frames: %d" % n in r.stdout and "bitrate, psnr:" in r.stdout and "H265 encoder passed!!!" in r.stdout and "POC 0 MD5" in r.stdout
+    ours = np.fromfile(rec, np.uint8)
+    dec = decode_with_reference(np.fromfile(bs, np.uint8), ours.size)
+    first_diff(dec, ours, "CLI: reference decoder output vs -o recon")
+    # three closed GOP shards (4+4+1 pictures) concatenated in order == the model's stream for the same settings
+    obs, orec = oracle_encode(np.frombuffer(yuv, np.uint8), w, h, n, 30, 4)
+    assert bytes(np.fromfile(bs, np.uint8)) == bytes(obs)
