@@ -23,7 +23,7 @@ typedef struct ks265_config {
     int qp;                     /* -qp */
     int iper;                   /* -iper: intra period = GOP shard length */
     int fixqp;                  /* -fixqp: 1 = same QP for I and P (default: P = QP+1 like the reference) */
-    int sao;                    /* -sao */
+    int sao;                    /* -sao level 0..4 (see ks_gpu_cfg.sao) */
     int sign_hiding;
     int me_range, me_iters, subpel;
     int satd;                   /* sub-pel cost metric: 0 SAD (ultrafast..veryfast), 1 SATD (fast..placebo), like the reference */

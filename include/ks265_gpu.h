@@ -32,7 +32,7 @@ typedef struct ks_gpu_cfg {
     int me_iters;       /* small-diamond steps (reference: tME.range >> shift, interMeDia E@0x4849d0) */
     int subpel;         /* 0 integer, 1 half, 2 quarter (reference -subme) */
     int sign_hiding;    /* PPS sign_data_hiding_enabled_flag (reference: 1 in every preset) */
-    int sao;            /* reference -sao > 0 */
+    int sao;            /* reference -sao level: 0 off; 1..3 BO + EO 0/1 with `_fast` (every 2nd row) statistics; 4 BO + EO 0..3, all rows */
     int strong_intra;
     int n_src_slots;    /* source pictures resident on the device (>= 2) */
     int n_rec_slots;    /* reconstructed/reference pictures resident on the device (>= 2) */

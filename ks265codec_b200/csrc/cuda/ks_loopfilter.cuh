@@ -242,8 +242,9 @@ ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_s
             int *h = sm->hist[warp][ci];
 #pragma unroll
             for (int b = 0; b < 20; b++) sm->ph[b][tid] = 0;
-            for (int i = tid; i < (bh << rl); i += blockDim.x) {
-                const int y = i >> rl, x = (i & ((1 << rl) - 1)) << 2;
+            const int step = pp.sao >= 4 ? 1 : 2, ncls = pp.sao >= 4 ? 4 : 2;     /* `_fast` statistics: every 2nd row, EO classes 0,1 */
+            for (int i = tid; i < (((bh + step - 1) / step) << rl); i += blockDim.x) {
+                const int y = (i >> rl) * step, x = (i & ((1 << rl) - 1)) << 2;
                 if (x >= bw) continue;
                 const KsSaoNb n = ks_sao_load_nb(&sm->tile[ci][(y + 1) * pitch + 4 + x], pitch);
                 const uint32_t s4 = __ldg(reinterpret_cast<const uint32_t *>(src.p[ci] + (size_t)(y0 + y) * PW + x0 + x));
@@ -258,7 +259,7 @@ ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_s
                     int cat[4];
                     ks_sao_cats(n, j, x0 + x + j == 0, x0 + x + j == PW - 1, top, bot, cat);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) sm->ph[k * 5 + cat[k]][tid] += v;      /* bin cat 0 collects the rest and is ignored */
+                    for (int k = 0; k < 4; k++) if (k < ncls) sm->ph[k * 5 + cat[k]][tid] += v;      /* bin cat 0 collects the rest and is ignored */
                 }
                 atomicAdd(&h[20 + cur_band], band_acc);
             }
@@ -294,7 +295,7 @@ ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_s
         const int c0 = tid ? 1 : 0, c1 = tid ? 2 : 0, lam = pp.lambda_sse_q4;
         int best_cost = 0, best_type = 0, best_class = 0, best_band[3] = {0, 0, 0};
         if (pp.sao) {
-            for (int k = 0; k < 4; k++) {
+            for (int k = 0; k < (pp.sao >= 4 ? 4 : 2); k++) {
                 int total = (lam * 4) >> 4;
                 for (int ci = c0; ci <= c1; ci++) for (int j = 0; j < 4; j++) total += sm->cost[ci][k * 4 + j];
                 if (total < best_cost) { best_cost = total; best_type = 2; best_class = k; }

@@ -99,7 +99,7 @@ int main(int argc, char **argv)
     a.cfg.width = a.w; a.cfg.height = a.h;
     if (ks265_config_default_preset(&a.cfg, a.preset)) { fprintf(stderr, "appencoder: unknown preset %s\n", a.preset); return 2; }
     a.cfg.fps = a.fr; a.cfg.qp = qp; a.cfg.iper = iper < 1 ? 1 : iper; a.cfg.fixqp = fixqp; a.cfg.psnr = a.psnr > 0 || 1;
-    if (sao >= 0) a.cfg.sao = sao > 0; if (subme >= 0) a.cfg.subpel = subme > 2 ? 2 : subme; if (merange > 0) a.cfg.me_range = merange;
+    if (sao >= 0) a.cfg.sao = sao > 4 ? 4 : sao; if (subme >= 0) a.cfg.subpel = subme > 2 ? 2 : subme; if (merange > 0) a.cfg.me_range = merange;
     if (a.gpus < 1) a.gpus = 1; if (a.streams < 1) a.streams = 1;
 
     job_t job; memset(&job, 0, sizeof(job));

@@ -32,7 +32,8 @@ int ks265_config_default_preset(ks265_config *cfg, const char *preset)
     int w = cfg->width, h = cfg->height;
     memset(cfg, 0, sizeof(*cfg));
     cfg->width = w; cfg->height = h; cfg->fps = 30.0; cfg->preset = p; cfg->rc = 0; cfg->qp = 27; cfg->iper = 128;
-    cfg->sao = 1; cfg->sign_hiding = 1; cfg->me_range = 64;
+    cfg->sao = p <= 3 ? 3 : 4;       /* reference -sao per preset: 1,1,3,3,4,4,4,4; 1 and 3 behave alike here */
+    cfg->sign_hiding = 1; cfg->me_range = 64;
     cfg->me_iters = p == 0 ? 8 : (p == 1 ? 12 : (p == 2 ? 16 : 32));
     cfg->subpel = p == 0 ? 1 : 2;
     cfg->satd = p >= 3;

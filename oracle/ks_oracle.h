@@ -99,7 +99,7 @@ void ora_sao_stat_boeo01(int *eo, int *bo, const uint8_t *org, const uint8_t *re
  * stats[0..3][cat 0..4] = {sum diff, count} for EO class c, stats[4][band 0..31] for BO */
 typedef struct { int32_t eo_sum[4][5], eo_cnt[4][5], bo_sum[32], bo_cnt[32]; } ora_sao_stats;
 void ora_sao_stats_ctb(ora_sao_stats *st, const uint8_t *org, int os, const uint8_t *rec, int rs,
-                       int x0, int y0, int w, int h, int pic_w, int pic_h);
+                       int x0, int y0, int w, int h, int pic_w, int pic_h, int row_step, int n_classes);
 /* normative SAO apply of one CTB (spec 8.7.3): src = deblocked picture, dst = output picture */
 void ora_sao_apply_ctb(uint8_t *dst, int ds, const uint8_t *src, int ss, int x0, int y0, int w, int h,
                        int pic_w, int pic_h, int type, int band_pos_or_class, const int8_t off[4]);

@@ -342,14 +342,14 @@ void ora_sao_picture(const ora_cfg *cfg, int qp, const ora_pic *src, const ora_p
         for (int ci = 0; ci < 3; ci++) {
             int sh = ci ? 1 : 0, x0 = (rx << 6) >> sh, y0 = (ry << 6) >> sh, pw = W >> sh, ph = H >> sh;
             int w = imin(64 >> sh, pw - x0), h = imin(64 >> sh, ph - y0);
-            ora_sao_stats_ctb(&st[ci], src->c[ci].p, src->c[ci].stride, deb->c[ci].p, deb->c[ci].stride, x0, y0, w, h, pw, ph);
+            ora_sao_stats_ctb(&st[ci], src->c[ci].p, src->c[ci].stride, deb->c[ci].p, deb->c[ci].stride, x0, y0, w, h, pw, ph, cfg->sao >= 4 ? 1 : 2, cfg->sao >= 4 ? 4 : 2);
         }
         for (int grp = 0; grp < 2; grp++) {
             int c0 = grp ? 1 : 0, c1 = grp ? 2 : 0;
             int best_cost = 0, best_type = 0, best_class = 0, best_off[3][4], best_band[3];
             memset(best_off, 0, sizeof(best_off)); memset(best_band, 0, sizeof(best_band));
             if (cfg->sao) {
-                for (int k = 0; k < 4; k++) {           /* edge classes */
+                for (int k = 0; k < (cfg->sao >= 4 ? 4 : 2); k++) {           /* edge classes */
                     int total = (lam * 4) >> 4, off[3][4];
                     for (int ci = c0; ci <= c1; ci++)
                         for (int cat = 1; cat <= 4; cat++)

@@ -24,7 +24,8 @@ typedef struct ora_cfg {
     int me_iters;           /* max small-diamond steps */
     int subpel;             /* 0 integer, 1 half, 2 quarter */
     int sign_hiding;
-    int sao;
+    int sao;                /* 0 off; 1..3: BO + EO classes 0,1, statistics from every 2nd row (reference `_fast` statSao variants,
+                               presets ultrafast..fast); 4: BO + all four EO classes, every row */
     int strong_intra;
     int satd;               /* sub-pel cost: SATD (had_c) instead of SAD */
 } ora_cfg;

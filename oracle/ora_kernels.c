@@ -434,14 +434,14 @@ static const int8_t sao_dx[4][2] = {{-1, 1}, {0, 0}, {-1, 1}, {1, -1}};
 static const int8_t sao_dy[4][2] = {{0, 0}, {-1, 1}, {-1, 1}, {-1, 1}};
 static const uint8_t sao_cat[5] = {1, 2, 0, 3, 4};
 void ora_sao_stats_ctb(ora_sao_stats *st, const uint8_t *org, int os, const uint8_t *rec, int rs,
-                       int x0, int y0, int w, int h, int pic_w, int pic_h)
-{
+                       int x0, int y0, int w, int h, int pic_w, int pic_h, int row_step, int n_classes)
+{   /* row_step > 1 = the reference's `_fast` statistics (statSao*_fast_*: rowStep argument of statSaoBoEo01_c) */
     memset(st, 0, sizeof(*st));
-    for (int y = y0; y < y0 + h; y++)
+    for (int y = y0; y < y0 + h; y += row_step)
         for (int x = x0; x < x0 + w; x++) {
             int c = rec[y * rs + x], d = (int)org[y * os + x] - c;
             st->bo_sum[c >> 3] += d; st->bo_cnt[c >> 3]++;
-            for (int k = 0; k < 4; k++) {
+            for (int k = 0; k < n_classes; k++) {
                 int xa = x + sao_dx[k][0], ya = y + sao_dy[k][0], xb = x + sao_dx[k][1], yb = y + sao_dy[k][1];
                 if (xa < 0 || xb < 0 || ya < 0 || yb < 0 || xa >= pic_w || xb >= pic_w || ya >= pic_h || yb >= pic_h) continue;
                 int cat = sao_cat[2 + sgn(c - rec[ya * rs + xa]) + sgn(c - rec[yb * rs + xb])];

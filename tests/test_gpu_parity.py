@@ -146,7 +146,7 @@ def run_oracle_picture(cfg, slice_type, qp, boff, toff, src, ref, prev_cells):
     return o
 
 
-@pytest.mark.parametrize("w,h,qp,sbh,sao,subpel,satd", [(192, 112, 32, 1, 1, 2, 0), (200, 120, 27, 1, 1, 2, 0), (320, 240, 24, 0, 0, 1, 0), (256, 128, 37, 1, 1, 0, 0), (272, 144, 29, 1, 1, 2, 1)])
+@pytest.mark.parametrize("w,h,qp,sbh,sao,subpel,satd", [(192, 112, 32, 1, 1, 2, 0), (200, 120, 27, 1, 1, 2, 0), (320, 240, 24, 0, 0, 1, 0), (256, 128, 37, 1, 4, 0, 0), (272, 144, 29, 1, 3, 2, 1), (336, 208, 30, 1, 4, 2, 0)])
 def test_picture_stages_match_oracle(w, h, qp, sbh, sao, subpel, satd):
     """I picture then 3 P pictures: every stage output of the device (ME field, pre-filter recon, dense levels, final
     recon after deblock+SAO, SAO parameters, CG bitmaps, packed level pool) equals the CPU model."""

@@ -33,7 +33,7 @@ def model_encode(yuv, w, h, n, qp, iper, sbh=1, sao=1, subpel=2):
     return bs[:nb], rec
 
 
-CASES = [("syn_192x112", 192, 112, 5, 32, 16, 1, 1, 2), ("syn_200x120_pad", 200, 120, 4, 27, 2, 1, 1, 2),
+CASES = [("syn_192x112", 192, 112, 5, 32, 16, 1, 3, 2), ("syn_256x144_sao4", 256, 144, 4, 30, 16, 1, 4, 2), ("syn_200x120_pad", 200, 120, 4, 27, 2, 1, 1, 2),
          ("syn_320x240_nosbh", 320, 240, 4, 24, 8, 0, 0, 1), ("syn_416x240_intra", 416, 240, 2, 35, 1, 1, 1, 2)]
 
 
