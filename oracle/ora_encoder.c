@@ -29,7 +29,7 @@ long ora_encode_sequence(const ora_seq_cfg *sc, const uint8_t *yuv, uint8_t *bs,
     ora_cfg cfg = {W, H, sc->me_range, sc->me_iters, sc->subpel, sc->sign_hiding, sc->sao, 1, sc->satd};
     ks_stream_params sp; memset(&sp, 0, sizeof(sp));
     sp.disp_width = sc->width; sp.disp_height = sc->height; sp.width = W; sp.height = H; sp.fps_num = 30; sp.fps_den = 1;
-    sp.sign_hiding = sc->sign_hiding; sp.sao = sc->sao; sp.max_merge_cand = sc->max_merge_cand;
+    sp.sign_hiding = sc->sign_hiding; sp.sao = sc->sao != 0; sp.max_merge_cand = sc->max_merge_cand;
     sp.pps_beta_offset_div2 = 2; sp.pps_tc_offset_div2 = 2; sp.strong_intra_smoothing = 1; sp.log2_max_poc_lsb = 8;
     int cw = W >> 4, ch = H >> 4, ctw = (W + 63) >> 6, cth = (H + 63) >> 6;
     size_t fsz = (size_t)sc->width * sc->height * 3 / 2;
@@ -68,7 +68,7 @@ long ora_encode_sequence(const ora_seq_cfg *sc, const uint8_t *yuv, uint8_t *bs,
         sl.nal_type = is_i ? 19 : 1; sl.slice_type = syn.slice_type; sl.poc = poc; sl.qp = qp;
         sl.num_neg_refs = is_i ? 0 : 1; sl.neg_delta_poc[0] = -1;
         sl.deblock_override = is_i; sl.beta_offset_div2 = boff; sl.tc_offset_div2 = toff;
-        sl.sao_luma = sl.sao_chroma = sc->sao;
+        sl.sao_luma = sl.sao_chroma = sc->sao != 0;
         if ((n = ks_write_slice(&sp, &sl, &syn, scratch, bs + pos, bs_cap - pos)) < 0) return -1;
         pos += n;
         if (recon_out) store_cropped(out, sc->width, sc->height, recon_out + fsz * f);

@@ -238,7 +238,7 @@ def decode_with_reference(bs, nbytes_expected):
         return np.fromfile(o, np.uint8)
 
 
-@pytest.mark.parametrize("w,h,n,qp,preset", [(192, 112, 5, 32, "veryfast"), (416, 240, 6, 27, "veryfast"), (200, 120, 4, 30, "superfast"), (1280, 720, 5, 32, "superfast"), (352, 288, 5, 28, "fast"), (1920, 1080, 3, 27, "veryfast")])
+@pytest.mark.parametrize("w,h,n,qp,preset", [(192, 112, 5, 32, "veryfast"), (416, 240, 6, 27, "veryfast"), (200, 120, 4, 30, "superfast"), (1280, 720, 5, 32, "superfast"), (352, 288, 5, 28, "fast"), (320, 176, 4, 31, "medium"), (1920, 1080, 3, 27, "veryfast")])
 def test_encoder_bitstream_equals_oracle_and_decodes(w, h, n, qp, preset):
     """ks265_encoder_encode_gop: (1) Annex-B bytes == CPU model's bytes, (2) recon == model recon,
     (3) the reference decoder's output of OUR stream == our recon (the vendor's own -hm style self-test)."""
