@@ -37,6 +37,13 @@ typedef struct ks_cell {
 #define KS_F_CBF_CB 4
 #define KS_F_CBF_CR 8
 
+/* B pictures only: list-1 motion + prediction direction of the cell (same raster as ks_cell) */
+typedef struct ks_cell_b {
+    int16_t mvx1, mvy1;      /* quarter-sample luma MV, list 1 (0 when unused) */
+    uint8_t dir;             /* 1 = list 0 only (MV in ks_cell), 2 = list 1 only, 3 = bi-prediction */
+    uint8_t rsv[3];
+} ks_cell_b;
+
 typedef struct ks_sao_param {
     uint8_t type;            /* 0 off, 1 band, 2 edge */
     uint8_t band_or_class;   /* band position (0..31) or EO class (0..3) */
@@ -66,6 +73,7 @@ typedef struct ks_frame_syn {
     const ks_ctu_syn *ctus;  /* ctus_w*ctus_h, raster */
     const int16_t    *levels;/* pool: n_cg * 16 int16, each CG row-major 4x4 */
     uint32_t          n_cg;
+    const ks_cell_b  *cells_b;/* B pictures: cells_w*cells_h entries, else NULL */
 } ks_frame_syn;
 
 #ifdef __cplusplus

@@ -65,7 +65,7 @@ long ks_write_vps(const ks_stream_params *sp, uint8_t *out, size_t cap)
     uint8_t tmp[128]; bitw b; bw_init(&b, tmp, sizeof(tmp));
     bw_put(&b, 0, 4); bw_put(&b, 3, 2); bw_put(&b, 0, 6); bw_put(&b, 0, 3); bw_put(&b, 1, 1); bw_put(&b, 0xffff, 16);
     write_ptl(&b, sp);
-    bw_put(&b, 1, 1); bw_ue(&b, 1); bw_ue(&b, 0); bw_ue(&b, 0);      /* sub_layer_ordering_info: dpb 2, no reorder */
+    bw_put(&b, 1, 1); bw_ue(&b, sp->bframes ? 2 : 1); bw_ue(&b, sp->bframes ? 1 : 0); bw_ue(&b, 0);      /* sub_layer_ordering_info: dpb 2 (3 with B), reorder 0 (1) */
     bw_put(&b, 0, 6); bw_ue(&b, 0); bw_put(&b, 0, 1); bw_put(&b, 0, 1);
     bw_trailing(&b);
     return nal_emit(out, cap, 32, 0, tmp, b.pos);
@@ -83,7 +83,7 @@ long ks_write_sps(const ks_stream_params *sp, uint8_t *out, size_t cap)
     } else bw_put(&b, 0, 1);
     bw_ue(&b, 0); bw_ue(&b, 0);
     bw_ue(&b, (uint32_t)sp->log2_max_poc_lsb - 4);
-    bw_put(&b, 1, 1); bw_ue(&b, 1); bw_ue(&b, 0); bw_ue(&b, 0);
+    bw_put(&b, 1, 1); bw_ue(&b, sp->bframes ? 2 : 1); bw_ue(&b, sp->bframes ? 1 : 0); bw_ue(&b, 0);
     bw_ue(&b, KS_CELL_LOG2 - 3);                 /* log2_min_luma_coding_block_size_minus3 */
     bw_ue(&b, KS_CTU_LOG2 - KS_CELL_LOG2);       /* log2_diff_max_min_luma_coding_block_size */
     bw_ue(&b, 0); bw_ue(&b, KS_MAX_TB_LOG2 - 2); /* TB 4..32 */
@@ -134,7 +134,7 @@ enum {
     CX_SPLIT_CU = 0, CX_SKIP = 3, CX_MERGE_FLAG = 6, CX_MERGE_IDX = 7, CX_PART_MODE = 8, CX_PRED_MODE = 12,
     CX_PREV_INTRA = 13, CX_CHROMA_PRED = 14, CX_MVD = 15, CX_CBF_LUMA = 17, CX_CBF_CHROMA = 19, CX_ROOT_CBF = 24,
     CX_LAST_X = 25, CX_LAST_Y = 43, CX_CSBF = 61, CX_SIG = 65, CX_GT1 = 107, CX_GT2 = 131, CX_MVP_IDX = 137,
-    CX_SAO_MERGE = 138, CX_SAO_TYPE = 139, CX_COUNT = 140
+    CX_SAO_MERGE = 138, CX_SAO_TYPE = 139, CX_INTER_DIR = 140, CX_COUNT = 145
 };
 #define CNU 154
 /* init values (Tables 9-5..9-37), rows: initType 0 (I), 1 (P), 2 (B) */
@@ -147,7 +147,7 @@ static const uint8_t init_values[3][CX_COUNT] = {
    111,111,125,110,110,94,124,108,124,107,125,141,179,153,125,107,125,141,179,153,125,107,125,141,179,153,125,
    140,139,182,182,152,136,152,136,153,136,139,111,136,139,111,
    140,92,137,138,140,152,138,139,153,74,149,92,139,107,122,152,140,179,166,182,140,227,122,197,
-   138,153,136,167,152,152, CNU, 153, 200 },
+   138,153,136,167,152,152, CNU, 153, 200, CNU,CNU,CNU,CNU,CNU },
  { /* P */
    107,139,126, 197,185,201, 110, 122, 154,139,154,154, 149, 154, 152, 140,198, 153,111, 149,107,167,154,154, 79,
    125,110,94,110,95,79,125,111,110,78,110,111,111,95,94,108,123,108,
@@ -156,7 +156,7 @@ static const uint8_t init_values[3][CX_COUNT] = {
    155,154,139,153,139,123,123,63,153,166,183,140,136,153,154,166,183,140,136,153,154,166,183,140,136,153,154,
    170,153,123,123,107,121,107,121,167,151,183,140,151,183,140,
    154,196,196,167,154,152,167,182,182,134,149,136,153,121,136,137,169,194,166,167,154,167,137,182,
-   107,167,91,122,107,167, 168, 153, 185 },
+   107,167,91,122,107,167, 168, 153, 185, 95,79,63,31,31 },
  { /* B */
    107,139,126, 197,185,201, 154, 137, 154,139,154,154, 134, 183, 152, 169,198, 153,111, 149,92,167,154,154, 79,
    125,110,124,110,95,94,125,111,111,79,125,126,111,111,79,108,123,93,
@@ -165,7 +165,7 @@ static const uint8_t init_values[3][CX_COUNT] = {
    170,154,139,153,139,123,123,63,124,166,183,140,136,153,154,166,183,140,136,153,154,166,183,140,136,153,154,
    170,153,138,138,122,121,122,121,167,151,183,140,151,183,140,
    154,196,167,167,154,152,167,182,182,134,149,136,153,121,136,122,169,208,166,167,154,152,167,182,
-   107,167,91,107,107,167, 168, 153, 160 },
+   107,167,91,107,107,167, 168, 153, 160, 95,79,63,31,31 },
 };
 
 typedef struct {
@@ -447,48 +447,92 @@ static void code_residual(slice_enc *e, int comp, int x0c, int y0c, int log2)
     }
 }
 
-/* ---- merge / AMVP candidates (8.5.3.2.2-.7 specialised: P slices, one reference picture, no TMVP) ---- */
+/* ---- merge / AMVP candidates (8.5.3.2.2-.7; one reference picture per list, no TMVP) ---- */
 typedef struct { int16_t x, y; } mv_t;
-static int inter_nb(const ks_frame_syn *s, int xc, int yc, int xn, int yn, mv_t *mv)
+typedef struct { int dir; mv_t mv[2]; } motion_t;          /* dir: bit0 list 0 used, bit1 list 1 used; unused MVs are 0 */
+static motion_t cell_motion(const ks_frame_syn *s, int x, int y)
+{
+    int i = (y >> KS_CELL_LOG2) * s->cells_w + (x >> KS_CELL_LOG2);
+    const ks_cell *c = &s->cells[i];
+    motion_t m; m.dir = 1; m.mv[0].x = c->mvx; m.mv[0].y = c->mvy; m.mv[1].x = m.mv[1].y = 0;
+    if (s->cells_b) {
+        const ks_cell_b *b = &s->cells_b[i];
+        m.dir = b->dir;
+        if (!(m.dir & 1)) m.mv[0].x = m.mv[0].y = 0;
+        if (m.dir & 2) { m.mv[1].x = b->mvx1; m.mv[1].y = b->mvy1; }
+    }
+    return m;
+}
+static int motion_eq(const motion_t *a, const motion_t *b)
+{
+    return a->dir == b->dir && a->mv[0].x == b->mv[0].x && a->mv[0].y == b->mv[0].y && a->mv[1].x == b->mv[1].x && a->mv[1].y == b->mv[1].y;
+}
+static int inter_nb(const ks_frame_syn *s, int xc, int yc, int xn, int yn, motion_t *m)
 {
     if (!avail(s, xc, yc, xn, yn)) return 0;
-    const ks_cell *n = cell_at(s, xn, yn);
-    if (n->flags & KS_F_INTRA) return 0;
-    mv->x = n->mvx; mv->y = n->mvy;
+    if (cell_at(s, xn, yn)->flags & KS_F_INTRA) return 0;
+    *m = cell_motion(s, xn, yn);
     return 1;
 }
-static int merge_list(const ks_frame_syn *s, int x, int y, int size, int maxc, mv_t *list)
+static int merge_list(const ks_frame_syn *s, int x, int y, int size, int maxc, motion_t *list)
 {
-    mv_t a1, b1, b0, a0, b2; int n = 0;
+    motion_t a1, b1, b0, a0, b2; int n = 0;
     int fa1 = inter_nb(s, x, y, x - 1, y + size - 1, &a1);
-    int fb1 = inter_nb(s, x, y, x + size - 1, y - 1, &b1);
-    if (fb1 && fa1 && a1.x == b1.x && a1.y == b1.y) fb1 = 0;
+    int ab1 = inter_nb(s, x, y, x + size - 1, y - 1, &b1), fb1 = ab1;
+    if (fb1 && fa1 && motion_eq(&a1, &b1)) fb1 = 0;
     int fb0 = inter_nb(s, x, y, x + size, y - 1, &b0);
-    int ab1 = avail(s, x, y, x + size - 1, y - 1) && !(cell_at(s, x + size - 1, y - 1)->flags & KS_F_INTRA);
-    if (fb0 && ab1) { const ks_cell *t = cell_at(s, x + size - 1, y - 1); if (t->mvx == b0.x && t->mvy == b0.y) fb0 = 0; }
+    if (fb0 && ab1 && motion_eq(&b1, &b0)) fb0 = 0;
     int fa0 = inter_nb(s, x, y, x - 1, y + size, &a0);
-    if (fa0 && fa1 && a1.x == a0.x && a1.y == a0.y) fa0 = 0;
+    if (fa0 && fa1 && motion_eq(&a1, &a0)) fa0 = 0;
     int fb2 = inter_nb(s, x, y, x - 1, y - 1, &b2);
-    if (fb2 && fa1 && a1.x == b2.x && a1.y == b2.y) fb2 = 0;
-    if (fb2 && ab1) { const ks_cell *t = cell_at(s, x + size - 1, y - 1); if (t->mvx == b2.x && t->mvy == b2.y) fb2 = 0; }
+    if (fb2 && fa1 && motion_eq(&a1, &b2)) fb2 = 0;
+    if (fb2 && ab1 && motion_eq(&b1, &b2)) fb2 = 0;
     if (fa0 + fa1 + fb0 + fb1 == 4) fb2 = 0;
     if (fa1 && n < maxc) list[n++] = a1;
     if (fb1 && n < maxc) list[n++] = b1;
     if (fb0 && n < maxc) list[n++] = b0;
     if (fa0 && n < maxc) list[n++] = a0;
     if (fb2 && n < maxc) list[n++] = b2;
-    while (n < maxc) { list[n].x = 0; list[n].y = 0; n++; }
+    if (s->slice_type == KS_SLICE_B && n > 1 && n < maxc) {        /* 8.5.3.2.4 combined bi-predictive candidates */
+        static const uint8_t l0i[12] = {0, 1, 0, 2, 1, 2, 0, 3, 1, 3, 2, 3}, l1i[12] = {1, 0, 2, 0, 2, 1, 3, 0, 3, 1, 3, 2};
+        int orig = n;
+        for (int k = 0; k < orig * (orig - 1) && n < maxc; k++) {
+            const motion_t *c0 = &list[l0i[k]], *c1 = &list[l1i[k]];
+            if ((c0->dir & 1) && (c1->dir & 2)) {                /* the two lists reference different pictures: always distinct */
+                motion_t m; m.dir = 3; m.mv[0] = c0->mv[0]; m.mv[1] = c1->mv[1];
+                list[n++] = m;
+            }
+        }
+    }
+    while (n < maxc) { memset(&list[n], 0, sizeof(list[n])); list[n].dir = s->slice_type == KS_SLICE_B ? 3 : 1; n++; }   /* 8.5.3.2.5 zero candidates */
     return n;
 }
-static void amvp_list(const ks_frame_syn *s, int x, int y, int size, mv_t list[2])
+static mv_t scale_mv(mv_t mv, int tb, int td)
+{   /* 8.5.3.2.7 (8-179..8-183) */
+    if (td < -128) td = -128; if (td > 127) td = 127; if (tb < -128) tb = -128; if (tb > 127) tb = 127;
+    int tx = (16384 + (abs(td) >> 1)) / td;
+    int dsf = (tb * tx + 32) >> 6; if (dsf < -4096) dsf = -4096; if (dsf > 4095) dsf = 4095;
+    mv_t r; int v;
+    v = dsf * mv.x; v = (v < 0 ? -1 : 1) * ((abs(v) + 127) >> 8); r.x = (int16_t)(v < -32768 ? -32768 : v > 32767 ? 32767 : v);
+    v = dsf * mv.y; v = (v < 0 ? -1 : 1) * ((abs(v) + 127) >> 8); r.y = (int16_t)(v < -32768 ? -32768 : v > 32767 ? 32767 : v);
+    return r;
+}
+/* AMVP list of list X for the 2Nx2N PU at (x,y); dpoc[l] = POC(cur) - POC(RefPicList_l[0]) */
+static void amvp_list(const ks_frame_syn *s, int x, int y, int size, int X, const int dpoc[2], mv_t list[2])
 {
-    mv_t a, b, t; int fa = 0, fb = 0, n = 0;
-    int sa0 = inter_nb(s, x, y, x - 1, y + size, &t); if (sa0) { a = t; fa = 1; }
-    int sa1 = inter_nb(s, x, y, x - 1, y + size - 1, &t); if (sa1 && !fa) { a = t; fa = 1; }
-    if (inter_nb(s, x, y, x + size, y - 1, &t)) { b = t; fb = 1; }
-    if (!fb && inter_nb(s, x, y, x + size - 1, y - 1, &t)) { b = t; fb = 1; }
-    if (!fb && inter_nb(s, x, y, x - 1, y - 1, &t)) { b = t; fb = 1; }
-    if (!(sa0 || sa1) && fb) { a = b; fa = 1; }       /* isScaledFlag == 0: A takes B (B re-derived identically) */
+    const int Y = 1 - X, nbx[5] = {x - 1, x - 1, x + size, x + size - 1, x - 1}, nby[5] = {y + size, y + size - 1, y - 1, y - 1, y - 1};
+    motion_t nb[5]; int av[5];
+    for (int k = 0; k < 5; k++) av[k] = inter_nb(s, x, y, nbx[k], nby[k], &nb[k]);      /* A0, A1, B0, B1, B2 */
+    mv_t a = {0, 0}, b = {0, 0}; int fa = 0, fb = 0, n = 0;
+    for (int k = 0; k < 2 && !fa; k++) if (av[k] && (nb[k].dir & (1 << X))) { a = nb[k].mv[X]; fa = 1; }
+    for (int k = 0; k < 2 && !fa; k++) if (av[k]) { a = scale_mv(nb[k].mv[Y], dpoc[X], dpoc[Y]); fa = 1; }       /* only list Y is left: scaled */
+    int scaled = av[0] || av[1];
+    for (int k = 2; k < 5 && !fb; k++) if (av[k] && (nb[k].dir & (1 << X))) { b = nb[k].mv[X]; fb = 1; }
+    if (!scaled && fb) { a = b; fa = 1; }
+    if (!scaled) {
+        fb = 0;
+        for (int k = 2; k < 5 && !fb; k++) if (av[k]) { b = (nb[k].dir & (1 << X)) ? nb[k].mv[X] : scale_mv(nb[k].mv[Y], dpoc[X], dpoc[Y]); fb = 1; }
+    }
     if (fa) list[n++] = a;
     if (fb && !(fa && a.x == b.x && a.y == b.y)) list[n++] = b;
     while (n < 2) { list[n].x = 0; list[n].y = 0; n++; }
@@ -566,10 +610,11 @@ static void code_cu(slice_enc *e, int x, int y, int log2)
     const ks_cell *cu = cell_at(s, x, y);
     int size = 1 << log2, intra = cu->flags & KS_F_INTRA;
     if (s->slice_type != KS_SLICE_I) {
-        mv_t ml[5]; int merge_idx = -1;
+        motion_t ml[5], cur; int merge_idx = -1;
         if (!intra) {
+            cur = cell_motion(s, x, y);
             int n = merge_list(s, x, y, size, e->sp->max_merge_cand, ml);
-            for (int k = 0; k < n; k++) if (ml[k].x == cu->mvx && ml[k].y == cu->mvy) { merge_idx = k; break; }
+            for (int k = 0; k < n; k++) if (motion_eq(&ml[k], &cur)) { merge_idx = k; break; }
         }
         int any = intra ? 1 : cu_cbf_any(s, x, y, size);
         int skip = !intra && merge_idx >= 0 && !any;
@@ -593,12 +638,21 @@ static void code_cu(slice_enc *e, int x, int y, int log2)
         if (!intra) {
             cb_bin(c, CX_PART_MODE, 1);              /* PART_2Nx2N */
             cb_bin(c, CX_MERGE_FLAG, 0);
-            mv_t pl[2]; amvp_list(s, x, y, size, pl);
-            int c0 = mvd_bits(cu->mvx - pl[0].x) + mvd_bits(cu->mvy - pl[0].y);
-            int c1 = mvd_bits(cu->mvx - pl[1].x) + mvd_bits(cu->mvy - pl[1].y);
-            int idx = c1 < c0;
-            code_mvd(c, cu->mvx - pl[idx].x, cu->mvy - pl[idx].y);
-            cb_bin(c, CX_MVP_IDX, idx);
+            if (s->slice_type == KS_SLICE_B) {       /* inter_pred_idc (9.3.4.2.2): nPbW+nPbH != 12 */
+                int depth = KS_CTU_LOG2 - log2;
+                cb_bin(c, CX_INTER_DIR + depth, cur.dir == 3);
+                if (cur.dir != 3) cb_bin(c, CX_INTER_DIR + 4, cur.dir == 2);
+            }
+            const int dpoc[2] = {-e->sl->neg_delta_poc[0], -e->sl->pos_delta_poc[0]};
+            for (int X = 0; X < 2; X++) {
+                if (!(cur.dir & (1 << X))) continue;
+                mv_t pl[2]; amvp_list(s, x, y, size, X, dpoc, pl);
+                int c0 = mvd_bits(cur.mv[X].x - pl[0].x) + mvd_bits(cur.mv[X].y - pl[0].y);
+                int c1 = mvd_bits(cur.mv[X].x - pl[1].x) + mvd_bits(cur.mv[X].y - pl[1].y);
+                int idx = c1 < c0;
+                code_mvd(c, cur.mv[X].x - pl[idx].x, cur.mv[X].y - pl[idx].y);
+                cb_bin(c, CX_MVP_IDX, idx);
+            }
             cb_bin(c, CX_ROOT_CBF, any);
             if (any) code_transform_tree(e, x, y, log2, 0);
             return;
@@ -710,13 +764,16 @@ long ks_write_slice(const ks_stream_params *sp, const ks_slice_params *sl, const
     if (!idr) {
         bw_put(&b, (uint32_t)sl->poc & ((1u << sp->log2_max_poc_lsb) - 1), sp->log2_max_poc_lsb);
         bw_put(&b, 0, 1);                        /* short_term_ref_pic_set_sps_flag = 0: explicit RPS (like the reference) */
-        bw_ue(&b, (uint32_t)sl->num_neg_refs); bw_ue(&b, 0);
+        bw_ue(&b, (uint32_t)sl->num_neg_refs); bw_ue(&b, (uint32_t)sl->num_pos_refs);
         int prev = 0;
         for (int i = 0; i < sl->num_neg_refs; i++) { bw_ue(&b, (uint32_t)(prev - sl->neg_delta_poc[i] - 1)); bw_put(&b, 1, 1); prev = sl->neg_delta_poc[i]; }
+        prev = 0;
+        for (int i = 0; i < sl->num_pos_refs; i++) { bw_ue(&b, (uint32_t)(sl->pos_delta_poc[i] - prev - 1)); bw_put(&b, 1, 1); prev = sl->pos_delta_poc[i]; }
     }
     if (sp->sao) { bw_put(&b, (uint32_t)sl->sao_luma, 1); bw_put(&b, (uint32_t)sl->sao_chroma, 1); }
     if (sl->slice_type != KS_SLICE_I) {
         bw_put(&b, 1, 1); bw_ue(&b, 0);          /* num_ref_idx_active_override: 1 active ref (reference does the same) */
+        if (sl->slice_type == KS_SLICE_B) { bw_ue(&b, 0); bw_put(&b, 0, 1); }      /* num_ref_idx_l1_active_minus1 = 0, mvd_l1_zero_flag = 0 */
         bw_ue(&b, (uint32_t)(5 - sp->max_merge_cand));
     }
     bw_se(&b, sl->qp - 26);

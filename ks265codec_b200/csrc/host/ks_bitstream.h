@@ -25,6 +25,7 @@ typedef struct ks_stream_params {
     int pps_beta_offset_div2, pps_tc_offset_div2;
     int strong_intra_smoothing;
     int log2_max_poc_lsb;            /* 8 */
+    int bframes;                     /* > 0: streams carry B pictures (DPB 3, one picture of reordering) */
 } ks_stream_params;
 
 typedef struct ks_slice_params {
@@ -34,7 +35,9 @@ typedef struct ks_slice_params {
     int poc;
     int qp;
     int num_neg_refs;                /* short-term RPS: negative pictures (delta POCs, all used by curr) */
-    int neg_delta_poc[4];            /* e.g. {-1} */
+    int neg_delta_poc[4];            /* e.g. {-1}; [0] is RefPicList0[0] */
+    int num_pos_refs;                /* short-term RPS: positive pictures (B pictures) */
+    int pos_delta_poc[4];            /* e.g. {+3}; [0] is RefPicList1[0] */
     int deblock_override;            /* slice-level override of beta/tc */
     int beta_offset_div2, tc_offset_div2;
     int sao_luma, sao_chroma;

@@ -172,7 +172,7 @@ void ora_intra_picture(const ora_cfg *cfg, int qp, const ora_pic *src, ora_pic *
 static const int8_t dia_dx[4] = {0, 0, -1, 1}, dia_dy[4] = {-1, 1, 0, 0};
 static const int8_t sq_dx[8] = {-1, 0, 1, -1, 1, -1, 0, 1}, sq_dy[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
 
-static void me_cell(const ora_cfg *cfg, int lam, const ora_plane *src, const ora_plane *ref, int x0, int y0, int tpx, int tpy, int *omx, int *omy)
+static int me_cell(const ora_cfg *cfg, int lam, const ora_plane *src, const ora_plane *ref, int x0, int y0, int tpx, int tpy, int *omx, int *omy)
 {   /* a5 (start point) + a3 (small diamond, x264 DIA) + a6 (half/quarter refinement with real interpolation, SAD cost) */
     const uint8_t *s = src->p + (size_t)y0 * src->stride + x0;
     const uint8_t *r0 = ref->p + (size_t)y0 * ref->stride + x0;
@@ -208,6 +208,7 @@ static void me_cell(const ora_cfg *cfg, int lam, const ora_plane *src, const ora
         if (bk >= 0) { mx += sq_dx[bk] * step; my += sq_dy[bk] * step; bc = lc; }
     }
     *omx = mx; *omy = my;
+    return bc;
 #undef ICOST
 #undef MVCOST
 }
@@ -273,6 +274,100 @@ void ora_inter_picture(const ora_cfg *cfg, int qp, const ora_pic *src, const ora
     }
 }
 
+/* ------------------------------------------------------------------ B picture (a7 bi-prediction) - */
+static int scale_pred(int mv, int num, int den) { return den ? (mv * num) / den : 0; }       /* C division: truncates toward zero */
+
+/* residual coding of one CU whose prediction is already assembled in pred[3] (pitch 64) */
+static void recon_cu_from_pred(const ora_cfg *cfg, int qp, int qpc, const ora_pic *src, uint8_t (*pred)[64 * 64], ora_pic *rec,
+                               ks_cell *cells, ora_levels *lv, int x0, int y0, int log2)
+{
+    int S = 1 << log2, W = cfg->width, cw = W >> 4;
+    int T = imin(S, 32), tl = log2 > 5 ? 5 : log2;
+    for (int ty = 0; ty < S; ty += T) for (int tx = 0; tx < S; tx += T) {
+        int x = x0 + tx, y = y0 + ty, f = 0;
+        if (code_tb(cfg, qp, 0, tl, 0, src->c[0].p + (size_t)y * src->c[0].stride + x, src->c[0].stride, pred[0] + ty * 64 + tx, 64,
+                    rec->c[0].p + (size_t)y * rec->c[0].stride + x, rec->c[0].stride, lv->c[0] + (size_t)y * W + x, W)) f |= KS_F_CBF_Y;
+        for (int ci = 1; ci < 3; ci++) {
+            int xc = x / 2, yc = y / 2;
+            if (code_tb(cfg, qpc, 0, tl - 1, 0, src->c[ci].p + (size_t)yc * src->c[ci].stride + xc, src->c[ci].stride,
+                        pred[ci] + (ty / 2) * 64 + tx / 2, 64, rec->c[ci].p + (size_t)yc * rec->c[ci].stride + xc, rec->c[ci].stride,
+                        lv->c[ci] + (size_t)yc * (W / 2) + xc, W / 2)) f |= ci == 1 ? KS_F_CBF_CB : KS_F_CBF_CR;
+        }
+        for (int yy = y; yy < y + T; yy += 16) for (int xx = x; xx < x + T; xx += 16) {
+            ks_cell *c = &cells[(yy >> 4) * cw + (xx >> 4)];
+            c->cu_log2 = (uint8_t)log2; c->flags = (uint8_t)f; c->intra_mode = 0; c->rsv = 0;
+        }
+    }
+}
+static void predict_cell(const ora_pic *ref0, const ora_pic *ref1, int x0, int y0, int n, int dir, int mx0, int my0, int mx1, int my1,
+                         uint8_t (*pred)[64 * 64], int px, int py)
+{   /* n x n luma (+ n/2 chroma) prediction of a block at picture (x0,y0), written at (px,py) of the CU buffers */
+    for (int ci = 0; ci < 3; ci++) {
+        int sh = ci ? 1 : 0, w = n >> sh, bx = x0 >> sh, by = y0 >> sh;
+        uint8_t *d = pred[ci] + (py >> sh) * 64 + (px >> sh);
+        const ora_plane *r0 = &ref0->c[ci], *r1 = &ref1->c[ci];
+        if (dir == 3) {
+            int16_t a[64 * 64], b[64 * 64];
+            if (ci == 0) { ora_mc_luma_16(a, 64, r0->p + (size_t)by * r0->stride + bx, r0->stride, w, w, mx0, my0); ora_mc_luma_16(b, 64, r1->p + (size_t)by * r1->stride + bx, r1->stride, w, w, mx1, my1); }
+            else { ora_mc_chroma_16(a, 64, r0->p + (size_t)by * r0->stride + bx, r0->stride, w, w, mx0, my0); ora_mc_chroma_16(b, 64, r1->p + (size_t)by * r1->stride + bx, r1->stride, w, w, mx1, my1); }
+            ora_weighted_bi(d, 64, a, b, 64, w, w);
+        } else {
+            const ora_plane *r = dir == 1 ? r0 : r1; int mx = dir == 1 ? mx0 : mx1, my = dir == 1 ? my0 : my1;
+            if (ci == 0) ora_mc_luma(d, 64, r->p + (size_t)by * r->stride + bx, r->stride, w, w, mx, my);
+            else ora_mc_chroma(d, 64, r->p + (size_t)by * r->stride + bx, r->stride, w, w, mx, my);
+        }
+    }
+}
+/* B picture between two anchors: list 0 = ref0 (earlier), list 1 = ref1 (later).  anchor_cells = motion field of the later
+ * anchor (a P picture predicted from ref0 over `da` pictures); d0 = POC(cur) - POC(ref0).  Predictors: the anchor's vector
+ * scaled to each list.  Per cell: best of list 0 / list 1 / bi-prediction (DefaultWeightedBi_c) by SAD(or SATD)+lambda*bits. */
+void ora_b_picture(const ora_cfg *cfg, int qp, const ora_pic *src, const ora_pic *ref0, const ora_pic *ref1, const ks_cell *anchor_cells,
+                   int d0, int da, ora_pic *rec, ks_cell *cells, ks_cell_b *cells_b, ora_levels *lv)
+{
+    build_scans();
+    int W = cfg->width, H = cfg->height, cw = W >> 4, ch = H >> 4;
+    int lam = ora_lambda_sad_q4[qp], qpc = ora_chroma_qp[qp];
+    static uint8_t pred[3][64 * 64];
+    for (int cy = 0; cy < ch; cy++) for (int cx = 0; cx < cw; cx++) {
+        int ax = 0, ay = 0;
+        if (anchor_cells && !(anchor_cells[cy * cw + cx].flags & KS_F_INTRA)) { ax = anchor_cells[cy * cw + cx].mvx; ay = anchor_cells[cy * cw + cx].mvy; }
+        int t0x = scale_pred(ax, d0, da), t0y = scale_pred(ay, d0, da), t1x = scale_pred(ax, d0 - da, da), t1y = scale_pred(ay, d0 - da, da);
+        int m0x, m0y, m1x, m1y;
+        int c0 = me_cell(cfg, lam, &src->c[0], &ref0->c[0], cx << 4, cy << 4, t0x, t0y, &m0x, &m0y);
+        int c1 = me_cell(cfg, lam, &src->c[0], &ref1->c[0], cx << 4, cy << 4, t1x, t1y, &m1x, &m1y);
+        predict_cell(ref0, ref1, cx << 4, cy << 4, 16, 3, m0x, m0y, m1x, m1y, pred, 0, 0);
+        const uint8_t *s = src->c[0].p + (size_t)(cy << 4) * src->c[0].stride + (cx << 4);
+        int cb = (int)(cfg->satd && cfg->subpel > 0 ? ora_satd(s, pred[0], src->c[0].stride, 64, 16, 16) : ora_sad(s, pred[0], src->c[0].stride, 64, 16, 16))
+                 + ((lam * (mvbits(m0x - t0x) + mvbits(m0y - t0y))) >> 4) + ((lam * (mvbits(m1x - t1x) + mvbits(m1y - t1y))) >> 4);
+        int dir = 1, best = c0;
+        if (c1 < best) { best = c1; dir = 2; }
+        if (cb < best) { best = cb; dir = 3; }
+        ks_cell *c = &cells[cy * cw + cx]; ks_cell_b *b = &cells_b[cy * cw + cx];
+        memset(c, 0, sizeof(*c)); memset(b, 0, sizeof(*b));
+        c->cu_log2 = 4; b->dir = (uint8_t)dir;
+        if (dir & 1) { c->mvx = (int16_t)m0x; c->mvy = (int16_t)m0y; }
+        if (dir & 2) { b->mvx1 = (int16_t)m1x; b->mvy1 = (int16_t)m1y; }
+    }
+#define SAMEM(i, j) (cells[i].mvx == cells[j].mvx && cells[i].mvy == cells[j].mvy && cells_b[i].dir == cells_b[j].dir && cells_b[i].mvx1 == cells_b[j].mvx1 && cells_b[i].mvy1 == cells_b[j].mvy1)
+    for (int y = 0; y + 32 <= H; y += 32) for (int x = 0; x + 32 <= W; x += 32) {
+        int a = (y >> 4) * cw + (x >> 4);
+        if (SAMEM(a, a + 1) && SAMEM(a, a + cw) && SAMEM(a, a + cw + 1)) cells[a].cu_log2 = cells[a + 1].cu_log2 = cells[a + cw].cu_log2 = cells[a + cw + 1].cu_log2 = 5;
+    }
+    for (int y = 0; y + 64 <= H; y += 64) for (int x = 0; x + 64 <= W; x += 64) {
+        int a = (y >> 4) * cw + (x >> 4), ok = 1;
+        for (int j = 0; j < 4 && ok; j++) for (int i = 0; i < 4; i++) { int t = a + j * cw + i; if (cells[t].cu_log2 != 5 || !SAMEM(a, t)) { ok = 0; break; } }
+        if (ok) for (int j = 0; j < 4; j++) for (int i = 0; i < 4; i++) cells[a + j * cw + i].cu_log2 = 6;
+    }
+#undef SAMEM
+    for (int y = 0; y < H; y += 16) for (int x = 0; x < W; x += 16) {
+        int i = (y >> 4) * cw + (x >> 4);
+        int log2 = cells[i].cu_log2, S = 1 << log2;
+        if ((x & (S - 1)) || (y & (S - 1))) continue;
+        predict_cell(ref0, ref1, x, y, S, cells_b[i].dir, cells[i].mvx, cells[i].mvy, cells_b[i].mvx1, cells_b[i].mvy1, pred, 0, 0);
+        recon_cu_from_pred(cfg, qp, qpc, src, pred, rec, cells, lv, x, y, log2);
+    }
+}
+
 /* ------------------------------------------------------------------ deblocking (a16) ------------- */
 static int is_tu_edge(const ks_cell *p, const ks_cell *q, int xp, int yp, int xq, int yq, int pos)
 {   /* pos = coordinate (x for vertical edges, y for horizontal) of the edge, a multiple of 16 */
@@ -281,14 +376,22 @@ static int is_tu_edge(const ks_cell *p, const ks_cell *q, int xp, int yp, int xq
     if (!same) return 1;
     return p->cu_log2 == 6 && (pos & 31) == 0;
 }
-static int edge_bs(const ks_cell *p, const ks_cell *q)
-{
+static int edge_bs(const ks_cell *p, const ks_cell *q, const ks_cell_b *pb, const ks_cell_b *qb)
+{   /* spec 8.7.2.4; with B pictures the two lists always name different pictures, so motion compares list by list */
     if ((p->flags | q->flags) & KS_F_INTRA) return 2;
     if ((p->flags | q->flags) & KS_F_CBF_Y) return 1;
-    if (iabs(p->mvx - q->mvx) >= 4 || iabs(p->mvy - q->mvy) >= 4) return 1;
+    int dp = pb ? pb->dir : 1, dq = qb ? qb->dir : 1;
+    if (dp != dq) return 1;                       /* different reference pictures or number of motion vectors */
+    if ((dp & 1) && (iabs(p->mvx - q->mvx) >= 4 || iabs(p->mvy - q->mvy) >= 4)) return 1;
+    if ((dp & 2) && (iabs(pb->mvx1 - qb->mvx1) >= 4 || iabs(pb->mvy1 - qb->mvy1) >= 4)) return 1;
     return 0;
 }
+void ora_deblock_picture_b(const ora_cfg *cfg, int qp, int beta_off, int tc_off, ora_pic *rec, const ks_cell *cells, const ks_cell_b *cells_b);
 void ora_deblock_picture(const ora_cfg *cfg, int qp, int beta_off, int tc_off, ora_pic *rec, const ks_cell *cells)
+{
+    ora_deblock_picture_b(cfg, qp, beta_off, tc_off, rec, cells, NULL);
+}
+void ora_deblock_picture_b(const ora_cfg *cfg, int qp, int beta_off, int tc_off, ora_pic *rec, const ks_cell *cells, const ks_cell_b *cells_b)
 {
     int W = cfg->width, H = cfg->height, cw = W >> 4;
     int beta = ora_beta_table[clip3(0, 51, qp + (beta_off << 1))];
@@ -299,7 +402,7 @@ void ora_deblock_picture(const ora_cfg *cfg, int qp, int beta_off, int tc_off, o
                 int xq = dir ? t : e, yq = dir ? e : t, xp = dir ? t : e - 1, yp = dir ? e - 1 : t;
                 const ks_cell *p = &cells[(yp >> 4) * cw + (xp >> 4)], *q = &cells[(yq >> 4) * cw + (xq >> 4)];
                 if (!is_tu_edge(p, q, xp, yp, xq, yq, e)) continue;
-                int bs = edge_bs(p, q);
+                int bs = edge_bs(p, q, cells_b ? &cells_b[(yp >> 4) * cw + (xp >> 4)] : NULL, cells_b ? &cells_b[(yq >> 4) * cw + (xq >> 4)] : NULL);
                 if (!bs) continue;
                 int tc = ora_tc_table[clip3(0, 53, qp + 2 * (bs - 1) + (tc_off << 1))];
                 ora_plane *pl = &rec->c[0];

@@ -45,7 +45,10 @@ typedef struct ora_levels { int16_t *c[3]; } ora_levels;
 void ora_intra_picture(const ora_cfg *cfg, int qp, const ora_pic *src, ora_pic *rec, ks_cell *cells, ora_levels *lv);
 void ora_inter_picture(const ora_cfg *cfg, int qp, const ora_pic *src, const ora_pic *ref, const ks_cell *prev_cells,
                        ora_pic *rec, ks_cell *cells, ora_levels *lv);
+void ora_b_picture(const ora_cfg *cfg, int qp, const ora_pic *src, const ora_pic *ref0, const ora_pic *ref1, const ks_cell *anchor_cells,
+                   int d0, int da, ora_pic *rec, ks_cell *cells, ks_cell_b *cells_b, ora_levels *lv);
 void ora_deblock_picture(const ora_cfg *cfg, int qp, int beta_offset_div2, int tc_offset_div2, ora_pic *rec, const ks_cell *cells);
+void ora_deblock_picture_b(const ora_cfg *cfg, int qp, int beta_offset_div2, int tc_offset_div2, ora_pic *rec, const ks_cell *cells, const ks_cell_b *cells_b);
 void ora_sao_picture(const ora_cfg *cfg, int qp, const ora_pic *src, const ora_pic *deblocked, ora_pic *out, ks_ctu_syn *ctus);
 /* pack dense levels into the boundary format (CG bitmaps + pool); returns number of CGs */
 uint32_t ora_pack_levels(const ora_cfg *cfg, const ora_levels *lv, ks_ctu_syn *ctus, int16_t *pool);

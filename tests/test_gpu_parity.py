@@ -27,7 +27,7 @@ class OraCfg(C.Structure):
 
 
 class SeqCfg(C.Structure):
-    _fields_ = [(n, C.c_int) for n in "width height nframes qp iper fixqp me_range me_iters subpel sign_hiding sao max_merge_cand satd".split()]
+    _fields_ = [(n, C.c_int) for n in "width height nframes qp iper fixqp me_range me_iters subpel sign_hiding sao max_merge_cand satd bframes".split()]
 
 
 def first_diff(a, b, what, shape=None):

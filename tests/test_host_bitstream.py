@@ -20,7 +20,7 @@ DEC = os.path.join(ROOT, "oracle", "_ref", "appdecoder")
 
 
 class SeqCfg(C.Structure):
-    _fields_ = [(n, C.c_int) for n in "width height nframes qp iper fixqp me_range me_iters subpel sign_hiding sao max_merge_cand satd".split()]
+    _fields_ = [(n, C.c_int) for n in "width height nframes qp iper fixqp me_range me_iters subpel sign_hiding sao max_merge_cand satd bframes".split()]
 
 
 def model_encode(yuv, w, h, n, qp, iper, sbh=1, sao=1, subpel=2):
