@@ -29,6 +29,7 @@ typedef struct ks265_config {
     int satd;                   /* sub-pel cost metric: 0 SAD (ultrafast..veryfast), 1 SATD (fast..placebo), like the reference */
     int device;                 /* CUDA device ordinal */
     int psnr;                   /* compute per-plane SSE on the device */
+    int bframes;                /* -bframes: B pictures between anchors (0 = IDR + P...; default 0 this round) */
 } ks265_config;
 
 typedef struct ks265_gop_stats {

@@ -41,7 +41,7 @@ typedef struct ks_gpu_cfg {
 } ks_gpu_cfg;
 
 typedef struct ks_pic_params {
-    int slice_type;     /* KS_SLICE_I / KS_SLICE_P */
+    int slice_type;     /* KS_SLICE_I / KS_SLICE_P / KS_SLICE_B */
     int qp;
     int src_slot;       /* source picture (ks_gpu_upload_frame*) */
     int ref_slot;       /* reconstructed picture used as list-0 reference (-1 for I) */
@@ -50,6 +50,11 @@ typedef struct ks_pic_params {
     int prev_syn_slot;  /* syntax slot of the previous coded picture: its MVs seed the search (-1: none) */
     int beta_offset_div2, tc_offset_div2;
     int want_sse;       /* accumulate per-plane SSE vs source (for -psnr) */
+    /* B pictures (reference: motionSearchB E@0x47c710 / interMeBiFull_c E@0x480040 / DefaultWeightedBi_c E@0x4350f0): */
+    int ref1_slot;      /* reconstructed picture used as list-1 reference (the LATER anchor); ref_slot is the earlier one */
+    int dist_l0;        /* POC(cur) - POC(list-0 reference) > 0 */
+    int dist_anchor;    /* POC(list-1 reference) - POC(list-0 reference); prev_syn_slot names the later anchor, whose vectors
+                           (spanning dist_anchor pictures) are scaled to seed both searches */
 } ks_pic_params;
 
 /* results of one picture: pointers into pinned host memory owned by the context, valid until the syntax slot is reused */
@@ -59,6 +64,7 @@ typedef struct ks_pic_out {
     const int16_t    *levels;
     uint32_t          n_cg;
     uint64_t          sse[3];
+    const ks_cell_b  *cells_b;     /* B pictures, else NULL */
 } ks_pic_out;
 
 /* replaces: createHevcEncoder/createModules (E@0x4b44f0/0x4b3380) device-side state; width/height = display size */

@@ -37,18 +37,22 @@ class KsGpuCfg(C.Structure):
 
 class KsPicParams(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("slice_type", "qp", "src_slot", "ref_slot", "out_slot", "syn_slot", "prev_syn_slot",
-                                       "beta_offset_div2", "tc_offset_div2", "want_sse")]
+                                       "beta_offset_div2", "tc_offset_div2", "want_sse", "ref1_slot", "dist_l0", "dist_anchor")]
+
+
+class KsCellB(C.Structure):
+    _fields_ = [("mvx1", C.c_int16), ("mvy1", C.c_int16), ("dir", C.c_uint8), ("rsv", C.c_uint8 * 3)]
 
 
 class KsPicOut(C.Structure):
     _fields_ = [("cells", C.POINTER(KsCell)), ("ctus", C.POINTER(KsCtuSyn)), ("levels", C.POINTER(C.c_int16)),
-                ("n_cg", C.c_uint32), ("sse", C.c_uint64 * 3)]
+                ("n_cg", C.c_uint32), ("sse", C.c_uint64 * 3), ("cells_b", C.POINTER(KsCellB))]
 
 
 class Ks265Config(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("fps", C.c_double), ("preset", C.c_int), ("rc", C.c_int),
                 ("qp", C.c_int), ("iper", C.c_int), ("fixqp", C.c_int), ("sao", C.c_int), ("sign_hiding", C.c_int),
-                ("me_range", C.c_int), ("me_iters", C.c_int), ("subpel", C.c_int), ("satd", C.c_int), ("device", C.c_int), ("psnr", C.c_int)]
+                ("me_range", C.c_int), ("me_iters", C.c_int), ("subpel", C.c_int), ("satd", C.c_int), ("device", C.c_int), ("psnr", C.c_int), ("bframes", C.c_int)]
 
 
 class Ks265GopStats(C.Structure):

@@ -17,7 +17,8 @@ static const uint8_t k_chroma_qp[58] = {0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,16
 
 #define KS_NSTAGE 6   /* me, recon_inter, recon_intra, deblock, sao, pack */
 struct ks_syn_slot {
-    ks_cell *d_cells; ks_ctu_syn *d_ctus; int16_t *d_pool; uint32_t *d_ncg; unsigned long long *d_sse;
+    ks_cell *d_cells; ks_ctu_syn *d_ctus; int16_t *d_pool; uint32_t *d_ncg; unsigned long long *d_sse; ks_cell_b *d_cells_b;
+    ks_cell_b *h_cells_b; int is_b;
     ks_cell *h_cells; ks_ctu_syn *h_ctus; int16_t *h_pool; uint32_t *h_ncg; unsigned long long *h_sse;
     cudaEvent_t done; int pending;
     cudaEvent_t ev[KS_NSTAGE + 1]; int stage_of[KS_NSTAGE + 1]; int nev; size_t d2h_bytes;
@@ -30,6 +31,8 @@ struct ks_gpu_ctx {
     uint8_t **d_src, **d_rec;   /* slots */
     uint8_t *d_pre;             /* pre-filter reconstruction / deblocked in place */
     uint8_t *d_pred;            /* inter prediction planes written by the motion search */
+    uint8_t *d_pred1;           /* B pictures: list-1 prediction planes */
+    ks_cell *d_cells1; int *d_cost0, *d_cost1;
     int16_t *d_lev;
     uint32_t *d_counts;
     int *d_sync;
@@ -82,6 +85,10 @@ extern "C" ks_gpu_ctx *ks_gpu_open(int device, int width, int height, const ks_g
         for (int i = 0; i < c->cfg.n_rec_slots; i++) ok = ok && cudaMalloc(&c->d_rec[i], c->fsz) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_pre, c->fsz) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_pred, c->fsz) == cudaSuccess;
+        ok = ok && cudaMalloc(&c->d_pred1, c->fsz) == cudaSuccess;
+        ok = ok && cudaMalloc(&c->d_cells1, (size_t)c->cw * c->ch * sizeof(ks_cell)) == cudaSuccess;
+        ok = ok && cudaMalloc(&c->d_cost0, (size_t)c->cw * c->ch * sizeof(int)) == cudaSuccess;
+        ok = ok && cudaMalloc(&c->d_cost1, (size_t)c->cw * c->ch * sizeof(int)) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_lev, c->fsz * 2) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_counts, sizeof(uint32_t) * c->ctw * c->cth) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_sync, sizeof(int) * ((size_t)c->ctw * c->cth + 1)) == cudaSuccess;
@@ -92,6 +99,8 @@ extern "C" ks_gpu_ctx *ks_gpu_open(int device, int width, int height, const ks_g
         for (int i = 0; i < c->cfg.n_syn_slots && ok; i++) {
             ks_syn_slot *s = &c->syn[i];
             ok = ok && cudaMalloc(&s->d_cells, ncell * sizeof(ks_cell)) == cudaSuccess;
+            ok = ok && cudaMalloc(&s->d_cells_b, ncell * sizeof(ks_cell_b)) == cudaSuccess;
+            ok = ok && cudaHostAlloc(&s->h_cells_b, ncell * sizeof(ks_cell_b), cudaHostAllocDefault) == cudaSuccess;
             ok = ok && cudaMalloc(&s->d_ctus, nctu * sizeof(ks_ctu_syn)) == cudaSuccess;
             ok = ok && cudaMalloc(&s->d_pool, poolb) == cudaSuccess;
             ok = ok && cudaMalloc(&s->d_ncg, sizeof(uint32_t)) == cudaSuccess;
@@ -121,11 +130,11 @@ extern "C" void ks_gpu_close(ks_gpu_ctx *c)
     if (c->st) cudaStreamSynchronize(c->st);
     if (c->d_src) for (int i = 0; i < c->cfg.n_src_slots; i++) cudaFree(c->d_src[i]);
     if (c->d_rec) for (int i = 0; i < c->cfg.n_rec_slots; i++) cudaFree(c->d_rec[i]);
-    cudaFree(c->d_pre); cudaFree(c->d_pred); cudaFree(c->d_lev); cudaFree(c->d_counts); cudaFree(c->d_sync); cudaFree(c->d_stage);
+    cudaFree(c->d_pre); cudaFree(c->d_pred); cudaFree(c->d_pred1); cudaFree(c->d_cells1); cudaFree(c->d_cost0); cudaFree(c->d_cost1); cudaFree(c->d_lev); cudaFree(c->d_counts); cudaFree(c->d_sync); cudaFree(c->d_stage);
     for (int i = 0; i < 2; i++) { if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]); if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]); }
     if (c->syn) for (int i = 0; i < c->cfg.n_syn_slots; i++) {
         ks_syn_slot *s = &c->syn[i];
-        cudaFree(s->d_cells); cudaFree(s->d_ctus); cudaFree(s->d_pool); cudaFree(s->d_ncg); cudaFree(s->d_sse);
+        cudaFree(s->d_cells); cudaFree(s->d_cells_b); if (s->h_cells_b) cudaFreeHost(s->h_cells_b); cudaFree(s->d_ctus); cudaFree(s->d_pool); cudaFree(s->d_ncg); cudaFree(s->d_sse);
         if (s->h_cells) cudaFreeHost(s->h_cells); if (s->h_ctus) cudaFreeHost(s->h_ctus); if (s->h_pool) cudaFreeHost(s->h_pool);
         if (s->h_ncg) cudaFreeHost(s->h_ncg); if (s->h_sse) cudaFreeHost(s->h_sse);
         if (s->done) cudaEventDestroy(s->done);
@@ -205,7 +214,9 @@ static int fill_params(const ks_gpu_ctx *c, const ks_pic_params *p, KsPicParams 
     if (p->qp < 0 || p->qp > 51) return KS_EINVAL;
     if (p->src_slot < 0 || p->src_slot >= c->cfg.n_src_slots || p->out_slot < 0 || p->out_slot >= c->cfg.n_rec_slots) return KS_EINVAL;
     if (p->syn_slot < 0 || p->syn_slot >= c->cfg.n_syn_slots || p->prev_syn_slot >= c->cfg.n_syn_slots) return KS_EINVAL;
-    if (p->slice_type != KS_SLICE_I && (p->slice_type != KS_SLICE_P || p->ref_slot < 0 || p->ref_slot >= c->cfg.n_rec_slots || p->ref_slot == p->out_slot)) return KS_EINVAL;
+    if (p->slice_type != KS_SLICE_I && (p->ref_slot < 0 || p->ref_slot >= c->cfg.n_rec_slots || p->ref_slot == p->out_slot)) return KS_EINVAL;
+    if (p->slice_type == KS_SLICE_B && (p->ref1_slot < 0 || p->ref1_slot >= c->cfg.n_rec_slots || p->ref1_slot == p->out_slot || p->ref1_slot == p->ref_slot
+                                         || p->dist_l0 <= 0 || p->dist_anchor <= p->dist_l0)) return KS_EINVAL;
     memset(pp, 0, sizeof(*pp));
     pp->W = c->W; pp->H = c->H; pp->cw = c->cw; pp->ch = c->ch; pp->ctw = c->ctw; pp->cth = c->cth;
     pp->slice_type = p->slice_type; pp->qp = p->qp; pp->qpc = k_chroma_qp[p->qp];
@@ -237,12 +248,26 @@ extern "C" int ks_gpu_encode_picture_submit(ks_gpu_ctx *c, const ks_pic_params *
         const ks_cell *prev = p->prev_syn_slot >= 0 ? c->syn[p->prev_syn_slot].d_cells : NULL;
         MARK(0);
         KsPlanes pred = planes_of(c, c->d_pred);
-        ks_launch_me(pp, src.p[0], ref, prev, s->d_cells, pred, c->st); c->launches += KS_LAUNCHES_ME;
+        const ks_cell_b *cb = NULL;
+        if (p->slice_type == KS_SLICE_B) {
+            /* list 0 and list 1 searches seeded by the later anchor's vectors scaled to each list, then the bi-prediction decision */
+            KsPlanes ref1 = planes_of(c, c->d_rec[p->ref1_slot]), pred1 = planes_of(c, c->d_pred1);
+            KsPicParams p0 = pp, p1 = pp;
+            p0.pred_num = p->dist_l0; p0.pred_den = p->dist_anchor; p1.pred_num = p->dist_l0 - p->dist_anchor; p1.pred_den = p->dist_anchor;
+            ks_launch_me(p0, src.p[0], ref, prev, s->d_cells, pred, c->d_cost0, c->st);
+            ks_launch_me(p1, src.p[0], ref1, prev, c->d_cells1, pred1, c->d_cost1, c->st);
+            ks_launch_bidir(pp, src.p[0], ref, ref1, prev, p0.pred_num, p1.pred_num, p->dist_anchor, c->d_cells1, c->d_cost0, c->d_cost1, pred1, s->d_cells, s->d_cells_b, pred, c->st);
+            c->launches += 2 * KS_LAUNCHES_ME + 1;
+            cb = s->d_cells_b;
+        } else {
+            ks_launch_me(pp, src.p[0], ref, prev, s->d_cells, pred, NULL, c->st); c->launches += KS_LAUNCHES_ME;
+        }
         MARK(1);
-        ks_launch_recon_inter(pp, src, pred, pre, lv, s->d_cells, c->st); c->launches += KS_LAUNCHES_RECON;
+        ks_launch_recon_inter(pp, src, pred, pre, lv, s->d_cells, cb, c->st); c->launches += KS_LAUNCHES_RECON;
     }
+    s->is_b = p->slice_type == KS_SLICE_B;
     MARK(3);
-    ks_launch_deblock(pp, pre, s->d_cells, c->st); c->launches += KS_LAUNCHES_DEBLOCK;
+    ks_launch_deblock(pp, pre, s->d_cells, s->is_b ? s->d_cells_b : NULL, c->st); c->launches += KS_LAUNCHES_DEBLOCK;
     if (p->want_sse) CK(cudaMemsetAsync(s->d_sse, 0, 3 * sizeof(unsigned long long), c->st));
     MARK(4);
     ks_launch_sao(pp, src, pre, out, s->d_ctus, p->want_sse ? s->d_sse : NULL, c->st); c->launches += KS_LAUNCHES_SAO - 1;
@@ -252,6 +277,7 @@ extern "C" int ks_gpu_encode_picture_submit(ks_gpu_ctx *c, const ks_pic_params *
 #undef MARK
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(s->h_cells, s->d_cells, (size_t)c->cw * c->ch * sizeof(ks_cell), cudaMemcpyDeviceToHost, c->st));
+    if (s->is_b) CK(cudaMemcpyAsync(s->h_cells_b, s->d_cells_b, (size_t)c->cw * c->ch * sizeof(ks_cell_b), cudaMemcpyDeviceToHost, c->st));
     CK(cudaMemcpyAsync(s->h_ctus, s->d_ctus, (size_t)c->ctw * c->cth * sizeof(ks_ctu_syn), cudaMemcpyDeviceToHost, c->st));
     CK(cudaMemcpyAsync(s->h_ncg, s->d_ncg, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->st));
     if (p->want_sse) CK(cudaMemcpyAsync(s->h_sse, s->d_sse, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->st));
@@ -285,6 +311,7 @@ extern "C" int ks_gpu_encode_picture_finish(ks_gpu_ctx *c, int syn_slot, ks_pic_
     s->pending = 0;
     out->cells = s->h_cells; out->ctus = s->h_ctus; out->levels = s->h_pool; out->n_cg = n;
     out->sse[0] = s->h_sse[0]; out->sse[1] = s->h_sse[1]; out->sse[2] = s->h_sse[2];
+    out->cells_b = s->is_b ? s->h_cells_b : NULL;
     return 0;
 }
 extern "C" int ks_gpu_encode_picture(ks_gpu_ctx *c, const ks_pic_params *p, ks_pic_out *out)
@@ -331,7 +358,7 @@ extern "C" int ks_gpu_debug_me(ks_gpu_ctx *c, const ks_pic_params *p, ks_cell *c
     KsPlanes src = planes_of(c, c->d_src[p->src_slot]), ref = planes_of(c, c->d_rec[p->ref_slot]);
     const ks_cell *prev = p->prev_syn_slot >= 0 ? c->syn[p->prev_syn_slot].d_cells : NULL;
     KsPlanes nopred; nopred.p[0] = nopred.p[1] = nopred.p[2] = NULL;
-    ks_launch_me(pp, src.p[0], ref, prev, s->d_cells, nopred, c->st); c->launches += KS_LAUNCHES_ME;
+    ks_launch_me(pp, src.p[0], ref, prev, s->d_cells, nopred, NULL, c->st); c->launches += KS_LAUNCHES_ME;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(cells_out, s->d_cells, (size_t)c->cw * c->ch * sizeof(ks_cell), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));

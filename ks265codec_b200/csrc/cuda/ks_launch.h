@@ -20,14 +20,18 @@ struct KsPicParams {
     int me_range, me_iters, subpel, satd;
     int sign_hiding, sao, strong_intra;
     int beta_offset_div2, tc_offset_div2;
+    int pred_num, pred_den;  /* motion-search predictor = co-located vector * pred_num / pred_den (C division); den 0 = vector as is */
 };
 
 /* all launches are asynchronous on `st` */
 void ks_upload_tables();
-void ks_launch_me(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref, const ks_cell *prev_cells, ks_cell *cells, KsPlanes pred, cudaStream_t st);
-void ks_launch_recon_inter(const KsPicParams &pp, KsPlanes src, KsPlanes pred, KsPlanes rec, KsLevels lv, ks_cell *cells, cudaStream_t st);
+void ks_launch_me(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref, const ks_cell *prev_cells, ks_cell *cells, KsPlanes pred, int *costs, cudaStream_t st);
+/* B pictures: per cell best of list 0 / list 1 / bi-prediction; finalises cells, cells_b and the prediction planes */
+void ks_launch_bidir(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref0, KsPlanes ref1, const ks_cell *anchor_cells, int num0, int num1, int den,
+                     const ks_cell *cells1, const int *cost0, const int *cost1, KsPlanes pred1, ks_cell *cells, ks_cell_b *cells_b, KsPlanes pred, cudaStream_t st);
+void ks_launch_recon_inter(const KsPicParams &pp, KsPlanes src, KsPlanes pred, KsPlanes rec, KsLevels lv, ks_cell *cells, const ks_cell_b *cells_b, cudaStream_t st);
 void ks_launch_recon_intra(const KsPicParams &pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *cells, int *sync_ws, cudaStream_t st);
-void ks_launch_deblock(const KsPicParams &pp, KsPlanes rec, const ks_cell *cells, cudaStream_t st);
+void ks_launch_deblock(const KsPicParams &pp, KsPlanes rec, const ks_cell *cells, const ks_cell_b *cells_b, cudaStream_t st);
 void ks_launch_sao(const KsPicParams &pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_syn *ctus, unsigned long long *sse_out, cudaStream_t st);
 void ks_launch_pack(const KsPicParams &pp, KsLevels lv, ks_ctu_syn *ctus, int16_t *pool, uint32_t *n_cg, uint32_t *scan_ws, cudaStream_t st);
 /* number of kernel launches each stage issues (for bench.py's gpu_launches accounting) */

@@ -26,11 +26,13 @@ __device__ __forceinline__ bool ks_is_tu_edge(ks_cell p, ks_cell q, int xp, int 
     if (!same) return true;
     return p.cu_log2 == 6 && (pos & 31) == 0;
 }
-__device__ __forceinline__ int ks_edge_bs(ks_cell p, ks_cell q)
-{
+__device__ __forceinline__ int ks_edge_bs(ks_cell p, ks_cell q, ks_cell_b pb, ks_cell_b qb)
+{   /* spec 8.7.2.4; in B pictures the two lists always name different pictures, so motion compares list by list */
     if ((p.flags | q.flags) & KS_F_INTRA) return 2;
     if ((p.flags | q.flags) & KS_F_CBF_Y) return 1;
-    if (abs(p.mvx - q.mvx) >= 4 || abs(p.mvy - q.mvy) >= 4) return 1;
+    if (pb.dir != qb.dir) return 1;
+    if ((pb.dir & 1) && (abs(p.mvx - q.mvx) >= 4 || abs(p.mvy - q.mvy) >= 4)) return 1;
+    if ((pb.dir & 2) && (abs(pb.mvx1 - qb.mvx1) >= 4 || abs(pb.mvy1 - qb.mvy1) >= 4)) return 1;
     return 0;
 }
 /* filter one 4-line segment held in registers: px[l][0..3] = p3..p0, px[l][4..7] = q0..q3 */
@@ -74,7 +76,7 @@ __device__ __forceinline__ bool ks_deblock_luma_regs(int (&px)[4][8], int beta, 
 /* dir 0: vertical edges (x = 16,32,..), thread per (edge, 4-row segment); dir 1: horizontal edges */
 template <int DIR>
 __global__ void __launch_bounds__(256)
-ks_deblock_kernel(KsPicParams pp, KsPlanes rec, const ks_cell *__restrict__ cells)
+ks_deblock_kernel(KsPicParams pp, KsPlanes rec, const ks_cell *__restrict__ cells, const ks_cell_b *__restrict__ cells_b)
 {
     const int W = pp.W, H = pp.H;
     const int nedge = ((DIR ? H : W) >> 4) - 1, nseg = (DIR ? W : H) >> 2;
@@ -86,7 +88,9 @@ ks_deblock_kernel(KsPicParams pp, KsPlanes rec, const ks_cell *__restrict__ cell
     const int xq = DIR ? t : e, yq = DIR ? e : t, xp = DIR ? t : e - 1, yp = DIR ? e - 1 : t;
     const ks_cell cp = cells[(yp >> 4) * pp.cw + (xp >> 4)], cq = cells[(yq >> 4) * pp.cw + (xq >> 4)];
     if (!ks_is_tu_edge(cp, cq, xp, yp, xq, yq, e)) return;
-    const int bs = ks_edge_bs(cp, cq);
+    ks_cell_b pb, qb; pb.mvx1 = pb.mvy1 = qb.mvx1 = qb.mvy1 = 0; pb.dir = qb.dir = 1;
+    if (cells_b) { pb = cells_b[(yp >> 4) * pp.cw + (xp >> 4)]; qb = cells_b[(yq >> 4) * pp.cw + (xq >> 4)]; }
+    const int bs = ks_edge_bs(cp, cq, pb, qb);
     if (!bs) return;
     const int beta = c_beta_table[ks_clip3(0, 51, pp.qp + (pp.beta_offset_div2 << 1))];
     const int tc = c_tc_table[ks_clip3(0, 53, pp.qp + 2 * (bs - 1) + (pp.tc_offset_div2 << 1))];
@@ -140,11 +144,11 @@ ks_deblock_kernel(KsPicParams pp, KsPlanes rec, const ks_cell *__restrict__ cell
     }
 }
 
-void ks_launch_deblock(const KsPicParams &pp, KsPlanes rec, const ks_cell *cells, cudaStream_t st)
+void ks_launch_deblock(const KsPicParams &pp, KsPlanes rec, const ks_cell *cells, const ks_cell_b *cells_b, cudaStream_t st)
 {
     int nev = (pp.W >> 4) - 1, nsv = pp.H >> 2, neh = (pp.H >> 4) - 1, nsh = pp.W >> 2;
-    if (nev > 0) ks_deblock_kernel<0><<<dim3((nev + 31) / 32, (nsv + 7) / 8), 256, 0, st>>>(pp, rec, cells);
-    if (neh > 0) ks_deblock_kernel<1><<<dim3((nsh + 31) / 32, (neh + 7) / 8), 256, 0, st>>>(pp, rec, cells);
+    if (nev > 0) ks_deblock_kernel<0><<<dim3((nev + 31) / 32, (nsv + 7) / 8), 256, 0, st>>>(pp, rec, cells, cells_b);
+    if (neh > 0) ks_deblock_kernel<1><<<dim3((nsh + 31) / 32, (neh + 7) / 8), 256, 0, st>>>(pp, rec, cells, cells_b);
 }
 
 /* ------------------------------------------------------------------ SAO -------------------------- */

@@ -371,7 +371,7 @@ __device__ __forceinline__ void ks_mc_chroma8(uint8_t *cwin, int16_t *tmp, const
 #define KS_ME_WARPS 8
 __global__ void __launch_bounds__(KS_ME_WARPS * KS_WARP, 4)
 ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref, const ks_cell *__restrict__ prev_cells,
-             ks_cell *__restrict__ cells, KsPlanes pred)
+             ks_cell *__restrict__ cells, KsPlanes pred, int *__restrict__ costs)
 {
     __shared__ __align__(16) KsWarpScratch scratch[KS_ME_WARPS];
     __shared__ uint8_t cwins[KS_ME_WARPS][144];
@@ -386,6 +386,7 @@ ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref, con
     const uint2 s = *reinterpret_cast<const uint2 *>(srcY + (size_t)(y0 + (lane >> 1)) * W + x0 + 8 * (lane & 1));
     int tpx = 0, tpy = 0;
     if (prev_cells) { ks_cell pc = prev_cells[cell]; if (!(pc.flags & KS_F_INTRA)) { tpx = pc.mvx; tpy = pc.mvy; } }
+    if (pp.pred_den) { tpx = (tpx * pp.pred_num) / pp.pred_den; tpy = (tpy * pp.pred_num) / pp.pred_den; }    /* B pictures: anchor vector scaled to this list */
 #define MVCOST(qx, qy) ((lam * (ks_mvbits((qx) - tpx) + ks_mvbits((qy) - tpy))) >> 4)
 
     /* ---- start point: zero vs rounded temporal predictor (reference: meInitPoint E@0x4818b0) ---- */
@@ -491,6 +492,7 @@ ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref, con
     if (lane == 0) {
         ks_cell c; c.mvx = (int16_t)mx; c.mvy = (int16_t)my; c.cu_log2 = 4; c.flags = 0; c.intra_mode = 0; c.rsv = 0;
         cells[cell] = c;
+        if (costs) costs[cell] = bc;
     }
     /* ---- the search already holds the winner's luma prediction: emit it (and the chroma prediction for the same vector) so
      *      the residual kernel needs no motion compensation pass of its own (reference: getReusSubMePred E@0x486770 re-uses the
@@ -505,8 +507,184 @@ ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref, con
     }
 }
 
-void ks_launch_me(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref, const ks_cell *prev_cells, ks_cell *cells, KsPlanes pred, cudaStream_t st)
+void ks_launch_me(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref, const ks_cell *prev_cells, ks_cell *cells, KsPlanes pred, int *costs, cudaStream_t st)
 {
     int ncell = pp.cw * pp.ch;
-    ks_me_kernel<<<(ncell + KS_ME_WARPS - 1) / KS_ME_WARPS, KS_ME_WARPS * KS_WARP, 0, st>>>(pp, srcY, ref, prev_cells, cells, pred);
+    ks_me_kernel<<<(ncell + KS_ME_WARPS - 1) / KS_ME_WARPS, KS_ME_WARPS * KS_WARP, 0, st>>>(pp, srcY, ref, prev_cells, cells, pred, costs);
+}
+
+/* ------------------------------------------------------------------ bi-prediction (B pictures) ---- */
+/* 14-bit intermediate prediction of the 16x16 block (reference interpolatePuBi E@0x488020: InterpolateCopy8to16 / interpLumaHor8to16 /
+ * interpLumaVer8to16 / Hor8to16+Ver16to16): lane's 8 samples.  == ora_mc_luma_16 */
+__device__ __forceinline__ void ks_interp16_raw(KsWarpScratch *sc, int bxw, int byw, int fx, int fy, int lane, int v[8])
+{
+    const int row = lane >> 1, half = lane & 1;
+    if (fx == 0 && fy == 0) {
+        uint32_t a, b; ks_win_px8(sc->win, bxw, byw, lane, a, b);
+#pragma unroll
+        for (int j = 0; j < 4; j++) { v[j] = (int)((a >> (8 * j)) & 255) << 6; v[4 + j] = (int)((b >> (8 * j)) & 255) << 6; }
+    } else if (fy == 0) {
+        uint32_t n[4];
+        ks_row16(sc->win, byw + row, bxw + 8 * half - 3, n);
+        ks_htaps8(n, c_luma_taps_packed[fx][0], c_luma_taps_packed[fx][1], v);
+    } else if (fx == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = 0;
+#pragma unroll 2
+        for (int t = 0; t < 8; t++) {
+            const int c = c_luma_taps[fy][t], wx = bxw + 8 * half;
+            const uint32_t *r = sc->win[byw + row - 3 + t] + (wx >> 2);
+            const unsigned sh = (wx & 3) * 8;
+            const uint32_t a = __funnelshift_r(r[0], r[1], sh), b = __funnelshift_r(r[1], r[2], sh);
+#pragma unroll
+            for (int j = 0; j < 4; j++) { v[j] += c * (int)((a >> (8 * j)) & 255); v[4 + j] += c * (int)((b >> (8 * j)) & 255); }
+        }
+    } else {
+        const int tlo = c_luma_taps_packed[fx][0], thi = c_luma_taps_packed[fx][1];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            int rr = row + 16 * k;
+            if (rr < 23) {
+                uint32_t n[4]; int h[8];
+                ks_row16(sc->win, byw - 3 + rr, bxw + 8 * half - 3, n);
+                ks_htaps8(n, tlo, thi, h);
+                uint32_t *d = reinterpret_cast<uint32_t *>(&sc->tmp[rr][8 * half]);
+#pragma unroll
+                for (int j = 0; j < 4; j++) d[j] = ((uint32_t)h[2 * j] & 0xffffu) | ((uint32_t)h[2 * j + 1] << 16);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = 0;
+#pragma unroll 2
+        for (int t = 0; t < 8; t++) {
+            const int c = c_luma_taps[fy][t];
+            const uint4 q = *reinterpret_cast<const uint4 *>(&sc->tmp[row + t][8 * half]);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) { v[2 * j] += c * (int)(short)(w[j] & 0xffffu); v[2 * j + 1] += c * ((int)w[j] >> 16); }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] >>= 6;
+        __syncwarp();
+    }
+}
+/* 14-bit chroma prediction (2 samples per lane: row lane>>2, columns 2*(lane&3)..+1) of the 8x8 block; == ora_mc_chroma_16 */
+__device__ __forceinline__ void ks_mc_chroma8_raw(uint8_t *cwin, int16_t *tmp, const uint8_t *__restrict__ ref, int PW, int PH,
+                                                  int xc, int yc, int mvx, int mvy, int lane, int &v0, int &v1)
+{
+    const int ix = xc + (mvx >> 3) - 1, iy = yc + (mvy >> 3) - 1, fx = mvx & 7, fy = mvy & 7;
+    {
+        uint8_t b[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            int idx = min(lane + k * KS_WARP, 143), r = idx / 12, c = idx - r * 12;
+            b[k] = __ldg(ref + (size_t)min(max(iy + r, 0), PH - 1) * PW + min(max(ix + c, 0), PW - 1));
+        }
+#pragma unroll
+        for (int k = 0; k < 5; k++) if (lane + k * KS_WARP < 144) cwin[lane + k * KS_WARP] = b[k];
+    }
+    __syncwarp();
+    const int row = lane >> 2, col = (lane & 3) * 2;
+    if (fx == 0 && fy == 0) { v0 = cwin[(row + 1) * 12 + col + 1] << 6; v1 = cwin[(row + 1) * 12 + col + 2] << 6; }
+    else if (fy == 0) {
+        const uint8_t *p = cwin + (row + 1) * 12 + col;
+        v0 = v1 = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) { int c = c_chroma_taps[fx][t]; v0 += c * p[t]; v1 += c * p[t + 1]; }
+    } else if (fx == 0) {
+        const uint8_t *p = cwin + row * 12 + col + 1;
+        v0 = v1 = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) { int c = c_chroma_taps[fy][t]; v0 += c * p[t * 12]; v1 += c * p[t * 12 + 1]; }
+    } else {
+        for (int idx = lane; idx < 88; idx += KS_WARP) {
+            int r = idx >> 3, c = idx & 7;
+            const uint8_t *p = cwin + r * 12 + c;
+            int a = 0;
+#pragma unroll
+            for (int t = 0; t < 4; t++) a += c_chroma_taps[fx][t] * p[t];
+            tmp[idx] = (int16_t)a;
+        }
+        __syncwarp();
+        v0 = v1 = 0;
+#pragma unroll
+        for (int t = 0; t < 4; t++) { int c = c_chroma_taps[fy][t]; v0 += c * tmp[(row + t) * 8 + col]; v1 += c * tmp[(row + t) * 8 + col + 1]; }
+        v0 >>= 6; v1 >>= 6;
+    }
+    __syncwarp();
+}
+
+/* One warp per cell of a B picture: cost of bi-prediction (DefaultWeightedBi_c E@0x4350f0: (p0+p1+64)>>7 on the 14-bit
+ * predictions) against the two single-list winners found by ks_me_kernel; writes the final motion (ks_cell + ks_cell_b) and
+ * patches the prediction planes (list-0 prediction is already there).  Mirror of ora_b_picture's decision. */
+__global__ void __launch_bounds__(KS_ME_WARPS * KS_WARP)
+ks_bidir_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref0, KsPlanes ref1, const ks_cell *__restrict__ anchor_cells,
+                int num0, int num1, int den, const ks_cell *__restrict__ cells1, const int *__restrict__ cost0, const int *__restrict__ cost1,
+                KsPlanes pred1, ks_cell *__restrict__ cells, ks_cell_b *__restrict__ cells_b, KsPlanes pred)
+{
+    __shared__ __align__(16) KsWarpScratch scratch[KS_ME_WARPS];
+    __shared__ uint8_t cwins[KS_ME_WARPS][144];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cell = blockIdx.x * KS_ME_WARPS + warp;
+    if (cell >= pp.cw * pp.ch) return;
+    KsWarpScratch *sc = &scratch[warp];
+    const int cyc = cell / pp.cw, cxc = cell - cyc * pp.cw, x0 = cxc << 4, y0 = cyc << 4;
+    const int W = pp.W, H = pp.H, CW = W >> 1, CH = H >> 1, lam = pp.lambda_sad_q4;
+    const uint2 s = *reinterpret_cast<const uint2 *>(srcY + (size_t)(y0 + (lane >> 1)) * W + x0 + 8 * (lane & 1));
+    const ks_cell c0 = cells[cell], c1 = cells1[cell];
+    int ax = 0, ay = 0;
+    if (anchor_cells) { ks_cell a = anchor_cells[cell]; if (!(a.flags & KS_F_INTRA)) { ax = a.mvx; ay = a.mvy; } }
+    const int t0x = den ? (ax * num0) / den : 0, t0y = den ? (ay * num0) / den : 0, t1x = den ? (ax * num1) / den : 0, t1y = den ? (ay * num1) / den : 0;
+    int p0[8], p1[8];
+    {
+        const int wx0 = (x0 + (c0.mvx >> 2) - 3) & ~3, wy0 = y0 + (c0.mvy >> 2) - 3;
+        ks_load_window_mc(sc->win, ref0.p[0], W, H, wx0, wy0, lane);
+        ks_interp16_raw(sc, x0 + (c0.mvx >> 2) - wx0, 3, c0.mvx & 3, c0.mvy & 3, lane, p0);
+        const int wx1 = (x0 + (c1.mvx >> 2) - 3) & ~3, wy1 = y0 + (c1.mvy >> 2) - 3;
+        __syncwarp();
+        ks_load_window_mc(sc->win, ref1.p[0], W, H, wx1, wy1, lane);
+        ks_interp16_raw(sc, x0 + (c1.mvx >> 2) - wx1, 3, c1.mvx & 3, c1.mvy & 3, lane, p1);
+    }
+    uint32_t b0 = 0, b1 = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { b0 |= (uint32_t)ks_clip8((p0[j] + p1[j] + 64) >> 7) << (8 * j); b1 |= (uint32_t)ks_clip8((p0[4 + j] + p1[4 + j] + 64) >> 7) << (8 * j); }
+    const int metric = (pp.satd && pp.subpel > 0) ? (int)ks_satd16(b0, b1, s.x, s.y, lane) : (int)ks_warp_sum(__vsadu4(b0, s.x) + __vsadu4(b1, s.y));
+    const int cb = metric + ((lam * (ks_mvbits(c0.mvx - t0x) + ks_mvbits(c0.mvy - t0y))) >> 4) + ((lam * (ks_mvbits(c1.mvx - t1x) + ks_mvbits(c1.mvy - t1y))) >> 4);
+    int dir = 1, best = cost0[cell];
+    if (cost1[cell] < best) { best = cost1[cell]; dir = 2; }
+    if (cb < best) { best = cb; dir = 3; }
+    if (lane == 0) {
+        ks_cell c; c.mvx = (dir & 1) ? c0.mvx : 0; c.mvy = (dir & 1) ? c0.mvy : 0; c.cu_log2 = 4; c.flags = 0; c.intra_mode = 0; c.rsv = 0;
+        ks_cell_b b; b.mvx1 = (dir & 2) ? c1.mvx : 0; b.mvy1 = (dir & 2) ? c1.mvy : 0; b.dir = (uint8_t)dir; b.rsv[0] = b.rsv[1] = b.rsv[2] = 0;
+        cells[cell] = c; cells_b[cell] = b;
+    }
+    if (dir == 1) return;                                   /* prediction planes already hold the list-0 prediction */
+    uint8_t *py = pred.p[0] + (size_t)(y0 + (lane >> 1)) * W + x0 + 8 * (lane & 1);
+    const int crow = lane >> 2, ccol = (lane & 3) * 2;
+    if (dir == 2) {
+        *reinterpret_cast<uint2 *>(py) = *reinterpret_cast<const uint2 *>(pred1.p[0] + (size_t)(y0 + (lane >> 1)) * W + x0 + 8 * (lane & 1));
+#pragma unroll
+        for (int ci = 1; ci < 3; ci++) {
+            size_t o = (size_t)((y0 >> 1) + crow) * CW + (x0 >> 1) + ccol;
+            *reinterpret_cast<uint16_t *>(pred.p[ci] + o) = *reinterpret_cast<const uint16_t *>(pred1.p[ci] + o);
+        }
+        return;
+    }
+    *reinterpret_cast<uint2 *>(py) = make_uint2(b0, b1);
+#pragma unroll 1
+    for (int ci = 1; ci < 3; ci++) {
+        int a0, a1, q0, q1;
+        ks_mc_chroma8_raw(cwins[warp], &sc->tmp[0][0], ref0.p[ci], CW, CH, x0 >> 1, y0 >> 1, c0.mvx, c0.mvy, lane, a0, a1);
+        ks_mc_chroma8_raw(cwins[warp], &sc->tmp[0][0], ref1.p[ci], CW, CH, x0 >> 1, y0 >> 1, c1.mvx, c1.mvy, lane, q0, q1);
+        uint8_t *d = pred.p[ci] + (size_t)((y0 >> 1) + crow) * CW + (x0 >> 1) + ccol;
+        d[0] = (uint8_t)ks_clip8((a0 + q0 + 64) >> 7); d[1] = (uint8_t)ks_clip8((a1 + q1 + 64) >> 7);
+    }
+}
+
+void ks_launch_bidir(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref0, KsPlanes ref1, const ks_cell *anchor_cells, int num0, int num1, int den,
+                     const ks_cell *cells1, const int *cost0, const int *cost1, KsPlanes pred1, ks_cell *cells, ks_cell_b *cells_b, KsPlanes pred, cudaStream_t st)
+{
+    int ncell = pp.cw * pp.ch;
+    ks_bidir_kernel<<<(ncell + KS_ME_WARPS - 1) / KS_ME_WARPS, KS_ME_WARPS * KS_WARP, 0, st>>>(pp, srcY, ref0, ref1, anchor_cells, num0, num1, den, cells1, cost0, cost1, pred1, cells, cells_b, pred);
 }

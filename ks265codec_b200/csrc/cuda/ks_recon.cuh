@@ -186,6 +186,8 @@ struct KsReconSmem {
     uint16_t scan[64 + 256 + 1024];            /* scan tables for 8x8, 16x16, 32x32 */
     int      t0[256];                          /* M32[2j+1][x], j,x < 16: level-0 odd part of the 32-point butterflies */
     int16_t  mvx[16], mvy[16];
+    int      m1[16];                           /* B pictures: list-1 vector (x | y << 16) and direction folded into one word pair */
+    uint8_t  dirv[16];
     uint8_t  valid[16];
     unsigned cbf[16];                          /* KS_F_CBF_* bits per cell, OR-ed by the transform tasks */
 };
@@ -200,7 +202,7 @@ __device__ __forceinline__ void ks_load_scans(uint16_t *scan, int tid, int nthre
 }
 
 __global__ void __launch_bounds__(KS_RECON_WARPS * KS_WARP, 2)
-ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes pred, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells)
+ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes pred, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells, const ks_cell_b *__restrict__ cells_b)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     KsReconSmem *sm = reinterpret_cast<KsReconSmem *>(smem_raw);
@@ -213,8 +215,11 @@ ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes pred, KsPlanes rec,
         int cx = tid & 3, cy = tid >> 2, x = X0 + (cx << 4), y = Y0 + (cy << 4);
         bool v = x < W && y < H;
         sm->valid[tid] = v; sm->cbf[tid] = 0;
-        if (v) { ks_cell c = cells[(y >> 4) * pp.cw + (x >> 4)]; sm->mvx[tid] = c.mvx; sm->mvy[tid] = c.mvy; }
-        else { sm->mvx[tid] = 0; sm->mvy[tid] = 0; }
+        sm->m1[tid] = 0; sm->dirv[tid] = 1;
+        if (v) {
+            ks_cell c = cells[(y >> 4) * pp.cw + (x >> 4)]; sm->mvx[tid] = c.mvx; sm->mvy[tid] = c.mvy;
+            if (cells_b) { ks_cell_b b = cells_b[(y >> 4) * pp.cw + (x >> 4)]; sm->m1[tid] = (int)(uint16_t)b.mvx1 | ((int)b.mvy1 << 16); sm->dirv[tid] = b.dir; }
+        } else { sm->mvx[tid] = 0; sm->mvy[tid] = 0; }
     }
     __syncthreads();
     /* CU size: four equal-MV siblings merge upward (16 -> 32 -> 64), mirror of ora_inter_picture step 2.
@@ -224,11 +229,13 @@ ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes pred, KsPlanes rec,
     for (int q = 0; q < 4; q++) {
         const int b0 = (q & 1) * 2 + (q >> 1) * 8;
         bool ok = sm->valid[b0] && sm->valid[b0 + 1] && sm->valid[b0 + 4] && sm->valid[b0 + 5];
-        const int mx = sm->mvx[b0], my = sm->mvy[b0];
+        const int mx = sm->mvx[b0], my = sm->mvy[b0], m1 = sm->m1[b0], dr = sm->dirv[b0];
         ok = ok && sm->mvx[b0 + 1] == mx && sm->mvx[b0 + 4] == mx && sm->mvx[b0 + 5] == mx
-                && sm->mvy[b0 + 1] == my && sm->mvy[b0 + 4] == my && sm->mvy[b0 + 5] == my;
+                && sm->mvy[b0 + 1] == my && sm->mvy[b0 + 4] == my && sm->mvy[b0 + 5] == my
+                && sm->m1[b0 + 1] == m1 && sm->m1[b0 + 4] == m1 && sm->m1[b0 + 5] == m1
+                && sm->dirv[b0 + 1] == dr && sm->dirv[b0 + 4] == dr && sm->dirv[b0 + 5] == dr;
         q32[q] = ok;
-        c64 = c64 && ok && mx == sm->mvx[0] && my == sm->mvy[0];
+        c64 = c64 && ok && mx == sm->mvx[0] && my == sm->mvy[0] && m1 == sm->m1[0] && dr == sm->dirv[0];
     }
     /* ---- transform tasks: 16 slots (k, q) = (kind 0..3, quadrant); a quadrant coded with one 32x32 TU uses kinds
      *      0 (luma 32) and 1 (Cb+Cr 16), otherwise kinds 0,1 (two luma 16 pairs) and 2,3 (four Cb 8 / four Cr 8).
@@ -278,12 +285,12 @@ ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes pred, KsPlanes rec,
     }
 }
 
-void ks_launch_recon_inter(const KsPicParams &pp, KsPlanes src, KsPlanes pred, KsPlanes rec, KsLevels lv, ks_cell *cells, cudaStream_t st)
+void ks_launch_recon_inter(const KsPicParams &pp, KsPlanes src, KsPlanes pred, KsPlanes rec, KsLevels lv, ks_cell *cells, const ks_cell_b *cells_b, cudaStream_t st)
 {
     static bool attr_done = false;
     if (!attr_done) { cudaFuncSetAttribute(ks_recon_inter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsReconSmem)); attr_done = true; }
     dim3 grid(pp.ctw, pp.cth);
-    ks_recon_inter_kernel<<<grid, KS_RECON_WARPS * KS_WARP, sizeof(KsReconSmem), st>>>(pp, src, pred, rec, lv, cells);
+    ks_recon_inter_kernel<<<grid, KS_RECON_WARPS * KS_WARP, sizeof(KsReconSmem), st>>>(pp, src, pred, rec, lv, cells, cells_b);
 }
 
 /* ------------------------------------------------------------------ intra picture (wavefront) ---- */

@@ -49,7 +49,7 @@ ks265_encoder *ks265_encoder_open(const ks265_config *cfg, int *err)
     if (cfg->rc != 0) { fprintf(stderr, "ks265: only -rc 0 (fixed QP) is implemented on the device path\n"); if (err) *err = -22; free(enc); return NULL; }
     ks_gpu_cfg g; memset(&g, 0, sizeof(g));
     g.me_range = cfg->me_range; g.me_iters = cfg->me_iters; g.subpel = cfg->subpel; g.sign_hiding = cfg->sign_hiding; g.sao = cfg->sao; g.satd = cfg->satd;
-    g.strong_intra = 1; g.n_src_slots = 3; g.n_rec_slots = 2; g.n_syn_slots = 2;
+    g.strong_intra = 1; g.n_src_slots = 3; g.n_rec_slots = cfg->bframes ? 4 : 2; g.n_syn_slots = cfg->bframes ? 4 : 2;
     enc->gpu = ks_gpu_open(cfg->device, cfg->width, cfg->height, &g, &e);
     if (!enc->gpu) { if (err) *err = e; free(enc); return NULL; }
     ks_gpu_coded_size(enc->gpu, &enc->W, &enc->H);
@@ -58,6 +58,7 @@ ks265_encoder *ks265_encoder_open(const ks265_config *cfg, int *err)
     sp->fps_num = (int)(cfg->fps * 1000 + 0.5); sp->fps_den = 1000;
     sp->sign_hiding = cfg->sign_hiding; sp->sao = cfg->sao != 0; sp->max_merge_cand = 3;
     sp->pps_beta_offset_div2 = 2; sp->pps_tc_offset_div2 = 2; sp->strong_intra_smoothing = 1; sp->log2_max_poc_lsb = 8;
+    sp->bframes = cfg->bframes;
     enc->scratch = malloc(ks_slice_scratch_bytes(sp));
     if (!enc->scratch) { ks_gpu_close(enc->gpu); free(enc); if (err) *err = -12; return NULL; }
     if (err) *err = 0;
@@ -69,96 +70,133 @@ void ks265_encoder_close(ks265_encoder *enc)
     ks_gpu_close(enc->gpu); free(enc->scratch); free(enc);
 }
 
-static void pic_setup(const ks265_encoder *enc, int f, ks_pic_params *pp)
+/* Coding schedule of one closed GOP shard of n pictures with bf B pictures between anchors: anchors at 0, bf+1, 2(bf+1), ...
+ * and the last picture; each anchor is coded before the B pictures that precede it in display order (reference:
+ * GopStructure::fillRpsInGop, EncGopStruct.cpp -- here non-hierarchical, non-reference B pictures).
+ * order[i] = display index, type[i] = KS_SLICE_*, l0/l1 = display index of the list-0 / list-1 reference (-1 none). */
+static int gop_schedule(int n, int bf, int *order, int *type, int *l0, int *l1)
+{
+    int k = 0, prev = 0;
+    order[k] = 0; type[k] = KS_SLICE_I; l0[k] = l1[k] = -1; k++;
+    while (prev < n - 1) {
+        int next = prev + bf + 1 < n - 1 ? prev + bf + 1 : n - 1;
+        order[k] = next; type[k] = KS_SLICE_P; l0[k] = prev; l1[k] = -1; k++;
+        for (int b = prev + 1; b < next; b++) { order[k] = b; type[k] = KS_SLICE_B; l0[k] = prev; l1[k] = next; k++; }
+        prev = next;
+    }
+    return k;
+}
+
+typedef struct { ks_pic_params pp; int disp, type, l0, l1; } coded_pic;
+
+/* device slots: anchors alternate reconstruction/syntax slots 0/1, B pictures alternate 2/3; sources rotate over 3 slots */
+static void plan_pictures(const ks265_encoder *enc, int n, coded_pic *cp, int *count)
 {
     const ks265_config *c = &enc->cfg;
-    int is_i = f == 0;
-    memset(pp, 0, sizeof(*pp));
-    pp->slice_type = is_i ? KS_SLICE_I : KS_SLICE_P;
-    pp->qp = (is_i || c->fixqp) ? c->qp : c->qp + 1;
-    if (pp->qp > 51) pp->qp = 51;
-    pp->src_slot = f % 3; pp->out_slot = f & 1; pp->ref_slot = is_i ? -1 : ((f & 1) ^ 1);
-    pp->syn_slot = f & 1; pp->prev_syn_slot = is_i ? -1 : ((f & 1) ^ 1);
-    pp->beta_offset_div2 = is_i ? 0 : 2; pp->tc_offset_div2 = is_i ? 0 : 2;      /* reference: I slices override to 0/0, P use PPS 2/2 */
-    pp->want_sse = c->psnr;
+    int *order = (int *)malloc(sizeof(int) * 4 * (size_t)(n + 1)), *type = order + n + 1, *l0 = type + n + 1, *l1 = l0 + n + 1;
+    int cnt = gop_schedule(n, c->bframes, order, type, l0, l1);
+    int anchors = 0, bs = 0, slot_prev = -1, slot_next = -1;
+    for (int i = 0; i < cnt; i++) {
+        ks_pic_params *pp = &cp[i].pp;
+        memset(pp, 0, sizeof(*pp));
+        cp[i].disp = order[i]; cp[i].type = type[i]; cp[i].l0 = l0[i]; cp[i].l1 = l1[i];
+        pp->slice_type = type[i];
+        pp->qp = c->fixqp ? c->qp : (type[i] == KS_SLICE_I ? c->qp : (type[i] == KS_SLICE_P ? c->qp + 1 : c->qp + 3));
+        if (pp->qp > 51) pp->qp = 51;
+        pp->src_slot = i % 3;
+        pp->beta_offset_div2 = type[i] == KS_SLICE_I ? 0 : 2; pp->tc_offset_div2 = pp->beta_offset_div2;   /* reference: I slices override to 0/0, others PPS 2/2 */
+        pp->want_sse = c->psnr;
+        pp->ref_slot = pp->ref1_slot = pp->prev_syn_slot = -1;
+        if (type[i] == KS_SLICE_B) {
+            pp->out_slot = pp->syn_slot = 2 + (bs & 1); bs++;
+            pp->ref_slot = slot_prev; pp->ref1_slot = slot_next; pp->prev_syn_slot = slot_next;
+            pp->dist_l0 = order[i] - l0[i]; pp->dist_anchor = l1[i] - l0[i];
+        } else {
+            int slot = anchors & 1; anchors++;
+            slot_prev = slot_next; slot_next = slot;
+            pp->out_slot = pp->syn_slot = slot;
+            if (type[i] == KS_SLICE_P) { pp->ref_slot = slot_prev; pp->prev_syn_slot = slot_prev; }
+        }
+    }
+    *count = cnt;
+    free(order);
 }
-static int upload(ks265_encoder *enc, int f, const uint8_t *frames, const void *frames_dev)
+static int upload(ks265_encoder *enc, int slot, int disp, const uint8_t *frames, const void *frames_dev)
 {
     size_t fsz = (size_t)enc->cfg.width * enc->cfg.height * 3 / 2;
     int w = enc->cfg.width, h = enc->cfg.height;
-    if (frames_dev) return ks_gpu_upload_frame_device(enc->gpu, f % 3, (const uint8_t *)frames_dev + fsz * f);
-    const uint8_t *y = frames + fsz * f;
-    return ks_gpu_upload_frame(enc->gpu, f % 3, y, y + (size_t)w * h, y + (size_t)w * h * 5 / 4, w, w / 2);
+    if (frames_dev) return ks_gpu_upload_frame_device(enc->gpu, slot, (const uint8_t *)frames_dev + fsz * disp);
+    const uint8_t *y = frames + fsz * disp;
+    return ks_gpu_upload_frame(enc->gpu, slot, y, y + (size_t)w * h, y + (size_t)w * h * 5 / 4, w, w / 2);
+}
+
+/* bs == NULL: device pipeline only (no entropy coding) */
+static long encode_gop_impl(ks265_encoder *enc, const uint8_t *frames, const void *frames_dev, int nframes,
+                            uint8_t *bs, size_t cap, uint8_t *recon, ks265_gop_stats *stats)
+{
+    const ks_stream_params *sp = &enc->sp;
+    size_t fsz = (size_t)enc->cfg.width * enc->cfg.height * 3 / 2;
+    int w = enc->cfg.width, h = enc->cfg.height, r, cnt = 0;
+    long pos = 0, n;
+    uint64_t l0c = ks_gpu_launch_count(enc->gpu), d0 = ks_gpu_d2h_bytes(enc->gpu), cg = 0;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    coded_pic *cp = (coded_pic *)malloc(sizeof(coded_pic) * (size_t)(nframes + 1));
+    if (!cp) return -12;
+    plan_pictures(enc, nframes, cp, &cnt);
+    if (bs) {
+        if ((n = ks_write_vps(sp, bs + pos, cap - pos)) < 0) { free(cp); return -28; } pos += n;
+        if ((n = ks_write_sps(sp, bs + pos, cap - pos)) < 0) { free(cp); return -28; } pos += n;
+        if ((n = ks_write_pps(sp, bs + pos, cap - pos)) < 0) { free(cp); return -28; } pos += n;
+    }
+#define FAIL(code) do { free(cp); return (code); } while (0)
+    if ((r = upload(enc, cp[0].pp.src_slot, cp[0].disp, frames, frames_dev))) FAIL(r);
+    if ((r = ks_gpu_encode_picture_submit(enc->gpu, &cp[0].pp))) FAIL(r);
+    for (int i = 0; i < cnt; i++) {
+        /* keep the device busy: picture i+1 is uploaded and submitted before picture i is entropy-coded */
+        ks_pic_out out;
+        if (i + 1 < cnt && (r = upload(enc, cp[i + 1].pp.src_slot, cp[i + 1].disp, frames, frames_dev))) FAIL(r);
+        if ((r = ks_gpu_encode_picture_finish(enc->gpu, cp[i].pp.syn_slot, &out))) FAIL(r);
+        if (i + 1 < cnt && (r = ks_gpu_encode_picture_submit(enc->gpu, &cp[i + 1].pp))) FAIL(r);
+        cg += out.n_cg;
+        if (recon) {      /* picture i's reconstruction slot is not rewritten before picture i+2 is submitted */
+            uint8_t *y = recon + fsz * cp[i].disp;
+            if ((r = ks_gpu_fetch_recon(enc->gpu, cp[i].pp.out_slot, y, y + (size_t)w * h, y + (size_t)w * h * 5 / 4, w, w / 2))) FAIL(r);
+        }
+        if (bs) {
+            const ks_pic_params *p = &cp[i].pp;
+            ks_frame_syn syn = {enc->W, enc->H, enc->W >> 4, enc->H >> 4, (enc->W + 63) >> 6, (enc->H + 63) >> 6, p->slice_type, p->qp, cp[i].disp,
+                                out.cells, out.ctus, out.levels, out.n_cg, out.cells_b};
+            ks_slice_params sl; memset(&sl, 0, sizeof(sl));
+            sl.nal_type = cp[i].type == KS_SLICE_I ? 19 : (cp[i].type == KS_SLICE_P ? 1 : 0); sl.slice_type = p->slice_type; sl.poc = cp[i].disp; sl.qp = p->qp;
+            if (cp[i].type != KS_SLICE_I) { sl.num_neg_refs = 1; sl.neg_delta_poc[0] = cp[i].l0 - cp[i].disp; }
+            if (cp[i].type == KS_SLICE_B) { sl.num_pos_refs = 1; sl.pos_delta_poc[0] = cp[i].l1 - cp[i].disp; }
+            sl.deblock_override = cp[i].type == KS_SLICE_I; sl.beta_offset_div2 = p->beta_offset_div2; sl.tc_offset_div2 = p->tc_offset_div2;
+            sl.sao_luma = sl.sao_chroma = sp->sao;
+            if ((n = ks_write_slice(sp, &sl, &syn, enc->scratch, bs + pos, cap - pos)) < 0) FAIL(-28);
+            pos += n;
+        }
+        if (stats) { stats->sse[0] += out.sse[0]; stats->sse[1] += out.sse[1]; stats->sse[2] += out.sse[2]; }
+    }
+#undef FAIL
+    free(cp);
+    if (stats) {
+        stats->frames = nframes; stats->bytes = bs ? (uint64_t)pos : cg * 32; stats->gpu_launches = ks_gpu_launch_count(enc->gpu) - l0c;
+        stats->d2h_bytes = ks_gpu_d2h_bytes(enc->gpu) - d0; stats->h2d_bytes = frames_dev ? 0 : (uint64_t)fsz * nframes;
+    }
+    return bs ? pos : (long)nframes;
 }
 
 long ks265_encoder_encode_gop(ks265_encoder *enc, const uint8_t *frames, const void *frames_dev, int nframes,
                               uint8_t *bs, size_t cap, uint8_t *recon, ks265_gop_stats *stats)
 {
     if (!enc || (!frames && !frames_dev) || nframes < 1 || !bs) return -22;
-    const ks_stream_params *sp = &enc->sp;
-    size_t fsz = (size_t)enc->cfg.width * enc->cfg.height * 3 / 2;
-    int w = enc->cfg.width, h = enc->cfg.height, r;
-    long pos = 0, n;
-    uint64_t l0 = ks_gpu_launch_count(enc->gpu), d0 = ks_gpu_d2h_bytes(enc->gpu);
-    if (stats) memset(stats, 0, sizeof(*stats));
-    if ((n = ks_write_vps(sp, bs + pos, cap - pos)) < 0) return -28; pos += n;
-    if ((n = ks_write_sps(sp, bs + pos, cap - pos)) < 0) return -28; pos += n;
-    if ((n = ks_write_pps(sp, bs + pos, cap - pos)) < 0) return -28; pos += n;
-    ks_pic_params pp[2];
-    if ((r = upload(enc, 0, frames, frames_dev))) return r;
-    pic_setup(enc, 0, &pp[0]);
-    if ((r = ks_gpu_encode_picture_submit(enc->gpu, &pp[0]))) return r;
-    for (int f = 0; f < nframes; f++) {
-        /* keep the device busy: upload + submit picture f+1 before entropy-coding picture f.
-         * (recon fetch of f, when requested, must precede submit(f+1)? no: f+1 writes the OTHER recon slot) */
-        ks_pic_out out;
-        if (f + 1 < nframes) {
-            if ((r = upload(enc, f + 1, frames, frames_dev))) return r;
-            /* syntax slot (f+1)&1 == (f-1)&1 was finished in the previous iteration; recon slot (f+1)&1 held picture f-1 */
-            pic_setup(enc, f + 1, &pp[(f + 1) & 1]);
-        }
-        if ((r = ks_gpu_encode_picture_finish(enc->gpu, f & 1, &out))) return r;
-        if (f + 1 < nframes && (r = ks_gpu_encode_picture_submit(enc->gpu, &pp[(f + 1) & 1]))) return r;
-        if (recon) {
-            /* picture f's reconstruction stays valid until picture f+2 is submitted */
-            uint8_t *y = recon + fsz * f;
-            if ((r = ks_gpu_fetch_recon(enc->gpu, f & 1, y, y + (size_t)w * h, y + (size_t)w * h * 5 / 4, w, w / 2))) return r;
-        }
-        const ks_pic_params *p = &pp[f & 1];
-        ks_frame_syn syn = {enc->W, enc->H, enc->W >> 4, enc->H >> 4, (enc->W + 63) >> 6, (enc->H + 63) >> 6, p->slice_type, p->qp, f,
-                            out.cells, out.ctus, out.levels, out.n_cg};
-        ks_slice_params sl; memset(&sl, 0, sizeof(sl));
-        sl.nal_type = f == 0 ? 19 : 1; sl.slice_type = p->slice_type; sl.poc = f; sl.qp = p->qp;
-        sl.num_neg_refs = f == 0 ? 0 : 1; sl.neg_delta_poc[0] = -1;
-        sl.deblock_override = f == 0; sl.beta_offset_div2 = p->beta_offset_div2; sl.tc_offset_div2 = p->tc_offset_div2;
-        sl.sao_luma = sl.sao_chroma = sp->sao;
-        if ((n = ks_write_slice(sp, &sl, &syn, enc->scratch, bs + pos, cap - pos)) < 0) return -28;
-        pos += n;
-        if (stats) { stats->sse[0] += out.sse[0]; stats->sse[1] += out.sse[1]; stats->sse[2] += out.sse[2]; }
-    }
-    if (stats) { stats->frames = nframes; stats->bytes = (uint64_t)pos; stats->gpu_launches = ks_gpu_launch_count(enc->gpu) - l0;
-                 stats->d2h_bytes = ks_gpu_d2h_bytes(enc->gpu) - d0; stats->h2d_bytes = frames_dev ? 0 : (uint64_t)fsz * nframes; }
-    return pos;
+    return encode_gop_impl(enc, frames, frames_dev, nframes, bs, cap, recon, stats);
 }
 
 long ks265_encoder_run_gop_device(ks265_encoder *enc, const void *frames_dev, int nframes, ks265_gop_stats *stats)
 {
     if (!enc || !frames_dev || nframes < 1) return -22;
-    int r;
-    uint64_t l0 = ks_gpu_launch_count(enc->gpu), d0 = ks_gpu_d2h_bytes(enc->gpu);
-    ks_pic_params pp;
-    ks_pic_out out;
-    uint64_t cg = 0;
-    for (int f = 0; f < nframes; f++) {
-        if ((r = upload(enc, f, NULL, frames_dev))) return r;
-        pic_setup(enc, f, &pp);
-        if ((r = ks_gpu_encode_picture_submit(enc->gpu, &pp))) return r;
-        if (f > 0) { if ((r = ks_gpu_encode_picture_finish(enc->gpu, (f - 1) & 1, &out))) return r; cg += out.n_cg; }
-    }
-    if ((r = ks_gpu_encode_picture_finish(enc->gpu, (nframes - 1) & 1, &out))) return r;
-    cg += out.n_cg;
-    if (stats) { memset(stats, 0, sizeof(*stats)); stats->frames = nframes; stats->bytes = cg * 32; stats->gpu_launches = ks_gpu_launch_count(enc->gpu) - l0; stats->d2h_bytes = ks_gpu_d2h_bytes(enc->gpu) - d0; }
-    return (long)nframes;
+    return encode_gop_impl(enc, NULL, frames_dev, nframes, NULL, 0, NULL, stats);
 }
 
 int ks265_encoder_set_profiling(ks265_encoder *enc, int on) { return enc ? ks_gpu_set_profiling(enc->gpu, on) : -22; }

@@ -217,10 +217,10 @@ def test_picture_stages_match_oracle(w, h, qp, sbh, sao, subpel, satd):
 
 
 # ---------------------------------------------------------------------------------------- whole encoder
-def oracle_encode(yuv, w, h, n, qp, iper, subpel=2, sbh=1, sao=1, iters=16, satd=0):
+def oracle_encode(yuv, w, h, n, qp, iper, subpel=2, sbh=1, sao=1, iters=16, satd=0, bframes=0):
     O = oracle()
     O.ora_encode_sequence.restype = C.c_long
-    cfg = SeqCfg(w, h, n, qp, iper, 0, 64, iters, subpel, sbh, sao, 3, satd)
+    cfg = SeqCfg(w, h, n, qp, iper, 0, 64, iters, subpel, sbh, sao, 3, satd, bframes)
     bs = np.zeros(w * h * 3 * n + 100000, np.uint8); rec = np.zeros(w * h * 3 // 2 * n, np.uint8)
     nb = O.ora_encode_sequence(C.byref(cfg), ptr(yuv), ptr(bs), C.c_size_t(bs.size), ptr(rec))
     assert nb > 0
@@ -252,6 +252,22 @@ def test_encoder_bitstream_equals_oracle_and_decodes(w, h, n, qp, preset):
     dec = decode_with_reference(bs, rec.size)
     first_diff(dec, rec, "reference decoder output vs our recon")
     assert st.frames == n and st.gpu_launches > 0
+
+
+@pytest.mark.parametrize("w,h,n,qp,preset,bf", [(192, 112, 6, 32, "veryfast", 1), (416, 240, 8, 27, "veryfast", 3), (320, 176, 7, 30, "medium", 2), (1280, 720, 6, 30, "veryfast", 2)])
+def test_encoder_bframes_equal_oracle_and_decode(w, h, n, qp, preset, bf):
+    """-bframes n (IDR, P anchors, non-reference B pictures between them): same three checks as the P-only streams.  The reference
+    decoder reorders to display order, so its output is compared against our display-order reconstruction."""
+    yuv = np.frombuffer(gen_yuv.make(w, h, n, seed=5), np.uint8)
+    cfg = ks.default_config(w, h, preset=preset, qp=qp, iper=n, psnr=1, bframes=bf)
+    with ks.Encoder(cfg) as e:
+        bs, rec, st = e.encode_gop(yuv, want_recon=True)
+    obs, orec = oracle_encode(yuv, w, h, n, qp, n, subpel=cfg.subpel, sbh=cfg.sign_hiding, sao=cfg.sao, iters=cfg.me_iters, satd=cfg.satd, bframes=bf)
+    first_diff(rec, orec, "recon vs oracle")
+    assert bytes(bs) == bytes(obs), "bitstream differs from the CPU model (%d vs %d bytes)" % (bs.size, obs.size)
+    dec = decode_with_reference(bs, rec.size)
+    first_diff(dec, rec, "reference decoder output vs our recon")
+    assert st.frames == n
 
 
 def test_natural_clip_closed_loop():
