@@ -127,7 +127,6 @@ static const uint8_t range_lps[64][4] = {
     {8,9,11,13},{7,9,11,12},{7,9,10,12},{7,8,10,11},{6,8,9,11},{6,7,9,10},{6,7,8,9},{2,2,2,2}};
 static const uint8_t next_lps[64] = {0,0,1,2,2,4,4,5,6,7,8,9,9,11,11,12,13,13,15,15,16,16,18,18,19,19,21,21,22,22,23,24,
     24,25,26,26,27,27,28,29,29,30,30,30,31,32,32,33,33,33,34,34,35,35,35,36,36,36,37,37,37,38,38,63};
-static const uint8_t renorm_tab[32] = {6,5,4,4,3,3,3,3,2,2,2,2,2,2,2,2,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1,1};
 
 /* context layout */
 enum {
@@ -203,24 +202,31 @@ static void cb_write_out(cabac *c)
         while (c->num_buffered > 1) { cb_byte(c, byte); c->num_buffered--; }
     } else { c->num_buffered = 1; c->buffered = (int)lead; }
 }
+/* context-coded bin (9.3.4.3.2 restated without the MPS/LPS branch): the LPS path is selected with a mask, the state
+ * transition and the renormalisation shift come from tables (g_cb_next / g_cb_shift, built once) */
+static uint8_t g_cb_next[128][2];      /* [(pStateIdx<<1)|valMps][bin] */
+static uint8_t g_cb_shift[64];         /* [range >> 3] -> left shifts until range >= 256 */
+__attribute__((constructor)) static void init_cb_tables(void)
+{
+    for (int s = 0; s < 128; s++) for (int bin = 0; bin < 2; bin++) {
+        int state = s >> 1, mps = s & 1;
+        if (bin != mps) { if (state == 0) mps ^= 1; g_cb_next[s][bin] = (uint8_t)((next_lps[state] << 1) | mps); }
+        else g_cb_next[s][bin] = (uint8_t)(((state < 62 ? state + 1 : state) << 1) | mps);
+    }
+    for (int k = 0; k < 64; k++) { int r = k << 3 | 7, n = 0; while (r < 256) { r <<= 1; n++; } g_cb_shift[k] = (uint8_t)n; }
+}
 static inline void cb_bin(cabac *c, int ctx, int bin)
 {
-    uint8_t s = c->ctx[ctx];
-    uint32_t state = s >> 1, mps = s & 1;
-    uint32_t lps = range_lps[state][(c->range >> 6) & 3];
-    c->range -= lps;
-    if ((uint32_t)bin != mps) {
-        int nb = renorm_tab[lps >> 3];
-        c->low = (c->low + c->range) << nb; c->range = lps << nb;
-        if (state == 0) mps ^= 1;
-        c->ctx[ctx] = (uint8_t)((next_lps[state] << 1) | mps);
-        c->bits_left -= nb;
-    } else {
-        c->ctx[ctx] = (uint8_t)(((state < 62 ? state + 1 : state) << 1) | mps);
-        if (c->range >= 256) return;
-        c->low <<= 1; c->range <<= 1; c->bits_left--;
-    }
-    if (c->bits_left < 12) cb_write_out(c);
+    uint32_t s = c->ctx[ctx], range = c->range, low = c->low;
+    uint32_t lps = range_lps[s >> 1][(range >> 6) & 3];
+    uint32_t is_lps = 0u - (uint32_t)((uint32_t)bin != (s & 1));
+    range -= lps;
+    low += range & is_lps;
+    range = (range & ~is_lps) | (lps & is_lps);
+    c->ctx[ctx] = g_cb_next[s][bin];
+    uint32_t nb = g_cb_shift[range >> 3];
+    c->low = low << nb; c->range = range << nb;
+    if ((c->bits_left -= (int)nb) < 12) cb_write_out(c);
 }
 static inline void cb_bypass(cabac *c, int bin)
 {
@@ -321,16 +327,23 @@ static void ctu_prefix(slice_enc *e, int ctu)
     e->cg_prefix[k] = (uint16_t)acc;
     e->cur_ctu = ctu;
 }
-static const int16_t *cg_levels(slice_enc *e, int comp, int cgx, int cgy)
-{   /* (cgx,cgy) relative to the current CTU, in CG units of that component */
-    const ks_ctu_syn *c = &e->syn->ctus[e->cur_ctu];
-    uint32_t bits; int row;
-    if (comp == 0) { bits = c->cg_y[cgy]; row = cgy; }
-    else if (comp == 1) { bits = c->cg_cb[cgy]; row = 16 + cgy; }
-    else { bits = c->cg_cr[cgy]; row = 24 + cgy; }
-    if (!((bits >> cgx) & 1)) return NULL;
-    uint32_t idx = c->cg_base + e->cg_prefix[row] + (uint32_t)__builtin_popcount(bits & ((1u << cgx) - 1));
-    return e->syn->levels + (size_t)idx * 16;
+/* sig_coeff_flag context increments (9.3.4.2.5), tabulated: [chroma][8x8 TB][CG != (0,0)][right | below<<1][raster pos in CG] */
+static uint8_t g_sig_ctx[2][2][2][4][16];
+__attribute__((constructor)) static void init_sig_ctx(void)
+{
+    for (int ch = 0; ch < 2; ch++) for (int l3 = 0; l3 < 2; l3++) for (int nz = 0; nz < 2; nz++) for (int prev = 0; prev < 4; prev++) for (int p = 0; p < 16; p++) {
+        int xp = p & 3, yp = p >> 2, sc;
+        if (!nz && p == 0) sc = 0;
+        else {
+            if (prev == 0) sc = (xp + yp == 0) ? 2 : (xp + yp < 3) ? 1 : 0;
+            else if (prev == 1) sc = yp == 0 ? 2 : yp == 1 ? 1 : 0;
+            else if (prev == 2) sc = xp == 0 ? 2 : xp == 1 ? 1 : 0;
+            else sc = 2;
+            if (!ch) { if (nz) sc += 3; sc += l3 ? 9 : 21; }
+            else sc += l3 ? 9 : 12;
+        }
+        g_sig_ctx[ch][l3][nz][prev][p] = (uint8_t)(sc + (ch ? 27 : 0));
+    }
 }
 
 /* ---- 7.3.8.11 residual_coding for one transform block (diagonal scan only: TB >= 8 or inter) ---- */
@@ -339,16 +352,39 @@ static void code_residual(slice_enc *e, int comp, int x0c, int y0c, int log2)
     cabac *c = &e->cb;
     int ncg = 1 << (log2 - 2);           /* CGs per side */
     const uint8_t *scg = g_scan_cg[log2 - 2];
-    const int16_t *cgp[64];
-    int last_cg = -1;
-    for (int i = 0; i < ncg * ncg; i++) {
-        int cx = scg[i] & 7, cy = scg[i] >> 3;
-        cgp[i] = cg_levels(e, comp, (x0c >> 2) + cx, (y0c >> 2) + cy);
-        if (cgp[i]) last_cg = i;
+    /* coded-CG bitmap of this TB, one byte per CG row, straight from the CTU record; level pointers are resolved lazily */
+    const ks_ctu_syn *cs = &e->syn->ctus[e->cur_ctu];
+    int cgx0 = x0c >> 2, cgy0 = y0c >> 2, row0 = comp == 0 ? 0 : (comp == 1 ? 16 : 24);
+    uint32_t rows[8], rmask = (1u << ncg) - 1, any = 0;
+    for (int r = 0; r < ncg; r++) {
+        uint32_t bits = comp == 0 ? cs->cg_y[cgy0 + r] : (comp == 1 ? cs->cg_cb[cgy0 + r] : cs->cg_cr[cgy0 + r]);
+        rows[r] = (bits >> cgx0) & rmask; any |= rows[r];
     }
-    if (last_cg < 0) return;             /* caller guarantees cbf=1 */
+    if (!any) return;                    /* caller guarantees cbf=1 */
+    /* the arithmetic coder's range/low live in locals for the whole block: the bin-to-bin dependency then runs through
+     * registers instead of store-to-load forwarding (context bytes alias the engine struct) */
+    uint32_t low = c->low, range = c->range; int bl = c->bits_left; uint8_t *ctxs = c->ctx;
+#define RFLUSH() do { c->low = low; c->bits_left = bl; cb_write_out(c); low = c->low; bl = c->bits_left; } while (0)
+#define RBIN(ci, bv) do { \
+        uint32_t s_ = ctxs[ci], b_ = (uint32_t)(bv), l_ = range_lps[s_ >> 1][(range >> 6) & 3], m_ = 0u - (uint32_t)(b_ != (s_ & 1)); \
+        range -= l_; low += range & m_; range = (range & ~m_) | (l_ & m_); \
+        ctxs[ci] = g_cb_next[s_][b_]; \
+        uint32_t n_ = (uint32_t)__builtin_clz(range) - 23u; low <<= n_; range <<= n_; \
+        if ((bl -= (int)n_) < 12) RFLUSH(); \
+    } while (0)
+#define RBYP(bits, nbits) do { \
+        uint32_t v_ = (uint32_t)(bits); int k_ = (int)(nbits); \
+        while (k_ > 8) { k_ -= 8; uint32_t p_ = v_ >> k_; low = (low << 8) + range * p_; v_ -= p_ << k_; if ((bl -= 8) < 12) RFLUSH(); } \
+        low = (low << k_) + range * v_; if ((bl -= k_) < 12) RFLUSH(); \
+    } while (0)
+#define CG_CODED(cx, cy) ((rows[cy] >> (cx)) & 1u)
+#define CG_PTR(cx, cy) (e->syn->levels + (size_t)(cs->cg_base + e->cg_prefix[row0 + cgy0 + (cy)] + \
+        (uint32_t)__builtin_popcount((comp == 0 ? cs->cg_y[cgy0 + (cy)] : (comp == 1 ? cs->cg_cb[cgy0 + (cy)] : cs->cg_cr[cgy0 + (cy)])) & ((1u << (cgx0 + (cx))) - 1))) * 16)
+    int last_cg = ncg * ncg - 1;
+    while (!CG_CODED(scg[last_cg] & 7, scg[last_cg] >> 3)) last_cg--;
+    const int16_t *lastp = CG_PTR(scg[last_cg] & 7, scg[last_cg] >> 3);
     int last_pos = 15;
-    while (!cgp[last_cg][g_scan4[last_pos]]) last_pos--;
+    while (!lastp[g_scan4[last_pos]]) last_pos--;
     int lx = ((scg[last_cg] & 7) << 2) + (g_scan4[last_pos] & 3), ly = ((scg[last_cg] >> 3) << 2) + (g_scan4[last_pos] >> 2);
     /* last_sig_coeff_{x,y}_prefix / suffix (9.3.4.2.3) */
     static const uint8_t group_idx[32] = {0,1,2,3,4,4,5,5,6,6,6,6,7,7,7,7,8,8,8,8,8,8,8,8,9,9,9,9,9,9,9,9};
@@ -357,44 +393,35 @@ static void code_residual(slice_enc *e, int comp, int x0c, int y0c, int log2)
     if (comp == 0) { off = 3 * (log2 - 2) + ((log2 - 1) >> 2); shift = (log2 + 1) >> 2; }
     else { off = 15; shift = log2 - 2; }
     int gx = group_idx[lx], gy = group_idx[ly], cmax = (log2 << 1) - 1, i;
-    for (i = 0; i < gx; i++) cb_bin(c, CX_LAST_X + off + (i >> shift), 1);
-    if (gx < cmax) cb_bin(c, CX_LAST_X + off + (i >> shift), 0);
-    for (i = 0; i < gy; i++) cb_bin(c, CX_LAST_Y + off + (i >> shift), 1);
-    if (gy < cmax) cb_bin(c, CX_LAST_Y + off + (i >> shift), 0);
-    if (gx > 3) cb_bypass_bins(c, (uint32_t)(lx - min_in_group[gx]), (gx - 2) >> 1);
-    if (gy > 3) cb_bypass_bins(c, (uint32_t)(ly - min_in_group[gy]), (gy - 2) >> 1);
+    for (i = 0; i < gx; i++) RBIN(CX_LAST_X + off + (i >> shift), 1);
+    if (gx < cmax) RBIN(CX_LAST_X + off + (i >> shift), 0);
+    for (i = 0; i < gy; i++) RBIN(CX_LAST_Y + off + (i >> shift), 1);
+    if (gy < cmax) RBIN(CX_LAST_Y + off + (i >> shift), 0);
+    if (gx > 3) RBYP((uint32_t)(lx - min_in_group[gx]), (gx - 2) >> 1);
+    if (gy > 3) RBYP((uint32_t)(ly - min_in_group[gy]), (gy - 2) >> 1);
 
     uint8_t csbf[8][8]; memset(csbf, 0, sizeof(csbf));
     int c1 = 1;
     for (int i2 = last_cg; i2 >= 0; i2--) {
         int cx = scg[i2] & 7, cy = scg[i2] >> 3;
         int right = cx + 1 < ncg ? csbf[cy][cx + 1] : 0, below = cy + 1 < ncg ? csbf[cy + 1][cx] : 0;
-        int coded = cgp[i2] != NULL, infer_dc = 0;
+        int present = (int)CG_CODED(cx, cy), coded = present, infer_dc = 0;
         if (i2 < last_cg && i2 > 0) {
-            cb_bin(c, CX_CSBF + ((right | below) ? 1 : 0) + (comp ? 2 : 0), coded);
+            RBIN(CX_CSBF + ((right | below) ? 1 : 0) + (comp ? 2 : 0), coded);
             infer_dc = 1;
         } else coded = 1;                 /* last and DC CGs are inferred coded */
         csbf[cy][cx] = (uint8_t)coded;
         if (!coded) continue;
         static const int16_t zero16[16] = {0};
-        const int16_t *lv = cgp[i2] ? cgp[i2] : zero16;
+        const int16_t *lv = present ? (i2 == last_cg ? lastp : CG_PTR(cx, cy)) : zero16;
         int prev = right | (below << 1);
+        const uint8_t *sctx = g_sig_ctx[comp != 0][log2 == 3][(cx | cy) != 0][prev];
         int start = i2 == last_cg ? last_pos - 1 : 15;
         uint16_t sig_mask = i2 == last_cg ? (uint16_t)(1u << last_pos) : 0;
         for (int n = start; n >= 0; n--) {
-            int p = g_scan4[n], xp = p & 3, yp = p >> 2, sig = lv[p] != 0;
+            int p = g_scan4[n], sig = lv[p] != 0;
             if (n > 0 || !infer_dc) {
-                int sc;
-                if (cx == 0 && cy == 0 && p == 0) sc = 0;
-                else {
-                    if (prev == 0) sc = (xp + yp == 0) ? 2 : (xp + yp < 3) ? 1 : 0;
-                    else if (prev == 1) sc = yp == 0 ? 2 : yp == 1 ? 1 : 0;
-                    else if (prev == 2) sc = xp == 0 ? 2 : xp == 1 ? 1 : 0;
-                    else sc = 2;
-                    if (comp == 0) { if (cx | cy) sc += 3; sc += log2 == 3 ? 9 : 21; }
-                    else sc += log2 == 3 ? 9 : 12;
-                }
-                cb_bin(c, CX_SIG + (comp ? 27 : 0) + sc, sig);
+                RBIN(CX_SIG + sctx[p], sig);
                 if (sig) infer_dc = 0;
             } else sig = 1;               /* inferred DC significance */
             if (sig) sig_mask |= (uint16_t)(1u << n);
@@ -416,13 +443,13 @@ static void code_residual(slice_enc *e, int comp, int x0c, int y0c, int log2)
         int ng1 = nsig < 8 ? nsig : 8;
         for (int k = 0; k < ng1; k++) {
             int g1 = absv[k] > 1;
-            cb_bin(c, CX_GT1 + (comp ? 16 : 0) + 4 * ctx_set + c1, g1);
+            RBIN(CX_GT1 + (comp ? 16 : 0) + 4 * ctx_set + c1, g1);
             if (g1) { c1 = 0; if (first_g1 < 0) first_g1 = k; }
             else if (c1 < 3 && c1 > 0) c1++;
         }
-        if (c1 == 0 && first_g1 >= 0) cb_bin(c, CX_GT2 + (comp ? 4 : 0) + ctx_set, absv[first_g1] > 2);
+        if (c1 == 0 && first_g1 >= 0) RBIN(CX_GT2 + (comp ? 4 : 0) + ctx_set, absv[first_g1] > 2);
         int hidden = e->sp->sign_hiding && (last_sig - first_sig > 3);
-        if (hidden) cb_bypass_bins(c, signs >> 1, nsig - 1); else cb_bypass_bins(c, signs, nsig);
+        if (hidden) RBYP(signs >> 1, nsig - 1); else RBYP(signs, nsig);
         int rice = 0;
         for (int k = 0; k < nsig; k++) {
             /* baseLevel the flags can express: 3 for the coefficient that carried greater2, 2 for the other
@@ -433,24 +460,30 @@ static void code_residual(slice_enc *e, int comp, int x0c, int y0c, int log2)
                 /* 9.3.3.11 coeff_abs_level_remaining: TR prefix (cMax 4<<rice) + EGk suffix */
                 if (rem < (3 << rice)) {
                     int len = rem >> rice;
-                    cb_bypass_bins(c, (1u << (len + 1)) - 2, len + 1);
-                    cb_bypass_bins(c, (uint32_t)rem & ((1u << rice) - 1), rice);
+                    RBYP((1u << (len + 1)) - 2, len + 1);
+                    RBYP((uint32_t)rem & ((1u << rice) - 1), rice);
                 } else {
                     int len = rice, code = rem - (3 << rice);
                     while (code >= (1 << len)) { code -= 1 << len; len++; }
-                    cb_bypass_bins(c, (1u << (3 + len + 1 - rice)) - 2, 3 + len + 1 - rice);
-                    cb_bypass_bins(c, (uint32_t)code, len);
+                    RBYP((1u << (3 + len + 1 - rice)) - 2, 3 + len + 1 - rice);
+                    RBYP((uint32_t)code, len);
                 }
                 if (absv[k] > 3 * (1 << rice) && rice < 4) rice++;
             }
         }
     }
+    c->low = low; c->range = range; c->bits_left = bl;
+#undef RBIN
+#undef RBYP
+#undef RFLUSH
+#undef CG_CODED
+#undef CG_PTR
 }
 
 /* ---- merge / AMVP candidates (8.5.3.2.2-.7; one reference picture per list, no TMVP) ---- */
 typedef struct { int16_t x, y; } mv_t;
 typedef struct { int dir; mv_t mv[2]; } motion_t;          /* dir: bit0 list 0 used, bit1 list 1 used; unused MVs are 0 */
-static motion_t cell_motion(const ks_frame_syn *s, int x, int y)
+static inline motion_t cell_motion(const ks_frame_syn *s, int x, int y)
 {
     int i = (y >> KS_CELL_LOG2) * s->cells_w + (x >> KS_CELL_LOG2);
     const ks_cell *c = &s->cells[i];
@@ -463,36 +496,46 @@ static motion_t cell_motion(const ks_frame_syn *s, int x, int y)
     }
     return m;
 }
-static int motion_eq(const motion_t *a, const motion_t *b)
+static inline int motion_eq(const motion_t *a, const motion_t *b)
 {
     return a->dir == b->dir && a->mv[0].x == b->mv[0].x && a->mv[0].y == b->mv[0].y && a->mv[1].x == b->mv[1].x && a->mv[1].y == b->mv[1].y;
 }
-static int inter_nb(const ks_frame_syn *s, int xc, int yc, int xn, int yn, motion_t *m)
+/* the five spatial neighbours of a 2Nx2N PU, fetched once per CU and shared by the merge and AMVP derivations.
+ * A1, B1 and B2 lie left of / above the CU and always precede it in z-scan order; A0 and B0 need the 6.4.1 test. */
+enum { NB_A0, NB_A1, NB_B0, NB_B1, NB_B2 };
+typedef struct { motion_t m[5]; int av[5]; } nb_set;
+static void fetch_nb(const ks_frame_syn *s, int x, int y, int size, nb_set *nb)
 {
-    if (!avail(s, xc, yc, xn, yn)) return 0;
-    if (cell_at(s, xn, yn)->flags & KS_F_INTRA) return 0;
-    *m = cell_motion(s, xn, yn);
-    return 1;
+    const int nx[5] = {x - 1, x - 1, x + size, x + size - 1, x - 1}, ny[5] = {y + size, y + size - 1, y - 1, y - 1, y - 1};
+    nb->av[NB_A0] = avail(s, x, y, nx[0], ny[0]);
+    nb->av[NB_A1] = x > 0;
+    nb->av[NB_B0] = avail(s, x, y, nx[2], ny[2]);
+    nb->av[NB_B1] = y > 0;
+    nb->av[NB_B2] = x > 0 && y > 0;
+    for (int k = 0; k < 5; k++) {
+        if (!nb->av[k]) continue;
+        if (cell_at(s, nx[k], ny[k])->flags & KS_F_INTRA) nb->av[k] = 0;
+        else nb->m[k] = cell_motion(s, nx[k], ny[k]);
+    }
 }
-static int merge_list(const ks_frame_syn *s, int x, int y, int size, int maxc, motion_t *list)
+static int merge_list(const ks_frame_syn *s, const nb_set *nb, int maxc, motion_t *list)
 {
-    motion_t a1, b1, b0, a0, b2; int n = 0;
-    int fa1 = inter_nb(s, x, y, x - 1, y + size - 1, &a1);
-    int ab1 = inter_nb(s, x, y, x + size - 1, y - 1, &b1), fb1 = ab1;
-    if (fb1 && fa1 && motion_eq(&a1, &b1)) fb1 = 0;
-    int fb0 = inter_nb(s, x, y, x + size, y - 1, &b0);
-    if (fb0 && ab1 && motion_eq(&b1, &b0)) fb0 = 0;
-    int fa0 = inter_nb(s, x, y, x - 1, y + size, &a0);
-    if (fa0 && fa1 && motion_eq(&a1, &a0)) fa0 = 0;
-    int fb2 = inter_nb(s, x, y, x - 1, y - 1, &b2);
-    if (fb2 && fa1 && motion_eq(&a1, &b2)) fb2 = 0;
-    if (fb2 && ab1 && motion_eq(&b1, &b2)) fb2 = 0;
+    const motion_t *a1 = &nb->m[NB_A1], *b1 = &nb->m[NB_B1], *b0 = &nb->m[NB_B0], *a0 = &nb->m[NB_A0], *b2 = &nb->m[NB_B2];
+    int n = 0, fa1 = nb->av[NB_A1], ab1 = nb->av[NB_B1], fb1 = ab1;
+    if (fb1 && fa1 && motion_eq(a1, b1)) fb1 = 0;
+    int fb0 = nb->av[NB_B0];
+    if (fb0 && ab1 && motion_eq(b1, b0)) fb0 = 0;
+    int fa0 = nb->av[NB_A0];
+    if (fa0 && fa1 && motion_eq(a1, a0)) fa0 = 0;
+    int fb2 = nb->av[NB_B2];
+    if (fb2 && fa1 && motion_eq(a1, b2)) fb2 = 0;
+    if (fb2 && ab1 && motion_eq(b1, b2)) fb2 = 0;
     if (fa0 + fa1 + fb0 + fb1 == 4) fb2 = 0;
-    if (fa1 && n < maxc) list[n++] = a1;
-    if (fb1 && n < maxc) list[n++] = b1;
-    if (fb0 && n < maxc) list[n++] = b0;
-    if (fa0 && n < maxc) list[n++] = a0;
-    if (fb2 && n < maxc) list[n++] = b2;
+    if (fa1 && n < maxc) list[n++] = *a1;
+    if (fb1 && n < maxc) list[n++] = *b1;
+    if (fb0 && n < maxc) list[n++] = *b0;
+    if (fa0 && n < maxc) list[n++] = *a0;
+    if (fb2 && n < maxc) list[n++] = *b2;
     if (s->slice_type == KS_SLICE_B && n > 1 && n < maxc) {        /* 8.5.3.2.4 combined bi-predictive candidates */
         static const uint8_t l0i[12] = {0, 1, 0, 2, 1, 2, 0, 3, 1, 3, 2, 3}, l1i[12] = {1, 0, 2, 0, 2, 1, 3, 0, 3, 1, 3, 2};
         int orig = n;
@@ -517,12 +560,11 @@ static mv_t scale_mv(mv_t mv, int tb, int td)
     v = dsf * mv.y; v = (v < 0 ? -1 : 1) * ((abs(v) + 127) >> 8); r.y = (int16_t)(v < -32768 ? -32768 : v > 32767 ? 32767 : v);
     return r;
 }
-/* AMVP list of list X for the 2Nx2N PU at (x,y); dpoc[l] = POC(cur) - POC(RefPicList_l[0]) */
-static void amvp_list(const ks_frame_syn *s, int x, int y, int size, int X, const int dpoc[2], mv_t list[2])
+/* AMVP list of list X for the 2Nx2N PU whose neighbours are in nbs; dpoc[l] = POC(cur) - POC(RefPicList_l[0]) */
+static void amvp_list(const nb_set *nbs, int X, const int dpoc[2], mv_t list[2])
 {
-    const int Y = 1 - X, nbx[5] = {x - 1, x - 1, x + size, x + size - 1, x - 1}, nby[5] = {y + size, y + size - 1, y - 1, y - 1, y - 1};
-    motion_t nb[5]; int av[5];
-    for (int k = 0; k < 5; k++) av[k] = inter_nb(s, x, y, nbx[k], nby[k], &nb[k]);      /* A0, A1, B0, B1, B2 */
+    const int Y = 1 - X;
+    const motion_t *nb = nbs->m; const int *av = nbs->av;      /* A0, A1, B0, B1, B2 */
     mv_t a = {0, 0}, b = {0, 0}; int fa = 0, fb = 0, n = 0;
     for (int k = 0; k < 2 && !fa; k++) if (av[k] && (nb[k].dir & (1 << X))) { a = nb[k].mv[X]; fa = 1; }
     for (int k = 0; k < 2 && !fa; k++) if (av[k]) { a = scale_mv(nb[k].mv[Y], dpoc[X], dpoc[Y]); fa = 1; }       /* only list Y is left: scaled */
@@ -610,17 +652,18 @@ static void code_cu(slice_enc *e, int x, int y, int log2)
     const ks_cell *cu = cell_at(s, x, y);
     int size = 1 << log2, intra = cu->flags & KS_F_INTRA;
     if (s->slice_type != KS_SLICE_I) {
-        motion_t ml[5], cur; int merge_idx = -1;
+        motion_t ml[5], cur; nb_set nbs; int merge_idx = -1;
         if (!intra) {
             cur = cell_motion(s, x, y);
-            int n = merge_list(s, x, y, size, e->sp->max_merge_cand, ml);
+            fetch_nb(s, x, y, size, &nbs);
+            int n = merge_list(s, &nbs, e->sp->max_merge_cand, ml);
             for (int k = 0; k < n; k++) if (motion_eq(&ml[k], &cur)) { merge_idx = k; break; }
         }
         int any = intra ? 1 : cu_cbf_any(s, x, y, size);
         int skip = !intra && merge_idx >= 0 && !any;
         int ctx = 0;
-        if (avail(s, x, y, x - 1, y)) ctx += e->skip[(y >> KS_CELL_LOG2) * s->cells_w + ((x - 1) >> KS_CELL_LOG2)];
-        if (avail(s, x, y, x, y - 1)) ctx += e->skip[((y - 1) >> KS_CELL_LOG2) * s->cells_w + (x >> KS_CELL_LOG2)];
+        if (x > 0) ctx += e->skip[(y >> KS_CELL_LOG2) * s->cells_w + ((x - 1) >> KS_CELL_LOG2)];      /* left / above always precede in z-scan */
+        if (y > 0) ctx += e->skip[((y - 1) >> KS_CELL_LOG2) * s->cells_w + (x >> KS_CELL_LOG2)];
         cb_bin(c, CX_SKIP + ctx, skip);
         for (int yy = y; yy < y + size; yy += KS_CELL) for (int xx = x; xx < x + size; xx += KS_CELL)
             e->skip[(yy >> KS_CELL_LOG2) * s->cells_w + (xx >> KS_CELL_LOG2)] = (uint8_t)skip;
@@ -646,7 +689,7 @@ static void code_cu(slice_enc *e, int x, int y, int log2)
             const int dpoc[2] = {-e->sl->neg_delta_poc[0], -e->sl->pos_delta_poc[0]};
             for (int X = 0; X < 2; X++) {
                 if (!(cur.dir & (1 << X))) continue;
-                mv_t pl[2]; amvp_list(s, x, y, size, X, dpoc, pl);
+                mv_t pl[2]; amvp_list(&nbs, X, dpoc, pl);
                 int c0 = mvd_bits(cur.mv[X].x - pl[0].x) + mvd_bits(cur.mv[X].y - pl[0].y);
                 int c1 = mvd_bits(cur.mv[X].x - pl[1].x) + mvd_bits(cur.mv[X].y - pl[1].y);
                 int idx = c1 < c0;
@@ -661,8 +704,8 @@ static void code_cu(slice_enc *e, int x, int y, int log2)
     /* intra 2Nx2N */
     if (log2 == KS_CELL_LOG2) cb_bin(c, CX_PART_MODE, 1);
     int cand_a = 1, cand_b = 1;                       /* 8.4.2 */
-    if (avail(s, x, y, x - 1, y)) { const ks_cell *n = cell_at(s, x - 1, y); if (n->flags & KS_F_INTRA) cand_a = n->intra_mode; }
-    if (avail(s, x, y, x, y - 1) && ((y - 1) >> KS_CTU_LOG2) == (y >> KS_CTU_LOG2)) { const ks_cell *n = cell_at(s, x, y - 1); if (n->flags & KS_F_INTRA) cand_b = n->intra_mode; }
+    if (x > 0) { const ks_cell *n = cell_at(s, x - 1, y); if (n->flags & KS_F_INTRA) cand_a = n->intra_mode; }
+    if (y > 0 && ((y - 1) >> KS_CTU_LOG2) == (y >> KS_CTU_LOG2)) { const ks_cell *n = cell_at(s, x, y - 1); if (n->flags & KS_F_INTRA) cand_b = n->intra_mode; }
     int mpm[3];
     if (cand_a == cand_b) {
         if (cand_a < 2) { mpm[0] = 0; mpm[1] = 1; mpm[2] = 26; }
@@ -695,8 +738,8 @@ static void code_quadtree(slice_enc *e, int x, int y, int log2)
     if (x + size <= s->width && y + size <= s->height && log2 > KS_CELL_LOG2) {
         split = cell_at(s, x, y)->cu_log2 < log2;
         int depth = KS_CTU_LOG2 - log2, ctx = 0;
-        if (avail(s, x, y, x - 1, y)) ctx += (KS_CTU_LOG2 - cell_at(s, x - 1, y)->cu_log2) > depth;
-        if (avail(s, x, y, x, y - 1)) ctx += (KS_CTU_LOG2 - cell_at(s, x, y - 1)->cu_log2) > depth;
+        if (x > 0) ctx += (KS_CTU_LOG2 - cell_at(s, x - 1, y)->cu_log2) > depth;
+        if (y > 0) ctx += (KS_CTU_LOG2 - cell_at(s, x, y - 1)->cu_log2) > depth;
         cb_bin(c, CX_SPLIT_CU + ctx, split);
     } else split = log2 > KS_CELL_LOG2;
     if (split) {
