@@ -30,6 +30,8 @@ typedef struct ks265_config {
     int device;                 /* CUDA device ordinal */
     int psnr;                   /* compute per-plane SSE on the device */
     int bframes;                /* -bframes: B pictures between anchors (0 = IDR + P...; default 0 this round) */
+    int me;                     /* -me: integer search, 0 small diamond (DIA), 1 hexagon (HEX); the reference's 2 (UMH) maps to 1 */
+    double crf;                 /* -crf (used with -rc 3) */
 } ks265_config;
 
 typedef struct ks265_gop_stats {

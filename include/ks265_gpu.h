@@ -38,6 +38,7 @@ typedef struct ks_gpu_cfg {
     int n_rec_slots;    /* reconstructed/reference pictures resident on the device (>= 2) */
     int n_syn_slots;    /* pictures in flight between submit and finish (>= 2) */
     int satd;           /* sub-pel cost = SATD (had_c) instead of SAD: reference `satdInter`, presets fast..placebo */
+    int me_method;      /* integer search: 0 small diamond (interMeDia E@0x4849d0), 1 hexagon + square refine (interMeHex E@0x484c00) */
 } ks_gpu_cfg;
 
 typedef struct ks_pic_params {
@@ -55,6 +56,7 @@ typedef struct ks_pic_params {
     int dist_l0;        /* POC(cur) - POC(list-0 reference) > 0 */
     int dist_anchor;    /* POC(list-1 reference) - POC(list-0 reference); prev_syn_slot names the later anchor, whose vectors
                            (spanning dist_anchor pictures) are scaled to seed both searches */
+    int want_me_cost;   /* P pictures: return the sum of the per-cell winning search costs (host rate control's complexity measure) */
 } ks_pic_params;
 
 /* results of one picture: pointers into pinned host memory owned by the context, valid until the syntax slot is reused */
@@ -65,6 +67,7 @@ typedef struct ks_pic_out {
     uint32_t          n_cg;
     uint64_t          sse[3];
     const ks_cell_b  *cells_b;     /* B pictures, else NULL */
+    uint64_t          me_cost;     /* want_me_cost: sum over cells of (SAD or SATD + lambda*mv bits) of the chosen vector, else 0 */
 } ks_pic_out;
 
 /* replaces: createHevcEncoder/createModules (E@0x4b44f0/0x4b3380) device-side state; width/height = display size */

@@ -32,12 +32,12 @@ class KsCtuSyn(C.Structure):
 
 class KsGpuCfg(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("me_range", "me_iters", "subpel", "sign_hiding", "sao", "strong_intra",
-                                       "n_src_slots", "n_rec_slots", "n_syn_slots", "satd")]
+                                       "n_src_slots", "n_rec_slots", "n_syn_slots", "satd", "me_method")]
 
 
 class KsPicParams(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("slice_type", "qp", "src_slot", "ref_slot", "out_slot", "syn_slot", "prev_syn_slot",
-                                       "beta_offset_div2", "tc_offset_div2", "want_sse", "ref1_slot", "dist_l0", "dist_anchor")]
+                                       "beta_offset_div2", "tc_offset_div2", "want_sse", "ref1_slot", "dist_l0", "dist_anchor", "want_me_cost")]
 
 
 class KsCellB(C.Structure):
@@ -46,13 +46,13 @@ class KsCellB(C.Structure):
 
 class KsPicOut(C.Structure):
     _fields_ = [("cells", C.POINTER(KsCell)), ("ctus", C.POINTER(KsCtuSyn)), ("levels", C.POINTER(C.c_int16)),
-                ("n_cg", C.c_uint32), ("sse", C.c_uint64 * 3), ("cells_b", C.POINTER(KsCellB))]
+                ("n_cg", C.c_uint32), ("sse", C.c_uint64 * 3), ("cells_b", C.POINTER(KsCellB)), ("me_cost", C.c_uint64)]
 
 
 class Ks265Config(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("fps", C.c_double), ("preset", C.c_int), ("rc", C.c_int),
                 ("qp", C.c_int), ("iper", C.c_int), ("fixqp", C.c_int), ("sao", C.c_int), ("sign_hiding", C.c_int),
-                ("me_range", C.c_int), ("me_iters", C.c_int), ("subpel", C.c_int), ("satd", C.c_int), ("device", C.c_int), ("psnr", C.c_int), ("bframes", C.c_int)]
+                ("me_range", C.c_int), ("me_iters", C.c_int), ("subpel", C.c_int), ("satd", C.c_int), ("device", C.c_int), ("psnr", C.c_int), ("bframes", C.c_int), ("me", C.c_int), ("crf", C.c_double)]
 
 
 class Ks265GopStats(C.Structure):

@@ -15,6 +15,11 @@ __constant__ int      c_chroma_taps[8][4];
 __constant__ int      c_luma_taps_packed[4][2];   /* taps 0..3 / 4..7 as 4 x s8 (dp4a operand) */
 __constant__ int      c_chroma_taps_packed[8];
 __constant__ int      c_vtaps_pk[4][2][3];        /* vertical luma taps as s8 pairs for dp2a over row-pair planes: [fy][first-row parity][word] */
+/* x264 hexagon pattern hex2[8] (wraps so that dir-1..dir+1 index without a modulo) and the square refinement order */
+__constant__ int      c_hex_dx[8] = {-1, -2, -1, 1, 2, 1, -1, -2};
+__constant__ int      c_hex_dy[8] = {-2, 0, 2, 2, 0, -2, -2, 0};
+__constant__ int      c_sq_dx[8] = {0, 0, -1, 1, -1, -1, 1, 1};
+__constant__ int      c_sq_dy[8] = {-1, 1, 0, 0, -1, 1, -1, 1};
 __constant__ uint8_t  c_tc_table[54];
 __constant__ uint8_t  c_beta_table[52];
 __constant__ uint8_t  c_chroma_qp[58];

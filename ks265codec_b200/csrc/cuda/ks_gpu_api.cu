@@ -17,9 +17,9 @@ static const uint8_t k_chroma_qp[58] = {0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,16
 
 #define KS_NSTAGE 6   /* me, recon_inter, recon_intra, deblock, sao, pack */
 struct ks_syn_slot {
-    ks_cell *d_cells; ks_ctu_syn *d_ctus; int16_t *d_pool; uint32_t *d_ncg; unsigned long long *d_sse; ks_cell_b *d_cells_b;
+    ks_cell *d_cells; ks_ctu_syn *d_ctus; int16_t *d_pool; uint32_t *d_ncg; unsigned long long *d_sse, *d_mecost; ks_cell_b *d_cells_b;
     ks_cell_b *h_cells_b; int is_b;
-    ks_cell *h_cells; ks_ctu_syn *h_ctus; int16_t *h_pool; uint32_t *h_ncg; unsigned long long *h_sse;
+    ks_cell *h_cells; ks_ctu_syn *h_ctus; int16_t *h_pool; uint32_t *h_ncg; unsigned long long *h_sse, *h_mecost;
     cudaEvent_t done; int pending;
     cudaEvent_t ev[KS_NSTAGE + 1]; int stage_of[KS_NSTAGE + 1]; int nev; size_t d2h_bytes;
 };
@@ -105,11 +105,13 @@ extern "C" ks_gpu_ctx *ks_gpu_open(int device, int width, int height, const ks_g
             ok = ok && cudaMalloc(&s->d_pool, poolb) == cudaSuccess;
             ok = ok && cudaMalloc(&s->d_ncg, sizeof(uint32_t)) == cudaSuccess;
             ok = ok && cudaMalloc(&s->d_sse, 3 * sizeof(unsigned long long)) == cudaSuccess;
+            ok = ok && cudaMalloc(&s->d_mecost, sizeof(unsigned long long)) == cudaSuccess;
             ok = ok && cudaHostAlloc(&s->h_cells, ncell * sizeof(ks_cell), cudaHostAllocDefault) == cudaSuccess;
             ok = ok && cudaHostAlloc(&s->h_ctus, nctu * sizeof(ks_ctu_syn), cudaHostAllocDefault) == cudaSuccess;
             ok = ok && cudaHostAlloc(&s->h_pool, poolb, cudaHostAllocDefault) == cudaSuccess;
             ok = ok && cudaHostAlloc(&s->h_ncg, sizeof(uint32_t), cudaHostAllocDefault) == cudaSuccess;
             ok = ok && cudaHostAlloc(&s->h_sse, 3 * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
+            ok = ok && cudaHostAlloc(&s->h_mecost, sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
             ok = ok && cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming) == cudaSuccess;
             for (int k = 0; k <= KS_NSTAGE; k++) ok = ok && cudaEventCreate(&s->ev[k]) == cudaSuccess;
             if (ok) cudaMemset(s->d_ctus, 0, nctu * sizeof(ks_ctu_syn));
@@ -134,7 +136,7 @@ extern "C" void ks_gpu_close(ks_gpu_ctx *c)
     for (int i = 0; i < 2; i++) { if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]); if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]); }
     if (c->syn) for (int i = 0; i < c->cfg.n_syn_slots; i++) {
         ks_syn_slot *s = &c->syn[i];
-        cudaFree(s->d_cells); cudaFree(s->d_cells_b); if (s->h_cells_b) cudaFreeHost(s->h_cells_b); cudaFree(s->d_ctus); cudaFree(s->d_pool); cudaFree(s->d_ncg); cudaFree(s->d_sse);
+        cudaFree(s->d_cells); cudaFree(s->d_cells_b); if (s->h_cells_b) cudaFreeHost(s->h_cells_b); cudaFree(s->d_ctus); cudaFree(s->d_pool); cudaFree(s->d_ncg); cudaFree(s->d_sse); cudaFree(s->d_mecost); if (s->h_mecost) cudaFreeHost(s->h_mecost);
         if (s->h_cells) cudaFreeHost(s->h_cells); if (s->h_ctus) cudaFreeHost(s->h_ctus); if (s->h_pool) cudaFreeHost(s->h_pool);
         if (s->h_ncg) cudaFreeHost(s->h_ncg); if (s->h_sse) cudaFreeHost(s->h_sse);
         if (s->done) cudaEventDestroy(s->done);
@@ -221,7 +223,7 @@ static int fill_params(const ks_gpu_ctx *c, const ks_pic_params *p, KsPicParams 
     pp->W = c->W; pp->H = c->H; pp->cw = c->cw; pp->ch = c->ch; pp->ctw = c->ctw; pp->cth = c->cth;
     pp->slice_type = p->slice_type; pp->qp = p->qp; pp->qpc = k_chroma_qp[p->qp];
     pp->lambda_sad_q4 = k_lambda_sad_q4[p->qp]; pp->lambda_sse_q4 = k_lambda_sse_q4[p->qp];
-    pp->me_range = c->cfg.me_range; pp->me_iters = c->cfg.me_iters; pp->subpel = c->cfg.subpel; pp->satd = c->cfg.satd;
+    pp->me_range = c->cfg.me_range; pp->me_iters = c->cfg.me_iters; pp->subpel = c->cfg.subpel; pp->satd = c->cfg.satd; pp->me_method = c->cfg.me_method;
     pp->sign_hiding = c->cfg.sign_hiding; pp->sao = c->cfg.sao; pp->strong_intra = c->cfg.strong_intra;
     pp->beta_offset_div2 = p->beta_offset_div2; pp->tc_offset_div2 = p->tc_offset_div2;
     return 0;
@@ -254,13 +256,15 @@ extern "C" int ks_gpu_encode_picture_submit(ks_gpu_ctx *c, const ks_pic_params *
             KsPlanes ref1 = planes_of(c, c->d_rec[p->ref1_slot]), pred1 = planes_of(c, c->d_pred1);
             KsPicParams p0 = pp, p1 = pp;
             p0.pred_num = p->dist_l0; p0.pred_den = p->dist_anchor; p1.pred_num = p->dist_l0 - p->dist_anchor; p1.pred_den = p->dist_anchor;
-            ks_launch_me(p0, src.p[0], ref, prev, s->d_cells, pred, c->d_cost0, c->st);
-            ks_launch_me(p1, src.p[0], ref1, prev, c->d_cells1, pred1, c->d_cost1, c->st);
+            ks_launch_me(p0, src.p[0], ref, prev, s->d_cells, pred, c->d_cost0, NULL, c->st);
+            ks_launch_me(p1, src.p[0], ref1, prev, c->d_cells1, pred1, c->d_cost1, NULL, c->st);
             ks_launch_bidir(pp, src.p[0], ref, ref1, prev, p0.pred_num, p1.pred_num, p->dist_anchor, c->d_cells1, c->d_cost0, c->d_cost1, pred1, s->d_cells, s->d_cells_b, pred, c->st);
             c->launches += 2 * KS_LAUNCHES_ME + 1;
             cb = s->d_cells_b;
         } else {
-            ks_launch_me(pp, src.p[0], ref, prev, s->d_cells, pred, NULL, c->st); c->launches += KS_LAUNCHES_ME;
+            const bool mc = p->want_me_cost != 0;
+            if (mc) CK(cudaMemsetAsync(s->d_mecost, 0, sizeof(unsigned long long), c->st));
+            ks_launch_me(pp, src.p[0], ref, prev, s->d_cells, pred, NULL, mc ? s->d_mecost : NULL, c->st); c->launches += KS_LAUNCHES_ME;
         }
         MARK(1);
         ks_launch_recon_inter(pp, src, pred, pre, lv, s->d_cells, cb, c->st); c->launches += KS_LAUNCHES_RECON;
@@ -282,6 +286,8 @@ extern "C" int ks_gpu_encode_picture_submit(ks_gpu_ctx *c, const ks_pic_params *
     CK(cudaMemcpyAsync(s->h_ncg, s->d_ncg, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->st));
     if (p->want_sse) CK(cudaMemcpyAsync(s->h_sse, s->d_sse, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->st));
     else { s->h_sse[0] = s->h_sse[1] = s->h_sse[2] = 0; }
+    if (p->slice_type == KS_SLICE_P && p->want_me_cost) CK(cudaMemcpyAsync(s->h_mecost, s->d_mecost, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->st));
+    else *s->h_mecost = 0;
     CK(cudaEventRecord(s->done, c->st));
     s->pending = 1;
     return 0;
@@ -311,6 +317,7 @@ extern "C" int ks_gpu_encode_picture_finish(ks_gpu_ctx *c, int syn_slot, ks_pic_
     s->pending = 0;
     out->cells = s->h_cells; out->ctus = s->h_ctus; out->levels = s->h_pool; out->n_cg = n;
     out->sse[0] = s->h_sse[0]; out->sse[1] = s->h_sse[1]; out->sse[2] = s->h_sse[2];
+    out->me_cost = *s->h_mecost;
     out->cells_b = s->is_b ? s->h_cells_b : NULL;
     return 0;
 }
@@ -358,7 +365,7 @@ extern "C" int ks_gpu_debug_me(ks_gpu_ctx *c, const ks_pic_params *p, ks_cell *c
     KsPlanes src = planes_of(c, c->d_src[p->src_slot]), ref = planes_of(c, c->d_rec[p->ref_slot]);
     const ks_cell *prev = p->prev_syn_slot >= 0 ? c->syn[p->prev_syn_slot].d_cells : NULL;
     KsPlanes nopred; nopred.p[0] = nopred.p[1] = nopred.p[2] = NULL;
-    ks_launch_me(pp, src.p[0], ref, prev, s->d_cells, nopred, NULL, c->st); c->launches += KS_LAUNCHES_ME;
+    ks_launch_me(pp, src.p[0], ref, prev, s->d_cells, nopred, NULL, NULL, c->st); c->launches += KS_LAUNCHES_ME;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(cells_out, s->d_cells, (size_t)c->cw * c->ch * sizeof(ks_cell), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));

@@ -17,7 +17,7 @@ struct KsPicParams {
     int ctw, cth;           /* 64x64 CTUs */
     int slice_type, qp, qpc;
     int lambda_sad_q4, lambda_sse_q4;
-    int me_range, me_iters, subpel, satd;
+    int me_range, me_iters, subpel, satd, me_method;
     int sign_hiding, sao, strong_intra;
     int beta_offset_div2, tc_offset_div2;
     int pred_num, pred_den;  /* motion-search predictor = co-located vector * pred_num / pred_den (C division); den 0 = vector as is */
@@ -25,7 +25,7 @@ struct KsPicParams {
 
 /* all launches are asynchronous on `st` */
 void ks_upload_tables();
-void ks_launch_me(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref, const ks_cell *prev_cells, ks_cell *cells, KsPlanes pred, int *costs, cudaStream_t st);
+void ks_launch_me(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref, const ks_cell *prev_cells, ks_cell *cells, KsPlanes pred, int *costs, unsigned long long *cost_sum, cudaStream_t st);
 /* B pictures: per cell best of list 0 / list 1 / bi-prediction; finalises cells, cells_b and the prediction planes */
 void ks_launch_bidir(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref0, KsPlanes ref1, const ks_cell *anchor_cells, int num0, int num1, int den,
                      const ks_cell *cells1, const int *cost0, const int *cost1, KsPlanes pred1, ks_cell *cells, ks_cell_b *cells_b, KsPlanes pred, cudaStream_t st);

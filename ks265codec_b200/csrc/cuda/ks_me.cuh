@@ -371,7 +371,7 @@ __device__ __forceinline__ void ks_mc_chroma8(uint8_t *cwin, int16_t *tmp, const
 #define KS_ME_WARPS 8
 __global__ void __launch_bounds__(KS_ME_WARPS * KS_WARP, 4)
 ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref, const ks_cell *__restrict__ prev_cells,
-             ks_cell *__restrict__ cells, KsPlanes pred, int *__restrict__ costs)
+             ks_cell *__restrict__ cells, KsPlanes pred, int *__restrict__ costs, unsigned long long *__restrict__ cost_sum)
 {
     __shared__ __align__(16) KsWarpScratch scratch[KS_ME_WARPS];
     __shared__ uint8_t cwins[KS_ME_WARPS][144];
@@ -408,6 +408,7 @@ ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref, con
             if (c < bc) { bc = c; bx = cx; by = cy; }
         }
     }
+    if (pp.me_method == 0) {
     /* ---- small diamond (reference: interMeDia E@0x4849d0, x264 DIA with sad4 order up,down,left,right) ---- */
     for (int it = 0; it < pp.me_iters; it++) {
         int bxw = x0 + bx - wx0, byw = y0 + by - wy0;
@@ -431,6 +432,48 @@ ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref, con
         }
         if (bk < 0) break;
         bx += dx[bk]; by += dy[bk]; bc = lc;
+    }
+    } else {
+    /* ---- hexagon + square refine (reference: interMeHex E@0x484c00 = x264 HEX: six points once, then the three new points of
+     *      the hexagon moved in the winning direction (mod6m1 rotation), then the eight square neighbours) ---- */
+#define KS_RECENTER(m, xhi, yhi) { int bxw_ = x0 + bx - wx0, byw_ = y0 + by - wy0; \
+        if (bxw_ < (m) || bxw_ > (xhi) || byw_ < (m) || byw_ > (yhi)) { ks_center_window(x0, y0, bx, by, wx0, wy0); ks_load_window(sc->win, refY, W, H, wx0, wy0, lane); } }
+#define KS_SAD2(ax, ay, cx_, cy_) ks_warp_sum(ks_sad_partial(sc->win, x0 + bx - wx0 + (ax), y0 + by - wy0 + (ay), lane, s.x, s.y) | \
+                                              (ks_sad_partial(sc->win, x0 + bx - wx0 + (cx_), y0 + by - wy0 + (cy_), lane, s.x, s.y) << 16))
+#define KS_TRY(sadv, ox, oy, tag) { int nx = bx + (ox), ny = by + (oy); \
+        if (abs(nx) <= R && abs(ny) <= R) { int c = (int)(sadv) + MVCOST(nx * 4, ny * 4); if (c < lc) { lc = c; bk = (tag); } } }
+        int dir, bk = -1, lc = bc;
+        KS_RECENTER(2, 33, 22)
+        {
+            const unsigned a = KS_SAD2(-2, 0, -1, 2), b = KS_SAD2(1, 2, 2, 0), c2 = KS_SAD2(1, -2, -1, -2);
+            KS_TRY(a & 0xffffu, -2, 0, 0) KS_TRY(a >> 16, -1, 2, 1) KS_TRY(b & 0xffffu, 1, 2, 2)
+            KS_TRY(b >> 16, 2, 0, 3) KS_TRY(c2 & 0xffffu, 1, -2, 4) KS_TRY(c2 >> 16, -1, -2, 5)
+        }
+        if (bk >= 0) {
+            dir = bk; bx += c_hex_dx[dir + 1]; by += c_hex_dy[dir + 1]; bc = lc;
+            for (int it = 1; it < pp.me_iters; it++) {
+                KS_RECENTER(2, 33, 22)
+                const int ax = c_hex_dx[dir], ay = c_hex_dy[dir], mx_ = c_hex_dx[dir + 1], my_ = c_hex_dy[dir + 1], ex = c_hex_dx[dir + 2], ey = c_hex_dy[dir + 2];
+                const unsigned a = KS_SAD2(ax, ay, mx_, my_);
+                const unsigned b = ks_warp_sum(ks_sad_partial(sc->win, x0 + bx - wx0 + ex, y0 + by - wy0 + ey, lane, s.x, s.y));
+                bk = -1; lc = bc;
+                KS_TRY(a & 0xffffu, ax, ay, 0) KS_TRY(a >> 16, mx_, my_, 1) KS_TRY(b & 0xffffu, ex, ey, 2)
+                if (bk < 0) break;
+                dir += bk - 1; dir = dir < 0 ? 5 : (dir > 5 ? 0 : dir);
+                bx += c_hex_dx[dir + 1]; by += c_hex_dy[dir + 1]; bc = lc;
+            }
+        }
+        KS_RECENTER(1, 34, 23)
+        {
+            const unsigned a = KS_SAD2(0, -1, 0, 1), b = KS_SAD2(-1, 0, 1, 0), c2 = KS_SAD2(-1, -1, -1, 1), d = KS_SAD2(1, -1, 1, 1);
+            bk = -1; lc = bc;
+            KS_TRY(a & 0xffffu, 0, -1, 0) KS_TRY(a >> 16, 0, 1, 1) KS_TRY(b & 0xffffu, -1, 0, 2) KS_TRY(b >> 16, 1, 0, 3)
+            KS_TRY(c2 & 0xffffu, -1, -1, 4) KS_TRY(c2 >> 16, -1, 1, 5) KS_TRY(d & 0xffffu, 1, -1, 6) KS_TRY(d >> 16, 1, 1, 7)
+            if (bk >= 0) { bx += c_sq_dx[bk]; by += c_sq_dy[bk]; bc = lc; }
+        }
+#undef KS_RECENTER
+#undef KS_SAD2
+#undef KS_TRY
     }
     /* ---- half then quarter refinement, 8 neighbours each (reference: subMeSquare E@0x4aee80).  The candidates of a
      *      stage share planes of raw horizontal sums: 2 planes + 2 vertical-only blocks for the half stage, 3 planes (one
@@ -493,6 +536,7 @@ ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref, con
         ks_cell c; c.mvx = (int16_t)mx; c.mvy = (int16_t)my; c.cu_log2 = 4; c.flags = 0; c.intra_mode = 0; c.rsv = 0;
         cells[cell] = c;
         if (costs) costs[cell] = bc;
+        if (cost_sum) atomicAdd(cost_sum, (unsigned long long)bc);      /* integer sum: order-independent */
     }
     /* ---- the search already holds the winner's luma prediction: emit it (and the chroma prediction for the same vector) so
      *      the residual kernel needs no motion compensation pass of its own (reference: getReusSubMePred E@0x486770 re-uses the
@@ -507,10 +551,10 @@ ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref, con
     }
 }
 
-void ks_launch_me(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref, const ks_cell *prev_cells, ks_cell *cells, KsPlanes pred, int *costs, cudaStream_t st)
+void ks_launch_me(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref, const ks_cell *prev_cells, ks_cell *cells, KsPlanes pred, int *costs, unsigned long long *cost_sum, cudaStream_t st)
 {
     int ncell = pp.cw * pp.ch;
-    ks_me_kernel<<<(ncell + KS_ME_WARPS - 1) / KS_ME_WARPS, KS_ME_WARPS * KS_WARP, 0, st>>>(pp, srcY, ref, prev_cells, cells, pred, costs);
+    ks_me_kernel<<<(ncell + KS_ME_WARPS - 1) / KS_ME_WARPS, KS_ME_WARPS * KS_WARP, 0, st>>>(pp, srcY, ref, prev_cells, cells, pred, costs, cost_sum);
 }
 
 /* ------------------------------------------------------------------ bi-prediction (B pictures) ---- */

@@ -69,14 +69,14 @@ static void usage(void)
     printf("ks265 B200 appencoder (AppEncoder-compatible)\n"
            "  -i <file.yuv> -wdt <w> -hgt <h> [-fr fps] [-frms n] [-b out.265] [-o recon.yuv]\n"
            "  [-preset ultrafast|superfast|veryfast|fast|medium|slow|veryslow|placebo] [-rc 0] [-qp q] [-iper n] [-fixqp 0|1]\n"
-           "  [-sao 0..4] [-subme 0..2] [-merange n] [-bframes n] [-psnr 0|1|2] [-md5 0|1] [-threads n] [-gpus n] [-streams n]\n");
+           "  [-sao 0..4] [-subme 0..2] [-merange n] [-bframes n] [-me 0|1] [-rc 0|3 -crf x] [-psnr 0|1|2] [-md5 0|1] [-threads n] [-gpus n] [-streams n]\n");
 }
 
 int main(int argc, char **argv)
 {
     app_cfg a; memset(&a, 0, sizeof(a));
     a.fr = 30.0; a.preset = "veryfast"; a.gpus = 1; a.streams = 4; a.frms = -1;
-    int qp = 27, iper = 128, fixqp = 0, rc = 0, sao = -1, subme = -1, merange = -1, bframes = -1;
+    int qp = 27, iper = 128, fixqp = 0, rc = 0, sao = -1, subme = -1, merange = -1, bframes = -1, me = -1; double crf = -1;
     for (int i = 1; i < argc; i++) {
         const char *k = argv[i], *v = i + 1 < argc ? argv[i + 1] : NULL;
         if (!strcmp(k, "-v") || !strcmp(k, "-h") || !strcmp(k, "--help")) { usage(); return 0; }
@@ -91,17 +91,21 @@ int main(int argc, char **argv)
         else if (!strcmp(k, "-md5")) a.md5 = atoi(v); else if (!strcmp(k, "-gpus")) a.gpus = atoi(v);
         else if (!strcmp(k, "-streams")) a.streams = atoi(v); else if (!strcmp(k, "-sao")) sao = atoi(v);
         else if (!strcmp(k, "-bframes")) bframes = atoi(v);
+        else if (!strcmp(k, "-me")) me = atoi(v);
+        else if (!strcmp(k, "-crf")) crf = atof(v);
         else if (!strcmp(k, "-subme")) subme = atoi(v); else if (!strcmp(k, "-merange")) merange = atoi(v);
         else if (!strcmp(k, "-threads")) { /* host worker count is -streams x -gpus here */ }
         else fprintf(stderr, "appencoder: warning: option %s %s is accepted for compatibility and ignored on the device path\n", k, v);
     }
     if (!a.in || a.w <= 0 || a.h <= 0) { usage(); return 2; }
-    if (rc != 0) { fprintf(stderr, "appencoder: -rc %d: rate control stays on the host and is not implemented yet; only -rc 0\n", rc); return 2; }
+    if (rc != 0 && rc != 3) { fprintf(stderr, "appencoder: -rc %d (ABR/CBR) is not implemented; use -rc 0 (fixed QP) or -rc 3 (CRF)\n", rc); return 2; }
     a.cfg.width = a.w; a.cfg.height = a.h;
     if (ks265_config_default_preset(&a.cfg, a.preset)) { fprintf(stderr, "appencoder: unknown preset %s\n", a.preset); return 2; }
     a.cfg.fps = a.fr; a.cfg.qp = qp; a.cfg.iper = iper < 1 ? 1 : iper; a.cfg.fixqp = fixqp; a.cfg.psnr = a.psnr > 0 || 1;
     if (sao >= 0) a.cfg.sao = sao > 4 ? 4 : sao; if (subme >= 0) a.cfg.subpel = subme > 2 ? 2 : subme; if (merange > 0) a.cfg.me_range = merange;
     if (bframes >= 0) a.cfg.bframes = bframes > 7 ? 7 : bframes;
+    if (me >= 0) a.cfg.me = me > 0;
+    a.cfg.rc = rc; if (crf >= 0) a.cfg.crf = crf;
     if (a.gpus < 1) a.gpus = 1; if (a.streams < 1) a.streams = 1;
 
     job_t job; memset(&job, 0, sizeof(job));

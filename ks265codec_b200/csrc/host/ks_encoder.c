@@ -7,6 +7,7 @@
 #include "ks265_enc.h"
 #include "ks265_gpu.h"
 #include "ks_bitstream.h"
+#include "ks_ratecontrol.h"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -37,6 +38,8 @@ int ks265_config_default_preset(ks265_config *cfg, const char *preset)
     cfg->me_iters = p == 0 ? 8 : (p == 1 ? 12 : (p == 2 ? 16 : 32));
     cfg->subpel = p == 0 ? 1 : 2;
     cfg->satd = p >= 3;
+    cfg->me = 0;                     /* small diamond, the search the north star names; -me 1 = the reference's per-preset default (HEX) */
+    cfg->crf = 24.0;
     return 0;
 }
 
@@ -46,9 +49,9 @@ ks265_encoder *ks265_encoder_open(const ks265_config *cfg, int *err)
     ks265_encoder *enc = (ks265_encoder *)calloc(1, sizeof(*enc));
     if (!enc) { if (err) *err = -12; return NULL; }
     enc->cfg = *cfg;
-    if (cfg->rc != 0) { fprintf(stderr, "ks265: only -rc 0 (fixed QP) is implemented on the device path\n"); if (err) *err = -22; free(enc); return NULL; }
+    if (cfg->rc != 0 && cfg->rc != 3) { fprintf(stderr, "ks265: -rc %d is not implemented (0 = fixed QP, 3 = CRF)\n", cfg->rc); if (err) *err = -22; free(enc); return NULL; }
     ks_gpu_cfg g; memset(&g, 0, sizeof(g));
-    g.me_range = cfg->me_range; g.me_iters = cfg->me_iters; g.subpel = cfg->subpel; g.sign_hiding = cfg->sign_hiding; g.sao = cfg->sao; g.satd = cfg->satd;
+    g.me_range = cfg->me_range; g.me_iters = cfg->me_iters; g.subpel = cfg->subpel; g.sign_hiding = cfg->sign_hiding; g.sao = cfg->sao; g.satd = cfg->satd; g.me_method = cfg->me;
     g.strong_intra = 1; g.n_src_slots = 3; g.n_rec_slots = cfg->bframes ? 4 : 2; g.n_syn_slots = cfg->bframes ? 4 : 2;
     enc->gpu = ks_gpu_open(cfg->device, cfg->width, cfg->height, &g, &e);
     if (!enc->gpu) { if (err) *err = e; free(enc); return NULL; }
@@ -101,8 +104,8 @@ static void plan_pictures(const ks265_encoder *enc, int n, coded_pic *cp, int *c
         memset(pp, 0, sizeof(*pp));
         cp[i].disp = order[i]; cp[i].type = type[i]; cp[i].l0 = l0[i]; cp[i].l1 = l1[i];
         pp->slice_type = type[i];
-        pp->qp = c->fixqp ? c->qp : (type[i] == KS_SLICE_I ? c->qp : (type[i] == KS_SLICE_P ? c->qp + 1 : c->qp + 3));
-        if (pp->qp > 51) pp->qp = 51;
+        pp->qp = c->qp;               /* the rate control sets the real value right before the picture is submitted */
+        pp->want_me_cost = c->rc == 3 && type[i] == KS_SLICE_P;
         pp->src_slot = i % 3;
         pp->beta_offset_div2 = type[i] == KS_SLICE_I ? 0 : 2; pp->tc_offset_div2 = pp->beta_offset_div2;   /* reference: I slices override to 0/0, others PPS 2/2 */
         pp->want_sse = c->psnr;
@@ -143,6 +146,9 @@ static long encode_gop_impl(ks265_encoder *enc, const uint8_t *frames, const voi
     coded_pic *cp = (coded_pic *)malloc(sizeof(coded_pic) * (size_t)(nframes + 1));
     if (!cp) return -12;
     plan_pictures(enc, nframes, cp, &cnt);
+    ks_rc rc;                          /* one rate-control state per closed-GOP shard: shards stay independent */
+    if (ks_rc_init(&rc, enc->cfg.rc, enc->cfg.qp, enc->cfg.fixqp, enc->cfg.crf, (enc->W >> 4) * (enc->H >> 4))) { free(cp); return -22; }
+    cp[0].pp.qp = ks_rc_picture_qp(&rc, cp[0].type);
     if (bs) {
         if ((n = ks_write_vps(sp, bs + pos, cap - pos)) < 0) { free(cp); return -28; } pos += n;
         if ((n = ks_write_sps(sp, bs + pos, cap - pos)) < 0) { free(cp); return -28; } pos += n;
@@ -156,7 +162,11 @@ static long encode_gop_impl(ks265_encoder *enc, const uint8_t *frames, const voi
         ks_pic_out out;
         if (i + 1 < cnt && (r = upload(enc, cp[i + 1].pp.src_slot, cp[i + 1].disp, frames, frames_dev))) FAIL(r);
         if ((r = ks_gpu_encode_picture_finish(enc->gpu, cp[i].pp.syn_slot, &out))) FAIL(r);
-        if (i + 1 < cnt && (r = ks_gpu_encode_picture_submit(enc->gpu, &cp[i + 1].pp))) FAIL(r);
+        ks_rc_update(&rc, cp[i].type, out.me_cost);
+        if (i + 1 < cnt) {
+            cp[i + 1].pp.qp = ks_rc_picture_qp(&rc, cp[i + 1].type);
+            if ((r = ks_gpu_encode_picture_submit(enc->gpu, &cp[i + 1].pp))) FAIL(r);
+        }
         cg += out.n_cg;
         if (recon) {      /* picture i's reconstruction slot is not rewritten before picture i+2 is submitted */
             uint8_t *y = recon + fsz * cp[i].disp;

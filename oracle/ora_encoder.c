@@ -6,12 +6,15 @@
 #include "../ks265codec_b200/csrc/host/ks_bitstream.h"
 #include <stdlib.h>
 #include <string.h>
+#include "../ks265codec_b200/csrc/host/ks_ratecontrol.h"
 
 typedef struct ora_seq_cfg {
     int width, height;        /* display size */
     int nframes, qp, iper, fixqp;
     int me_range, me_iters, subpel, sign_hiding, sao, max_merge_cand, satd;
     int bframes;              /* B pictures between anchors (0 = IPPP) */
+    int me_method;            /* 0 diamond, 1 hexagon */
+    int rc, crf_x100;         /* rc 0: fixed QP; rc 3: CRF (crf * 100), QP per picture from the host rate control (ks_ratecontrol.c) */
 } ora_seq_cfg;
 
 static void store_cropped(const ora_pic *p, int w, int h, uint8_t *dst)
@@ -43,7 +46,7 @@ int ora_gop_schedule(int n, int bf, int *order, int *type, int *l0, int *l1)
 long ora_encode_sequence(const ora_seq_cfg *sc, const uint8_t *yuv, uint8_t *bs, size_t bs_cap, uint8_t *recon_out)
 {
     int W = (sc->width + 15) & ~15, H = (sc->height + 15) & ~15;
-    ora_cfg cfg = {W, H, sc->me_range, sc->me_iters, sc->subpel, sc->sign_hiding, sc->sao, 1, sc->satd};
+    ora_cfg cfg = {W, H, sc->me_range, sc->me_iters, sc->subpel, sc->sign_hiding, sc->sao, 1, sc->satd, sc->me_method};
     ks_stream_params sp; memset(&sp, 0, sizeof(sp));
     sp.disp_width = sc->width; sp.disp_height = sc->height; sp.width = W; sp.height = H; sp.fps_num = 30; sp.fps_den = 1;
     sp.sign_hiding = sc->sign_hiding; sp.sao = sc->sao != 0; sp.max_merge_cand = sc->max_merge_cand;
@@ -65,20 +68,22 @@ long ora_encode_sequence(const ora_seq_cfg *sc, const uint8_t *yuv, uint8_t *bs,
     for (int g0 = 0; g0 < sc->nframes; g0 += sc->iper) {
         int gn = sc->nframes - g0 < sc->iper ? sc->nframes - g0 : sc->iper;
         int cnt = ora_gop_schedule(gn, sc->bframes, order, type, l0, l1);
+        ks_rc rc;                 /* one rate-control state per closed-GOP shard, like the product */
+        if (ks_rc_init(&rc, sc->rc, sc->qp, sc->fixqp, sc->crf_x100 / 100.0, cw * ch)) return -3;
         /* anchors alternate between fin[0]/fin[1] (+cells[0]/[1]); B pictures reconstruct into fin[2] (+cells[2]) */
         int slot_of_prev = -1, slot_of_next = -1, anchor_idx = 0;
         for (int i = 0; i < cnt; i++) {
             int f = order[i], t = type[i];
             ora_pic_load(&src, yuv + fsz * (size_t)(g0 + f), sc->width, sc->height);
-            int qp = sc->fixqp ? sc->qp : (t == KS_SLICE_I ? sc->qp : (t == KS_SLICE_P ? sc->qp + 1 : sc->qp + 3));
-            if (qp > 51) qp = 51;
+            int qp = ks_rc_picture_qp(&rc, t);
+            uint64_t me_cost = 0;
             memset(lv.c[0], 0, (size_t)W * H * 2); memset(lv.c[1], 0, (size_t)W * H / 2); memset(lv.c[2], 0, (size_t)W * H / 2);
             int slot; ks_cell *cur; ora_pic *out;
             if (t == KS_SLICE_B) { slot = 2; }
             else { slot = anchor_idx & 1; anchor_idx++; slot_of_prev = slot_of_next; slot_of_next = slot; }
             cur = cells[slot]; out = &fin[slot];
             if (t == KS_SLICE_I) ora_intra_picture(&cfg, qp, &src, &pre, cur, &lv);
-            else if (t == KS_SLICE_P) ora_inter_picture(&cfg, qp, &src, &fin[slot_of_prev], slot_of_prev >= 0 && i > 1 ? cells[slot_of_prev] : cells[slot_of_prev], &pre, cur, &lv);
+            else if (t == KS_SLICE_P) me_cost = ora_inter_picture(&cfg, qp, &src, &fin[slot_of_prev], slot_of_prev >= 0 && i > 1 ? cells[slot_of_prev] : cells[slot_of_prev], &pre, cur, &lv);
             else ora_b_picture(&cfg, qp, &src, &fin[slot_of_prev], &fin[slot_of_next], cells[slot_of_next], f - l0[i], l1[i] - l0[i], &pre, cur, cells_b, &lv);
             for (int ci = 0; ci < 3; ci++) memcpy(deb.c[ci].base, pre.c[ci].base, (size_t)pre.c[ci].stride * (pre.c[ci].h + 2 * ORA_PAD));
             int boff = t == KS_SLICE_I ? 0 : 2, toff = boff;
@@ -101,6 +106,7 @@ long ora_encode_sequence(const ora_seq_cfg *sc, const uint8_t *yuv, uint8_t *bs,
             if ((n = ks_write_slice(&sp, &sl, &syn, scratch, bs + pos, bs_cap - pos)) < 0) return -1;
             pos += n;
             if (recon_out) store_cropped(out, sc->width, sc->height, recon_out + fsz * (size_t)(g0 + f));
+            ks_rc_update(&rc, t, me_cost);
         }
     }
     ora_pic_free(&src); ora_pic_free(&pre); ora_pic_free(&deb); ora_pic_free(&fin[0]); ora_pic_free(&fin[1]); ora_pic_free(&fin[2]);

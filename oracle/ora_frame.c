@@ -182,16 +182,53 @@ static int me_cell(const ora_cfg *cfg, int lam, const ora_plane *src, const ora_
     int bx = 0, by = 0, bc = ICOST(0, 0);
     int cx = clip3(-R, R, (tpx + 2) >> 2), cy = clip3(-R, R, (tpy + 2) >> 2);
     if (cx || cy) { int c = ICOST(cx, cy); if (c < bc) { bc = c; bx = cx; by = cy; } }
-    for (int it = 0; it < cfg->me_iters; it++) {
-        int bk = -1, lc = bc;
-        for (int k = 0; k < 4; k++) {
-            int nx = bx + dia_dx[k], ny = by + dia_dy[k];
+    if (cfg->me_method == 0) {
+        for (int it = 0; it < cfg->me_iters; it++) {
+            int bk = -1, lc = bc;
+            for (int k = 0; k < 4; k++) {
+                int nx = bx + dia_dx[k], ny = by + dia_dy[k];
+                if (iabs(nx) > R || iabs(ny) > R) continue;
+                int c = ICOST(nx, ny);
+                if (c < lc) { lc = c; bk = k; }
+            }
+            if (bk < 0) break;
+            bx += dia_dx[bk]; by += dia_dy[bk]; bc = lc;
+        }
+    } else {
+        /* a4: x264 hexagon search (me.c X264_ME_HEX): all six points once, then only the three new points of the hexagon
+         * moved in the winning direction, rotating with mod6m1; finally the 8-neighbour square.  Ties keep the earlier point. */
+        static const int hx[8] = {-1, -2, -1, 1, 2, 1, -1, -2}, hy[8] = {-2, 0, 2, 2, 0, -2, -2, 0}, mod6m1[8] = {5, 0, 1, 2, 3, 4, 5, 0};
+        int dir = -1, lc = bc;
+        for (int k = 0; k < 6; k++) {
+            int nx = bx + hx[k + 1], ny = by + hy[k + 1];
+            if (iabs(nx) > R || iabs(ny) > R) continue;
+            int c = ICOST(nx, ny);
+            if (c < lc) { lc = c; dir = k; }
+        }
+        if (dir >= 0) {
+            bx += hx[dir + 1]; by += hy[dir + 1]; bc = lc;
+            for (int it = 1; it < cfg->me_iters; it++) {
+                int bk = -1; lc = bc;
+                for (int j = 0; j < 3; j++) {
+                    int nx = bx + hx[dir + j], ny = by + hy[dir + j];
+                    if (iabs(nx) > R || iabs(ny) > R) continue;
+                    int c = ICOST(nx, ny);
+                    if (c < lc) { lc = c; bk = j; }
+                }
+                if (bk < 0) break;
+                dir = mod6m1[dir + bk - 1 + 1];
+                bx += hx[dir + 1]; by += hy[dir + 1]; bc = lc;
+            }
+        }
+        static const int qx8[8] = {0, 0, -1, 1, -1, -1, 1, 1}, qy8[8] = {-1, 1, 0, 0, -1, 1, -1, 1};
+        int bk = -1; lc = bc;
+        for (int k = 0; k < 8; k++) {
+            int nx = bx + qx8[k], ny = by + qy8[k];
             if (iabs(nx) > R || iabs(ny) > R) continue;
             int c = ICOST(nx, ny);
             if (c < lc) { lc = c; bk = k; }
         }
-        if (bk < 0) break;
-        bx += dia_dx[bk]; by += dia_dy[bk]; bc = lc;
+        if (bk >= 0) { bx += qx8[bk]; by += qy8[bk]; bc = lc; }
     }
     int mx = bx * 4, my = by * 4;
     if (cfg->satd && cfg->subpel > 0) bc = (int)ora_satd(s, r0 + by * rs + bx, ss, rs, 16, 16) + MVCOST(mx, my);
@@ -239,17 +276,18 @@ static void recon_inter_cu(const ora_cfg *cfg, int qp, int qpc, const ora_pic *s
     }
 }
 
-void ora_inter_picture(const ora_cfg *cfg, int qp, const ora_pic *src, const ora_pic *ref, const ks_cell *prev_cells,
+uint64_t ora_inter_picture(const ora_cfg *cfg, int qp, const ora_pic *src, const ora_pic *ref, const ks_cell *prev_cells,
                        ora_pic *rec, ks_cell *cells, ora_levels *lv)
 {
     build_scans();
     int W = cfg->width, H = cfg->height, cw = W >> 4, ch = H >> 4;
     int lam = ora_lambda_sad_q4[qp], qpc = ora_chroma_qp[qp];
+    uint64_t cost_sum = 0;
     /* 1. motion search per 16x16 cell (independent of neighbours: predictor = co-located MV of the previous picture) */
     for (int cy = 0; cy < ch; cy++) for (int cx = 0; cx < cw; cx++) {
         int tpx = 0, tpy = 0, mx, my;
         if (prev_cells && !(prev_cells[cy * cw + cx].flags & KS_F_INTRA)) { tpx = prev_cells[cy * cw + cx].mvx; tpy = prev_cells[cy * cw + cx].mvy; }
-        me_cell(cfg, lam, &src->c[0], &ref->c[0], cx << 4, cy << 4, tpx, tpy, &mx, &my);
+        cost_sum += (uint64_t)me_cell(cfg, lam, &src->c[0], &ref->c[0], cx << 4, cy << 4, tpx, tpy, &mx, &my);
         ks_cell *c = &cells[cy * cw + cx];
         memset(c, 0, sizeof(*c)); c->mvx = (int16_t)mx; c->mvy = (int16_t)my; c->cu_log2 = 4;
     }
@@ -272,6 +310,7 @@ void ora_inter_picture(const ora_cfg *cfg, int qp, const ora_pic *src, const ora
         if ((x & (S - 1)) || (y & (S - 1))) continue;
         recon_inter_cu(cfg, qp, qpc, src, ref, rec, cells, lv, x, y, c.cu_log2, c.mvx, c.mvy);
     }
+    return cost_sum;
 }
 
 /* ------------------------------------------------------------------ B picture (a7 bi-prediction) - */

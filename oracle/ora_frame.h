@@ -28,6 +28,7 @@ typedef struct ora_cfg {
                                presets ultrafast..fast); 4: BO + all four EO classes, every row */
     int strong_intra;
     int satd;               /* sub-pel cost: SATD (had_c) instead of SAD */
+    int me_method;          /* integer search: 0 small diamond (a3 interMeDia), 1 hexagon + square refine (a4 interMeHex) */
 } ora_cfg;
 
 typedef struct ora_plane { uint8_t *base, *p; int stride, w, h; } ora_plane;
@@ -43,7 +44,8 @@ typedef struct ora_levels { int16_t *c[3]; } ora_levels;
 
 /* picture-level stages.  `cells` has (w/16)*(h/16) entries. */
 void ora_intra_picture(const ora_cfg *cfg, int qp, const ora_pic *src, ora_pic *rec, ks_cell *cells, ora_levels *lv);
-void ora_inter_picture(const ora_cfg *cfg, int qp, const ora_pic *src, const ora_pic *ref, const ks_cell *prev_cells,
+/* returns the sum of the per-cell winning search costs (the rate control's complexity measure) */
+uint64_t ora_inter_picture(const ora_cfg *cfg, int qp, const ora_pic *src, const ora_pic *ref, const ks_cell *prev_cells,
                        ora_pic *rec, ks_cell *cells, ora_levels *lv);
 void ora_b_picture(const ora_cfg *cfg, int qp, const ora_pic *src, const ora_pic *ref0, const ora_pic *ref1, const ks_cell *anchor_cells,
                    int d0, int da, ora_pic *rec, ks_cell *cells, ks_cell_b *cells_b, ora_levels *lv);

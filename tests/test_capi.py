@@ -59,5 +59,5 @@ def test_product_never_links_the_oracle():
 def test_cli_usage_and_flag_surface():
     r = subprocess.run([ks.CLI_PATH, "-v"], capture_output=True, text=True)
     assert r.returncode == 0 and "-preset" in r.stdout and "-wdt" in r.stdout
-    r = subprocess.run([ks.CLI_PATH, "-i", "/nonexistent.yuv", "-wdt", "64", "-hgt", "64", "-rc", "3"], capture_output=True, text=True)
+    r = subprocess.run([ks.CLI_PATH, "-i", "/nonexistent.yuv", "-wdt", "64", "-hgt", "64", "-rc", "1"], capture_output=True, text=True)   # ABR is not implemented: must be refused, not silently ignored
     assert r.returncode != 0 and "rc" in r.stderr

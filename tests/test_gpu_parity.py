@@ -23,11 +23,11 @@ DEC = os.path.join(ROOT, "oracle", "_ref", "appdecoder")
 
 
 class OraCfg(C.Structure):
-    _fields_ = [(n, C.c_int) for n in ("width", "height", "me_range", "me_iters", "subpel", "sign_hiding", "sao", "strong_intra", "satd")]
+    _fields_ = [(n, C.c_int) for n in ("width", "height", "me_range", "me_iters", "subpel", "sign_hiding", "sao", "strong_intra", "satd", "me_method")]
 
 
 class SeqCfg(C.Structure):
-    _fields_ = [(n, C.c_int) for n in "width height nframes qp iper fixqp me_range me_iters subpel sign_hiding sao max_merge_cand satd bframes".split()]
+    _fields_ = [(n, C.c_int) for n in "width height nframes qp iper fixqp me_range me_iters subpel sign_hiding sao max_merge_cand satd bframes me_method rc crf_x100".split()]
 
 
 def first_diff(a, b, what, shape=None):
@@ -40,10 +40,10 @@ def first_diff(a, b, what, shape=None):
         pytest.fail("%s: %d mismatches, first at %s: gpu=%s oracle=%s" % (what, d.size, where, a[loc], b[loc]))
 
 
-def gpu_cfg(subpel=2, sbh=1, sao=1, iters=16, satd=0):
+def gpu_cfg(subpel=2, sbh=1, sao=1, iters=16, satd=0, me=0):
     g = ks.KsGpuCfg()
     g.me_range, g.me_iters, g.subpel, g.sign_hiding, g.sao, g.strong_intra = 64, iters, subpel, sbh, sao, 1
-    g.n_src_slots, g.n_rec_slots, g.n_syn_slots, g.satd = 3, 2, 2, satd
+    g.n_src_slots, g.n_rec_slots, g.n_syn_slots, g.satd, g.me_method = 3, 2, 2, satd, me
     return g
 
 
@@ -146,14 +146,15 @@ def run_oracle_picture(cfg, slice_type, qp, boff, toff, src, ref, prev_cells):
     return o
 
 
-@pytest.mark.parametrize("w,h,qp,sbh,sao,subpel,satd", [(192, 112, 32, 1, 1, 2, 0), (200, 120, 27, 1, 1, 2, 0), (320, 240, 24, 0, 0, 1, 0), (256, 128, 37, 1, 4, 0, 0), (272, 144, 29, 1, 3, 2, 1), (336, 208, 30, 1, 4, 2, 0)])
-def test_picture_stages_match_oracle(w, h, qp, sbh, sao, subpel, satd):
+@pytest.mark.parametrize("w,h,qp,sbh,sao,subpel,satd,me", [(192, 112, 32, 1, 1, 2, 0, 0), (200, 120, 27, 1, 1, 2, 0, 0), (320, 240, 24, 0, 0, 1, 0, 0), (256, 128, 37, 1, 4, 0, 0, 0), (272, 144, 29, 1, 3, 2, 1, 0), (336, 208, 30, 1, 4, 2, 0, 0),
+                                                            (352, 208, 28, 1, 3, 2, 0, 1), (208, 128, 33, 1, 1, 2, 1, 1)])
+def test_picture_stages_match_oracle(w, h, qp, sbh, sao, subpel, satd, me):
     """I picture then 3 P pictures: every stage output of the device (ME field, pre-filter recon, dense levels, final
     recon after deblock+SAO, SAO parameters, CG bitmaps, packed level pool) equals the CPU model."""
     L = ks.lib()
     nfr = 4
     yuv = np.frombuffer(gen_yuv.make(w, h, nfr, seed=7), np.uint8)
-    g = gpu_cfg(subpel, sbh, sao, satd=satd)
+    g = gpu_cfg(subpel, sbh, sao, satd=satd, me=me)
     err = C.c_int(0)
     ctx = L.ks_gpu_open(0, w, h, C.byref(g), C.byref(err))
     assert ctx, "ks_gpu_open failed: %d" % err.value
@@ -162,7 +163,7 @@ def test_picture_stages_match_oracle(w, h, qp, sbh, sao, subpel, satd):
         L.ks_gpu_coded_size(ctx, C.byref(cw_), C.byref(ch_))
         W, H = cw_.value, ch_.value
         assert (W, H) == ((w + 15) & ~15, (h + 15) & ~15)
-        cfg = OraCfg(W, H, 64, 16, subpel, sbh, sao, 1, satd)
+        cfg = OraCfg(W, H, 64, 16, subpel, sbh, sao, 1, satd, me)
         fsz, dsz = W * H * 3 // 2, w * h * 3 // 2
         ncell, nctu = (W >> 4) * (H >> 4), ((W + 63) >> 6) * ((H + 63) >> 6)
         ref_fin = None; prev_cells = None
@@ -217,10 +218,10 @@ def test_picture_stages_match_oracle(w, h, qp, sbh, sao, subpel, satd):
 
 
 # ---------------------------------------------------------------------------------------- whole encoder
-def oracle_encode(yuv, w, h, n, qp, iper, subpel=2, sbh=1, sao=1, iters=16, satd=0, bframes=0):
+def oracle_encode(yuv, w, h, n, qp, iper, subpel=2, sbh=1, sao=1, iters=16, satd=0, bframes=0, me=0, rc=0, crf=24.0):
     O = oracle()
     O.ora_encode_sequence.restype = C.c_long
-    cfg = SeqCfg(w, h, n, qp, iper, 0, 64, iters, subpel, sbh, sao, 3, satd, bframes)
+    cfg = SeqCfg(w, h, n, qp, iper, 0, 64, iters, subpel, sbh, sao, 3, satd, bframes, me, rc, int(round(crf * 100)))
     bs = np.zeros(w * h * 3 * n + 100000, np.uint8); rec = np.zeros(w * h * 3 // 2 * n, np.uint8)
     nb = O.ora_encode_sequence(C.byref(cfg), ptr(yuv), ptr(bs), C.c_size_t(bs.size), ptr(rec))
     assert nb > 0
@@ -268,6 +269,21 @@ def test_encoder_bframes_equal_oracle_and_decode(w, h, n, qp, preset, bf):
     dec = decode_with_reference(bs, rec.size)
     first_diff(dec, rec, "reference decoder output vs our recon")
     assert st.frames == n
+
+
+@pytest.mark.parametrize("w,h,n,preset,bf,me,rc,crf", [(416, 240, 6, "veryfast", 0, 1, 0, 0.0), (320, 176, 8, "veryfast", 0, 0, 3, 26.0), (352, 288, 9, "slow", 2, 1, 3, 24.0), (1280, 720, 6, "slow", 0, 1, 3, 24.0)])
+def test_encoder_hex_and_crf_equal_oracle_and_decode(w, h, n, preset, bf, me, rc, crf):
+    """-me 1 (hexagon search) and -rc 3 -crf (host rate control fed by the device's search cost): stream bytes == CPU model,
+    recon == model, reference decoder output == recon.  BASELINE configs[3] uses -preset slow -rc 3 -crf 24."""
+    yuv = np.frombuffer(gen_yuv.make(w, h, n, seed=9), np.uint8)
+    cfg = ks.default_config(w, h, preset=preset, qp=30, iper=n, psnr=1, bframes=bf, me=me, rc=rc, crf=crf)
+    with ks.Encoder(cfg) as e:
+        bs, rec, st = e.encode_gop(yuv, want_recon=True)
+    obs, orec = oracle_encode(yuv, w, h, n, 30, n, subpel=cfg.subpel, sbh=cfg.sign_hiding, sao=cfg.sao, iters=cfg.me_iters, satd=cfg.satd, bframes=bf, me=me, rc=rc, crf=crf)
+    first_diff(rec, orec, "recon vs oracle")
+    assert bytes(bs) == bytes(obs), "bitstream differs from the CPU model (%d vs %d bytes)" % (bs.size, obs.size)
+    dec = decode_with_reference(bs, rec.size)
+    first_diff(dec, rec, "reference decoder output vs our recon")
 
 
 def test_natural_clip_closed_loop():

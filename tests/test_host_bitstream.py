@@ -20,13 +20,13 @@ DEC = os.path.join(ROOT, "oracle", "_ref", "appdecoder")
 
 
 class SeqCfg(C.Structure):
-    _fields_ = [(n, C.c_int) for n in "width height nframes qp iper fixqp me_range me_iters subpel sign_hiding sao max_merge_cand satd bframes".split()]
+    _fields_ = [(n, C.c_int) for n in "width height nframes qp iper fixqp me_range me_iters subpel sign_hiding sao max_merge_cand satd bframes me_method rc crf_x100".split()]
 
 
-def model_encode(yuv, w, h, n, qp, iper, sbh=1, sao=1, subpel=2, bframes=0):
+def model_encode(yuv, w, h, n, qp, iper, sbh=1, sao=1, subpel=2, bframes=0, me=0, rc=0, crf=24.0):
     O = oracle()
     O.ora_encode_sequence.restype = C.c_long
-    cfg = SeqCfg(w, h, n, qp, iper, 0, 64, 16, subpel, sbh, sao, 3, 0, bframes)
+    cfg = SeqCfg(w, h, n, qp, iper, 0, 64, 16, subpel, sbh, sao, 3, 0, bframes, me, rc, int(round(crf * 100)))
     bs = np.zeros(w * h * 3 * n + 100000, np.uint8); rec = np.zeros(w * h * 3 // 2 * n, np.uint8)
     nb = O.ora_encode_sequence(C.byref(cfg), ptr(yuv), ptr(bs), C.c_size_t(bs.size), ptr(rec))
     assert nb > 0
@@ -35,7 +35,8 @@ def model_encode(yuv, w, h, n, qp, iper, sbh=1, sao=1, subpel=2, bframes=0):
 
 CASES = [("syn_192x112", 192, 112, 5, 32, 16, 1, 3, 2), ("syn_256x144_sao4", 256, 144, 4, 30, 16, 1, 4, 2), ("syn_200x120_pad", 200, 120, 4, 27, 2, 1, 1, 2),
          ("syn_320x240_nosbh", 320, 240, 4, 24, 8, 0, 0, 1), ("syn_416x240_intra", 416, 240, 2, 35, 1, 1, 1, 2),
-         ("syn_192x112_b1", 192, 112, 6, 32, 16, 1, 3, 2, 1), ("syn_320x176_b3", 320, 176, 9, 28, 16, 1, 1, 2, 3), ("syn_200x120_b2_gops", 200, 120, 9, 30, 4, 1, 4, 2, 2)]
+         ("syn_192x112_b1", 192, 112, 6, 32, 16, 1, 3, 2, 1), ("syn_320x176_b3", 320, 176, 9, 28, 16, 1, 1, 2, 3), ("syn_200x120_b2_gops", 200, 120, 9, 30, 4, 1, 4, 2, 2),
+         ("syn_256x144_hex", 256, 144, 5, 30, 16, 1, 3, 2, 0, 1), ("syn_320x176_crf26", 320, 176, 8, 0, 4, 1, 3, 2, 0, 0, 3, 26.0), ("syn_192x112_crf22_b2_hex", 192, 112, 7, 0, 16, 1, 1, 2, 2, 1, 3, 22.0)]
 
 
 def _yuv(name, w, h, n):
@@ -45,10 +46,10 @@ def _yuv(name, w, h, n):
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
 def test_closed_loop_with_reference_decoder(case):
     name, w, h, n, qp, iper, sbh, sao, subpel = case[:9]
-    bframes = case[9] if len(case) > 9 else 0
+    extra = case[9:]
     if not os.path.exists(DEC):
         pytest.skip("oracle/_ref/appdecoder not staged (needs /root/reference once: make -C oracle)")
-    bs, rec = model_encode(_yuv(name, w, h, n), w, h, n, qp, iper, sbh, sao, subpel, bframes)
+    bs, rec = model_encode(_yuv(name, w, h, n), w, h, n, qp, iper, sbh, sao, subpel, *extra)
     with tempfile.TemporaryDirectory() as d:
         p, o = os.path.join(d, "t.265"), os.path.join(d, "t.yuv")
         open(p, "wb").write(bs.tobytes())
@@ -79,7 +80,7 @@ def test_stream_digests_are_frozen():
     got = {}
     for case in CASES:
         name, w, h, n, qp, iper, sbh, sao, subpel = case[:9]
-        bs, rec = model_encode(_yuv(name, w, h, n), w, h, n, qp, iper, sbh, sao, subpel, case[9] if len(case) > 9 else 0)
+        bs, rec = model_encode(_yuv(name, w, h, n), w, h, n, qp, iper, sbh, sao, subpel, *case[9:])
         got[name] = {"bs_md5": hashlib.md5(bs.tobytes()).hexdigest(), "rec_md5": hashlib.md5(rec.tobytes()).hexdigest(), "bytes": int(bs.size)}
     if os.environ.get("KS_WRITE_GOLDEN") == "1":
         json.dump(got, open(path, "w"), indent=1, sort_keys=True)

@@ -22,7 +22,7 @@ rank, world = dist.get_rank(), dist.get_world_size()
 w, h, n, iper = 96, 64, 10, 3
 yuv = np.frombuffer(gen_yuv.make(w, h, n, seed=9), np.uint8)
 class SeqCfg(C.Structure):
-    _fields_ = [(k, C.c_int) for k in "width height nframes qp iper fixqp me_range me_iters subpel sign_hiding sao max_merge_cand satd bframes".split()]
+    _fields_ = [(k, C.c_int) for k in "width height nframes qp iper fixqp me_range me_iters subpel sign_hiding sao max_merge_cand satd bframes me_method rc crf_x100".split()]
 O = oracle(); O.ora_encode_sequence.restype = C.c_long
 def enc(first, cnt):
     cfg = SeqCfg(w, h, cnt, 30, iper, 0, 64, 16, 2, 1, 1, 3)
