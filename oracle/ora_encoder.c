@@ -6,6 +6,7 @@
 #include "../ks265codec_b200/csrc/host/ks_bitstream.h"
 #include <stdlib.h>
 #include <string.h>
+#include <stdio.h>
 #include "../ks265codec_b200/csrc/host/ks_ratecontrol.h"
 
 typedef struct ora_seq_cfg {
@@ -106,6 +107,7 @@ long ora_encode_sequence(const ora_seq_cfg *sc, const uint8_t *yuv, uint8_t *bs,
             if ((n = ks_write_slice(&sp, &sl, &syn, scratch, bs + pos, bs_cap - pos)) < 0) return -1;
             pos += n;
             if (recon_out) store_cropped(out, sc->width, sc->height, recon_out + fsz * (size_t)(g0 + f));
+            if (getenv("ORA_RC_DEBUG")) fprintf(stderr, "poc %d type %d qp %d me_cost/cell %.1f bytes %ld\n", f, t, qp, (double)me_cost / (cw * ch), n);
             ks_rc_update(&rc, t, me_cost);
         }
     }
