@@ -147,8 +147,8 @@ static long encode_gop_impl(ks265_encoder *enc, const uint8_t *frames, const voi
     if (!cp) return -12;
     plan_pictures(enc, nframes, cp, &cnt);
     ks_rc rc;                          /* one rate-control state per closed-GOP shard: shards stay independent */
-    if (ks_rc_init(&rc, enc->cfg.rc, enc->cfg.qp, enc->cfg.fixqp, enc->cfg.crf, (enc->W >> 4) * (enc->H >> 4))) { free(cp); return -22; }
-    cp[0].pp.qp = ks_rc_picture_qp(&rc, cp[0].type);
+    if (ks_rc_init(&rc, enc->cfg.rc, enc->cfg.qp, enc->cfg.fixqp, enc->cfg.crf, (enc->W >> 4) * (enc->H >> 4), enc->cfg.bframes)) { free(cp); return -22; }
+    cp[0].pp.qp = ks_rc_picture_qp(&rc, cp[0].type, cp[0].disp);
     if (bs) {
         if ((n = ks_write_vps(sp, bs + pos, cap - pos)) < 0) { free(cp); return -28; } pos += n;
         if ((n = ks_write_sps(sp, bs + pos, cap - pos)) < 0) { free(cp); return -28; } pos += n;
@@ -164,7 +164,7 @@ static long encode_gop_impl(ks265_encoder *enc, const uint8_t *frames, const voi
         if ((r = ks_gpu_encode_picture_finish(enc->gpu, cp[i].pp.syn_slot, &out))) FAIL(r);
         ks_rc_update(&rc, cp[i].type, out.me_cost);
         if (i + 1 < cnt) {
-            cp[i + 1].pp.qp = ks_rc_picture_qp(&rc, cp[i + 1].type);
+            cp[i + 1].pp.qp = ks_rc_picture_qp(&rc, cp[i + 1].type, cp[i + 1].disp);
             if ((r = ks_gpu_encode_picture_submit(enc->gpu, &cp[i + 1].pp))) FAIL(r);
         }
         cg += out.n_cg;

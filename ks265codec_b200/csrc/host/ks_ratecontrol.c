@@ -9,11 +9,11 @@
 #define KS_RC_IP_OFFSET    3        /* 6*log2(1.4): I pictures below the P level */
 #define KS_RC_PB_OFFSET    2        /* 6*log2(1.3): non-reference B pictures above it */
 
-int ks_rc_init(ks_rc *rc, int mode, int qp, int fixqp, double crf, int cells)
+int ks_rc_init(ks_rc *rc, int mode, int qp, int fixqp, double crf, int cells, int bframes)
 {
     memset(rc, 0, sizeof(*rc));
     if (mode != 0 && mode != 3) return -1;
-    rc->mode = mode; rc->qp = qp; rc->fixqp = fixqp; rc->crf = crf;
+    rc->mode = mode; rc->qp = qp; rc->fixqp = fixqp; rc->crf = crf; rc->bframes = bframes;
     rc->base_cplx = KS_RC_BASE_COST * (double)cells;
     rc->qp_min = 0; rc->qp_max = 51;
     return 0;
@@ -21,11 +21,18 @@ int ks_rc_init(ks_rc *rc, int mode, int qp, int fixqp, double crf, int cells)
 
 static int clip_qp(const ks_rc *rc, int q) { return q < rc->qp_min ? rc->qp_min : (q > rc->qp_max ? rc->qp_max : q); }
 
-int ks_rc_picture_qp(const ks_rc *rc, int slice_type)
+/* P-only streams: the reference's 4-picture QP cascade (every 4th P is the better-quality anchor of the next three) */
+static int p_cascade(const ks_rc *rc, int poc)
+{
+    static const int off[4] = {1, 3, 2, 3};
+    return rc->bframes ? 1 : off[poc & 3];
+}
+
+int ks_rc_picture_qp(const ks_rc *rc, int slice_type, int poc)
 {
     if (rc->mode == 0) {
         int q = rc->qp;
-        if (!rc->fixqp) q += slice_type == KS_SLICE_I ? 0 : (slice_type == KS_SLICE_P ? 1 : 3);
+        if (!rc->fixqp) q += slice_type == KS_SLICE_I ? 0 : (slice_type == KS_SLICE_P ? p_cascade(rc, poc) : 3);
         return clip_qp(rc, q);
     }
     double q = rc->crf;
@@ -36,6 +43,7 @@ int ks_rc_picture_qp(const ks_rc *rc, int slice_type)
     }
     if (slice_type == KS_SLICE_I) q -= KS_RC_IP_OFFSET;
     else if (slice_type == KS_SLICE_B) q += KS_RC_PB_OFFSET;
+    else q += p_cascade(rc, poc) - 1;
     return clip_qp(rc, (int)floor(q + 0.5));
 }
 

@@ -70,13 +70,13 @@ long ora_encode_sequence(const ora_seq_cfg *sc, const uint8_t *yuv, uint8_t *bs,
         int gn = sc->nframes - g0 < sc->iper ? sc->nframes - g0 : sc->iper;
         int cnt = ora_gop_schedule(gn, sc->bframes, order, type, l0, l1);
         ks_rc rc;                 /* one rate-control state per closed-GOP shard, like the product */
-        if (ks_rc_init(&rc, sc->rc, sc->qp, sc->fixqp, sc->crf_x100 / 100.0, cw * ch)) return -3;
+        if (ks_rc_init(&rc, sc->rc, sc->qp, sc->fixqp, sc->crf_x100 / 100.0, cw * ch, sc->bframes)) return -3;
         /* anchors alternate between fin[0]/fin[1] (+cells[0]/[1]); B pictures reconstruct into fin[2] (+cells[2]) */
         int slot_of_prev = -1, slot_of_next = -1, anchor_idx = 0;
         for (int i = 0; i < cnt; i++) {
             int f = order[i], t = type[i];
             ora_pic_load(&src, yuv + fsz * (size_t)(g0 + f), sc->width, sc->height);
-            int qp = ks_rc_picture_qp(&rc, t);
+            int qp = ks_rc_picture_qp(&rc, t, f);
             uint64_t me_cost = 0;
             memset(lv.c[0], 0, (size_t)W * H * 2); memset(lv.c[1], 0, (size_t)W * H / 2); memset(lv.c[2], 0, (size_t)W * H / 2);
             int slot; ks_cell *cur; ora_pic *out;
