@@ -6,6 +6,7 @@
  * g_invQuantScales E@0x4cfb20, uiTCTable E@0x4cc660, uiBetaTable E@0x4cc6a0, g_ucChromaScale E@0x4cfb40).
  */
 #pragma once
+#include <cstring>
 #include "ks_launch.h"
 #define KS_WARP 32
 
@@ -26,11 +27,23 @@ __constant__ uint8_t  c_chroma_qp[58];
 __constant__ int      c_quant_scales[6];
 __constant__ int      c_inv_quant_scales[6];
 __constant__ uint16_t c_scan_tb[4][1024];         /* per log2 (2..5): scan position -> (y<<8)|x */
+/* the residual kernel's shared-memory tables as one 16-byte-aligned global image (scan 8x8 | 16x16 | 32x32 | t0): every lane of a
+ * CTA reads a different entry, which the constant cache would serialise 32 ways; from global memory it is 2 coalesced loads */
+#define KS_RECON_TAB_U4 ((64 + 256 + 1024) * 2 / 16 + 256 * 4 / 16)
+__device__ uint4 g_recon_tab[KS_RECON_TAB_U4];
 __constant__ int8_t   c_intra_angle[35];
 __constant__ int16_t  c_intra_inv_angle[35];
 
 __device__ __forceinline__ int ks_clip3(int lo, int hi, int v) { return min(max(v, lo), hi); }
 __device__ __forceinline__ int ks_clip8(int v) { return min(max(v, 0), 255); }
+/* four s32 -> four u8 with saturation, v0 in the low byte (cvt.pack: d = c << 16 | sat(a) << 8 | sat(b)) */
+__device__ __forceinline__ uint32_t ks_pack_sat4(int v0, int v1, int v2, int v3)
+{
+    uint32_t t, d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(v3), "r"(v2), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(v1), "r"(v0), "r"(t));
+    return d;
+}
 __device__ __forceinline__ int ks_mvbits(int d) { int a = abs(d); return a ? 2 * (32 - __clz(a)) + 1 : 1; }
 
 /* u8 x s8 dot product with accumulate (dp4a.u32.s32): a = 4 unsigned bytes, b = 4 signed bytes */
@@ -40,12 +53,8 @@ __device__ __forceinline__ int ks_dp4a_us(unsigned a, int b, int c)
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
-__device__ __forceinline__ unsigned ks_warp_sum(unsigned v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
+/* warp-wide integer sum, result in every lane: one REDUX instead of five shuffle+add steps (callers pack two 16-bit sums per word) */
+__device__ __forceinline__ unsigned ks_warp_sum(unsigned v) { return __reduce_add_sync(0xffffffffu, v); }
 __device__ __forceinline__ int ks_zidx(int x, int y)
 {
     int cx = (x >> 4) & 3, cy = (y >> 4) & 3;
@@ -116,6 +125,14 @@ static void ks_upload_tables_impl()
                 scan[l - 2][c * 16 + k] = (uint16_t)(((((dcg[c] >> 3) << 2) + (d4[k] >> 3)) << 8) | (((dcg[c] & 7) << 2) + (d4[k] & 7)));
     }
     cudaMemcpyToSymbol(c_scan_tb, scan, sizeof(scan));
+    {
+        static uint4 img[KS_RECON_TAB_U4];
+        uint16_t *sp = reinterpret_cast<uint16_t *>(img);
+        memcpy(sp, scan[1], 64 * 2); memcpy(sp + 64, scan[2], 256 * 2); memcpy(sp + 320, scan[3], 1024 * 2);
+        int *tp = reinterpret_cast<int *>(sp + 1344);
+        for (int i = 0; i < 256; i++) tp[i] = dct[2 * (i >> 4) + 1][i & 15];
+        cudaMemcpyToSymbol(g_recon_tab, img, sizeof(img));
+    }
     static const int8_t ang[35] = {0,0,32,26,21,17,13,9,5,2,0,-2,-5,-9,-13,-17,-21,-26,-32,-26,-21,-17,-13,-9,-5,-2,0,2,5,9,13,17,21,26,32};
     static const int16_t inv[35] = {0,0,0,0,0,0,0,0,0,0,0,-4096,-1638,-910,-630,-482,-390,-315,-256,-315,-390,-482,-630,-910,-1638,-4096,0,0,0,0,0,0,0,0,0};
     cudaMemcpyToSymbol(c_intra_angle, ang, sizeof(ang));

@@ -193,6 +193,7 @@ __device__ __forceinline__ KsSaoNb ks_sao_load_nb(const uint8_t *t, int pitch)
     return n;
 }
 /* edge categories (0 none, 1..4) of sample j of the run for the four EO classes; out-of-picture neighbours -> 0 */
+template <bool DIAG>
 __device__ __forceinline__ void ks_sao_cats(const KsSaoNb &n, int j, bool lft, bool rgt, bool top, bool bot, int cat[4])
 {
     const int lut = 0x43021;                       /* cat_of[0..4] = {1,2,0,3,4} as nibbles */
@@ -204,8 +205,23 @@ __device__ __forceinline__ void ks_sao_cats(const KsSaoNb &n, int j, bool lft, b
     bool h = !(lft || rgt), v = !(top || bot), hv = h && v;
     cat[0] = h ? (lut >> (4 * (2 + ks_sgn(c - l) + ks_sgn(c - r)))) & 15 : 0;
     cat[1] = v ? (lut >> (4 * (2 + ks_sgn(c - u) + ks_sgn(c - d)))) & 15 : 0;
-    cat[2] = hv ? (lut >> (4 * (2 + ks_sgn(c - ul) + ks_sgn(c - dr)))) & 15 : 0;
-    cat[3] = hv ? (lut >> (4 * (2 + ks_sgn(c - ur) + ks_sgn(c - dl)))) & 15 : 0;
+    if (DIAG) {        /* the 135/45 degree classes are only gathered at -sao 4 (reference: SaoApplyOffsetEo2/3 only then) */
+        cat[2] = hv ? (lut >> (4 * (2 + ks_sgn(c - ul) + ks_sgn(c - dr)))) & 15 : 0;
+        cat[3] = hv ? (lut >> (4 * (2 + ks_sgn(c - ur) + ks_sgn(c - dl)))) & 15 : 0;
+    } else cat[2] = cat[3] = 0;
+}
+
+/* edge category of sample j for EO class k only (the apply pass needs just the chosen class; k is uniform per component) */
+__device__ __forceinline__ int ks_sao_cat_of(const KsSaoNb &n, int j, int k, bool lft, bool rgt, bool top, bool bot)
+{
+    const int lut = 0x43021;
+    const int c = (n.ce >> (8 * j)) & 255;
+    int a, b; bool ok;
+    if (k == 0) { a = j ? (n.ce >> (8 * j - 8)) & 255 : n.cl; b = j < 3 ? (n.ce >> (8 * j + 8)) & 255 : n.cr; ok = !(lft || rgt); }
+    else if (k == 1) { a = (n.up >> (8 * j)) & 255; b = (n.dn >> (8 * j)) & 255; ok = !(top || bot); }
+    else if (k == 2) { a = j ? (n.up >> (8 * j - 8)) & 255 : n.ul; b = j < 3 ? (n.dn >> (8 * j + 8)) & 255 : n.dr; ok = !(lft || rgt || top || bot); }
+    else { a = j < 3 ? (n.up >> (8 * j + 8)) & 255 : n.ur; b = j ? (n.dn >> (8 * j - 8)) & 255 : n.dl; ok = !(lft || rgt || top || bot); }
+    return ok ? (lut >> (4 * (2 + ks_sgn(c - a) + ks_sgn(c - b)))) & 15 : 0;
 }
 
 __global__ void __launch_bounds__(KS_SAO_WARPS * KS_WARP)
@@ -261,9 +277,14 @@ ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_s
                     if (band != cur_band) { if (cur_band >= 0) atomicAdd(&h[20 + cur_band], band_acc); cur_band = band; band_acc = 0; }
                     band_acc += v;
                     int cat[4];
-                    ks_sao_cats(n, j, x0 + x + j == 0, x0 + x + j == PW - 1, top, bot, cat);
+                    if (ncls == 4) {
+                        ks_sao_cats<true>(n, j, x0 + x + j == 0, x0 + x + j == PW - 1, top, bot, cat);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) if (k < ncls) sm->ph[k * 5 + cat[k]][tid] += v;      /* bin cat 0 collects the rest and is ignored */
+                        for (int k = 0; k < 4; k++) sm->ph[k * 5 + cat[k]][tid] += v;      /* bin cat 0 collects the rest and is ignored */
+                    } else {
+                        ks_sao_cats<false>(n, j, x0 + x + j == 0, x0 + x + j == PW - 1, top, bot, cat);
+                        sm->ph[cat[0]][tid] += v; sm->ph[5 + cat[1]][tid] += v;
+                    }
                 }
                 atomicAdd(&h[20 + cur_band], band_acc);
             }
@@ -273,8 +294,7 @@ ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_s
                 int s_ = 0, n_ = 0;
 #pragma unroll
                 for (int i = 0; i < KS_SAO_WARPS; i++) { int v = sm->ph[b][lane + 32 * i]; int c = v & 4095; n_ += c; s_ += (v - c) >> 12; }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) { s_ += __shfl_xor_sync(0xffffffffu, s_, o); n_ += __shfl_xor_sync(0xffffffffu, n_, o); }
+                s_ = __reduce_add_sync(0xffffffffu, s_); n_ = __reduce_add_sync(0xffffffffu, n_);
                 if (lane == 0) { sm->sum[ci][b] = s_; sm->cnt[ci][b] = n_; }
             }
             __syncthreads();
@@ -348,9 +368,7 @@ ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_s
                 int c = (n.ce >> (8 * j)) & 255, v = c;
                 if (p.type == 1) { int b = ((c >> 3) - k) & 31; if (b < 4) v = c + (b == 0 ? o0 : b == 1 ? o1 : b == 2 ? o2 : o3); }
                 else if (p.type == 2) {
-                    int cat[4];
-                    ks_sao_cats(n, j, x0 + x + j == 0, x0 + x + j == PW - 1, top, bot, cat);
-                    int ct = k == 0 ? cat[0] : k == 1 ? cat[1] : k == 2 ? cat[2] : cat[3];
+                    const int ct = ks_sao_cat_of(n, j, k, x0 + x + j == 0, x0 + x + j == PW - 1, top, bot);
                     if (ct) v = c + (ct == 1 ? o0 : ct == 2 ? o1 : ct == 3 ? o2 : o3);
                 }
                 v = ks_clip8(v);

@@ -192,22 +192,24 @@ __device__ __forceinline__ void ks_interp16(KsWarpScratch *sc, int bxw, int byw,
         ks_row16(sc->win, byw + row, bxw + 8 * half - 3, n);
         ks_htaps8(n, c_luma_taps_packed[fx][0], c_luma_taps_packed[fx][1], v);
 #pragma unroll
-        for (int j = 0; j < 8; j++) v[j] = ks_clip8((v[j] + 32) >> 6);
+        for (int j = 0; j < 8; j++) v[j] = (v[j] + 32) >> 6;
     } else if (fx == 0) {
-#pragma unroll
-        for (int j = 0; j < 8; j++) v[j] = 0;
+        /* vertical taps straight from the samples, two 16-bit lanes per multiply: partial sums stay inside [-4080, 20400] */
+        int e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+        const int wx = bxw + 8 * half;
+        const unsigned sh = (wx & 3) * 8;
 #pragma unroll 2
         for (int t = 0; t < 8; t++) {
-            uint32_t a, b; int c = c_luma_taps[fy][t];
-            int wx = bxw + 8 * half;
+            const int c = c_luma_taps[fy][t];
             const uint32_t *r = sc->win[byw + row - 3 + t] + (wx >> 2);
-            unsigned sh = (wx & 3) * 8;
-            a = __funnelshift_r(r[0], r[1], sh); b = __funnelshift_r(r[1], r[2], sh);
-#pragma unroll
-            for (int j = 0; j < 4; j++) { v[j] += c * (int)((a >> (8 * j)) & 255); v[4 + j] += c * (int)((b >> (8 * j)) & 255); }
+            const uint32_t a = __funnelshift_r(r[0], r[1], sh), b = __funnelshift_r(r[1], r[2], sh);
+            e0 += c * (int)__byte_perm(a, 0, 0x4240); e1 += c * (int)__byte_perm(a, 0, 0x4341);
+            e2 += c * (int)__byte_perm(b, 0, 0x4240); e3 += c * (int)__byte_perm(b, 0, 0x4341);
         }
+        v[0] = (int)(short)(e0 & 0xffff); v[2] = (e0 + 0x8000) >> 16; v[1] = (int)(short)(e1 & 0xffff); v[3] = (e1 + 0x8000) >> 16;
+        v[4] = (int)(short)(e2 & 0xffff); v[6] = (e2 + 0x8000) >> 16; v[5] = (int)(short)(e3 & 0xffff); v[7] = (e3 + 0x8000) >> 16;
 #pragma unroll
-        for (int j = 0; j < 8; j++) v[j] = ks_clip8((v[j] + 32) >> 6);
+        for (int j = 0; j < 8; j++) v[j] = (v[j] + 32) >> 6;
     } else {
         const int tlo = c_luma_taps_packed[fx][0], thi = c_luma_taps_packed[fx][1];
 #pragma unroll
@@ -234,11 +236,11 @@ __device__ __forceinline__ void ks_interp16(KsWarpScratch *sc, int bxw, int byw,
             for (int j = 0; j < 4; j++) { v[2 * j] += c * (int)(short)(w[j] & 0xffffu); v[2 * j + 1] += c * ((int)w[j] >> 16); }
         }
 #pragma unroll
-        for (int j = 0; j < 8; j++) v[j] = ks_clip8((v[j] + 2048) >> 12);
+        for (int j = 0; j < 8; j++) v[j] = (v[j] + 2048) >> 12;
         __syncwarp();
     }
-    o0 = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
-    o1 = (uint32_t)v[4] | ((uint32_t)v[5] << 8) | ((uint32_t)v[6] << 16) | ((uint32_t)v[7] << 24);
+    o0 = ks_pack_sat4(v[0], v[1], v[2], v[3]);
+    o1 = ks_pack_sat4(v[4], v[5], v[6], v[7]);
 }
 
 /* ---- shared intermediates for the sub-pel search (reference: subMeQpel_8Sad_* pick a variant "so H/V intermediate
@@ -287,7 +289,7 @@ __device__ __forceinline__ void ks_plane_pred(const KsPlane pl, int roff, int fy
         const uint4 qa = *reinterpret_cast<const uint4 *>(&pl[R >> 1][8 * half]), qb = *reinterpret_cast<const uint4 *>(&pl[R >> 1][8 * half + 4]);
         const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
-        for (int j = 0; j < 8; j++) { int t = (R & 1) ? ((int)w[j] >> 16) : (int)(short)(w[j] & 0xffffu); v[j] = ks_clip8((t + 32) >> 6); }
+        for (int j = 0; j < 8; j++) { int t = (R & 1) ? ((int)w[j] >> 16) : (int)(short)(w[j] & 0xffffu); v[j] = (t + 32) >> 6; }
     } else {
         const int R0 = roff + row, par = R0 & 1;
         const int k0 = c_vtaps_pk[fy][par][0], k1 = c_vtaps_pk[fy][par][1], k2 = c_vtaps_pk[fy][par][2];
@@ -303,10 +305,10 @@ __device__ __forceinline__ void ks_plane_pred(const KsPlane pl, int roff, int fy
             for (int j = 0; j < 8; j++) v[j] = (i & 1) ? ks_dp2a_hi((int)w[j], kk, v[j]) : ks_dp2a_lo((int)w[j], kk, v[j]);
         }
 #pragma unroll
-        for (int j = 0; j < 8; j++) v[j] = ks_clip8(v[j] >> 12);
+        for (int j = 0; j < 8; j++) v[j] >>= 12;
     }
-    o0 = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
-    o1 = (uint32_t)v[4] | ((uint32_t)v[5] << 8) | ((uint32_t)v[6] << 16) | ((uint32_t)v[7] << 24);
+    o0 = ks_pack_sat4(v[0], v[1], v[2], v[3]);      /* clip to 8 bits and pack in one step */
+    o1 = ks_pack_sat4(v[4], v[5], v[6], v[7]);
 }
 
 /* window origin that centres integer offset (cx, cy) of the cell at (x0, y0) */
@@ -369,6 +371,9 @@ __device__ __forceinline__ void ks_mc_chroma8(uint8_t *cwin, int16_t *tmp, const
 }
 
 #define KS_ME_WARPS 8
+/* METHOD (0 diamond / 1 hexagon) and SATD are compile-time: each instantiation carries only the code it runs, which keeps the
+ * hot configuration (diamond + SAD, veryfast) inside the instruction cache */
+template <int METHOD, bool SATD>
 __global__ void __launch_bounds__(KS_ME_WARPS * KS_WARP, 4)
 ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref, const ks_cell *__restrict__ prev_cells,
              ks_cell *__restrict__ cells, KsPlanes pred, int *__restrict__ costs, unsigned long long *__restrict__ cost_sum)
@@ -408,7 +413,7 @@ ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref, con
             if (c < bc) { bc = c; bx = cx; by = cy; }
         }
     }
-    if (pp.me_method == 0) {
+    if (METHOD == 0) {
     /* ---- small diamond (reference: interMeDia E@0x4849d0, x264 DIA with sad4 order up,down,left,right) ---- */
     for (int it = 0; it < pp.me_iters; it++) {
         int bxw = x0 + bx - wx0, byw = y0 + by - wy0;
@@ -489,7 +494,7 @@ ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref, con
             bxw = x0 + bx - wx0; byw = y0 + by - wy0;
         }
         const int sqx[8] = {-1, 0, 1, -1, 1, -1, 0, 1}, sqy[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
-        const bool satd = pp.satd != 0;
+        const bool satd = SATD;
 #define KS_SUBCOST(o0, o1) (satd ? ks_satd16(o0, o1, s.x, s.y, lane) : ks_warp_sum(__vsadu4(o0, s.x) + __vsadu4(o1, s.y)))
         if (satd) {     /* the metric changes for the sub-pel stages: re-cost the integer winner with SATD (x264 does the same) */
             uint32_t c0, c1;
@@ -502,13 +507,16 @@ ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref, con
             ks_make_plane(P0, sc->win, bxw - 1, wyb, 2, lane);
             ks_make_plane(P2, sc->win, bxw, wyb, 2, lane);
             int bk = -1, lc = bc;
+            /* the 8 candidates share 3 x and 3 y vector components: their bit costs are computed once */
+            const int hbx0 = ks_mvbits(mx - 2 - tpx), hbx1 = ks_mvbits(mx - tpx), hbx2 = ks_mvbits(mx + 2 - tpx);
+            const int hby0 = ks_mvbits(my - 2 - tpy), hby1 = ks_mvbits(my - tpy), hby2 = ks_mvbits(my + 2 - tpy);
 #pragma unroll 1
             for (int k = 0; k < 8; k++) {
-                const int dx = sqx[k], dy = sqy[k], qx = mx + 2 * dx, qy = my + 2 * dy;
+                const int dx = sqx[k], dy = sqy[k];
                 uint32_t o0, o1;
                 if (dx == 0) ks_interp16(sc, bxw, byw + (dy < 0 ? -1 : 0), 0, 2, lane, o0, o1);      /* vertical-only, straight from the samples */
                 else ks_plane_pred(dx < 0 ? P0 : P2, dy < 0 ? 0 : 1, dy ? 2 : 0, lane, o0, o1);
-                int c = (int)KS_SUBCOST(o0, o1) + MVCOST(qx, qy);
+                int c = (int)KS_SUBCOST(o0, o1) + ((lam * ((dx < 0 ? hbx0 : (dx == 0 ? hbx1 : hbx2)) + (dy < 0 ? hby0 : (dy == 0 ? hby1 : hby2)))) >> 4);
                 if (c < lc) { lc = c; bk = k; best0 = o0; best1 = o1; }
             }
             if (bk >= 0) { mx += sqx[bk] * 2; my += sqy[bk] * 2; bc = lc; }
@@ -519,12 +527,14 @@ ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref, con
             ks_make_plane(P1, sc->win, x0 + (mx >> 2) - wx0, wyb, mx & 3, lane);
             ks_make_plane(P2, sc->win, x0 + ((mx + 1) >> 2) - wx0, wyb, (mx + 1) & 3, lane);
             int bk = -1, lc = bc;
+            const int qbx0 = ks_mvbits(mx - 1 - tpx), qbx1 = ks_mvbits(mx - tpx), qbx2 = ks_mvbits(mx + 1 - tpx);
+            const int qby0 = ks_mvbits(my - 1 - tpy), qby1 = ks_mvbits(my - tpy), qby2 = ks_mvbits(my + 1 - tpy);
 #pragma unroll 1
             for (int k = 0; k < 8; k++) {
-                const int dx = sqx[k], dy = sqy[k], qx = mx + dx, qy = my + dy;
+                const int dx = sqx[k], dy = sqy[k], qy = my + dy;
                 uint32_t o0, o1;
                 ks_plane_pred(dx < 0 ? P0 : (dx == 0 ? P1 : P2), (qy >> 2) - iym, qy & 3, lane, o0, o1);
-                int c = (int)KS_SUBCOST(o0, o1) + MVCOST(qx, qy);
+                int c = (int)KS_SUBCOST(o0, o1) + ((lam * ((dx < 0 ? qbx0 : (dx == 0 ? qbx1 : qbx2)) + (dy < 0 ? qby0 : (dy == 0 ? qby1 : qby2)))) >> 4);
                 if (c < lc) { lc = c; bk = k; best0 = o0; best1 = o1; }
             }
             if (bk >= 0) { mx += sqx[bk]; my += sqy[bk]; bc = lc; }
@@ -553,8 +563,15 @@ ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref, con
 
 void ks_launch_me(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref, const ks_cell *prev_cells, ks_cell *cells, KsPlanes pred, int *costs, unsigned long long *cost_sum, cudaStream_t st)
 {
-    int ncell = pp.cw * pp.ch;
-    ks_me_kernel<<<(ncell + KS_ME_WARPS - 1) / KS_ME_WARPS, KS_ME_WARPS * KS_WARP, 0, st>>>(pp, srcY, ref, prev_cells, cells, pred, costs, cost_sum);
+    const int ncell = pp.cw * pp.ch;
+    const dim3 grid((ncell + KS_ME_WARPS - 1) / KS_ME_WARPS), block(KS_ME_WARPS * KS_WARP);
+    if (pp.me_method == 0) {
+        if (pp.satd) ks_me_kernel<0, true><<<grid, block, 0, st>>>(pp, srcY, ref, prev_cells, cells, pred, costs, cost_sum);
+        else ks_me_kernel<0, false><<<grid, block, 0, st>>>(pp, srcY, ref, prev_cells, cells, pred, costs, cost_sum);
+    } else {
+        if (pp.satd) ks_me_kernel<1, true><<<grid, block, 0, st>>>(pp, srcY, ref, prev_cells, cells, pred, costs, cost_sum);
+        else ks_me_kernel<1, false><<<grid, block, 0, st>>>(pp, srcY, ref, prev_cells, cells, pred, costs, cost_sum);
+    }
 }
 
 /* ------------------------------------------------------------------ bi-prediction (B pictures) ---- */

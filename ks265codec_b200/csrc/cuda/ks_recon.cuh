@@ -180,7 +180,7 @@ __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, c
 }
 
 /* ------------------------------------------------------------------ inter picture: one CTA per CTU - */
-#define KS_RECON_WARPS 8
+#define KS_RECON_WARPS 4                       /* one warp per 32x32 quadrant of the CTU: every warp gets the same mix of work */
 struct KsReconSmem {
     KsTbScratch tb[KS_RECON_WARPS];
     uint16_t scan[64 + 256 + 1024];            /* scan tables for 8x8, 16x16, 32x32 */
@@ -201,7 +201,7 @@ __device__ __forceinline__ void ks_load_scans(uint16_t *scan, int tid, int nthre
     for (int i = tid; i < 64 + 256 + 1024; i += nthreads) scan[i] = i < 64 ? c_scan_tb[1][i] : (i < 320 ? c_scan_tb[2][i - 64] : c_scan_tb[3][i - 320]);
 }
 
-__global__ void __launch_bounds__(KS_RECON_WARPS * KS_WARP, 2)
+__global__ void __launch_bounds__(KS_RECON_WARPS * KS_WARP, 4)
 ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes pred, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells, const ks_cell_b *__restrict__ cells_b)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -209,8 +209,7 @@ ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes pred, KsPlanes rec,
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ctx = blockIdx.x, cty = blockIdx.y, X0 = ctx << 6, Y0 = cty << 6;
     const int W = pp.W, H = pp.H, CW = W >> 1, CH = H >> 1;
-    ks_load_scans(sm->scan, tid, blockDim.x);
-    ks_load_t0(sm->t0, tid, blockDim.x);
+    for (int i = tid; i < KS_RECON_TAB_U4; i += KS_RECON_WARPS * KS_WARP) reinterpret_cast<uint4 *>(sm->scan)[i] = __ldg(&g_recon_tab[i]);   /* scan[] and t0[] are adjacent */
     if (tid < 16) {
         int cx = tid & 3, cy = tid >> 2, x = X0 + (cx << 4), y = Y0 + (cy << 4);
         bool v = x < W && y < H;
@@ -239,7 +238,7 @@ ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes pred, KsPlanes rec,
     }
     /* ---- transform tasks: 16 slots (k, q) = (kind 0..3, quadrant); a quadrant coded with one 32x32 TU uses kinds
      *      0 (luma 32) and 1 (Cb+Cr 16), otherwise kinds 0,1 (two luma 16 pairs) and 2,3 (four Cb 8 / four Cr 8).
-     *      Slot order k*4+q gives every warp one heavy and one light task. ---- */
+     *      Warp w owns quadrant w (slots w, w+4, w+8, w+12), so the warps of a CTA finish together whatever the CU sizes. ---- */
 #pragma unroll 1
     for (int sl = warp; sl < 16; sl += KS_RECON_WARPS) {
         const int k = sl >> 2, q = sl & 3;
