@@ -30,6 +30,8 @@ struct ks_gpu_ctx {
     size_t fsz;                 /* bytes of one coded picture (W*H*3/2) */
     uint8_t **d_src, **d_rec;   /* slots */
     uint8_t *d_pre;             /* pre-filter reconstruction / deblocked in place */
+    CUtensorMap tm_pre[3];      /* TMA descriptors of d_pre's planes for the SAO tile staging */
+    int tma_mask;               /* bit c: plane c qualifies (pitch multiple of 16 bytes) */
     uint8_t *d_pred;            /* inter prediction planes written by the motion search */
     uint8_t *d_pred1;           /* B pictures: list-1 prediction planes */
     ks_cell *d_cells1; int *d_cost0, *d_cost1;
@@ -55,6 +57,27 @@ __global__ void ks_extend_kernel(const uint8_t *in, int dw, int dh, uint8_t *out
     const uint8_t *ip = in + (plane == 0 ? 0 : (size_t)dw * dh + (plane == 2 ? (size_t)sw * shh : 0));
     uint8_t *op = out + (plane == 0 ? 0 : (size_t)W * H + (plane == 2 ? (size_t)pw * ph : 0));
     op[(size_t)y * pw + x] = ip[(size_t)min(y, shh - 1) * sw + min(x, sw - 1)];
+}
+
+/* 2-D u8 tensor map of one picture plane with a (bw x bh)-byte box, no swizzle, zero fill outside the picture.  The driver entry point is
+ * resolved at run time (cudaGetDriverEntryPoint), so the library links against the runtime only. */
+typedef CUresult (*ks_tmap_encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                      const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int make_plane_map(CUtensorMap *tm, void *ptr, int pw, int ph, int bw, int bh)
+{
+    static ks_tmap_encode_fn fn = NULL;
+    if (!fn) {
+        void *p = NULL; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) return -1;
+        fn = (ks_tmap_encode_fn)p;
+    }
+    if ((pw & 15) || ((uintptr_t)ptr & 15)) return 1;             /* row pitch / base must be multiples of 16 bytes: caller falls back */
+    cuuint64_t dims[2] = {(cuuint64_t)pw, (cuuint64_t)ph}, strides[1] = {(cuuint64_t)pw};
+    cuuint32_t box[2] = {(cuuint32_t)bw, (cuuint32_t)bh}, estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -1;
 }
 
 extern "C" ks_gpu_ctx *ks_gpu_open(int device, int width, int height, const ks_gpu_cfg *cfg, int *err)
@@ -84,6 +107,14 @@ extern "C" ks_gpu_ctx *ks_gpu_open(int device, int width, int height, const ks_g
         for (int i = 0; i < c->cfg.n_src_slots; i++) ok = ok && cudaMalloc(&c->d_src[i], c->fsz) == cudaSuccess;
         for (int i = 0; i < c->cfg.n_rec_slots; i++) ok = ok && cudaMalloc(&c->d_rec[i], c->fsz) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_pre, c->fsz) == cudaSuccess;
+        if (ok) {   /* TMA descriptors for the SAO tile staging: Y box 80x66, chroma 48x34 (ks_loopfilter.cuh KS_SAO_PITCH_*) */
+            uint8_t *pl[3] = {c->d_pre, c->d_pre + (size_t)c->W * c->H, c->d_pre + (size_t)c->W * c->H * 5 / 4};
+            c->tma_mask = 0;
+            for (int ci = 0; ci < 3 && ok; ci++) {
+                int r = make_plane_map(&c->tm_pre[ci], pl[ci], c->W >> (ci ? 1 : 0), c->H >> (ci ? 1 : 0), ci ? 48 : 80, ci ? 34 : 66);
+                if (r < 0) ok = false; else if (r == 0) c->tma_mask |= 1 << ci;
+            }
+        }
         ok = ok && cudaMalloc(&c->d_pred, c->fsz) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_pred1, c->fsz) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_cells1, (size_t)c->cw * c->ch * sizeof(ks_cell)) == cudaSuccess;
@@ -274,7 +305,7 @@ extern "C" int ks_gpu_encode_picture_submit(ks_gpu_ctx *c, const ks_pic_params *
     ks_launch_deblock(pp, pre, s->d_cells, s->is_b ? s->d_cells_b : NULL, c->st); c->launches += KS_LAUNCHES_DEBLOCK;
     if (p->want_sse) CK(cudaMemsetAsync(s->d_sse, 0, 3 * sizeof(unsigned long long), c->st));
     MARK(4);
-    ks_launch_sao(pp, src, pre, out, s->d_ctus, p->want_sse ? s->d_sse : NULL, c->st); c->launches += KS_LAUNCHES_SAO - 1;
+    ks_launch_sao(pp, src, pre, out, s->d_ctus, p->want_sse ? s->d_sse : NULL, c->tm_pre, c->tma_mask, c->st); c->launches += KS_LAUNCHES_SAO - 1;
     MARK(5);
     ks_launch_pack(pp, lv, s->d_ctus, s->d_pool, s->d_ncg, c->d_counts, c->st); c->launches += KS_LAUNCHES_PACK;
     MARK(-1);

@@ -153,10 +153,16 @@ void ks_launch_deblock(const KsPicParams &pp, KsPlanes rec, const ks_cell *cells
 
 /* ------------------------------------------------------------------ SAO -------------------------- */
 #define KS_SAO_WARPS 8
-#define KS_SAO_PITCH_Y 72      /* tile row: [3] left halo, [4..67] samples, [68] right halo (word-aligned interior) */
-#define KS_SAO_PITCH_C 40
+#define KS_SAO_PITCH_Y 80      /* tile row: [3] left halo, [4..67] samples, [68] right halo (word-aligned interior); = TMA box width */
+#define KS_SAO_PITCH_C 48
+#define KS_SAO_TILE_Y (66 * KS_SAO_PITCH_Y)
+#define KS_SAO_TILE_C (34 * KS_SAO_PITCH_C)
 struct KsSaoSmem {
-    uint8_t tile[3][66 * KS_SAO_PITCH_Y];  /* deblocked samples incl. 1-sample halo; chroma uses 34 x 40 */
+    /* deblocked samples incl. 1-sample halo, one TMA box per component (cp.async.bulk.tensor.2d, out-of-picture bytes arrive as
+     * zeros and are masked by the passes below); 128-byte aligned destinations */
+    __align__(128) uint8_t tileY[(KS_SAO_TILE_Y + 127) / 128 * 128];
+    __align__(128) uint8_t tileC[2][(KS_SAO_TILE_C + 127) / 128 * 128];
+    __align__(8) unsigned long long mbar;
     int hist[KS_SAO_WARPS][3][52];         /* packed (sum<<12)|count per warp: [20..51] BO band ([0..19] unused) */
     int ph[20][KS_SAO_WARPS * KS_WARP];    /* per-THREAD EO histograms (bin-major: conflict-free, no atomics), packed the same way */
     int sum[3][52], cnt[3][52];
@@ -224,34 +230,78 @@ __device__ __forceinline__ int ks_sao_cat_of(const KsSaoNb &n, int j, int k, boo
     return ok ? (lut >> (4 * (2 + ks_sgn(c - a) + ks_sgn(c - b)))) & 15 : 0;
 }
 
-__global__ void __launch_bounds__(KS_SAO_WARPS * KS_WARP)
-ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_syn *__restrict__ ctus, unsigned long long *sse_out)
+/* ---- TMA helpers (sm_90+ PTX): one thread arms an mbarrier with the byte count and issues the tile copies; everyone polls ---- */
+__device__ __forceinline__ uint32_t ks_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ks_mbar_init(unsigned long long *bar, int count)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(ks_smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void ks_mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(ks_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ks_tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(ks_smem_addr(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(ks_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void ks_mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    unsigned ok = 0;
+    for (int spin = 0; !ok; spin++) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(ok) : "r"(ks_smem_addr(bar)), "r"(parity) : "memory");
+        if (spin > (1 << 22)) __trap();       /* a copy that never lands must fail the launch, not hang the stream */
+    }
+}
+
+__global__ void __launch_bounds__(KS_SAO_WARPS * KS_WARP)
+ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_syn *__restrict__ ctus, unsigned long long *sse_out,
+              const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmCb, const __grid_constant__ CUtensorMap tmCr, int tma_mask)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     KsSaoSmem *sm = reinterpret_cast<KsSaoSmem *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rx = blockIdx.x, ry = blockIdx.y;
+    /* ---- stage the deblocked tile (+1 sample halo).  Components whose plane pitch is a multiple of 16 bytes come in as ONE TMA
+     *      box each (80x66 / 48x34 bytes at (x0-4, y0-1)); the others (odd chroma pitch) with plain word loads.  Neighbours outside
+     *      the picture are masked out in the statistics/apply passes, so the zero fill of out-of-bounds box parts is harmless. ---- */
+    if (tid == 0) {
+        ks_mbar_init(&sm->mbar, 1);
+        unsigned bytes = 0;
+        if (tma_mask & 1) bytes += KS_SAO_TILE_Y;
+        if (tma_mask & 2) bytes += KS_SAO_TILE_C;
+        if (tma_mask & 4) bytes += KS_SAO_TILE_C;
+        if (bytes) {
+            ks_mbar_expect_tx(&sm->mbar, bytes);
+            if (tma_mask & 1) ks_tma_load_2d(sm->tileY, &tmY, (rx << 6) - 4, (ry << 6) - 1, &sm->mbar);
+            if (tma_mask & 2) ks_tma_load_2d(sm->tileC[0], &tmCb, (rx << 5) - 4, (ry << 5) - 1, &sm->mbar);
+            if (tma_mask & 4) ks_tma_load_2d(sm->tileC[1], &tmCr, (rx << 5) - 4, (ry << 5) - 1, &sm->mbar);
+        }
+    }
     for (int i = tid; i < KS_SAO_WARPS * 3 * 52; i += blockDim.x) (&sm->hist[0][0][0])[i] = 0;
     if (tid < 3) sm->sse[tid] = 0;
-    /* ---- stage the deblocked tile: interior rows as 32-bit words, halo columns as bytes (coordinates clamped;
-     *      neighbours outside the picture are masked out in the statistics/apply passes) ---- */
     for (int ci = 0; ci < 3; ci++) {
+        if ((tma_mask >> ci) & 1) continue;
         const int sh = ci ? 1 : 0, PW = pp.W >> sh, PH = pp.H >> sh, x0 = (rx << 6) >> sh, y0 = (ry << 6) >> sh;
         const int tw = 64 >> sh, pitch = ci ? KS_SAO_PITCH_C : KS_SAO_PITCH_Y, wpr = tw >> 2, bw = min(tw, PW - x0);
         const uint8_t *plane = deb.p[ci];
+        uint8_t *tile = ci ? sm->tileC[ci - 1] : sm->tileY;
         for (int i = tid; i < (tw + 2) * wpr; i += blockDim.x) {
             int r = i / wpr, c = i - r * wpr;
             int gy = min(max(y0 - 1 + r, 0), PH - 1);
             uint32_t w = (4 * c < bw) ? __ldg(reinterpret_cast<const uint32_t *>(plane + (size_t)gy * PW + x0 + 4 * c)) : 0u;
-            *reinterpret_cast<uint32_t *>(&sm->tile[ci][r * pitch + 4 + 4 * c]) = w;
+            *reinterpret_cast<uint32_t *>(&tile[r * pitch + 4 + 4 * c]) = w;
         }
         for (int i = tid; i < (tw + 2) * 2; i += blockDim.x) {
             int r = i >> 1, side = i & 1;
             int gy = min(max(y0 - 1 + r, 0), PH - 1), gx = side ? min(x0 + bw, PW - 1) : max(x0 - 1, 0);
-            sm->tile[ci][r * pitch + (side ? 4 + bw : 3)] = __ldg(plane + (size_t)gy * PW + gx);
+            tile[r * pitch + (side ? 4 + bw : 3)] = __ldg(plane + (size_t)gy * PW + gx);
         }
     }
-    __syncthreads();
+    __syncthreads();                           /* also publishes the mbarrier initialisation to the pollers */
+    if (tma_mask) ks_mbar_wait(&sm->mbar, 0);
     /* ---- statistics: runs of 4 samples per thread.  EO: every thread owns a private column of a bin-major shared
      *      histogram (plain read-modify-write, conflict-free, no atomics; the reference's packed (d<<12)|1 accumulator);
      *      BO: per-warp shared histograms with run aggregation. ---- */
@@ -266,7 +316,7 @@ ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_s
             for (int i = tid; i < (((bh + step - 1) / step) << rl); i += blockDim.x) {
                 const int y = (i >> rl) * step, x = (i & ((1 << rl) - 1)) << 2;
                 if (x >= bw) continue;
-                const KsSaoNb n = ks_sao_load_nb(&sm->tile[ci][(y + 1) * pitch + 4 + x], pitch);
+                const KsSaoNb n = ks_sao_load_nb(&(ci ? sm->tileC[ci - 1] : sm->tileY)[(y + 1) * pitch + 4 + x], pitch);
                 const uint32_t s4 = __ldg(reinterpret_cast<const uint32_t *>(src.p[ci] + (size_t)(y0 + y) * PW + x0 + x));
                 const bool top = y0 + y == 0, bot = y0 + y == PH - 1;
                 int cur_band = -1, band_acc = 0;
@@ -359,7 +409,7 @@ ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_s
         for (int i = tid; i < (bh << rl); i += blockDim.x) {
             const int y = i >> rl, x = (i & ((1 << rl) - 1)) << 2;
             if (x >= bw) continue;
-            const KsSaoNb n = ks_sao_load_nb(&sm->tile[ci][(y + 1) * pitch + 4 + x], pitch);
+            const KsSaoNb n = ks_sao_load_nb(&(ci ? sm->tileC[ci - 1] : sm->tileY)[(y + 1) * pitch + 4 + x], pitch);
             const uint32_t s4 = __ldg(reinterpret_cast<const uint32_t *>(src.p[ci] + (size_t)(y0 + y) * PW + x0 + x));
             const bool top = y0 + y == 0, bot = y0 + y == PH - 1;
             uint32_t o4 = 0;
@@ -389,9 +439,10 @@ ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_s
     }
 }
 
-void ks_launch_sao(const KsPicParams &pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_syn *ctus, unsigned long long *sse_out, cudaStream_t st)
+void ks_launch_sao(const KsPicParams &pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_syn *ctus, unsigned long long *sse_out,
+                   const CUtensorMap *tm, int tma_mask, cudaStream_t st)
 {
     static bool attr_done = false;
     if (!attr_done) { cudaFuncSetAttribute(ks_sao_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsSaoSmem)); attr_done = true; }
-    ks_sao_kernel<<<dim3(pp.ctw, pp.cth), KS_SAO_WARPS * KS_WARP, sizeof(KsSaoSmem), st>>>(pp, src, deb, out, ctus, sse_out);
+    ks_sao_kernel<<<dim3(pp.ctw, pp.cth), KS_SAO_WARPS * KS_WARP, sizeof(KsSaoSmem), st>>>(pp, src, deb, out, ctus, sse_out, tm[0], tm[1], tm[2], tma_mask);
 }

@@ -29,37 +29,36 @@ struct KsWarpScratch {
 __device__ __forceinline__ void ks_load_window(uint32_t (*win)[KS_WIN_WW], const uint8_t *__restrict__ ref, int W, int H,
                                                int wx0, int wy0, int lane)
 {
-    /* all 17 loads of a lane are issued before the first store (memory-level parallelism: one L2 round trip per window,
-     * not 17); words that straddle the picture border are patched afterwards with clamped byte loads (rare) */
-    constexpr int NW = KS_WIN_H * KS_WIN_WW, PER = (NW + KS_WARP - 1) / KS_WARP;
+    /* lanes 0..12 / 13..25 own one word column of an even / odd row (26 of 32 lanes busy): the column, its bounds test and the
+     * shared-memory address are loop invariants, a row costs a clamp, one multiply-add and the load.  All 20 loads of a lane are issued
+     * before the first store (one L2 round trip per window); words that straddle the picture border are patched afterwards with
+     * clamped byte loads (rare) */
+    constexpr int PER = KS_WIN_H / 2;
+    const int half = lane >= KS_WIN_WW ? 1 : 0, c = lane - half * KS_WIN_WW, gx = wx0 + 4 * c;
+    const bool act = lane < 2 * KS_WIN_WW, in = act && gx >= 0 && gx + 3 < W;
+    const uint8_t *col = ref + gx;
     uint32_t v[PER];
-    unsigned border = 0;
 #pragma unroll
     for (int k = 0; k < PER; k++) {
-        int idx = lane + k * KS_WARP;
-        int r = idx / KS_WIN_WW, c = idx - r * KS_WIN_WW;
-        int gy = min(max(wy0 + r, 0), H - 1), gx = wx0 + 4 * c;
-        bool in = idx < NW && gx >= 0 && gx + 3 < W;
-        v[k] = in ? __ldg(reinterpret_cast<const uint32_t *>(ref + (size_t)gy * W + gx)) : 0u;
-        if (idx < NW && !in) border |= 1u << k;
+        const int gy = min(max(wy0 + 2 * k + half, 0), H - 1);
+        v[k] = in ? __ldg(reinterpret_cast<const uint32_t *>(col + (size_t)gy * W)) : 0u;
     }
+    if (act) {
+        uint32_t *dst = &win[half][c];
 #pragma unroll
-    for (int k = 0; k < PER; k++) {
-        int idx = lane + k * KS_WARP;
-        if (idx < NW) (&win[0][0])[idx] = v[k];
+        for (int k = 0; k < PER; k++) dst[2 * k * KS_WIN_WW] = v[k];
     }
-    if (__any_sync(0xffffffffu, border != 0)) {
+    if (__any_sync(0xffffffffu, act && !in)) {
+        if (act && !in) {
 #pragma unroll 1
-        for (int k = 0; k < PER; k++) {
-            if (!((border >> k) & 1)) continue;
-            int idx = lane + k * KS_WARP;
-            int r = idx / KS_WIN_WW, c = idx - r * KS_WIN_WW;
-            int gy = min(max(wy0 + r, 0), H - 1), gx = wx0 + 4 * c;
-            const uint8_t *row = ref + (size_t)gy * W;
-            uint32_t w = 0;
+            for (int k = 0; k < PER; k++) {
+                const int gy = min(max(wy0 + 2 * k + half, 0), H - 1);
+                const uint8_t *row = ref + (size_t)gy * W;
+                uint32_t w = 0;
 #pragma unroll
-            for (int b = 0; b < 4; b++) w |= (uint32_t)row[min(max(gx + b, 0), W - 1)] << (8 * b);
-            (&win[0][0])[idx] = w;
+                for (int b = 0; b < 4; b++) w |= (uint32_t)row[min(max(gx + b, 0), W - 1)] << (8 * b);
+                win[2 * k + half][c] = w;
+            }
         }
     }
     __syncwarp();
