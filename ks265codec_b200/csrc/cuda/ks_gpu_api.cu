@@ -75,9 +75,12 @@ static int make_plane_map(CUtensorMap *tm, void *ptr, int pw, int ph, int bw, in
     if ((pw & 15) || ((uintptr_t)ptr & 15)) return 1;             /* row pitch / base must be multiples of 16 bytes: caller falls back */
     cuuint64_t dims[2] = {(cuuint64_t)pw, (cuuint64_t)ph}, strides[1] = {(cuuint64_t)pw};
     cuuint32_t box[2] = {(cuuint32_t)bw, (cuuint32_t)bh}, estr[2] = {1, 1};
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    alignas(64) CUtensorMap tmp;                                  /* the encoder wants a 64-byte aligned destination; the context is calloc'ed */
+    CUresult r = fn(&tmp, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? 0 : -1;
+    if (r != CUDA_SUCCESS) { fprintf(stderr, "ks265gpu: cuTensorMapEncodeTiled failed (%d) for a %dx%d plane\n", (int)r, pw, ph); return -1; }
+    memcpy(tm, &tmp, sizeof(tmp));
+    return 0;
 }
 
 extern "C" ks_gpu_ctx *ks_gpu_open(int device, int width, int height, const ks_gpu_cfg *cfg, int *err)
@@ -107,13 +110,14 @@ extern "C" ks_gpu_ctx *ks_gpu_open(int device, int width, int height, const ks_g
         for (int i = 0; i < c->cfg.n_src_slots; i++) ok = ok && cudaMalloc(&c->d_src[i], c->fsz) == cudaSuccess;
         for (int i = 0; i < c->cfg.n_rec_slots; i++) ok = ok && cudaMalloc(&c->d_rec[i], c->fsz) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_pre, c->fsz) == cudaSuccess;
-        if (ok) {   /* TMA descriptors for the SAO tile staging: Y box 80x66, chroma 48x34 (ks_loopfilter.cuh KS_SAO_PITCH_*) */
+        if (ok) {   /* TMA descriptors for the SAO tile staging: Y box 96x66, chroma 64x34 (ks_loopfilter.cuh KS_SAO_PITCH_*) */
             uint8_t *pl[3] = {c->d_pre, c->d_pre + (size_t)c->W * c->H, c->d_pre + (size_t)c->W * c->H * 5 / 4};
             c->tma_mask = 0;
             for (int ci = 0; ci < 3 && ok; ci++) {
-                int r = make_plane_map(&c->tm_pre[ci], pl[ci], c->W >> (ci ? 1 : 0), c->H >> (ci ? 1 : 0), ci ? 48 : 80, ci ? 34 : 66);
+                int r = make_plane_map(&c->tm_pre[ci], pl[ci], c->W >> (ci ? 1 : 0), c->H >> (ci ? 1 : 0), ci ? 64 : 96, ci ? 34 : 66);
                 if (r < 0) ok = false; else if (r == 0) c->tma_mask |= 1 << ci;
             }
+            if (const char *e = getenv("KS_TMA_MASK")) c->tma_mask &= atoi(e);      /* debugging aid: 0 = stage every SAO tile with plain loads */
         }
         ok = ok && cudaMalloc(&c->d_pred, c->fsz) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_pred1, c->fsz) == cudaSuccess;

@@ -33,7 +33,7 @@ void ks_launch_bidir(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref0, 
 void ks_launch_recon_inter(const KsPicParams &pp, KsPlanes src, KsPlanes pred, KsPlanes rec, KsLevels lv, ks_cell *cells, const ks_cell_b *cells_b, cudaStream_t st);
 void ks_launch_recon_intra(const KsPicParams &pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *cells, int *sync_ws, cudaStream_t st);
 void ks_launch_deblock(const KsPicParams &pp, KsPlanes rec, const ks_cell *cells, const ks_cell_b *cells_b, cudaStream_t st);
-/* tm[3]: tensor maps of the three `deb` planes (box 80x66 / 48x34 bytes); tma_mask bit c = component c is staged by TMA */
+/* tm[3]: tensor maps of the three `deb` planes (box 96x66 / 64x34 bytes); tma_mask bit c = component c is staged by TMA */
 void ks_launch_sao(const KsPicParams &pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_syn *ctus, unsigned long long *sse_out,
                    const CUtensorMap *tm, int tma_mask, cudaStream_t st);
 void ks_launch_pack(const KsPicParams &pp, KsLevels lv, ks_ctu_syn *ctus, int16_t *pool, uint32_t *n_cg, uint32_t *scan_ws, cudaStream_t st);

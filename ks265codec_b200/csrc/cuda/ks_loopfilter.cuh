@@ -153,8 +153,11 @@ void ks_launch_deblock(const KsPicParams &pp, KsPlanes rec, const ks_cell *cells
 
 /* ------------------------------------------------------------------ SAO -------------------------- */
 #define KS_SAO_WARPS 8
-#define KS_SAO_PITCH_Y 80      /* tile row: [3] left halo, [4..67] samples, [68] right halo (word-aligned interior); = TMA box width */
-#define KS_SAO_PITCH_C 48
+#define KS_SAO_XOFF 16         /* tile row: [15] left halo, [16..] samples, then the right halo.  TMA needs the box's first byte on a 16-byte
+                                  boundary of the plane (probed: x = -4 or 60 raise an illegal-instruction fault, x = -16 works), so the box
+                                  starts 16 samples left of the CTU and its width is the row pitch */
+#define KS_SAO_PITCH_Y 96
+#define KS_SAO_PITCH_C 64
 #define KS_SAO_TILE_Y (66 * KS_SAO_PITCH_Y)
 #define KS_SAO_TILE_C (34 * KS_SAO_PITCH_C)
 struct KsSaoSmem {
@@ -265,7 +268,7 @@ ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_s
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rx = blockIdx.x, ry = blockIdx.y;
     /* ---- stage the deblocked tile (+1 sample halo).  Components whose plane pitch is a multiple of 16 bytes come in as ONE TMA
-     *      box each (80x66 / 48x34 bytes at (x0-4, y0-1)); the others (odd chroma pitch) with plain word loads.  Neighbours outside
+     *      box each (96x66 / 64x34 bytes at (x0-16, y0-1)); the others (odd chroma pitch) with plain word loads.  Neighbours outside
      *      the picture are masked out in the statistics/apply passes, so the zero fill of out-of-bounds box parts is harmless. ---- */
     if (tid == 0) {
         ks_mbar_init(&sm->mbar, 1);
@@ -275,9 +278,9 @@ ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_s
         if (tma_mask & 4) bytes += KS_SAO_TILE_C;
         if (bytes) {
             ks_mbar_expect_tx(&sm->mbar, bytes);
-            if (tma_mask & 1) ks_tma_load_2d(sm->tileY, &tmY, (rx << 6) - 4, (ry << 6) - 1, &sm->mbar);
-            if (tma_mask & 2) ks_tma_load_2d(sm->tileC[0], &tmCb, (rx << 5) - 4, (ry << 5) - 1, &sm->mbar);
-            if (tma_mask & 4) ks_tma_load_2d(sm->tileC[1], &tmCr, (rx << 5) - 4, (ry << 5) - 1, &sm->mbar);
+            if (tma_mask & 1) ks_tma_load_2d(sm->tileY, &tmY, (rx << 6) - KS_SAO_XOFF, (ry << 6) - 1, &sm->mbar);
+            if (tma_mask & 2) ks_tma_load_2d(sm->tileC[0], &tmCb, (rx << 5) - KS_SAO_XOFF, (ry << 5) - 1, &sm->mbar);
+            if (tma_mask & 4) ks_tma_load_2d(sm->tileC[1], &tmCr, (rx << 5) - KS_SAO_XOFF, (ry << 5) - 1, &sm->mbar);
         }
     }
     for (int i = tid; i < KS_SAO_WARPS * 3 * 52; i += blockDim.x) (&sm->hist[0][0][0])[i] = 0;
@@ -292,12 +295,12 @@ ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_s
             int r = i / wpr, c = i - r * wpr;
             int gy = min(max(y0 - 1 + r, 0), PH - 1);
             uint32_t w = (4 * c < bw) ? __ldg(reinterpret_cast<const uint32_t *>(plane + (size_t)gy * PW + x0 + 4 * c)) : 0u;
-            *reinterpret_cast<uint32_t *>(&tile[r * pitch + 4 + 4 * c]) = w;
+            *reinterpret_cast<uint32_t *>(&tile[r * pitch + KS_SAO_XOFF + 4 * c]) = w;
         }
         for (int i = tid; i < (tw + 2) * 2; i += blockDim.x) {
             int r = i >> 1, side = i & 1;
             int gy = min(max(y0 - 1 + r, 0), PH - 1), gx = side ? min(x0 + bw, PW - 1) : max(x0 - 1, 0);
-            tile[r * pitch + (side ? 4 + bw : 3)] = __ldg(plane + (size_t)gy * PW + gx);
+            tile[r * pitch + (side ? KS_SAO_XOFF + bw : KS_SAO_XOFF - 1)] = __ldg(plane + (size_t)gy * PW + gx);
         }
     }
     __syncthreads();                           /* also publishes the mbarrier initialisation to the pollers */
@@ -316,7 +319,7 @@ ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_s
             for (int i = tid; i < (((bh + step - 1) / step) << rl); i += blockDim.x) {
                 const int y = (i >> rl) * step, x = (i & ((1 << rl) - 1)) << 2;
                 if (x >= bw) continue;
-                const KsSaoNb n = ks_sao_load_nb(&(ci ? sm->tileC[ci - 1] : sm->tileY)[(y + 1) * pitch + 4 + x], pitch);
+                const KsSaoNb n = ks_sao_load_nb(&(ci ? sm->tileC[ci - 1] : sm->tileY)[(y + 1) * pitch + KS_SAO_XOFF + x], pitch);
                 const uint32_t s4 = __ldg(reinterpret_cast<const uint32_t *>(src.p[ci] + (size_t)(y0 + y) * PW + x0 + x));
                 const bool top = y0 + y == 0, bot = y0 + y == PH - 1;
                 int cur_band = -1, band_acc = 0;
@@ -409,7 +412,7 @@ ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_s
         for (int i = tid; i < (bh << rl); i += blockDim.x) {
             const int y = i >> rl, x = (i & ((1 << rl) - 1)) << 2;
             if (x >= bw) continue;
-            const KsSaoNb n = ks_sao_load_nb(&(ci ? sm->tileC[ci - 1] : sm->tileY)[(y + 1) * pitch + 4 + x], pitch);
+            const KsSaoNb n = ks_sao_load_nb(&(ci ? sm->tileC[ci - 1] : sm->tileY)[(y + 1) * pitch + KS_SAO_XOFF + x], pitch);
             const uint32_t s4 = __ldg(reinterpret_cast<const uint32_t *>(src.p[ci] + (size_t)(y0 + y) * PW + x0 + x));
             const bool top = y0 + y == 0, bot = y0 + y == PH - 1;
             uint32_t o4 = 0;
@@ -443,6 +446,8 @@ void ks_launch_sao(const KsPicParams &pp, KsPlanes src, KsPlanes deb, KsPlanes o
                    const CUtensorMap *tm, int tma_mask, cudaStream_t st)
 {
     static bool attr_done = false;
-    if (!attr_done) { cudaFuncSetAttribute(ks_sao_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsSaoSmem)); attr_done = true; }
-    ks_sao_kernel<<<dim3(pp.ctw, pp.cth), KS_SAO_WARPS * KS_WARP, sizeof(KsSaoSmem), st>>>(pp, src, deb, out, ctus, sse_out, tm[0], tm[1], tm[2], tma_mask);
+    if (!attr_done) { cudaFuncSetAttribute(ks_sao_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsSaoSmem) + 128); attr_done = true; }
+    alignas(64) CUtensorMap m[3];                   /* the caller's copy may sit at any alignment */
+    memcpy(m, tm, sizeof(m));
+    ks_sao_kernel<<<dim3(pp.ctw, pp.cth), KS_SAO_WARPS * KS_WARP, sizeof(KsSaoSmem) + 128, st>>>(pp, src, deb, out, ctus, sse_out, m[0], m[1], m[2], tma_mask);
 }
