@@ -201,7 +201,8 @@ __device__ __forceinline__ void ks_load_scans(uint16_t *scan, int tid, int nthre
     for (int i = tid; i < 64 + 256 + 1024; i += nthreads) scan[i] = i < 64 ? c_scan_tb[1][i] : (i < 320 ? c_scan_tb[2][i - 64] : c_scan_tb[3][i - 320]);
 }
 
-__global__ void __launch_bounds__(KS_RECON_WARPS * KS_WARP, 4)
+template <int MINB>
+__global__ void __launch_bounds__(KS_RECON_WARPS * KS_WARP, MINB)
 ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes pred, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells, const ks_cell_b *__restrict__ cells_b)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -287,9 +288,15 @@ ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes pred, KsPlanes rec,
 void ks_launch_recon_inter(const KsPicParams &pp, KsPlanes src, KsPlanes pred, KsPlanes rec, KsLevels lv, ks_cell *cells, const ks_cell_b *cells_b, cudaStream_t st)
 {
     static bool attr_done = false;
-    if (!attr_done) { cudaFuncSetAttribute(ks_recon_inter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsReconSmem)); attr_done = true; }
+    static const int minb = getenv("KS_RECON_MINB") ? atoi(getenv("KS_RECON_MINB")) : 4;       /* tuning knob: 4 (128 registers) or 5 (102) CTAs per SM */
+    if (!attr_done) {
+        cudaFuncSetAttribute(ks_recon_inter_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsReconSmem));
+        cudaFuncSetAttribute(ks_recon_inter_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsReconSmem));
+        attr_done = true;
+    }
     dim3 grid(pp.ctw, pp.cth);
-    ks_recon_inter_kernel<<<grid, KS_RECON_WARPS * KS_WARP, sizeof(KsReconSmem), st>>>(pp, src, pred, rec, lv, cells, cells_b);
+    if (minb >= 5) ks_recon_inter_kernel<5><<<grid, KS_RECON_WARPS * KS_WARP, sizeof(KsReconSmem), st>>>(pp, src, pred, rec, lv, cells, cells_b);
+    else ks_recon_inter_kernel<4><<<grid, KS_RECON_WARPS * KS_WARP, sizeof(KsReconSmem), st>>>(pp, src, pred, rec, lv, cells, cells_b);
 }
 
 /* ------------------------------------------------------------------ intra picture (wavefront) ---- */
@@ -378,7 +385,11 @@ __device__ __forceinline__ void ks_intra_substitute(const uint8_t *raw, const ui
  * dependency DAG itself: two CTAs per CTU row take alternate CTUs (CTU c+1 may start once CTU c finished its first 8 blocks),
  * rows follow each other with a one-CTU lag, all inside ONE launch.  Progress = blocks finished per CTU, published in HBM;
  * CTAs take (row, parity) tickets in start order so a CTA only ever waits on work that is already running or done. */
-__global__ void __launch_bounds__(KS_INTRA_WARPS * KS_WARP, 1)
+/* MINB = CTAs per SM the register budget is sized for: 1 lets the compiler take 128 registers x 512 threads = the whole register file,
+ * which locks every other stream's kernels out of up to 68 SMs for the ~15 ms an I picture takes; 2 caps it at 64 and leaves half
+ * of each of those SMs to the P pictures of the other GOP shards */
+template <int MINB>
+__global__ void __launch_bounds__(KS_INTRA_WARPS * KS_WARP, MINB)
 ks_recon_intra_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells, int *sync_ws)
 {
     __shared__ __align__(16) KsIntraSmem sm;
@@ -517,5 +528,7 @@ ks_recon_intra_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, k
 void ks_launch_recon_intra(const KsPicParams &pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *cells, int *sync_ws, cudaStream_t st)
 {
     cudaMemsetAsync(sync_ws, 0, sizeof(int) * (size_t)(1 + pp.ctw * pp.cth), st);
-    ks_recon_intra_kernel<<<2 * pp.cth, KS_INTRA_WARPS * KS_WARP, 0, st>>>(pp, src, rec, lv, cells, sync_ws);
+    static const int minb = getenv("KS_INTRA_MINB") ? atoi(getenv("KS_INTRA_MINB")) : 2;     /* tuning knob, see the kernel comment */
+    if (minb <= 1) ks_recon_intra_kernel<1><<<2 * pp.cth, KS_INTRA_WARPS * KS_WARP, 0, st>>>(pp, src, rec, lv, cells, sync_ws);
+    else ks_recon_intra_kernel<2><<<2 * pp.cth, KS_INTRA_WARPS * KS_WARP, 0, st>>>(pp, src, rec, lv, cells, sync_ws);
 }

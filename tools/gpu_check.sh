@@ -1,11 +1,16 @@
 #!/bin/bash
-# development helper: full GPU parity suite, bench (TMA on / off), one ncu --set full capture of the three big kernels
+# development helper: full GPU parity suite, then bench under the tuning knobs named on the command line (e.g. "KS_INTRA_MINB=1" "KS_RECON_MINB=5")
 cd "${GRAFT_REPO_ROOT:-$(dirname "$0")/..}"
 mkdir -p gpurun_out
-echo "== GPU suite"; timeout 700 python -m pytest tests -m gpu -x -q 2>&1 | tail -6; rc=${PIPESTATUS[0]}
-if [ "$rc" != "0" ]; then
-  echo "== suite with SAO TMA staging off"; KS_TMA_MASK=0 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-fi
-timeout 500 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_r1_g.json 2> gpurun_out/bench_r1_g.err; tail -c 300 gpurun_out/bench_r1_g.json; echo
-KS_TMA_MASK=0 timeout 500 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_r1_f.json 2> gpurun_out/bench_r1_f.err; tail -c 300 gpurun_out/bench_r1_f.json; echo
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:"ks_me_kernel|ks_recon_inter|ks_sao" -s 3 -c 3 -f -o gpurun_out/prof_r1_h python tools/profile_driver.py 4 > gpurun_out/ncu_full_h.log 2>&1; tail -2 gpurun_out/ncu_full_h.log
+echo "== GPU suite"; timeout 700 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+i=0
+for knob in "" "$@"; do
+  echo "== bench [$knob]"
+  env $knob timeout 500 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_knob_$i.json 2> gpurun_out/bench_knob_$i.err
+  python - <<PY
+import json
+d=json.loads(open('gpurun_out/bench_knob_$i.json').read().strip().splitlines()[-1])
+print('value %.0f e2e %.0f'%(d['value'],d['e2e']['value']), {k:round(v,4) for k,v in d['roofline']['solo_stage_ms'].items()})
+PY
+  i=$((i+1))
+done
