@@ -234,7 +234,7 @@ def main():
            "recon_intra": S + S + 2.0 * S, "deblock": 2.0 * W * H, "sao": 3.0 * S, "pack": 2.0 * S + 0.1 * S}
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/ncu_full_r1.md);
     # ncu flushes L2 before each replay, writes mostly stay in the 126 MB L2, so traffic can be BELOW the algorithmic bytes
-    ncu_traffic = {"me": 16.9e6, "recon_inter": 31.4e6, "sao": 25.1e6, "deblock": 12.9e6, "pack": 31.6e6, "recon_intra": None}
+    ncu_traffic = {"me": 21.9e6, "recon_inter": 32.0e6, "sao": 25.0e6, "deblock": 12.9e6, "pack": 31.6e6, "recon_intra": None}
     # every stage timed ALONE (one stream, nothing else on the GPU): these are the launch durations the roofline uses.
     # dominant stage = largest solo time per picture, weighted by how often the stage runs in a GOP shard.
     solo = encs[0]

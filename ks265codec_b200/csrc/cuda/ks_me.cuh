@@ -248,15 +248,19 @@ __device__ __forceinline__ void ks_interp16(KsWarpScratch *sc, int bxw, int byw,
  * (InterpolateCopy8to16_c), rows interleaved in pairs: word [r>>1][c] = (row r even | row r odd << 16).
  * Every candidate of the stage is then one vertical pass over a plane: 5 dp2a (s16 x s8 pairs) per sample. ---- */
 typedef uint32_t (*KsPlane)[16];
+/* physical 16-byte segment of logical segment `seg` (4 columns) in pair-row `pr`: every other PAIR of pair-rows has its segments swapped
+ * pairwise, so the quarter-warp that spans pair-rows p, p+1, p+2 (odd first row) reads six distinct bank groups instead of colliding on p / p+2 */
+#define KS_PLANE_SEG(pr, seg) ((seg) ^ (((pr) >> 1) & 1))
 __device__ __forceinline__ void ks_make_plane(KsPlane pl, const uint32_t (*win)[KS_WIN_WW], int wxb, int wyb, int fx, int lane)
 {
     const int tlo = c_luma_taps_packed[fx][0], thi = c_luma_taps_packed[fx][1];
 #pragma unroll
     for (int k = 0; k < 2; k++) {
-        const int u = lane + 32 * k;               /* 48 units: (row, 8-column group) */
+        const int u = lane + 32 * k;               /* 48 units: (row, 8-column group); the lane two over holds the other row of the pair */
+        const int r = u >> 1, g = u & 1;
+        int h[8];
         if (u < 48) {
-            const int r = u >> 1, g = u & 1;
-            uint32_t n[4]; int h[8];
+            uint32_t n[4];
             if (fx) {
                 ks_row16(win, wyb + r, wxb + 8 * g - 3, n);
                 ks_htaps8(n, tlo, thi, h);
@@ -268,9 +272,27 @@ __device__ __forceinline__ void ks_make_plane(KsPlane pl, const uint32_t (*win)[
 #pragma unroll
                 for (int j = 0; j < 4; j++) { h[j] = (int)((a >> (8 * j)) & 255) << 6; h[4 + j] = (int)((b >> (8 * j)) & 255) << 6; }
             }
-            int16_t *d = reinterpret_cast<int16_t *>(&pl[r >> 1][8 * g]) + (r & 1);
+        } else {
 #pragma unroll
-            for (int j = 0; j < 8; j++) d[2 * j] = (int16_t)h[j];
+            for (int j = 0; j < 8; j++) h[j] = 0;
+        }
+        /* pair interleave in registers: the even row keeps columns 0..3 and receives the odd row's, the odd row keeps 4..7 and receives the
+         * even row's; each lane then stores four complete (even | odd << 16) words with one 128-bit store (was eight 16-bit stores) */
+        const int odd = r & 1;
+        const uint32_t s0 = ((uint32_t)h[odd ? 0 : 4] & 0xffffu) | ((uint32_t)h[odd ? 1 : 5] << 16);
+        const uint32_t s1 = ((uint32_t)h[odd ? 2 : 6] & 0xffffu) | ((uint32_t)h[odd ? 3 : 7] << 16);
+        const uint32_t g0 = __shfl_xor_sync(0xffffffffu, s0, 2), g1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+        if (u < 48) {
+            uint4 w;
+            if (!odd) {
+                w.x = ((uint32_t)h[0] & 0xffffu) | (g0 << 16);          w.y = ((uint32_t)h[1] & 0xffffu) | (g0 & 0xffff0000u);
+                w.z = ((uint32_t)h[2] & 0xffffu) | (g1 << 16);          w.w = ((uint32_t)h[3] & 0xffffu) | (g1 & 0xffff0000u);
+            } else {
+                w.x = (g0 & 0xffffu) | ((uint32_t)h[4] << 16);          w.y = (g0 >> 16) | ((uint32_t)h[5] << 16);
+                w.z = (g1 & 0xffffu) | ((uint32_t)h[6] << 16);          w.w = (g1 >> 16) | ((uint32_t)h[7] << 16);
+            }
+            const int pr = r >> 1;
+            *reinterpret_cast<uint4 *>(&pl[pr][KS_PLANE_SEG(pr, 2 * g + odd) * 4]) = w;
         }
     }
     __syncwarp();
@@ -285,7 +307,8 @@ __device__ __forceinline__ void ks_plane_pred(const KsPlane pl, int roff, int fy
     int v[8];
     if (fy == 0) {
         const int R = roff + 3 + row;
-        const uint4 qa = *reinterpret_cast<const uint4 *>(&pl[R >> 1][8 * half]), qb = *reinterpret_cast<const uint4 *>(&pl[R >> 1][8 * half + 4]);
+        const int prc = R >> 1;
+        const uint4 qa = *reinterpret_cast<const uint4 *>(&pl[prc][KS_PLANE_SEG(prc, 2 * half) * 4]), qb = *reinterpret_cast<const uint4 *>(&pl[prc][KS_PLANE_SEG(prc, 2 * half + 1) * 4]);
         const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
         for (int j = 0; j < 8; j++) { int t = (R & 1) ? ((int)w[j] >> 16) : (int)(short)(w[j] & 0xffffu); v[j] = (t + 32) >> 6; }
@@ -297,7 +320,7 @@ __device__ __forceinline__ void ks_plane_pred(const KsPlane pl, int roff, int fy
 #pragma unroll
         for (int i = 0; i < 5; i++) {
             const int pr = min((R0 >> 1) + i, 11);      /* the 5th pair only matters for odd R0; clamp keeps the even case in bounds (its taps are 0) */
-            const uint4 qa = *reinterpret_cast<const uint4 *>(&pl[pr][8 * half]), qb = *reinterpret_cast<const uint4 *>(&pl[pr][8 * half + 4]);
+            const uint4 qa = *reinterpret_cast<const uint4 *>(&pl[pr][KS_PLANE_SEG(pr, 2 * half) * 4]), qb = *reinterpret_cast<const uint4 *>(&pl[pr][KS_PLANE_SEG(pr, 2 * half + 1) * 4]);
             const uint32_t w[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
             const int kk = i < 2 ? k0 : (i < 4 ? k1 : k2);
 #pragma unroll

@@ -10,9 +10,8 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
         "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
         "smsp__inst_executed.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
-        "lts__t_sector_hit_rate.pct", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct",
-        "smsp__warp_issue_stalled_barrier_per_warp_active.pct", "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct",
-        "smsp__warp_issue_stalled_mio_throttle_per_warp_active.pct", "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct"]
+        "lts__t_sector_hit_rate.pct"] + ["smsp__average_warps_issue_stalled_%s_per_issue_active.ratio" % k for k in
+        ("long_scoreboard", "short_scoreboard", "barrier", "no_instruction", "math_pipe_throttle", "mio_throttle", "wait", "not_selected")]
 
 
 def main():
@@ -23,7 +22,7 @@ def main():
     units = rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
     name_i = idx.get("Kernel Name")
-    lines = ["# ncu --set full summary of %s" % rep, "", "| kernel | " + " | ".join(k.split(".")[0].replace("smsp__warp_issue_stalled_", "stall_").replace("_per_warp_active", "") for k in KEYS) + " |",
+    lines = ["# ncu --set full summary of %s" % rep, "", "| kernel | " + " | ".join(k.split(".")[0].replace("smsp__average_warps_issue_stalled_", "stall_").replace("_per_issue_active", "") for k in KEYS) + " |",
              "|---|" + "---|" * len(KEYS)]
     for r in rows[2:]:
         if not r or name_i is None:
