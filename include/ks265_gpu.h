@@ -98,6 +98,9 @@ int  ks_gpu_set_profiling(ks_gpu_ctx *ctx, int on);
 int  ks_gpu_get_stage_times(const ks_gpu_ctx *ctx, double ms[6], uint64_t launches[6]);
 /* bytes copied device->host so far (syntax blocks) */
 uint64_t ks_gpu_d2h_bytes(const ks_gpu_ctx *ctx);
+/* sizeof() of the ABI structs as this library was built (binding self-check: 0 ks_gpu_cfg, 1 ks_pic_params, 2 ks_pic_out, 3 ks_cell,
+ * 4 ks_cell_b, 5 ks_ctu_syn, 6 ks265_config, 7 ks265_gop_stats; 0 for an unknown index) */
+size_t ks_gpu_abi_sizeof(int which);
 
 /* ---- stage-level debug/test access (tests compare every stage with the oracle) ---- */
 enum { KS_DBG_PRE_RECON = 0, KS_DBG_LEVELS = 1, KS_DBG_SRC = 2 };

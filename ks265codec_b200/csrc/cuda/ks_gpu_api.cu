@@ -3,6 +3,7 @@
  * per-picture launch sequence and the asynchronous syntax download.
  */
 #include "ks265_gpu.h"
+#include "ks265_enc.h"
 #include "ks_launch.h"
 #include "ks_kat.h"
 #include <stdio.h>
@@ -198,6 +199,12 @@ extern "C" int ks_gpu_get_stage_times(const ks_gpu_ctx *c, double ms[6], uint64_
     return 0;
 }
 extern "C" uint64_t ks_gpu_d2h_bytes(const ks_gpu_ctx *c) { return c ? c->d2h_total : 0; }
+extern "C" size_t ks_gpu_abi_sizeof(int which)
+{
+    static const size_t sz[8] = {sizeof(ks_gpu_cfg), sizeof(ks_pic_params), sizeof(ks_pic_out), sizeof(ks_cell), sizeof(ks_cell_b), sizeof(ks_ctu_syn),
+                                 sizeof(ks265_config), sizeof(ks265_gop_stats)};
+    return which >= 0 && which < 8 ? sz[which] : 0;
+}
 
 static int extend_into_slot(ks_gpu_ctx *c, const uint8_t *dev_i420, int slot)
 {

@@ -56,3 +56,7 @@ void ora_run_me(const ora_cfg *cfg, int qp, const uint8_t *src, const uint8_t *r
     for (int i = 0; i < (W >> 4) * (H >> 4); i++) { cells_out[i].cu_log2 = 4; cells_out[i].flags = 0; }
     ora_pic_free(&s); ora_pic_free(&r); ora_pic_free(&pre); free(lv.c[0]); free(lv.c[1]); free(lv.c[2]);
 }
+
+/* sizeof() of the configuration structs (binding self-check for the ctypes mirrors in tests/katlib.py): 0 ora_cfg, 1 ora_seq_cfg */
+size_t ora_sizeof_seq_cfg(void);
+size_t ora_abi_sizeof(int which) { return which == 0 ? sizeof(ora_cfg) : (which == 1 ? ora_sizeof_seq_cfg() : 0); }

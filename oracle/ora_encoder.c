@@ -18,6 +18,8 @@ typedef struct ora_seq_cfg {
     int rc, crf_x100;         /* rc 0: fixed QP; rc 3: CRF (crf * 100), QP per picture from the host rate control (ks_ratecontrol.c) */
 } ora_seq_cfg;
 
+size_t ora_sizeof_seq_cfg(void) { return sizeof(ora_seq_cfg); }
+
 static void store_cropped(const ora_pic *p, int w, int h, uint8_t *dst)
 {
     for (int ci = 0; ci < 3; ci++) {

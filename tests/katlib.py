@@ -63,3 +63,14 @@ def oracle():
 
 def ptr(a, byte_off=0):
     return C.c_void_p(a.ctypes.data + byte_off)
+
+
+# ---- ctypes mirrors of the CPU model's configuration structs (ONE definition: tests, smoke() and tools import these) ----
+class OraCfg(C.Structure):
+    """oracle/ora_frame.h: ora_cfg"""
+    _fields_ = [(n, C.c_int) for n in ("width", "height", "me_range", "me_iters", "subpel", "sign_hiding", "sao", "strong_intra", "satd", "me_method")]
+
+
+class SeqCfg(C.Structure):
+    """oracle/ora_encoder.c: ora_seq_cfg"""
+    _fields_ = [(n, C.c_int) for n in "width height nframes qp iper fixqp me_range me_iters subpel sign_hiding sao max_merge_cand satd bframes me_method rc crf_x100".split()]

@@ -34,6 +34,31 @@ def test_struct_layouts_match_header():
     assert ks.KsCtuSyn.cg_base.offset == 48 and ks.KsCtuSyn.sao.offset == 52
 
 
+def test_ctypes_mirrors_have_the_librarys_struct_sizes():
+    """a field added to a C struct but not to its ctypes mirror silently shifts everything behind it: compare sizeof() on both sides"""
+    from katlib import OraCfg, SeqCfg, oracle
+    L = ks.lib()
+    L.ks_gpu_abi_sizeof.restype = C.c_size_t
+    mirrors = [ks.KsGpuCfg, ks.KsPicParams, ks.KsPicOut, ks.KsCell, ks.KsCellB, ks.KsCtuSyn, ks.Ks265Config, ks.Ks265GopStats]
+    for i, m in enumerate(mirrors):
+        assert L.ks_gpu_abi_sizeof(i) == C.sizeof(m), "%s: library %d bytes, ctypes mirror %d" % (m.__name__, L.ks_gpu_abi_sizeof(i), C.sizeof(m))
+    O = oracle()
+    O.ora_abi_sizeof.restype = C.c_size_t
+    assert O.ora_abi_sizeof(0) == C.sizeof(OraCfg) and O.ora_abi_sizeof(1) == C.sizeof(SeqCfg)
+
+
+def test_smoke_checker_leg_runs_on_cpu():
+    """__graft_entry__.smoke() compares the device against this oracle call; keep that half green where there is no GPU"""
+    import numpy as np
+    import __graft_entry__ as g
+    import gen_yuv
+    w, h, n = 192, 112, 3
+    yuv = np.frombuffer(gen_yuv.make(w, h, n, seed=3), np.uint8)
+    cfg = ks.default_config(w, h, preset="veryfast", qp=30, iper=n)
+    bs, rec = g._oracle_stream(cfg, yuv, n)
+    assert bs.size > 100 and rec.size == w * h * 3 // 2 * n and bytes(bs[:4]) == b"\x00\x00\x00\x01"
+
+
 def test_no_gpu_fails_loudly():
     import torch
     if torch.cuda.is_available():

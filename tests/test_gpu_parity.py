@@ -10,7 +10,7 @@ import tempfile
 import numpy as np
 import pytest
 
-from katlib import ROOT, oracle, ptr
+from katlib import ROOT, OraCfg, SeqCfg, oracle, ptr
 
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import gen_yuv  # noqa: E402
@@ -20,14 +20,6 @@ pytestmark = pytest.mark.gpu
 import ks265codec_b200 as ks  # noqa: E402
 
 DEC = os.path.join(ROOT, "oracle", "_ref", "appdecoder")
-
-
-class OraCfg(C.Structure):
-    _fields_ = [(n, C.c_int) for n in ("width", "height", "me_range", "me_iters", "subpel", "sign_hiding", "sao", "strong_intra", "satd", "me_method")]
-
-
-class SeqCfg(C.Structure):
-    _fields_ = [(n, C.c_int) for n in "width height nframes qp iper fixqp me_range me_iters subpel sign_hiding sao max_merge_cand satd bframes me_method rc crf_x100".split()]
 
 
 def first_diff(a, b, what, shape=None):

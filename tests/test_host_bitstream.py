@@ -11,16 +11,12 @@ import tempfile
 import numpy as np
 import pytest
 
-from katlib import GOLDEN, ROOT, oracle, ptr
+from katlib import GOLDEN, ROOT, SeqCfg, oracle, ptr
 
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import gen_yuv  # noqa: E402
 
 DEC = os.path.join(ROOT, "oracle", "_ref", "appdecoder")
-
-
-class SeqCfg(C.Structure):
-    _fields_ = [(n, C.c_int) for n in "width height nframes qp iper fixqp me_range me_iters subpel sign_hiding sao max_merge_cand satd bframes me_method rc crf_x100".split()]
 
 
 def model_encode(yuv, w, h, n, qp, iper, sbh=1, sao=1, subpel=2, bframes=0, me=0, rc=0, crf=24.0):

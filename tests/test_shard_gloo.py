@@ -15,14 +15,12 @@ import numpy as np
 sys.path.insert(0, %(root)r); sys.path.insert(0, os.path.join(%(root)r, "tests")); sys.path.insert(0, os.path.join(%(root)r, "tools"))
 import torch.distributed as dist
 import gen_yuv
-from katlib import oracle, ptr
+from katlib import SeqCfg, oracle, ptr
 from ks265codec_b200 import shard as ksh
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
 rank, world = dist.get_rank(), dist.get_world_size()
 w, h, n, iper = 96, 64, 10, 3
 yuv = np.frombuffer(gen_yuv.make(w, h, n, seed=9), np.uint8)
-class SeqCfg(C.Structure):
-    _fields_ = [(k, C.c_int) for k in "width height nframes qp iper fixqp me_range me_iters subpel sign_hiding sao max_merge_cand satd bframes me_method rc crf_x100".split()]
 O = oracle(); O.ora_encode_sequence.restype = C.c_long
 def enc(first, cnt):
     cfg = SeqCfg(w, h, cnt, 30, iper, 0, 64, 16, 2, 1, 1, 3)
