@@ -28,6 +28,9 @@ struct ks_gpu_ctx {
     int device, dw, dh, W, H, cw, ch, ctw, cth;
     ks_gpu_cfg cfg;
     cudaStream_t st;
+    cudaStream_t st_up;         /* source uploads run beside the previous picture's kernels of the same shard */
+    cudaEvent_t *ev_up;         /* per source slot: upload finished (the picture's kernels wait for it) */
+    cudaEvent_t *ev_src_read;   /* per source slot: the last picture that read it has finished (the next upload waits for it) */
     size_t fsz;                 /* bytes of one coded picture (W*H*3/2) */
     uint8_t **d_src, **d_rec;   /* slots */
     uint8_t *d_pre;             /* pre-filter reconstruction / deblocked in place */
@@ -103,6 +106,11 @@ extern "C" ks_gpu_ctx *ks_gpu_open(int device, int width, int height, const ks_g
     c->fsz = (size_t)c->W * c->H * 3 / 2;
     ks_upload_tables();
     if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { e = KS_ECUDA; goto fail; }
+    if (cudaStreamCreateWithFlags(&c->st_up, cudaStreamNonBlocking) != cudaSuccess) { e = KS_ECUDA; goto fail; }
+    c->ev_up = (cudaEvent_t *)calloc(c->cfg.n_src_slots, sizeof(cudaEvent_t));
+    c->ev_src_read = (cudaEvent_t *)calloc(c->cfg.n_src_slots, sizeof(cudaEvent_t));
+    for (int i = 0; i < c->cfg.n_src_slots; i++)
+        if (cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_src_read[i], cudaEventDisableTiming) != cudaSuccess) { e = KS_ECUDA; goto fail; }
     c->d_src = (uint8_t **)calloc(c->cfg.n_src_slots, sizeof(uint8_t *));
     c->d_rec = (uint8_t **)calloc(c->cfg.n_rec_slots, sizeof(uint8_t *));
     c->syn = (ks_syn_slot *)calloc(c->cfg.n_syn_slots, sizeof(ks_syn_slot));
@@ -179,6 +187,9 @@ extern "C" void ks_gpu_close(ks_gpu_ctx *c)
         for (int k = 0; k <= KS_NSTAGE; k++) if (s->ev[k]) cudaEventDestroy(s->ev[k]);
     }
     if (c->st) cudaStreamDestroy(c->st);
+    if (c->st_up) cudaStreamDestroy(c->st_up);
+    for (int i = 0; i < c->cfg.n_src_slots; i++) { if (c->ev_up && c->ev_up[i]) cudaEventDestroy(c->ev_up[i]); if (c->ev_src_read && c->ev_src_read[i]) cudaEventDestroy(c->ev_src_read[i]); }
+    free(c->ev_up); free(c->ev_src_read);
     free(c->d_src); free(c->d_rec); free(c->syn); free(c);
 }
 
@@ -209,7 +220,7 @@ extern "C" size_t ks_gpu_abi_sizeof(int which)
 static int extend_into_slot(ks_gpu_ctx *c, const uint8_t *dev_i420, int slot)
 {
     dim3 grid((c->W + 255) / 256, c->H, 3);
-    ks_extend_kernel<<<grid, 256, 0, c->st>>>(dev_i420, c->dw, c->dh, c->d_src[slot], c->W, c->H);
+    ks_extend_kernel<<<grid, 256, 0, c->st_up>>>(dev_i420, c->dw, c->dh, c->d_src[slot], c->W, c->H);
     c->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -222,11 +233,12 @@ extern "C" int ks_gpu_upload_frame(ks_gpu_ctx *c, int slot, const uint8_t *y, co
     const bool tight = sy == c->dw && suv == c->dw / 2 && u == y + (size_t)c->dw * c->dh && v == u + (size_t)c->dw * c->dh / 4;
     const bool same = c->dw == c->W && c->dh == c->H;
     uint8_t *dst = same ? c->d_src[slot] : c->d_stage;          /* no padding needed: land directly in the slot */
+    CK(cudaStreamWaitEvent(c->st_up, c->ev_src_read[slot], 0)); /* whoever last read this slot is done (no-op if nobody did) */
     cudaPointerAttributes at;
     if (tight && cudaPointerGetAttributes(&at, y) == cudaSuccess && at.type == cudaMemoryTypeHost) {
         /* caller's buffer is page-locked: DMA straight out of it (caller keeps it alive until the picture is finished,
          * the same ownership rule as QY265Picture, qy265enc.h:153-157) */
-        CK(cudaMemcpyAsync(dst, y, dsz, cudaMemcpyHostToDevice, c->st));
+        CK(cudaMemcpyAsync(dst, y, dsz, cudaMemcpyHostToDevice, c->st_up));
     } else {
         (void)cudaGetLastError();
         const int si = c->stage_idx; c->stage_idx ^= 1;
@@ -237,20 +249,23 @@ extern "C" int ks_gpu_upload_frame(ks_gpu_ctx *c, int slot, const uint8_t *y, co
         for (int r = 0; r < c->dh / 2; r++) memcpy(d + (size_t)r * (c->dw / 2), u + (size_t)r * suv, c->dw / 2);
         d += (size_t)c->dw * c->dh / 4;
         for (int r = 0; r < c->dh / 2; r++) memcpy(d + (size_t)r * (c->dw / 2), v + (size_t)r * suv, c->dw / 2);
-        CK(cudaMemcpyAsync(dst, c->h_stage[si], dsz, cudaMemcpyHostToDevice, c->st));
-        CK(cudaEventRecord(c->ev_stage[si], c->st));
+        CK(cudaMemcpyAsync(dst, c->h_stage[si], dsz, cudaMemcpyHostToDevice, c->st_up));
+        CK(cudaEventRecord(c->ev_stage[si], c->st_up));
     }
-    return same ? 0 : extend_into_slot(c, c->d_stage, slot);
+    int r = same ? 0 : extend_into_slot(c, c->d_stage, slot);
+    if (r) return r;
+    CK(cudaEventRecord(c->ev_up[slot], c->st_up));
+    return 0;
 }
 extern "C" int ks_gpu_upload_frame_device(ks_gpu_ctx *c, int slot, const void *dev_i420)
 {
     if (!c || slot < 0 || slot >= c->cfg.n_src_slots || !dev_i420) return KS_EINVAL;
     CK(cudaSetDevice(c->device));
-    if (c->dw == c->W && c->dh == c->H) {
-        CK(cudaMemcpyAsync(c->d_src[slot], dev_i420, c->fsz, cudaMemcpyDeviceToDevice, c->st));
-        return 0;
-    }
-    return extend_into_slot(c, (const uint8_t *)dev_i420, slot);
+    CK(cudaStreamWaitEvent(c->st_up, c->ev_src_read[slot], 0));
+    if (c->dw == c->W && c->dh == c->H) CK(cudaMemcpyAsync(c->d_src[slot], dev_i420, c->fsz, cudaMemcpyDeviceToDevice, c->st_up));
+    else { int r = extend_into_slot(c, (const uint8_t *)dev_i420, slot); if (r) return r; }
+    CK(cudaEventRecord(c->ev_up[slot], c->st_up));
+    return 0;
 }
 
 static int fill_params(const ks_gpu_ctx *c, const ks_pic_params *p, KsPicParams *pp)
@@ -282,6 +297,7 @@ extern "C" int ks_gpu_encode_picture_submit(ks_gpu_ctx *c, const ks_pic_params *
     if (s->pending) return KS_EINVAL;
     KsPlanes src = planes_of(c, c->d_src[p->src_slot]), pre = planes_of(c, c->d_pre), out = planes_of(c, c->d_rec[p->out_slot]);
     KsLevels lv; lv.p[0] = c->d_lev; lv.p[1] = c->d_lev + (size_t)c->W * c->H; lv.p[2] = lv.p[1] + (size_t)c->W * c->H / 4;
+    CK(cudaStreamWaitEvent(c->st, c->ev_up[p->src_slot], 0));  /* the source picture's upload (separate stream) */
     s->nev = 0;
 #define MARK(stage) do { if (c->profiling) { cudaEventRecord(s->ev[s->nev], c->st); s->stage_of[s->nev++] = (stage); } } while (0)
     if (p->slice_type == KS_SLICE_I) {
@@ -317,6 +333,7 @@ extern "C" int ks_gpu_encode_picture_submit(ks_gpu_ctx *c, const ks_pic_params *
     if (p->want_sse) CK(cudaMemsetAsync(s->d_sse, 0, 3 * sizeof(unsigned long long), c->st));
     MARK(4);
     ks_launch_sao(pp, src, pre, out, s->d_ctus, p->want_sse ? s->d_sse : NULL, c->tm_pre, c->tma_mask, c->st); c->launches += KS_LAUNCHES_SAO - 1;
+    CK(cudaEventRecord(c->ev_src_read[p->src_slot], c->st));   /* SAO was the last stage to read the source picture */
     MARK(5);
     ks_launch_pack(pp, lv, s->d_ctus, s->d_pool, s->d_ncg, c->d_counts, c->st); c->launches += KS_LAUNCHES_PACK;
     MARK(-1);
@@ -407,6 +424,7 @@ extern "C" int ks_gpu_debug_me(ks_gpu_ctx *c, const ks_pic_params *p, ks_cell *c
     KsPlanes src = planes_of(c, c->d_src[p->src_slot]), ref = planes_of(c, c->d_rec[p->ref_slot]);
     const ks_cell *prev = p->prev_syn_slot >= 0 ? c->syn[p->prev_syn_slot].d_cells : NULL;
     KsPlanes nopred; nopred.p[0] = nopred.p[1] = nopred.p[2] = NULL;
+    CK(cudaStreamWaitEvent(c->st, c->ev_up[p->src_slot], 0));
     ks_launch_me(pp, src.p[0], ref, prev, s->d_cells, nopred, NULL, NULL, c->st); c->launches += KS_LAUNCHES_ME;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(cells_out, s->d_cells, (size_t)c->cw * c->ch * sizeof(ks_cell), cudaMemcpyDeviceToHost, c->st));
