@@ -156,7 +156,10 @@ extern "C" ks_gpu_ctx *ks_gpu_open(int device, int width, int height, const ks_g
             ok = ok && cudaHostAlloc(&s->h_ncg, sizeof(uint32_t), cudaHostAllocDefault) == cudaSuccess;
             ok = ok && cudaHostAlloc(&s->h_sse, 3 * sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
             ok = ok && cudaHostAlloc(&s->h_mecost, sizeof(unsigned long long), cudaHostAllocDefault) == cudaSuccess;
-            ok = ok && cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming) == cudaSuccess;
+            /* KS_BLOCKING_SYNC=1: the shard's host thread sleeps instead of spinning while it waits for a picture (frees its core for the
+             * entropy coders of other shards when every logical core is taken, e.g. 8 GPUs x 16 shards on a 128-thread host) */
+            static const bool blocking = getenv("KS_BLOCKING_SYNC") && atoi(getenv("KS_BLOCKING_SYNC")) != 0;
+            ok = ok && cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming | (blocking ? cudaEventBlockingSync : 0)) == cudaSuccess;
             for (int k = 0; k <= KS_NSTAGE; k++) ok = ok && cudaEventCreate(&s->ev[k]) == cudaSuccess;
             if (ok) cudaMemset(s->d_ctus, 0, nctu * sizeof(ks_ctu_syn));
         }
