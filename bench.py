@@ -83,6 +83,25 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
+def bind_to_gpu_numa(gpu_index, min_cpus):
+    """pin this process (and the shard threads it will start, and the pinned buffers it will first-touch) to the CPUs NVML reports as local to
+    the GPU: kernel launches and H2D/D2H descriptors then stay on the GPU's own socket.  Returns (n_cpus, previous mask) or (0, None)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, ((os.cpu_count() or 64) + 63) // 64)
+        cpus = {i * 64 + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        prev = os.sched_getaffinity(0)
+        cpus &= prev
+        if len(cpus) >= min_cpus and cpus != prev:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus), prev
+    except Exception:
+        pass
+    return 0, None
+
+
 def run_reference(sample_frames, yuv_path, threads):
     """reference encoder on host cores; returns fps from its own 'test time' line"""
     enc = os.path.join(ROOT, "oracle", "_ref", "appencoder")
@@ -158,6 +177,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     streams = a.streams or max(2, min(16, cores // max(1, a.gpus)))      # measured on a 128-core host: 8 -> host-bound e2e, 24 -> launch contention
+    visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+    nvml_index = int(visible.split(",")[local_rank]) if visible and all(v.strip().isdigit() for v in visible.split(",")) else local_rank
+    numa_cpus, full_mask = bind_to_gpu_numa(nvml_index, 2 * streams) if os.environ.get("KS_NO_NUMA_BIND") is None else (0, None)
     if 2 * world * streams > cores:      # every logical core has work: waiting shard threads sleep instead of spinning next to the entropy coders (N=1: spinning is 2 % faster)
         os.environ.setdefault("KS_BLOCKING_SYNC", "1")
 
@@ -268,6 +290,8 @@ def main():
         n = a.cpu_sample_frames
         try:
             write_sample_yuv(frames, order, n, path)
+            if full_mask:
+                os.sched_setaffinity(0, full_mask)      # the reference gets every host core, not just this GPU's socket
             fps, wall = run_reference(n, path, 0)
             cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference",
                    "sample": "%d pictures of the same synthetic 4K sequence, oracle/_ref/appencoder (centos_x64) -threads 0, fps from its 'test time' line (wall %.1f s)" % (n, wall)}
@@ -283,7 +307,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": "3840x2160 I420 -preset veryfast -rc 0 -qp 27 -iper 128 (BASELINE configs[2])", "gop_shard": "1 IDR + 127 P, closed GOP",
-                       "streams_per_gpu": streams, "pictures_per_step": frames_per_step, "parallelism": "gop-shard x%d" % world,
+                       "streams_per_gpu": streams, "cpu_binding": ("%d CPUs local to the GPU (NVML affinity)" % numa_cpus) if numa_cpus else "none", "pictures_per_step": frames_per_step, "parallelism": "gop-shard x%d" % world,
                        "l2": "inputs larger than L2 (%.1f GB of pictures per step per GPU)" % (streams * IPER * FSZ / 1e9),
                        "value_scope": "device hot path (ME, MC+transform+quant, deblock, SAO, level pack, syntax D2H), pictures resident in HBM; host CABAC excluded",
                        "e2e_scope": "host I420 -> H2D -> device hot path -> syntax D2H -> host CABAC -> Annex-B (+NCCL NAL gather if N>1)"},
