@@ -179,7 +179,8 @@ def main():
     streams = a.streams or max(2, min(16, cores // max(1, a.gpus)))      # measured on a 128-core host: 8 -> host-bound e2e, 24 -> launch contention
     visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
     nvml_index = int(visible.split(",")[local_rank]) if visible and all(v.strip().isdigit() for v in visible.split(",")) else local_rank
-    numa_cpus, full_mask = bind_to_gpu_numa(nvml_index, 2 * streams) if os.environ.get("KS_NO_NUMA_BIND") is None else (0, None)
+    # opt-in: measured neutral on the 2-socket pool hosts (N=2: value 4403 bound vs 4414 unbound, e2e 3638 vs 3838), profiles/README.md
+    numa_cpus, full_mask = bind_to_gpu_numa(nvml_index, 2 * streams) if os.environ.get("KS_NUMA_BIND") == "1" else (0, None)
     if 2 * world * streams > cores:      # every logical core has work: waiting shard threads sleep instead of spinning next to the entropy coders (N=1: spinning is 2 % faster)
         os.environ.setdefault("KS_BLOCKING_SYNC", "1")
 
