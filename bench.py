@@ -181,7 +181,10 @@ def main():
     nvml_index = int(visible.split(",")[local_rank]) if visible and all(v.strip().isdigit() for v in visible.split(",")) else local_rank
     # opt-in: measured neutral on the 2-socket pool hosts (N=2: value 4403 bound vs 4414 unbound, e2e 3638 vs 3838), profiles/README.md
     numa_cpus, full_mask = bind_to_gpu_numa(nvml_index, 2 * streams) if os.environ.get("KS_NUMA_BIND") == "1" else (0, None)
-    if 2 * world * streams > cores:      # every logical core has work: waiting shard threads sleep instead of spinning next to the entropy coders (N=1: spinning is 2 % faster)
+    # shard threads that wait for a picture SLEEP (cudaEventBlockingSync) whenever more than one GPU process shares the host: measured at
+    # N=2, 16 shards per GPU: spinning waits 4414 / 3838 fps (value / e2e), blocking waits 5226 / 4440 -- the spinners of one process slow
+    # the launch threads of the other.  A single process is 2 % faster spinning (2493 vs 2445 e2e), so N=1 keeps the default.
+    if world > 1 or 2 * streams > cores:
         os.environ.setdefault("KS_BLOCKING_SYNC", "1")
 
     # ---- synthetic input: DISTINCT pictures, shard = 128-picture ping-pong sequence; device copy + pinned host copy ----
