@@ -3,6 +3,9 @@
  * See ks_bitstream.h for the reference counterparts.  Section numbers refer to ITU-T H.265 (v3+).
  */
 #include "ks_bitstream.h"
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <stdlib.h>
 #include <string.h>
 
@@ -329,6 +332,8 @@ static void ctu_prefix(slice_enc *e, int ctu)
 }
 /* sig_coeff_flag context increments (9.3.4.2.5), tabulated: [chroma][8x8 TB][CG != (0,0)][right | below<<1][raster pos in CG] */
 static uint8_t g_sig_ctx[2][2][2][4][16];
+static uint8_t g_sig_ctx_scan[2][2][2][4][16];      /* the same, indexed by scan position inside the CG */
+static uint16_t g_r2s_lo[256], g_r2s_hi[256];      /* raster -> scan bit permutation of a 4x4 group, low / high raster byte */
 __attribute__((constructor)) static void init_sig_ctx(void)
 {
     for (int ch = 0; ch < 2; ch++) for (int l3 = 0; l3 < 2; l3++) for (int nz = 0; nz < 2; nz++) for (int prev = 0; prev < 4; prev++) for (int p = 0; p < 16; p++) {
@@ -344,6 +349,37 @@ __attribute__((constructor)) static void init_sig_ctx(void)
         }
         g_sig_ctx[ch][l3][nz][prev][p] = (uint8_t)(sc + (ch ? 27 : 0));
     }
+    /* scan-ordered copies + the raster->scan bit permutation of a 4x4 group (cg_scan_mask) */
+    scans_init();
+    for (int ch = 0; ch < 2; ch++) for (int l3 = 0; l3 < 2; l3++) for (int nz = 0; nz < 2; nz++) for (int prev = 0; prev < 4; prev++) for (int n = 0; n < 16; n++) {
+        int p = g_scan4[n], yx = (p >> 2) * 4 + (p & 3);
+        g_sig_ctx_scan[ch][l3][nz][prev][n] = g_sig_ctx[ch][l3][nz][prev][yx];
+    }
+    for (int v = 0; v < 256; v++) {
+        uint16_t lo = 0, hi = 0;
+        for (int n = 0; n < 16; n++) {
+            int p = g_scan4[n], r = (p >> 2) * 4 + (p & 3);          /* raster index of scan position n */
+            if (r < 8) { if ((v >> r) & 1) lo |= (uint16_t)(1u << n); }
+            else if ((v >> (r - 8)) & 1) hi |= (uint16_t)(1u << n);
+        }
+        g_r2s_lo[v] = lo; g_r2s_hi[v] = hi;
+    }
+}
+
+/* non-zero mask of one 4x4 coefficient group in SCAN order (bit n = scan position n): raster-order compare mask (SSE2 where available),
+ * then the raster->scan bit permutation through two 256-entry tables */
+static inline uint32_t cg_scan_mask(const int16_t *lv)
+{
+    uint32_t raster;
+#if defined(__SSE2__)
+    const __m128i z = _mm_setzero_si128();
+    const __m128i a = _mm_cmpeq_epi16(_mm_loadu_si128((const __m128i *)lv), z), b = _mm_cmpeq_epi16(_mm_loadu_si128((const __m128i *)(lv + 8)), z);
+    raster = ~(uint32_t)_mm_movemask_epi8(_mm_packs_epi16(a, b)) & 0xffffu;
+#else
+    raster = 0;
+    for (int i = 0; i < 16; i++) raster |= (uint32_t)(lv[i] != 0) << i;
+#endif
+    return (uint32_t)g_r2s_lo[raster & 255] | g_r2s_hi[raster >> 8];
 }
 
 /* ---- 7.3.8.11 residual_coding for one transform block (diagonal scan only: TB >= 8 or inter) ---- */
@@ -412,34 +448,29 @@ static void code_residual(slice_enc *e, int comp, int x0c, int y0c, int log2)
         } else coded = 1;                 /* last and DC CGs are inferred coded */
         csbf[cy][cx] = (uint8_t)coded;
         if (!coded) continue;
-        static const int16_t zero16[16] = {0};
-        const int16_t *lv = present ? (i2 == last_cg ? lastp : CG_PTR(cx, cy)) : zero16;
         int prev = right | (below << 1);
-        const uint8_t *sctx = g_sig_ctx[comp != 0][log2 == 3][(cx | cy) != 0][prev];
+        const uint8_t *sctx = g_sig_ctx_scan[comp != 0][log2 == 3][(cx | cy) != 0][prev];      /* indexed by scan position */
+        const int16_t *lv = NULL;
+        uint32_t nz = 0;                   /* bit n: the coefficient at scan position n of this CG is non-zero */
+        if (present) { lv = i2 == last_cg ? lastp : CG_PTR(cx, cy); nz = cg_scan_mask(lv); }
         int start = i2 == last_cg ? last_pos - 1 : 15;
-        uint16_t sig_mask = i2 == last_cg ? (uint16_t)(1u << last_pos) : 0;
-        for (int n = start; n >= 0; n--) {
-            int p = g_scan4[n], sig = lv[p] != 0;
-            if (n > 0 || !infer_dc) {
-                RBIN(CX_SIG + sctx[p], sig);
-                if (sig) infer_dc = 0;
-            } else sig = 1;               /* inferred DC significance */
-            if (sig) sig_mask |= (uint16_t)(1u << n);
-        }
-        /* greater1 / greater2 / signs / remaining */
+        for (int n = start; n > 0; n--) RBIN(CX_SIG + sctx[n], (nz >> n) & 1);
+        if (start >= 0 && !(infer_dc && !(nz >> 1))) RBIN(CX_SIG + sctx[0], nz & 1);      /* DC flag unless inferred (all others zero in a coded CG) */
+        if (!nz) continue;                 /* inferred-coded CG without levels (only the DC group can be one) */
+        /* greater1 / greater2 / signs / remaining, visiting only the non-zero positions (high scan position first) */
         int ctx_set = (i2 > 0 && comp == 0) ? 2 : 0;
         if (c1 == 0) ctx_set++;
         c1 = 1;
-        int nsig = 0, first_sig = 16, last_sig = -1, first_g1 = -1;
-        int absv[16], pos[16];
-        for (int n = 15; n >= 0; n--) if (sig_mask & (1u << n)) {
-            int v = lv[g_scan4[n]];
-            absv[nsig] = v < 0 ? -v : v; pos[nsig] = n; nsig++;
-            if (last_sig < 0) last_sig = n;
-            first_sig = n;
-        }
+        int nsig = 0, first_g1 = -1;
+        int absv[16];
         uint32_t signs = 0;
-        for (int k = 0; k < nsig; k++) signs = (signs << 1) | (uint32_t)(lv[g_scan4[pos[k]]] < 0);
+        const int last_sig = 31 - __builtin_clz(nz), first_sig = __builtin_ctz(nz);
+        for (uint32_t m = nz; m; ) {
+            const int n = 31 - __builtin_clz(m); m &= ~(1u << n);
+            const int v = lv[g_scan4[n]];
+            absv[nsig++] = v < 0 ? -v : v;
+            signs = (signs << 1) | (uint32_t)(v < 0);
+        }
         int ng1 = nsig < 8 ? nsig : 8;
         for (int k = 0; k < ng1; k++) {
             int g1 = absv[k] > 1;
