@@ -676,6 +676,33 @@ static int cu_cbf_any(const ks_frame_syn *s, int x, int y, int size)
     return any != 0;
 }
 
+/* P slices: merge_idx of the CU's own vector without materialising the candidate list.  A motion is one 32-bit word (mvx | mvy << 16, one
+ * list, one reference), candidates are produced in list order A1, B1, B0, A0, B2, zero... with the 8.5.3.2.3 prunings, and the walk stops at
+ * the first candidate equal to `cur` (typically A1) or when maxc candidates exist.  Same result as merge_list() + search. */
+static inline uint32_t cell_mvw(const ks_cell *c) { uint32_t w; memcpy(&w, &c->mvx, 4); return w; }
+static int merge_idx_p(const ks_frame_syn *s, int x, int y, int size, int maxc, uint32_t cur)
+{
+    int n = 0;
+    uint32_t a1 = 0, b1 = 0, b0 = 0, a0 = 0, b2;
+    int fa1 = 0, ab1 = 0, fb1, fb0 = 0, fa0 = 0, fb2 = 0;
+    if (x > 0) { const ks_cell *c = cell_at(s, x - 1, y + size - 1); if (!(c->flags & KS_F_INTRA)) { fa1 = 1; a1 = cell_mvw(c); } }
+    if (fa1) { if (a1 == cur) return n; if (++n == maxc) return -1; }
+    if (y > 0) { const ks_cell *c = cell_at(s, x + size - 1, y - 1); if (!(c->flags & KS_F_INTRA)) { ab1 = 1; b1 = cell_mvw(c); } }
+    fb1 = ab1 && !(fa1 && a1 == b1);
+    if (fb1) { if (b1 == cur) return n; if (++n == maxc) return -1; }
+    if (avail(s, x, y, x + size, y - 1)) { const ks_cell *c = cell_at(s, x + size, y - 1); if (!(c->flags & KS_F_INTRA)) { fb0 = 1; b0 = cell_mvw(c); } }
+    if (fb0 && ab1 && b1 == b0) fb0 = 0;
+    if (fb0) { if (b0 == cur) return n; if (++n == maxc) return -1; }
+    if (avail(s, x, y, x - 1, y + size)) { const ks_cell *c = cell_at(s, x - 1, y + size); if (!(c->flags & KS_F_INTRA)) { fa0 = 1; a0 = cell_mvw(c); } }
+    if (fa0 && fa1 && a1 == a0) fa0 = 0;
+    if (fa0) { if (a0 == cur) return n; if (++n == maxc) return -1; }
+    if (x > 0 && y > 0 && fa0 + fa1 + fb0 + fb1 != 4) {
+        const ks_cell *c = cell_at(s, x - 1, y - 1);
+        if (!(c->flags & KS_F_INTRA)) { b2 = cell_mvw(c); fb2 = !(fa1 && a1 == b2) && !(ab1 && b1 == b2); if (fb2) { if (b2 == cur) return n; if (++n == maxc) return -1; } }
+    }
+    return cur == 0 ? n : -1;             /* zero candidates fill the rest of the list: the first of them sits at index n */
+}
+
 /* ---- 7.3.8.5 coding_unit ---- */
 static void code_cu(slice_enc *e, int x, int y, int log2)
 {
@@ -686,9 +713,12 @@ static void code_cu(slice_enc *e, int x, int y, int log2)
         motion_t ml[5], cur; nb_set nbs; int merge_idx = -1;
         if (!intra) {
             cur = cell_motion(s, x, y);
-            fetch_nb(s, x, y, size, &nbs);
-            int n = merge_list(s, &nbs, e->sp->max_merge_cand, ml);
-            for (int k = 0; k < n; k++) if (motion_eq(&ml[k], &cur)) { merge_idx = k; break; }
+            if (!s->cells_b) merge_idx = merge_idx_p(s, x, y, size, e->sp->max_merge_cand, cell_mvw(cu));     /* P slice fast path */
+            else {
+                fetch_nb(s, x, y, size, &nbs);
+                int n = merge_list(s, &nbs, e->sp->max_merge_cand, ml);
+                for (int k = 0; k < n; k++) if (motion_eq(&ml[k], &cur)) { merge_idx = k; break; }
+            }
         }
         int any = intra ? 1 : cu_cbf_any(s, x, y, size);
         int skip = !intra && merge_idx >= 0 && !any;
@@ -718,6 +748,7 @@ static void code_cu(slice_enc *e, int x, int y, int log2)
                 if (cur.dir != 3) cb_bin(c, CX_INTER_DIR + 4, cur.dir == 2);
             }
             const int dpoc[2] = {-e->sl->neg_delta_poc[0], -e->sl->pos_delta_poc[0]};
+            if (!s->cells_b) fetch_nb(s, x, y, size, &nbs);      /* the P fast path above did not need the neighbour set */
             for (int X = 0; X < 2; X++) {
                 if (!(cur.dir & (1 << X))) continue;
                 mv_t pl[2]; amvp_list(&nbs, X, dpoc, pl);
