@@ -209,6 +209,8 @@ static void cb_write_out(cabac *c)
  * transition and the renormalisation shift come from tables (g_cb_next / g_cb_shift, built once) */
 static uint8_t g_cb_next[128][2];      /* [(pStateIdx<<1)|valMps][bin] */
 static uint8_t g_cb_shift[64];         /* [range >> 3] -> left shifts until range >= 256 */
+static uint32_t g_cb_lps4[128];        /* [(pStateIdx<<1)|valMps] -> the four rangeTabLps entries as bytes: the load depends on the context only,
+                                          the range then just selects a byte (keeps a memory access out of the bin-to-bin dependency chain) */
 __attribute__((constructor)) static void init_cb_tables(void)
 {
     for (int s = 0; s < 128; s++) for (int bin = 0; bin < 2; bin++) {
@@ -217,11 +219,12 @@ __attribute__((constructor)) static void init_cb_tables(void)
         else g_cb_next[s][bin] = (uint8_t)(((state < 62 ? state + 1 : state) << 1) | mps);
     }
     for (int k = 0; k < 64; k++) { int r = k << 3 | 7, n = 0; while (r < 256) { r <<= 1; n++; } g_cb_shift[k] = (uint8_t)n; }
+    for (int s = 0; s < 128; s++) g_cb_lps4[s] = (uint32_t)range_lps[s >> 1][0] | ((uint32_t)range_lps[s >> 1][1] << 8) | ((uint32_t)range_lps[s >> 1][2] << 16) | ((uint32_t)range_lps[s >> 1][3] << 24);
 }
 static inline void cb_bin(cabac *c, int ctx, int bin)
 {
     uint32_t s = c->ctx[ctx], range = c->range, low = c->low;
-    uint32_t lps = range_lps[s >> 1][(range >> 6) & 3];
+    uint32_t lps = (g_cb_lps4[s] >> ((range >> 3) & 24)) & 255u;
     uint32_t is_lps = 0u - (uint32_t)((uint32_t)bin != (s & 1));
     range -= lps;
     low += range & is_lps;
@@ -402,7 +405,7 @@ static void code_residual(slice_enc *e, int comp, int x0c, int y0c, int log2)
     uint32_t low = c->low, range = c->range; int bl = c->bits_left; uint8_t *ctxs = c->ctx;
 #define RFLUSH() do { c->low = low; c->bits_left = bl; cb_write_out(c); low = c->low; bl = c->bits_left; } while (0)
 #define RBIN(ci, bv) do { \
-        uint32_t s_ = ctxs[ci], b_ = (uint32_t)(bv), l_ = range_lps[s_ >> 1][(range >> 6) & 3], m_ = 0u - (uint32_t)(b_ != (s_ & 1)); \
+        uint32_t s_ = ctxs[ci], b_ = (uint32_t)(bv), l_ = (g_cb_lps4[s_] >> ((range >> 3) & 24)) & 255u, m_ = 0u - (uint32_t)(b_ != (s_ & 1)); \
         range -= l_; low += range & m_; range = (range & ~m_) | (l_ & m_); \
         ctxs[ci] = g_cb_next[s_][b_]; \
         uint32_t n_ = (uint32_t)__builtin_clz(range) - 23u; low <<= n_; range <<= n_; \
