@@ -176,16 +176,17 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    streams = a.streams or max(2, min(16, cores // max(1, a.gpus)))      # measured on a 128-core host: 8 -> host-bound e2e, 24 -> launch contention
+    # shards in flight per GPU, measured on the 64-core/128-thread pool host at N=1 (value / e2e fps): 8 -> e2e host-bound, 16 -> 2625 / 2487,
+    # 24 with sleeping waits -> 2614 / 2601 (with spinning waits 24 shards collapse to 2037 / 1813: the spinners starve the launch threads)
+    streams = a.streams or max(2, min(24, cores // max(1, a.gpus)))
     visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
     nvml_index = int(visible.split(",")[local_rank]) if visible and all(v.strip().isdigit() for v in visible.split(",")) else local_rank
     # opt-in: measured neutral on the 2-socket pool hosts (N=2: value 4403 bound vs 4414 unbound, e2e 3638 vs 3838), profiles/README.md
     numa_cpus, full_mask = bind_to_gpu_numa(nvml_index, 2 * streams) if os.environ.get("KS_NUMA_BIND") == "1" else (0, None)
-    # shard threads that wait for a picture SLEEP (cudaEventBlockingSync) whenever more than one GPU process shares the host: measured at
-    # N=2, 16 shards per GPU: spinning waits 4414 / 3838 fps (value / e2e), blocking waits 5226 / 4440 -- the spinners of one process slow
-    # the launch threads of the other.  A single process is 2 % faster spinning (2493 vs 2445 e2e), so N=1 keeps the default.
-    if world > 1 or 2 * streams > cores:
-        os.environ.setdefault("KS_BLOCKING_SYNC", "1")
+    # shard threads SLEEP while they wait for a picture (cudaEventBlockingSync).  Spinning waits are 2 % faster only for <= 16 shards of ONE
+    # process; beyond that, and whenever several GPU processes share the host, the spinners slow everybody's launch threads
+    # (N=2, 16 shards per GPU: 4414 / 3838 fps spinning vs 5226 / 4440 sleeping).
+    os.environ.setdefault("KS_BLOCKING_SYNC", "1")
 
     # ---- synthetic input: DISTINCT pictures, shard = 128-picture ping-pong sequence; device copy + pinned host copy ----
     frames = [np.frombuffer(fr, np.uint8) for fr in gen_yuv.frames(W, H, DISTINCT, seed=1234)]
