@@ -107,7 +107,7 @@ int main(int argc, char **argv)
     if (me >= 0) a.cfg.me = me > 0;
     a.cfg.rc = rc; if (crf >= 0) a.cfg.crf = crf;
     if (a.gpus < 1) a.gpus = 1; if (a.streams < 1) a.streams = 1;
-    if (a.gpus > 1) setenv("KS_BLOCKING_SYNC", "1", 0);     /* several GPUs fed from one host: waiting shard threads sleep instead of spinning (bench.py has the numbers) */
+    if (a.gpus > 1 || a.streams > 16) setenv("KS_BLOCKING_SYNC", "1", 0);     /* many shard threads: they sleep instead of spinning while they wait (bench.py has the numbers) */
 
     job_t job; memset(&job, 0, sizeof(job));
     job.a = &a; job.fsz = (size_t)a.w * a.h * 3 / 2; pthread_mutex_init(&job.mu, NULL);
