@@ -57,6 +57,8 @@ typedef struct ks_pic_params {
     int dist_anchor;    /* POC(list-1 reference) - POC(list-0 reference); prev_syn_slot names the later anchor, whose vectors
                            (spanning dist_anchor pictures) are scaled to seed both searches */
     int want_me_cost;   /* P pictures: return the sum of the per-cell winning search costs (host rate control's complexity measure) */
+    int lambda_qp_delta;/* >= 0: the CU/merge decision and the RD zero-out of residual blocks use the lambda of QP = qp + delta (the host raises it on
+                           the non-key P pictures of the 4-picture cascade, ks_rc_lambda_qp) */
 } ks_pic_params;
 
 /* results of one picture: pointers into pinned host memory owned by the context, valid until the syntax slot is reused */
@@ -78,8 +80,9 @@ int  ks_gpu_coded_size(const ks_gpu_ctx *ctx, int *width, int *height);
 int  ks_gpu_upload_frame(ks_gpu_ctx *ctx, int slot, const uint8_t *y, const uint8_t *u, const uint8_t *v, int stride_y, int stride_uv);
 /* same, but the I420 picture (display size, tightly packed) already lives in device memory */
 int  ks_gpu_upload_frame_device(ks_gpu_ctx *ctx, int slot, const void *dev_i420);
-/* replaces: IEncTaskManage::executeTasks -> processOneCtu for a whole picture: ME + sub-pel (a1-a7), MC + residual
- * DCT/quant/SBH/dequant/IDCT (a8-a14), deblock (a16), SAO (a17-a20), level packing; starts the D2H of the syntax */
+/* replaces: IEncTaskManage::executeTasks -> processOneCtu for a whole picture: ME + sub-pel (a1-a7), CU quadtree / merge decision
+ * (processTree E@0x46b610), MC + residual DCT/quant/SBH/dequant/IDCT with RD zero-out (a8-a14), deblock (a16), SAO (a17-a20), level packing;
+ * starts the D2H of the syntax */
 int  ks_gpu_encode_picture_submit(ks_gpu_ctx *ctx, const ks_pic_params *pp);
 /* waits for the picture submitted on `syn_slot` and returns its syntax */
 int  ks_gpu_encode_picture_finish(ks_gpu_ctx *ctx, int syn_slot, ks_pic_out *out);
@@ -93,9 +96,12 @@ uint64_t ks_gpu_launch_count(const ks_gpu_ctx *ctx);
 void *ks_gpu_stream(ks_gpu_ctx *ctx);
 
 /* per-stage device timing (CUDA events on the context's stream, accumulated at finish): stage order
- * 0 motion search, 1 inter prediction+residual, 2 intra picture, 3 deblock, 4 SAO, 5 level packing */
+ * 0 motion search, 1 inter prediction+residual, 2 intra picture, 3 deblock, 4 SAO, 5 level packing, 6 CU/merge decision */
+#define KS_NSTAGES 7
 int  ks_gpu_set_profiling(ks_gpu_ctx *ctx, int on);
-int  ks_gpu_get_stage_times(const ks_gpu_ctx *ctx, double ms[6], uint64_t launches[6]);
+int  ks_gpu_get_stage_times(const ks_gpu_ctx *ctx, double ms[KS_NSTAGES], uint64_t launches[KS_NSTAGES]);
+/* drop every picture still in flight (submitted, not finished): waits for the device, clears the pending marks.  For error paths. */
+int  ks_gpu_abort(ks_gpu_ctx *ctx);
 /* bytes copied device->host so far (syntax blocks) */
 uint64_t ks_gpu_d2h_bytes(const ks_gpu_ctx *ctx);
 /* sizeof() of the ABI structs as this library was built (binding self-check: 0 ks_gpu_cfg, 1 ks_pic_params, 2 ks_pic_out, 3 ks_cell,

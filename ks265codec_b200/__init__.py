@@ -37,7 +37,7 @@ class KsGpuCfg(C.Structure):
 
 class KsPicParams(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("slice_type", "qp", "src_slot", "ref_slot", "out_slot", "syn_slot", "prev_syn_slot",
-                                       "beta_offset_div2", "tc_offset_div2", "want_sse", "ref1_slot", "dist_l0", "dist_anchor", "want_me_cost")]
+                                       "beta_offset_div2", "tc_offset_div2", "want_sse", "ref1_slot", "dist_l0", "dist_anchor", "want_me_cost", "lambda_qp_delta")]
 
 
 class KsCellB(C.Structure):
@@ -64,7 +64,7 @@ assert C.sizeof(KsCell) == 8 and C.sizeof(KsCtuSyn) == 72
 
 GPU_SYMBOLS = ["ks_gpu_open", "ks_gpu_close", "ks_gpu_coded_size", "ks_gpu_upload_frame", "ks_gpu_upload_frame_device",
                "ks_gpu_encode_picture_submit", "ks_gpu_encode_picture_finish", "ks_gpu_encode_picture", "ks_gpu_fetch_recon",
-               "ks_gpu_launch_count", "ks_gpu_stream", "ks_gpu_set_profiling", "ks_gpu_get_stage_times", "ks_gpu_d2h_bytes", "ks_gpu_abi_sizeof", "ks_gpu_debug_fetch", "ks_gpu_debug_me", "ks_gpu_kat_sad16", "ks_gpu_kat_satd16",
+               "ks_gpu_launch_count", "ks_gpu_stream", "ks_gpu_set_profiling", "ks_gpu_get_stage_times", "ks_gpu_d2h_bytes", "ks_gpu_abi_sizeof", "ks_gpu_abort", "ks_gpu_debug_fetch", "ks_gpu_debug_me", "ks_gpu_kat_sad16", "ks_gpu_kat_satd16",
                "ks_gpu_kat_interp_luma16", "ks_gpu_kat_tb"]
 ENC_SYMBOLS = ["ks265_config_default_preset", "ks265_preset_index", "ks265_encoder_open", "ks265_encoder_close",
                "ks265_encoder_encode_gop", "ks265_encoder_run_gop_device", "ks265_encoder_set_profiling", "ks265_encoder_get_stage_times"]
@@ -99,6 +99,7 @@ def lib():
     L.ks_gpu_fetch_recon.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     L.ks_gpu_launch_count.restype = C.c_uint64
     L.ks_gpu_launch_count.argtypes = [C.c_void_p]
+    L.ks_gpu_abort.argtypes = [C.c_void_p]
     L.ks_gpu_stream.restype = C.c_void_p
     L.ks_gpu_stream.argtypes = [C.c_void_p]
     L.ks_gpu_debug_fetch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]

@@ -16,7 +16,7 @@ static const int k_lambda_sad_q4[52] = {4,4,5,5,6,7,7,8,9,10,12,13,15,17,19,21,2
 static const int k_lambda_sse_q4[52] = {1,1,1,2,2,3,3,4,5,7,9,11,14,17,22,27,34,43,54,69,86,109,137,173,218,274,345,435,548,691,870,1097,1382,1741,2193,2763,3482,4387,5527,6963,8773,11053,13926,17546,22107,27853,35092,44214,55706,70185,88427,111411};
 static const uint8_t k_chroma_qp[58] = {0,1,2,3,4,5,6,7,8,9,10,11,12,13,14,15,16,17,18,19,20,21,22,23,24,25,26,27,28,29,29,30,31,32,33,33,34,34,35,35,36,36,37,37,38,39,40,41,42,43,44,45,46,47,48,49,50,51};
 
-#define KS_NSTAGE 6   /* me, recon_inter, recon_intra, deblock, sao, pack */
+#define KS_NSTAGE KS_NSTAGES   /* me, recon_inter, recon_intra, deblock, sao, pack, decide */
 struct ks_syn_slot {
     ks_cell *d_cells; ks_ctu_syn *d_ctus; int16_t *d_pool; uint32_t *d_ncg; unsigned long long *d_sse, *d_mecost; ks_cell_b *d_cells_b;
     ks_cell_b *h_cells_b; int is_b;
@@ -38,7 +38,7 @@ struct ks_gpu_ctx {
     int tma_mask;               /* bit c: plane c qualifies (pitch multiple of 16 bytes) */
     uint8_t *d_pred;            /* inter prediction planes written by the motion search */
     uint8_t *d_pred1;           /* B pictures: list-1 prediction planes */
-    ks_cell *d_cells1; int *d_cost0, *d_cost1;
+    ks_cell *d_cells1; int *d_cost0, *d_cost1;   /* d_cells1: list-1 field (B) / search field before the CU decision (P); d_cost0 doubles as its distortions */
     int16_t *d_lev;
     uint32_t *d_counts;
     int *d_sync;
@@ -104,7 +104,7 @@ extern "C" ks_gpu_ctx *ks_gpu_open(int device, int width, int height, const ks_g
     if (c->cfg.n_rec_slots < 2) c->cfg.n_rec_slots = 2;
     if (c->cfg.n_syn_slots < 2) c->cfg.n_syn_slots = 2;
     c->fsz = (size_t)c->W * c->H * 3 / 2;
-    ks_upload_tables();
+    if (ks_init_device(device)) { e = KS_ECUDA; goto fail; }
     if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) { e = KS_ECUDA; goto fail; }
     if (cudaStreamCreateWithFlags(&c->st_up, cudaStreamNonBlocking) != cudaSuccess) { e = KS_ECUDA; goto fail; }
     c->ev_up = (cudaEvent_t *)calloc(c->cfg.n_src_slots, sizeof(cudaEvent_t));
@@ -206,7 +206,7 @@ extern "C" int ks_gpu_set_profiling(ks_gpu_ctx *c, int on)
     for (int k = 0; k < KS_NSTAGE; k++) { c->stage_ms[k] = 0; c->stage_n[k] = 0; }
     return 0;
 }
-extern "C" int ks_gpu_get_stage_times(const ks_gpu_ctx *c, double ms[6], uint64_t n[6])
+extern "C" int ks_gpu_get_stage_times(const ks_gpu_ctx *c, double ms[KS_NSTAGES], uint64_t n[KS_NSTAGES])
 {
     if (!c) return KS_EINVAL;
     for (int k = 0; k < KS_NSTAGE; k++) { ms[k] = c->stage_ms[k]; n[k] = c->stage_n[k]; }
@@ -283,6 +283,9 @@ static int fill_params(const ks_gpu_ctx *c, const ks_pic_params *p, KsPicParams 
     pp->W = c->W; pp->H = c->H; pp->cw = c->cw; pp->ch = c->ch; pp->ctw = c->ctw; pp->cth = c->cth;
     pp->slice_type = p->slice_type; pp->qp = p->qp; pp->qpc = k_chroma_qp[p->qp];
     pp->lambda_sad_q4 = k_lambda_sad_q4[p->qp]; pp->lambda_sse_q4 = k_lambda_sse_q4[p->qp];
+    if (p->lambda_qp_delta < 0) return KS_EINVAL;
+    { const int lqp = p->qp + p->lambda_qp_delta > 51 ? 51 : p->qp + p->lambda_qp_delta;
+      pp->lambda_dec_q4 = k_lambda_sad_q4[lqp]; pp->rdz_lambda_q4 = p->slice_type == KS_SLICE_I ? 0 : k_lambda_sse_q4[lqp]; }
     pp->me_range = c->cfg.me_range; pp->me_iters = c->cfg.me_iters; pp->subpel = c->cfg.subpel; pp->satd = c->cfg.satd; pp->me_method = c->cfg.me_method;
     pp->sign_hiding = c->cfg.sign_hiding; pp->sao = c->cfg.sao; pp->strong_intra = c->cfg.strong_intra;
     pp->beta_offset_div2 = p->beta_offset_div2; pp->tc_offset_div2 = p->tc_offset_div2;
@@ -317,15 +320,18 @@ extern "C" int ks_gpu_encode_picture_submit(ks_gpu_ctx *c, const ks_pic_params *
             KsPlanes ref1 = planes_of(c, c->d_rec[p->ref1_slot]), pred1 = planes_of(c, c->d_pred1);
             KsPicParams p0 = pp, p1 = pp;
             p0.pred_num = p->dist_l0; p0.pred_den = p->dist_anchor; p1.pred_num = p->dist_l0 - p->dist_anchor; p1.pred_den = p->dist_anchor;
-            ks_launch_me(p0, src.p[0], ref, prev, s->d_cells, pred, c->d_cost0, NULL, c->st);
-            ks_launch_me(p1, src.p[0], ref1, prev, c->d_cells1, pred1, c->d_cost1, NULL, c->st);
+            ks_launch_me(p0, src.p[0], ref, prev, s->d_cells, pred, c->d_cost0, NULL, NULL, c->st);
+            ks_launch_me(p1, src.p[0], ref1, prev, c->d_cells1, pred1, c->d_cost1, NULL, NULL, c->st);
             ks_launch_bidir(pp, src.p[0], ref, ref1, prev, p0.pred_num, p1.pred_num, p->dist_anchor, c->d_cells1, c->d_cost0, c->d_cost1, pred1, s->d_cells, s->d_cells_b, pred, c->st);
             c->launches += 2 * KS_LAUNCHES_ME + 1;
             cb = s->d_cells_b;
         } else {
             const bool mc = p->want_me_cost != 0;
             if (mc) CK(cudaMemsetAsync(s->d_mecost, 0, sizeof(unsigned long long), c->st));
-            ks_launch_me(pp, src.p[0], ref, prev, s->d_cells, pred, NULL, mc ? s->d_mecost : NULL, c->st); c->launches += KS_LAUNCHES_ME;
+            /* search field -> d_cells1 (+ distortions), then the CU quadtree / merge decision writes the final cells */
+            ks_launch_me(pp, src.p[0], ref, prev, c->d_cells1, pred, NULL, c->d_cost0, mc ? s->d_mecost : NULL, c->st); c->launches += KS_LAUNCHES_ME;
+            MARK(6);
+            ks_launch_decide(pp, src.p[0], ref, c->d_cells1, c->d_cost0, s->d_cells, pred, c->st); c->launches += KS_LAUNCHES_DECIDE;
         }
         MARK(1);
         ks_launch_recon_inter(pp, src, pred, pre, lv, s->d_cells, cb, c->st); c->launches += KS_LAUNCHES_RECON;
@@ -383,6 +389,15 @@ extern "C" int ks_gpu_encode_picture_finish(ks_gpu_ctx *c, int syn_slot, ks_pic_
     out->cells_b = s->is_b ? s->h_cells_b : NULL;
     return 0;
 }
+extern "C" int ks_gpu_abort(ks_gpu_ctx *c)
+{
+    if (!c) return KS_EINVAL;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->st_up));
+    CK(cudaStreamSynchronize(c->st));
+    for (int i = 0; i < c->cfg.n_syn_slots; i++) c->syn[i].pending = 0;
+    return 0;
+}
 extern "C" int ks_gpu_encode_picture(ks_gpu_ctx *c, const ks_pic_params *p, ks_pic_out *out)
 {
     int r = ks_gpu_encode_picture_submit(c, p);
@@ -428,7 +443,7 @@ extern "C" int ks_gpu_debug_me(ks_gpu_ctx *c, const ks_pic_params *p, ks_cell *c
     const ks_cell *prev = p->prev_syn_slot >= 0 ? c->syn[p->prev_syn_slot].d_cells : NULL;
     KsPlanes nopred; nopred.p[0] = nopred.p[1] = nopred.p[2] = NULL;
     CK(cudaStreamWaitEvent(c->st, c->ev_up[p->src_slot], 0));
-    ks_launch_me(pp, src.p[0], ref, prev, s->d_cells, nopred, NULL, NULL, c->st); c->launches += KS_LAUNCHES_ME;
+    ks_launch_me(pp, src.p[0], ref, prev, s->d_cells, nopred, NULL, NULL, NULL, c->st); c->launches += KS_LAUNCHES_ME;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(cells_out, s->d_cells, (size_t)c->cw * c->ch * sizeof(ks_cell), cudaMemcpyDeviceToHost, c->st));
     CK(cudaStreamSynchronize(c->st));
@@ -442,7 +457,7 @@ template <typename T> struct dev_buf {
 extern "C" int ks_gpu_kat_sad16(const uint8_t *a, const uint8_t *b, long sa, long sb, uint32_t *out)
 {
     int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return KS_ENODEV;
-    ks_upload_tables();
+    if (ks_init_device(-1)) return KS_ECUDA;
     uint8_t ha[256], hb[256];
     for (int y = 0; y < 16; y++) { memcpy(ha + 16 * y, a + y * sa, 16); memcpy(hb + 16 * y, b + y * sb, 16); }
     dev_buf<uint8_t> da(256), db(256); dev_buf<uint32_t> dout(1);
@@ -468,7 +483,7 @@ extern "C" int ks_gpu_kat_interp_luma16(const uint8_t *plane, int w, int h, int 
 {
     int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return KS_ENODEV;
     if ((w & 3) || w < 16 || h < 16) return KS_EINVAL;
-    ks_upload_tables();
+    if (ks_init_device(-1)) return KS_ECUDA;
     dev_buf<uint8_t> dp((size_t)w * h), dd(256);
     if (!dp.p || !dd.p) return KS_ENOMEM;
     CK(cudaMemcpy(dp.p, plane, (size_t)w * h, cudaMemcpyHostToDevice));
@@ -481,7 +496,7 @@ extern "C" int ks_gpu_kat_tb(int log2n, const uint8_t *src, const uint8_t *pred,
 {
     int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return KS_ENODEV;
     if (log2n < 3 || log2n > 5 || qp < 0 || qp > 51) return KS_EINVAL;
-    ks_upload_tables();
+    if (ks_init_device(-1)) return KS_ECUDA;
     size_t nn = (size_t)1 << (2 * log2n);
     dev_buf<uint8_t> ds(nn), dp(nn), dr(nn); dev_buf<int16_t> dl(nn); dev_buf<int> dc(1);
     if (!ds.p || !dp.p || !dr.p || !dl.p || !dc.p) return KS_ENOMEM;

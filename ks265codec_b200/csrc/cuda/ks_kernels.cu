@@ -4,12 +4,34 @@
  */
 #include "ks_common.cuh"
 #include "ks_me.cuh"
+#include "ks_decide.cuh"
 #include "ks_recon.cuh"
 #include "ks_loopfilter.cuh"
 #include "ks_pack.cuh"
 #include "ks_kat.h"
 
-void ks_upload_tables() { ks_upload_tables_impl(); }
+#include <cstdio>
+#include <mutex>
+int ks_init_device(int device)
+{
+    static std::mutex mu;
+    static bool done[64];
+    std::lock_guard<std::mutex> lock(mu);
+    if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return -1;
+    if (device >= 64) return -1;
+    if (done[device]) return 0;
+    if (cudaSetDevice(device) != cudaSuccess) return -1;
+    ks_upload_tables_impl();
+    bool ok = true;
+    ok = ok && cudaFuncSetAttribute(ks_recon_inter_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsReconSmem)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(ks_recon_inter_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsReconSmem)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(ks_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsDecideSmem)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(ks_sao_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsSaoSmem) + 128) == cudaSuccess;
+    ok = ok && cudaDeviceSynchronize() == cudaSuccess;
+    if (!ok) { fprintf(stderr, "ks265gpu: device %d initialisation failed: %s\n", device, cudaGetErrorString(cudaGetLastError())); return -1; }
+    done[device] = true;
+    return 0;
+}
 
 /* ------------------------------------------------------------------ KAT kernels ------------------ */
 __global__ void ks_kat_sad16_kernel(const uint8_t *a, const uint8_t *b16, uint32_t *out)

@@ -445,8 +445,6 @@ ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_s
 void ks_launch_sao(const KsPicParams &pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_syn *ctus, unsigned long long *sse_out,
                    const CUtensorMap *tm, int tma_mask, cudaStream_t st)
 {
-    static bool attr_done = false;
-    if (!attr_done) { cudaFuncSetAttribute(ks_sao_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsSaoSmem) + 128); attr_done = true; }
     alignas(64) CUtensorMap m[3];                   /* the caller's copy may sit at any alignment */
     memcpy(m, tm, sizeof(m));
     ks_sao_kernel<<<dim3(pp.ctw, pp.cth), KS_SAO_WARPS * KS_WARP, sizeof(KsSaoSmem) + 128, st>>>(pp, src, deb, out, ctus, sse_out, m[0], m[1], m[2], tma_mask);

@@ -398,7 +398,7 @@ __device__ __forceinline__ void ks_mc_chroma8(uint8_t *cwin, int16_t *tmp, const
 template <int METHOD, bool SATD>
 __global__ void __launch_bounds__(KS_ME_WARPS * KS_WARP, 4)
 ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref, const ks_cell *__restrict__ prev_cells,
-             ks_cell *__restrict__ cells, KsPlanes pred, int *__restrict__ costs, unsigned long long *__restrict__ cost_sum)
+             ks_cell *__restrict__ cells, KsPlanes pred, int *__restrict__ costs, int *__restrict__ dists, unsigned long long *__restrict__ cost_sum)
 {
     __shared__ __align__(16) KsWarpScratch scratch[KS_ME_WARPS];
     __shared__ uint8_t cwins[KS_ME_WARPS][144];
@@ -563,11 +563,13 @@ ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref, con
         }
 #undef KS_SUBCOST
     }
+    const int dist = bc - MVCOST(mx, my);
 #undef MVCOST
     if (lane == 0) {
         ks_cell c; c.mvx = (int16_t)mx; c.mvy = (int16_t)my; c.cu_log2 = 4; c.flags = 0; c.intra_mode = 0; c.rsv = 0;
         cells[cell] = c;
         if (costs) costs[cell] = bc;
+        if (dists) dists[cell] = dist;
         if (cost_sum) atomicAdd(cost_sum, (unsigned long long)bc);      /* integer sum: order-independent */
     }
     /* ---- the search already holds the winner's luma prediction: emit it (and the chroma prediction for the same vector) so
@@ -583,16 +585,16 @@ ks_me_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref, con
     }
 }
 
-void ks_launch_me(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref, const ks_cell *prev_cells, ks_cell *cells, KsPlanes pred, int *costs, unsigned long long *cost_sum, cudaStream_t st)
+void ks_launch_me(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref, const ks_cell *prev_cells, ks_cell *cells, KsPlanes pred, int *costs, int *dists, unsigned long long *cost_sum, cudaStream_t st)
 {
     const int ncell = pp.cw * pp.ch;
     const dim3 grid((ncell + KS_ME_WARPS - 1) / KS_ME_WARPS), block(KS_ME_WARPS * KS_WARP);
     if (pp.me_method == 0) {
-        if (pp.satd) ks_me_kernel<0, true><<<grid, block, 0, st>>>(pp, srcY, ref, prev_cells, cells, pred, costs, cost_sum);
-        else ks_me_kernel<0, false><<<grid, block, 0, st>>>(pp, srcY, ref, prev_cells, cells, pred, costs, cost_sum);
+        if (pp.satd) ks_me_kernel<0, true><<<grid, block, 0, st>>>(pp, srcY, ref, prev_cells, cells, pred, costs, dists, cost_sum);
+        else ks_me_kernel<0, false><<<grid, block, 0, st>>>(pp, srcY, ref, prev_cells, cells, pred, costs, dists, cost_sum);
     } else {
-        if (pp.satd) ks_me_kernel<1, true><<<grid, block, 0, st>>>(pp, srcY, ref, prev_cells, cells, pred, costs, cost_sum);
-        else ks_me_kernel<1, false><<<grid, block, 0, st>>>(pp, srcY, ref, prev_cells, cells, pred, costs, cost_sum);
+        if (pp.satd) ks_me_kernel<1, true><<<grid, block, 0, st>>>(pp, srcY, ref, prev_cells, cells, pred, costs, dists, cost_sum);
+        else ks_me_kernel<1, false><<<grid, block, 0, st>>>(pp, srcY, ref, prev_cells, cells, pred, costs, dists, cost_sum);
     }
 }
 

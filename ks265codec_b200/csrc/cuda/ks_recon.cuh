@@ -74,13 +74,16 @@ __device__ __noinline__ void ks_sbh_cg(const int16_t *C, int16_t *L, const int16
  *   rec_row : global pointer to row r of the lane's reconstruction
  *   lev_row : global pointer to row r of the lane's level block (dense int16 plane)
  *   t0      : shared 16x16 int table, t0[j][x] = M32[2j+1][x] (level-0 odd part of the 32-point butterflies)
+ *   rdz_lambda_q4 > 0: RD zero-out (our restatement of the reference's zero-block decisions in tuDecision E@0x47e2f0 / skipFastDecision
+ *             E@0x47f720): the block's levels are dropped when SSE(src,pred) <= SSE(src,rec) + lambda * bits, bits estimated as
+ *             3 per level + 2 per magnitude doubling + 4 per coded 4x4 group + the anti-diagonal of the outermost level (== ora level_bits_est)
  * returns, per lane, whether the lane's block has any non-zero level (cbf).
  */
 template <int N>
 __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, const int *t0, bool valid,
                                         const uint8_t *__restrict__ src_row, const uint8_t *pred_row,
                                         uint8_t *__restrict__ rec_row, int16_t *__restrict__ lev_row,
-                                        int qp, int intra_slice, int sign_hiding, int lane)
+                                        int qp, int intra_slice, int sign_hiding, int lane, int rdz_lambda_q4 = 0)
 {
     constexpr int LOG2 = KsLog2<N>::v, G = 32 / N, SP = N + 8;
     const int g = lane / N, r = lane % N;
@@ -150,11 +153,6 @@ __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, c
         }
     }
     __syncwarp();
-    /* f. store the level row (dense plane) */
-    if (valid) {
-#pragma unroll
-        for (int x = 0; x < N; x += 8) *reinterpret_cast<uint4 *>(lev_row + x) = *reinterpret_cast<const uint4 *>(&L[r * N + x]);
-    }
     /* g. reconstruction */
     if (nzb) {
         const int shift = LOG2 - 1, dq = c_inv_quant_scales[qp % 6] << (qp / 6), rnd = 1 << (shift - 1);
@@ -169,8 +167,46 @@ __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, c
         ks_inv_pass<N>([&](int k) { return (int)S[r * SP + k]; }, t, 12, false, t0);
 #pragma unroll
         for (int x = 0; x < N; x++) pred[x] = (uint8_t)ks_clip8((int)pred[x] + t[x]);
+        if (rdz_lambda_q4) {
+            /* h. RD zero-out: per-block sums over the N lanes of the group (xor butterflies stay inside the aligned group) */
+            int nnz = 0, slog = 0, maxd = 0, d0 = 0, d1 = 0; unsigned cgm = 0;
+#pragma unroll
+            for (int x = 0; x < N; x += 4) {
+                const uint2 l4 = *reinterpret_cast<const uint2 *>(&L[r * N + x]);
+                const uint32_t p4 = *reinterpret_cast<const uint32_t *>(pred_row + x);
+                const uint32_t s4 = valid ? __ldg(reinterpret_cast<const uint32_t *>(src_row + x)) : p4;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int l = (int)(short)(((b & 2) ? l4.y : l4.x) >> (16 * (b & 1))), a = abs(l);
+                    if (a) { nnz++; slog += 31 - __clz(a); maxd = max(maxd, x + b + r); cgm |= 1u << (x >> 2); }
+                    const int sv = (int)((s4 >> (8 * b)) & 255), e0 = sv - (int)((p4 >> (8 * b)) & 255), e1 = valid ? sv - (int)pred[x + b] : 0;
+                    d0 += e0 * e0; d1 += e1 * e1;
+                }
+            }
+            cgm |= __shfl_xor_sync(0xffffffffu, cgm, 1); cgm |= __shfl_xor_sync(0xffffffffu, cgm, 2);
+            int ncg = (r & 3) == 0 ? __popc(cgm) : 0;
+#pragma unroll
+            for (int o = 1; o < N; o <<= 1) {
+                nnz += __shfl_xor_sync(0xffffffffu, nnz, o); slog += __shfl_xor_sync(0xffffffffu, slog, o); ncg += __shfl_xor_sync(0xffffffffu, ncg, o);
+                d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
+            }
+            const int bits = 3 * nnz + 2 * slog + 4 * ncg + maxd;
+            if (nnz && (long long)d0 * 16 <= (long long)d1 * 16 + (long long)rdz_lambda_q4 * bits) {
+                cbf = false;
+#pragma unroll
+                for (int x = 0; x < N; x += 4) {
+                    *reinterpret_cast<uint2 *>(&L[r * N + x]) = make_uint2(0u, 0u);
+                    const uint32_t p4 = *reinterpret_cast<const uint32_t *>(pred_row + x);
+#pragma unroll
+                    for (int b = 0; b < 4; b++) pred[x + b] = (uint8_t)(p4 >> (8 * b));
+                }
+            }
+        }
     }
+    /* f. store the level row (dense plane) and the reconstruction */
     if (valid) {
+#pragma unroll
+        for (int x = 0; x < N; x += 8) *reinterpret_cast<uint4 *>(lev_row + x) = *reinterpret_cast<const uint4 *>(&L[r * N + x]);
 #pragma unroll
         for (int x = 0; x < N; x += 4)
             *reinterpret_cast<uint32_t *>(rec_row + x) = (uint32_t)pred[x] | ((uint32_t)pred[x + 1] << 8) | ((uint32_t)pred[x + 2] << 16) | ((uint32_t)pred[x + 3] << 24);
@@ -189,6 +225,7 @@ struct KsReconSmem {
     int      m1[16];                           /* B pictures: list-1 vector (x | y << 16) and direction folded into one word pair */
     uint8_t  dirv[16];
     uint8_t  valid[16];
+    uint8_t  clog2[16];                        /* P pictures: CU size chosen by ks_decide_kernel */
     unsigned cbf[16];                          /* KS_F_CBF_* bits per cell, OR-ed by the transform tasks */
 };
 __device__ __forceinline__ const uint16_t *ks_scan_ptr(const KsReconSmem *sm, int n) { return sm->scan + (n == 8 ? 0 : (n == 16 ? 64 : 320)); }
@@ -215,19 +252,20 @@ ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes pred, KsPlanes rec,
         int cx = tid & 3, cy = tid >> 2, x = X0 + (cx << 4), y = Y0 + (cy << 4);
         bool v = x < W && y < H;
         sm->valid[tid] = v; sm->cbf[tid] = 0;
-        sm->m1[tid] = 0; sm->dirv[tid] = 1;
+        sm->m1[tid] = 0; sm->dirv[tid] = 1; sm->clog2[tid] = 4;
         if (v) {
-            ks_cell c = cells[(y >> 4) * pp.cw + (x >> 4)]; sm->mvx[tid] = c.mvx; sm->mvy[tid] = c.mvy;
+            ks_cell c = cells[(y >> 4) * pp.cw + (x >> 4)]; sm->mvx[tid] = c.mvx; sm->mvy[tid] = c.mvy; sm->clog2[tid] = c.cu_log2;
             if (cells_b) { ks_cell_b b = cells_b[(y >> 4) * pp.cw + (x >> 4)]; sm->m1[tid] = (int)(uint16_t)b.mvx1 | ((int)b.mvy1 << 16); sm->dirv[tid] = b.dir; }
         } else { sm->mvx[tid] = 0; sm->mvy[tid] = 0; }
     }
     __syncthreads();
-    /* CU size: four equal-MV siblings merge upward (16 -> 32 -> 64), mirror of ora_inter_picture step 2.
-     * Every thread derives the same flags from shared memory: no serial section, no task list. */
+    /* CU size.  P pictures: decided by ks_decide_kernel (cu_log2 of the cells).  B pictures: four siblings with equal motion merge upward
+     * (16 -> 32 -> 64), mirror of ora_b_picture.  Every thread derives the same flags from shared memory: no serial section, no task list. */
     bool q32[4], c64 = true;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
         const int b0 = (q & 1) * 2 + (q >> 1) * 8;
+        if (!cells_b) { q32[q] = sm->valid[b0] && sm->clog2[b0] >= 5; c64 = c64 && q32[q] && sm->clog2[b0] == 6; continue; }
         bool ok = sm->valid[b0] && sm->valid[b0 + 1] && sm->valid[b0 + 4] && sm->valid[b0 + 5];
         const int mx = sm->mvx[b0], my = sm->mvy[b0], m1 = sm->m1[b0], dr = sm->dirv[b0];
         ok = ok && sm->mvx[b0 + 1] == mx && sm->mvx[b0 + 4] == mx && sm->mvx[b0 + 5] == mx
@@ -251,7 +289,7 @@ ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes pred, KsPlanes rec,
             if (k == 0) {
                 int r = lane, x = X0 + qx, y = Y0 + qy + r;
                 bool cbf = ks_tb_code<32>(ts, ks_scan_ptr(sm, 32), sm->t0, true, src.p[0] + (size_t)y * W + x, pred.p[0] + (size_t)y * W + x,
-                                          rec.p[0] + (size_t)y * W + x, lv.p[0] + (size_t)y * W + x, pp.qp, 0, pp.sign_hiding, lane);
+                                          rec.p[0] + (size_t)y * W + x, lv.p[0] + (size_t)y * W + x, pp.qp, 0, pp.sign_hiding, lane, pp.rdz_lambda_q4);
                 if (lane == 0 && cbf) { atomicOr(&sm->cbf[b0], KS_F_CBF_Y); atomicOr(&sm->cbf[b0 + 1], KS_F_CBF_Y); atomicOr(&sm->cbf[b0 + 4], KS_F_CBF_Y); atomicOr(&sm->cbf[b0 + 5], KS_F_CBF_Y); }
             } else if (k == 1) {
                 int g = lane >> 4, r = lane & 15, x = (X0 + qx) >> 1, y = ((Y0 + qy) >> 1) + r;
@@ -265,7 +303,7 @@ ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes pred, KsPlanes rec,
             bool v = sm->valid[cidx];
             int lx = qx + (kc & 1) * 16, ly = qy + (kc >> 1) * 16 + r, x = X0 + lx, y = Y0 + ly;
             bool cbf = ks_tb_code<16>(ts, ks_scan_ptr(sm, 16), sm->t0, v, src.p[0] + (size_t)y * W + x, pred.p[0] + (size_t)(v ? y : Y0) * W + (v ? x : X0),
-                                      rec.p[0] + (size_t)y * W + x, lv.p[0] + (size_t)y * W + x, pp.qp, 0, pp.sign_hiding, lane);
+                                      rec.p[0] + (size_t)y * W + x, lv.p[0] + (size_t)y * W + x, pp.qp, 0, pp.sign_hiding, lane, pp.rdz_lambda_q4);
             if (r == 0 && cbf) atomicOr(&sm->cbf[cidx], KS_F_CBF_Y);
         } else {
             int g = lane >> 3, r = lane & 7, kc = g, ci = k - 2;
@@ -287,13 +325,7 @@ ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes pred, KsPlanes rec,
 
 void ks_launch_recon_inter(const KsPicParams &pp, KsPlanes src, KsPlanes pred, KsPlanes rec, KsLevels lv, ks_cell *cells, const ks_cell_b *cells_b, cudaStream_t st)
 {
-    static bool attr_done = false;
     static const int minb = getenv("KS_RECON_MINB") ? atoi(getenv("KS_RECON_MINB")) : 4;       /* tuning knob: 4 (128 registers) or 5 (102) CTAs per SM */
-    if (!attr_done) {
-        cudaFuncSetAttribute(ks_recon_inter_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsReconSmem));
-        cudaFuncSetAttribute(ks_recon_inter_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsReconSmem));
-        attr_done = true;
-    }
     dim3 grid(pp.ctw, pp.cth);
     if (minb >= 5) ks_recon_inter_kernel<5><<<grid, KS_RECON_WARPS * KS_WARP, sizeof(KsReconSmem), st>>>(pp, src, pred, rec, lv, cells, cells_b);
     else ks_recon_inter_kernel<4><<<grid, KS_RECON_WARPS * KS_WARP, sizeof(KsReconSmem), st>>>(pp, src, pred, rec, lv, cells, cells_b);

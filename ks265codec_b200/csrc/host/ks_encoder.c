@@ -149,12 +149,13 @@ static long encode_gop_impl(ks265_encoder *enc, const uint8_t *frames, const voi
     ks_rc rc;                          /* one rate-control state per closed-GOP shard: shards stay independent */
     if (ks_rc_init(&rc, enc->cfg.rc, enc->cfg.qp, enc->cfg.fixqp, enc->cfg.crf, (enc->W >> 4) * (enc->H >> 4), enc->cfg.bframes)) { free(cp); return -22; }
     cp[0].pp.qp = ks_rc_picture_qp(&rc, cp[0].type, cp[0].disp);
+    cp[0].pp.lambda_qp_delta = ks_rc_lambda_qp(&rc, cp[0].type, cp[0].disp, cp[0].pp.qp) - cp[0].pp.qp;
     if (bs) {
         if ((n = ks_write_vps(sp, bs + pos, cap - pos)) < 0) { free(cp); return -28; } pos += n;
         if ((n = ks_write_sps(sp, bs + pos, cap - pos)) < 0) { free(cp); return -28; } pos += n;
         if ((n = ks_write_pps(sp, bs + pos, cap - pos)) < 0) { free(cp); return -28; } pos += n;
     }
-#define FAIL(code) do { free(cp); return (code); } while (0)
+#define FAIL(code) do { ks_gpu_abort(enc->gpu); free(cp); return (code); } while (0)      /* pictures still in flight are dropped: the handle stays usable */
     if ((r = upload(enc, cp[0].pp.src_slot, cp[0].disp, frames, frames_dev))) FAIL(r);
     if ((r = ks_gpu_encode_picture_submit(enc->gpu, &cp[0].pp))) FAIL(r);
     for (int i = 0; i < cnt; i++) {
@@ -165,6 +166,7 @@ static long encode_gop_impl(ks265_encoder *enc, const uint8_t *frames, const voi
         ks_rc_update(&rc, cp[i].type, out.me_cost);
         if (i + 1 < cnt) {
             cp[i + 1].pp.qp = ks_rc_picture_qp(&rc, cp[i + 1].type, cp[i + 1].disp);
+            cp[i + 1].pp.lambda_qp_delta = ks_rc_lambda_qp(&rc, cp[i + 1].type, cp[i + 1].disp, cp[i + 1].pp.qp) - cp[i + 1].pp.qp;
             if ((r = ks_gpu_encode_picture_submit(enc->gpu, &cp[i + 1].pp))) FAIL(r);
         }
         cg += out.n_cg;
@@ -210,4 +212,4 @@ long ks265_encoder_run_gop_device(ks265_encoder *enc, const void *frames_dev, in
 }
 
 int ks265_encoder_set_profiling(ks265_encoder *enc, int on) { return enc ? ks_gpu_set_profiling(enc->gpu, on) : -22; }
-int ks265_encoder_get_stage_times(ks265_encoder *enc, double ms[6], uint64_t launches[6]) { return enc ? ks_gpu_get_stage_times(enc->gpu, ms, launches) : -22; }
+int ks265_encoder_get_stage_times(ks265_encoder *enc, double ms[KS_NSTAGES], uint64_t launches[KS_NSTAGES]) { return enc ? ks_gpu_get_stage_times(enc->gpu, ms, launches) : -22; }

@@ -47,6 +47,15 @@ int ks_rc_picture_qp(const ks_rc *rc, int slice_type, int poc)
     return clip_qp(rc, (int)floor(q + 0.5));
 }
 
+/* The QP whose lambda drives the device's CU/merge decision and RD zero-out.  P-only streams: the three pictures between two
+ * better-quality anchors of the 4-picture cascade decide with the lambda of QP+3 (twice the Lagrangian; HM's low-delay configuration scales
+ * lambda by 2..4 on exactly those pictures, and the reference's per-picture sizes and PSNRs at -bframes 0 show the same pattern [probe]). */
+int ks_rc_lambda_qp(const ks_rc *rc, int slice_type, int poc, int qp)
+{
+    int d = (slice_type == KS_SLICE_P && !rc->bframes && !rc->fixqp && (poc & 3)) ? 3 : 0;
+    return qp + d > 51 ? 51 : qp + d;
+}
+
 void ks_rc_update(ks_rc *rc, int slice_type, uint64_t me_cost)
 {
     if (rc->mode != 3 || slice_type != KS_SLICE_P) return;

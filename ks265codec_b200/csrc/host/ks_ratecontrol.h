@@ -27,6 +27,8 @@ typedef struct ks_rc {
 int  ks_rc_init(ks_rc *rc, int mode, int qp, int fixqp, double crf, int cells, int bframes);
 /* QP of the next picture to be coded (poc = display index inside the shard), given everything fed to ks_rc_update so far */
 int  ks_rc_picture_qp(const ks_rc *rc, int slice_type, int poc);
+/* QP whose lambda the device's mode decision / RD zero-out use for this picture (ks_pic_params.lambda_qp), >= qp */
+int  ks_rc_lambda_qp(const ks_rc *rc, int slice_type, int poc, int qp);
 /* feed a finished picture: me_cost = ks_pic_out.me_cost (0 for I and B pictures, which do not update the model) */
 void ks_rc_update(ks_rc *rc, int slice_type, uint64_t me_cost);
 

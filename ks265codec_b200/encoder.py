@@ -75,13 +75,13 @@ class Encoder:
             raise RuntimeError("ks265_encoder_run_gop_device failed: %d" % r)
         return st
 
-    STAGES = ("me", "recon_inter", "recon_intra", "deblock", "sao", "pack")
+    STAGES = ("me", "recon_inter", "recon_intra", "deblock", "sao", "pack", "decide")
 
     def set_profiling(self, on=True):
         self._lib.ks265_encoder_set_profiling(self._h, int(on))
 
     def stage_times(self):
         """{stage: (total ms, launches of the stage)} measured with CUDA events on the encoder's stream"""
-        ms = (C.c_double * 6)(); n = (C.c_uint64 * 6)()
+        ms = (C.c_double * len(self.STAGES))(); n = (C.c_uint64 * len(self.STAGES))()
         self._lib.ks265_encoder_get_stage_times(self._h, ms, n)
         return {k: (ms[i], int(n[i])) for i, k in enumerate(self.STAGES)}

@@ -16,7 +16,7 @@ static void pic_to_flat(const ora_pic *p, uint8_t *flat)
 }
 /* one picture through the model.  ref/prev_cells NULL for I pictures.  outputs (any may be NULL):
  * pre (pre-filter reconstruction), fin (final), cells, lev (dense levels Y,U,V), ctus, pool; returns n_cg or <0 */
-long ora_run_picture(const ora_cfg *cfg, int slice_type, int qp, int beta_off, int tc_off,
+long ora_run_picture(const ora_cfg *cfg, int slice_type, int qp, int lambda_qp, int beta_off, int tc_off,
                      const uint8_t *src, const uint8_t *ref, const ks_cell *prev_cells,
                      uint8_t *pre_out, uint8_t *fin_out, ks_cell *cells_out, int16_t *lev_out, ks_ctu_syn *ctus_out, int16_t *pool_out)
 {
@@ -29,7 +29,7 @@ long ora_run_picture(const ora_cfg *cfg, int slice_type, int qp, int beta_off, i
     int16_t *pool = malloc((size_t)W * H * 3);
     pic_from_flat(&s, src, W, H);
     if (slice_type == KS_SLICE_I) ora_intra_picture(cfg, qp, &s, &pre, cells, &lv);
-    else { pic_from_flat(&r, ref, W, H); ora_inter_picture(cfg, qp, &s, &r, prev_cells, &pre, cells, &lv); }
+    else { pic_from_flat(&r, ref, W, H); ora_inter_picture(cfg, qp, lambda_qp, &s, &r, prev_cells, &pre, cells, &lv); }
     for (int ci = 0; ci < 3; ci++) memcpy(deb.c[ci].base, pre.c[ci].base, (size_t)pre.c[ci].stride * (pre.c[ci].h + 2 * ORA_PAD));
     ora_deblock_picture(cfg, qp, beta_off, tc_off, &deb, cells);
     ora_sao_picture(cfg, qp, &s, &deb, &fin, ctus);
@@ -47,14 +47,11 @@ long ora_run_picture(const ora_cfg *cfg, int slice_type, int qp, int beta_off, i
 /* motion search only (for ks_gpu_debug_me) */
 void ora_run_me(const ora_cfg *cfg, int qp, const uint8_t *src, const uint8_t *ref, const ks_cell *prev_cells, ks_cell *cells_out)
 {
-    /* the model's ME is the first stage of ora_inter_picture; rerun it and undo the later stages' cell edits */
     int W = cfg->width, H = cfg->height;
-    ora_pic s, r, pre; ora_pic_alloc(&s, W, H); ora_pic_alloc(&r, W, H); ora_pic_alloc(&pre, W, H);
-    ora_levels lv; lv.c[0] = calloc((size_t)W * H, 2); lv.c[1] = calloc((size_t)W * H / 4, 2); lv.c[2] = calloc((size_t)W * H / 4, 2);
+    ora_pic s, r; ora_pic_alloc(&s, W, H); ora_pic_alloc(&r, W, H);
     pic_from_flat(&s, src, W, H); pic_from_flat(&r, ref, W, H);
-    ora_inter_picture(cfg, qp, &s, &r, prev_cells, &pre, cells_out, &lv);
-    for (int i = 0; i < (W >> 4) * (H >> 4); i++) { cells_out[i].cu_log2 = 4; cells_out[i].flags = 0; }
-    ora_pic_free(&s); ora_pic_free(&r); ora_pic_free(&pre); free(lv.c[0]); free(lv.c[1]); free(lv.c[2]);
+    ora_me_field(cfg, qp, &s, &r, prev_cells, cells_out, NULL);
+    ora_pic_free(&s); ora_pic_free(&r);
 }
 
 /* sizeof() of the configuration structs (binding self-check for the ctypes mirrors in tests/katlib.py): 0 ora_cfg, 1 ora_seq_cfg */

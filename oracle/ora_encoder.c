@@ -78,7 +78,7 @@ long ora_encode_sequence(const ora_seq_cfg *sc, const uint8_t *yuv, uint8_t *bs,
         for (int i = 0; i < cnt; i++) {
             int f = order[i], t = type[i];
             ora_pic_load(&src, yuv + fsz * (size_t)(g0 + f), sc->width, sc->height);
-            int qp = ks_rc_picture_qp(&rc, t, f);
+            int qp = ks_rc_picture_qp(&rc, t, f), lqp = ks_rc_lambda_qp(&rc, t, f, qp);
             uint64_t me_cost = 0;
             memset(lv.c[0], 0, (size_t)W * H * 2); memset(lv.c[1], 0, (size_t)W * H / 2); memset(lv.c[2], 0, (size_t)W * H / 2);
             int slot; ks_cell *cur; ora_pic *out;
@@ -86,8 +86,8 @@ long ora_encode_sequence(const ora_seq_cfg *sc, const uint8_t *yuv, uint8_t *bs,
             else { slot = anchor_idx & 1; anchor_idx++; slot_of_prev = slot_of_next; slot_of_next = slot; }
             cur = cells[slot]; out = &fin[slot];
             if (t == KS_SLICE_I) ora_intra_picture(&cfg, qp, &src, &pre, cur, &lv);
-            else if (t == KS_SLICE_P) me_cost = ora_inter_picture(&cfg, qp, &src, &fin[slot_of_prev], slot_of_prev >= 0 && i > 1 ? cells[slot_of_prev] : cells[slot_of_prev], &pre, cur, &lv);
-            else ora_b_picture(&cfg, qp, &src, &fin[slot_of_prev], &fin[slot_of_next], cells[slot_of_next], f - l0[i], l1[i] - l0[i], &pre, cur, cells_b, &lv);
+            else if (t == KS_SLICE_P) me_cost = ora_inter_picture(&cfg, qp, lqp, &src, &fin[slot_of_prev], slot_of_prev >= 0 && i > 1 ? cells[slot_of_prev] : cells[slot_of_prev], &pre, cur, &lv);
+            else ora_b_picture(&cfg, qp, lqp, &src, &fin[slot_of_prev], &fin[slot_of_next], cells[slot_of_next], f - l0[i], l1[i] - l0[i], &pre, cur, cells_b, &lv);
             for (int ci = 0; ci < 3; ci++) memcpy(deb.c[ci].base, pre.c[ci].base, (size_t)pre.c[ci].stride * (pre.c[ci].h + 2 * ORA_PAD));
             int boff = t == KS_SLICE_I ? 0 : 2, toff = boff;
             ora_deblock_picture_b(&cfg, qp, boff, toff, &deb, cur, t == KS_SLICE_B ? cells_b : NULL);

@@ -93,9 +93,27 @@ static int avail(const ora_cfg *cfg, int xc, int yc, int xn, int yn)
 }
 static inline int mvbits(int d) { int a = iabs(d); return a ? 2 * (32 - __builtin_clz((unsigned)a)) + 1 : 1; }
 
-/* one transform block: residual -> fdct -> quant (-> sign hiding) -> dequant -> idct+pred.  returns cbf */
+/* estimated bits of a transform block's levels (fit against the host CABAC on natural clips: 3 per non-zero level + 2 per magnitude
+ * doubling + 4 per coded 4x4 group + the anti-diagonal of the outermost level); 0 for an all-zero block */
+static int level_bits_est(const int16_t *q, int n)
+{
+    int nnz = 0, slog = 0, ncg = 0, maxd = 0;
+    for (int gy = 0; gy < n; gy += 4) for (int gx = 0; gx < n; gx += 4) {
+        int any = 0;
+        for (int y = gy; y < gy + 4; y++) for (int x = gx; x < gx + 4; x++) {
+            int a = iabs(q[y * n + x]);
+            if (!a) continue;
+            any = 1; nnz++; slog += 31 - __builtin_clz((unsigned)a); if (x + y > maxd) maxd = x + y;
+        }
+        ncg += any;
+    }
+    return nnz ? 3 * nnz + 2 * slog + 4 * ncg + maxd : 0;
+}
+/* one transform block: residual -> fdct -> quant (-> sign hiding) -> dequant -> idct+pred.  returns cbf.
+ * rdz: RD zero-out (inter blocks; reference: the zero-block / skip decisions of tuDecision E@0x47e2f0 and skipFastDecision E@0x47f720 -- closed,
+ * this is our rule): drop the levels when SSE(src,pred) <= SSE(src,rec) + lambda * bits. */
 static int code_tb(const ora_cfg *cfg, int qp, int intra_slice, int log2, int is_dst,
-                   const uint8_t *src, int ss, const uint8_t *pred, int ps, uint8_t *rec, int rs, int16_t *lev, int ls)
+                   const uint8_t *src, int ss, const uint8_t *pred, int ps, uint8_t *rec, int rs, int16_t *lev, int ls, int rdz_lambda_q4)
 {
     int n = 1 << log2;
     int16_t res[1024], coef[1024], q[1024], du[1024], deq[1024];
@@ -103,10 +121,20 @@ static int code_tb(const ora_cfg *cfg, int qp, int intra_slice, int log2, int is
     ora_fdct(res, coef, n, n, log2, is_dst);
     int nnz = ora_quant(coef, q, n, qp, log2, intra_slice, du);
     if (nnz && cfg->sign_hiding) nnz = ora_sign_hide(coef, q, du, n, log2, scan_tb[log2 - 2]);
+    if (nnz) {
+        ora_dequant(q, deq, n, qp, log2);
+        ora_idct_add(deq, rec, pred, n, rs, ps, log2, is_dst);
+        if (rdz_lambda_q4) {
+            int64_t d0 = 0, d1 = 0;
+            for (int y = 0; y < n; y++) for (int x = 0; x < n; x++) {
+                int a = res[y * n + x], b = (int)src[y * ss + x] - (int)rec[y * rs + x];
+                d0 += a * a; d1 += b * b;
+            }
+            if (d0 * 16 <= d1 * 16 + (int64_t)rdz_lambda_q4 * level_bits_est(q, n)) { nnz = 0; memset(q, 0, sizeof(int16_t) * (size_t)n * n); }
+        }
+    }
     for (int y = 0; y < n; y++) memcpy(lev + (size_t)y * ls, q + y * n, (size_t)n * 2);
     if (!nnz) { for (int y = 0; y < n; y++) memcpy(rec + (size_t)y * rs, pred + (size_t)y * ps, (size_t)n); return 0; }
-    ora_dequant(q, deq, n, qp, log2);
-    ora_idct_add(deq, rec, pred, n, rs, ps, log2, is_dst);
     return 1;
 }
 
@@ -154,7 +182,7 @@ void ora_intra_picture(const ora_cfg *cfg, int qp, const ora_pic *src, ora_pic *
             memset(c, 0, sizeof(*c));
             c->cu_log2 = 4; c->flags = KS_F_INTRA; c->intra_mode = (uint8_t)best;
             uint8_t *r = rec->c[0].p + (size_t)y0 * rec->c[0].stride + x0;
-            if (code_tb(cfg, qp, 1, 4, 0, s, src->c[0].stride, pred, 16, r, rec->c[0].stride, lv->c[0] + (size_t)y0 * W + x0, W)) c->flags |= KS_F_CBF_Y;
+            if (code_tb(cfg, qp, 1, 4, 0, s, src->c[0].stride, pred, 16, r, rec->c[0].stride, lv->c[0] + (size_t)y0 * W + x0, W, 0)) c->flags |= KS_F_CBF_Y;
             for (int ci = 1; ci < 3; ci++) {
                 int xc = x0 >> 1, yc = y0 >> 1;
                 uint8_t nbc[33], pc[64];
@@ -162,7 +190,7 @@ void ora_intra_picture(const ora_cfg *cfg, int qp, const ora_pic *src, ora_pic *
                 ora_intra_pred(pc, 8, nbc, 3, best, 0, 0);
                 const uint8_t *sc = src->c[ci].p + (size_t)yc * src->c[ci].stride + xc;
                 uint8_t *rc = rec->c[ci].p + (size_t)yc * rec->c[ci].stride + xc;
-                if (code_tb(cfg, qpc, 1, 3, 0, sc, src->c[ci].stride, pc, 8, rc, rec->c[ci].stride, lv->c[ci] + (size_t)yc * (W / 2) + xc, W / 2))
+                if (code_tb(cfg, qpc, 1, 3, 0, sc, src->c[ci].stride, pc, 8, rc, rec->c[ci].stride, lv->c[ci] + (size_t)yc * (W / 2) + xc, W / 2, 0))
                     c->flags |= ci == 1 ? KS_F_CBF_CB : KS_F_CBF_CR;
             }
         }
@@ -172,7 +200,7 @@ void ora_intra_picture(const ora_cfg *cfg, int qp, const ora_pic *src, ora_pic *
 static const int8_t dia_dx[4] = {0, 0, -1, 1}, dia_dy[4] = {-1, 1, 0, 0};
 static const int8_t sq_dx[8] = {-1, 0, 1, -1, 1, -1, 0, 1}, sq_dy[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
 
-static int me_cell(const ora_cfg *cfg, int lam, const ora_plane *src, const ora_plane *ref, int x0, int y0, int tpx, int tpy, int *omx, int *omy)
+static int me_cell(const ora_cfg *cfg, int lam, const ora_plane *src, const ora_plane *ref, int x0, int y0, int tpx, int tpy, int *omx, int *omy, int *odist)
 {   /* a5 (start point) + a3 (small diamond, x264 DIA) + a6 (half/quarter refinement with real interpolation, SAD cost) */
     const uint8_t *s = src->p + (size_t)y0 * src->stride + x0;
     const uint8_t *r0 = ref->p + (size_t)y0 * ref->stride + x0;
@@ -245,12 +273,13 @@ static int me_cell(const ora_cfg *cfg, int lam, const ora_plane *src, const ora_
         if (bk >= 0) { mx += sq_dx[bk] * step; my += sq_dy[bk] * step; bc = lc; }
     }
     *omx = mx; *omy = my;
+    if (odist) *odist = bc - MVCOST(mx, my);
     return bc;
 #undef ICOST
 #undef MVCOST
 }
 
-static void recon_inter_cu(const ora_cfg *cfg, int qp, int qpc, const ora_pic *src, const ora_pic *ref, ora_pic *rec,
+static void recon_inter_cu(const ora_cfg *cfg, int qp, int qpc, int rdz, const ora_pic *src, const ora_pic *ref, ora_pic *rec,
                            ks_cell *cells, ora_levels *lv, int x0, int y0, int log2, int mvx, int mvy)
 {
     int S = 1 << log2, W = cfg->width, cw = W >> 4;
@@ -262,12 +291,12 @@ static void recon_inter_cu(const ora_cfg *cfg, int qp, int qpc, const ora_pic *s
     for (int ty = 0; ty < S; ty += T) for (int tx = 0; tx < S; tx += T) {
         int x = x0 + tx, y = y0 + ty, f = 0;
         if (code_tb(cfg, qp, 0, tl, 0, src->c[0].p + (size_t)y * src->c[0].stride + x, src->c[0].stride, pred[0] + ty * 64 + tx, 64,
-                    rec->c[0].p + (size_t)y * rec->c[0].stride + x, rec->c[0].stride, lv->c[0] + (size_t)y * W + x, W)) f |= KS_F_CBF_Y;
+                    rec->c[0].p + (size_t)y * rec->c[0].stride + x, rec->c[0].stride, lv->c[0] + (size_t)y * W + x, W, rdz)) f |= KS_F_CBF_Y;
         for (int ci = 1; ci < 3; ci++) {
             int xc = x / 2, yc = y / 2;
             if (code_tb(cfg, qpc, 0, tl - 1, 0, src->c[ci].p + (size_t)yc * src->c[ci].stride + xc, src->c[ci].stride,
                         pred[ci] + (ty / 2) * 64 + tx / 2, 64, rec->c[ci].p + (size_t)yc * rec->c[ci].stride + xc, rec->c[ci].stride,
-                        lv->c[ci] + (size_t)yc * (W / 2) + xc, W / 2)) f |= ci == 1 ? KS_F_CBF_CB : KS_F_CBF_CR;
+                        lv->c[ci] + (size_t)yc * (W / 2) + xc, W / 2, 0)) f |= ci == 1 ? KS_F_CBF_CB : KS_F_CBF_CR;
         }
         for (int yy = y; yy < y + T; yy += 16) for (int xx = x; xx < x + T; xx += 16) {
             ks_cell *c = &cells[(yy >> 4) * cw + (xx >> 4)];
@@ -276,39 +305,172 @@ static void recon_inter_cu(const ora_cfg *cfg, int qp, int qpc, const ora_pic *s
     }
 }
 
-uint64_t ora_inter_picture(const ora_cfg *cfg, int qp, const ora_pic *src, const ora_pic *ref, const ks_cell *prev_cells,
+/* ---- mode decision of a P picture (reference: processTree E@0x46b610 / checkInterPu2Nx2N / skipFullMergeDecision E@0x47f720 /
+ * GetMergeCandsForP -- closed; this is OUR algorithm, designed so that every heavy step is independent per cell):
+ *   stage E  per CTU: one candidate list = the search results of the CTU's own cells (z-order), zero, and of the cells bordering it on
+ *            the left / above (distinct vectors, <= ORA_NCAND); per cell the distortion (search metric) of EVERY list entry;
+ *   stage D  per CTU, in coding order: 64 -> 32 -> 16 quadtree by J = distortion + lambda * bits, bits from the 2Nx2N merge list /
+ *            AMVP predictors of the vectors decided so far (cells of other CTUs count with their search results). ---- */
+#define ORA_NCAND 16
+typedef struct { int n; int16_t mvx[ORA_NCAND], mvy[ORA_NCAND]; int dist[16][ORA_NCAND]; } ora_ctu_cands;   /* dist[j * 4 + i][k] */
+
+static int mvd_bits_est(int d) { int a = iabs(d); if (a == 0) return 1; if (a == 1) return 3; int v = a - 2, k = 1, b = 3; while (v >= (1 << k)) { v -= 1 << k; k++; b++; } return b + k + 1; }
+
+static void cand_add(ora_ctu_cands *t, const ks_cell *mv0, int cw, int ch, int cx, int cy, int zero)
+{
+    if (!zero && (cx < 0 || cy < 0 || cx >= cw || cy >= ch)) return;
+    int mvx = zero ? 0 : mv0[cy * cw + cx].mvx, mvy = zero ? 0 : mv0[cy * cw + cx].mvy;
+    for (int k = 0; k < t->n; k++) if (t->mvx[k] == mvx && t->mvy[k] == mvy) return;
+    if (t->n >= ORA_NCAND) return;
+    t->mvx[t->n] = (int16_t)mvx; t->mvy[t->n] = (int16_t)mvy; t->n++;
+}
+static void decide_candidates(const ora_cfg *cfg, const ora_plane *src, const ora_plane *ref, const ks_cell *mv0, const int *dist0, int X, int Y, ora_ctu_cands *t)
+{   /* (X,Y) = cell coordinates of the CTU */
+    int cw = cfg->width >> 4, ch = cfg->height >> 4;
+    t->n = 0;
+    for (int z = 0; z < 16; z++) cand_add(t, mv0, cw, ch, X + ((z & 1) | ((z >> 1) & 2)), Y + (((z >> 1) & 1) | ((z >> 2) & 2)), 0);
+    cand_add(t, mv0, cw, ch, 0, 0, 1);
+    for (int b = 3; b >= 0; b--) cand_add(t, mv0, cw, ch, X - 1, Y + b, 0);
+    for (int a = 0; a < 4; a++) cand_add(t, mv0, cw, ch, X + a, Y - 1, 0);
+    cand_add(t, mv0, cw, ch, X + 4, Y - 1, 0); cand_add(t, mv0, cw, ch, X - 1, Y + 4, 0); cand_add(t, mv0, cw, ch, X - 1, Y - 1, 0);
+    for (int j = 0; j < 4; j++) for (int i = 0; i < 4; i++) {
+        int cx = X + i, cy = Y + j;
+        if (cx >= cw || cy >= ch) continue;
+        const uint8_t *s0 = src->p + (size_t)(cy << 4) * src->stride + (cx << 4), *r0 = ref->p + (size_t)(cy << 4) * ref->stride + (cx << 4);
+        for (int k = 0; k < t->n; k++) {
+            if (t->mvx[k] == mv0[cy * cw + cx].mvx && t->mvy[k] == mv0[cy * cw + cx].mvy) { t->dist[j * 4 + i][k] = dist0[cy * cw + cx]; continue; }
+            uint8_t pred[256];
+            ora_mc_luma(pred, 16, r0, ref->stride, 16, 16, t->mvx[k], t->mvy[k]);
+            t->dist[j * 4 + i][k] = (int)((cfg->satd && cfg->subpel > 0) ? ora_satd(s0, pred, src->stride, 16, 16, 16) : ora_sad(s0, pred, src->stride, 16, 16, 16));
+        }
+    }
+}
+
+/* stage D state of one CTU: vectors of the 4x4 cells plus a one-cell border (row -1: above CTUs incl. above-left / above-right,
+ * column -1: left CTU); index [j + 1][i + 1], i = -1..4, j = -1..4 */
+typedef struct {
+    int16_t mvx[6][6], mvy[6][6];
+    uint8_t ok[6][6];            /* the cell exists, precedes the current block in coding order and carries a vector */
+    uint8_t log2[4][4];
+} ora_ctu_state;
+static inline int zcell(int i, int j) { return (i & 1) | ((j & 1) << 1) | ((i & 2) << 1) | ((j & 2) << 2); }
+static int nb_ok(const ora_ctu_state *st, int i, int j, int zcur)
+{   /* (i,j) CTU-local cell coordinates of the neighbour; zcur = z-index of the current block's first cell */
+    if (i < -1 || j < -1 || i > 4 || j > 3) return 0;
+    if (!st->ok[j + 1][i + 1]) return 0;
+    if (j == -1 || i == -1) return 1;
+    if (i > 3) return 0;
+    return zcell(i, j) < zcur;
+}
+/* bits to code vector (mx,my) for the 2Nx2N CU at local cell (i,j), size s cells: merge index, or AMVP + mvd (an estimate: the host codes the real thing) */
+static int motion_bits(const ora_ctu_state *st, int i, int j, int s, int maxc, int mx, int my)
+{
+    int zc = zcell(i, j);
+    const int ci[5] = {i - 1, i + s - 1, i + s, i - 1, i - 1}, cj[5] = {j + s - 1, j - 1, j - 1, j + s, j - 1};   /* A1 B1 B0 A0 B2 */
+    int av[5], vx[5], vy[5];
+    for (int k = 0; k < 5; k++) {
+        av[k] = nb_ok(st, ci[k], cj[k], zc);
+        vx[k] = av[k] ? st->mvx[cj[k] + 1][ci[k] + 1] : 0; vy[k] = av[k] ? st->mvy[cj[k] + 1][ci[k] + 1] : 0;
+    }
+#define SAME(a, b) (vx[a] == vx[b] && vy[a] == vy[b])
+    int use[5] = {av[0], av[1] && !(av[0] && SAME(0, 1)), av[2] && !(av[1] && SAME(1, 2)), av[3] && !(av[0] && SAME(0, 3)),
+                  av[4] && !(av[0] && SAME(0, 4)) && !(av[1] && SAME(1, 4))};
+    if (use[0] + use[1] + use[2] + use[3] == 4) use[4] = 0;
+#undef SAME
+    int n = 0, idx = -1;
+    for (int k = 0; k < 5 && n < maxc && idx < 0; k++) if (use[k]) { if (vx[k] == mx && vy[k] == my) idx = n; n++; }
+    if (idx < 0 && n < maxc && mx == 0 && my == 0) idx = n;
+    if (idx >= 0) return 1 + (maxc > 1 ? (idx < maxc - 1 ? idx + 1 : maxc - 1) : 0);
+    /* AMVP: a = first of (A0, A1), b = first of (B0, B1, B2) */
+    int fa = av[3] ? 3 : (av[0] ? 0 : -1), fb = av[2] ? 2 : (av[1] ? 1 : (av[4] ? 4 : -1));
+    int best = 0x7fffffff;
+    if (fa >= 0) best = imin(best, mvd_bits_est(mx - vx[fa]) + mvd_bits_est(my - vy[fa]));
+    if (fb >= 0) best = imin(best, mvd_bits_est(mx - vx[fb]) + mvd_bits_est(my - vy[fb]));
+    if (fa < 0 || fb < 0 || (vx[fa] == vx[fb] && vy[fa] == vy[fb])) best = imin(best, mvd_bits_est(mx) + mvd_bits_est(my));
+    return 5 + best;
+}
+static int decide_block(const ora_ctu_cands *t, int ncx, int ncy, int lam, int maxc, ora_ctu_state *st, int i, int j, int s)
+{   /* ncx/ncy = cells of the CTU inside the picture */
+    if (i >= ncx || j >= ncy) return 0;
+    int inside = i + s <= ncx && j + s <= ncy, jsplit = 0;
+    if (s > 1) {
+        int h = s >> 1;
+        jsplit = inside ? (lam >> 4) : 0;          /* split_cu_flag = 1 */
+        for (int k = 0; k < 4; k++) jsplit += decide_block(t, ncx, ncy, lam, maxc, st, i + (k & 1) * h, j + (k >> 1) * h, h);
+        if (!inside) return jsplit;
+    }
+    int best = 0x7fffffff, bk = 0;
+    for (int k = 0; k < t->n; k++) {
+        int sum = 0;
+        for (int b = 0; b < s; b++) for (int a = 0; a < s; a++) sum += t->dist[(j + b) * 4 + i + a][k];
+        int c = sum + ((lam * (motion_bits(st, i, j, s, maxc, t->mvx[k], t->mvy[k]) + (s > 1))) >> 4);     /* + split_cu_flag = 0 above the minimum size */
+        if (c < best) { best = c; bk = k; }
+    }
+    if (s > 1 && best > jsplit) return jsplit;
+    for (int b = 0; b < s; b++) for (int a = 0; a < s; a++) {
+        st->mvx[j + b + 1][i + a + 1] = t->mvx[bk]; st->mvy[j + b + 1][i + a + 1] = t->mvy[bk]; st->ok[j + b + 1][i + a + 1] = 1;
+        st->log2[j + b][i + a] = (uint8_t)(s == 4 ? 6 : (s == 2 ? 5 : 4));
+    }
+    return best;
+}
+static void decide_ctu(const ora_cfg *cfg, int lam, int maxc, const ks_cell *mv0, const ora_ctu_cands *t, int X, int Y, ks_cell *cells)
+{
+    int cw = cfg->width >> 4, ch = cfg->height >> 4;
+    ora_ctu_state st; memset(&st, 0, sizeof(st));
+    for (int j = -1; j <= 4; j++) for (int i = -1; i <= 4; i++) {
+        int cx = X + i, cy = Y + j;
+        if (cx < 0 || cy < 0 || cx >= cw || cy >= ch) continue;
+        if (j == -1 || (i == -1 && j <= 3)) { st.ok[j + 1][i + 1] = 1; st.mvx[j + 1][i + 1] = mv0[cy * cw + cx].mvx; st.mvy[j + 1][i + 1] = mv0[cy * cw + cx].mvy; }
+    }
+    int ncx = imin(4, cw - X), ncy = imin(4, ch - Y);
+    decide_block(t, ncx, ncy, lam, maxc, &st, 0, 0, 4);
+    for (int j = 0; j < ncy; j++) for (int i = 0; i < ncx; i++) {
+        ks_cell *c = &cells[(Y + j) * cw + X + i];
+        memset(c, 0, sizeof(*c)); c->mvx = st.mvx[j + 1][i + 1]; c->mvy = st.mvy[j + 1][i + 1]; c->cu_log2 = st.log2[j][i];
+    }
+}
+
+/* motion search of every 16x16 cell (independent of neighbours: predictor = co-located MV of the previous picture); returns the cost sum */
+uint64_t ora_me_field(const ora_cfg *cfg, int qp, const ora_pic *src, const ora_pic *ref, const ks_cell *prev_cells, ks_cell *cells, int *dist)
+{
+    int W = cfg->width, H = cfg->height, cw = W >> 4, ch = H >> 4, lam = ora_lambda_sad_q4[qp];
+    uint64_t cost_sum = 0;
+    for (int cy = 0; cy < ch; cy++) for (int cx = 0; cx < cw; cx++) {
+        int tpx = 0, tpy = 0, mx, my, d;
+        if (prev_cells && !(prev_cells[cy * cw + cx].flags & KS_F_INTRA)) { tpx = prev_cells[cy * cw + cx].mvx; tpy = prev_cells[cy * cw + cx].mvy; }
+        cost_sum += (uint64_t)me_cell(cfg, lam, &src->c[0], &ref->c[0], cx << 4, cy << 4, tpx, tpy, &mx, &my, &d);
+        ks_cell *c = &cells[cy * cw + cx];
+        memset(c, 0, sizeof(*c)); c->mvx = (int16_t)mx; c->mvy = (int16_t)my; c->cu_log2 = 4;
+        if (dist) dist[cy * cw + cx] = d;
+    }
+    return cost_sum;
+}
+
+/* lambda_qp: the QP whose lambda drives the mode decision and the RD zero-out (>= qp; the encoder raises it on the non-key P pictures) */
+uint64_t ora_inter_picture(const ora_cfg *cfg, int qp, int lambda_qp, const ora_pic *src, const ora_pic *ref, const ks_cell *prev_cells,
                        ora_pic *rec, ks_cell *cells, ora_levels *lv)
 {
     build_scans();
     int W = cfg->width, H = cfg->height, cw = W >> 4, ch = H >> 4;
-    int lam = ora_lambda_sad_q4[qp], qpc = ora_chroma_qp[qp];
-    uint64_t cost_sum = 0;
-    /* 1. motion search per 16x16 cell (independent of neighbours: predictor = co-located MV of the previous picture) */
-    for (int cy = 0; cy < ch; cy++) for (int cx = 0; cx < cw; cx++) {
-        int tpx = 0, tpy = 0, mx, my;
-        if (prev_cells && !(prev_cells[cy * cw + cx].flags & KS_F_INTRA)) { tpx = prev_cells[cy * cw + cx].mvx; tpy = prev_cells[cy * cw + cx].mvy; }
-        cost_sum += (uint64_t)me_cell(cfg, lam, &src->c[0], &ref->c[0], cx << 4, cy << 4, tpx, tpy, &mx, &my);
-        ks_cell *c = &cells[cy * cw + cx];
-        memset(c, 0, sizeof(*c)); c->mvx = (int16_t)mx; c->mvy = (int16_t)my; c->cu_log2 = 4;
+    lambda_qp = clip3(0, 51, lambda_qp);
+    int lam = ora_lambda_sad_q4[lambda_qp], rdz = ora_lambda_sse_q4[lambda_qp], qpc = ora_chroma_qp[qp];
+    /* 1. motion search per 16x16 cell */
+    ks_cell *mv0 = malloc(sizeof(ks_cell) * (size_t)cw * ch);
+    int *dist0 = malloc(sizeof(int) * (size_t)cw * ch);
+    uint64_t cost_sum = ora_me_field(cfg, qp, src, ref, prev_cells, mv0, dist0);
+    /* 2. candidate distortions, then the CU quadtree / merge decision, CTU by CTU */
+    for (int Y = 0; Y < ch; Y += 4) for (int X = 0; X < cw; X += 4) {
+        ora_ctu_cands t;
+        decide_candidates(cfg, &src->c[0], &ref->c[0], mv0, dist0, X, Y, &t);
+        decide_ctu(cfg, lam, getenv("MAXC") ? atoi(getenv("MAXC")) : 3, mv0, &t, X, Y, cells);
     }
-    /* 2. CU size: merge four equal-MV siblings upward (16 -> 32 -> 64) when the larger CU lies inside the picture */
-    for (int y = 0; y + 32 <= H; y += 32) for (int x = 0; x + 32 <= W; x += 32) {
-        ks_cell *a = &cells[(y >> 4) * cw + (x >> 4)], *b = a + 1, *c = a + cw, *d = c + 1;
-        if (a->mvx == b->mvx && a->mvx == c->mvx && a->mvx == d->mvx && a->mvy == b->mvy && a->mvy == c->mvy && a->mvy == d->mvy)
-            a->cu_log2 = b->cu_log2 = c->cu_log2 = d->cu_log2 = 5;
-    }
-    for (int y = 0; y + 64 <= H; y += 64) for (int x = 0; x + 64 <= W; x += 64) {
-        ks_cell *a = &cells[(y >> 4) * cw + (x >> 4)];
-        int ok = 1;
-        for (int j = 0; j < 4 && ok; j++) for (int i = 0; i < 4; i++) { ks_cell *t = a + j * cw + i; if (t->cu_log2 != 5 || t->mvx != a->mvx || t->mvy != a->mvy) { ok = 0; break; } }
-        if (ok) for (int j = 0; j < 4; j++) for (int i = 0; i < 4; i++) a[j * cw + i].cu_log2 = 6;
-    }
+    free(mv0); free(dist0);
     /* 3. prediction + residual coding + reconstruction per CU */
     for (int y = 0; y < H; y += 16) for (int x = 0; x < W; x += 16) {
         ks_cell c = cells[(y >> 4) * cw + (x >> 4)];
         int S = 1 << c.cu_log2;
         if ((x & (S - 1)) || (y & (S - 1))) continue;
-        recon_inter_cu(cfg, qp, qpc, src, ref, rec, cells, lv, x, y, c.cu_log2, c.mvx, c.mvy);
+        recon_inter_cu(cfg, qp, qpc, rdz, src, ref, rec, cells, lv, x, y, c.cu_log2, c.mvx, c.mvy);
     }
     return cost_sum;
 }
@@ -317,7 +479,7 @@ uint64_t ora_inter_picture(const ora_cfg *cfg, int qp, const ora_pic *src, const
 static int scale_pred(int mv, int num, int den) { return den ? (mv * num) / den : 0; }       /* C division: truncates toward zero */
 
 /* residual coding of one CU whose prediction is already assembled in pred[3] (pitch 64) */
-static void recon_cu_from_pred(const ora_cfg *cfg, int qp, int qpc, const ora_pic *src, uint8_t (*pred)[64 * 64], ora_pic *rec,
+static void recon_cu_from_pred(const ora_cfg *cfg, int qp, int qpc, int rdz, const ora_pic *src, uint8_t (*pred)[64 * 64], ora_pic *rec,
                                ks_cell *cells, ora_levels *lv, int x0, int y0, int log2)
 {
     int S = 1 << log2, W = cfg->width, cw = W >> 4;
@@ -325,12 +487,12 @@ static void recon_cu_from_pred(const ora_cfg *cfg, int qp, int qpc, const ora_pi
     for (int ty = 0; ty < S; ty += T) for (int tx = 0; tx < S; tx += T) {
         int x = x0 + tx, y = y0 + ty, f = 0;
         if (code_tb(cfg, qp, 0, tl, 0, src->c[0].p + (size_t)y * src->c[0].stride + x, src->c[0].stride, pred[0] + ty * 64 + tx, 64,
-                    rec->c[0].p + (size_t)y * rec->c[0].stride + x, rec->c[0].stride, lv->c[0] + (size_t)y * W + x, W)) f |= KS_F_CBF_Y;
+                    rec->c[0].p + (size_t)y * rec->c[0].stride + x, rec->c[0].stride, lv->c[0] + (size_t)y * W + x, W, rdz)) f |= KS_F_CBF_Y;
         for (int ci = 1; ci < 3; ci++) {
             int xc = x / 2, yc = y / 2;
             if (code_tb(cfg, qpc, 0, tl - 1, 0, src->c[ci].p + (size_t)yc * src->c[ci].stride + xc, src->c[ci].stride,
                         pred[ci] + (ty / 2) * 64 + tx / 2, 64, rec->c[ci].p + (size_t)yc * rec->c[ci].stride + xc, rec->c[ci].stride,
-                        lv->c[ci] + (size_t)yc * (W / 2) + xc, W / 2)) f |= ci == 1 ? KS_F_CBF_CB : KS_F_CBF_CR;
+                        lv->c[ci] + (size_t)yc * (W / 2) + xc, W / 2, 0)) f |= ci == 1 ? KS_F_CBF_CB : KS_F_CBF_CR;
         }
         for (int yy = y; yy < y + T; yy += 16) for (int xx = x; xx < x + T; xx += 16) {
             ks_cell *c = &cells[(yy >> 4) * cw + (xx >> 4)];
@@ -360,7 +522,7 @@ static void predict_cell(const ora_pic *ref0, const ora_pic *ref1, int x0, int y
 /* B picture between two anchors: list 0 = ref0 (earlier), list 1 = ref1 (later).  anchor_cells = motion field of the later
  * anchor (a P picture predicted from ref0 over `da` pictures); d0 = POC(cur) - POC(ref0).  Predictors: the anchor's vector
  * scaled to each list.  Per cell: best of list 0 / list 1 / bi-prediction (DefaultWeightedBi_c) by SAD(or SATD)+lambda*bits. */
-void ora_b_picture(const ora_cfg *cfg, int qp, const ora_pic *src, const ora_pic *ref0, const ora_pic *ref1, const ks_cell *anchor_cells,
+void ora_b_picture(const ora_cfg *cfg, int qp, int lambda_qp, const ora_pic *src, const ora_pic *ref0, const ora_pic *ref1, const ks_cell *anchor_cells,
                    int d0, int da, ora_pic *rec, ks_cell *cells, ks_cell_b *cells_b, ora_levels *lv)
 {
     build_scans();
@@ -372,8 +534,8 @@ void ora_b_picture(const ora_cfg *cfg, int qp, const ora_pic *src, const ora_pic
         if (anchor_cells && !(anchor_cells[cy * cw + cx].flags & KS_F_INTRA)) { ax = anchor_cells[cy * cw + cx].mvx; ay = anchor_cells[cy * cw + cx].mvy; }
         int t0x = scale_pred(ax, d0, da), t0y = scale_pred(ay, d0, da), t1x = scale_pred(ax, d0 - da, da), t1y = scale_pred(ay, d0 - da, da);
         int m0x, m0y, m1x, m1y;
-        int c0 = me_cell(cfg, lam, &src->c[0], &ref0->c[0], cx << 4, cy << 4, t0x, t0y, &m0x, &m0y);
-        int c1 = me_cell(cfg, lam, &src->c[0], &ref1->c[0], cx << 4, cy << 4, t1x, t1y, &m1x, &m1y);
+        int c0 = me_cell(cfg, lam, &src->c[0], &ref0->c[0], cx << 4, cy << 4, t0x, t0y, &m0x, &m0y, NULL);
+        int c1 = me_cell(cfg, lam, &src->c[0], &ref1->c[0], cx << 4, cy << 4, t1x, t1y, &m1x, &m1y, NULL);
         predict_cell(ref0, ref1, cx << 4, cy << 4, 16, 3, m0x, m0y, m1x, m1y, pred, 0, 0);
         const uint8_t *s = src->c[0].p + (size_t)(cy << 4) * src->c[0].stride + (cx << 4);
         int cb = (int)(cfg->satd && cfg->subpel > 0 ? ora_satd(s, pred[0], src->c[0].stride, 64, 16, 16) : ora_sad(s, pred[0], src->c[0].stride, 64, 16, 16))
@@ -403,7 +565,7 @@ void ora_b_picture(const ora_cfg *cfg, int qp, const ora_pic *src, const ora_pic
         int log2 = cells[i].cu_log2, S = 1 << log2;
         if ((x & (S - 1)) || (y & (S - 1))) continue;
         predict_cell(ref0, ref1, x, y, S, cells_b[i].dir, cells[i].mvx, cells[i].mvy, cells_b[i].mvx1, cells_b[i].mvy1, pred, 0, 0);
-        recon_cu_from_pred(cfg, qp, qpc, src, pred, rec, cells, lv, x, y, log2);
+        recon_cu_from_pred(cfg, qp, qpc, ora_lambda_sse_q4[clip3(0, 51, lambda_qp)], src, pred, rec, cells, lv, x, y, log2);
     }
 }
 

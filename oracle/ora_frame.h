@@ -45,9 +45,12 @@ typedef struct ora_levels { int16_t *c[3]; } ora_levels;
 /* picture-level stages.  `cells` has (w/16)*(h/16) entries. */
 void ora_intra_picture(const ora_cfg *cfg, int qp, const ora_pic *src, ora_pic *rec, ks_cell *cells, ora_levels *lv);
 /* returns the sum of the per-cell winning search costs (the rate control's complexity measure) */
-uint64_t ora_inter_picture(const ora_cfg *cfg, int qp, const ora_pic *src, const ora_pic *ref, const ks_cell *prev_cells,
+/* lambda_qp: the QP whose lambda drives the CU/merge decision and the RD zero-out of residual blocks (ks_pic_params.lambda_qp) */
+uint64_t ora_inter_picture(const ora_cfg *cfg, int qp, int lambda_qp, const ora_pic *src, const ora_pic *ref, const ks_cell *prev_cells,
                        ora_pic *rec, ks_cell *cells, ora_levels *lv);
-void ora_b_picture(const ora_cfg *cfg, int qp, const ora_pic *src, const ora_pic *ref0, const ora_pic *ref1, const ks_cell *anchor_cells,
+/* the motion search alone: per-cell vectors + the distortion of each winner */
+uint64_t ora_me_field(const ora_cfg *cfg, int qp, const ora_pic *src, const ora_pic *ref, const ks_cell *prev_cells, ks_cell *cells, int *dist);
+void ora_b_picture(const ora_cfg *cfg, int qp, int lambda_qp, const ora_pic *src, const ora_pic *ref0, const ora_pic *ref1, const ks_cell *anchor_cells,
                    int d0, int da, ora_pic *rec, ks_cell *cells, ks_cell_b *cells_b, ora_levels *lv);
 void ora_deblock_picture(const ora_cfg *cfg, int qp, int beta_offset_div2, int tc_offset_div2, ora_pic *rec, const ks_cell *cells);
 void ora_deblock_picture_b(const ora_cfg *cfg, int qp, int beta_offset_div2, int tc_offset_div2, ora_pic *rec, const ks_cell *cells, const ks_cell_b *cells_b);

@@ -122,7 +122,7 @@ def build_scan(log2n):
 
 
 # ---------------------------------------------------------------------------------------- picture stages
-def run_oracle_picture(cfg, slice_type, qp, boff, toff, src, ref, prev_cells):
+def run_oracle_picture(cfg, slice_type, qp, boff, toff, src, ref, prev_cells, lambda_qp=None):
     O = oracle()
     O.ora_run_picture.restype = C.c_long
     W, H = cfg.width, cfg.height
@@ -130,7 +130,7 @@ def run_oracle_picture(cfg, slice_type, qp, boff, toff, src, ref, prev_cells):
     fsz = W * H * 3 // 2
     o = dict(pre=np.zeros(fsz, np.uint8), fin=np.zeros(fsz, np.uint8), cells=np.zeros(ncell * 8, np.uint8),
              lev=np.zeros(fsz, np.int16), ctus=np.zeros(nctu * 72, np.uint8), pool=np.zeros(fsz, np.int16))
-    n = O.ora_run_picture(C.byref(cfg), slice_type, qp, boff, toff, ptr(src), ptr(ref) if ref is not None else None,
+    n = O.ora_run_picture(C.byref(cfg), slice_type, qp, min(51, qp if lambda_qp is None else lambda_qp), boff, toff, ptr(src), ptr(ref) if ref is not None else None,
                           ptr(prev_cells) if prev_cells is not None else None, ptr(o["pre"]), ptr(o["fin"]), ptr(o["cells"]),
                           ptr(o["lev"]), ptr(o["ctus"]), ptr(o["pool"]))
     assert n >= 0
@@ -167,13 +167,14 @@ def test_picture_stages_match_oracle(w, h, qp, sbh, sao, subpel, satd, me):
             is_i = f == 0
             pp = ks.KsPicParams(ks.KS_SLICE_I if is_i else ks.KS_SLICE_P, qp if is_i else qp + 1, f % 3, -1 if is_i else (f & 1) ^ 1, f & 1, f & 1,
                                 -1 if is_i else (f & 1) ^ 1, 0 if is_i else 2, 0 if is_i else 2, 1)
+            pp.lambda_qp_delta = 3 if f == 2 else 0          # one P picture decides with the raised lambda (non-key pictures of the cascade)
             if not is_i:
                 me = np.zeros(ncell * 8, np.uint8)
                 assert L.ks_gpu_debug_me(ctx, C.byref(pp), ptr(me)) == 0
             out = ks.KsPicOut()
             assert L.ks_gpu_encode_picture(ctx, C.byref(pp), C.byref(out)) == 0
             assert L.ks_gpu_debug_fetch(ctx, 2, f % 3, ptr(src), fsz) == 0           # coded-size source as the device sees it
-            o = run_oracle_picture(cfg, pp.slice_type, pp.qp, pp.beta_offset_div2, pp.tc_offset_div2, src, ref_fin, prev_cells)
+            o = run_oracle_picture(cfg, pp.slice_type, pp.qp, pp.beta_offset_div2, pp.tc_offset_div2, src, ref_fin, prev_cells, pp.qp + pp.lambda_qp_delta)
             tag = "%dx%d f%d " % (w, h, f)
             if not is_i:
                 O = oracle()
