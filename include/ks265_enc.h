@@ -43,6 +43,13 @@ typedef struct ks265_gop_stats {
     uint64_t h2d_bytes;         /* picture bytes copied host->device */
 } ks265_gop_stats;
 
+/* per-picture record (the rows of the reference's `-psnr 2` table), coding order */
+typedef struct ks265_pic_stat {
+    int poc, slice_type, qp;    /* poc = display index inside the shard; slice_type KS_SLICE_* (0 B, 1 P, 2 I) */
+    uint64_t bits;
+    uint64_t sse[3];
+} ks265_pic_stat;
+
 typedef struct ks265_encoder ks265_encoder;
 
 int  ks265_config_default_preset(ks265_config *cfg, const char *preset);     /* fills everything but width/height */
@@ -55,6 +62,11 @@ void ks265_encoder_close(ks265_encoder *enc);
  * Returns bytes written or a negative error. */
 long ks265_encoder_encode_gop(ks265_encoder *enc, const uint8_t *frames, const void *frames_dev, int nframes,
                               uint8_t *bs, size_t bs_cap, uint8_t *recon, ks265_gop_stats *stats);
+/* the next encode_gop calls also fill `stats[0..cap)` with one record per coded picture (NULL / 0 turns it off) */
+void ks265_encoder_set_picture_stats(ks265_encoder *enc, ks265_pic_stat *stats, int cap);
+/* page-locked host memory for picture buffers: pictures handed to encode_gop from such a buffer are DMA-ed in place (no staging copy) */
+void *ks265_alloc_host(size_t bytes);
+void ks265_free_host(void *p);
 /* per-stage device times accumulated since `on` (see ks_gpu_get_stage_times) */
 int  ks265_encoder_set_profiling(ks265_encoder *enc, int on);
 int  ks265_encoder_get_stage_times(ks265_encoder *enc, double ms[7], uint64_t launches[7]);   /* KS_NSTAGES entries */

@@ -78,7 +78,8 @@ void ks_gpu_close(ks_gpu_ctx *ctx);
 int  ks_gpu_coded_size(const ks_gpu_ctx *ctx, int *width, int *height);
 /* replaces: ctuCacheLoadSrcYuv (EncCtuCache.cpp) -- host planes -> device source slot (pinned staging + async H2D) */
 int  ks_gpu_upload_frame(ks_gpu_ctx *ctx, int slot, const uint8_t *y, const uint8_t *u, const uint8_t *v, int stride_y, int stride_uv);
-/* same, but the I420 picture (display size, tightly packed) already lives in device memory */
+/* same, but the I420 picture (display size, tightly packed) already lives in device memory.  When the display size is already a multiple of 16
+ * (and the pointer 16-byte aligned) the kernels read it IN PLACE -- no copy; the caller keeps it unchanged until the picture has finished */
 int  ks_gpu_upload_frame_device(ks_gpu_ctx *ctx, int slot, const void *dev_i420);
 /* replaces: IEncTaskManage::executeTasks -> processOneCtu for a whole picture: ME + sub-pel (a1-a7), CU quadtree / merge decision
  * (processTree E@0x46b610), MC + residual DCT/quant/SBH/dequant/IDCT with RD zero-out (a8-a14), deblock (a16), SAO (a17-a20), level packing;

@@ -33,6 +33,7 @@ struct ks_gpu_ctx {
     cudaEvent_t *ev_src_read;   /* per source slot: the last picture that read it has finished (the next upload waits for it) */
     size_t fsz;                 /* bytes of one coded picture (W*H*3/2) */
     uint8_t **d_src, **d_rec;   /* slots */
+    uint8_t **src_cur;          /* where each source slot's picture currently lives: d_src[slot], or the caller's device buffer (zero-copy) */
     uint8_t *d_pre;             /* pre-filter reconstruction / deblocked in place */
     CUtensorMap tm_pre[3];      /* TMA descriptors of d_pre's planes for the SAO tile staging */
     int tma_mask;               /* bit c: plane c qualifies (pitch multiple of 16 bytes) */
@@ -112,11 +113,12 @@ extern "C" ks_gpu_ctx *ks_gpu_open(int device, int width, int height, const ks_g
     for (int i = 0; i < c->cfg.n_src_slots; i++)
         if (cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&c->ev_src_read[i], cudaEventDisableTiming) != cudaSuccess) { e = KS_ECUDA; goto fail; }
     c->d_src = (uint8_t **)calloc(c->cfg.n_src_slots, sizeof(uint8_t *));
+    c->src_cur = (uint8_t **)calloc(c->cfg.n_src_slots, sizeof(uint8_t *));
     c->d_rec = (uint8_t **)calloc(c->cfg.n_rec_slots, sizeof(uint8_t *));
     c->syn = (ks_syn_slot *)calloc(c->cfg.n_syn_slots, sizeof(ks_syn_slot));
     {
         bool ok = true;
-        for (int i = 0; i < c->cfg.n_src_slots; i++) ok = ok && cudaMalloc(&c->d_src[i], c->fsz) == cudaSuccess;
+        for (int i = 0; i < c->cfg.n_src_slots; i++) { ok = ok && cudaMalloc(&c->d_src[i], c->fsz) == cudaSuccess; c->src_cur[i] = c->d_src[i]; }
         for (int i = 0; i < c->cfg.n_rec_slots; i++) ok = ok && cudaMalloc(&c->d_rec[i], c->fsz) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_pre, c->fsz) == cudaSuccess;
         if (ok) {   /* TMA descriptors for the SAO tile staging: Y box 96x66, chroma 64x34 (ks_loopfilter.cuh KS_SAO_PITCH_*) */
@@ -193,9 +195,11 @@ extern "C" void ks_gpu_close(ks_gpu_ctx *c)
     if (c->st_up) cudaStreamDestroy(c->st_up);
     for (int i = 0; i < c->cfg.n_src_slots; i++) { if (c->ev_up && c->ev_up[i]) cudaEventDestroy(c->ev_up[i]); if (c->ev_src_read && c->ev_src_read[i]) cudaEventDestroy(c->ev_src_read[i]); }
     free(c->ev_up); free(c->ev_src_read);
-    free(c->d_src); free(c->d_rec); free(c->syn); free(c);
+    free(c->d_src); free(c->src_cur); free(c->d_rec); free(c->syn); free(c);
 }
 
+extern "C" void *ks265_alloc_host(size_t bytes) { void *p = NULL; return cudaHostAlloc(&p, bytes, cudaHostAllocPortable) == cudaSuccess ? p : NULL; }
+extern "C" void ks265_free_host(void *p) { if (p) cudaFreeHost(p); }
 extern "C" int ks_gpu_coded_size(const ks_gpu_ctx *c, int *w, int *h) { if (!c) return KS_EINVAL; if (w) *w = c->W; if (h) *h = c->H; return 0; }
 extern "C" uint64_t ks_gpu_launch_count(const ks_gpu_ctx *c) { return c ? c->launches : 0; }
 extern "C" void *ks_gpu_stream(ks_gpu_ctx *c) { return c ? (void *)c->st : NULL; }
@@ -255,6 +259,7 @@ extern "C" int ks_gpu_upload_frame(ks_gpu_ctx *c, int slot, const uint8_t *y, co
         CK(cudaMemcpyAsync(dst, c->h_stage[si], dsz, cudaMemcpyHostToDevice, c->st_up));
         CK(cudaEventRecord(c->ev_stage[si], c->st_up));
     }
+    c->src_cur[slot] = c->d_src[slot];
     int r = same ? 0 : extend_into_slot(c, c->d_stage, slot);
     if (r) return r;
     CK(cudaEventRecord(c->ev_up[slot], c->st_up));
@@ -265,8 +270,10 @@ extern "C" int ks_gpu_upload_frame_device(ks_gpu_ctx *c, int slot, const void *d
     if (!c || slot < 0 || slot >= c->cfg.n_src_slots || !dev_i420) return KS_EINVAL;
     CK(cudaSetDevice(c->device));
     CK(cudaStreamWaitEvent(c->st_up, c->ev_src_read[slot], 0));
-    if (c->dw == c->W && c->dh == c->H) CK(cudaMemcpyAsync(c->d_src[slot], dev_i420, c->fsz, cudaMemcpyDeviceToDevice, c->st_up));
-    else { int r = extend_into_slot(c, (const uint8_t *)dev_i420, slot); if (r) return r; }
+    /* coded size == display size: the kernels read the caller's buffer in place (no copy; the caller keeps it unchanged until the picture that
+     * uses the slot has finished); otherwise the edge-extension kernel writes the padded picture into the slot */
+    if (c->dw == c->W && c->dh == c->H && !((uintptr_t)dev_i420 & 15)) c->src_cur[slot] = (uint8_t *)dev_i420;
+    else { c->src_cur[slot] = c->d_src[slot]; int r = extend_into_slot(c, (const uint8_t *)dev_i420, slot); if (r) return r; }
     CK(cudaEventRecord(c->ev_up[slot], c->st_up));
     return 0;
 }
@@ -301,7 +308,7 @@ extern "C" int ks_gpu_encode_picture_submit(ks_gpu_ctx *c, const ks_pic_params *
     CK(cudaSetDevice(c->device));
     ks_syn_slot *s = &c->syn[p->syn_slot];
     if (s->pending) return KS_EINVAL;
-    KsPlanes src = planes_of(c, c->d_src[p->src_slot]), pre = planes_of(c, c->d_pre), out = planes_of(c, c->d_rec[p->out_slot]);
+    KsPlanes src = planes_of(c, c->src_cur[p->src_slot]), pre = planes_of(c, c->d_pre), out = planes_of(c, c->d_rec[p->out_slot]);
     KsLevels lv; lv.p[0] = c->d_lev; lv.p[1] = c->d_lev + (size_t)c->W * c->H; lv.p[2] = lv.p[1] + (size_t)c->W * c->H / 4;
     CK(cudaStreamWaitEvent(c->st, c->ev_up[p->src_slot], 0));  /* the source picture's upload (separate stream) */
     s->nev = 0;
@@ -425,7 +432,7 @@ extern "C" int ks_gpu_debug_fetch(ks_gpu_ctx *c, int what, int slot, void *dst, 
     const void *srcp; size_t need;
     if (what == KS_DBG_PRE_RECON) { srcp = c->d_pre; need = c->fsz; }
     else if (what == KS_DBG_LEVELS) { srcp = c->d_lev; need = c->fsz * 2; }
-    else if (what == KS_DBG_SRC) { if (slot < 0 || slot >= c->cfg.n_src_slots) return KS_EINVAL; srcp = c->d_src[slot]; need = c->fsz; }
+    else if (what == KS_DBG_SRC) { if (slot < 0 || slot >= c->cfg.n_src_slots) return KS_EINVAL; srcp = c->src_cur[slot]; need = c->fsz; }
     else return KS_EINVAL;
     if (bytes < need) return KS_EINVAL;
     CK(cudaMemcpy(dst, srcp, need, cudaMemcpyDeviceToHost));
@@ -439,7 +446,7 @@ extern "C" int ks_gpu_debug_me(ks_gpu_ctx *c, const ks_pic_params *p, ks_cell *c
     if (r) return r;
     CK(cudaSetDevice(c->device));
     ks_syn_slot *s = &c->syn[p->syn_slot];
-    KsPlanes src = planes_of(c, c->d_src[p->src_slot]), ref = planes_of(c, c->d_rec[p->ref_slot]);
+    KsPlanes src = planes_of(c, c->src_cur[p->src_slot]), ref = planes_of(c, c->d_rec[p->ref_slot]);
     const ks_cell *prev = p->prev_syn_slot >= 0 ? c->syn[p->prev_syn_slot].d_cells : NULL;
     KsPlanes nopred; nopred.p[0] = nopred.p[1] = nopred.p[2] = NULL;
     CK(cudaStreamWaitEvent(c->st, c->ev_up[p->src_slot], 0));

@@ -26,17 +26,36 @@ typedef struct {
 } app_cfg;
 
 typedef struct {
-    uint8_t *bs; long bs_bytes; ks265_gop_stats st; int first, n; int err;
+    uint8_t *bs; long bs_bytes; ks265_gop_stats st; int first, n; int err, done;
+    ks265_pic_stat *pics;          /* -psnr 2: per-picture table */
 } shard_t;
 
 typedef struct {
     app_cfg *a; shard_t *shards; int nshards; int next; pthread_mutex_t mu;
     int in_fd, rec_fd; size_t fsz;
+    int live_workers;              /* workers that opened an encoder */
+    double enc_ms;                 /* time inside ks265_encoder_encode_gop, summed over workers */
 } job_t;
 
 typedef struct { job_t *job; int device; } worker_arg;
+typedef struct { job_t *job; shard_t *sh; uint8_t *dst; int ok; } read_arg;
 
 static double now_ms(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+
+/* reader thread (reference: CInputYUV::startReadThread E@0x4cbe80): the next shard's pictures arrive while the current one is encoded */
+static void *reader(void *argp)
+{
+    read_arg *r = (read_arg *)argp; job_t *j = r->job;
+    size_t want = j->fsz * (size_t)r->sh->n, got = 0;
+    while (got < want) {
+        ssize_t k = pread(j->in_fd, r->dst + got, want - got, (off_t)(j->fsz * (size_t)r->sh->first + got));
+        if (k <= 0) break;
+        got += (size_t)k;
+    }
+    r->ok = got == want;
+    return NULL;
+}
+static int claim(job_t *j) { pthread_mutex_lock(&j->mu); int s = j->next < j->nshards ? j->next++ : -1; pthread_mutex_unlock(&j->mu); return s; }
 
 static void *worker(void *argp)
 {
@@ -44,22 +63,46 @@ static void *worker(void *argp)
     ks265_config cfg = a->cfg; cfg.device = wa->device;
     int err = 0;
     ks265_encoder *enc = ks265_encoder_open(&cfg, &err);
-    if (!enc) { fprintf(stderr, "appencoder: cannot open encoder on device %d (error %d)\n", wa->device, err); pthread_mutex_lock(&j->mu); for (int i = 0; i < j->nshards; i++) if (!j->shards[i].bs) j->shards[i].err = err ? err : -1; pthread_mutex_unlock(&j->mu); return NULL; }
-    int maxn = a->cfg.iper;
-    uint8_t *frames = (uint8_t *)malloc(j->fsz * maxn), *recon = j->rec_fd >= 0 ? (uint8_t *)malloc(j->fsz * maxn) : NULL;
-    size_t cap = j->fsz * maxn + (1 << 20);
-    for (;;) {
-        pthread_mutex_lock(&j->mu); int s = j->next++; pthread_mutex_unlock(&j->mu);
-        if (s >= j->nshards) break;
-        shard_t *sh = &j->shards[s];
-        if (pread(j->in_fd, frames, j->fsz * sh->n, (off_t)(j->fsz * sh->first)) != (ssize_t)(j->fsz * sh->n)) { sh->err = -5; continue; }
-        sh->bs = (uint8_t *)malloc(cap);
-        long n = ks265_encoder_encode_gop(enc, frames, NULL, sh->n, sh->bs, cap, recon, &sh->st);
-        if (n < 0) { sh->err = (int)n; continue; }
-        sh->bs_bytes = n;
-        if (recon && pwrite(j->rec_fd, recon, j->fsz * sh->n, (off_t)(j->fsz * sh->first)) < 0) sh->err = -5;
+    /* a worker that cannot open its encoder (e.g. out of device memory on the Nth stream) just leaves: the others take its shards */
+    if (!enc) { fprintf(stderr, "appencoder: cannot open an encoder on device %d (error %d)\n", wa->device, err); return NULL; }
+    pthread_mutex_lock(&j->mu); j->live_workers++; pthread_mutex_unlock(&j->mu);
+    int maxn = j->shards[0].n;     /* shard 0 is the longest */
+    /* page-locked picture buffers: the file lands where the DMA engine reads it (no staging copy) */
+    uint8_t *frames[2] = {(uint8_t *)ks265_alloc_host(j->fsz * (size_t)maxn), (uint8_t *)ks265_alloc_host(j->fsz * (size_t)maxn)};
+    uint8_t *recon = j->rec_fd >= 0 ? (uint8_t *)malloc(j->fsz * (size_t)maxn) : NULL;
+    size_t cap = j->fsz * (size_t)maxn * 2 + (1 << 20);                 /* CABAC worst case is above 1.5 bytes per sample on noise at low QP */
+    double enc_ms = 0;
+    if (!frames[0] || !frames[1] || (j->rec_fd >= 0 && !recon)) { fprintf(stderr, "appencoder: out of memory for %d-picture shard buffers\n", maxn); goto out; }
+    {
+        int cur = claim(j), b = 0;
+        read_arg ra = {j, cur >= 0 ? &j->shards[cur] : NULL, frames[0], 0};
+        if (cur >= 0) reader(&ra);
+        while (cur >= 0) {
+            shard_t *sh = &j->shards[cur];
+            int cur_ok = ra.ok, nxt = claim(j);
+            pthread_t rt; read_arg rn = {j, nxt >= 0 ? &j->shards[nxt] : NULL, frames[b ^ 1], 0};
+            if (nxt >= 0) pthread_create(&rt, NULL, reader, &rn);
+            if (!cur_ok) sh->err = -5;
+            else {
+                sh->bs = (uint8_t *)malloc(cap);
+                if (a->psnr >= 2) sh->pics = (ks265_pic_stat *)calloc((size_t)sh->n, sizeof(ks265_pic_stat));
+                ks265_encoder_set_picture_stats(enc, sh->pics, sh->pics ? sh->n : 0);
+                double t0 = now_ms();
+                long n = sh->bs ? ks265_encoder_encode_gop(enc, frames[b], NULL, sh->n, sh->bs, cap, recon, &sh->st) : -12;
+                enc_ms += now_ms() - t0;
+                if (n < 0) { sh->err = (int)n; free(sh->bs); sh->bs = NULL; }
+                else {
+                    sh->bs_bytes = n; sh->done = 1;
+                    if (recon && pwrite(j->rec_fd, recon, j->fsz * (size_t)sh->n, (off_t)(j->fsz * (size_t)sh->first)) < 0) sh->err = -5;
+                }
+            }
+            if (nxt >= 0) pthread_join(rt, NULL);
+            ra = rn; cur = nxt; b ^= 1;
+        }
     }
-    free(frames); free(recon);
+out:
+    pthread_mutex_lock(&j->mu); j->enc_ms += enc_ms; pthread_mutex_unlock(&j->mu);
+    ks265_free_host(frames[0]); ks265_free_host(frames[1]); free(recon);
     ks265_encoder_close(enc);
     return NULL;
 }
@@ -76,7 +119,7 @@ int main(int argc, char **argv)
 {
     app_cfg a; memset(&a, 0, sizeof(a));
     a.fr = 30.0; a.preset = "veryfast"; a.gpus = 1; a.streams = 4; a.frms = -1;
-    int qp = 27, iper = 128, fixqp = 0, rc = 0, sao = -1, subme = -1, merange = -1, bframes = -1, me = -1; double crf = -1;
+    int qp = 27, iper = 128, fixqp = 0, rc = 0, sao = -1, subme = -1, merange = -1, bframes = -1, me = -1, threads = 0; double crf = -1;
     for (int i = 1; i < argc; i++) {
         const char *k = argv[i], *v = i + 1 < argc ? argv[i + 1] : NULL;
         if (!strcmp(k, "-v") || !strcmp(k, "-h") || !strcmp(k, "--help")) { usage(); return 0; }
@@ -94,14 +137,15 @@ int main(int argc, char **argv)
         else if (!strcmp(k, "-me")) me = atoi(v);
         else if (!strcmp(k, "-crf")) crf = atof(v);
         else if (!strcmp(k, "-subme")) subme = atoi(v); else if (!strcmp(k, "-merange")) merange = atoi(v);
-        else if (!strcmp(k, "-threads")) { /* host worker count is -streams x -gpus here */ }
+        else if (!strcmp(k, "-threads")) threads = atoi(v);      /* host worker count is -streams x -gpus here; 1 additionally prints the reference's `pure encoding time` line */
         else fprintf(stderr, "appencoder: warning: option %s %s is accepted for compatibility and ignored on the device path\n", k, v);
     }
     if (!a.in || a.w <= 0 || a.h <= 0) { usage(); return 2; }
     if (rc != 0 && rc != 3) { fprintf(stderr, "appencoder: -rc %d (ABR/CBR) is not implemented; use -rc 0 (fixed QP) or -rc 3 (CRF)\n", rc); return 2; }
     a.cfg.width = a.w; a.cfg.height = a.h;
     if (ks265_config_default_preset(&a.cfg, a.preset)) { fprintf(stderr, "appencoder: unknown preset %s\n", a.preset); return 2; }
-    a.cfg.fps = a.fr; a.cfg.qp = qp; a.cfg.iper = iper < 1 ? 1 : iper; a.cfg.fixqp = fixqp; a.cfg.psnr = a.psnr > 0 || 1;
+    a.cfg.fps = a.fr; a.cfg.qp = qp; a.cfg.iper = iper < 1 ? 1 : iper; a.cfg.fixqp = fixqp;
+    a.cfg.psnr = 1;         /* like the reference, the summary line always carries the PSNR (it prints it without -psnr too [probe]) */
     if (sao >= 0) a.cfg.sao = sao > 4 ? 4 : sao; if (subme >= 0) a.cfg.subpel = subme > 2 ? 2 : subme; if (merange > 0) a.cfg.me_range = merange;
     if (bframes >= 0) a.cfg.bframes = bframes > 7 ? 7 : bframes;
     if (me >= 0) a.cfg.me = me > 0;
@@ -114,7 +158,8 @@ int main(int argc, char **argv)
     FILE *fi = fopen(a.in, "rb");
     if (!fi) { perror(a.in); return 1; }
     struct stat sb; fstat(fileno(fi), &sb);
-    int total = (int)(sb.st_size / (off_t)job.fsz);
+    long total_l = (long)(sb.st_size / (off_t)job.fsz);
+    int total = total_l > 0x7fffffff ? 0x7fffffff : (int)total_l;
     if (a.frms > 0 && a.frms < total) total = a.frms;
     if (total < 1) { fprintf(stderr, "appencoder: input holds no complete %dx%d frame\n", a.w, a.h); return 1; }
     job.in_fd = fileno(fi); job.rec_fd = -1;
@@ -123,8 +168,12 @@ int main(int argc, char **argv)
     job.nshards = (total + a.cfg.iper - 1) / a.cfg.iper;
     job.shards = (shard_t *)calloc(job.nshards, sizeof(shard_t));
     for (int s = 0; s < job.nshards; s++) { job.shards[s].first = s * a.cfg.iper; job.shards[s].n = total - s * a.cfg.iper < a.cfg.iper ? total - s * a.cfg.iper : a.cfg.iper; }
-    printf("ks265 B200 encoder: %dx%d %.3f fps, %d frames, preset %s, rc 0 qp %d (P %+d), iper %d, sao %d, subme %d, merange %d, %d GOP shards on %d gpu(s) x %d stream(s)\n",
-           a.w, a.h, a.fr, total, a.preset, qp, fixqp ? 0 : 1, a.cfg.iper, a.cfg.sao, a.cfg.subpel, a.cfg.me_range, job.nshards, a.gpus, a.streams);
+    /* echo of the effective configuration, `name: value` like the reference's start-up table */
+    printf("ks265 B200 encoder (AppEncoder-compatible front end)\n");
+    printf("preset: %-16s SourceWidth: %-11d SourceHeight: %-10d\nFrameRate: %-13.3f FrameToBeEncoded: %-6d IntraPeriod: %-11d\n", a.preset, a.w, a.h, a.fr, total, a.cfg.iper);
+    printf("RCType: %-16d QP: %-20d Crf: %-19.2f\nFixedQp: %-15d BiPredFrames: %-10d IntMeSearchMethod: %-5d\n", rc, qp, a.cfg.crf, fixqp, a.cfg.bframes, a.cfg.me);
+    printf("SubMeSearchMethod: %-5d SearchRange: %-11d SAO: %-19d\nActiveRefNum: 1          GopShards: %-13d Gpus x Streams: %d x %d\n", a.cfg.subpel, a.cfg.me_range, a.cfg.sao, job.nshards, a.gpus, a.streams);
+    printf("encoder test start: %s\t res %dx%d\n", a.in, a.w, a.h);
     int nw = a.gpus * a.streams; if (nw > job.nshards) nw = job.nshards;
     pthread_t *th = (pthread_t *)calloc(nw, sizeof(pthread_t)); worker_arg *wa = (worker_arg *)calloc(nw, sizeof(worker_arg));
     double t0 = now_ms();
@@ -135,7 +184,8 @@ int main(int argc, char **argv)
     uint64_t bytes = 0, sse[3] = {0, 0, 0}, launches = 0; int rcode = 0;
     for (int s = 0; s < job.nshards; s++) {
         shard_t *sh = &job.shards[s];
-        if (sh->err || !sh->bs) { fprintf(stderr, "appencoder: GOP shard %d failed (error %d)\n", s, sh->err); rcode = 1; continue; }
+        if (!sh->done || !sh->bs) { fprintf(stderr, "appencoder: GOP shard %d failed (error %d)\n", s, sh->err ? sh->err : -1); rcode = 1; continue; }
+        if (sh->err) { fprintf(stderr, "appencoder: GOP shard %d: reconstruction not written (error %d)\n", s, sh->err); rcode = 1; }
         if (fb) fwrite(sh->bs, 1, (size_t)sh->bs_bytes, fb);
         bytes += (uint64_t)sh->bs_bytes; launches += sh->st.gpu_launches;
         for (int k = 0; k < 3; k++) sse[k] += sh->st.sse[k];
@@ -153,8 +203,21 @@ int main(int argc, char **argv)
         if (f) fclose(f); free(buf);
     }
     double ms = t1 - t0, W = (double)((a.w + 15) & ~15), H = (double)((a.h + 15) & ~15), psnr[3];
+    if (a.psnr >= 2) {       /* the reference's per-picture table (coding order inside each shard) */
+        printf("poc\tslice\tbits\tpsnr\t\t\tqp\n");
+        for (int s = 0; s < job.nshards; s++) {
+            shard_t *sh = &job.shards[s];
+            for (int i = 0; sh->pics && i < sh->n; i++) {
+                const ks265_pic_stat *p = &sh->pics[i]; double q[3];
+                for (int k = 0; k < 3; k++) { double npx = k ? W * H / 4 : W * H; q[k] = p->sse[k] ? 10.0 * log10(255.0 * 255.0 * npx / (double)p->sse[k]) : 99.99; }
+                printf("%d\t%c\t%llu\t%.4f\t%.4f\t%.4f\t%d\n", sh->first + p->poc, p->slice_type == 2 ? 'I' : (p->slice_type == 1 ? 'P' : 'B'), (unsigned long long)p->bits, q[0], q[1], q[2], p->qp);
+            }
+            free(sh->pics);
+        }
+    }
     for (int k = 0; k < 3; k++) { double npx = (k ? W * H / 4 : W * H) * total; psnr[k] = sse[k] ? 10.0 * log10(255.0 * 255.0 * npx / (double)sse[k]) : 99.99; }
     printf("Total Frames: %d, test time: %.0fms, FPS: %.4f\n", total, ms, total * 1000.0 / ms);
+    if (threads == 1 && job.enc_ms > 0) printf("Total Frames: %d, pure encoding time: %.0fms, %.4f fps\n", total, job.enc_ms, total * 1000.0 / job.enc_ms);
     printf("gpu kernel launches: %llu\n", (unsigned long long)launches);
     printf("bitrate, psnr: %.4f\t%.4f\t%.4f\t%.4f\n", bytes * 8.0 * a.fr / total / 1000.0, psnr[0], psnr[1], psnr[2]);
     if (!rcode) printf("H265 encoder passed!!!\n");

@@ -18,6 +18,7 @@ struct ks265_encoder {
     ks_stream_params sp;
     void *scratch;
     int W, H;
+    ks265_pic_stat *pic_stats; int pic_stats_cap;
 };
 
 static const char *const k_presets[] = {"ultrafast", "superfast", "veryfast", "fast", "medium", "slow", "slower", "veryslow", "placebo"};
@@ -38,7 +39,8 @@ int ks265_config_default_preset(ks265_config *cfg, const char *preset)
     cfg->me_iters = p == 0 ? 8 : (p == 1 ? 12 : (p == 2 ? 16 : 32));
     cfg->subpel = p == 0 ? 1 : 2;
     cfg->satd = p >= 3;
-    cfg->me = 0;                     /* small diamond, the search the north star names; -me 1 = the reference's per-preset default (HEX) */
+    cfg->me = p >= 5 ? 1 : 0;        /* small diamond, the search the north star names (-me 1 = HEX, the reference's default up to medium); slow.. use HEX,
+                                        the closest implemented search to the reference's UMH */
     cfg->crf = 24.0;
     return 0;
 }
@@ -140,7 +142,7 @@ static long encode_gop_impl(ks265_encoder *enc, const uint8_t *frames, const voi
     const ks_stream_params *sp = &enc->sp;
     size_t fsz = (size_t)enc->cfg.width * enc->cfg.height * 3 / 2;
     int w = enc->cfg.width, h = enc->cfg.height, r, cnt = 0;
-    long pos = 0, n;
+    long pos = 0, n = 0;
     uint64_t l0c = ks_gpu_launch_count(enc->gpu), d0 = ks_gpu_d2h_bytes(enc->gpu), cg = 0;
     if (stats) memset(stats, 0, sizeof(*stats));
     coded_pic *cp = (coded_pic *)malloc(sizeof(coded_pic) * (size_t)(nframes + 1));
@@ -188,6 +190,11 @@ static long encode_gop_impl(ks265_encoder *enc, const uint8_t *frames, const voi
             pos += n;
         }
         if (stats) { stats->sse[0] += out.sse[0]; stats->sse[1] += out.sse[1]; stats->sse[2] += out.sse[2]; }
+        if (enc->pic_stats && i < enc->pic_stats_cap) {
+            ks265_pic_stat *ps = &enc->pic_stats[i];
+            ps->poc = cp[i].disp; ps->slice_type = cp[i].type; ps->qp = cp[i].pp.qp; ps->bits = bs ? (uint64_t)n * 8 : 0;
+            ps->sse[0] = out.sse[0]; ps->sse[1] = out.sse[1]; ps->sse[2] = out.sse[2];
+        }
     }
 #undef FAIL
     free(cp);
@@ -210,6 +217,8 @@ long ks265_encoder_run_gop_device(ks265_encoder *enc, const void *frames_dev, in
     if (!enc || !frames_dev || nframes < 1) return -22;
     return encode_gop_impl(enc, NULL, frames_dev, nframes, NULL, 0, NULL, stats);
 }
+
+void ks265_encoder_set_picture_stats(ks265_encoder *enc, ks265_pic_stat *stats, int cap) { if (enc) { enc->pic_stats = stats; enc->pic_stats_cap = stats ? cap : 0; } }
 
 int ks265_encoder_set_profiling(ks265_encoder *enc, int on) { return enc ? ks_gpu_set_profiling(enc->gpu, on) : -22; }
 int ks265_encoder_get_stage_times(ks265_encoder *enc, double ms[KS_NSTAGES], uint64_t launches[KS_NSTAGES]) { return enc ? ks_gpu_get_stage_times(enc->gpu, ms, launches) : -22; }

@@ -56,7 +56,7 @@ class Encoder:
         else:
             n = nframes
             hp, dp = None, C.c_void_p(device_ptr)
-        cap = self.frame_bytes * n + (1 << 20)
+        cap = self.frame_bytes * n * 2 + (1 << 20)      # CABAC worst case (noise at QP 0) is ~2.1 bytes per luma sample = 1.4 x the picture bytes
         bs = out if out is not None else np.empty(cap, np.uint8)
         rec = np.empty(self.frame_bytes * n, np.uint8) if want_recon else None
         st = Ks265GopStats()

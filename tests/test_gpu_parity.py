@@ -314,6 +314,65 @@ def test_4k_roundtrip_property():
     assert st.sse[0] == sse_y          # device-side SSE (PSNR line) agrees with the host recomputation
 
 
+def _bench_sequence(w, h, n):
+    """the benchmark's own input: bench.py's ping-pong shard of 16 generated pictures"""
+    sys.path.insert(0, ROOT)
+    import bench
+    frames = [np.frombuffer(fr, np.uint8) for fr in gen_yuv.frames(w, h, bench.DISTINCT, seed=1234)]
+    return np.concatenate([frames[i] for i in bench.shard_order(n)])
+
+
+def test_4k_full_shard_decodes_to_recon():
+    """the benchmarked workload at full size: one whole 128-picture 3840x2160 GOP shard (bench.py's sequence, POC lsb wraps at 256 not reached,
+    QP cascade, raised-lambda pictures) -> reference decoder output == our reconstruction, byte for byte"""
+    w, h, n = 3840, 2160, 128
+    yuv = _bench_sequence(w, h, n)
+    cfg = ks.default_config(w, h, preset="veryfast", qp=27, iper=128, psnr=1)
+    with ks.Encoder(cfg) as e:
+        bs, rec, st = e.encode_gop(yuv, want_recon=True)
+    assert st.frames == n
+    dec = decode_with_reference(bs, rec.size)
+    assert dec.size == rec.size
+    for f in range(n):           # picture by picture: a failure names the first bad POC
+        a, b = dec[f * (w * h * 3 // 2):(f + 1) * (w * h * 3 // 2)], rec[f * (w * h * 3 // 2):(f + 1) * (w * h * 3 // 2)]
+        assert np.array_equal(a, b), "4K shard: reference decoder output != our recon at POC %d" % f
+    sse_y = sum(int(((rec[f * (w * h * 3 // 2):f * (w * h * 3 // 2) + w * h].astype(np.int64) - yuv[f * (w * h * 3 // 2):f * (w * h * 3 // 2) + w * h]) ** 2).sum()) for f in range(n))
+    assert st.sse[0] == sse_y
+    assert 10 * np.log10(255.0 ** 2 * w * h * n / sse_y) > 34.0
+
+
+def test_1080p_long_shard_equals_oracle_and_decodes():
+    """BASELINE configs[1] size: 128-picture 1920x1080 shard -> reference decoder == recon; its first 20 pictures == the CPU model's bytes
+    (the model needs ~2.5 s per 1080p picture, so the bit-exact leg is bounded)"""
+    w, h, n, m = 1920, 1080, 128, 20
+    yuv = _bench_sequence(w, h, n)
+    cfg = ks.default_config(w, h, preset="veryfast", qp=27, iper=128, psnr=1)
+    with ks.Encoder(cfg) as e:
+        bs, rec, st = e.encode_gop(yuv, want_recon=True)
+        bsm, recm, _ = e.encode_gop(yuv[:m * w * h * 3 // 2], want_recon=True)
+    dec = decode_with_reference(bs, rec.size)
+    first_diff(dec, rec, "1080p shard: reference decoder output vs our recon")
+    obs, orec = oracle_encode(yuv[:m * w * h * 3 // 2], w, h, m, 27, 128, subpel=cfg.subpel, sbh=cfg.sign_hiding, sao=cfg.sao, iters=cfg.me_iters, satd=cfg.satd)
+    first_diff(recm, orec, "1080p recon vs oracle")
+    assert bytes(bsm) == bytes(obs)
+    assert np.array_equal(rec[:recm.size], recm), "a shard's first pictures do not depend on its length"
+
+
+def test_encoder_recovers_after_output_overflow():
+    """an encode_gop that fails with -28 (output buffer too small) must not poison the handle: the pictures in flight are dropped
+    and the next call works"""
+    w, h, n = 416, 240, 6
+    yuv = np.frombuffer(gen_yuv.make(w, h, n, seed=13), np.uint8)
+    cfg = ks.default_config(w, h, preset="veryfast", qp=22, iper=n)
+    with ks.Encoder(cfg) as e:
+        good, rec, _ = e.encode_gop(yuv, want_recon=True)
+        small = np.empty(max(4096, good.size // 3), np.uint8)
+        with pytest.raises(RuntimeError):
+            e.encode_gop(yuv, out=small)
+        again, rec2, _ = e.encode_gop(yuv, want_recon=True)
+    assert bytes(again) == bytes(good) and np.array_equal(rec, rec2)
+
+
 def test_8k_roundtrip_property():
     """BASELINE configs[4] size (7680x4320): one IDR + one P picture decode with the reference decoder to exactly our recon"""
     w, h, n = 7680, 4320, 2
