@@ -156,43 +156,49 @@ static void build_nb(const ora_cfg *cfg, const ora_plane *rec, int comp, int x0,
     if (!av[0]) { int i = 1; while (!av[i]) i++; nb[0] = nb[i]; }
     for (int i = 1; i < tot; i++) if (!av[i]) nb[i] = nb[i - 1];
 }
+/* one 16x16 intra CU: 35-mode decision by SAD + lambda*bits against the reconstructed neighbours, then luma + chroma (DM) residual coding */
+static void intra_cell(const ora_cfg *cfg, int qp, int intra_slice, const ora_pic *src, ora_pic *rec, ks_cell *cells, ora_levels *lv, int x0, int y0)
+{
+    int cw = cfg->width >> 4, W = cfg->width;
+    int lam = ora_lambda_sad_q4[qp], qpc = ora_chroma_qp[qp];
+    uint8_t nb[65], pred[256];
+    const uint8_t *s = src->c[0].p + (size_t)y0 * src->c[0].stride + x0;
+    build_nb(cfg, &rec->c[0], 0, x0, y0, 16, nb);
+    int best = 0, best_cost = 0x7fffffff;
+    for (int m = 0; m < 35; m++) {
+        ora_intra_pred(pred, 16, nb, 4, m, 1, cfg->strong_intra);
+        int bits = (m == 0 || m == 1 || m == 10 || m == 26) ? 3 : 6;
+        int cost = (int)ora_sad(s, pred, src->c[0].stride, 16, 16, 16) + ((lam * bits) >> 4);
+        if (cost < best_cost) { best_cost = cost; best = m; }
+    }
+    ora_intra_pred(pred, 16, nb, 4, best, 1, cfg->strong_intra);
+    ks_cell *c = &cells[(y0 >> 4) * cw + (x0 >> 4)];
+    memset(c, 0, sizeof(*c));
+    c->cu_log2 = 4; c->flags = KS_F_INTRA; c->intra_mode = (uint8_t)best;
+    uint8_t *r = rec->c[0].p + (size_t)y0 * rec->c[0].stride + x0;
+    if (code_tb(cfg, qp, intra_slice, 4, 0, s, src->c[0].stride, pred, 16, r, rec->c[0].stride, lv->c[0] + (size_t)y0 * W + x0, W, 0)) c->flags |= KS_F_CBF_Y;
+    for (int ci = 1; ci < 3; ci++) {
+        int xc = x0 >> 1, yc = y0 >> 1;
+        uint8_t nbc[33], pc[64];
+        build_nb(cfg, &rec->c[ci], ci, xc, yc, 8, nbc);
+        ora_intra_pred(pc, 8, nbc, 3, best, 0, 0);
+        const uint8_t *sc = src->c[ci].p + (size_t)yc * src->c[ci].stride + xc;
+        uint8_t *rc = rec->c[ci].p + (size_t)yc * rec->c[ci].stride + xc;
+        if (code_tb(cfg, qpc, intra_slice, 3, 0, sc, src->c[ci].stride, pc, 8, rc, rec->c[ci].stride, lv->c[ci] + (size_t)yc * (W / 2) + xc, W / 2, 0))
+            c->flags |= ci == 1 ? KS_F_CBF_CB : KS_F_CBF_CR;
+    }
+}
 void ora_intra_picture(const ora_cfg *cfg, int qp, const ora_pic *src, ora_pic *rec, ks_cell *cells, ora_levels *lv)
 {
     build_scans();
-    int cw = cfg->width >> 4, W = cfg->width, H = cfg->height;
+    int W = cfg->width, H = cfg->height;
     int ctus_w = (W + 63) >> 6, ctus_h = (H + 63) >> 6;
-    int lam = ora_lambda_sad_q4[qp], qpc = ora_chroma_qp[qp];
     for (int cty = 0; cty < ctus_h; cty++) for (int ctx = 0; ctx < ctus_w; ctx++)
         for (int z = 0; z < 16; z++) {
             int cx = (z & 1) | ((z >> 1) & 2), cy = ((z >> 1) & 1) | ((z >> 2) & 2);
             int x0 = (ctx << 6) + (cx << 4), y0 = (cty << 6) + (cy << 4);
             if (x0 >= W || y0 >= H) continue;
-            uint8_t nb[65], pred[256];
-            const uint8_t *s = src->c[0].p + (size_t)y0 * src->c[0].stride + x0;
-            build_nb(cfg, &rec->c[0], 0, x0, y0, 16, nb);
-            int best = 0, best_cost = 0x7fffffff;
-            for (int m = 0; m < 35; m++) {
-                ora_intra_pred(pred, 16, nb, 4, m, 1, cfg->strong_intra);
-                int bits = (m == 0 || m == 1 || m == 10 || m == 26) ? 3 : 6;
-                int cost = (int)ora_sad(s, pred, src->c[0].stride, 16, 16, 16) + ((lam * bits) >> 4);
-                if (cost < best_cost) { best_cost = cost; best = m; }
-            }
-            ora_intra_pred(pred, 16, nb, 4, best, 1, cfg->strong_intra);
-            ks_cell *c = &cells[(y0 >> 4) * cw + (x0 >> 4)];
-            memset(c, 0, sizeof(*c));
-            c->cu_log2 = 4; c->flags = KS_F_INTRA; c->intra_mode = (uint8_t)best;
-            uint8_t *r = rec->c[0].p + (size_t)y0 * rec->c[0].stride + x0;
-            if (code_tb(cfg, qp, 1, 4, 0, s, src->c[0].stride, pred, 16, r, rec->c[0].stride, lv->c[0] + (size_t)y0 * W + x0, W, 0)) c->flags |= KS_F_CBF_Y;
-            for (int ci = 1; ci < 3; ci++) {
-                int xc = x0 >> 1, yc = y0 >> 1;
-                uint8_t nbc[33], pc[64];
-                build_nb(cfg, &rec->c[ci], ci, xc, yc, 8, nbc);
-                ora_intra_pred(pc, 8, nbc, 3, best, 0, 0);
-                const uint8_t *sc = src->c[ci].p + (size_t)yc * src->c[ci].stride + xc;
-                uint8_t *rc = rec->c[ci].p + (size_t)yc * rec->c[ci].stride + xc;
-                if (code_tb(cfg, qpc, 1, 3, 0, sc, src->c[ci].stride, pc, 8, rc, rec->c[ci].stride, lv->c[ci] + (size_t)yc * (W / 2) + xc, W / 2, 0))
-                    c->flags |= ci == 1 ? KS_F_CBF_CB : KS_F_CBF_CR;
-            }
+            intra_cell(cfg, qp, 1, src, rec, cells, lv, x0, y0);
         }
 }
 
