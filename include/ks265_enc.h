@@ -67,6 +67,12 @@ void ks265_encoder_set_picture_stats(ks265_encoder *enc, ks265_pic_stat *stats, 
 /* page-locked host memory for picture buffers: pictures handed to encode_gop from such a buffer are DMA-ed in place (no staging copy) */
 void *ks265_alloc_host(size_t bytes);
 void ks265_free_host(void *p);
+/* the same GOP shard with the pictures PULLED through a callback: `read_picture(opaque, display_index, dst)` fills dst with one display-size
+ * I420 picture (dst is page-locked staging memory of the device context: a file read lands where the DMA engine picks it up) and returns 0.
+ * The reference's counterpart is its reader thread (CInputYUV::startReadThread E@0x4cbe80) feeding QY265EncoderEncodeFrame. */
+typedef int (*ks265_read_fn)(void *opaque, int display_index, uint8_t *dst);
+long ks265_encoder_encode_gop_cb(ks265_encoder *enc, ks265_read_fn read_picture, void *opaque, int nframes,
+                                 uint8_t *bs, size_t bs_cap, uint8_t *recon, ks265_gop_stats *stats);
 /* per-stage device times accumulated since `on` (see ks_gpu_get_stage_times) */
 int  ks265_encoder_set_profiling(ks265_encoder *enc, int on);
 int  ks265_encoder_get_stage_times(ks265_encoder *enc, double ms[7], uint64_t launches[7]);   /* KS_NSTAGES entries */

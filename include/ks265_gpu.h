@@ -78,6 +78,10 @@ void ks_gpu_close(ks_gpu_ctx *ctx);
 int  ks_gpu_coded_size(const ks_gpu_ctx *ctx, int *width, int *height);
 /* replaces: ctuCacheLoadSrcYuv (EncCtuCache.cpp) -- host planes -> device source slot (pinned staging + async H2D) */
 int  ks_gpu_upload_frame(ks_gpu_ctx *ctx, int slot, const uint8_t *y, const uint8_t *u, const uint8_t *v, int stride_y, int stride_uv);
+/* same without a caller-side picture buffer: acquire the context's next page-locked staging buffer (display-size I420, tightly packed), fill it
+ * (e.g. read() a file straight into it), then start its H2D into `slot`.  Two buffers alternate; acquire waits for the buffer's previous copy. */
+uint8_t *ks_gpu_stage_acquire(ks_gpu_ctx *ctx);
+int  ks_gpu_upload_staged(ks_gpu_ctx *ctx, int slot);
 /* same, but the I420 picture (display size, tightly packed) already lives in device memory.  When the display size is already a multiple of 16
  * (and the pointer 16-byte aligned) the kernels read it IN PLACE -- no copy; the caller keeps it unchanged until the picture has finished */
 int  ks_gpu_upload_frame_device(ks_gpu_ctx *ctx, int slot, const void *dev_i420);

@@ -4,20 +4,20 @@
  *
  * The motion search (ks_me_kernel) works per 16x16 cell against a temporal predictor, so its field is spatially noisy and every cell would pay
  * an mvd.  This kernel makes the field coherent without giving up picture-level parallelism: one CTA per CTU,
- *   stage E  (16 warps, one per cell)  one candidate list per CTU = the search results of its own cells (z-order), zero, the cells bordering
+ *   stage E  (8 warps, two cells each)  one candidate list per CTU = the search results of its own cells (z-order), zero, the cells bordering
  *            it on the left / above (distinct vectors, <= KS_NCAND); every cell measures the search metric of EVERY list entry with the real
  *            8-tap interpolation (one 40x52 window serves all candidates that land inside it);
  *   stage D  (warp 0, lane = candidate)  64 -> 32 -> 16 quadtree in coding order by J = distortion + lambda * bits, bits from the 2Nx2N merge
  *            list / AMVP predictors of the vectors decided so far (cells of other CTUs count with their search results: Jacobi across
  *            CTUs, Gauss-Seidel inside one);
- *   stage F  (16 warps)  cells whose vector changed get their luma + chroma prediction rewritten.
+ *   stage F  (8 warps)  cells whose vector changed get their luma + chroma prediction rewritten.
  * Bit-exact mirror of oracle/ora_frame.c: decide_candidates / decide_ctu.
  */
 #pragma once
 #include "ks_me.cuh"
 
 #define KS_NCAND 16
-#define KS_DECIDE_WARPS 16
+#define KS_DECIDE_WARPS 8            /* two cells per warp: 4 CTAs per SM instead of 2, so the serial stage D of one CTU idles 7 warps, not 15 */
 
 struct KsDecideSmem {
     KsWarpScratch sc[KS_DECIDE_WARPS];
@@ -94,7 +94,7 @@ __device__ __forceinline__ void ks_decide_commit(KsDecideSmem *sm, int i, int j,
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(KS_DECIDE_WARPS * KS_WARP, 2)
+__global__ void __launch_bounds__(KS_DECIDE_WARPS * KS_WARP, 4)
 ks_decide_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref, const ks_cell *__restrict__ mv0, const int *__restrict__ dist0,
                  ks_cell *__restrict__ cells, KsPlanes pred)
 {
@@ -137,19 +137,19 @@ ks_decide_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref,
         }
     }
     __syncthreads();
-    /* ---- stage E: this warp's cell against every candidate ---- */
-    const int ci = warp & 3, cj = warp >> 2, cx = X + ci, cy = Y + cj, x0 = cx << 4, y0 = cy << 4;
-    const bool inside = cx < cw && cy < ch;
+    /* ---- stage E: this warp's cells against every candidate ---- */
     KsWarpScratch *sc = &sm->sc[warp];
-    ks_cell own; own.mvx = own.mvy = 0;
-    uint2 s = make_uint2(0u, 0u);
-    int wx0 = 0, wy0 = 0;
     const bool satd = pp.satd && pp.subpel > 0;
-    if (inside) {
-        own = mv0[cy * cw + cx];
+#pragma unroll 1
+    for (int cell = warp; cell < 16; cell += KS_DECIDE_WARPS) {
+        const int ci = cell & 3, cj = cell >> 2, cx = X + ci, cy = Y + cj, x0 = cx << 4, y0 = cy << 4;
+        if (cx >= cw || cy >= ch) continue;
+        const ks_cell own = mv0[cy * cw + cx];
         const int d0 = dist0[cy * cw + cx];
-        s = *reinterpret_cast<const uint2 *>(srcY + (size_t)(y0 + (lane >> 1)) * W + x0 + 8 * (lane & 1));
+        const uint2 s = *reinterpret_cast<const uint2 *>(srcY + (size_t)(y0 + (lane >> 1)) * W + x0 + 8 * (lane & 1));
+        int wx0, wy0;
         ks_center_window(x0, y0, own.mvx >> 2, own.mvy >> 2, wx0, wy0);
+        __syncwarp();
         ks_load_window(sc->win, ref.p[0], W, H, wx0, wy0, lane);
         const int n = sm->n;
 #pragma unroll 1
@@ -161,6 +161,7 @@ ks_decide_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref,
                 int bxw = x0 + (mx >> 2) - wx0, byw = y0 + (my >> 2) - wy0;
                 if (bxw < 4 || bxw > 27 || byw < 4 || byw > 19) {
                     ks_center_window(x0, y0, mx >> 2, my >> 2, wx0, wy0);
+                    __syncwarp();
                     ks_load_window(sc->win, ref.p[0], W, H, wx0, wy0, lane);
                     bxw = x0 + (mx >> 2) - wx0; byw = y0 + (my >> 2) - wy0;
                 }
@@ -168,7 +169,7 @@ ks_decide_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref,
                 ks_interp16(sc, bxw, byw, mx & 3, my & 3, lane, o0, o1);
                 d = satd ? (int)ks_satd16(o0, o1, s.x, s.y, lane) : (int)ks_warp_sum(__vsadu4(o0, s.x) + __vsadu4(o1, s.y));
             }
-            if (lane == 0) sm->dist[warp][k] = d;
+            if (lane == 0) sm->dist[cell][k] = d;
         }
     }
     __syncthreads();
@@ -204,22 +205,23 @@ ks_decide_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes ref,
     }
     __syncthreads();
     /* ---- final cells + stage F: re-predict the cells whose vector changed ---- */
-    if (!inside) return;
-    const int fmx = sm->smx[cj + 1][ci + 1], fmy = sm->smy[cj + 1][ci + 1];
-    if (lane == 0) {
-        ks_cell c; c.mvx = (int16_t)fmx; c.mvy = (int16_t)fmy; c.cu_log2 = sm->slog2[cj * 4 + ci]; c.flags = 0; c.intra_mode = 0; c.rsv = 0;
-        cells[cy * cw + cx] = c;
-    }
-    if (fmx == own.mvx && fmy == own.mvy) return;
-    {
-        int bxw = x0 + (fmx >> 2) - wx0, byw = y0 + (fmy >> 2) - wy0;
-        if (bxw < 4 || bxw > 27 || byw < 4 || byw > 19) {
-            ks_center_window(x0, y0, fmx >> 2, fmy >> 2, wx0, wy0);
-            ks_load_window(sc->win, ref.p[0], W, H, wx0, wy0, lane);
-            bxw = x0 + (fmx >> 2) - wx0; byw = y0 + (fmy >> 2) - wy0;
+#pragma unroll 1
+    for (int cell = warp; cell < 16; cell += KS_DECIDE_WARPS) {
+        const int ci = cell & 3, cj = cell >> 2, cx = X + ci, cy = Y + cj, x0 = cx << 4, y0 = cy << 4;
+        if (cx >= cw || cy >= ch) continue;
+        const ks_cell own = mv0[cy * cw + cx];
+        const int fmx = sm->smx[cj + 1][ci + 1], fmy = sm->smy[cj + 1][ci + 1];
+        if (lane == 0) {
+            ks_cell c; c.mvx = (int16_t)fmx; c.mvy = (int16_t)fmy; c.cu_log2 = sm->slog2[cell]; c.flags = 0; c.intra_mode = 0; c.rsv = 0;
+            cells[cy * cw + cx] = c;
         }
+        if (fmx == own.mvx && fmy == own.mvy) continue;
+        int wx0, wy0;
+        ks_center_window(x0, y0, fmx >> 2, fmy >> 2, wx0, wy0);
+        __syncwarp();
+        ks_load_window(sc->win, ref.p[0], W, H, wx0, wy0, lane);
         uint32_t o0, o1;
-        ks_interp16(sc, bxw, byw, fmx & 3, fmy & 3, lane, o0, o1);
+        ks_interp16(sc, x0 + (fmx >> 2) - wx0, y0 + (fmy >> 2) - wy0, fmx & 3, fmy & 3, lane, o0, o1);
         *reinterpret_cast<uint2 *>(pred.p[0] + (size_t)(y0 + (lane >> 1)) * W + x0 + 8 * (lane & 1)) = make_uint2(o0, o1);
         const int CW = W >> 1, CH = H >> 1;
 #pragma unroll 1

@@ -42,6 +42,7 @@ struct ks_gpu_ctx {
     ks_cell *d_cells1; int *d_cost0, *d_cost1;   /* d_cells1: list-1 field (B) / search field before the CU decision (P); d_cost0 doubles as its distortions */
     int16_t *d_lev;
     uint32_t *d_counts;
+    uint32_t *d_sse_ctu;         /* per-CTU squared error partial sums (SAO kernel -> pack scan kernel) */
     int *d_sync;
     uint8_t *d_stage;           /* display-size I420 staging on device (upload + edge extension) */
     uint8_t *h_stage[2];        /* pinned, double-buffered */
@@ -137,6 +138,7 @@ extern "C" ks_gpu_ctx *ks_gpu_open(int device, int width, int height, const ks_g
         ok = ok && cudaMalloc(&c->d_cost1, (size_t)c->cw * c->ch * sizeof(int)) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_lev, c->fsz * 2) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_counts, sizeof(uint32_t) * c->ctw * c->cth) == cudaSuccess;
+        ok = ok && cudaMalloc(&c->d_sse_ctu, sizeof(uint32_t) * 3 * c->ctw * c->cth) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_sync, sizeof(int) * ((size_t)c->ctw * c->cth + 1)) == cudaSuccess;
         size_t dsz = (size_t)width * height * 3 / 2;
         ok = ok && cudaMalloc(&c->d_stage, dsz) == cudaSuccess;
@@ -181,7 +183,7 @@ extern "C" void ks_gpu_close(ks_gpu_ctx *c)
     if (c->st) cudaStreamSynchronize(c->st);
     if (c->d_src) for (int i = 0; i < c->cfg.n_src_slots; i++) cudaFree(c->d_src[i]);
     if (c->d_rec) for (int i = 0; i < c->cfg.n_rec_slots; i++) cudaFree(c->d_rec[i]);
-    cudaFree(c->d_pre); cudaFree(c->d_pred); cudaFree(c->d_pred1); cudaFree(c->d_cells1); cudaFree(c->d_cost0); cudaFree(c->d_cost1); cudaFree(c->d_lev); cudaFree(c->d_counts); cudaFree(c->d_sync); cudaFree(c->d_stage);
+    cudaFree(c->d_pre); cudaFree(c->d_pred); cudaFree(c->d_pred1); cudaFree(c->d_cells1); cudaFree(c->d_cost0); cudaFree(c->d_cost1); cudaFree(c->d_lev); cudaFree(c->d_counts); cudaFree(c->d_sse_ctu); cudaFree(c->d_sync); cudaFree(c->d_stage);
     for (int i = 0; i < 2; i++) { if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]); if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]); }
     if (c->syn) for (int i = 0; i < c->cfg.n_syn_slots; i++) {
         ks_syn_slot *s = &c->syn[i];
@@ -259,6 +261,28 @@ extern "C" int ks_gpu_upload_frame(ks_gpu_ctx *c, int slot, const uint8_t *y, co
         CK(cudaMemcpyAsync(dst, c->h_stage[si], dsz, cudaMemcpyHostToDevice, c->st_up));
         CK(cudaEventRecord(c->ev_stage[si], c->st_up));
     }
+    c->src_cur[slot] = c->d_src[slot];
+    int r = same ? 0 : extend_into_slot(c, c->d_stage, slot);
+    if (r) return r;
+    CK(cudaEventRecord(c->ev_up[slot], c->st_up));
+    return 0;
+}
+extern "C" uint8_t *ks_gpu_stage_acquire(ks_gpu_ctx *c)
+{
+    if (!c || cudaSetDevice(c->device) != cudaSuccess) return NULL;
+    if (cudaEventSynchronize(c->ev_stage[c->stage_idx]) != cudaSuccess) return NULL;      /* this buffer's previous H2D must be done */
+    return c->h_stage[c->stage_idx];
+}
+extern "C" int ks_gpu_upload_staged(ks_gpu_ctx *c, int slot)
+{
+    if (!c || slot < 0 || slot >= c->cfg.n_src_slots) return KS_EINVAL;
+    CK(cudaSetDevice(c->device));
+    const size_t dsz = (size_t)c->dw * c->dh * 3 / 2;
+    const bool same = c->dw == c->W && c->dh == c->H;
+    const int si = c->stage_idx; c->stage_idx ^= 1;
+    CK(cudaStreamWaitEvent(c->st_up, c->ev_src_read[slot], 0));
+    CK(cudaMemcpyAsync(same ? c->d_src[slot] : c->d_stage, c->h_stage[si], dsz, cudaMemcpyHostToDevice, c->st_up));
+    CK(cudaEventRecord(c->ev_stage[si], c->st_up));
     c->src_cur[slot] = c->d_src[slot];
     int r = same ? 0 : extend_into_slot(c, c->d_stage, slot);
     if (r) return r;
@@ -346,12 +370,11 @@ extern "C" int ks_gpu_encode_picture_submit(ks_gpu_ctx *c, const ks_pic_params *
     s->is_b = p->slice_type == KS_SLICE_B;
     MARK(3);
     ks_launch_deblock(pp, pre, s->d_cells, s->is_b ? s->d_cells_b : NULL, c->st); c->launches += KS_LAUNCHES_DEBLOCK;
-    if (p->want_sse) CK(cudaMemsetAsync(s->d_sse, 0, 3 * sizeof(unsigned long long), c->st));
     MARK(4);
-    ks_launch_sao(pp, src, pre, out, s->d_ctus, p->want_sse ? s->d_sse : NULL, c->tm_pre, c->tma_mask, c->st); c->launches += KS_LAUNCHES_SAO - 1;
+    ks_launch_sao(pp, src, pre, out, s->d_ctus, p->want_sse ? c->d_sse_ctu : NULL, c->tm_pre, c->tma_mask, c->st); c->launches += KS_LAUNCHES_SAO - 1;
     CK(cudaEventRecord(c->ev_src_read[p->src_slot], c->st));   /* SAO was the last stage to read the source picture */
     MARK(5);
-    ks_launch_pack(pp, lv, s->d_ctus, s->d_pool, s->d_ncg, c->d_counts, c->st); c->launches += KS_LAUNCHES_PACK;
+    ks_launch_pack(pp, lv, s->d_ctus, s->d_pool, s->d_ncg, c->d_counts, p->want_sse ? c->d_sse_ctu : NULL, s->d_sse, c->st); c->launches += KS_LAUNCHES_PACK;
     MARK(-1);
 #undef MARK
     CK(cudaGetLastError());

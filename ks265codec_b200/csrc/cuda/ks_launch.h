@@ -40,8 +40,9 @@ void ks_launch_recon_inter(const KsPicParams &pp, KsPlanes src, KsPlanes pred, K
 void ks_launch_recon_intra(const KsPicParams &pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *cells, int *sync_ws, cudaStream_t st);
 void ks_launch_deblock(const KsPicParams &pp, KsPlanes rec, const ks_cell *cells, const ks_cell_b *cells_b, cudaStream_t st);
 /* tm[3]: tensor maps of the three `deb` planes (box 96x66 / 64x34 bytes); tma_mask bit c = component c is staged by TMA */
-void ks_launch_sao(const KsPicParams &pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_syn *ctus, unsigned long long *sse_out,
+/* sse_ctu: per-CTU squared error of the three planes (3 x u32 per CTU) or NULL; ks_launch_pack sums them into the picture SSE */
+void ks_launch_sao(const KsPicParams &pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_syn *ctus, uint32_t *sse_ctu,
                    const CUtensorMap *tm, int tma_mask, cudaStream_t st);
-void ks_launch_pack(const KsPicParams &pp, KsLevels lv, ks_ctu_syn *ctus, int16_t *pool, uint32_t *n_cg, uint32_t *scan_ws, cudaStream_t st);
+void ks_launch_pack(const KsPicParams &pp, KsLevels lv, ks_ctu_syn *ctus, int16_t *pool, uint32_t *n_cg, uint32_t *scan_ws, const uint32_t *sse_ctu, unsigned long long *sse_out, cudaStream_t st);
 /* number of kernel launches each stage issues (for bench.py's gpu_launches accounting) */
 enum { KS_LAUNCHES_DECIDE = 1, KS_LAUNCHES_ME = 1, KS_LAUNCHES_RECON = 1, KS_LAUNCHES_DEBLOCK = 2, KS_LAUNCHES_SAO = 2, KS_LAUNCHES_PACK = 3 };

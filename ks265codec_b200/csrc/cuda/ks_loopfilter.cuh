@@ -260,7 +260,7 @@ __device__ __forceinline__ void ks_mbar_wait(unsigned long long *bar, unsigned p
 }
 
 __global__ void __launch_bounds__(KS_SAO_WARPS * KS_WARP)
-ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_syn *__restrict__ ctus, unsigned long long *sse_out,
+ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_syn *__restrict__ ctus, uint32_t *__restrict__ sse_out,
               const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmCb, const __grid_constant__ CUtensorMap tmCr, int tma_mask)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -436,13 +436,13 @@ ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_s
             if (lane == 0) atomicAdd(&sm->sse[ci], (unsigned long long)lo);
         }
     }
-    if (sse_out) {
+    if (sse_out) {       /* per-CTU partial sums (<= 64*64*255^2 fits 32 bits); ks_pack_scan_kernel adds them up: no contended global atomics */
         __syncthreads();
-        if (tid < 3) atomicAdd(&sse_out[tid], sm->sse[tid]);
+        if (tid < 3) sse_out[(ry * pp.ctw + rx) * 3 + tid] = (uint32_t)sm->sse[tid];
     }
 }
 
-void ks_launch_sao(const KsPicParams &pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_syn *ctus, unsigned long long *sse_out,
+void ks_launch_sao(const KsPicParams &pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_syn *ctus, uint32_t *sse_out,
                    const CUtensorMap *tm, int tma_mask, cudaStream_t st)
 {
     alignas(64) CUtensorMap m[3];                   /* the caller's copy may sit at any alignment */

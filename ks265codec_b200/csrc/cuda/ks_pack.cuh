@@ -48,9 +48,21 @@ ks_pack_count_kernel(KsPicParams pp, KsLevels lv, ks_ctu_syn *__restrict__ ctus,
 
 /* exclusive scan of the per-CTU counts (<= 8160 CTUs at 8K): one block */
 __global__ void __launch_bounds__(1024)
-ks_pack_scan_kernel(int nctu, const uint32_t *__restrict__ counts, ks_ctu_syn *__restrict__ ctus, uint32_t *__restrict__ n_cg)
+ks_pack_scan_kernel(int nctu, const uint32_t *__restrict__ counts, ks_ctu_syn *__restrict__ ctus, uint32_t *__restrict__ n_cg,
+                    const uint32_t *__restrict__ sse_ctu, unsigned long long *__restrict__ sse_out)
 {
     __shared__ uint32_t part[1024];
+    if (sse_ctu) {       /* picture SSE = sum of the SAO kernel's per-CTU partial sums (three planes) */
+        __shared__ unsigned long long acc[3];
+        if (threadIdx.x < 3) acc[threadIdx.x] = 0;
+        __syncthreads();
+        unsigned long long a0 = 0, a1 = 0, a2 = 0;
+        for (int i = threadIdx.x; i < nctu; i += 1024) { a0 += sse_ctu[3 * i]; a1 += sse_ctu[3 * i + 1]; a2 += sse_ctu[3 * i + 2]; }
+        for (int o = 16; o; o >>= 1) { a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&acc[0], a0); atomicAdd(&acc[1], a1); atomicAdd(&acc[2], a2); }
+        __syncthreads();
+        if (threadIdx.x < 3) sse_out[threadIdx.x] = acc[threadIdx.x];
+    }
     const int tid = threadIdx.x, per = (nctu + 1023) / 1024, b = tid * per, e = min(b + per, nctu);
     uint32_t s = 0;
     for (int i = b; i < e; i++) s += counts[i];
@@ -85,10 +97,10 @@ ks_pack_write_kernel(KsPicParams pp, KsLevels lv, const ks_ctu_syn *__restrict__
     for (int j = 0; j < 4; j++) d[j] = *reinterpret_cast<const unsigned long long *>(s + (size_t)j * PW);
 }
 
-void ks_launch_pack(const KsPicParams &pp, KsLevels lv, ks_ctu_syn *ctus, int16_t *pool, uint32_t *n_cg, uint32_t *scan_ws, cudaStream_t st)
+void ks_launch_pack(const KsPicParams &pp, KsLevels lv, ks_ctu_syn *ctus, int16_t *pool, uint32_t *n_cg, uint32_t *scan_ws, const uint32_t *sse_ctu, unsigned long long *sse_out, cudaStream_t st)
 {
     dim3 grid(pp.ctw, pp.cth);
     ks_pack_count_kernel<<<grid, 384, 0, st>>>(pp, lv, ctus, scan_ws);
-    ks_pack_scan_kernel<<<1, 1024, 0, st>>>(pp.ctw * pp.cth, scan_ws, ctus, n_cg);
+    ks_pack_scan_kernel<<<1, 1024, 0, st>>>(pp.ctw * pp.cth, scan_ws, ctus, n_cg, sse_ctu, sse_out);
     ks_pack_write_kernel<<<grid, 384, 0, st>>>(pp, lv, ctus, pool);
 }

@@ -38,22 +38,22 @@ typedef struct {
 } job_t;
 
 typedef struct { job_t *job; int device; } worker_arg;
-typedef struct { job_t *job; shard_t *sh; uint8_t *dst; int ok; } read_arg;
+typedef struct { job_t *job; shard_t *sh; } read_arg;
 
 static double now_ms(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
 
-/* reader thread (reference: CInputYUV::startReadThread E@0x4cbe80): the next shard's pictures arrive while the current one is encoded */
-static void *reader(void *argp)
+/* picture source of one shard (reference: CInputYUV::startReadThread E@0x4cbe80 + readOneFrame): the encoder pulls picture i+1 while the device
+ * works on picture i, straight into page-locked staging memory -- no shard-sized buffers, no extra copy */
+static int read_picture(void *opaque, int disp, uint8_t *dst)
 {
-    read_arg *r = (read_arg *)argp; job_t *j = r->job;
-    size_t want = j->fsz * (size_t)r->sh->n, got = 0;
-    while (got < want) {
-        ssize_t k = pread(j->in_fd, r->dst + got, want - got, (off_t)(j->fsz * (size_t)r->sh->first + got));
-        if (k <= 0) break;
+    read_arg *r = (read_arg *)opaque; job_t *j = r->job;
+    size_t got = 0;
+    while (got < j->fsz) {
+        ssize_t k = pread(j->in_fd, dst + got, j->fsz - got, (off_t)(j->fsz * (size_t)(r->sh->first + disp) + got));
+        if (k <= 0) return -1;
         got += (size_t)k;
     }
-    r->ok = got == want;
-    return NULL;
+    return 0;
 }
 static int claim(job_t *j) { pthread_mutex_lock(&j->mu); int s = j->next < j->nshards ? j->next++ : -1; pthread_mutex_unlock(&j->mu); return s; }
 
@@ -67,42 +67,34 @@ static void *worker(void *argp)
     if (!enc) { fprintf(stderr, "appencoder: cannot open an encoder on device %d (error %d)\n", wa->device, err); return NULL; }
     pthread_mutex_lock(&j->mu); j->live_workers++; pthread_mutex_unlock(&j->mu);
     int maxn = j->shards[0].n;     /* shard 0 is the longest */
-    /* page-locked picture buffers: the file lands where the DMA engine reads it (no staging copy) */
-    uint8_t *frames[2] = {(uint8_t *)ks265_alloc_host(j->fsz * (size_t)maxn), (uint8_t *)ks265_alloc_host(j->fsz * (size_t)maxn)};
     uint8_t *recon = j->rec_fd >= 0 ? (uint8_t *)malloc(j->fsz * (size_t)maxn) : NULL;
-    size_t cap = j->fsz * (size_t)maxn * 2 + (1 << 20);                 /* CABAC worst case is above 1.5 bytes per sample on noise at low QP */
+    size_t cap = j->fsz * (size_t)maxn / 2 + (4 << 20);                 /* grown and retried on -28 (CABAC worst case is ~1.4 x the picture bytes) */
+    uint8_t *bsbuf = (uint8_t *)malloc(cap);
     double enc_ms = 0;
-    if (!frames[0] || !frames[1] || (j->rec_fd >= 0 && !recon)) { fprintf(stderr, "appencoder: out of memory for %d-picture shard buffers\n", maxn); goto out; }
-    {
-        int cur = claim(j), b = 0;
-        read_arg ra = {j, cur >= 0 ? &j->shards[cur] : NULL, frames[0], 0};
-        if (cur >= 0) reader(&ra);
-        while (cur >= 0) {
-            shard_t *sh = &j->shards[cur];
-            int cur_ok = ra.ok, nxt = claim(j);
-            pthread_t rt; read_arg rn = {j, nxt >= 0 ? &j->shards[nxt] : NULL, frames[b ^ 1], 0};
-            if (nxt >= 0) pthread_create(&rt, NULL, reader, &rn);
-            if (!cur_ok) sh->err = -5;
-            else {
-                sh->bs = (uint8_t *)malloc(cap);
-                if (a->psnr >= 2) sh->pics = (ks265_pic_stat *)calloc((size_t)sh->n, sizeof(ks265_pic_stat));
-                ks265_encoder_set_picture_stats(enc, sh->pics, sh->pics ? sh->n : 0);
-                double t0 = now_ms();
-                long n = sh->bs ? ks265_encoder_encode_gop(enc, frames[b], NULL, sh->n, sh->bs, cap, recon, &sh->st) : -12;
-                enc_ms += now_ms() - t0;
-                if (n < 0) { sh->err = (int)n; free(sh->bs); sh->bs = NULL; }
-                else {
-                    sh->bs_bytes = n; sh->done = 1;
-                    if (recon && pwrite(j->rec_fd, recon, j->fsz * (size_t)sh->n, (off_t)(j->fsz * (size_t)sh->first)) < 0) sh->err = -5;
-                }
-            }
-            if (nxt >= 0) pthread_join(rt, NULL);
-            ra = rn; cur = nxt; b ^= 1;
+    if (!bsbuf || (j->rec_fd >= 0 && !recon)) { fprintf(stderr, "appencoder: out of memory for %d-picture shard buffers\n", maxn); goto out; }
+    for (int cur = claim(j); cur >= 0; cur = claim(j)) {
+        shard_t *sh = &j->shards[cur];
+        read_arg ra = {j, sh};
+        if (a->psnr >= 2) sh->pics = (ks265_pic_stat *)calloc((size_t)sh->n, sizeof(ks265_pic_stat));
+        ks265_encoder_set_picture_stats(enc, sh->pics, sh->pics ? sh->n : 0);
+        double t0 = now_ms();
+        long n = ks265_encoder_encode_gop_cb(enc, read_picture, &ra, sh->n, bsbuf, cap, recon, &sh->st);
+        if (n == -28) {             /* output buffer too small: the handle stays usable (pictures in flight are dropped), retry with the worst-case size */
+            size_t big = j->fsz * (size_t)maxn * 2 + (4 << 20);
+            uint8_t *nb = (uint8_t *)realloc(bsbuf, big);
+            if (nb) { bsbuf = nb; cap = big; n = ks265_encoder_encode_gop_cb(enc, read_picture, &ra, sh->n, bsbuf, cap, recon, &sh->st); }
         }
+        enc_ms += now_ms() - t0;
+        if (n < 0) { sh->err = (int)n; continue; }
+        sh->bs = (uint8_t *)malloc((size_t)n);
+        if (!sh->bs) { sh->err = -12; continue; }
+        memcpy(sh->bs, bsbuf, (size_t)n);
+        sh->bs_bytes = n; sh->done = 1;
+        if (recon && pwrite(j->rec_fd, recon, j->fsz * (size_t)sh->n, (off_t)(j->fsz * (size_t)sh->first)) < 0) sh->err = -5;
     }
 out:
     pthread_mutex_lock(&j->mu); j->enc_ms += enc_ms; pthread_mutex_unlock(&j->mu);
-    ks265_free_host(frames[0]); ks265_free_host(frames[1]); free(recon);
+    free(bsbuf); free(recon);
     ks265_encoder_close(enc);
     return NULL;
 }

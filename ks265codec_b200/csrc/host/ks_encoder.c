@@ -19,6 +19,7 @@ struct ks265_encoder {
     void *scratch;
     int W, H;
     ks265_pic_stat *pic_stats; int pic_stats_cap;
+    ks265_read_fn read_fn; void *read_opaque;     /* encode_gop_cb: pictures are pulled into the context's pinned staging */
 };
 
 static const char *const k_presets[] = {"ultrafast", "superfast", "veryfast", "fast", "medium", "slow", "slower", "veryslow", "placebo"};
@@ -131,6 +132,12 @@ static int upload(ks265_encoder *enc, int slot, int disp, const uint8_t *frames,
     size_t fsz = (size_t)enc->cfg.width * enc->cfg.height * 3 / 2;
     int w = enc->cfg.width, h = enc->cfg.height;
     if (frames_dev) return ks_gpu_upload_frame_device(enc->gpu, slot, (const uint8_t *)frames_dev + fsz * disp);
+    if (enc->read_fn) {
+        uint8_t *d = ks_gpu_stage_acquire(enc->gpu);
+        if (!d) return KS_ECUDA;
+        if (enc->read_fn(enc->read_opaque, disp, d)) return -5;
+        return ks_gpu_upload_staged(enc->gpu, slot);
+    }
     const uint8_t *y = frames + fsz * disp;
     return ks_gpu_upload_frame(enc->gpu, slot, y, y + (size_t)w * h, y + (size_t)w * h * 5 / 4, w, w / 2);
 }
@@ -210,6 +217,17 @@ long ks265_encoder_encode_gop(ks265_encoder *enc, const uint8_t *frames, const v
 {
     if (!enc || (!frames && !frames_dev) || nframes < 1 || !bs) return -22;
     return encode_gop_impl(enc, frames, frames_dev, nframes, bs, cap, recon, stats);
+}
+
+long ks265_encoder_encode_gop_cb(ks265_encoder *enc, ks265_read_fn read_picture, void *opaque, int nframes,
+                                 uint8_t *bs, size_t cap, uint8_t *recon, ks265_gop_stats *stats)
+{
+    if (!enc || !read_picture || nframes < 1 || !bs) return -22;
+    enc->read_fn = read_picture; enc->read_opaque = opaque;
+    long r = encode_gop_impl(enc, NULL, NULL, nframes, bs, cap, recon, stats);
+    enc->read_fn = NULL; enc->read_opaque = NULL;
+    if (r >= 0 && stats) stats->h2d_bytes = (uint64_t)enc->cfg.width * enc->cfg.height * 3 / 2 * (uint64_t)nframes;
+    return r;
 }
 
 long ks265_encoder_run_gop_device(ks265_encoder *enc, const void *frames_dev, int nframes, ks265_gop_stats *stats)
