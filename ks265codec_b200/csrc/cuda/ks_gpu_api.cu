@@ -42,6 +42,7 @@ struct ks_gpu_ctx {
     ks_cell *d_cells1; int *d_cost0, *d_cost1;   /* d_cells1: list-1 field (B) / search field before the CU decision (P); d_cost0 doubles as its distortions */
     int16_t *d_lev;
     uint32_t *d_counts;
+    void *d_cands;               /* per-CTU candidate tables of the CU decision (stage E -> stage D) */
     uint32_t *d_sse_ctu;         /* per-CTU squared error partial sums (SAO kernel -> pack scan kernel) */
     int *d_sync;
     uint8_t *d_stage;           /* display-size I420 staging on device (upload + edge extension) */
@@ -138,6 +139,7 @@ extern "C" ks_gpu_ctx *ks_gpu_open(int device, int width, int height, const ks_g
         ok = ok && cudaMalloc(&c->d_cost1, (size_t)c->cw * c->ch * sizeof(int)) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_lev, c->fsz * 2) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_counts, sizeof(uint32_t) * c->ctw * c->cth) == cudaSuccess;
+        ok = ok && cudaMalloc(&c->d_cands, ks_decide_workspace_bytes(c->ctw * c->cth)) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_sse_ctu, sizeof(uint32_t) * 3 * c->ctw * c->cth) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_sync, sizeof(int) * ((size_t)c->ctw * c->cth + 1)) == cudaSuccess;
         size_t dsz = (size_t)width * height * 3 / 2;
@@ -183,7 +185,7 @@ extern "C" void ks_gpu_close(ks_gpu_ctx *c)
     if (c->st) cudaStreamSynchronize(c->st);
     if (c->d_src) for (int i = 0; i < c->cfg.n_src_slots; i++) cudaFree(c->d_src[i]);
     if (c->d_rec) for (int i = 0; i < c->cfg.n_rec_slots; i++) cudaFree(c->d_rec[i]);
-    cudaFree(c->d_pre); cudaFree(c->d_pred); cudaFree(c->d_pred1); cudaFree(c->d_cells1); cudaFree(c->d_cost0); cudaFree(c->d_cost1); cudaFree(c->d_lev); cudaFree(c->d_counts); cudaFree(c->d_sse_ctu); cudaFree(c->d_sync); cudaFree(c->d_stage);
+    cudaFree(c->d_pre); cudaFree(c->d_pred); cudaFree(c->d_pred1); cudaFree(c->d_cells1); cudaFree(c->d_cost0); cudaFree(c->d_cost1); cudaFree(c->d_lev); cudaFree(c->d_counts); cudaFree(c->d_sse_ctu); cudaFree(c->d_cands); cudaFree(c->d_sync); cudaFree(c->d_stage);
     for (int i = 0; i < 2; i++) { if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]); if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]); }
     if (c->syn) for (int i = 0; i < c->cfg.n_syn_slots; i++) {
         ks_syn_slot *s = &c->syn[i];
@@ -362,7 +364,7 @@ extern "C" int ks_gpu_encode_picture_submit(ks_gpu_ctx *c, const ks_pic_params *
             /* search field -> d_cells1 (+ distortions), then the CU quadtree / merge decision writes the final cells */
             ks_launch_me(pp, src.p[0], ref, prev, c->d_cells1, pred, NULL, c->d_cost0, mc ? s->d_mecost : NULL, c->st); c->launches += KS_LAUNCHES_ME;
             MARK(6);
-            ks_launch_decide(pp, src.p[0], ref, c->d_cells1, c->d_cost0, s->d_cells, pred, c->st); c->launches += KS_LAUNCHES_DECIDE;
+            ks_launch_decide(pp, src.p[0], ref, c->d_cells1, c->d_cost0, c->d_cands, s->d_cells, pred, c->st); c->launches += KS_LAUNCHES_DECIDE;
         }
         MARK(1);
         ks_launch_recon_inter(pp, src, pred, pre, lv, s->d_cells, cb, c->st); c->launches += KS_LAUNCHES_RECON;

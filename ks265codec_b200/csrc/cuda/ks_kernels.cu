@@ -25,7 +25,7 @@ int ks_init_device(int device)
     bool ok = true;
     ok = ok && cudaFuncSetAttribute(ks_recon_inter_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsReconSmem)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(ks_recon_inter_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsReconSmem)) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(ks_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsDecideSmem)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(ks_decide_cand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsCandSmem)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(ks_sao_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(KsSaoSmem) + 128) == cudaSuccess;
     ok = ok && cudaDeviceSynchronize() == cudaSuccess;
     if (!ok) { fprintf(stderr, "ks265gpu: device %d initialisation failed: %s\n", device, cudaGetErrorString(cudaGetLastError())); return -1; }

@@ -32,7 +32,8 @@ int ks_init_device(int device);
 void ks_launch_me(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref, const ks_cell *prev_cells, ks_cell *cells, KsPlanes pred, int *costs, int *dists, unsigned long long *cost_sum, cudaStream_t st);
 /* P pictures: candidate distortions + CU quadtree / merge decision per CTU (reads the search field mv0/dist0, writes the final cells and
  * re-predicts the cells whose vector changed) */
-void ks_launch_decide(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref, const ks_cell *mv0, const int *dist0, ks_cell *cells, KsPlanes pred, cudaStream_t st);
+void ks_launch_decide(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref, const ks_cell *mv0, const int *dist0, void *cands_ws, ks_cell *cells, KsPlanes pred, cudaStream_t st);
+size_t ks_decide_workspace_bytes(int nctu);
 /* B pictures: per cell best of list 0 / list 1 / bi-prediction; finalises cells, cells_b and the prediction planes */
 void ks_launch_bidir(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref0, KsPlanes ref1, const ks_cell *anchor_cells, int num0, int num1, int den,
                      const ks_cell *cells1, const int *cost0, const int *cost1, KsPlanes pred1, ks_cell *cells, ks_cell_b *cells_b, KsPlanes pred, cudaStream_t st);
@@ -45,4 +46,4 @@ void ks_launch_sao(const KsPicParams &pp, KsPlanes src, KsPlanes deb, KsPlanes o
                    const CUtensorMap *tm, int tma_mask, cudaStream_t st);
 void ks_launch_pack(const KsPicParams &pp, KsLevels lv, ks_ctu_syn *ctus, int16_t *pool, uint32_t *n_cg, uint32_t *scan_ws, const uint32_t *sse_ctu, unsigned long long *sse_out, cudaStream_t st);
 /* number of kernel launches each stage issues (for bench.py's gpu_launches accounting) */
-enum { KS_LAUNCHES_DECIDE = 1, KS_LAUNCHES_ME = 1, KS_LAUNCHES_RECON = 1, KS_LAUNCHES_DEBLOCK = 2, KS_LAUNCHES_SAO = 2, KS_LAUNCHES_PACK = 3 };
+enum { KS_LAUNCHES_DECIDE = 3, KS_LAUNCHES_ME = 1, KS_LAUNCHES_RECON = 1, KS_LAUNCHES_DEBLOCK = 2, KS_LAUNCHES_SAO = 2, KS_LAUNCHES_PACK = 3 };

@@ -318,7 +318,30 @@ static void recon_inter_cu(const ora_cfg *cfg, int qp, int qpc, int rdz, const o
  *   stage D  per CTU, in coding order: 64 -> 32 -> 16 quadtree by J = distortion + lambda * bits, bits from the 2Nx2N merge list /
  *            AMVP predictors of the vectors decided so far (cells of other CTUs count with their search results). ---- */
 #define ORA_NCAND 16
-typedef struct { int n; int16_t mvx[ORA_NCAND], mvy[ORA_NCAND]; int dist[16][ORA_NCAND]; } ora_ctu_cands;   /* dist[j * 4 + i][k] */
+#define ORA_INTRA_HDR_BITS 10
+typedef struct { int n; int16_t mvx[ORA_NCAND], mvy[ORA_NCAND]; int dist[16][ORA_NCAND]; int intra[16]; } ora_ctu_cands;   /* dist[j * 4 + i][k]; intra[j * 4 + i] */
+
+/* intra ESTIMATE of a 16x16 cell (search metric): best of DC / planar / horizontal / vertical predicted from the SOURCE picture's neighbours
+ * (left column, top row, the samples right of / below them clamped to the picture; 128 where the picture ends; no boundary smoothing).  It only
+ * decides inter vs intra in stage D; the real mode search runs on reconstructed neighbours (intra_cell). */
+static int intra_estimate(const ora_cfg *cfg, const ora_plane *src, int x0, int y0)
+{
+    const uint8_t *s = src->p + (size_t)y0 * src->stride + x0;
+    int W = cfg->width, H = cfg->height, st = src->stride;
+    int left[16], top[16], hl = x0 > 0, ht = y0 > 0, sl = 0, stp = 0;
+    for (int i = 0; i < 16; i++) { left[i] = hl ? s[i * st - 1] : 128; top[i] = ht ? s[i - st] : 128; sl += left[i]; stp += top[i]; }
+    int tr = ht ? src->p[(size_t)(y0 - 1) * st + imin(x0 + 16, W - 1)] : 128, bl = hl ? src->p[(size_t)imin(y0 + 16, H - 1) * st + x0 - 1] : 128;
+    int dc = (hl && ht) ? (sl + stp + 16) >> 5 : (hl ? (sl + 8) >> 4 : (ht ? (stp + 8) >> 4 : 128));
+    int best = 0x7fffffff;
+    for (int m = 0; m < 4; m++) {
+        uint8_t pred[256];
+        for (int y = 0; y < 16; y++) for (int x = 0; x < 16; x++)
+            pred[y * 16 + x] = (uint8_t)(m == 0 ? dc : (m == 1 ? left[y] : (m == 2 ? top[x] : ((15 - x) * left[y] + (x + 1) * tr + (15 - y) * top[x] + (y + 1) * bl + 16) >> 5)));
+        int c = (int)((cfg->satd && cfg->subpel > 0) ? ora_satd(s, pred, st, 16, 16, 16) : ora_sad(s, pred, st, 16, 16, 16));
+        if (c < best) best = c;
+    }
+    return best;
+}
 
 static int mvd_bits_est(int d) { int a = iabs(d); if (a == 0) return 1; if (a == 1) return 3; int v = a - 2, k = 1, b = 3; while (v >= (1 << k)) { v -= 1 << k; k++; b++; } return b + k + 1; }
 
@@ -343,6 +366,7 @@ static void decide_candidates(const ora_cfg *cfg, const ora_plane *src, const or
         int cx = X + i, cy = Y + j;
         if (cx >= cw || cy >= ch) continue;
         const uint8_t *s0 = src->p + (size_t)(cy << 4) * src->stride + (cx << 4), *r0 = ref->p + (size_t)(cy << 4) * ref->stride + (cx << 4);
+        t->intra[j * 4 + i] = intra_estimate(cfg, src, cx << 4, cy << 4);
         for (int k = 0; k < t->n; k++) {
             if (t->mvx[k] == mv0[cy * cw + cx].mvx && t->mvy[k] == mv0[cy * cw + cx].mvy) { t->dist[j * 4 + i][k] = dist0[cy * cw + cx]; continue; }
             uint8_t pred[256];
@@ -357,7 +381,7 @@ static void decide_candidates(const ora_cfg *cfg, const ora_plane *src, const or
 typedef struct {
     int16_t mvx[6][6], mvy[6][6];
     uint8_t ok[6][6];            /* the cell exists, precedes the current block in coding order and carries a vector */
-    uint8_t log2[4][4];
+    uint8_t log2[4][4], intra[4][4];
 } ora_ctu_state;
 static inline int zcell(int i, int j) { return (i & 1) | ((j & 1) << 1) | ((i & 2) << 1) | ((j & 2) << 2); }
 static int nb_ok(const ora_ctu_state *st, int i, int j, int zcur)
@@ -413,7 +437,14 @@ static int decide_block(const ora_ctu_cands *t, int ncx, int ncy, int lam, int m
         if (c < best) { best = c; bk = k; }
     }
     if (s > 1 && best > jsplit) return jsplit;
-    for (int b = 0; b < s; b++) for (int a = 0; a < s; a++) {
+    if (s == 1) {       /* intra 16x16 CU (reference: intra CUs in P slices are a third of the CUs on natural clips [probe]): ~10 bits of header */
+        int ji = getenv("ORA_NO_INTRA_P") ? 0x7fffffff : t->intra[j * 4 + i] + ((lam * ORA_INTRA_HDR_BITS) >> 4);
+        if (ji < best) {
+            st->mvx[j + 1][i + 1] = 0; st->mvy[j + 1][i + 1] = 0; st->ok[j + 1][i + 1] = 0; st->log2[j][i] = 4; st->intra[j][i] = 1;
+            return ji;
+        }
+    }
+    for (int b = 0; b < s; b++) for (int a = 0; a < s; a++) { st->intra[j + b][i + a] = 0;
         st->mvx[j + b + 1][i + a + 1] = t->mvx[bk]; st->mvy[j + b + 1][i + a + 1] = t->mvy[bk]; st->ok[j + b + 1][i + a + 1] = 1;
         st->log2[j + b][i + a] = (uint8_t)(s == 4 ? 6 : (s == 2 ? 5 : 4));
     }
@@ -433,6 +464,7 @@ static void decide_ctu(const ora_cfg *cfg, int lam, int maxc, const ks_cell *mv0
     for (int j = 0; j < ncy; j++) for (int i = 0; i < ncx; i++) {
         ks_cell *c = &cells[(Y + j) * cw + X + i];
         memset(c, 0, sizeof(*c)); c->mvx = st.mvx[j + 1][i + 1]; c->mvy = st.mvy[j + 1][i + 1]; c->cu_log2 = st.log2[j][i];
+        if (st.intra[j][i]) c->flags = KS_F_INTRA;
     }
 }
 
@@ -475,9 +507,16 @@ uint64_t ora_inter_picture(const ora_cfg *cfg, int qp, int lambda_qp, const ora_
     for (int y = 0; y < H; y += 16) for (int x = 0; x < W; x += 16) {
         ks_cell c = cells[(y >> 4) * cw + (x >> 4)];
         int S = 1 << c.cu_log2;
-        if ((x & (S - 1)) || (y & (S - 1))) continue;
+        if ((x & (S - 1)) || (y & (S - 1)) || (c.flags & KS_F_INTRA)) continue;
         recon_inter_cu(cfg, qp, qpc, rdz, src, ref, rec, cells, lv, x, y, c.cu_log2, c.mvx, c.mvy);
     }
+    /* 4. intra CUs, in coding order: their neighbours (the inter CUs of step 3, earlier intra CUs) are reconstructed */
+    for (int cty = 0; cty < (H + 63) >> 6; cty++) for (int ctx = 0; ctx < (W + 63) >> 6; ctx++)
+        for (int z = 0; z < 16; z++) {
+            int x0 = (ctx << 6) + (((z & 1) | ((z >> 1) & 2)) << 4), y0 = (cty << 6) + ((((z >> 1) & 1) | ((z >> 2) & 2)) << 4);
+            if (x0 >= W || y0 >= H || !(cells[(y0 >> 4) * cw + (x0 >> 4)].flags & KS_F_INTRA)) continue;
+            intra_cell(cfg, qp, 0, src, rec, cells, lv, x0, y0);
+        }
     return cost_sum;
 }
 
