@@ -337,7 +337,7 @@ def main():
     alg = {"me": S + S + S + 12.0 * W * H / 256,                # source luma+ (S_luma) + reference picture -> MV field + distortions + prediction planes
            "decide": 2.0 * W * H + 24.0 * W * H / 256,          # source luma + reference luma, search field in, final cells out (re-predicted cells extra)
            "recon_inter": S + S + S + 2.0 * S + 8.0 * W * H / 256,    # source + prediction in, reconstruction + int16 levels out
-           "recon_intra": S + S + 2.0 * S, "deblock": 2.0 * W * H, "sao": 3.0 * S, "pack": 2.0 * S + 0.1 * S}
+           "recon_intra": S + S + 2.0 * S, "intra_p": 16.0 * W * H / 256, "deblock": 2.0 * W * H, "sao": 3.0 * S, "pack": 2.0 * S + 0.1 * S}
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of the 4K configuration (profiles/);
     # ncu flushes L2 before each replay, writes mostly stay in the 126 MB L2, so traffic can be BELOW the algorithmic bytes
     ncu_traffic = {"me": 21.9e6, "recon_inter": 32.0e6, "sao": 25.0e6, "deblock": 12.9e6, "pack": 31.6e6, "recon_intra": None, "decide": None} if a.config == "4k" else {}
@@ -356,7 +356,7 @@ def main():
     torch.cuda.synchronize()
     solo_t = solo.stage_times()
     solo.set_profiling(False)
-    per_pic = {k: (v[0] / v[1] if v[1] else 0.0) * ((1.0 / IPER) if k == "recon_intra" else ((IPER - 1.0) / IPER if k in ("me", "decide", "recon_inter") else 1.0))
+    per_pic = {k: (v[0] / v[1] if v[1] else 0.0) * ((1.0 / IPER) if k == "recon_intra" else ((IPER - 1.0) / IPER if k in ("me", "decide", "recon_inter", "intra_p") else 1.0))
                for k, v in solo_t.items()}
     dom = max(per_pic, key=per_pic.get)
     avg_ms = solo_t[dom][0] / max(1, solo_t[dom][1])
@@ -373,7 +373,7 @@ def main():
                               for k in solo_t if solo_t[k][1] and solo_t[k][0] > 0},
                 "limiter": {"me": "issue slots (integer SAD/interpolation ALU), not HBM", "decide": "issue slots (interpolation of the candidate vectors) + the serial quadtree decision, not HBM",
                             "recon_inter": "issue slots + barriers (integer transforms), not HBM",
-                            "recon_intra": "dependency chain of the CTU wavefront", "sao": "shared-memory/ALU, then HBM", "deblock": "latency", "pack": "HBM"}[dom],
+                            "recon_intra": "dependency chain of the CTU wavefront", "intra_p": "dependency chain / latency (few cells)", "sao": "shared-memory/ALU, then HBM", "deblock": "latency", "pack": "HBM"}[dom],
                 "note": "dominant stage = largest solo time per picture (GOP-weighted); avg_launch_ms = that stage timed alone on an idle GPU with CUDA events on its stream (%d pictures, one stream); peak = burst copy bandwidth. stage_ms_share = event intervals inside the timed region with %d streams sharing the GPU (includes co-scheduling waits)." % (min(24, IPER), streams)}
 
     for e in encs:

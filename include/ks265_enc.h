@@ -75,7 +75,7 @@ long ks265_encoder_encode_gop_cb(ks265_encoder *enc, ks265_read_fn read_picture,
                                  uint8_t *bs, size_t bs_cap, uint8_t *recon, ks265_gop_stats *stats);
 /* per-stage device times accumulated since `on` (see ks_gpu_get_stage_times) */
 int  ks265_encoder_set_profiling(ks265_encoder *enc, int on);
-int  ks265_encoder_get_stage_times(ks265_encoder *enc, double ms[7], uint64_t launches[7]);   /* KS_NSTAGES entries */
+int  ks265_encoder_get_stage_times(ks265_encoder *enc, double ms[8], uint64_t launches[8]);   /* KS_NSTAGES entries */
 /* device-only variant for measurement: runs the device pipeline of a GOP without entropy coding */
 long ks265_encoder_run_gop_device(ks265_encoder *enc, const void *frames_dev, int nframes, ks265_gop_stats *stats);
 

@@ -101,8 +101,8 @@ uint64_t ks_gpu_launch_count(const ks_gpu_ctx *ctx);
 void *ks_gpu_stream(ks_gpu_ctx *ctx);
 
 /* per-stage device timing (CUDA events on the context's stream, accumulated at finish): stage order
- * 0 motion search, 1 inter prediction+residual, 2 intra picture, 3 deblock, 4 SAO, 5 level packing, 6 CU/merge decision */
-#define KS_NSTAGES 7
+ * 0 motion search, 1 inter prediction+residual, 2 intra picture, 3 deblock, 4 SAO, 5 level packing, 6 CU/merge decision, 7 intra CUs of P pictures */
+#define KS_NSTAGES 8
 int  ks_gpu_set_profiling(ks_gpu_ctx *ctx, int on);
 int  ks_gpu_get_stage_times(const ks_gpu_ctx *ctx, double ms[KS_NSTAGES], uint64_t launches[KS_NSTAGES]);
 /* drop every picture still in flight (submitted, not finished): waits for the device, clears the pending marks.  For error paths. */

@@ -18,6 +18,7 @@
 #include "ks_me.cuh"
 
 #define KS_NCAND 16
+#define KS_INTRA_HDR_BITS 10
 #define KS_DECIDE_WARPS 8            /* two cells per warp: 4 CTAs per SM instead of 2, so the serial stage D of one CTU idles 7 warps, not 15 */
 
 /* per-CTU result of stage E (global memory, 1.1 KB): the candidate list and every cell's distortion for every entry */
@@ -25,6 +26,7 @@ struct KsCtuCands {
     int      n;
     int16_t  cmx[KS_NCAND], cmy[KS_NCAND];
     int      dist[16][KS_NCAND];          /* [j * 4 + i][k] */
+    int      intra[16];                   /* intra estimate of each cell (ks_intra_estimate) */
 };
 /* stage D working set of one CTU (one warp) */
 struct KsDecideSmem {
@@ -33,7 +35,8 @@ struct KsDecideSmem {
     int      dist[16][KS_NCAND];
     uint32_t smv[36];                     /* vectors (x | y << 16) of the CTU's cells + a one-cell border, index (j + 1) * 6 + i + 1 */
     uint8_t  sok[36];
-    uint8_t  slog2[16];
+    uint8_t  slog2[16], sintra[16];
+    int      intra[16];
 };
 struct KsCandSmem {
     KsWarpScratch sc[KS_DECIDE_WARPS];
@@ -103,9 +106,45 @@ __device__ __forceinline__ void ks_decide_commit(KsDecideSmem *sm, int i, int j,
     if (lane < s * s) {
         const int a = lane % s, b = lane / s;
         sm->smv[(j + b + 1) * 6 + i + a + 1] = (uint32_t)(uint16_t)sm->cmx[k] | ((uint32_t)(uint16_t)sm->cmy[k] << 16); sm->sok[(j + b + 1) * 6 + i + a + 1] = 1;
-        sm->slog2[(j + b) * 4 + i + a] = (uint8_t)(s == 4 ? 6 : (s == 2 ? 5 : 4));
+        sm->slog2[(j + b) * 4 + i + a] = (uint8_t)(s == 4 ? 6 : (s == 2 ? 5 : 4)); sm->sintra[(j + b) * 4 + i + a] = 0;
     }
     __syncwarp();
+}
+
+/* intra ESTIMATE of a 16x16 cell in the search metric (== ora intra_estimate): best of DC / horizontal / vertical / planar predicted from the
+ * SOURCE picture's neighbours (128 where the picture ends, no boundary smoothing).  It only decides inter vs intra in stage D; the real 35-mode
+ * search runs on reconstructed neighbours (ks_recon_intra_kernel, masked mode).  Warp-collective; lane = row lane>>1, columns 8*(lane&1)..+7. */
+__device__ __forceinline__ int ks_intra_estimate(const uint8_t *__restrict__ srcY, int W, int H, int x0, int y0, uint2 s, bool satd, int lane)
+{
+    const int row = lane >> 1, half = lane & 1;
+    const bool hl = x0 > 0, ht = y0 > 0;
+    const int l = hl ? (int)srcY[(size_t)(y0 + row) * W + x0 - 1] : 128;
+    uint32_t t0 = 0x80808080u, t1 = 0x80808080u;
+    if (ht) { const uint2 t = *reinterpret_cast<const uint2 *>(srcY + (size_t)(y0 - 1) * W + x0 + 8 * half); t0 = t.x; t1 = t.y; }
+    const int tsum = (int)(__vsadu4(t0, 0u) + __vsadu4(t1, 0u));
+    const int sl = (int)ks_warp_sum(half == 0 ? (unsigned)l : 0u), stp = (int)ks_warp_sum(row == 0 ? (unsigned)tsum : 0u);
+    const int tr = ht ? (int)srcY[(size_t)(y0 - 1) * W + min(x0 + 16, W - 1)] : 128, bl = hl ? (int)srcY[(size_t)min(y0 + 16, H - 1) * W + x0 - 1] : 128;
+    const int dc = (hl && ht) ? (sl + stp + 16) >> 5 : (hl ? (sl + 8) >> 4 : (ht ? (stp + 8) >> 4 : 128));
+    int best = 0x7fffffff;
+#pragma unroll
+    for (int m = 0; m < 4; m++) {
+        uint32_t o0, o1;
+        if (m == 0) o0 = o1 = (uint32_t)dc * 0x01010101u;
+        else if (m == 1) o0 = o1 = (uint32_t)l * 0x01010101u;
+        else if (m == 2) { o0 = t0; o1 = t1; }
+        else {
+            o0 = o1 = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int x = 8 * half + k, t = (int)(((k < 4 ? t0 : t1) >> (8 * (k & 3))) & 255u);
+                const uint32_t v = (uint32_t)(((15 - x) * l + (x + 1) * tr + (15 - row) * t + (row + 1) * bl + 16) >> 5);
+                if (k < 4) o0 |= v << (8 * k); else o1 |= v << (8 * (k - 4));
+            }
+        }
+        const int c = satd ? (int)ks_satd16(o0, o1, s.x, s.y, lane) : (int)ks_warp_sum(__vsadu4(o0, s.x) + __vsadu4(o1, s.y));
+        best = min(best, c);
+    }
+    return best;
 }
 
 /* ---- stage E: one CTA per CTU, 8 warps x 2 cells ---- */
@@ -182,13 +221,15 @@ ks_decide_cand_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, KsPlanes
             if (lane == k) mine = d;
         }
         if (lane < n) out->dist[cell][lane] = mine;
+        const int ie = ks_intra_estimate(srcY, W, H, x0, y0, s, satd, lane);
+        if (lane == 0) out->intra[cell] = ie;
     }
 }
 
 /* ---- stage D: one WARP per CTU (lane = candidate); children first, then the whole block; the whole block wins ties ---- */
 #define KS_TREE_WARPS 4
 __global__ void __launch_bounds__(KS_TREE_WARPS * KS_WARP)
-ks_decide_tree_kernel(KsPicParams pp, const ks_cell *__restrict__ mv0, const KsCtuCands *__restrict__ cands, ks_cell *__restrict__ cells)
+ks_decide_tree_kernel(KsPicParams pp, const ks_cell *__restrict__ mv0, const KsCtuCands *__restrict__ cands, ks_cell *__restrict__ cells, int *__restrict__ n_intra)
 {
     __shared__ __align__(16) KsDecideSmem smem[KS_TREE_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -202,6 +243,7 @@ ks_decide_tree_kernel(KsPicParams pp, const ks_cell *__restrict__ mv0, const KsC
         const int n = in->n;
         if (lane == 0) sm->n = n;
         if (lane < n) { sm->cmx[lane] = in->cmx[lane]; sm->cmy[lane] = in->cmy[lane]; }
+        if (lane < 16) { sm->intra[lane] = in->intra[lane]; sm->sintra[lane] = 0; }
         for (int e = lane; e < 16 * KS_NCAND; e += 32) sm->dist[e / KS_NCAND][e % KS_NCAND] = (e % KS_NCAND) < n ? in->dist[e / KS_NCAND][e % KS_NCAND] : 0;
         /* border cells carry their search results, the CTU's own cells are undecided */
         for (int e = lane; e < 36; e += 32) {
@@ -227,8 +269,16 @@ ks_decide_tree_kernel(KsPicParams pp, const ks_cell *__restrict__ mv0, const KsC
             const int i = qi + (c & 1), j = qj + (c >> 1);
             if (i >= ncx || j >= ncy) continue;
             const unsigned key = ks_decide_eval(sm, i, j, 1, lam, maxc, lane);
-            ks_decide_commit(sm, i, j, 1, (int)(key & 15u), lane);
-            j32 += (int)(key >> 4);
+            /* intra 16x16 CU (about KS_INTRA_HDR_BITS of header) against the best vector */
+            const int ji = sm->intra[j * 4 + i] + ((lam * KS_INTRA_HDR_BITS) >> 4);
+            if (ji < (int)(key >> 4)) {
+                if (lane == 0) { sm->smv[(j + 1) * 6 + i + 1] = 0u; sm->sok[(j + 1) * 6 + i + 1] = 0; sm->slog2[j * 4 + i] = 4; sm->sintra[j * 4 + i] = 1; }
+                __syncwarp();
+                j32 += ji;
+            } else {
+                ks_decide_commit(sm, i, j, 1, (int)(key & 15u), lane);
+                j32 += (int)(key >> 4);
+            }
         }
         if (in32) {
             const unsigned key = ks_decide_eval(sm, qi, qj, 2, lam, maxc, lane);
@@ -245,10 +295,12 @@ ks_decide_tree_kernel(KsPicParams pp, const ks_cell *__restrict__ mv0, const KsC
         const int ci = lane & 3, cj = lane >> 2;
         if (ci < ncx && cj < ncy) {
             const uint32_t v = sm->smv[(cj + 1) * 6 + ci + 1];
-            ks_cell c; c.mvx = (int16_t)(v & 0xffffu); c.mvy = (int16_t)(v >> 16); c.cu_log2 = sm->slog2[lane]; c.flags = 0; c.intra_mode = 0; c.rsv = 0;
+            ks_cell c; c.mvx = (int16_t)(v & 0xffffu); c.mvy = (int16_t)(v >> 16); c.cu_log2 = sm->slog2[lane]; c.flags = sm->sintra[lane] ? KS_F_INTRA : 0; c.intra_mode = 0; c.rsv = 0;
             cells[(Y + cj) * cw + X + ci] = c;
         }
     }
+    const unsigned ib = __ballot_sync(0xffffffffu, lane < 16 && (lane & 3) < ncx && (lane >> 2) < ncy && sm->sintra[lane]);
+    if (ib && lane == 0) atomicAdd(n_intra, __popc(ib));
 }
 
 /* ---- stage F: one warp per cell; cells whose vector changed get their luma + chroma prediction rewritten ---- */
@@ -261,7 +313,7 @@ ks_decide_pred_kernel(KsPicParams pp, KsPlanes ref, const ks_cell *__restrict__ 
     const int cell = blockIdx.x * KS_ME_WARPS + warp;
     if (cell >= pp.cw * pp.ch) return;
     const ks_cell own = mv0[cell], fin = cells[cell];
-    if (fin.mvx == own.mvx && fin.mvy == own.mvy) return;
+    if ((fin.flags & KS_F_INTRA) || (fin.mvx == own.mvx && fin.mvy == own.mvy)) return;
     KsWarpScratch *sc = &scratch[warp];
     const int cyc = cell / pp.cw, cxc = cell - cyc * pp.cw, x0 = cxc << 4, y0 = cyc << 4, W = pp.W, H = pp.H;
     const int fmx = fin.mvx, fmy = fin.mvy;
@@ -278,12 +330,13 @@ ks_decide_pred_kernel(KsPicParams pp, KsPlanes ref, const ks_cell *__restrict__ 
                       pred.p[1 + c] + (size_t)(y0 >> 1) * CW + (x0 >> 1), CW, lane);
 }
 
-void ks_launch_decide(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref, const ks_cell *mv0, const int *dist0, void *cands_ws, ks_cell *cells, KsPlanes pred, cudaStream_t st)
+void ks_launch_decide(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref, const ks_cell *mv0, const int *dist0, void *cands_ws, ks_cell *cells, KsPlanes pred, int *n_intra, cudaStream_t st)
 {
     KsCtuCands *cands = reinterpret_cast<KsCtuCands *>(cands_ws);
     const int nctu = pp.ctw * pp.cth, ncell = pp.cw * pp.ch;
+    cudaMemsetAsync(n_intra, 0, sizeof(int), st);
     ks_decide_cand_kernel<<<dim3(pp.ctw, pp.cth), KS_DECIDE_WARPS * KS_WARP, sizeof(KsCandSmem), st>>>(pp, srcY, ref, mv0, dist0, cands);
-    ks_decide_tree_kernel<<<(nctu + KS_TREE_WARPS - 1) / KS_TREE_WARPS, KS_TREE_WARPS * KS_WARP, 0, st>>>(pp, mv0, cands, cells);
+    ks_decide_tree_kernel<<<(nctu + KS_TREE_WARPS - 1) / KS_TREE_WARPS, KS_TREE_WARPS * KS_WARP, 0, st>>>(pp, mv0, cands, cells, n_intra);
     ks_decide_pred_kernel<<<(ncell + KS_ME_WARPS - 1) / KS_ME_WARPS, KS_ME_WARPS * KS_WARP, 0, st>>>(pp, ref, mv0, cells, pred);
 }
 size_t ks_decide_workspace_bytes(int nctu) { return (size_t)nctu * sizeof(KsCtuCands); }

@@ -32,13 +32,15 @@ int ks_init_device(int device);
 void ks_launch_me(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref, const ks_cell *prev_cells, ks_cell *cells, KsPlanes pred, int *costs, int *dists, unsigned long long *cost_sum, cudaStream_t st);
 /* P pictures: candidate distortions + CU quadtree / merge decision per CTU (reads the search field mv0/dist0, writes the final cells and
  * re-predicts the cells whose vector changed) */
-void ks_launch_decide(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref, const ks_cell *mv0, const int *dist0, void *cands_ws, ks_cell *cells, KsPlanes pred, cudaStream_t st);
+/* n_intra (device int): number of cells the decision made intra CUs (their prediction + residual: ks_launch_recon_intra in masked mode) */
+void ks_launch_decide(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref, const ks_cell *mv0, const int *dist0, void *cands_ws, ks_cell *cells, KsPlanes pred, int *n_intra, cudaStream_t st);
 size_t ks_decide_workspace_bytes(int nctu);
 /* B pictures: per cell best of list 0 / list 1 / bi-prediction; finalises cells, cells_b and the prediction planes */
 void ks_launch_bidir(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref0, KsPlanes ref1, const ks_cell *anchor_cells, int num0, int num1, int den,
                      const ks_cell *cells1, const int *cost0, const int *cost1, KsPlanes pred1, ks_cell *cells, ks_cell_b *cells_b, KsPlanes pred, cudaStream_t st);
 void ks_launch_recon_inter(const KsPicParams &pp, KsPlanes src, KsPlanes pred, KsPlanes rec, KsLevels lv, ks_cell *cells, const ks_cell_b *cells_b, cudaStream_t st);
-void ks_launch_recon_intra(const KsPicParams &pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *cells, int *sync_ws, cudaStream_t st);
+/* n_intra == NULL: I picture, every cell; else P picture: only the cells flagged KS_F_INTRA (nothing if *n_intra == 0), inter-slice rounding */
+void ks_launch_recon_intra(const KsPicParams &pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *cells, int *sync_ws, const int *n_intra, cudaStream_t st);
 void ks_launch_deblock(const KsPicParams &pp, KsPlanes rec, const ks_cell *cells, const ks_cell_b *cells_b, cudaStream_t st);
 /* tm[3]: tensor maps of the three `deb` planes (box 96x66 / 64x34 bytes); tma_mask bit c = component c is staged by TMA */
 /* sse_ctu: per-CTU squared error of the three planes (3 x u32 per CTU) or NULL; ks_launch_pack sums them into the picture SSE */

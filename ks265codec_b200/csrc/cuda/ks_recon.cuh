@@ -225,7 +225,8 @@ struct KsReconSmem {
     int      m1[16];                           /* B pictures: list-1 vector (x | y << 16) and direction folded into one word pair */
     uint8_t  dirv[16];
     uint8_t  valid[16];
-    uint8_t  clog2[16];                        /* P pictures: CU size chosen by ks_decide_kernel */
+    uint8_t  clog2[16];                        /* P pictures: CU size chosen by ks_decide_tree_kernel */
+    uint8_t  intra[16];                        /* P pictures: intra CU (coded by ks_recon_intra_kernel afterwards): nothing to do here */
     unsigned cbf[16];                          /* KS_F_CBF_* bits per cell, OR-ed by the transform tasks */
 };
 __device__ __forceinline__ const uint16_t *ks_scan_ptr(const KsReconSmem *sm, int n) { return sm->scan + (n == 8 ? 0 : (n == 16 ? 64 : 320)); }
@@ -252,9 +253,9 @@ ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes pred, KsPlanes rec,
         int cx = tid & 3, cy = tid >> 2, x = X0 + (cx << 4), y = Y0 + (cy << 4);
         bool v = x < W && y < H;
         sm->valid[tid] = v; sm->cbf[tid] = 0;
-        sm->m1[tid] = 0; sm->dirv[tid] = 1; sm->clog2[tid] = 4;
+        sm->m1[tid] = 0; sm->dirv[tid] = 1; sm->clog2[tid] = 4; sm->intra[tid] = 0;
         if (v) {
-            ks_cell c = cells[(y >> 4) * pp.cw + (x >> 4)]; sm->mvx[tid] = c.mvx; sm->mvy[tid] = c.mvy; sm->clog2[tid] = c.cu_log2;
+            ks_cell c = cells[(y >> 4) * pp.cw + (x >> 4)]; sm->mvx[tid] = c.mvx; sm->mvy[tid] = c.mvy; sm->clog2[tid] = c.cu_log2; sm->intra[tid] = (c.flags & KS_F_INTRA) != 0;
             if (cells_b) { ks_cell_b b = cells_b[(y >> 4) * pp.cw + (x >> 4)]; sm->m1[tid] = (int)(uint16_t)b.mvx1 | ((int)b.mvy1 << 16); sm->dirv[tid] = b.dir; }
         } else { sm->mvx[tid] = 0; sm->mvy[tid] = 0; }
     }
@@ -300,7 +301,7 @@ ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes pred, KsPlanes rec,
         } else if (k < 2) {
             int g = lane >> 4, r = lane & 15, kc = k * 2 + g;                 /* cell inside the quadrant */
             int cidx = b0 + (kc & 1) + (kc >> 1) * 4;
-            bool v = sm->valid[cidx];
+            bool v = sm->valid[cidx] && !sm->intra[cidx];
             int lx = qx + (kc & 1) * 16, ly = qy + (kc >> 1) * 16 + r, x = X0 + lx, y = Y0 + ly;
             bool cbf = ks_tb_code<16>(ts, ks_scan_ptr(sm, 16), sm->t0, v, src.p[0] + (size_t)y * W + x, pred.p[0] + (size_t)(v ? y : Y0) * W + (v ? x : X0),
                                       rec.p[0] + (size_t)y * W + x, lv.p[0] + (size_t)y * W + x, pp.qp, 0, pp.sign_hiding, lane, pp.rdz_lambda_q4);
@@ -308,7 +309,7 @@ ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes pred, KsPlanes rec,
         } else {
             int g = lane >> 3, r = lane & 7, kc = g, ci = k - 2;
             int cidx = b0 + (kc & 1) + (kc >> 1) * 4;
-            bool v = sm->valid[cidx];
+            bool v = sm->valid[cidx] && !sm->intra[cidx];
             int lx = (qx >> 1) + (kc & 1) * 8, ly = (qy >> 1) + (kc >> 1) * 8 + r, x = (X0 >> 1) + lx, y = (Y0 >> 1) + ly;
             bool cbf = ks_tb_code<8>(ts, ks_scan_ptr(sm, 8), sm->t0, v, src.p[1 + ci] + (size_t)y * CW + x, pred.p[1 + ci] + (size_t)(v ? y : (Y0 >> 1)) * CW + (v ? x : (X0 >> 1)),
                                      rec.p[1 + ci] + (size_t)y * CW + x, lv.p[1 + ci] + (size_t)y * CW + x, pp.qpc, 0, pp.sign_hiding, lane);
@@ -316,7 +317,7 @@ ks_recon_inter_kernel(KsPicParams pp, KsPlanes src, KsPlanes pred, KsPlanes rec,
         }
     }
     __syncthreads();
-    if (tid < 16 && sm->valid[tid]) {
+    if (tid < 16 && sm->valid[tid] && !sm->intra[tid]) {
         int cx = tid & 3, cy = tid >> 2;
         ks_cell c; c.mvx = sm->mvx[tid]; c.mvy = sm->mvy[tid]; c.cu_log2 = (uint8_t)(c64 ? 6 : (q32[(cx >> 1) + (cy >> 1) * 2] ? 5 : 4)); c.flags = (uint8_t)sm->cbf[tid]; c.intra_mode = 0; c.rsv = 0;
         cells[((Y0 >> 4) + cy) * pp.cw + (X0 >> 4) + cx] = c;
@@ -381,6 +382,7 @@ struct KsIntraSmem {
     int      dc[3];
     int      ticket;
     unsigned cbf;
+    unsigned todo;
 };
 
 /* reference-sample substitution (spec 8.4.4.2.2) for one component by one warp: every entry takes the nearest available
@@ -422,11 +424,16 @@ __device__ __forceinline__ void ks_intra_substitute(const uint8_t *raw, const ui
  * of each of those SMs to the P pictures of the other GOP shards */
 template <int MINB>
 __global__ void __launch_bounds__(KS_INTRA_WARPS * KS_WARP, MINB)
-ks_recon_intra_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells, int *sync_ws)
+ks_recon_intra_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells, int *sync_ws, const int *__restrict__ n_intra)
 {
     __shared__ __align__(16) KsIntraSmem sm;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int W = pp.W, H = pp.H, CW = W >> 1;
+    /* masked mode (P pictures): only the cells the CU decision flagged intra are coded, with the inter-slice quantiser rounding; everything else
+     * already holds its inter reconstruction and counts as finished */
+    const bool masked = n_intra != nullptr;
+    if (masked && *n_intra == 0) return;
+    const int intra_slice = masked ? 0 : 1;
     int *ticket = sync_ws, *progress = sync_ws + 1;              /* progress[cty * ctw + ctx] = blocks done (0..16) */
     ks_load_scans(sm.scan, tid, blockDim.x);
     if (tid == 0) sm.ticket = atomicAdd(ticket, 1);
@@ -434,10 +441,24 @@ ks_recon_intra_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, k
     const int cty = sm.ticket >> 1, par = sm.ticket & 1;
     if (cty >= pp.cth) return;
     for (int ctx = par; ctx < pp.ctw; ctx += 2) {
+        unsigned todo = 0xffffu;                       /* bit z: block z of this CTU is coded here */
+        if (masked) {
+            bool f = false;
+            if (tid < 16) {
+                const int cx = (tid & 1) | ((tid >> 1) & 2), cy = ((tid >> 1) & 1) | ((tid >> 2) & 2), x = (ctx << 6) + (cx << 4), y = (cty << 6) + (cy << 4);
+                f = x < W && y < H && (cells[(y >> 4) * pp.cw + (x >> 4)].flags & KS_F_INTRA);
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, f);
+            __syncthreads();                           /* the previous CTU's reads of sm.todo are done */
+            if (tid == 0) sm.todo = b & 0xffffu;
+            __syncthreads();
+            todo = sm.todo;
+            if (!todo) { if (tid == 0) { __threadfence(); atomicExch(&progress[cty * pp.ctw + ctx], 16); } continue; }
+        }
         for (int z = 0; z < 16; z++) {
             const int cx = (z & 1) | ((z >> 1) & 2), cy = ((z >> 1) & 1) | ((z >> 2) & 2);
             const int x0 = (ctx << 6) + (cx << 4), y0 = (cty << 6) + (cy << 4);
-            const bool inside = x0 < W && y0 < H;
+            const bool inside = x0 < W && y0 < H && ((todo >> z) & 1u);
             /* 0. wait for the blocks this one reads (see the kernel comment); skipped (outside) blocks still publish progress */
             if (tid == 0 && inside) {
                 const int need_left = z == 0 ? 8 : (z == 2 ? 14 : ((z == 8 || z == 10) ? 16 : 0));
@@ -538,12 +559,12 @@ ks_recon_intra_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, k
                 if (warp == 0) {
                     int g = lane >> 4, r = lane & 15, y = y0 + r;
                     bool cbf = ks_tb_code<16>(&sm.tb[0], sm.scan + 64, nullptr, g == 0, src.p[0] + (size_t)y * W + x0, &sm.predY[r * 16],
-                                              rec.p[0] + (size_t)y * W + x0, lv.p[0] + (size_t)y * W + x0, pp.qp, 1, pp.sign_hiding, lane);
+                                              rec.p[0] + (size_t)y * W + x0, lv.p[0] + (size_t)y * W + x0, pp.qp, intra_slice, pp.sign_hiding, lane);
                     if (lane == 0 && cbf) atomicOr(&sm.cbf, KS_F_CBF_Y);
                 } else if (warp == 1) {
                     int g = lane >> 3, r = lane & 7, ci = g & 1, x = x0 >> 1, y = (y0 >> 1) + r;
                     bool cbf = ks_tb_code<8>(&sm.tb[1], sm.scan, nullptr, g < 2, src.p[1 + ci] + (size_t)y * CW + x, &sm.predC[ci][r * 8],
-                                             rec.p[1 + ci] + (size_t)y * CW + x, lv.p[1 + ci] + (size_t)y * CW + x, pp.qpc, 1, pp.sign_hiding, lane);
+                                             rec.p[1 + ci] + (size_t)y * CW + x, lv.p[1 + ci] + (size_t)y * CW + x, pp.qpc, intra_slice, pp.sign_hiding, lane);
                     if (r == 0 && g < 2 && cbf) atomicOr(&sm.cbf, ci ? KS_F_CBF_CR : KS_F_CBF_CB);
                 }
                 __syncthreads();
@@ -557,10 +578,10 @@ ks_recon_intra_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, k
     }
 }
 
-void ks_launch_recon_intra(const KsPicParams &pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *cells, int *sync_ws, cudaStream_t st)
+void ks_launch_recon_intra(const KsPicParams &pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *cells, int *sync_ws, const int *n_intra, cudaStream_t st)
 {
     cudaMemsetAsync(sync_ws, 0, sizeof(int) * (size_t)(1 + pp.ctw * pp.cth), st);
     static const int minb = getenv("KS_INTRA_MINB") ? atoi(getenv("KS_INTRA_MINB")) : 2;     /* tuning knob, see the kernel comment */
-    if (minb <= 1) ks_recon_intra_kernel<1><<<2 * pp.cth, KS_INTRA_WARPS * KS_WARP, 0, st>>>(pp, src, rec, lv, cells, sync_ws);
-    else ks_recon_intra_kernel<2><<<2 * pp.cth, KS_INTRA_WARPS * KS_WARP, 0, st>>>(pp, src, rec, lv, cells, sync_ws);
+    if (minb <= 1) ks_recon_intra_kernel<1><<<2 * pp.cth, KS_INTRA_WARPS * KS_WARP, 0, st>>>(pp, src, rec, lv, cells, sync_ws, n_intra);
+    else ks_recon_intra_kernel<2><<<2 * pp.cth, KS_INTRA_WARPS * KS_WARP, 0, st>>>(pp, src, rec, lv, cells, sync_ws, n_intra);
 }

@@ -75,7 +75,7 @@ class Encoder:
             raise RuntimeError("ks265_encoder_run_gop_device failed: %d" % r)
         return st
 
-    STAGES = ("me", "recon_inter", "recon_intra", "deblock", "sao", "pack", "decide")
+    STAGES = ("me", "recon_inter", "recon_intra", "deblock", "sao", "pack", "decide", "intra_p")
 
     def set_profiling(self, on=True):
         self._lib.ks265_encoder_set_profiling(self._h, int(on))

@@ -438,7 +438,7 @@ static int decide_block(const ora_ctu_cands *t, int ncx, int ncy, int lam, int m
     }
     if (s > 1 && best > jsplit) return jsplit;
     if (s == 1) {       /* intra 16x16 CU (reference: intra CUs in P slices are a third of the CUs on natural clips [probe]): ~10 bits of header */
-        int ji = getenv("ORA_NO_INTRA_P") ? 0x7fffffff : t->intra[j * 4 + i] + ((lam * ORA_INTRA_HDR_BITS) >> 4);
+        int ji = t->intra[j * 4 + i] + ((lam * ORA_INTRA_HDR_BITS) >> 4);
         if (ji < best) {
             st->mvx[j + 1][i + 1] = 0; st->mvy[j + 1][i + 1] = 0; st->ok[j + 1][i + 1] = 0; st->log2[j][i] = 4; st->intra[j][i] = 1;
             return ji;
