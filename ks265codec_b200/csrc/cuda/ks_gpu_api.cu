@@ -143,7 +143,7 @@ extern "C" ks_gpu_ctx *ks_gpu_open(int device, int width, int height, const ks_g
         ok = ok && cudaMalloc(&c->d_nintra, sizeof(int)) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_cands, ks_decide_workspace_bytes(c->ctw * c->cth)) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_sse_ctu, sizeof(uint32_t) * 3 * c->ctw * c->cth) == cudaSuccess;
-        ok = ok && cudaMalloc(&c->d_sync, sizeof(int) * ((size_t)c->ctw * c->cth + 1)) == cudaSuccess;
+        ok = ok && cudaMalloc(&c->d_sync, sizeof(int) * ((size_t)c->cw * c->ch + 1)) == cudaSuccess;
         size_t dsz = (size_t)width * height * 3 / 2;
         ok = ok && cudaMalloc(&c->d_stage, dsz) == cudaSuccess;
         for (int i = 0; i < 2; i++) { ok = ok && cudaHostAlloc(&c->h_stage[i], dsz, cudaHostAllocDefault) == cudaSuccess; ok = ok && cudaEventCreateWithFlags(&c->ev_stage[i], cudaEventDisableTiming) == cudaSuccess; }

@@ -415,6 +415,116 @@ __device__ __forceinline__ void ks_intra_substitute(const uint8_t *raw, const ui
     __syncwarp();
 }
 
+/* one 16x16 intra CU by a whole CTA (KS_INTRA_WARPS warps): reference samples with availability, 35-mode decision by SAD + lambda * bits,
+ * prediction, luma + chroma (DM) residual coding, cell record.  Mirror of ora intra_cell. */
+__device__ __forceinline__ void ks_intra_code_cell(KsIntraSmem &sm, const KsPicParams &pp, const KsPlanes &src, const KsPlanes &rec, const KsLevels &lv,
+                                                   ks_cell *__restrict__ cells, int x0, int y0, int intra_slice, int tid, int warp, int lane)
+{
+    const int W = pp.W, H = pp.H, CW = W >> 1;
+    /* 1. reference samples with availability (8.4.4.2.2); neighbours come from the pre-filter reconstruction.
+     *    __ldcg: other CTAs wrote these lines, bypass the (non-coherent) L1 */
+    if (tid < 65 + 33 + 33) {
+        int idx = tid;
+        int ci = idx < 65 ? 0 : (idx < 98 ? 1 : 2), i = idx - (ci == 0 ? 0 : (ci == 1 ? 65 : 98));
+        int n = ci ? 8 : 16, sh = ci ? 1 : 0, bx = x0 >> sh, by = y0 >> sh, xn, yn;
+        if (i < 2 * n) { xn = bx - 1; yn = by + 2 * n - 1 - i; }
+        else if (i == 2 * n) { xn = bx - 1; yn = by - 1; }
+        else { xn = bx + i - 2 * n - 1; yn = by - 1; }
+        bool a = ks_avail(W, H, pp.ctw, x0, y0, xn << sh, yn << sh);
+        sm.av[ci][i] = a;
+        sm.raw[ci][i] = a ? __ldcg(rec.p[ci] + (size_t)yn * (W >> sh) + xn) : 0;
+    }
+    if (tid == 255) { sm.best_key = 0xffffffffu; sm.cbf = 0; }
+    __syncthreads();
+    if (warp < 3) {
+        ks_intra_substitute(sm.raw[warp], sm.av[warp], sm.nb[warp], warp ? 33 : 65, warp ? 8 : 16, &sm.dc[warp], lane);
+        if (warp == 0)
+            for (int i = lane; i < 65; i += 32)
+                sm.fb[i] = (i == 0 || i == 64) ? sm.nb[0][i] : (uint8_t)((sm.nb[0][i - 1] + 2 * sm.nb[0][i] + sm.nb[0][i + 1] + 2) >> 2);
+    }
+    __syncthreads();
+    /* 2. mode decision by SAD + lambda*bits: warp w evaluates modes w, w+16, w+32 on all 256 samples.
+     *    Angular modes first project the (possibly filtered) references onto one extended main-reference array
+     *    per mode (spec 8.4.4.2.6 ref[]), so a sample costs two shared loads + one interpolation. */
+    {
+        unsigned best = 0xffffffffu;
+        const int px = lane & 15, py0 = lane >> 4;
+        uint8_t s[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) s[j] = src.p[0][(size_t)(y0 + py0 + 2 * j) * W + x0 + px];
+        uint8_t *mref = sm.mref[warp];
+#pragma unroll 1
+        for (int m = warp; m < 35; m += KS_INTRA_WARPS) {
+            int d1 = abs(m - 26), d2 = abs(m - 10);
+            bool filt = m != 1 && min(d1, d2) > 1;            /* intraHorVerDistThres[16] = 1 */
+            const uint8_t *p = filt ? sm.fb : sm.nb[0];
+            unsigned sad = 0;
+            if (m < 2) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) sad += abs(ks_intra_sample(p, 16, 4, m, px, py0 + 2 * j, sm.dc[0], true) - (int)s[j]);
+            } else {
+                const int ang = c_intra_angle[m], inv = c_intra_inv_angle[m];
+                const bool vert = m >= 18;
+                __syncwarp();
+                for (int e = lane; e < 49; e += 32) {           /* k = e - 16 in -16..32 */
+                    int k = e - 16, v;
+                    if (k >= 0) v = vert ? p[32 + k] : p[32 - k];
+                    else { int i2 = -1 + ((k * inv + 128) >> 8); i2 = min(max(i2, -1), 31); v = vert ? p[31 - i2] : p[33 + i2]; }
+                    mref[e] = (uint8_t)v;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int x = px, y = py0 + 2 * j, ii = vert ? x : y, jj = vert ? y : x;
+                    int v;
+                    if (ang == 0 && ii == 0)
+                        v = vert ? ks_clip8(p[33] + ((p[31 - jj] - p[32]) >> 1)) : ks_clip8(p[31] + ((p[33 + jj] - p[32]) >> 1));
+                    else {
+                        const int idx = ((jj + 1) * ang) >> 5, f = ((jj + 1) * ang) & 31;
+                        const int a = mref[16 + ii + idx + 1], b2 = mref[16 + ii + idx + 2];
+                        v = f ? ((32 - f) * a + f * b2 + 16) >> 5 : a;
+                    }
+                    sad += abs(v - (int)s[j]);
+                }
+            }
+            sad = ks_warp_sum(sad);
+            int bits = (m == 0 || m == 1 || m == 10 || m == 26) ? 3 : 6;
+            unsigned key = ((sad + ((pp.lambda_sad_q4 * bits) >> 4)) << 6) | (unsigned)m;
+            best = min(best, key);
+        }
+        if (lane == 0) atomicMin(&sm.best_key, best);
+    }
+    __syncthreads();
+    const int mode = (int)(sm.best_key & 63);
+    /* 3. prediction blocks: threads 0..255 luma, 256..383 chroma */
+    if (tid < 256) {
+        int d1 = abs(mode - 26), d2 = abs(mode - 10);
+        bool filt = mode != 1 && min(d1, d2) > 1;
+        sm.predY[tid] = (uint8_t)ks_intra_sample(filt ? sm.fb : sm.nb[0], 16, 4, mode, tid & 15, tid >> 4, sm.dc[0], true);
+    } else if (tid < 384) {
+        int t = tid - 256, ci = t >> 6, k = t & 63;
+        sm.predC[ci][k] = (uint8_t)ks_intra_sample(sm.nb[1 + ci], 8, 3, mode, k & 7, k >> 3, sm.dc[1 + ci], false);
+    }
+    __syncthreads();
+    /* 4. residual coding: warp 0 luma 16x16 (lanes 0..15), warp 1 Cb+Cr 8x8 (lanes 0..15) */
+    if (warp == 0) {
+        int g = lane >> 4, r = lane & 15, y = y0 + r;
+        bool cbf = ks_tb_code<16>(&sm.tb[0], sm.scan + 64, nullptr, g == 0, src.p[0] + (size_t)y * W + x0, &sm.predY[r * 16],
+                                  rec.p[0] + (size_t)y * W + x0, lv.p[0] + (size_t)y * W + x0, pp.qp, intra_slice, pp.sign_hiding, lane);
+        if (lane == 0 && cbf) atomicOr(&sm.cbf, KS_F_CBF_Y);
+    } else if (warp == 1) {
+        int g = lane >> 3, r = lane & 7, ci = g & 1, x = x0 >> 1, y = (y0 >> 1) + r;
+        bool cbf = ks_tb_code<8>(&sm.tb[1], sm.scan, nullptr, g < 2, src.p[1 + ci] + (size_t)y * CW + x, &sm.predC[ci][r * 8],
+                                 rec.p[1 + ci] + (size_t)y * CW + x, lv.p[1 + ci] + (size_t)y * CW + x, pp.qpc, intra_slice, pp.sign_hiding, lane);
+        if (r == 0 && g < 2 && cbf) atomicOr(&sm.cbf, ci ? KS_F_CBF_CR : KS_F_CBF_CB);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        ks_cell c; c.mvx = 0; c.mvy = 0; c.cu_log2 = 4; c.flags = (uint8_t)(KS_F_INTRA | sm.cbf); c.intra_mode = (uint8_t)mode; c.rsv = 0;
+        cells[(y0 >> 4) * pp.cw + (x0 >> 4)] = c;
+    }
+}
+
 /* I pictures.  The block order inside a CTU (z-scan) and the availability rules are normative, so the parallelism is the
  * dependency DAG itself: two CTAs per CTU row take alternate CTUs (CTU c+1 may start once CTU c finished its first 8 blocks),
  * rows follow each other with a one-CTU lag, all inside ONE launch.  Progress = blocks finished per CTU, published in HBM;
@@ -424,16 +534,11 @@ __device__ __forceinline__ void ks_intra_substitute(const uint8_t *raw, const ui
  * of each of those SMs to the P pictures of the other GOP shards */
 template <int MINB>
 __global__ void __launch_bounds__(KS_INTRA_WARPS * KS_WARP, MINB)
-ks_recon_intra_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells, int *sync_ws, const int *__restrict__ n_intra)
+ks_recon_intra_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells, int *sync_ws)
 {
     __shared__ __align__(16) KsIntraSmem sm;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int W = pp.W, H = pp.H, CW = W >> 1;
-    /* masked mode (P pictures): only the cells the CU decision flagged intra are coded, with the inter-slice quantiser rounding; everything else
-     * already holds its inter reconstruction and counts as finished */
-    const bool masked = n_intra != nullptr;
-    if (masked && *n_intra == 0) return;
-    const int intra_slice = masked ? 0 : 1;
     int *ticket = sync_ws, *progress = sync_ws + 1;              /* progress[cty * ctw + ctx] = blocks done (0..16) */
     ks_load_scans(sm.scan, tid, blockDim.x);
     if (tid == 0) sm.ticket = atomicAdd(ticket, 1);
@@ -441,24 +546,10 @@ ks_recon_intra_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, k
     const int cty = sm.ticket >> 1, par = sm.ticket & 1;
     if (cty >= pp.cth) return;
     for (int ctx = par; ctx < pp.ctw; ctx += 2) {
-        unsigned todo = 0xffffu;                       /* bit z: block z of this CTU is coded here */
-        if (masked) {
-            bool f = false;
-            if (tid < 16) {
-                const int cx = (tid & 1) | ((tid >> 1) & 2), cy = ((tid >> 1) & 1) | ((tid >> 2) & 2), x = (ctx << 6) + (cx << 4), y = (cty << 6) + (cy << 4);
-                f = x < W && y < H && (cells[(y >> 4) * pp.cw + (x >> 4)].flags & KS_F_INTRA);
-            }
-            const unsigned b = __ballot_sync(0xffffffffu, f);
-            __syncthreads();                           /* the previous CTU's reads of sm.todo are done */
-            if (tid == 0) sm.todo = b & 0xffffu;
-            __syncthreads();
-            todo = sm.todo;
-            if (!todo) { if (tid == 0) { __threadfence(); atomicExch(&progress[cty * pp.ctw + ctx], 16); } continue; }
-        }
         for (int z = 0; z < 16; z++) {
             const int cx = (z & 1) | ((z >> 1) & 2), cy = ((z >> 1) & 1) | ((z >> 2) & 2);
             const int x0 = (ctx << 6) + (cx << 4), y0 = (cty << 6) + (cy << 4);
-            const bool inside = x0 < W && y0 < H && ((todo >> z) & 1u);
+            const bool inside = x0 < W && y0 < H;
             /* 0. wait for the blocks this one reads (see the kernel comment); skipped (outside) blocks still publish progress */
             if (tid == 0 && inside) {
                 const int need_left = z == 0 ? 8 : (z == 2 ? 14 : ((z == 8 || z == 10) ? 16 : 0));
@@ -469,119 +560,72 @@ ks_recon_intra_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, k
                 __threadfence();
             }
             __syncthreads();
-            if (inside) {
-                /* 1. reference samples with availability (8.4.4.2.2); neighbours come from the pre-filter reconstruction.
-                 *    __ldcg: other CTAs wrote these lines, bypass the (non-coherent) L1 */
-                if (tid < 65 + 33 + 33) {
-                    int idx = tid;
-                    int ci = idx < 65 ? 0 : (idx < 98 ? 1 : 2), i = idx - (ci == 0 ? 0 : (ci == 1 ? 65 : 98));
-                    int n = ci ? 8 : 16, sh = ci ? 1 : 0, bx = x0 >> sh, by = y0 >> sh, xn, yn;
-                    if (i < 2 * n) { xn = bx - 1; yn = by + 2 * n - 1 - i; }
-                    else if (i == 2 * n) { xn = bx - 1; yn = by - 1; }
-                    else { xn = bx + i - 2 * n - 1; yn = by - 1; }
-                    bool a = ks_avail(W, H, pp.ctw, x0, y0, xn << sh, yn << sh);
-                    sm.av[ci][i] = a;
-                    sm.raw[ci][i] = a ? __ldcg(rec.p[ci] + (size_t)yn * (W >> sh) + xn) : 0;
-                }
-                if (tid == 255) { sm.best_key = 0xffffffffu; sm.cbf = 0; }
-                __syncthreads();
-                if (warp < 3) {
-                    ks_intra_substitute(sm.raw[warp], sm.av[warp], sm.nb[warp], warp ? 33 : 65, warp ? 8 : 16, &sm.dc[warp], lane);
-                    if (warp == 0)
-                        for (int i = lane; i < 65; i += 32)
-                            sm.fb[i] = (i == 0 || i == 64) ? sm.nb[0][i] : (uint8_t)((sm.nb[0][i - 1] + 2 * sm.nb[0][i] + sm.nb[0][i + 1] + 2) >> 2);
-                }
-                __syncthreads();
-                /* 2. mode decision by SAD + lambda*bits: warp w evaluates modes w, w+16, w+32 on all 256 samples.
-                 *    Angular modes first project the (possibly filtered) references onto one extended main-reference array
-                 *    per mode (spec 8.4.4.2.6 ref[]), so a sample costs two shared loads + one interpolation. */
-                {
-                    unsigned best = 0xffffffffu;
-                    const int px = lane & 15, py0 = lane >> 4;
-                    uint8_t s[8];
-#pragma unroll
-                    for (int j = 0; j < 8; j++) s[j] = src.p[0][(size_t)(y0 + py0 + 2 * j) * W + x0 + px];
-                    uint8_t *mref = sm.mref[warp];
-#pragma unroll 1
-                    for (int m = warp; m < 35; m += KS_INTRA_WARPS) {
-                        int d1 = abs(m - 26), d2 = abs(m - 10);
-                        bool filt = m != 1 && min(d1, d2) > 1;            /* intraHorVerDistThres[16] = 1 */
-                        const uint8_t *p = filt ? sm.fb : sm.nb[0];
-                        unsigned sad = 0;
-                        if (m < 2) {
-#pragma unroll
-                            for (int j = 0; j < 8; j++) sad += abs(ks_intra_sample(p, 16, 4, m, px, py0 + 2 * j, sm.dc[0], true) - (int)s[j]);
-                        } else {
-                            const int ang = c_intra_angle[m], inv = c_intra_inv_angle[m];
-                            const bool vert = m >= 18;
-                            __syncwarp();
-                            for (int e = lane; e < 49; e += 32) {           /* k = e - 16 in -16..32 */
-                                int k = e - 16, v;
-                                if (k >= 0) v = vert ? p[32 + k] : p[32 - k];
-                                else { int i2 = -1 + ((k * inv + 128) >> 8); i2 = min(max(i2, -1), 31); v = vert ? p[31 - i2] : p[33 + i2]; }
-                                mref[e] = (uint8_t)v;
-                            }
-                            __syncwarp();
-#pragma unroll
-                            for (int j = 0; j < 8; j++) {
-                                const int x = px, y = py0 + 2 * j, ii = vert ? x : y, jj = vert ? y : x;
-                                int v;
-                                if (ang == 0 && ii == 0)
-                                    v = vert ? ks_clip8(p[33] + ((p[31 - jj] - p[32]) >> 1)) : ks_clip8(p[31] + ((p[33 + jj] - p[32]) >> 1));
-                                else {
-                                    const int idx = ((jj + 1) * ang) >> 5, f = ((jj + 1) * ang) & 31;
-                                    const int a = mref[16 + ii + idx + 1], b2 = mref[16 + ii + idx + 2];
-                                    v = f ? ((32 - f) * a + f * b2 + 16) >> 5 : a;
-                                }
-                                sad += abs(v - (int)s[j]);
-                            }
-                        }
-                        sad = ks_warp_sum(sad);
-                        int bits = (m == 0 || m == 1 || m == 10 || m == 26) ? 3 : 6;
-                        unsigned key = ((sad + ((pp.lambda_sad_q4 * bits) >> 4)) << 6) | (unsigned)m;
-                        best = min(best, key);
-                    }
-                    if (lane == 0) atomicMin(&sm.best_key, best);
-                }
-                __syncthreads();
-                const int mode = (int)(sm.best_key & 63);
-                /* 3. prediction blocks: threads 0..255 luma, 256..383 chroma */
-                if (tid < 256) {
-                    int d1 = abs(mode - 26), d2 = abs(mode - 10);
-                    bool filt = mode != 1 && min(d1, d2) > 1;
-                    sm.predY[tid] = (uint8_t)ks_intra_sample(filt ? sm.fb : sm.nb[0], 16, 4, mode, tid & 15, tid >> 4, sm.dc[0], true);
-                } else if (tid < 384) {
-                    int t = tid - 256, ci = t >> 6, k = t & 63;
-                    sm.predC[ci][k] = (uint8_t)ks_intra_sample(sm.nb[1 + ci], 8, 3, mode, k & 7, k >> 3, sm.dc[1 + ci], false);
-                }
-                __syncthreads();
-                /* 4. residual coding: warp 0 luma 16x16 (lanes 0..15), warp 1 Cb+Cr 8x8 (lanes 0..15) */
-                if (warp == 0) {
-                    int g = lane >> 4, r = lane & 15, y = y0 + r;
-                    bool cbf = ks_tb_code<16>(&sm.tb[0], sm.scan + 64, nullptr, g == 0, src.p[0] + (size_t)y * W + x0, &sm.predY[r * 16],
-                                              rec.p[0] + (size_t)y * W + x0, lv.p[0] + (size_t)y * W + x0, pp.qp, intra_slice, pp.sign_hiding, lane);
-                    if (lane == 0 && cbf) atomicOr(&sm.cbf, KS_F_CBF_Y);
-                } else if (warp == 1) {
-                    int g = lane >> 3, r = lane & 7, ci = g & 1, x = x0 >> 1, y = (y0 >> 1) + r;
-                    bool cbf = ks_tb_code<8>(&sm.tb[1], sm.scan, nullptr, g < 2, src.p[1 + ci] + (size_t)y * CW + x, &sm.predC[ci][r * 8],
-                                             rec.p[1 + ci] + (size_t)y * CW + x, lv.p[1 + ci] + (size_t)y * CW + x, pp.qpc, intra_slice, pp.sign_hiding, lane);
-                    if (r == 0 && g < 2 && cbf) atomicOr(&sm.cbf, ci ? KS_F_CBF_CR : KS_F_CBF_CB);
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    ks_cell c; c.mvx = 0; c.mvy = 0; c.cu_log2 = 4; c.flags = (uint8_t)(KS_F_INTRA | sm.cbf); c.intra_mode = (uint8_t)mode; c.rsv = 0;
-                    cells[(y0 >> 4) * pp.cw + (x0 >> 4)] = c;
-                }
-            }
+            if (inside) ks_intra_code_cell(sm, pp, src, rec, lv, cells, x0, y0, 1, tid, warp, lane);
             if (tid == 0) { __threadfence(); atomicExch(&progress[cty * pp.ctw + ctx], z + 1); }
         }
     }
 }
 
+/* P pictures: the (few) cells the CU decision flagged intra, after the inter reconstruction of everything else.  Persistent CTAs take CTUs in
+ * raster order (ticket counter) and code their flagged cells in z-order; a cell waits only for the flagged cells it really reads -- left,
+ * above-left, above, above-right, below-left neighbours that precede it in coding order -- through per-cell done flags in HBM.  A CTA only ever
+ * waits on cells of CTUs with smaller tickets (or its own earlier cells), which are running or finished: no deadlock.  CTUs without flagged
+ * cells cost one 16-cell read.  (The wavefront kernel above took 0.3 ms per P picture in this role: it walks every CTU row serially.) */
+__global__ void __launch_bounds__(KS_INTRA_WARPS * KS_WARP, 2)
+ks_recon_intra_sparse_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells, int *sync_ws, const int *__restrict__ n_intra)
+{
+    __shared__ __align__(16) KsIntraSmem sm;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (*n_intra == 0) return;
+    const int W = pp.W, H = pp.H, nctu = pp.ctw * pp.cth;
+    int *ticket = sync_ws, *done = sync_ws + 1;                  /* done[cell] = 1 once an intra cell's reconstruction is in HBM */
+    ks_load_scans(sm.scan, tid, blockDim.x);
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sm.ticket = atomicAdd(ticket, 1);
+        __syncthreads();
+        const int ctu = sm.ticket;
+        if (ctu >= nctu) return;
+        const int ctx = ctu % pp.ctw, cty = ctu / pp.ctw;
+        bool f = false;
+        if (tid < 16) {
+            const int cx = (tid & 1) | ((tid >> 1) & 2), cy = ((tid >> 1) & 1) | ((tid >> 2) & 2), x = (ctx << 6) + (cx << 4), y = (cty << 6) + (cy << 4);
+            f = x < W && y < H && (cells[(y >> 4) * pp.cw + (x >> 4)].flags & KS_F_INTRA);
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, f);
+        if (tid == 0) sm.todo = b & 0xffffu;
+        __syncthreads();
+        const unsigned todo = sm.todo;
+        for (int z = 0; z < 16; z++) {
+            if (!((todo >> z) & 1u)) continue;
+            const int cx = (z & 1) | ((z >> 1) & 2), cy = ((z >> 1) & 1) | ((z >> 2) & 2);
+            const int x0 = (ctx << 6) + (cx << 4), y0 = (cty << 6) + (cy << 4), gx = x0 >> 4, gy = y0 >> 4;
+            if (tid < 5) {
+                const int ox[5] = {-1, -1, 0, 1, -1}, oy[5] = {0, -1, -1, -1, 1};
+                const int nx = gx + ox[tid], ny = gy + oy[tid];
+                if (ks_avail(W, H, pp.ctw, x0, y0, nx << 4, ny << 4) && (cells[ny * pp.cw + nx].flags & KS_F_INTRA)) {
+                    while (atomicAdd(&done[ny * pp.cw + nx], 0) == 0) __nanosleep(100);
+                    __threadfence();
+                }
+            }
+            __syncthreads();
+            ks_intra_code_cell(sm, pp, src, rec, lv, cells, x0, y0, 0, tid, warp, lane);
+            __syncthreads();
+            if (tid == 0) { __threadfence(); atomicExch(&done[gy * pp.cw + gx], 1); }
+        }
+    }
+}
+
+/* n_intra == NULL: I picture (every cell, wavefront kernel); else P picture: only the cells flagged KS_F_INTRA, inter-slice rounding */
 void ks_launch_recon_intra(const KsPicParams &pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *cells, int *sync_ws, const int *n_intra, cudaStream_t st)
 {
+    if (n_intra) {
+        cudaMemsetAsync(sync_ws, 0, sizeof(int) * (size_t)(1 + pp.cw * pp.ch), st);
+        ks_recon_intra_sparse_kernel<<<2 * 148, KS_INTRA_WARPS * KS_WARP, 0, st>>>(pp, src, rec, lv, cells, sync_ws, n_intra);
+        return;
+    }
     cudaMemsetAsync(sync_ws, 0, sizeof(int) * (size_t)(1 + pp.ctw * pp.cth), st);
     static const int minb = getenv("KS_INTRA_MINB") ? atoi(getenv("KS_INTRA_MINB")) : 2;     /* tuning knob, see the kernel comment */
-    if (minb <= 1) ks_recon_intra_kernel<1><<<2 * pp.cth, KS_INTRA_WARPS * KS_WARP, 0, st>>>(pp, src, rec, lv, cells, sync_ws, n_intra);
-    else ks_recon_intra_kernel<2><<<2 * pp.cth, KS_INTRA_WARPS * KS_WARP, 0, st>>>(pp, src, rec, lv, cells, sync_ws, n_intra);
+    if (minb <= 1) ks_recon_intra_kernel<1><<<2 * pp.cth, KS_INTRA_WARPS * KS_WARP, 0, st>>>(pp, src, rec, lv, cells, sync_ws);
+    else ks_recon_intra_kernel<2><<<2 * pp.cth, KS_INTRA_WARPS * KS_WARP, 0, st>>>(pp, src, rec, lv, cells, sync_ws);
 }
