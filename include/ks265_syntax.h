@@ -17,14 +17,17 @@ extern "C" {
 
 #define KS_CTU_LOG2   6      /* CTB 64x64 (reference: CTB 64) */
 #define KS_CTU        64
-#define KS_CELL_LOG2  4      /* side-info granularity = minimum CU = 16x16 luma */
+#define KS_CELL_LOG2  4      /* side-info granularity = 16x16 luma (inter CUs are 16..64) */
 #define KS_CELL       16
+#define KS_MIN_CB_LOG2 3     /* minimum coding block 8x8: an INTRA cell may be four 8x8 CUs (cu_log2 == 3, see ks_cell) */
 #define KS_MAX_TB_LOG2 5     /* TB 4..32 */
 
 enum { KS_SLICE_B = 0, KS_SLICE_P = 1, KS_SLICE_I = 2 };
 
 /* one 16x16 luma cell (8 bytes).  A CU of size 2^cu_log2 covers (2^cu_log2/16)^2 cells, all carrying the same
- * cu_log2/mv/mode; cbf bits are those of the transform unit (min(CU,32)) covering the cell. */
+ * cu_log2/mv/mode; cbf bits are those of the transform unit (min(CU,32)) covering the cell.
+ * cu_log2 == 3 (intra only): the cell holds FOUR 8x8 intra CUs (2Nx2N, luma TB 8x8, chroma TBs 4x4), sub-block k = (x half) | (y half) << 1:
+ *   luma modes in the vector bytes (KS_SUB_MODE), per-sub-block cbf bits in intra_mode / rsv (KS_SUB_CBF_*), flags = KS_F_INTRA | OR of them. */
 typedef struct ks_cell {
     int16_t mvx, mvy;        /* quarter-sample luma MV, list 0 (inter CUs) */
     uint8_t cu_log2;         /* 4, 5 or 6 */
@@ -32,6 +35,10 @@ typedef struct ks_cell {
     uint8_t intra_mode;      /* luma intra mode 0..34 (chroma uses DM = same mode) */
     uint8_t rsv;
 } ks_cell;
+#define KS_SUB_MODE(c, k)   ((int)(((k) & 2 ? (uint16_t)(c)->mvy : (uint16_t)(c)->mvx) >> (((k) & 1) * 8)) & 255)
+#define KS_SUB_CBF_Y(c, k)  (((c)->intra_mode >> (k)) & 1)
+#define KS_SUB_CBF_CB(c, k) (((c)->intra_mode >> (4 + (k))) & 1)
+#define KS_SUB_CBF_CR(c, k) (((c)->rsv >> (k)) & 1)
 #define KS_F_INTRA 1
 #define KS_F_CBF_Y 2
 #define KS_F_CBF_CB 4

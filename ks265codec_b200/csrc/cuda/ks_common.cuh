@@ -56,11 +56,11 @@ __device__ __forceinline__ int ks_dp4a_us(unsigned a, int b, int c)
 /* warp-wide integer sum, result in every lane: one REDUX instead of five shuffle+add steps (callers pack two 16-bit sums per word) */
 __device__ __forceinline__ unsigned ks_warp_sum(unsigned v) { return __reduce_add_sync(0xffffffffu, v); }
 __device__ __forceinline__ int ks_zidx(int x, int y)
-{
-    int cx = (x >> 4) & 3, cy = (y >> 4) & 3;
-    return (cx & 1) | ((cy & 1) << 1) | ((cx & 2) << 1) | ((cy & 2) << 2);
+{   /* z-scan index of the 8x8 block containing (x,y) inside its CTB (same order as the 16x16 one for blocks of 16 and up) */
+    int cx = (x >> 3) & 7, cy = (y >> 3) & 7;
+    return (cx & 1) | ((cy & 1) << 1) | ((cx & 2) << 1) | ((cy & 2) << 2) | ((cx & 4) << 2) | ((cy & 4) << 3);
 }
-/* H.265 6.4.1 z-scan availability at 16x16 granularity, one slice per picture */
+/* H.265 6.4.1 z-scan availability at 8x8 granularity, one slice per picture */
 __device__ __forceinline__ bool ks_avail(int W, int H, int ctw, int xc, int yc, int xn, int yn)
 {
     if (xn < 0 || yn < 0 || xn >= W || yn >= H) return false;

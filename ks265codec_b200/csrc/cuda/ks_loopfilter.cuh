@@ -4,8 +4,8 @@
  *  deblocking (spec 8.7.2; reference ctuDeblockFilterVer E@0x4144a0, CtuDeblockFilterHorT<> E@0x471d40, leaf
  *  EdgeFilterLuma{Ver,Hor}_c E@0x413100/0x4133f0, PixelFilterChroma*_c E@0x4137d0, Bs from CalcBsInterP E@0x413990):
  *  HEVC deblocking is picture-parallel by design -- all vertical edges first, then all horizontal edges on the
- *  result -- so it is two flat launches, one thread per 4-sample edge segment, in place.  All edges lie on the
- *  16-sample grid (minimum CU/TU is 16x16 here).
+ *  result -- so it is two flat launches, one thread per 4-sample edge segment, in place.  Edges lie on the 16-sample grid,
+ *  plus the 8-sample lines inside the cells that hold four 8x8 intra CUs (cu_log2 == 3).
  *
  *  SAO (spec 8.7.3; reference statSao*_c E@0x4a6370.., CEncSao::modeDecisionCtu E@0x4a9870, SaoApplyOffset*_c
  *  E@0x43dba0..): ONE launch, one CTA per CTU: the deblocked 64x64(+1 halo) tile is staged in shared memory once,
@@ -79,19 +79,26 @@ __global__ void __launch_bounds__(256)
 ks_deblock_kernel(KsPicParams pp, KsPlanes rec, const ks_cell *__restrict__ cells, const ks_cell_b *__restrict__ cells_b)
 {
     const int W = pp.W, H = pp.H;
-    const int nedge = ((DIR ? H : W) >> 4) - 1, nseg = (DIR ? W : H) >> 2;
+    const int nedge = ((DIR ? H : W) >> 3) - 1, nseg = (DIR ? W : H) >> 2;
     int ei, si;
     if (DIR == 0) { ei = blockIdx.x * 32 + (threadIdx.x & 31); si = blockIdx.y * 8 + (threadIdx.x >> 5); }   /* lanes across edges of one row band */
     else { si = blockIdx.x * 32 + (threadIdx.x & 31); ei = blockIdx.y * 8 + (threadIdx.x >> 5); }           /* lanes across columns (coalesced) */
     if (ei >= nedge || si >= nseg) return;
-    const int e = (ei + 1) << 4, t = si << 2;
+    const int e = (ei + 1) << 3, t = si << 2;
     const int xq = DIR ? t : e, yq = DIR ? e : t, xp = DIR ? t : e - 1, yp = DIR ? e - 1 : t;
-    const ks_cell cp = cells[(yp >> 4) * pp.cw + (xp >> 4)], cq = cells[(yq >> 4) * pp.cw + (xq >> 4)];
-    if (!ks_is_tu_edge(cp, cq, xp, yp, xq, yq, e)) return;
-    ks_cell_b pb, qb; pb.mvx1 = pb.mvy1 = qb.mvx1 = qb.mvy1 = 0; pb.dir = qb.dir = 1;
-    if (cells_b) { pb = cells_b[(yp >> 4) * pp.cw + (xp >> 4)]; qb = cells_b[(yq >> 4) * pp.cw + (xq >> 4)]; }
-    const int bs = ks_edge_bs(cp, cq, pb, qb);
-    if (!bs) return;
+    const ks_cell cp = cells[(yp >> 4) * pp.cw + (xp >> 4)];
+    int bs;
+    if (e & 8) {                /* inside a cell: only the boundaries between the four 8x8 intra CUs of a split cell (Bs 2, luma only) */
+        if (cp.cu_log2 != 3) return;
+        bs = 2;
+    } else {
+        const ks_cell cq = cells[(yq >> 4) * pp.cw + (xq >> 4)];
+        if (!ks_is_tu_edge(cp, cq, xp, yp, xq, yq, e)) return;
+        ks_cell_b pb, qb; pb.mvx1 = pb.mvy1 = qb.mvx1 = qb.mvy1 = 0; pb.dir = qb.dir = 1;
+        if (cells_b) { pb = cells_b[(yp >> 4) * pp.cw + (xp >> 4)]; qb = cells_b[(yq >> 4) * pp.cw + (xq >> 4)]; }
+        bs = ks_edge_bs(cp, cq, pb, qb);
+        if (!bs) return;
+    }
     const int beta = c_beta_table[ks_clip3(0, 51, pp.qp + (pp.beta_offset_div2 << 1))];
     const int tc = c_tc_table[ks_clip3(0, 53, pp.qp + 2 * (bs - 1) + (pp.tc_offset_div2 << 1))];
     uint8_t *Y = rec.p[0];
@@ -127,7 +134,7 @@ ks_deblock_kernel(KsPicParams pp, KsPlanes rec, const ks_cell *__restrict__ cell
                     (uint32_t)px[0][i] | ((uint32_t)px[1][i] << 8) | ((uint32_t)px[2][i] << 16) | ((uint32_t)px[3][i] << 24);
         }
     }
-    if (bs == 2) {      /* chroma: only intra edges, 2 chroma lines per 4 luma lines (spec 8.7.2.5.5/.8) */
+    if (bs == 2 && !(e & 8)) {      /* chroma: only intra edges on the 8-sample chroma grid, 2 chroma lines per 4 luma lines (spec 8.7.2.5.5/.8) */
         const int tcc = c_tc_table[ks_clip3(0, 53, pp.qpc + 2 + (pp.tc_offset_div2 << 1))];
         const int CW = W >> 1, xs = DIR ? CW : 1, ys = DIR ? 1 : CW;
 #pragma unroll
@@ -146,7 +153,7 @@ ks_deblock_kernel(KsPicParams pp, KsPlanes rec, const ks_cell *__restrict__ cell
 
 void ks_launch_deblock(const KsPicParams &pp, KsPlanes rec, const ks_cell *cells, const ks_cell_b *cells_b, cudaStream_t st)
 {
-    int nev = (pp.W >> 4) - 1, nsv = pp.H >> 2, neh = (pp.H >> 4) - 1, nsh = pp.W >> 2;
+    int nev = (pp.W >> 3) - 1, nsv = pp.H >> 2, neh = (pp.H >> 3) - 1, nsh = pp.W >> 2;
     if (nev > 0) ks_deblock_kernel<0><<<dim3((nev + 31) / 32, (nsv + 7) / 8), 256, 0, st>>>(pp, rec, cells, cells_b);
     if (neh > 0) ks_deblock_kernel<1><<<dim3((nsh + 31) / 32, (neh + 7) / 8), 256, 0, st>>>(pp, rec, cells, cells_b);
 }

@@ -27,7 +27,9 @@ struct KsTbScratch {
     int16_t D[32 * 32];        /* deltaU */
 };
 
-template <int N> struct KsLog2 { static const int v = N == 32 ? 5 : (N == 16 ? 4 : 3); };
+template <int N> struct KsLog2 { static const int v = N == 32 ? 5 : (N == 16 ? 4 : (N == 8 ? 3 : 2)); };
+/* per-block statistics of ks_tb_code (the intra 16x16 vs 8x8 decision): SSE(src, rec) and the estimated level bits as coded */
+struct KsTbStat { int d1, bits; };
 
 /* transform passes: generated partial butterflies with immediate coefficients (tools/gen_dct.py) */
 #include "ks_dct_gen.cuh"
@@ -83,7 +85,7 @@ template <int N>
 __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, const int *t0, bool valid,
                                         const uint8_t *__restrict__ src_row, const uint8_t *pred_row,
                                         uint8_t *__restrict__ rec_row, int16_t *__restrict__ lev_row,
-                                        int qp, int intra_slice, int sign_hiding, int lane, int rdz_lambda_q4 = 0)
+                                        int qp, int intra_slice, int sign_hiding, int lane, int rdz_lambda_q4 = 0, KsTbStat *stat_out = nullptr)
 {
     constexpr int LOG2 = KsLog2<N>::v, G = 32 / N, SP = N + 8;
     const int g = lane / N, r = lane % N;
@@ -103,12 +105,17 @@ __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, c
     ks_fwd_pass<N>(res, 2 * LOG2 - 2, t0, [&](int u, int v) { S[u * SP + r] = (int16_t)v; });
     __syncwarp();
     /* c. forward pass 2 (columns): lane = horizontal frequency u = r; d. quantise each coefficient (v, u=r) as it appears */
+    if constexpr (N == 4) {
+        const uint2 q = *reinterpret_cast<const uint2 *>(&S[r * SP]);
+        res[0] = (int)(short)(q.x & 0xffffu); res[1] = (int)q.x >> 16; res[2] = (int)(short)(q.y & 0xffffu); res[3] = (int)q.y >> 16;
+    } else {
 #pragma unroll
-    for (int y = 0; y < N; y += 8) {
-        uint4 q = *reinterpret_cast<const uint4 *>(&S[r * SP + y]);
-        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+        for (int y = 0; y < N; y += 8) {
+            uint4 q = *reinterpret_cast<const uint4 *>(&S[r * SP + y]);
+            uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-        for (int j = 0; j < 4; j++) { res[y + 2 * j] = (int)(short)(w[j] & 0xffffu); res[y + 2 * j + 1] = (int)w[j] >> 16; }
+            for (int j = 0; j < 4; j++) { res[y + 2 * j] = (int)(short)(w[j] & 0xffffu); res[y + 2 * j + 1] = (int)w[j] >> 16; }
+        }
     }
     const int qbits = 21 + qp / 6 - LOG2, scale = c_quant_scales[qp % 6];
     const int add = (intra_slice ? 171 : 85) << (qbits - 9);
@@ -167,46 +174,50 @@ __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, c
         ks_inv_pass<N>([&](int k) { return (int)S[r * SP + k]; }, t, 12, false, t0);
 #pragma unroll
         for (int x = 0; x < N; x++) pred[x] = (uint8_t)ks_clip8((int)pred[x] + t[x]);
-        if (rdz_lambda_q4) {
-            /* h. RD zero-out: per-block sums over the N lanes of the group (xor butterflies stay inside the aligned group) */
-            int nnz = 0, slog = 0, maxd = 0, d0 = 0, d1 = 0; unsigned cgm = 0;
+    }
+    /* h. RD zero-out and/or per-block statistics: sums over the N lanes of the group (xor butterflies stay inside the aligned group) */
+    if ((rdz_lambda_q4 && nzb) || stat_out) {
+        int nnz = 0, slog = 0, maxd = 0, d0 = 0, d1 = 0; unsigned cgm = 0;
 #pragma unroll
-            for (int x = 0; x < N; x += 4) {
-                const uint2 l4 = *reinterpret_cast<const uint2 *>(&L[r * N + x]);
-                const uint32_t p4 = *reinterpret_cast<const uint32_t *>(pred_row + x);
-                const uint32_t s4 = valid ? __ldg(reinterpret_cast<const uint32_t *>(src_row + x)) : p4;
+        for (int x = 0; x < N; x += 4) {
+            const uint2 l4 = *reinterpret_cast<const uint2 *>(&L[r * N + x]);
+            const uint32_t p4 = *reinterpret_cast<const uint32_t *>(pred_row + x);
+            const uint32_t s4 = valid ? __ldg(reinterpret_cast<const uint32_t *>(src_row + x)) : p4;
 #pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const int l = (int)(short)(((b & 2) ? l4.y : l4.x) >> (16 * (b & 1))), a = abs(l);
-                    if (a) { nnz++; slog += 31 - __clz(a); maxd = max(maxd, x + b + r); cgm |= 1u << (x >> 2); }
-                    const int sv = (int)((s4 >> (8 * b)) & 255), e0 = sv - (int)((p4 >> (8 * b)) & 255), e1 = valid ? sv - (int)pred[x + b] : 0;
-                    d0 += e0 * e0; d1 += e1 * e1;
-                }
-            }
-            cgm |= __shfl_xor_sync(0xffffffffu, cgm, 1); cgm |= __shfl_xor_sync(0xffffffffu, cgm, 2);
-            int ncg = (r & 3) == 0 ? __popc(cgm) : 0;
-#pragma unroll
-            for (int o = 1; o < N; o <<= 1) {
-                nnz += __shfl_xor_sync(0xffffffffu, nnz, o); slog += __shfl_xor_sync(0xffffffffu, slog, o); ncg += __shfl_xor_sync(0xffffffffu, ncg, o);
-                d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
-            }
-            const int bits = 3 * nnz + 2 * slog + 4 * ncg + maxd;
-            if (nnz && (long long)d0 * 16 <= (long long)d1 * 16 + (long long)rdz_lambda_q4 * bits) {
-                cbf = false;
-#pragma unroll
-                for (int x = 0; x < N; x += 4) {
-                    *reinterpret_cast<uint2 *>(&L[r * N + x]) = make_uint2(0u, 0u);
-                    const uint32_t p4 = *reinterpret_cast<const uint32_t *>(pred_row + x);
-#pragma unroll
-                    for (int b = 0; b < 4; b++) pred[x + b] = (uint8_t)(p4 >> (8 * b));
-                }
+            for (int b = 0; b < 4; b++) {
+                const int l = (int)(short)(((b & 2) ? l4.y : l4.x) >> (16 * (b & 1))), a = abs(l);
+                if (a) { nnz++; slog += 31 - __clz(a); maxd = max(maxd, x + b + r); cgm |= 1u << (x >> 2); }
+                const int sv = (int)((s4 >> (8 * b)) & 255), e0 = sv - (int)((p4 >> (8 * b)) & 255), e1 = valid ? sv - (int)pred[x + b] : 0;
+                d0 += e0 * e0; d1 += e1 * e1;
             }
         }
+        cgm |= __shfl_xor_sync(0xffffffffu, cgm, 1); cgm |= __shfl_xor_sync(0xffffffffu, cgm, 2);
+        int ncg = (r & 3) == 0 ? __popc(cgm) : 0;
+#pragma unroll
+        for (int o = 1; o < N; o <<= 1) {
+            nnz += __shfl_xor_sync(0xffffffffu, nnz, o); slog += __shfl_xor_sync(0xffffffffu, slog, o); ncg += __shfl_xor_sync(0xffffffffu, ncg, o);
+            d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
+        }
+        int bits = nnz ? 3 * nnz + 2 * slog + 4 * ncg + maxd : 0;
+        if (rdz_lambda_q4 && nnz && (long long)d0 * 16 <= (long long)d1 * 16 + (long long)rdz_lambda_q4 * bits) {
+            cbf = false; d1 = d0; bits = 0;
+#pragma unroll
+            for (int x = 0; x < N; x += 4) {
+                *reinterpret_cast<uint2 *>(&L[r * N + x]) = make_uint2(0u, 0u);
+                const uint32_t p4 = *reinterpret_cast<const uint32_t *>(pred_row + x);
+#pragma unroll
+                for (int b = 0; b < 4; b++) pred[x + b] = (uint8_t)(p4 >> (8 * b));
+            }
+        }
+        if (stat_out && r == 0 && valid) { stat_out[g].d1 = d1; stat_out[g].bits = bits; }
     }
     /* f. store the level row (dense plane) and the reconstruction */
     if (valid) {
+        if constexpr (N == 4) *reinterpret_cast<uint2 *>(lev_row) = *reinterpret_cast<const uint2 *>(&L[r * N]);
+        else {
 #pragma unroll
-        for (int x = 0; x < N; x += 8) *reinterpret_cast<uint4 *>(lev_row + x) = *reinterpret_cast<const uint4 *>(&L[r * N + x]);
+            for (int x = 0; x < N; x += 8) *reinterpret_cast<uint4 *>(lev_row + x) = *reinterpret_cast<const uint4 *>(&L[r * N + x]);
+        }
 #pragma unroll
         for (int x = 0; x < N; x += 4)
             *reinterpret_cast<uint32_t *>(rec_row + x) = (uint32_t)pred[x] | ((uint32_t)pred[x + 1] << 8) | ((uint32_t)pred[x + 2] << 16) | ((uint32_t)pred[x + 3] << 24);
@@ -368,26 +379,35 @@ __device__ __forceinline__ int ks_intra_sample(const uint8_t *p, int n, int log2
 }
 
 #define KS_INTRA_WARPS 16
+#define KS_SPLIT8_MIN_BITS 100          /* == ORA_SPLIT8_MIN_BITS */
 struct KsIntraSmem {
     KsTbScratch tb[2];
     uint16_t scan[64 + 256 + 1024];
-    uint8_t  nb[3][72];          /* substituted reference samples: luma 65, chroma 33 */
+    uint16_t scan4[3][16];       /* 4x4 blocks: diagonal, horizontal, vertical (7.4.9.11 scanIdx 0, 1, 2) */
+    uint16_t scan8hv[2][64];     /* 8x8 blocks: horizontal, vertical (groups in the same order, 6.5.4 / 6.5.5) */
+    uint8_t  nb[3][72];          /* substituted reference samples: luma 4n+1, chroma 2n+1 */
     uint8_t  raw[3][72];         /* as loaded (before substitution) */
     uint8_t  fb[72];             /* [1 2 1]-filtered luma references */
     uint8_t  av[3][72];
     uint8_t  predY[16 * 16];
     uint8_t  predC[2][8 * 8];
-    uint8_t  mref[KS_INTRA_WARPS][64];  /* per-warp extended main reference of the mode under test: index k+16, k = -16..32 */
+    uint8_t  mref[KS_INTRA_WARPS][64];  /* per-warp extended main reference of the mode under test: index k+n, k = -n..2n */
     unsigned best_key;
     int      dc[3];
     int      ticket;
     unsigned cbf;
     unsigned todo;
+    KsTbStat stat_y[4], stat_c[8];      /* ks_tb_code statistics of the block just coded: luma [0], Cb [0], Cr [1] */
+    uint8_t  save_rec[256 + 64 + 64];   /* the 16x16 CU's result while the four 8x8 CUs are tried over it */
+    int16_t  save_lev[256 + 64 + 64];
+    int      try8, use8;
+    long long j16, j8;
+    int      mode16, cbf16, modes8[4], cbf8[3];
 };
 
 /* reference-sample substitution (spec 8.4.4.2.2) for one component by one warp: every entry takes the nearest available
  * entry at or before it in scan order (bottom-left -> corner -> top-right), leading unavailable entries take the first
- * available one, 128 if nothing is available.  Also the DC value.  tot = 65 (luma 16x16) or 33 (chroma 8x8). */
+ * available one, 128 if nothing is available.  Also the DC value.  tot = 4n+1 (<= 65). */
 __device__ __forceinline__ void ks_intra_substitute(const uint8_t *raw, const uint8_t *av, uint8_t *nb, int tot, int n, int *dc_out, int lane)
 {
     const unsigned m0 = __ballot_sync(0xffffffffu, lane < tot && av[lane]);
@@ -411,22 +431,35 @@ __device__ __forceinline__ void ks_intra_substitute(const uint8_t *raw, const ui
         }
     }
     dc = (int)ks_warp_sum((unsigned)dc);
-    if (lane == 0) *dc_out = (dc + n) >> (n == 16 ? 5 : 4);
+    if (lane == 0) *dc_out = (dc + n) >> (n == 16 ? 5 : (n == 8 ? 4 : 3));
     __syncwarp();
 }
 
-/* one 16x16 intra CU by a whole CTA (KS_INTRA_WARPS warps): reference samples with availability, 35-mode decision by SAD + lambda * bits,
- * prediction, luma + chroma (DM) residual coding, cell record.  Mirror of ora intra_cell. */
-__device__ __forceinline__ void ks_intra_code_cell(KsIntraSmem &sm, const KsPicParams &pp, const KsPlanes &src, const KsPlanes &rec, const KsLevels &lv,
-                                                   ks_cell *__restrict__ cells, int x0, int y0, int intra_slice, int tid, int warp, int lane)
+__device__ __forceinline__ void ks_intra_load_small_scans(KsIntraSmem &sm, int tid)
 {
+    if (tid < 16) { sm.scan4[0][tid] = c_scan_tb[0][tid]; sm.scan4[1][tid] = (uint16_t)(((tid >> 2) << 8) | (tid & 3)); sm.scan4[2][tid] = (uint16_t)(((tid & 3) << 8) | (tid >> 2)); }
+    if (tid < 64) {
+        const int c = tid >> 4, k = tid & 15, gx = c & 1, gy = c >> 1, px = k & 3, py = k >> 2;
+        sm.scan8hv[0][tid] = (uint16_t)((((gy << 2) + py) << 8) | ((gx << 2) + px));
+        sm.scan8hv[1][tid] = (uint16_t)((((gx << 2) + px) << 8) | ((gy << 2) + py));
+    }
+}
+
+/* one intra CU of 16x16 (LG = 4) or 8x8 (LG = 3) by a whole CTA (KS_INTRA_WARPS warps): reference samples with availability, 35-mode decision
+ * by SAD + lambda * bits, prediction, luma + chroma (DM) residual coding with the mode-dependent scans.  Results in shared memory: best_key & 63
+ * = mode, cbf, stat_y[0] / stat_c[0..1].  Ends with a CTA barrier.  Mirror of ora intra_block. */
+template <int LG>
+__device__ __forceinline__ void ks_intra_code_block(KsIntraSmem &sm, const KsPicParams &pp, const KsPlanes &src, const KsPlanes &rec, const KsLevels &lv,
+                                                    int x0, int y0, int intra_slice, int tid, int warp, int lane)
+{
+    constexpr int N = 1 << LG, NC = N / 2, TL = 4 * N + 1, TC = 2 * N + 1;
     const int W = pp.W, H = pp.H, CW = W >> 1;
     /* 1. reference samples with availability (8.4.4.2.2); neighbours come from the pre-filter reconstruction.
-     *    __ldcg: other CTAs wrote these lines, bypass the (non-coherent) L1 */
-    if (tid < 65 + 33 + 33) {
+     *    __ldcg: other CTAs (or earlier blocks of this one) wrote these lines, bypass the (non-coherent) L1 */
+    if (tid < TL + 2 * TC) {
         int idx = tid;
-        int ci = idx < 65 ? 0 : (idx < 98 ? 1 : 2), i = idx - (ci == 0 ? 0 : (ci == 1 ? 65 : 98));
-        int n = ci ? 8 : 16, sh = ci ? 1 : 0, bx = x0 >> sh, by = y0 >> sh, xn, yn;
+        int ci = idx < TL ? 0 : (idx < TL + TC ? 1 : 2), i = idx - (ci == 0 ? 0 : (ci == 1 ? TL : TL + TC));
+        int n = ci ? NC : N, sh = ci ? 1 : 0, bx = x0 >> sh, by = y0 >> sh, xn, yn;
         if (i < 2 * n) { xn = bx - 1; yn = by + 2 * n - 1 - i; }
         else if (i == 2 * n) { xn = bx - 1; yn = by - 1; }
         else { xn = bx + i - 2 * n - 1; yn = by - 1; }
@@ -437,51 +470,53 @@ __device__ __forceinline__ void ks_intra_code_cell(KsIntraSmem &sm, const KsPicP
     if (tid == 255) { sm.best_key = 0xffffffffu; sm.cbf = 0; }
     __syncthreads();
     if (warp < 3) {
-        ks_intra_substitute(sm.raw[warp], sm.av[warp], sm.nb[warp], warp ? 33 : 65, warp ? 8 : 16, &sm.dc[warp], lane);
+        ks_intra_substitute(sm.raw[warp], sm.av[warp], sm.nb[warp], warp ? TC : TL, warp ? NC : N, &sm.dc[warp], lane);
         if (warp == 0)
-            for (int i = lane; i < 65; i += 32)
-                sm.fb[i] = (i == 0 || i == 64) ? sm.nb[0][i] : (uint8_t)((sm.nb[0][i - 1] + 2 * sm.nb[0][i] + sm.nb[0][i + 1] + 2) >> 2);
+            for (int i = lane; i < TL; i += 32)
+                sm.fb[i] = (i == 0 || i == 4 * N) ? sm.nb[0][i] : (uint8_t)((sm.nb[0][i - 1] + 2 * sm.nb[0][i] + sm.nb[0][i + 1] + 2) >> 2);
     }
     __syncthreads();
-    /* 2. mode decision by SAD + lambda*bits: warp w evaluates modes w, w+16, w+32 on all 256 samples.
+    /* 2. mode decision by SAD + lambda*bits: warp w evaluates modes w, w+16, w+32 on all N*N samples.
      *    Angular modes first project the (possibly filtered) references onto one extended main-reference array
      *    per mode (spec 8.4.4.2.6 ref[]), so a sample costs two shared loads + one interpolation. */
+    constexpr int FTHR = N == 16 ? 1 : 7;                        /* intraHorVerDistThres[nTbS] */
     {
+        constexpr int PER = N * N / 32, STEP = 32 / N;
         unsigned best = 0xffffffffu;
-        const int px = lane & 15, py0 = lane >> 4;
-        uint8_t s[8];
+        const int px = lane & (N - 1), py0 = lane >> LG;
+        uint8_t s[PER];
 #pragma unroll
-        for (int j = 0; j < 8; j++) s[j] = src.p[0][(size_t)(y0 + py0 + 2 * j) * W + x0 + px];
+        for (int j = 0; j < PER; j++) s[j] = src.p[0][(size_t)(y0 + py0 + STEP * j) * W + x0 + px];
         uint8_t *mref = sm.mref[warp];
 #pragma unroll 1
         for (int m = warp; m < 35; m += KS_INTRA_WARPS) {
             int d1 = abs(m - 26), d2 = abs(m - 10);
-            bool filt = m != 1 && min(d1, d2) > 1;            /* intraHorVerDistThres[16] = 1 */
+            bool filt = m != 1 && min(d1, d2) > FTHR;
             const uint8_t *p = filt ? sm.fb : sm.nb[0];
             unsigned sad = 0;
             if (m < 2) {
 #pragma unroll
-                for (int j = 0; j < 8; j++) sad += abs(ks_intra_sample(p, 16, 4, m, px, py0 + 2 * j, sm.dc[0], true) - (int)s[j]);
+                for (int j = 0; j < PER; j++) sad += abs(ks_intra_sample(p, N, LG, m, px, py0 + STEP * j, sm.dc[0], true) - (int)s[j]);
             } else {
                 const int ang = c_intra_angle[m], inv = c_intra_inv_angle[m];
                 const bool vert = m >= 18;
                 __syncwarp();
-                for (int e = lane; e < 49; e += 32) {           /* k = e - 16 in -16..32 */
-                    int k = e - 16, v;
-                    if (k >= 0) v = vert ? p[32 + k] : p[32 - k];
-                    else { int i2 = -1 + ((k * inv + 128) >> 8); i2 = min(max(i2, -1), 31); v = vert ? p[31 - i2] : p[33 + i2]; }
+                for (int e = lane; e < 3 * N + 1; e += 32) {           /* k = e - N in -N..2N */
+                    int k = e - N, v;
+                    if (k >= 0) v = vert ? p[2 * N + k] : p[2 * N - k];
+                    else { int i2 = -1 + ((k * inv + 128) >> 8); i2 = min(max(i2, -1), 2 * N - 1); v = vert ? p[2 * N - 1 - i2] : p[2 * N + 1 + i2]; }
                     mref[e] = (uint8_t)v;
                 }
                 __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const int x = px, y = py0 + 2 * j, ii = vert ? x : y, jj = vert ? y : x;
+                for (int j = 0; j < PER; j++) {
+                    const int x = px, y = py0 + STEP * j, ii = vert ? x : y, jj = vert ? y : x;
                     int v;
                     if (ang == 0 && ii == 0)
-                        v = vert ? ks_clip8(p[33] + ((p[31 - jj] - p[32]) >> 1)) : ks_clip8(p[31] + ((p[33 + jj] - p[32]) >> 1));
+                        v = vert ? ks_clip8(p[2 * N + 1] + ((p[2 * N - 1 - jj] - p[2 * N]) >> 1)) : ks_clip8(p[2 * N - 1] + ((p[2 * N + 1 + jj] - p[2 * N]) >> 1));
                     else {
                         const int idx = ((jj + 1) * ang) >> 5, f = ((jj + 1) * ang) & 31;
-                        const int a = mref[16 + ii + idx + 1], b2 = mref[16 + ii + idx + 2];
+                        const int a = mref[N + ii + idx + 1], b2 = mref[N + ii + idx + 2];
                         v = f ? ((32 - f) * a + f * b2 + 16) >> 5 : a;
                     }
                     sad += abs(v - (int)s[j]);
@@ -496,31 +531,92 @@ __device__ __forceinline__ void ks_intra_code_cell(KsIntraSmem &sm, const KsPicP
     }
     __syncthreads();
     const int mode = (int)(sm.best_key & 63);
-    /* 3. prediction blocks: threads 0..255 luma, 256..383 chroma */
-    if (tid < 256) {
+    const int scan_idx = (mode >= 22 && mode <= 30) ? 1 : ((mode >= 6 && mode <= 14) ? 2 : 0);
+    /* 3. prediction blocks: threads 0..N*N-1 luma, then 2 x NC*NC chroma */
+    if (tid < N * N) {
         int d1 = abs(mode - 26), d2 = abs(mode - 10);
-        bool filt = mode != 1 && min(d1, d2) > 1;
-        sm.predY[tid] = (uint8_t)ks_intra_sample(filt ? sm.fb : sm.nb[0], 16, 4, mode, tid & 15, tid >> 4, sm.dc[0], true);
-    } else if (tid < 384) {
-        int t = tid - 256, ci = t >> 6, k = t & 63;
-        sm.predC[ci][k] = (uint8_t)ks_intra_sample(sm.nb[1 + ci], 8, 3, mode, k & 7, k >> 3, sm.dc[1 + ci], false);
+        bool filt = mode != 1 && min(d1, d2) > FTHR;
+        sm.predY[tid] = (uint8_t)ks_intra_sample(filt ? sm.fb : sm.nb[0], N, LG, mode, tid & (N - 1), tid >> LG, sm.dc[0], true);
+    } else if (tid < N * N + 2 * NC * NC) {
+        int t = tid - N * N, ci = t / (NC * NC), k = t % (NC * NC);
+        sm.predC[ci][k] = (uint8_t)ks_intra_sample(sm.nb[1 + ci], NC, LG - 1, mode, k & (NC - 1), k / NC, sm.dc[1 + ci], false);
     }
     __syncthreads();
-    /* 4. residual coding: warp 0 luma 16x16 (lanes 0..15), warp 1 Cb+Cr 8x8 (lanes 0..15) */
+    /* 4. residual coding: warp 0 luma (lanes 0..N-1), warp 1 Cb + Cr (lanes 0..2*NC-1) */
     if (warp == 0) {
-        int g = lane >> 4, r = lane & 15, y = y0 + r;
-        bool cbf = ks_tb_code<16>(&sm.tb[0], sm.scan + 64, nullptr, g == 0, src.p[0] + (size_t)y * W + x0, &sm.predY[r * 16],
-                                  rec.p[0] + (size_t)y * W + x0, lv.p[0] + (size_t)y * W + x0, pp.qp, intra_slice, pp.sign_hiding, lane);
+        int g = lane / N, r = lane % N, y = y0 + r;
+        const uint16_t *scan = LG == 4 ? sm.scan + 64 : (scan_idx == 0 ? sm.scan : sm.scan8hv[scan_idx - 1]);
+        bool cbf = ks_tb_code<N>(&sm.tb[0], scan, nullptr, g == 0, src.p[0] + (size_t)y * W + x0, &sm.predY[r * N],
+                                 rec.p[0] + (size_t)y * W + x0, lv.p[0] + (size_t)y * W + x0, pp.qp, intra_slice, pp.sign_hiding, lane, 0, sm.stat_y);
         if (lane == 0 && cbf) atomicOr(&sm.cbf, KS_F_CBF_Y);
     } else if (warp == 1) {
-        int g = lane >> 3, r = lane & 7, ci = g & 1, x = x0 >> 1, y = (y0 >> 1) + r;
-        bool cbf = ks_tb_code<8>(&sm.tb[1], sm.scan, nullptr, g < 2, src.p[1 + ci] + (size_t)y * CW + x, &sm.predC[ci][r * 8],
-                                 rec.p[1 + ci] + (size_t)y * CW + x, lv.p[1 + ci] + (size_t)y * CW + x, pp.qpc, intra_slice, pp.sign_hiding, lane);
+        int g = lane / NC, r = lane % NC, ci = g & 1, x = x0 >> 1, y = (y0 >> 1) + r;
+        const uint16_t *scan = LG == 4 ? sm.scan : sm.scan4[scan_idx];
+        bool cbf = ks_tb_code<NC>(&sm.tb[1], scan, nullptr, g < 2, src.p[1 + ci] + (size_t)y * CW + x, &sm.predC[ci][r * NC],
+                                  rec.p[1 + ci] + (size_t)y * CW + x, lv.p[1 + ci] + (size_t)y * CW + x, pp.qpc, intra_slice, pp.sign_hiding, lane, 0, sm.stat_c);
         if (r == 0 && g < 2 && cbf) atomicOr(&sm.cbf, ci ? KS_F_CBF_CR : KS_F_CBF_CB);
     }
     __syncthreads();
+}
+
+/* one 16x16 intra cell by a whole CTA: a 16x16 CU, or four 8x8 CUs coded in z-order when that is cheaper in J = 16 * SSE + lambda * bits (both
+ * are really coded; the 8x8 alternative is only tried when the 16x16 luma block costs at least KS_SPLIT8_MIN_BITS estimated bits).  Writes the
+ * cell record.  Mirror of ora intra_cell. */
+__device__ __forceinline__ void ks_intra_code_cell(KsIntraSmem &sm, const KsPicParams &pp, const KsPlanes &src, const KsPlanes &rec, const KsLevels &lv,
+                                                   ks_cell *__restrict__ cells, int x0, int y0, int intra_slice, int tid, int warp, int lane)
+{
+    const int W = pp.W;
+    const long long lamq = pp.lambda_sse_q4;
+    ks_intra_code_block<4>(sm, pp, src, rec, lv, x0, y0, intra_slice, tid, warp, lane);
     if (tid == 0) {
-        ks_cell c; c.mvx = 0; c.mvy = 0; c.cu_log2 = 4; c.flags = (uint8_t)(KS_F_INTRA | sm.cbf); c.intra_mode = (uint8_t)mode; c.rsv = 0;
+        sm.mode16 = (int)(sm.best_key & 63); sm.cbf16 = (int)sm.cbf;
+        sm.j16 = 16ll * sm.stat_y[0].d1 + lamq * (sm.stat_y[0].bits + 1) + 16ll * sm.stat_c[0].d1 + lamq * (sm.stat_c[0].bits + 1)
+               + 16ll * sm.stat_c[1].d1 + lamq * (sm.stat_c[1].bits + 1) + lamq * 8;
+        sm.try8 = sm.stat_y[0].bits >= KS_SPLIT8_MIN_BITS;
+        sm.j8 = lamq * (8 * 4 + 2);
+        sm.cbf8[0] = sm.cbf8[1] = sm.cbf8[2] = 0;
+    }
+    __syncthreads();
+    if (sm.try8) {
+        /* keep the 16x16 result (its stores are visible after the barrier above), then code the four 8x8 CUs over it */
+        if (tid < 384) {
+            const int ci = tid < 256 ? 0 : (tid < 320 ? 1 : 2), k = tid - (ci == 0 ? 0 : (ci == 1 ? 256 : 320)), m = ci ? 8 : 16, sh = ci ? 1 : 0;
+            const size_t o = (size_t)((y0 >> sh) + k / m) * (W >> sh) + (x0 >> sh) + k % m;
+            sm.save_rec[tid] = __ldcg(rec.p[ci] + o); sm.save_lev[tid] = __ldcg(lv.p[ci] + o);
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int k = 0; k < 4; k++) {
+            ks_intra_code_block<3>(sm, pp, src, rec, lv, x0 + 8 * (k & 1), y0 + 8 * (k >> 1), intra_slice, tid, warp, lane);
+            if (tid == 0) {
+                sm.modes8[k] = (int)(sm.best_key & 63);
+                if (sm.cbf & KS_F_CBF_Y) sm.cbf8[0] |= 1 << k; if (sm.cbf & KS_F_CBF_CB) sm.cbf8[1] |= 1 << k; if (sm.cbf & KS_F_CBF_CR) sm.cbf8[2] |= 1 << k;
+                sm.j8 += 16ll * sm.stat_y[0].d1 + lamq * (sm.stat_y[0].bits + 1) + 16ll * sm.stat_c[0].d1 + lamq * (sm.stat_c[0].bits + 1)
+                       + 16ll * sm.stat_c[1].d1 + lamq * (sm.stat_c[1].bits + 1);
+            }
+            __syncthreads();
+        }
+        if (tid == 0) sm.use8 = sm.j8 < sm.j16;
+        __syncthreads();
+        if (sm.use8) {
+            if (tid == 0) {
+                ks_cell c; c.cu_log2 = 3;
+                c.flags = (uint8_t)(KS_F_INTRA | (sm.cbf8[0] ? KS_F_CBF_Y : 0) | (sm.cbf8[1] ? KS_F_CBF_CB : 0) | (sm.cbf8[2] ? KS_F_CBF_CR : 0));
+                c.mvx = (int16_t)(uint16_t)(sm.modes8[0] | (sm.modes8[1] << 8)); c.mvy = (int16_t)(uint16_t)(sm.modes8[2] | (sm.modes8[3] << 8));
+                c.intra_mode = (uint8_t)(sm.cbf8[0] | (sm.cbf8[1] << 4)); c.rsv = (uint8_t)sm.cbf8[2];
+                cells[(y0 >> 4) * pp.cw + (x0 >> 4)] = c;
+            }
+            return;
+        }
+        if (tid < 384) {          /* the 16x16 CU wins: put its reconstruction and levels back */
+            const int ci = tid < 256 ? 0 : (tid < 320 ? 1 : 2), k = tid - (ci == 0 ? 0 : (ci == 1 ? 256 : 320)), m = ci ? 8 : 16, sh = ci ? 1 : 0;
+            const size_t o = (size_t)((y0 >> sh) + k / m) * (W >> sh) + (x0 >> sh) + k % m;
+            rec.p[ci][o] = sm.save_rec[tid]; lv.p[ci][o] = sm.save_lev[tid];
+        }
+        __syncthreads();          /* the caller publishes the cell as finished right after this function */
+    }
+    if (tid == 0) {
+        ks_cell c; c.mvx = 0; c.mvy = 0; c.cu_log2 = 4; c.flags = (uint8_t)(KS_F_INTRA | sm.cbf16); c.intra_mode = (uint8_t)sm.mode16; c.rsv = 0;
         cells[(y0 >> 4) * pp.cw + (x0 >> 4)] = c;
     }
 }
@@ -541,6 +637,7 @@ ks_recon_intra_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, k
     const int W = pp.W, H = pp.H, CW = W >> 1;
     int *ticket = sync_ws, *progress = sync_ws + 1;              /* progress[cty * ctw + ctx] = blocks done (0..16) */
     ks_load_scans(sm.scan, tid, blockDim.x);
+    ks_intra_load_small_scans(sm, tid);
     if (tid == 0) sm.ticket = atomicAdd(ticket, 1);
     __syncthreads();
     const int cty = sm.ticket >> 1, par = sm.ticket & 1;
@@ -580,6 +677,7 @@ ks_recon_intra_sparse_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevel
     const int W = pp.W, H = pp.H, nctu = pp.ctw * pp.cth;
     int *ticket = sync_ws, *done = sync_ws + 1;                  /* done[cell] = 1 once an intra cell's reconstruction is in HBM */
     ks_load_scans(sm.scan, tid, blockDim.x);
+    ks_intra_load_small_scans(sm, tid);
     for (;;) {
         __syncthreads();
         if (tid == 0) sm.ticket = atomicAdd(ticket, 1);

@@ -87,8 +87,8 @@ long ks_write_sps(const ks_stream_params *sp, uint8_t *out, size_t cap)
     bw_ue(&b, 0); bw_ue(&b, 0);
     bw_ue(&b, (uint32_t)sp->log2_max_poc_lsb - 4);
     bw_put(&b, 1, 1); bw_ue(&b, sp->bframes ? 2 : 1); bw_ue(&b, sp->bframes ? 1 : 0); bw_ue(&b, 0);
-    bw_ue(&b, KS_CELL_LOG2 - 3);                 /* log2_min_luma_coding_block_size_minus3 */
-    bw_ue(&b, KS_CTU_LOG2 - KS_CELL_LOG2);       /* log2_diff_max_min_luma_coding_block_size */
+    bw_ue(&b, KS_MIN_CB_LOG2 - 3);               /* log2_min_luma_coding_block_size_minus3: 8x8 (used by intra CUs only) */
+    bw_ue(&b, KS_CTU_LOG2 - KS_MIN_CB_LOG2);     /* log2_diff_max_min_luma_coding_block_size */
     bw_ue(&b, 0); bw_ue(&b, KS_MAX_TB_LOG2 - 2); /* TB 4..32 */
     bw_ue(&b, 0); bw_ue(&b, 0);                  /* max_transform_hierarchy_depth inter/intra = 0 (reference: 0/0) */
     bw_put(&b, 0, 1); bw_put(&b, 0, 1);          /* scaling lists off, AMP off */
@@ -514,6 +514,131 @@ static void code_residual(slice_enc *e, int comp, int x0c, int y0c, int log2)
 #undef CG_PTR
 }
 
+/* ---- residual_coding of the SMALL intra blocks (luma 8x8, chroma 4x4 of an 8x8 intra CU): any scanIdx (7.4.9.11: 0 diagonal, 1 horizontal,
+ *      2 vertical), 4x4 blocks with the ctxIdxMap contexts (9.3.4.2.5).  Straightforward (these blocks are a small share of the bins). ---- */
+static const uint8_t *cg_levels(const slice_enc *e, int comp, int cgx, int cgy)
+{   /* (cgx, cgy): coefficient group inside the CTU, in 4x4 units of the component plane; NULL when the group holds no level */
+    const ks_ctu_syn *cs = &e->syn->ctus[e->cur_ctu];
+    uint32_t bits = comp == 0 ? cs->cg_y[cgy] : (comp == 1 ? cs->cg_cb[cgy] : cs->cg_cr[cgy]);
+    if (!((bits >> cgx) & 1)) return NULL;
+    int row0 = comp == 0 ? 0 : (comp == 1 ? 16 : 24);
+    return (const uint8_t *)(e->syn->levels + (size_t)(cs->cg_base + e->cg_prefix[row0 + cgy] + (uint32_t)__builtin_popcount(bits & ((1u << cgx) - 1))) * 16);
+}
+static void code_residual_small(slice_enc *e, int comp, int x0c, int y0c, int log2, int scan_idx)
+{
+    cabac *c = &e->cb;
+    const int ncg = 1 << (log2 - 2), is_luma = comp == 0;
+    int16_t blk[64]; memset(blk, 0, sizeof(blk));                 /* the block's levels, raster n x n */
+    const int n = 1 << log2;
+    int any = 0;
+    for (int gy = 0; gy < ncg; gy++) for (int gx = 0; gx < ncg; gx++) {
+        const int16_t *lv = (const int16_t *)cg_levels(e, comp, (x0c >> 2) + gx, (y0c >> 2) + gy);
+        if (!lv) continue;
+        any = 1;
+        for (int k = 0; k < 16; k++) blk[((gy << 2) + (k >> 2)) * n + (gx << 2) + (k & 3)] = lv[k];
+    }
+    if (!any) return;
+    /* scan tables: position i -> (x, y) */
+    uint8_t sx[64], sy[64];
+    for (int cgi = 0; cgi < ncg * ncg; cgi++) {
+        int gx, gy;
+        if (ncg == 1) gx = gy = 0;
+        else if (scan_idx == 0) { static const uint8_t dx[4] = {0, 0, 1, 1}, dy[4] = {0, 1, 0, 1}; gx = dx[cgi]; gy = dy[cgi]; }
+        else if (scan_idx == 1) { gx = cgi & 1; gy = cgi >> 1; }
+        else { gx = cgi >> 1; gy = cgi & 1; }
+        for (int k = 0; k < 16; k++) {
+            int px, py;
+            if (scan_idx == 0) { px = g_scan4[k] & 3; py = g_scan4[k] >> 2; }
+            else if (scan_idx == 1) { px = k & 3; py = k >> 2; }
+            else { px = k >> 2; py = k & 3; }
+            sx[cgi * 16 + k] = (uint8_t)((gx << 2) + px); sy[cgi * 16 + k] = (uint8_t)((gy << 2) + py);
+        }
+    }
+    int last = n * n - 1;
+    while (!blk[sy[last] * n + sx[last]]) last--;
+    int lx = sx[last], ly = sy[last];
+    if (scan_idx == 2) { int t = lx; lx = ly; ly = t; }          /* 7.3.8.11: coordinates are swapped for the vertical scan */
+    static const uint8_t group_idx[32] = {0,1,2,3,4,4,5,5,6,6,6,6,7,7,7,7,8,8,8,8,8,8,8,8,9,9,9,9,9,9,9,9};
+    static const uint8_t min_in_group[10] = {0,1,2,3,4,6,8,12,16,24};
+    int off, shift;
+    if (is_luma) { off = 3 * (log2 - 2) + ((log2 - 1) >> 2); shift = (log2 + 1) >> 2; } else { off = 15; shift = log2 - 2; }
+    int gx = group_idx[lx], gy = group_idx[ly], cmax = (log2 << 1) - 1, i;
+    for (i = 0; i < gx; i++) cb_bin(c, CX_LAST_X + off + (i >> shift), 1);
+    if (gx < cmax) cb_bin(c, CX_LAST_X + off + (i >> shift), 0);
+    for (i = 0; i < gy; i++) cb_bin(c, CX_LAST_Y + off + (i >> shift), 1);
+    if (gy < cmax) cb_bin(c, CX_LAST_Y + off + (i >> shift), 0);
+    if (gx > 3) cb_bypass_bins(c, (uint32_t)(lx - min_in_group[gx]), (gx - 2) >> 1);
+    if (gy > 3) cb_bypass_bins(c, (uint32_t)(ly - min_in_group[gy]), (gy - 2) >> 1);
+    static const uint8_t ctx_idx_map4[16] = {0, 1, 4, 5, 2, 3, 4, 5, 6, 6, 8, 8, 7, 7, 8, 8};
+    uint8_t csbf[2][2] = {{0, 0}, {0, 0}};
+    int last_cg = last >> 4, last_pos = last & 15, c1 = 1;
+    for (int cgi = last_cg; cgi >= 0; cgi--) {
+        const int cx = sx[cgi * 16] >> 2, cy = sy[cgi * 16] >> 2;
+        const int right = cx + 1 < ncg ? csbf[cy][cx + 1] : 0, below = cy + 1 < ncg ? csbf[cy + 1][cx] : 0;
+        int nzc = 0;
+        for (int k = 0; k < 16; k++) nzc += blk[sy[cgi * 16 + k] * n + sx[cgi * 16 + k]] != 0;
+        int coded = nzc != 0, infer_dc = 0;
+        if (cgi < last_cg && cgi > 0) { cb_bin(c, CX_CSBF + ((right | below) ? 1 : 0) + (is_luma ? 0 : 2), coded); infer_dc = 1; }
+        else coded = 1;
+        csbf[cy][cx] = (uint8_t)coded;
+        if (!coded) continue;
+        const int prev = right | (below << 1);
+        int start = cgi == last_cg ? last_pos - 1 : 15, seen = cgi == last_cg;
+        for (int k = start; k >= 0; k--) {
+            const int x = sx[cgi * 16 + k], y = sy[cgi * 16 + k], xp = x & 3, yp = y & 3, sig = blk[y * n + x] != 0;
+            if (k == 0 && infer_dc && !seen) break;           /* inferred significant */
+            int sc;
+            if (log2 == 2) sc = ctx_idx_map4[(yp << 2) + xp];
+            else if (cx == 0 && cy == 0 && xp == 0 && yp == 0) sc = 0;
+            else {
+                if (prev == 0) sc = (xp + yp == 0) ? 2 : (xp + yp < 3) ? 1 : 0;
+                else if (prev == 1) sc = yp == 0 ? 2 : yp == 1 ? 1 : 0;
+                else if (prev == 2) sc = xp == 0 ? 2 : xp == 1 ? 1 : 0;
+                else sc = 2;
+                if (is_luma) { if (cx || cy) sc += 3; sc += scan_idx == 0 ? 9 : 15; } else sc += 9;
+            }
+            cb_bin(c, CX_SIG + sc + (is_luma ? 0 : 27), sig);
+            seen |= sig;
+        }
+        if (!nzc) continue;
+        int absv[16], npos[16], nsig = 0;
+        uint32_t signs = 0;
+        for (int k = 15; k >= 0; k--) {
+            const int v = blk[sy[cgi * 16 + k] * n + sx[cgi * 16 + k]];
+            if (!v) continue;
+            npos[nsig] = k; absv[nsig++] = v < 0 ? -v : v; signs = (signs << 1) | (uint32_t)(v < 0);
+        }
+        int ctx_set = (cgi > 0 && is_luma) ? 2 : 0;
+        if (c1 == 0) ctx_set++;
+        c1 = 1;
+        int first_g1 = -1, ng1 = nsig < 8 ? nsig : 8;
+        for (int k = 0; k < ng1; k++) {
+            const int g1 = absv[k] > 1;
+            cb_bin(c, CX_GT1 + (is_luma ? 0 : 16) + 4 * ctx_set + c1, g1);
+            if (g1) { c1 = 0; if (first_g1 < 0) first_g1 = k; } else if (c1 < 3 && c1 > 0) c1++;
+        }
+        if (first_g1 >= 0) cb_bin(c, CX_GT2 + (is_luma ? 0 : 4) + ctx_set, absv[first_g1] > 2);
+        const int hidden = e->sp->sign_hiding && (npos[0] - npos[nsig - 1] > 3);
+        if (hidden) cb_bypass_bins(c, signs >> 1, nsig - 1); else cb_bypass_bins(c, signs, nsig);
+        int rice = 0;
+        for (int k = 0; k < nsig; k++) {
+            const int base = k < 8 ? (k == first_g1 ? 3 : 2) : 1;
+            if (absv[k] >= base) {
+                const int rem = absv[k] - base;
+                if (rem < (3 << rice)) { const int len = rem >> rice; cb_bypass_bins(c, (1u << (len + 1)) - 2, len + 1); cb_bypass_bins(c, (uint32_t)rem & ((1u << rice) - 1), rice); }
+                else {
+                    int len = rice, code = rem - (3 << rice);
+                    while (code >= (1 << len)) { code -= 1 << len; len++; }
+                    cb_bypass_bins(c, (1u << (3 + len + 1 - rice)) - 2, 3 + len + 1 - rice);
+                    cb_bypass_bins(c, (uint32_t)code, len);
+                }
+                if (absv[k] > 3 * (1 << rice) && rice < 4) rice++;
+            }
+        }
+    }
+}
+static inline int intra_scan_idx(int mode) { return (mode >= 22 && mode <= 30) ? 1 : ((mode >= 6 && mode <= 14) ? 2 : 0); }
+
 /* ---- merge / AMVP candidates (8.5.3.2.2-.7; one reference picture per list, no TMVP) ---- */
 typedef struct { int16_t x, y; } mv_t;
 typedef struct { int dir; mv_t mv[2]; } motion_t;          /* dir: bit0 list 0 used, bit1 list 1 used; unused MVs are 0 */
@@ -706,6 +831,42 @@ static int merge_idx_p(const ks_frame_syn *s, int x, int y, int size, int maxc, 
     return cur == 0 ? n : -1;             /* zero candidates fill the rest of the list: the first of them sits at index n */
 }
 
+/* luma intra mode of the prediction block covering (x,y) as a NEIGHBOUR sees it (8.4.2): DC for non-intra blocks */
+static inline int intra_mode_at(const ks_frame_syn *s, int x, int y)
+{
+    const ks_cell *n = cell_at(s, x, y);
+    if (!(n->flags & KS_F_INTRA)) return 1;
+    return n->cu_log2 == 3 ? KS_SUB_MODE(n, ((x >> 3) & 1) | (((y >> 3) & 1) << 1)) : n->intra_mode;
+}
+/* prev_intra_luma_pred_flag / mpm_idx / rem_intra_luma_pred_mode of the block at (x,y) (7.3.8.5, 8.4.2) */
+static void code_intra_mode(slice_enc *e, int x, int y, int mode)
+{
+    cabac *c = &e->cb; const ks_frame_syn *s = e->syn;
+    int cand_a = 1, cand_b = 1;
+    if (x > 0) cand_a = intra_mode_at(s, x - 1, y);
+    if (y > 0 && ((y - 1) >> KS_CTU_LOG2) == (y >> KS_CTU_LOG2)) cand_b = intra_mode_at(s, x, y - 1);
+    int mpm[3];
+    if (cand_a == cand_b) {
+        if (cand_a < 2) { mpm[0] = 0; mpm[1] = 1; mpm[2] = 26; }
+        else { mpm[0] = cand_a; mpm[1] = 2 + ((cand_a + 29) & 31); mpm[2] = 2 + ((cand_a - 2 + 1) & 31); }
+    } else {
+        mpm[0] = cand_a; mpm[1] = cand_b;
+        mpm[2] = (cand_a != 0 && cand_b != 0) ? 0 : (cand_a != 1 && cand_b != 1) ? 1 : 26;
+    }
+    int mi = -1;
+    for (int k = 0; k < 3; k++) if (mpm[k] == mode) mi = k;
+    cb_bin(c, CX_PREV_INTRA, mi >= 0);
+    if (mi >= 0) { cb_bypass(c, mi > 0); if (mi > 0) cb_bypass(c, mi > 1); }
+    else {
+        if (mpm[0] > mpm[1]) { int t = mpm[0]; mpm[0] = mpm[1]; mpm[1] = t; }
+        if (mpm[0] > mpm[2]) { int t = mpm[0]; mpm[0] = mpm[2]; mpm[2] = t; }
+        if (mpm[1] > mpm[2]) { int t = mpm[1]; mpm[1] = mpm[2]; mpm[2] = t; }
+        int rem = mode;
+        for (int k = 2; k >= 0; k--) if (rem > mpm[k]) rem--;
+        cb_bypass_bins(c, (uint32_t)rem, 5);
+    }
+}
+
 /* ---- 7.3.8.5 coding_unit ---- */
 static void code_cu(slice_enc *e, int x, int y, int log2)
 {
@@ -766,33 +927,37 @@ static void code_cu(slice_enc *e, int x, int y, int log2)
             return;
         }
     }
-    /* intra 2Nx2N */
-    if (log2 == KS_CELL_LOG2) cb_bin(c, CX_PART_MODE, 1);
-    int cand_a = 1, cand_b = 1;                       /* 8.4.2 */
-    if (x > 0) { const ks_cell *n = cell_at(s, x - 1, y); if (n->flags & KS_F_INTRA) cand_a = n->intra_mode; }
-    if (y > 0 && ((y - 1) >> KS_CTU_LOG2) == (y >> KS_CTU_LOG2)) { const ks_cell *n = cell_at(s, x, y - 1); if (n->flags & KS_F_INTRA) cand_b = n->intra_mode; }
-    int mpm[3];
-    if (cand_a == cand_b) {
-        if (cand_a < 2) { mpm[0] = 0; mpm[1] = 1; mpm[2] = 26; }
-        else { mpm[0] = cand_a; mpm[1] = 2 + ((cand_a + 29) & 31); mpm[2] = 2 + ((cand_a - 2 + 1) & 31); }
-    } else {
-        mpm[0] = cand_a; mpm[1] = cand_b;
-        mpm[2] = (cand_a != 0 && cand_b != 0) ? 0 : (cand_a != 1 && cand_b != 1) ? 1 : 26;
-    }
-    int mode = cu->intra_mode, mi = -1;
-    for (int k = 0; k < 3; k++) if (mpm[k] == mode) mi = k;
-    cb_bin(c, CX_PREV_INTRA, mi >= 0);
-    if (mi >= 0) { cb_bypass(c, mi > 0); if (mi > 0) cb_bypass(c, mi > 1); }
-    else {
-        if (mpm[0] > mpm[1]) { int t = mpm[0]; mpm[0] = mpm[1]; mpm[1] = t; }
-        if (mpm[0] > mpm[2]) { int t = mpm[0]; mpm[0] = mpm[2]; mpm[2] = t; }
-        if (mpm[1] > mpm[2]) { int t = mpm[1]; mpm[1] = mpm[2]; mpm[2] = t; }
-        int rem = mode;
-        for (int k = 2; k >= 0; k--) if (rem > mpm[k]) rem--;
-        cb_bypass_bins(c, (uint32_t)rem, 5);
-    }
+    /* intra 2Nx2N (part_mode is only present at the minimum CU size, 8x8: code_cu8) */
+    code_intra_mode(e, x, y, cu->intra_mode);
     cb_bin(c, CX_CHROMA_PRED, 0);                     /* intra_chroma_pred_mode = 4 (DM) */
     code_transform_tree(e, x, y, log2, 1);
+}
+
+/* ---- one 8x8 intra CU (sub-block k of an intra cell with cu_log2 == 3): 2Nx2N, luma TB 8x8, chroma TBs 4x4, mode-dependent scans ---- */
+static void code_cu8(slice_enc *e, int x, int y, int k)
+{
+    cabac *c = &e->cb; const ks_frame_syn *s = e->syn;
+    const ks_cell *cu = cell_at(s, x, y);
+    if (s->slice_type != KS_SLICE_I) {
+        int ctx = 0;          /* the cell's skip mark is 0 (intra): neighbours inside the cell count as not skipped */
+        if (x > 0) ctx += e->skip[(y >> KS_CELL_LOG2) * s->cells_w + ((x - 1) >> KS_CELL_LOG2)];
+        if (y > 0) ctx += e->skip[((y - 1) >> KS_CELL_LOG2) * s->cells_w + (x >> KS_CELL_LOG2)];
+        cb_bin(c, CX_SKIP + ctx, 0);
+        e->skip[(y >> KS_CELL_LOG2) * s->cells_w + (x >> KS_CELL_LOG2)] = 0;
+        cb_bin(c, CX_PRED_MODE, 1);
+    }
+    cb_bin(c, CX_PART_MODE, 1);                       /* PART_2Nx2N */
+    const int mode = KS_SUB_MODE(cu, k), scan_idx = intra_scan_idx(mode);
+    code_intra_mode(e, x, y, mode);
+    cb_bin(c, CX_CHROMA_PRED, 0);
+    const int fy = KS_SUB_CBF_Y(cu, k), fcb = KS_SUB_CBF_CB(cu, k), fcr = KS_SUB_CBF_CR(cu, k);
+    cb_bin(c, CX_CBF_CHROMA + 0, fcb);
+    cb_bin(c, CX_CBF_CHROMA + 0, fcr);
+    cb_bin(c, CX_CBF_LUMA + 1, fy);
+    const int xc = x & (KS_CTU - 1), yc = y & (KS_CTU - 1);
+    if (fy) code_residual_small(e, 0, xc, yc, 3, scan_idx);
+    if (fcb) code_residual_small(e, 1, xc >> 1, yc >> 1, 2, scan_idx);
+    if (fcr) code_residual_small(e, 2, xc >> 1, yc >> 1, 2, scan_idx);
 }
 
 /* ---- 7.3.8.4 coding_quadtree ---- */
@@ -800,14 +965,16 @@ static void code_quadtree(slice_enc *e, int x, int y, int log2)
 {
     const ks_frame_syn *s = e->syn; cabac *c = &e->cb;
     int size = 1 << log2, split;
-    if (x + size <= s->width && y + size <= s->height && log2 > KS_CELL_LOG2) {
+    if (x + size <= s->width && y + size <= s->height && log2 > KS_MIN_CB_LOG2) {
         split = cell_at(s, x, y)->cu_log2 < log2;
         int depth = KS_CTU_LOG2 - log2, ctx = 0;
         if (x > 0) ctx += (KS_CTU_LOG2 - cell_at(s, x - 1, y)->cu_log2) > depth;
         if (y > 0) ctx += (KS_CTU_LOG2 - cell_at(s, x, y - 1)->cu_log2) > depth;
         cb_bin(c, CX_SPLIT_CU + ctx, split);
-    } else split = log2 > KS_CELL_LOG2;
-    if (split) {
+    } else split = log2 > KS_CELL_LOG2;              /* coded sizes are multiples of 16: a CU of 16 or less never crosses the picture edge */
+    if (split && log2 == KS_CELL_LOG2) {
+        for (int k = 0; k < 4; k++) code_cu8(e, x + (k & 1) * 8, y + (k >> 1) * 8, k);
+    } else if (split) {
         int h = size >> 1;
         for (int k = 0; k < 4; k++) {
             int xx = x + (k & 1) * h, yy = y + (k >> 1) * h;

@@ -59,6 +59,7 @@ void ora_pic_load(ora_pic *pic, const uint8_t *i420, int sw, int sh)
 
 /* ------------------------------------------------------------------ helpers ---------------------- */
 static uint16_t scan_tb[4][1024];    /* per log2 (2..5): scan position -> (y<<8)|x, diag CG order x diag 4x4 */
+static uint16_t scan_hv[2][2][64];   /* [log2 - 2][0 horizontal, 1 vertical]: the mode-dependent scans of intra 4x4 / 8x8 blocks (7.4.9.11, 6.5.4/6.5.5) */
 static int scan_ready;
 static void build_scans(void)
 {
@@ -76,15 +77,34 @@ static void build_scans(void)
                 scan_tb[l - 2][c * 16 + k] = (uint16_t)((yy << 8) | xx);
             }
     }
+    for (int l = 2; l <= 3; l++) {
+        int ncg = 1 << (l - 2);
+        for (int c = 0; c < ncg * ncg; c++) for (int k = 0; k < 16; k++) {
+            /* horizontal: groups row by row, samples row by row; vertical: the transpose */
+            int gx = c % ncg, gy = c / ncg, px = k & 3, py = k >> 2;
+            scan_hv[l - 2][0][c * 16 + k] = (uint16_t)((((gy << 2) + py) << 8) | ((gx << 2) + px));
+            scan_hv[l - 2][1][c * 16 + k] = (uint16_t)((((gx << 2) + px) << 8) | ((gy << 2) + py));
+        }
+    }
     scan_ready = 1;
 }
-static inline int zidx(int x, int y)
+/* scan of an intra transform block (7.4.9.11): luma 4x4 / 8x8 and chroma 4x4 blocks scan horizontally for the near-vertical modes 22..30,
+ * vertically for the near-horizontal modes 6..14, diagonally otherwise */
+static const uint16_t *intra_scan(int log2, int is_luma, int mode)
 {
-    int cx = (x >> 4) & 3, cy = (y >> 4) & 3;
-    return (cx & 1) | ((cy & 1) << 1) | ((cx & 2) << 1) | ((cy & 2) << 2);
+    if (log2 == 2 || (log2 == 3 && is_luma)) {
+        if (mode >= 22 && mode <= 30) return scan_hv[log2 - 2][0];
+        if (mode >= 6 && mode <= 14) return scan_hv[log2 - 2][1];
+    }
+    return scan_tb[log2 - 2];
+}
+static inline int zidx(int x, int y)
+{   /* z-scan index of the 8x8 block containing (x,y) inside its CTB (equivalent to the 16x16 order for blocks of 16 and up) */
+    int cx = (x >> 3) & 7, cy = (y >> 3) & 7;
+    return (cx & 1) | ((cy & 1) << 1) | ((cx & 2) << 1) | ((cy & 2) << 2) | ((cx & 4) << 2) | ((cy & 4) << 3);
 }
 static int avail(const ora_cfg *cfg, int xc, int yc, int xn, int yn)
-{   /* H.265 6.4.1, one slice, CTB 64, 16x16 granularity */
+{   /* H.265 6.4.1, one slice, CTB 64, 8x8 granularity */
     if (xn < 0 || yn < 0 || xn >= cfg->width || yn >= cfg->height) return 0;
     int cw = (cfg->width + 63) >> 6;
     int ac = (yc >> 6) * cw + (xc >> 6), an = (yn >> 6) * cw + (xn >> 6);
@@ -112,15 +132,16 @@ static int level_bits_est(const int16_t *q, int n)
 /* one transform block: residual -> fdct -> quant (-> sign hiding) -> dequant -> idct+pred.  returns cbf.
  * rdz: RD zero-out (inter blocks; reference: the zero-block / skip decisions of tuDecision E@0x47e2f0 and skipFastDecision E@0x47f720 -- closed,
  * this is our rule): drop the levels when SSE(src,pred) <= SSE(src,rec) + lambda * bits. */
+static int64_t tb_d1; static int tb_bits;      /* of the last code_tb call: SSE(src, rec) and level_bits_est of the block as coded */
 static int code_tb(const ora_cfg *cfg, int qp, int intra_slice, int log2, int is_dst,
-                   const uint8_t *src, int ss, const uint8_t *pred, int ps, uint8_t *rec, int rs, int16_t *lev, int ls, int rdz_lambda_q4)
+                   const uint8_t *src, int ss, const uint8_t *pred, int ps, uint8_t *rec, int rs, int16_t *lev, int ls, int rdz_lambda_q4, const uint16_t *scan)
 {
     int n = 1 << log2;
     int16_t res[1024], coef[1024], q[1024], du[1024], deq[1024];
     ora_residual(res, src, pred, ss, ps, n);
     ora_fdct(res, coef, n, n, log2, is_dst);
     int nnz = ora_quant(coef, q, n, qp, log2, intra_slice, du);
-    if (nnz && cfg->sign_hiding) nnz = ora_sign_hide(coef, q, du, n, log2, scan_tb[log2 - 2]);
+    if (nnz && cfg->sign_hiding) nnz = ora_sign_hide(coef, q, du, n, log2, scan ? scan : scan_tb[log2 - 2]);
     if (nnz) {
         ora_dequant(q, deq, n, qp, log2);
         ora_idct_add(deq, rec, pred, n, rs, ps, log2, is_dst);
@@ -134,8 +155,10 @@ static int code_tb(const ora_cfg *cfg, int qp, int intra_slice, int log2, int is
         }
     }
     for (int y = 0; y < n; y++) memcpy(lev + (size_t)y * ls, q + y * n, (size_t)n * 2);
-    if (!nnz) { for (int y = 0; y < n; y++) memcpy(rec + (size_t)y * rs, pred + (size_t)y * ps, (size_t)n); return 0; }
-    return 1;
+    if (!nnz) for (int y = 0; y < n; y++) memcpy(rec + (size_t)y * rs, pred + (size_t)y * ps, (size_t)n);
+    tb_d1 = 0; tb_bits = nnz ? level_bits_est(q, n) : 0;
+    for (int y = 0; y < n; y++) for (int x = 0; x < n; x++) { int e = (int)src[y * ss + x] - (int)rec[y * rs + x]; tb_d1 += e * e; }
+    return nnz != 0;
 }
 
 /* ------------------------------------------------------------------ intra picture ---------------- */
@@ -156,36 +179,104 @@ static void build_nb(const ora_cfg *cfg, const ora_plane *rec, int comp, int x0,
     if (!av[0]) { int i = 1; while (!av[i]) i++; nb[0] = nb[i]; }
     for (int i = 1; i < tot; i++) if (!av[i]) nb[i] = nb[i - 1];
 }
-/* one 16x16 intra CU: 35-mode decision by SAD + lambda*bits against the reconstructed neighbours, then luma + chroma (DM) residual coding */
-static void intra_cell(const ora_cfg *cfg, int qp, int intra_slice, const ora_pic *src, ora_pic *rec, ks_cell *cells, ora_levels *lv, int x0, int y0)
+/* intra ESTIMATE of an n x n block (n = 16 or 8) in the search metric: best of DC / horizontal / vertical / planar predicted from the SOURCE
+ * picture's neighbours (left column, top row, the samples right of / below them clamped to the picture; 128 where the picture ends; no
+ * boundary smoothing).  It decides inter vs intra (stage D) and 16x16 vs four 8x8 intra CUs; the real mode search runs on reconstructed
+ * neighbours (intra_block). */
+static int intra_estimate(const ora_cfg *cfg, const ora_plane *src, int x0, int y0, int n)
 {
-    int cw = cfg->width >> 4, W = cfg->width;
-    int lam = ora_lambda_sad_q4[qp], qpc = ora_chroma_qp[qp];
+    const uint8_t *s = src->p + (size_t)y0 * src->stride + x0;
+    int W = cfg->width, H = cfg->height, st = src->stride, lg = n == 16 ? 4 : 3;
+    int left[16], top[16], hl = x0 > 0, ht = y0 > 0, sl = 0, stp = 0;
+    for (int i = 0; i < n; i++) { left[i] = hl ? s[i * st - 1] : 128; top[i] = ht ? s[i - st] : 128; sl += left[i]; stp += top[i]; }
+    int tr = ht ? src->p[(size_t)(y0 - 1) * st + imin(x0 + n, W - 1)] : 128, bl = hl ? src->p[(size_t)imin(y0 + n, H - 1) * st + x0 - 1] : 128;
+    int dc = (hl && ht) ? (sl + stp + n) >> (lg + 1) : (hl ? (sl + n / 2) >> lg : (ht ? (stp + n / 2) >> lg : 128));
+    int best = 0x7fffffff;
+    for (int m = 0; m < 4; m++) {
+        uint8_t pred[256];
+        for (int y = 0; y < n; y++) for (int x = 0; x < n; x++)
+            pred[y * n + x] = (uint8_t)(m == 0 ? dc : (m == 1 ? left[y] : (m == 2 ? top[x] : ((n - 1 - x) * left[y] + (x + 1) * tr + (n - 1 - y) * top[x] + (y + 1) * bl + n) >> (lg + 1))));
+        int c = (int)((cfg->satd && cfg->subpel > 0) ? ora_satd(s, pred, st, n, n, n) : ora_sad(s, pred, st, n, n, n));
+        if (c < best) best = c;
+    }
+    return best;
+}
+/* one intra CU of 16x16 (lg = 4) or 8x8 (lg = 3): 35-mode decision by SAD + lambda*bits against the reconstructed neighbours, then luma +
+ * chroma (DM) residual coding with the mode-dependent scans.  cost_q4 = 16 * SSE(Y,Cb,Cr) + lambda_sse * (estimated level bits + 1 per block) */
+typedef struct { int mode, cbf, luma_bits; int64_t cost_q4; } intra_res;
+static intra_res intra_block(const ora_cfg *cfg, int qp, int intra_slice, const ora_pic *src, ora_pic *rec, ora_levels *lv, int x0, int y0, int lg)
+{
+    int W = cfg->width, n = 1 << lg;
+    int lam = ora_lambda_sad_q4[qp], lamq = ora_lambda_sse_q4[qp], qpc = ora_chroma_qp[qp];
     uint8_t nb[65], pred[256];
     const uint8_t *s = src->c[0].p + (size_t)y0 * src->c[0].stride + x0;
-    build_nb(cfg, &rec->c[0], 0, x0, y0, 16, nb);
-    int best = 0, best_cost = 0x7fffffff;
+    build_nb(cfg, &rec->c[0], 0, x0, y0, n, nb);
+    intra_res r; r.mode = 0; r.cbf = 0; r.cost_q4 = 0;
+    int best_cost = 0x7fffffff;
     for (int m = 0; m < 35; m++) {
-        ora_intra_pred(pred, 16, nb, 4, m, 1, cfg->strong_intra);
+        ora_intra_pred(pred, n, nb, lg, m, 1, cfg->strong_intra);
         int bits = (m == 0 || m == 1 || m == 10 || m == 26) ? 3 : 6;
-        int cost = (int)ora_sad(s, pred, src->c[0].stride, 16, 16, 16) + ((lam * bits) >> 4);
-        if (cost < best_cost) { best_cost = cost; best = m; }
+        int cost = (int)ora_sad(s, pred, src->c[0].stride, n, n, n) + ((lam * bits) >> 4);
+        if (cost < best_cost) { best_cost = cost; r.mode = m; }
     }
-    ora_intra_pred(pred, 16, nb, 4, best, 1, cfg->strong_intra);
-    ks_cell *c = &cells[(y0 >> 4) * cw + (x0 >> 4)];
-    memset(c, 0, sizeof(*c));
-    c->cu_log2 = 4; c->flags = KS_F_INTRA; c->intra_mode = (uint8_t)best;
-    uint8_t *r = rec->c[0].p + (size_t)y0 * rec->c[0].stride + x0;
-    if (code_tb(cfg, qp, intra_slice, 4, 0, s, src->c[0].stride, pred, 16, r, rec->c[0].stride, lv->c[0] + (size_t)y0 * W + x0, W, 0)) c->flags |= KS_F_CBF_Y;
+    ora_intra_pred(pred, n, nb, lg, r.mode, 1, cfg->strong_intra);
+    uint8_t *rp = rec->c[0].p + (size_t)y0 * rec->c[0].stride + x0;
+    if (code_tb(cfg, qp, intra_slice, lg, 0, s, src->c[0].stride, pred, n, rp, rec->c[0].stride, lv->c[0] + (size_t)y0 * W + x0, W, 0, intra_scan(lg, 1, r.mode))) r.cbf |= KS_F_CBF_Y;
+    r.luma_bits = tb_bits; r.cost_q4 += tb_d1 * 16 + (int64_t)lamq * (tb_bits + 1);
     for (int ci = 1; ci < 3; ci++) {
-        int xc = x0 >> 1, yc = y0 >> 1;
+        int xc = x0 >> 1, yc = y0 >> 1, nc = n >> 1;
         uint8_t nbc[33], pc[64];
-        build_nb(cfg, &rec->c[ci], ci, xc, yc, 8, nbc);
-        ora_intra_pred(pc, 8, nbc, 3, best, 0, 0);
+        build_nb(cfg, &rec->c[ci], ci, xc, yc, nc, nbc);
+        ora_intra_pred(pc, nc, nbc, lg - 1, r.mode, 0, 0);
         const uint8_t *sc = src->c[ci].p + (size_t)yc * src->c[ci].stride + xc;
         uint8_t *rc = rec->c[ci].p + (size_t)yc * rec->c[ci].stride + xc;
-        if (code_tb(cfg, qpc, intra_slice, 3, 0, sc, src->c[ci].stride, pc, 8, rc, rec->c[ci].stride, lv->c[ci] + (size_t)yc * (W / 2) + xc, W / 2, 0))
-            c->flags |= ci == 1 ? KS_F_CBF_CB : KS_F_CBF_CR;
+        if (code_tb(cfg, qpc, intra_slice, lg - 1, 0, sc, src->c[ci].stride, pc, nc, rc, rec->c[ci].stride, lv->c[ci] + (size_t)yc * (W / 2) + xc, W / 2, 0, intra_scan(lg - 1, 0, r.mode)))
+            r.cbf |= ci == 1 ? KS_F_CBF_CB : KS_F_CBF_CR;
+        r.cost_q4 += tb_d1 * 16 + (int64_t)lamq * (tb_bits + 1);
+    }
+    return r;
+}
+/* one 16x16 intra cell: a 16x16 CU, or four 8x8 CUs coded in z-order when that is cheaper in J = SSE + lambda * bits (both are really coded;
+ * the 8x8 alternative is only tried when the 16x16 luma block costs at least ORA_SPLIT8_MIN_BITS estimated bits: smooth blocks never
+ * gain).  Reference: its intra CUs go down to 8x8 / 4x4 partitions; 8x8 CUs dominate its I pictures on natural content
+ * [probe: tools/stream_stats.py].  Header bits: 8 for a 16x16 CU, 4 x 8 + 2 for the four. */
+#define ORA_SPLIT8_MIN_BITS 100
+static void intra_cell(const ora_cfg *cfg, int qp, int intra_slice, const ora_pic *src, ora_pic *rec, ks_cell *cells, ora_levels *lv, int x0, int y0)
+{
+    int cw = cfg->width >> 4, W = cfg->width, lamq = ora_lambda_sse_q4[qp];
+    ks_cell *c = &cells[(y0 >> 4) * cw + (x0 >> 4)];
+    memset(c, 0, sizeof(*c));
+    intra_res r16 = intra_block(cfg, qp, intra_slice, src, rec, lv, x0, y0, 4);
+    c->cu_log2 = 4; c->flags = (uint8_t)(KS_F_INTRA | r16.cbf); c->intra_mode = (uint8_t)r16.mode;
+    if (r16.luma_bits < ORA_SPLIT8_MIN_BITS) return;
+    int64_t j16 = r16.cost_q4 + (int64_t)lamq * 8, j8 = (int64_t)lamq * (8 * 4 + 2);
+    /* keep the 16x16 result, then code the four 8x8 CUs over it */
+    uint8_t srec[3][256]; int16_t slev[3][256];
+    for (int ci = 0; ci < 3; ci++) {
+        int sh = ci ? 1 : 0, m = 16 >> sh, pw = W >> sh;
+        for (int y = 0; y < m; y++) {
+            memcpy(srec[ci] + y * m, rec->c[ci].p + (size_t)((y0 >> sh) + y) * rec->c[ci].stride + (x0 >> sh), (size_t)m);
+            memcpy(slev[ci] + y * m, lv->c[ci] + (size_t)((y0 >> sh) + y) * pw + (x0 >> sh), (size_t)m * 2);
+        }
+    }
+    int modes[4], cy = 0, cb = 0, cr = 0, any = 0;
+    for (int k = 0; k < 4; k++) {
+        intra_res r = intra_block(cfg, qp, intra_slice, src, rec, lv, x0 + 8 * (k & 1), y0 + 8 * (k >> 1), 3);
+        modes[k] = r.mode; any |= r.cbf; j8 += r.cost_q4;
+        if (r.cbf & KS_F_CBF_Y) cy |= 1 << k; if (r.cbf & KS_F_CBF_CB) cb |= 1 << k; if (r.cbf & KS_F_CBF_CR) cr |= 1 << k;
+    }
+    if (j8 < j16) {
+        c->cu_log2 = 3; c->flags = (uint8_t)(KS_F_INTRA | any);
+        c->mvx = (int16_t)(uint16_t)(modes[0] | (modes[1] << 8)); c->mvy = (int16_t)(uint16_t)(modes[2] | (modes[3] << 8));
+        c->intra_mode = (uint8_t)(cy | (cb << 4)); c->rsv = (uint8_t)cr;
+        return;
+    }
+    for (int ci = 0; ci < 3; ci++) {
+        int sh = ci ? 1 : 0, m = 16 >> sh, pw = W >> sh;
+        for (int y = 0; y < m; y++) {
+            memcpy(rec->c[ci].p + (size_t)((y0 >> sh) + y) * rec->c[ci].stride + (x0 >> sh), srec[ci] + y * m, (size_t)m);
+            memcpy(lv->c[ci] + (size_t)((y0 >> sh) + y) * pw + (x0 >> sh), slev[ci] + y * m, (size_t)m * 2);
+        }
     }
 }
 void ora_intra_picture(const ora_cfg *cfg, int qp, const ora_pic *src, ora_pic *rec, ks_cell *cells, ora_levels *lv)
@@ -297,12 +388,12 @@ static void recon_inter_cu(const ora_cfg *cfg, int qp, int qpc, int rdz, const o
     for (int ty = 0; ty < S; ty += T) for (int tx = 0; tx < S; tx += T) {
         int x = x0 + tx, y = y0 + ty, f = 0;
         if (code_tb(cfg, qp, 0, tl, 0, src->c[0].p + (size_t)y * src->c[0].stride + x, src->c[0].stride, pred[0] + ty * 64 + tx, 64,
-                    rec->c[0].p + (size_t)y * rec->c[0].stride + x, rec->c[0].stride, lv->c[0] + (size_t)y * W + x, W, rdz)) f |= KS_F_CBF_Y;
+                    rec->c[0].p + (size_t)y * rec->c[0].stride + x, rec->c[0].stride, lv->c[0] + (size_t)y * W + x, W, rdz, NULL)) f |= KS_F_CBF_Y;
         for (int ci = 1; ci < 3; ci++) {
             int xc = x / 2, yc = y / 2;
             if (code_tb(cfg, qpc, 0, tl - 1, 0, src->c[ci].p + (size_t)yc * src->c[ci].stride + xc, src->c[ci].stride,
                         pred[ci] + (ty / 2) * 64 + tx / 2, 64, rec->c[ci].p + (size_t)yc * rec->c[ci].stride + xc, rec->c[ci].stride,
-                        lv->c[ci] + (size_t)yc * (W / 2) + xc, W / 2, 0)) f |= ci == 1 ? KS_F_CBF_CB : KS_F_CBF_CR;
+                        lv->c[ci] + (size_t)yc * (W / 2) + xc, W / 2, 0, NULL)) f |= ci == 1 ? KS_F_CBF_CB : KS_F_CBF_CR;
         }
         for (int yy = y; yy < y + T; yy += 16) for (int xx = x; xx < x + T; xx += 16) {
             ks_cell *c = &cells[(yy >> 4) * cw + (xx >> 4)];
@@ -320,28 +411,6 @@ static void recon_inter_cu(const ora_cfg *cfg, int qp, int qpc, int rdz, const o
 #define ORA_NCAND 16
 #define ORA_INTRA_HDR_BITS 10
 typedef struct { int n; int16_t mvx[ORA_NCAND], mvy[ORA_NCAND]; int dist[16][ORA_NCAND]; int intra[16]; } ora_ctu_cands;   /* dist[j * 4 + i][k]; intra[j * 4 + i] */
-
-/* intra ESTIMATE of a 16x16 cell (search metric): best of DC / planar / horizontal / vertical predicted from the SOURCE picture's neighbours
- * (left column, top row, the samples right of / below them clamped to the picture; 128 where the picture ends; no boundary smoothing).  It only
- * decides inter vs intra in stage D; the real mode search runs on reconstructed neighbours (intra_cell). */
-static int intra_estimate(const ora_cfg *cfg, const ora_plane *src, int x0, int y0)
-{
-    const uint8_t *s = src->p + (size_t)y0 * src->stride + x0;
-    int W = cfg->width, H = cfg->height, st = src->stride;
-    int left[16], top[16], hl = x0 > 0, ht = y0 > 0, sl = 0, stp = 0;
-    for (int i = 0; i < 16; i++) { left[i] = hl ? s[i * st - 1] : 128; top[i] = ht ? s[i - st] : 128; sl += left[i]; stp += top[i]; }
-    int tr = ht ? src->p[(size_t)(y0 - 1) * st + imin(x0 + 16, W - 1)] : 128, bl = hl ? src->p[(size_t)imin(y0 + 16, H - 1) * st + x0 - 1] : 128;
-    int dc = (hl && ht) ? (sl + stp + 16) >> 5 : (hl ? (sl + 8) >> 4 : (ht ? (stp + 8) >> 4 : 128));
-    int best = 0x7fffffff;
-    for (int m = 0; m < 4; m++) {
-        uint8_t pred[256];
-        for (int y = 0; y < 16; y++) for (int x = 0; x < 16; x++)
-            pred[y * 16 + x] = (uint8_t)(m == 0 ? dc : (m == 1 ? left[y] : (m == 2 ? top[x] : ((15 - x) * left[y] + (x + 1) * tr + (15 - y) * top[x] + (y + 1) * bl + 16) >> 5)));
-        int c = (int)((cfg->satd && cfg->subpel > 0) ? ora_satd(s, pred, st, 16, 16, 16) : ora_sad(s, pred, st, 16, 16, 16));
-        if (c < best) best = c;
-    }
-    return best;
-}
 
 static int mvd_bits_est(int d) { int a = iabs(d); if (a == 0) return 1; if (a == 1) return 3; int v = a - 2, k = 1, b = 3; while (v >= (1 << k)) { v -= 1 << k; k++; b++; } return b + k + 1; }
 
@@ -366,7 +435,7 @@ static void decide_candidates(const ora_cfg *cfg, const ora_plane *src, const or
         int cx = X + i, cy = Y + j;
         if (cx >= cw || cy >= ch) continue;
         const uint8_t *s0 = src->p + (size_t)(cy << 4) * src->stride + (cx << 4), *r0 = ref->p + (size_t)(cy << 4) * ref->stride + (cx << 4);
-        t->intra[j * 4 + i] = intra_estimate(cfg, src, cx << 4, cy << 4);
+        t->intra[j * 4 + i] = intra_estimate(cfg, src, cx << 4, cy << 4, 16);
         for (int k = 0; k < t->n; k++) {
             if (t->mvx[k] == mv0[cy * cw + cx].mvx && t->mvy[k] == mv0[cy * cw + cx].mvy) { t->dist[j * 4 + i][k] = dist0[cy * cw + cx]; continue; }
             uint8_t pred[256];
@@ -532,12 +601,12 @@ static void recon_cu_from_pred(const ora_cfg *cfg, int qp, int qpc, int rdz, con
     for (int ty = 0; ty < S; ty += T) for (int tx = 0; tx < S; tx += T) {
         int x = x0 + tx, y = y0 + ty, f = 0;
         if (code_tb(cfg, qp, 0, tl, 0, src->c[0].p + (size_t)y * src->c[0].stride + x, src->c[0].stride, pred[0] + ty * 64 + tx, 64,
-                    rec->c[0].p + (size_t)y * rec->c[0].stride + x, rec->c[0].stride, lv->c[0] + (size_t)y * W + x, W, rdz)) f |= KS_F_CBF_Y;
+                    rec->c[0].p + (size_t)y * rec->c[0].stride + x, rec->c[0].stride, lv->c[0] + (size_t)y * W + x, W, rdz, NULL)) f |= KS_F_CBF_Y;
         for (int ci = 1; ci < 3; ci++) {
             int xc = x / 2, yc = y / 2;
             if (code_tb(cfg, qpc, 0, tl - 1, 0, src->c[ci].p + (size_t)yc * src->c[ci].stride + xc, src->c[ci].stride,
                         pred[ci] + (ty / 2) * 64 + tx / 2, 64, rec->c[ci].p + (size_t)yc * rec->c[ci].stride + xc, rec->c[ci].stride,
-                        lv->c[ci] + (size_t)yc * (W / 2) + xc, W / 2, 0)) f |= ci == 1 ? KS_F_CBF_CB : KS_F_CBF_CR;
+                        lv->c[ci] + (size_t)yc * (W / 2) + xc, W / 2, 0, NULL)) f |= ci == 1 ? KS_F_CBF_CB : KS_F_CBF_CR;
         }
         for (int yy = y; yy < y + T; yy += 16) for (int xx = x; xx < x + T; xx += 16) {
             ks_cell *c = &cells[(yy >> 4) * cw + (xx >> 4)];
@@ -643,17 +712,23 @@ void ora_deblock_picture_b(const ora_cfg *cfg, int qp, int beta_off, int tc_off,
     int beta = ora_beta_table[clip3(0, 51, qp + (beta_off << 1))];
     int qpc = ora_chroma_qp[qp];
     for (int dir = 0; dir < 2; dir++)
-        for (int e = 16; e < (dir ? H : W); e += 16)
+        for (int e = 8; e < (dir ? H : W); e += 8)
             for (int t = 0; t < (dir ? W : H); t += 4) {
                 int xq = dir ? t : e, yq = dir ? e : t, xp = dir ? t : e - 1, yp = dir ? e - 1 : t;
                 const ks_cell *p = &cells[(yp >> 4) * cw + (xp >> 4)], *q = &cells[(yq >> 4) * cw + (xq >> 4)];
-                if (!is_tu_edge(p, q, xp, yp, xq, yq, e)) continue;
-                int bs = edge_bs(p, q, cells_b ? &cells_b[(yp >> 4) * cw + (xp >> 4)] : NULL, cells_b ? &cells_b[(yq >> 4) * cw + (xq >> 4)] : NULL);
-                if (!bs) continue;
+                int bs;
+                if (e & 8) {                        /* inside a cell: only the CU/TU boundaries of a cell split into four 8x8 intra CUs */
+                    if (p->cu_log2 != 3) continue;
+                    bs = 2;
+                } else {
+                    if (!is_tu_edge(p, q, xp, yp, xq, yq, e)) continue;
+                    bs = edge_bs(p, q, cells_b ? &cells_b[(yp >> 4) * cw + (xp >> 4)] : NULL, cells_b ? &cells_b[(yq >> 4) * cw + (xq >> 4)] : NULL);
+                    if (!bs) continue;
+                }
                 int tc = ora_tc_table[clip3(0, 53, qp + 2 * (bs - 1) + (tc_off << 1))];
                 ora_plane *pl = &rec->c[0];
                 ora_deblock_luma_seg(pl->p + (size_t)yq * pl->stride + xq, dir ? pl->stride : 1, dir ? 1 : pl->stride, beta, tc);
-                if (bs == 2) {
+                if (bs == 2 && !(e & 8)) {          /* chroma edges lie on the 8-sample chroma grid = multiples of 16 luma samples */
                     int tcc = ora_tc_table[clip3(0, 53, qpc + 2 + (tc_off << 1))];
                     for (int ci = 1; ci < 3; ci++) {
                         ora_plane *pc = &rec->c[ci];

@@ -58,6 +58,7 @@ def test_our_streams_parse_and_match_the_model(case):
     assert err == 0 and len(pics) == n and all(oks)
     W, H = (w + 15) & ~15, (h + 15) & ~15
     for st in pics:
-        assert sum(c << (2 * (3 + i)) for i, c in enumerate(st.n_cu)) == W * H and st.n_cu[0] == 0       # our streams: CUs of 16..64, coded size
+        assert sum(c << (2 * (3 + i)) for i, c in enumerate(st.n_cu)) == W * H              # our streams: CUs of 8 (intra only) .. 64 tile the coded size
+        assert st.n_cu[0] <= sum(st.n_intra) and st.n_intra_nxn == 0
         assert st.bits_total > 0 and st.bits_sao + st.bits_split + st.bits_cu_hdr + st.bits_luma + st.bits_chroma <= st.bits_total + 64
     assert sorted(st.poc for st in pics if st.slice_type == 2)[0] == 0

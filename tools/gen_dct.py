@@ -105,15 +105,15 @@ def inv(N):
 
 def main():
     out = ["/* GENERATED by tools/gen_dct.py -- do not edit.  HEVC core transform passes (H.265 8.6.4.2 matrix) as fully unrolled",
-           " * partial butterflies with immediate coefficients.  Reference counterparts: H265_Dct{8,16,32}x*_c E@0x4b6230.. (forward,",
+           " * partial butterflies with immediate coefficients.  Reference counterparts: H265_Dct{4,8,16,32}x*_c E@0x4b6230.. (forward,",
            " * partial butterfly) and H265_2dIDct*_c E@0x4417f0.. (inverse). */", "#pragma once", "",
            "/* t0: 16x16 int table in SHARED memory, t0[j][x] = M32[2j+1][x] (only the 32-point passes read it) */", ""]
-    for n in (8, 16, 32):
+    for n in (4, 8, 16, 32):
         out.append(fwd(n)); out.append(""); out.append(inv(n)); out.append("")
     out.append("template <int N, class F> __device__ __forceinline__ void ks_fwd_pass(const int (&in)[N], int shift, const int *t0, F &&store)")
-    out.append("{ if constexpr (N == 8) ks_fwd_pass8(in, shift, t0, store); else if constexpr (N == 16) ks_fwd_pass16(in, shift, t0, store); else ks_fwd_pass32(in, shift, t0, store); }")
+    out.append("{ if constexpr (N == 4) ks_fwd_pass4(in, shift, t0, store); else if constexpr (N == 8) ks_fwd_pass8(in, shift, t0, store); else if constexpr (N == 16) ks_fwd_pass16(in, shift, t0, store); else ks_fwd_pass32(in, shift, t0, store); }")
     out.append("template <int N, class F> __device__ __forceinline__ void ks_inv_pass(F &&ld, int (&out)[N], int shift, bool clip16, const int *t0)")
-    out.append("{ if constexpr (N == 8) ks_inv_pass8(ld, out, shift, clip16, t0); else if constexpr (N == 16) ks_inv_pass16(ld, out, shift, clip16, t0); else ks_inv_pass32(ld, out, shift, clip16, t0); }")
+    out.append("{ if constexpr (N == 4) ks_inv_pass4(ld, out, shift, clip16, t0); else if constexpr (N == 8) ks_inv_pass8(ld, out, shift, clip16, t0); else if constexpr (N == 16) ks_inv_pass16(ld, out, shift, clip16, t0); else ks_inv_pass32(ld, out, shift, clip16, t0); }")
     open(sys.argv[1], "w").write("\n".join(out))
 
 
