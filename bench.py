@@ -170,6 +170,10 @@ def main():
     ref_frames = a.cpu_sample_frames or IPER
 
     import numpy as np
+    t_start = time.time()
+
+    def note(msg):          # progress marks on stderr (the JSON line on stdout stays alone)
+        print("[bench %6.1fs] %s" % (time.time() - t_start, msg), file=sys.stderr, flush=True)
 
     if a.impl == "reference":
         if rank != 0:
@@ -231,8 +235,10 @@ def main():
 
     # ---- synthetic input: one sequence PER STREAM = the base shard shifted cyclically by a stream-specific offset (different content at
     #      every CTU position, different addresses); device copies for `value`, pinned host copies for `e2e` ----
+    note("generating the synthetic sequence")
     seq = base_sequence(c)
-    base = torch.empty(IPER * FSZ, dtype=torch.uint8).pin_memory()
+    note("staging %d per-stream sequences (HBM + pinned host)" % streams)
+    base = torch.empty(IPER * FSZ, dtype=torch.uint8, pin_memory=True)
     bv = base.numpy()
     for k, fr in enumerate(seq):
         bv[k * FSZ:(k + 1) * FSZ] = fr
@@ -255,7 +261,7 @@ def main():
         avail = 0
     distinct_host = avail > 3 * streams * IPER * FSZ * max(1, world)
     if distinct_host:
-        host_seqs = [base] + [torch.empty(IPER * FSZ, dtype=torch.uint8).pin_memory() for _ in range(1, streams)]
+        host_seqs = [base] + [torch.empty(IPER * FSZ, dtype=torch.uint8, pin_memory=True) for _ in range(1, streams)]
         for s in range(1, streams):
             host_seqs[s].copy_(dev_seqs[s])
     else:
@@ -263,6 +269,7 @@ def main():
     host_np = [t.numpy() for t in host_seqs]
     torch.cuda.synchronize()
 
+    note("opening %d encoders" % streams)
     kw = dict(preset=c["preset"], qp=c["qp"], iper=IPER, device=local_rank, psnr=1, rc=c["rc"])
     if c["crf"] is not None:
         kw["crf"] = c["crf"]
@@ -307,6 +314,7 @@ def main():
         return ms, clk
 
     # ---- value: device hot path, inputs resident in HBM ----
+    note("value arm")
     for e in encs:
         e.set_profiling(True)
     ms_dev, clocks = timed(step_device, a.steps, a.warmup, ClockSampler(local_rank) if rank == 0 else None)
@@ -320,6 +328,7 @@ def main():
     value = frames_per_step * a.steps / (ms_dev / 1000.0)
 
     # ---- e2e: host buffers -> Annex-B bytes through the public API ----
+    note("e2e arm")
     ms_e2e, _ = timed(step_e2e, a.steps, max(1, min(a.warmup, 1)))
     e2e = frames_per_step * a.steps / (ms_e2e / 1000.0)
     h2d = sum(int(r[2].h2d_bytes) for r in results)
@@ -382,6 +391,7 @@ def main():
     torch.cuda.empty_cache()
 
     # ---- cpu baseline + the CLI-binary end-to-end leg (rank 0, N=1 only) ----
+    note("cpu baseline / CLI leg")
     cpu, cli = None, None
     if rank == 0 and world == 1:
         path = "/dev/shm/ks265_bench_%d.yuv" % os.getpid()
@@ -407,6 +417,7 @@ def main():
                 cli = {"value": None, "scope": "failed: %s" % str(ex)[:200]}
         if os.path.exists(path):
             os.remove(path)
+    note("done")
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,

@@ -379,7 +379,7 @@ __device__ __forceinline__ int ks_intra_sample(const uint8_t *p, int n, int log2
 }
 
 #define KS_INTRA_WARPS 16
-#define KS_SPLIT8_MIN_BITS 100          /* == ORA_SPLIT8_MIN_BITS */
+#define KS_SPLIT8_MIN_BITS 200          /* == ORA_SPLIT8_MIN_BITS */
 struct KsIntraSmem {
     KsTbScratch tb[2];
     uint16_t scan[64 + 256 + 1024];
@@ -560,7 +560,7 @@ __device__ __forceinline__ void ks_intra_code_block(KsIntraSmem &sm, const KsPic
 }
 
 /* one 16x16 intra cell by a whole CTA: a 16x16 CU, or four 8x8 CUs coded in z-order when that is cheaper in J = 16 * SSE + lambda * bits (both
- * are really coded; the 8x8 alternative is only tried when the 16x16 luma block costs at least KS_SPLIT8_MIN_BITS estimated bits).  Writes the
+ * are really coded; the 8x8 alternative is only tried in I pictures and when the 16x16 luma block costs at least KS_SPLIT8_MIN_BITS estimated bits).  Writes the
  * cell record.  Mirror of ora intra_cell. */
 __device__ __forceinline__ void ks_intra_code_cell(KsIntraSmem &sm, const KsPicParams &pp, const KsPlanes &src, const KsPlanes &rec, const KsLevels &lv,
                                                    ks_cell *__restrict__ cells, int x0, int y0, int intra_slice, int tid, int warp, int lane)
@@ -572,7 +572,7 @@ __device__ __forceinline__ void ks_intra_code_cell(KsIntraSmem &sm, const KsPicP
         sm.mode16 = (int)(sm.best_key & 63); sm.cbf16 = (int)sm.cbf;
         sm.j16 = 16ll * sm.stat_y[0].d1 + lamq * (sm.stat_y[0].bits + 1) + 16ll * sm.stat_c[0].d1 + lamq * (sm.stat_c[0].bits + 1)
                + 16ll * sm.stat_c[1].d1 + lamq * (sm.stat_c[1].bits + 1) + lamq * 8;
-        sm.try8 = sm.stat_y[0].bits >= KS_SPLIT8_MIN_BITS;
+        sm.try8 = intra_slice && sm.stat_y[0].bits >= KS_SPLIT8_MIN_BITS;       /* I pictures only: the intra CUs of P pictures stay 16x16 */
         sm.j8 = lamq * (8 * 4 + 2);
         sm.cbf8[0] = sm.cbf8[1] = sm.cbf8[2] = 0;
     }
