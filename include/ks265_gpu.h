@@ -128,7 +128,7 @@ int  ks_gpu_kat_satd16(const uint8_t *a, const uint8_t *b, long stride_a, long s
 /* interpLuma{Hor,Ver}8to8 / Hor8to16+Ver16to8 composition for a 16x16 block at quarter-sample (fx,fy);
  * `ref` points at integer sample (0,0) of a plane of size w x h (coordinates clamp at the borders) */
 int  ks_gpu_kat_interp_luma16(const uint8_t *ref_plane, int w, int h, int x, int y, int mvx, int mvy, uint8_t *dst16x16);
-/* H265_2dDct{8,16,32}_c + H265QuantBlock_c + H265DeQuantBlock_c + H265_2dIDct*_c chain on one block:
+/* H265_2dDct{4,8,16,32}_c + H265QuantBlock_c + H265DeQuantBlock_c + H265_2dIDct*_c chain on one block (log2n 2..5; the 4x4 DST is not on the device):
  * src/pred N x N (stride N); outputs levels (N x N int16) and reconstruction (N x N) */
 int  ks_gpu_kat_tb(int log2n, const uint8_t *src, const uint8_t *pred, int qp, int intra_slice, int sign_hiding,
                    int16_t *levels, uint8_t *recon, int *cbf);

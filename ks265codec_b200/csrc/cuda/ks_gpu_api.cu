@@ -533,7 +533,7 @@ extern "C" int ks_gpu_kat_tb(int log2n, const uint8_t *src, const uint8_t *pred,
                              int16_t *levels, uint8_t *recon, int *cbf)
 {
     int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) return KS_ENODEV;
-    if (log2n < 3 || log2n > 5 || qp < 0 || qp > 51) return KS_EINVAL;
+    if (log2n < 2 || log2n > 5 || qp < 0 || qp > 51) return KS_EINVAL;
     if (ks_init_device(-1)) return KS_ECUDA;
     size_t nn = (size_t)1 << (2 * log2n);
     dev_buf<uint8_t> ds(nn), dp(nn), dr(nn); dev_buf<int16_t> dl(nn); dev_buf<int> dc(1);

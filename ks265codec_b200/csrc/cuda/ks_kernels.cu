@@ -87,7 +87,8 @@ int ks_kat_interp_dev(const uint8_t *plane, int w, int h, int x, int y, int mvx,
 { ks_kat_interp_kernel<<<1, 32>>>(plane, w, h, x, y, mvx, mvy, dst); return cudaGetLastError() == cudaSuccess ? 0 : -1; }
 int ks_kat_tb_dev(int log2n, const uint8_t *src, const uint8_t *pred, int qp, int intra_slice, int sign_hiding, int16_t *levels, uint8_t *recon, int *cbf)
 {
-    if (log2n == 3) ks_kat_tb_kernel<8><<<1, 32>>>(src, pred, qp, intra_slice, sign_hiding, levels, recon, cbf);
+    if (log2n == 2) ks_kat_tb_kernel<4><<<1, 32>>>(src, pred, qp, intra_slice, sign_hiding, levels, recon, cbf);
+    else if (log2n == 3) ks_kat_tb_kernel<8><<<1, 32>>>(src, pred, qp, intra_slice, sign_hiding, levels, recon, cbf);
     else if (log2n == 4) ks_kat_tb_kernel<16><<<1, 32>>>(src, pred, qp, intra_slice, sign_hiding, levels, recon, cbf);
     else if (log2n == 5) ks_kat_tb_kernel<32><<<1, 32>>>(src, pred, qp, intra_slice, sign_hiding, levels, recon, cbf);
     else return -1;

@@ -76,7 +76,7 @@ def test_kat_interp_luma16_all_phases_and_borders():
                 first_diff(got, exp, "interp x=%d y=%d mv=(%d,%d)" % (x, y, mvx, mvy), (16, 16))
 
 
-@pytest.mark.parametrize("log2n", [3, 4, 5])
+@pytest.mark.parametrize("log2n", [2, 3, 4, 5])
 def test_kat_transform_block(log2n):
     """fdct -> quant -> (sign hiding) -> dequant -> idct+pred on the device == oracle chain (itself == reference KATs)"""
     L, O = ks.lib(), oracle()
@@ -119,6 +119,38 @@ def build_scan(log2n):
         return out
     d4, dcg = diag(4), diag(1 << (log2n - 2))
     return np.array([(((cy << 2) + py) << 8) | ((cx << 2) + px) for (cx, cy) in dcg for (px, py) in d4], np.uint16)
+
+
+def test_harvested_reference_vectors_on_the_device():
+    """the vectors harvested from the REFERENCE binary's own sad_c / had_c / interpLuma{Hor,Ver}8to8_c (tests/golden/kat_*.bin.gz) replayed
+    on the device entry points: device output == the reference's output, with no oracle in between"""
+    from katlib import GOLDEN, read_kat
+    L = ks.lib()
+    n_sad = n_had = n_int = 0
+    for name, p, ins, outs in read_kat(os.path.join(GOLDEN, "kat_sad.bin.gz")):
+        if name not in ("sad", "had") or tuple(p[:2]) != (16, 16):
+            continue
+        w, h, sa, sb = p
+        a = np.frombuffer(ins[0], np.uint8).copy(); b = np.frombuffer(ins[1], np.uint8).copy()
+        out = np.zeros(1, np.uint32)
+        fn = L.ks_gpu_kat_sad16 if name == "sad" else L.ks_gpu_kat_satd16
+        assert fn(ptr(a), ptr(b, sb + 1), sa, sb, ptr(out)) == 0
+        assert int(out[0]) == int(np.frombuffer(outs[0], np.uint32)[0]), (name, p)
+        n_sad += name == "sad"; n_had += name == "had"
+    for name, p, ins, outs in read_kat(os.path.join(GOLDEN, "kat_interp.bin.gz")):
+        if name not in ("luma_h_8to8", "luma_v_8to8") or p[0] != 32:
+            continue
+        w, h, frac, ss, ds = p
+        src = np.frombuffer(ins[0], np.uint8).copy().reshape(-1, ss)              # 80 x 80 plane; the block's sample (0,0) sits at (4,4)
+        ref = np.frombuffer(outs[0], np.uint8)[:h * ds].reshape(h, ds)[:, :w]
+        plane = np.ascontiguousarray(src[:80, :80])
+        for (bx, by) in ((0, 0), (16, 16), (8, 4)):           # 16x16 sub-blocks of the 32x32 result; all taps stay inside the harvested buffer
+            got = np.zeros((16, 16), np.uint8)
+            mvx, mvy = (frac, 0) if name == "luma_h_8to8" else (0, frac)
+            assert L.ks_gpu_kat_interp_luma16(ptr(plane), 80, 80, 4 + bx, 4 + by, mvx, mvy, ptr(got)) == 0
+            first_diff(got, ref[by:by + 16, bx:bx + 16], "%s frac %d block (%d,%d) vs the reference binary" % (name, frac, bx, by), (16, 16))
+            n_int += 1
+    assert n_sad >= 2 and n_had >= 2 and n_int >= 18
 
 
 # ---------------------------------------------------------------------------------------- picture stages
