@@ -43,6 +43,7 @@ struct ks_gpu_ctx {
     int16_t *d_lev;
     uint32_t *d_counts;
     int *d_nintra;               /* number of intra CUs the decision placed in the current P picture */
+    void *d_imodes;              /* per-cell intra luma modes (mode search kernel -> dependent intra pass) */
     void *d_cands;               /* per-CTU candidate tables of the CU decision (stage E -> stage D) */
     uint32_t *d_sse_ctu;         /* per-CTU squared error partial sums (SAO kernel -> pack scan kernel) */
     int *d_sync;
@@ -141,6 +142,7 @@ extern "C" ks_gpu_ctx *ks_gpu_open(int device, int width, int height, const ks_g
         ok = ok && cudaMalloc(&c->d_lev, c->fsz * 2) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_counts, sizeof(uint32_t) * c->ctw * c->cth) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_nintra, sizeof(int)) == cudaSuccess;
+        ok = ok && cudaMalloc(&c->d_imodes, ks_intra_workspace_bytes(c->cw * c->ch)) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_cands, ks_decide_workspace_bytes(c->ctw * c->cth)) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_sse_ctu, sizeof(uint32_t) * 3 * c->ctw * c->cth) == cudaSuccess;
         ok = ok && cudaMalloc(&c->d_sync, sizeof(int) * ((size_t)c->cw * c->ch + 1)) == cudaSuccess;
@@ -187,7 +189,7 @@ extern "C" void ks_gpu_close(ks_gpu_ctx *c)
     if (c->st) cudaStreamSynchronize(c->st);
     if (c->d_src) for (int i = 0; i < c->cfg.n_src_slots; i++) cudaFree(c->d_src[i]);
     if (c->d_rec) for (int i = 0; i < c->cfg.n_rec_slots; i++) cudaFree(c->d_rec[i]);
-    cudaFree(c->d_pre); cudaFree(c->d_pred); cudaFree(c->d_pred1); cudaFree(c->d_cells1); cudaFree(c->d_cost0); cudaFree(c->d_cost1); cudaFree(c->d_lev); cudaFree(c->d_counts); cudaFree(c->d_sse_ctu); cudaFree(c->d_cands); cudaFree(c->d_nintra); cudaFree(c->d_sync); cudaFree(c->d_stage);
+    cudaFree(c->d_pre); cudaFree(c->d_pred); cudaFree(c->d_pred1); cudaFree(c->d_cells1); cudaFree(c->d_cost0); cudaFree(c->d_cost1); cudaFree(c->d_lev); cudaFree(c->d_counts); cudaFree(c->d_sse_ctu); cudaFree(c->d_cands); cudaFree(c->d_imodes); cudaFree(c->d_nintra); cudaFree(c->d_sync); cudaFree(c->d_stage);
     for (int i = 0; i < 2; i++) { if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]); if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]); }
     if (c->syn) for (int i = 0; i < c->cfg.n_syn_slots; i++) {
         ks_syn_slot *s = &c->syn[i];
@@ -343,7 +345,7 @@ extern "C" int ks_gpu_encode_picture_submit(ks_gpu_ctx *c, const ks_pic_params *
 #define MARK(stage) do { if (c->profiling) { cudaEventRecord(s->ev[s->nev], c->st); s->stage_of[s->nev++] = (stage); } } while (0)
     if (p->slice_type == KS_SLICE_I) {
         MARK(2);
-        ks_launch_recon_intra(pp, src, pre, lv, s->d_cells, c->d_sync, NULL, c->st); c->launches += KS_LAUNCHES_RECON;
+        ks_launch_recon_intra(pp, src, pre, lv, s->d_cells, c->d_sync, NULL, c->d_imodes, c->st); c->launches += KS_LAUNCHES_INTRA;
     } else {
         KsPlanes ref = planes_of(c, c->d_rec[p->ref_slot]);
         const ks_cell *prev = p->prev_syn_slot >= 0 ? c->syn[p->prev_syn_slot].d_cells : NULL;
@@ -372,7 +374,7 @@ extern "C" int ks_gpu_encode_picture_submit(ks_gpu_ctx *c, const ks_pic_params *
         ks_launch_recon_inter(pp, src, pred, pre, lv, s->d_cells, cb, c->st); c->launches += KS_LAUNCHES_RECON;
         if (p->slice_type == KS_SLICE_P) {      /* the intra CUs the decision placed: their neighbours' inter reconstruction now exists */
             MARK(7);
-            ks_launch_recon_intra(pp, src, pre, lv, s->d_cells, c->d_sync, c->d_nintra, c->st); c->launches += KS_LAUNCHES_RECON;
+            ks_launch_recon_intra(pp, src, pre, lv, s->d_cells, c->d_sync, c->d_nintra, c->d_imodes, c->st); c->launches += KS_LAUNCHES_INTRA;
         }
     }
     s->is_b = p->slice_type == KS_SLICE_B;

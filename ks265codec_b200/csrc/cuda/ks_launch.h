@@ -40,7 +40,8 @@ void ks_launch_bidir(const KsPicParams &pp, const uint8_t *srcY, KsPlanes ref0, 
                      const ks_cell *cells1, const int *cost0, const int *cost1, KsPlanes pred1, ks_cell *cells, ks_cell_b *cells_b, KsPlanes pred, cudaStream_t st);
 void ks_launch_recon_inter(const KsPicParams &pp, KsPlanes src, KsPlanes pred, KsPlanes rec, KsLevels lv, ks_cell *cells, const ks_cell_b *cells_b, cudaStream_t st);
 /* n_intra == NULL: I picture, every cell; else P picture: only the cells flagged KS_F_INTRA (nothing if *n_intra == 0), inter-slice rounding */
-void ks_launch_recon_intra(const KsPicParams &pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *cells, int *sync_ws, const int *n_intra, cudaStream_t st);
+void ks_launch_recon_intra(const KsPicParams &pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *cells, int *sync_ws, const int *n_intra, void *modes_ws, cudaStream_t st);
+size_t ks_intra_workspace_bytes(int ncell);
 void ks_launch_deblock(const KsPicParams &pp, KsPlanes rec, const ks_cell *cells, const ks_cell_b *cells_b, cudaStream_t st);
 /* tm[3]: tensor maps of the three `deb` planes (box 96x66 / 64x34 bytes); tma_mask bit c = component c is staged by TMA */
 /* sse_ctu: per-CTU squared error of the three planes (3 x u32 per CTU) or NULL; ks_launch_pack sums them into the picture SSE */
@@ -48,4 +49,4 @@ void ks_launch_sao(const KsPicParams &pp, KsPlanes src, KsPlanes deb, KsPlanes o
                    const CUtensorMap *tm, int tma_mask, cudaStream_t st);
 void ks_launch_pack(const KsPicParams &pp, KsLevels lv, ks_ctu_syn *ctus, int16_t *pool, uint32_t *n_cg, uint32_t *scan_ws, const uint32_t *sse_ctu, unsigned long long *sse_out, cudaStream_t st);
 /* number of kernel launches each stage issues (for bench.py's gpu_launches accounting) */
-enum { KS_LAUNCHES_DECIDE = 3, KS_LAUNCHES_ME = 1, KS_LAUNCHES_RECON = 1, KS_LAUNCHES_DEBLOCK = 2, KS_LAUNCHES_SAO = 2, KS_LAUNCHES_PACK = 3 };
+enum { KS_LAUNCHES_DECIDE = 3, KS_LAUNCHES_ME = 1, KS_LAUNCHES_RECON = 1, KS_LAUNCHES_INTRA = 2, KS_LAUNCHES_DEBLOCK = 2, KS_LAUNCHES_SAO = 2, KS_LAUNCHES_PACK = 3 };

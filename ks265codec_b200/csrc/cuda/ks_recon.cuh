@@ -378,8 +378,12 @@ __device__ __forceinline__ int ks_intra_sample(const uint8_t *p, int n, int log2
     return ((32 - f) * a + f * refv(k1) + 16) >> 5;
 }
 
-#define KS_INTRA_WARPS 16
+#define KS_INTRA_WARPS 4              /* CTA of the dependent block coder: warps 0..2 substitute the three components, warps 0/1 code luma/chroma */
+#define KS_MODES_WARPS 4              /* CTA of the (independent) mode search: the 35 modes are spread over the warps */
 #define KS_SPLIT8_MIN_BITS 200          /* == ORA_SPLIT8_MIN_BITS */
+/* luma modes of one cell, chosen by ks_intra_modes_kernel: the 16x16 CU's and the four 8x8 CUs' */
+struct KsIntraModes { uint8_t m16, m8[4], rsv[3]; };
+
 struct KsIntraSmem {
     KsTbScratch tb[2];
     uint16_t scan[64 + 256 + 1024];
@@ -391,8 +395,6 @@ struct KsIntraSmem {
     uint8_t  av[3][72];
     uint8_t  predY[16 * 16];
     uint8_t  predC[2][8 * 8];
-    uint8_t  mref[KS_INTRA_WARPS][64];  /* per-warp extended main reference of the mode under test: index k+n, k = -n..2n */
-    unsigned best_key;
     int      dc[3];
     int      ticket;
     unsigned cbf;
@@ -402,7 +404,15 @@ struct KsIntraSmem {
     int16_t  save_lev[256 + 64 + 64];
     int      try8, use8;
     long long j16, j8;
-    int      mode16, cbf16, modes8[4], cbf8[3];
+    int      cbf16, cbf8[3];
+    KsIntraModes modes;
+};
+/* working set of the mode search (one cell per CTA) */
+struct KsModesSmem {
+    uint8_t  nb[72], raw[72], fb[72], av[72];
+    uint8_t  mref[KS_MODES_WARPS][64];  /* per-warp extended main reference of the mode under test: index k+n, k = -n..2n */
+    unsigned best_key;
+    int      dc;
 };
 
 /* reference-sample substitution (spec 8.4.4.2.2) for one component by one warp: every entry takes the nearest available
@@ -445,58 +455,49 @@ __device__ __forceinline__ void ks_intra_load_small_scans(KsIntraSmem &sm, int t
     }
 }
 
-/* one intra CU of 16x16 (LG = 4) or 8x8 (LG = 3) by a whole CTA (KS_INTRA_WARPS warps): reference samples with availability, 35-mode decision
- * by SAD + lambda * bits, prediction, luma + chroma (DM) residual coding with the mode-dependent scans.  Results in shared memory: best_key & 63
- * = mode, cbf, stat_y[0] / stat_c[0..1].  Ends with a CTA barrier.  Mirror of ora intra_block. */
+/* ---- the 35-mode search of one intra block (LG = 4: 16x16, 3: 8x8) against the SOURCE picture's neighbours, by the KS_MODES_WARPS warps of a CTA:
+ *      SAD + lambda * bits; warp w evaluates modes w, w+4, ... on all N*N samples.  Angular modes first project the (possibly filtered) references
+ *      onto one extended main-reference array per mode (spec 8.4.4.2.6 ref[]), so a sample costs two shared loads + one interpolation.
+ *      Taking the neighbours from the source (not the reconstruction) makes every block of the picture independent: the search leaves the
+ *      wavefront's dependency chain.  Returns the mode (in every thread); ends with a CTA barrier.  Mirror of ora intra_block's decision. ---- */
 template <int LG>
-__device__ __forceinline__ void ks_intra_code_block(KsIntraSmem &sm, const KsPicParams &pp, const KsPlanes &src, const KsPlanes &rec, const KsLevels &lv,
-                                                    int x0, int y0, int intra_slice, int tid, int warp, int lane)
+__device__ __forceinline__ int ks_intra_search(KsModesSmem &sm, const KsPicParams &pp, const uint8_t *__restrict__ srcY, int x0, int y0, int tid, int warp, int lane)
 {
-    constexpr int N = 1 << LG, NC = N / 2, TL = 4 * N + 1, TC = 2 * N + 1;
-    const int W = pp.W, H = pp.H, CW = W >> 1;
-    /* 1. reference samples with availability (8.4.4.2.2); neighbours come from the pre-filter reconstruction.
-     *    __ldcg: other CTAs (or earlier blocks of this one) wrote these lines, bypass the (non-coherent) L1 */
-    if (tid < TL + 2 * TC) {
-        int idx = tid;
-        int ci = idx < TL ? 0 : (idx < TL + TC ? 1 : 2), i = idx - (ci == 0 ? 0 : (ci == 1 ? TL : TL + TC));
-        int n = ci ? NC : N, sh = ci ? 1 : 0, bx = x0 >> sh, by = y0 >> sh, xn, yn;
-        if (i < 2 * n) { xn = bx - 1; yn = by + 2 * n - 1 - i; }
-        else if (i == 2 * n) { xn = bx - 1; yn = by - 1; }
-        else { xn = bx + i - 2 * n - 1; yn = by - 1; }
-        bool a = ks_avail(W, H, pp.ctw, x0, y0, xn << sh, yn << sh);
-        sm.av[ci][i] = a;
-        sm.raw[ci][i] = a ? __ldcg(rec.p[ci] + (size_t)yn * (W >> sh) + xn) : 0;
+    constexpr int N = 1 << LG, TL = 4 * N + 1, FTHR = N == 16 ? 1 : 7, PER = N * N / 32, STEP = 32 / N;
+    const int W = pp.W, H = pp.H;
+    if (tid < TL) {
+        int xn, yn;
+        if (tid < 2 * N) { xn = x0 - 1; yn = y0 + 2 * N - 1 - tid; }
+        else if (tid == 2 * N) { xn = x0 - 1; yn = y0 - 1; }
+        else { xn = x0 + tid - 2 * N - 1; yn = y0 - 1; }
+        const bool a = ks_avail(W, H, pp.ctw, x0, y0, xn, yn);
+        sm.av[tid] = a;
+        sm.raw[tid] = a ? srcY[(size_t)yn * W + xn] : 0;
     }
-    if (tid == 255) { sm.best_key = 0xffffffffu; sm.cbf = 0; }
+    if (tid == 127) sm.best_key = 0xffffffffu;
     __syncthreads();
-    if (warp < 3) {
-        ks_intra_substitute(sm.raw[warp], sm.av[warp], sm.nb[warp], warp ? TC : TL, warp ? NC : N, &sm.dc[warp], lane);
-        if (warp == 0)
-            for (int i = lane; i < TL; i += 32)
-                sm.fb[i] = (i == 0 || i == 4 * N) ? sm.nb[0][i] : (uint8_t)((sm.nb[0][i - 1] + 2 * sm.nb[0][i] + sm.nb[0][i + 1] + 2) >> 2);
+    if (warp == 0) {
+        ks_intra_substitute(sm.raw, sm.av, sm.nb, TL, N, &sm.dc, lane);
+        for (int i = lane; i < TL; i += 32)
+            sm.fb[i] = (i == 0 || i == 4 * N) ? sm.nb[i] : (uint8_t)((sm.nb[i - 1] + 2 * sm.nb[i] + sm.nb[i + 1] + 2) >> 2);
     }
     __syncthreads();
-    /* 2. mode decision by SAD + lambda*bits: warp w evaluates modes w, w+16, w+32 on all N*N samples.
-     *    Angular modes first project the (possibly filtered) references onto one extended main-reference array
-     *    per mode (spec 8.4.4.2.6 ref[]), so a sample costs two shared loads + one interpolation. */
-    constexpr int FTHR = N == 16 ? 1 : 7;                        /* intraHorVerDistThres[nTbS] */
     {
-        constexpr int PER = N * N / 32, STEP = 32 / N;
         unsigned best = 0xffffffffu;
         const int px = lane & (N - 1), py0 = lane >> LG;
         uint8_t s[PER];
 #pragma unroll
-        for (int j = 0; j < PER; j++) s[j] = src.p[0][(size_t)(y0 + py0 + STEP * j) * W + x0 + px];
+        for (int j = 0; j < PER; j++) s[j] = srcY[(size_t)(y0 + py0 + STEP * j) * W + x0 + px];
         uint8_t *mref = sm.mref[warp];
 #pragma unroll 1
-        for (int m = warp; m < 35; m += KS_INTRA_WARPS) {
+        for (int m = warp; m < 35; m += KS_MODES_WARPS) {
             int d1 = abs(m - 26), d2 = abs(m - 10);
-            bool filt = m != 1 && min(d1, d2) > FTHR;
-            const uint8_t *p = filt ? sm.fb : sm.nb[0];
+            bool filt = m != 1 && min(d1, d2) > FTHR;            /* intraHorVerDistThres[nTbS] */
+            const uint8_t *p = filt ? sm.fb : sm.nb;
             unsigned sad = 0;
             if (m < 2) {
 #pragma unroll
-                for (int j = 0; j < PER; j++) sad += abs(ks_intra_sample(p, N, LG, m, px, py0 + STEP * j, sm.dc[0], true) - (int)s[j]);
+                for (int j = 0; j < PER; j++) sad += abs(ks_intra_sample(p, N, LG, m, px, py0 + STEP * j, sm.dc, true) - (int)s[j]);
             } else {
                 const int ang = c_intra_angle[m], inv = c_intra_inv_angle[m];
                 const bool vert = m >= 18;
@@ -531,18 +532,74 @@ __device__ __forceinline__ void ks_intra_code_block(KsIntraSmem &sm, const KsPic
     }
     __syncthreads();
     const int mode = (int)(sm.best_key & 63);
-    const int scan_idx = (mode >= 22 && mode <= 30) ? 1 : ((mode >= 6 && mode <= 14) ? 2 : 0);
-    /* 3. prediction blocks: threads 0..N*N-1 luma, then 2 x NC*NC chroma */
-    if (tid < N * N) {
-        int d1 = abs(mode - 26), d2 = abs(mode - 10);
-        bool filt = mode != 1 && min(d1, d2) > FTHR;
-        sm.predY[tid] = (uint8_t)ks_intra_sample(filt ? sm.fb : sm.nb[0], N, LG, mode, tid & (N - 1), tid >> LG, sm.dc[0], true);
-    } else if (tid < N * N + 2 * NC * NC) {
-        int t = tid - N * N, ci = t / (NC * NC), k = t % (NC * NC);
-        sm.predC[ci][k] = (uint8_t)ks_intra_sample(sm.nb[1 + ci], NC, LG - 1, mode, k & (NC - 1), k / NC, sm.dc[1 + ci], false);
+    __syncthreads();                                     /* best_key is reset by the next call */
+    return mode;
+}
+
+/* the luma modes of every intra cell of the picture (I pictures: all cells incl. the four 8x8 alternatives; P pictures: the cells flagged
+ * KS_F_INTRA, 16x16 only): one CTA per cell, no dependencies between cells */
+__global__ void __launch_bounds__(KS_MODES_WARPS * KS_WARP)
+ks_intra_modes_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, const ks_cell *__restrict__ cells, const int *__restrict__ n_intra, KsIntraModes *__restrict__ modes)
+{
+    __shared__ KsModesSmem sm;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int cell = blockIdx.x, cy = cell / pp.cw, cx = cell - cy * pp.cw, x0 = cx << 4, y0 = cy << 4;
+    const bool masked = n_intra != nullptr;
+    if (masked && (*n_intra == 0 || !(cells[cell].flags & KS_F_INTRA))) return;
+    KsIntraModes r; r.rsv[0] = r.rsv[1] = r.rsv[2] = 0; r.m8[0] = r.m8[1] = r.m8[2] = r.m8[3] = 0;
+    r.m16 = (uint8_t)ks_intra_search<4>(sm, pp, srcY, x0, y0, tid, warp, lane);
+    if (!masked) {
+#pragma unroll 1
+        for (int k = 0; k < 4; k++) r.m8[k] = (uint8_t)ks_intra_search<3>(sm, pp, srcY, x0 + 8 * (k & 1), y0 + 8 * (k >> 1), tid, warp, lane);
+    }
+    if (tid == 0) modes[cell] = r;
+}
+
+/* one intra CU of 16x16 (LG = 4) or 8x8 (LG = 3) with a GIVEN luma mode, by a CTA of KS_INTRA_WARPS warps: reference samples (reconstruction,
+ * with availability), prediction, luma + chroma (DM) residual coding with the mode-dependent scans.  Results in shared memory: cbf,
+ * stat_y[0] / stat_c[0..1].  Ends with a CTA barrier.  Mirror of ora intra_block after its decision. */
+template <int LG>
+__device__ __forceinline__ void ks_intra_code_block(KsIntraSmem &sm, const KsPicParams &pp, const KsPlanes &src, const KsPlanes &rec, const KsLevels &lv,
+                                                    int x0, int y0, int mode, int intra_slice, int tid, int warp, int lane)
+{
+    constexpr int N = 1 << LG, NC = N / 2, TL = 4 * N + 1, TC = 2 * N + 1, FTHR = N == 16 ? 1 : 7, NT = KS_INTRA_WARPS * KS_WARP;
+    const int W = pp.W, H = pp.H, CW = W >> 1;
+    /* 1. reference samples with availability (8.4.4.2.2); neighbours come from the pre-filter reconstruction.
+     *    __ldcg: other CTAs (or earlier blocks of this one) wrote these lines, bypass the (non-coherent) L1 */
+    for (int idx = tid; idx < TL + 2 * TC; idx += NT) {
+        int ci = idx < TL ? 0 : (idx < TL + TC ? 1 : 2), i = idx - (ci == 0 ? 0 : (ci == 1 ? TL : TL + TC));
+        int n = ci ? NC : N, sh = ci ? 1 : 0, bx = x0 >> sh, by = y0 >> sh, xn, yn;
+        if (i < 2 * n) { xn = bx - 1; yn = by + 2 * n - 1 - i; }
+        else if (i == 2 * n) { xn = bx - 1; yn = by - 1; }
+        else { xn = bx + i - 2 * n - 1; yn = by - 1; }
+        bool a = ks_avail(W, H, pp.ctw, x0, y0, xn << sh, yn << sh);
+        sm.av[ci][i] = a;
+        sm.raw[ci][i] = a ? __ldcg(rec.p[ci] + (size_t)yn * (W >> sh) + xn) : 0;
+    }
+    if (tid == 0) sm.cbf = 0;
+    __syncthreads();
+    if (warp < 3) {
+        ks_intra_substitute(sm.raw[warp], sm.av[warp], sm.nb[warp], warp ? TC : TL, warp ? NC : N, &sm.dc[warp], lane);
+        if (warp == 0)
+            for (int i = lane; i < TL; i += 32)
+                sm.fb[i] = (i == 0 || i == 4 * N) ? sm.nb[0][i] : (uint8_t)((sm.nb[0][i - 1] + 2 * sm.nb[0][i] + sm.nb[0][i + 1] + 2) >> 2);
     }
     __syncthreads();
-    /* 4. residual coding: warp 0 luma (lanes 0..N-1), warp 1 Cb + Cr (lanes 0..2*NC-1) */
+    const int scan_idx = (mode >= 22 && mode <= 30) ? 1 : ((mode >= 6 && mode <= 14) ? 2 : 0);
+    /* 2. prediction blocks: N*N luma samples, then 2 x NC*NC chroma */
+    {
+        const int d1 = abs(mode - 26), d2 = abs(mode - 10);
+        const bool filt = mode != 1 && min(d1, d2) > FTHR;
+        for (int t = tid; t < N * N + 2 * NC * NC; t += NT) {
+            if (t < N * N) sm.predY[t] = (uint8_t)ks_intra_sample(filt ? sm.fb : sm.nb[0], N, LG, mode, t & (N - 1), t >> LG, sm.dc[0], true);
+            else {
+                const int u = t - N * N, ci = u / (NC * NC), k = u % (NC * NC);
+                sm.predC[ci][k] = (uint8_t)ks_intra_sample(sm.nb[1 + ci], NC, LG - 1, mode, k & (NC - 1), k / NC, sm.dc[1 + ci], false);
+            }
+        }
+    }
+    __syncthreads();
+    /* 3. residual coding: warp 0 luma (lanes 0..N-1), warp 1 Cb + Cr (lanes 0..2*NC-1) */
     if (warp == 0) {
         int g = lane / N, r = lane % N, y = y0 + r;
         const uint16_t *scan = LG == 4 ? sm.scan + 64 : (scan_idx == 0 ? sm.scan : sm.scan8hv[scan_idx - 1]);
@@ -559,17 +616,20 @@ __device__ __forceinline__ void ks_intra_code_block(KsIntraSmem &sm, const KsPic
     __syncthreads();
 }
 
-/* one 16x16 intra cell by a whole CTA: a 16x16 CU, or four 8x8 CUs coded in z-order when that is cheaper in J = 16 * SSE + lambda * bits (both
- * are really coded; the 8x8 alternative is only tried in I pictures and when the 16x16 luma block costs at least KS_SPLIT8_MIN_BITS estimated bits).  Writes the
- * cell record.  Mirror of ora intra_cell. */
+/* one 16x16 intra cell by a CTA: a 16x16 CU, or four 8x8 CUs coded in z-order when that is cheaper in J = 16 * SSE + lambda * bits (both
+ * are really coded; the 8x8 alternative is only tried in I pictures and when the 16x16 luma block costs at least KS_SPLIT8_MIN_BITS estimated bits).
+ * The luma modes come from ks_intra_modes_kernel.  Writes the cell record.  Mirror of ora intra_cell. */
 __device__ __forceinline__ void ks_intra_code_cell(KsIntraSmem &sm, const KsPicParams &pp, const KsPlanes &src, const KsPlanes &rec, const KsLevels &lv,
-                                                   ks_cell *__restrict__ cells, int x0, int y0, int intra_slice, int tid, int warp, int lane)
+                                                   ks_cell *__restrict__ cells, const KsIntraModes *__restrict__ modes, int x0, int y0, int intra_slice, int tid, int warp, int lane)
 {
-    const int W = pp.W;
+    const int W = pp.W, NT = KS_INTRA_WARPS * KS_WARP;
     const long long lamq = pp.lambda_sse_q4;
-    ks_intra_code_block<4>(sm, pp, src, rec, lv, x0, y0, intra_slice, tid, warp, lane);
+    if (tid == 0) sm.modes = modes[(y0 >> 4) * pp.cw + (x0 >> 4)];
+    __syncthreads();
+    const KsIntraModes md = sm.modes;
+    ks_intra_code_block<4>(sm, pp, src, rec, lv, x0, y0, md.m16, intra_slice, tid, warp, lane);
     if (tid == 0) {
-        sm.mode16 = (int)(sm.best_key & 63); sm.cbf16 = (int)sm.cbf;
+        sm.cbf16 = (int)sm.cbf;
         sm.j16 = 16ll * sm.stat_y[0].d1 + lamq * (sm.stat_y[0].bits + 1) + 16ll * sm.stat_c[0].d1 + lamq * (sm.stat_c[0].bits + 1)
                + 16ll * sm.stat_c[1].d1 + lamq * (sm.stat_c[1].bits + 1) + lamq * 8;
         sm.try8 = intra_slice && sm.stat_y[0].bits >= KS_SPLIT8_MIN_BITS;       /* I pictures only: the intra CUs of P pictures stay 16x16 */
@@ -579,17 +639,16 @@ __device__ __forceinline__ void ks_intra_code_cell(KsIntraSmem &sm, const KsPicP
     __syncthreads();
     if (sm.try8) {
         /* keep the 16x16 result (its stores are visible after the barrier above), then code the four 8x8 CUs over it */
-        if (tid < 384) {
-            const int ci = tid < 256 ? 0 : (tid < 320 ? 1 : 2), k = tid - (ci == 0 ? 0 : (ci == 1 ? 256 : 320)), m = ci ? 8 : 16, sh = ci ? 1 : 0;
+        for (int t = tid; t < 384; t += NT) {
+            const int ci = t < 256 ? 0 : (t < 320 ? 1 : 2), k = t - (ci == 0 ? 0 : (ci == 1 ? 256 : 320)), m = ci ? 8 : 16, sh = ci ? 1 : 0;
             const size_t o = (size_t)((y0 >> sh) + k / m) * (W >> sh) + (x0 >> sh) + k % m;
-            sm.save_rec[tid] = __ldcg(rec.p[ci] + o); sm.save_lev[tid] = __ldcg(lv.p[ci] + o);
+            sm.save_rec[t] = __ldcg(rec.p[ci] + o); sm.save_lev[t] = __ldcg(lv.p[ci] + o);
         }
         __syncthreads();
 #pragma unroll 1
         for (int k = 0; k < 4; k++) {
-            ks_intra_code_block<3>(sm, pp, src, rec, lv, x0 + 8 * (k & 1), y0 + 8 * (k >> 1), intra_slice, tid, warp, lane);
+            ks_intra_code_block<3>(sm, pp, src, rec, lv, x0 + 8 * (k & 1), y0 + 8 * (k >> 1), md.m8[k], intra_slice, tid, warp, lane);
             if (tid == 0) {
-                sm.modes8[k] = (int)(sm.best_key & 63);
                 if (sm.cbf & KS_F_CBF_Y) sm.cbf8[0] |= 1 << k; if (sm.cbf & KS_F_CBF_CB) sm.cbf8[1] |= 1 << k; if (sm.cbf & KS_F_CBF_CR) sm.cbf8[2] |= 1 << k;
                 sm.j8 += 16ll * sm.stat_y[0].d1 + lamq * (sm.stat_y[0].bits + 1) + 16ll * sm.stat_c[0].d1 + lamq * (sm.stat_c[0].bits + 1)
                        + 16ll * sm.stat_c[1].d1 + lamq * (sm.stat_c[1].bits + 1);
@@ -602,23 +661,24 @@ __device__ __forceinline__ void ks_intra_code_cell(KsIntraSmem &sm, const KsPicP
             if (tid == 0) {
                 ks_cell c; c.cu_log2 = 3;
                 c.flags = (uint8_t)(KS_F_INTRA | (sm.cbf8[0] ? KS_F_CBF_Y : 0) | (sm.cbf8[1] ? KS_F_CBF_CB : 0) | (sm.cbf8[2] ? KS_F_CBF_CR : 0));
-                c.mvx = (int16_t)(uint16_t)(sm.modes8[0] | (sm.modes8[1] << 8)); c.mvy = (int16_t)(uint16_t)(sm.modes8[2] | (sm.modes8[3] << 8));
+                c.mvx = (int16_t)(uint16_t)(md.m8[0] | (md.m8[1] << 8)); c.mvy = (int16_t)(uint16_t)(md.m8[2] | (md.m8[3] << 8));
                 c.intra_mode = (uint8_t)(sm.cbf8[0] | (sm.cbf8[1] << 4)); c.rsv = (uint8_t)sm.cbf8[2];
                 cells[(y0 >> 4) * pp.cw + (x0 >> 4)] = c;
             }
+            __syncthreads();
             return;
         }
-        if (tid < 384) {          /* the 16x16 CU wins: put its reconstruction and levels back */
-            const int ci = tid < 256 ? 0 : (tid < 320 ? 1 : 2), k = tid - (ci == 0 ? 0 : (ci == 1 ? 256 : 320)), m = ci ? 8 : 16, sh = ci ? 1 : 0;
+        for (int t = tid; t < 384; t += NT) {          /* the 16x16 CU wins: put its reconstruction and levels back */
+            const int ci = t < 256 ? 0 : (t < 320 ? 1 : 2), k = t - (ci == 0 ? 0 : (ci == 1 ? 256 : 320)), m = ci ? 8 : 16, sh = ci ? 1 : 0;
             const size_t o = (size_t)((y0 >> sh) + k / m) * (W >> sh) + (x0 >> sh) + k % m;
-            rec.p[ci][o] = sm.save_rec[tid]; lv.p[ci][o] = sm.save_lev[tid];
+            rec.p[ci][o] = sm.save_rec[t]; lv.p[ci][o] = sm.save_lev[t];
         }
-        __syncthreads();          /* the caller publishes the cell as finished right after this function */
     }
     if (tid == 0) {
-        ks_cell c; c.mvx = 0; c.mvy = 0; c.cu_log2 = 4; c.flags = (uint8_t)(KS_F_INTRA | sm.cbf16); c.intra_mode = (uint8_t)sm.mode16; c.rsv = 0;
+        ks_cell c; c.mvx = 0; c.mvy = 0; c.cu_log2 = 4; c.flags = (uint8_t)(KS_F_INTRA | sm.cbf16); c.intra_mode = md.m16; c.rsv = 0;
         cells[(y0 >> 4) * pp.cw + (x0 >> 4)] = c;
     }
+    __syncthreads();          /* the caller publishes the cell as finished right after this function */
 }
 
 /* I pictures.  The block order inside a CTU (z-scan) and the availability rules are normative, so the parallelism is the
@@ -628,9 +688,8 @@ __device__ __forceinline__ void ks_intra_code_cell(KsIntraSmem &sm, const KsPicP
 /* MINB = CTAs per SM the register budget is sized for: 1 lets the compiler take 128 registers x 512 threads = the whole register file,
  * which locks every other stream's kernels out of up to 68 SMs for the ~15 ms an I picture takes; 2 caps it at 64 and leaves half
  * of each of those SMs to the P pictures of the other GOP shards */
-template <int MINB>
-__global__ void __launch_bounds__(KS_INTRA_WARPS * KS_WARP, MINB)
-ks_recon_intra_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells, int *sync_ws)
+__global__ void __launch_bounds__(KS_INTRA_WARPS * KS_WARP)
+ks_recon_intra_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells, int *sync_ws, const KsIntraModes *__restrict__ modes)
 {
     __shared__ __align__(16) KsIntraSmem sm;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -657,7 +716,7 @@ ks_recon_intra_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, k
                 __threadfence();
             }
             __syncthreads();
-            if (inside) ks_intra_code_cell(sm, pp, src, rec, lv, cells, x0, y0, 1, tid, warp, lane);
+            if (inside) ks_intra_code_cell(sm, pp, src, rec, lv, cells, modes, x0, y0, 1, tid, warp, lane);
             if (tid == 0) { __threadfence(); atomicExch(&progress[cty * pp.ctw + ctx], z + 1); }
         }
     }
@@ -668,8 +727,9 @@ ks_recon_intra_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, k
  * above-left, above, above-right, below-left neighbours that precede it in coding order -- through per-cell done flags in HBM.  A CTA only ever
  * waits on cells of CTUs with smaller tickets (or its own earlier cells), which are running or finished: no deadlock.  CTUs without flagged
  * cells cost one 16-cell read.  (The wavefront kernel above took 0.3 ms per P picture in this role: it walks every CTU row serially.) */
-__global__ void __launch_bounds__(KS_INTRA_WARPS * KS_WARP, 2)
-ks_recon_intra_sparse_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells, int *sync_ws, const int *__restrict__ n_intra)
+__global__ void __launch_bounds__(KS_INTRA_WARPS * KS_WARP)
+ks_recon_intra_sparse_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells, int *sync_ws, const int *__restrict__ n_intra,
+                             const KsIntraModes *__restrict__ modes)
 {
     __shared__ __align__(16) KsIntraSmem sm;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -707,7 +767,7 @@ ks_recon_intra_sparse_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevel
                 }
             }
             __syncthreads();
-            ks_intra_code_cell(sm, pp, src, rec, lv, cells, x0, y0, 0, tid, warp, lane);
+            ks_intra_code_cell(sm, pp, src, rec, lv, cells, modes, x0, y0, 0, tid, warp, lane);
             __syncthreads();
             if (tid == 0) { __threadfence(); atomicExch(&done[gy * pp.cw + gx], 1); }
         }
@@ -715,15 +775,17 @@ ks_recon_intra_sparse_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevel
 }
 
 /* n_intra == NULL: I picture (every cell, wavefront kernel); else P picture: only the cells flagged KS_F_INTRA, inter-slice rounding */
-void ks_launch_recon_intra(const KsPicParams &pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *cells, int *sync_ws, const int *n_intra, cudaStream_t st)
+void ks_launch_recon_intra(const KsPicParams &pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *cells, int *sync_ws, const int *n_intra, void *modes_ws, cudaStream_t st)
 {
+    KsIntraModes *modes = reinterpret_cast<KsIntraModes *>(modes_ws);
+    /* the mode search of every (flagged) cell, independent of the reconstruction; then the dependent prediction + residual pass */
+    ks_intra_modes_kernel<<<pp.cw * pp.ch, KS_MODES_WARPS * KS_WARP, 0, st>>>(pp, src.p[0], cells, n_intra, modes);
     if (n_intra) {
         cudaMemsetAsync(sync_ws, 0, sizeof(int) * (size_t)(1 + pp.cw * pp.ch), st);
-        ks_recon_intra_sparse_kernel<<<2 * 148, KS_INTRA_WARPS * KS_WARP, 0, st>>>(pp, src, rec, lv, cells, sync_ws, n_intra);
+        ks_recon_intra_sparse_kernel<<<4 * 148, KS_INTRA_WARPS * KS_WARP, 0, st>>>(pp, src, rec, lv, cells, sync_ws, n_intra, modes);
         return;
     }
     cudaMemsetAsync(sync_ws, 0, sizeof(int) * (size_t)(1 + pp.ctw * pp.cth), st);
-    static const int minb = getenv("KS_INTRA_MINB") ? atoi(getenv("KS_INTRA_MINB")) : 2;     /* tuning knob, see the kernel comment */
-    if (minb <= 1) ks_recon_intra_kernel<1><<<2 * pp.cth, KS_INTRA_WARPS * KS_WARP, 0, st>>>(pp, src, rec, lv, cells, sync_ws);
-    else ks_recon_intra_kernel<2><<<2 * pp.cth, KS_INTRA_WARPS * KS_WARP, 0, st>>>(pp, src, rec, lv, cells, sync_ws);
+    ks_recon_intra_kernel<<<2 * pp.cth, KS_INTRA_WARPS * KS_WARP, 0, st>>>(pp, src, rec, lv, cells, sync_ws, modes);
 }
+size_t ks_intra_workspace_bytes(int ncell) { return (size_t)ncell * sizeof(KsIntraModes); }
