@@ -681,111 +681,59 @@ __device__ __forceinline__ void ks_intra_code_cell(KsIntraSmem &sm, const KsPicP
     __syncthreads();          /* the caller publishes the cell as finished right after this function */
 }
 
-/* I pictures.  The block order inside a CTU (z-scan) and the availability rules are normative, so the parallelism is the
- * dependency DAG itself: two CTAs per CTU row take alternate CTUs (CTU c+1 may start once CTU c finished its first 8 blocks),
- * rows follow each other with a one-CTU lag, all inside ONE launch.  Progress = blocks finished per CTU, published in HBM;
- * CTAs take (row, parity) tickets in start order so a CTA only ever waits on work that is already running or done. */
-/* MINB = CTAs per SM the register budget is sized for: 1 lets the compiler take 128 registers x 512 threads = the whole register file,
- * which locks every other stream's kernels out of up to 68 SMs for the ~15 ms an I picture takes; 2 caps it at 64 and leaves half
- * of each of those SMs to the P pictures of the other GOP shards */
+/* The dependent pass of the intra CUs (I pictures: every cell; P pictures: the cells the CU decision flagged KS_F_INTRA, after the inter
+ * reconstruction of everything else).  Which neighbours a block may read is fixed by the normative z-scan order, but the order in which blocks
+ * are PROCESSED is free as long as those neighbours are finished.  So: one CTA per 16-sample cell row (rows handed out by a ticket counter,
+ * top first), walking its row left to right; before a cell it waits -- per-cell done flags in HBM -- for exactly the cells it reads:
+ * above-left, above, above-right and below-left, each only if the z-scan order makes it available (and, in P pictures, only if it is an intra
+ * cell; inter cells were finished by the previous kernel).  Every wait is on a cell that precedes this one in decoding order, and a row only
+ * ever waits on cells of rows that are running (all rows are resident: <= 270 CTAs at 8K, 3 per SM): no deadlock.  The critical path is
+ * (cells per row + 2 x rows) cell steps instead of the (CTUs per row + 2 x CTU rows) x 16 of a CTU wavefront: 510 vs 2048 steps at 4K.
+ * (The CTU wavefront kernel this replaces spent 28 % of its issue slots polling for the left / upper CTU.) */
 __global__ void __launch_bounds__(KS_INTRA_WARPS * KS_WARP)
-ks_recon_intra_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells, int *sync_ws, const KsIntraModes *__restrict__ modes)
+ks_recon_intra_rows_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells, int *sync_ws, const int *__restrict__ n_intra,
+                           const KsIntraModes *__restrict__ modes)
 {
     __shared__ __align__(16) KsIntraSmem sm;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int W = pp.W, H = pp.H, CW = W >> 1;
-    int *ticket = sync_ws, *progress = sync_ws + 1;              /* progress[cty * ctw + ctx] = blocks done (0..16) */
+    const bool masked = n_intra != nullptr;
+    if (masked && *n_intra == 0) return;
+    const int W = pp.W, H = pp.H, cw = pp.cw;
+    int *ticket = sync_ws, *done = sync_ws + 1;                  /* done[cell] = 1 once an intra cell's reconstruction is in HBM */
     ks_load_scans(sm.scan, tid, blockDim.x);
     ks_intra_load_small_scans(sm, tid);
     if (tid == 0) sm.ticket = atomicAdd(ticket, 1);
     __syncthreads();
-    const int cty = sm.ticket >> 1, par = sm.ticket & 1;
-    if (cty >= pp.cth) return;
-    for (int ctx = par; ctx < pp.ctw; ctx += 2) {
-        for (int z = 0; z < 16; z++) {
-            const int cx = (z & 1) | ((z >> 1) & 2), cy = ((z >> 1) & 1) | ((z >> 2) & 2);
-            const int x0 = (ctx << 6) + (cx << 4), y0 = (cty << 6) + (cy << 4);
-            const bool inside = x0 < W && y0 < H;
-            /* 0. wait for the blocks this one reads (see the kernel comment); skipped (outside) blocks still publish progress */
-            if (tid == 0 && inside) {
-                const int need_left = z == 0 ? 8 : (z == 2 ? 14 : ((z == 8 || z == 10) ? 16 : 0));
-                const int need_up = (cy == 0) ? 16 : 0, need_ur = (z == 5) ? 11 : 0;
-                if (need_left && ctx > 0) while (atomicAdd(&progress[cty * pp.ctw + ctx - 1], 0) < need_left) __nanosleep(100);
-                if (need_up && cty > 0) while (atomicAdd(&progress[(cty - 1) * pp.ctw + ctx], 0) < need_up) __nanosleep(100);
-                if (need_ur && cty > 0 && ctx + 1 < pp.ctw) while (atomicAdd(&progress[(cty - 1) * pp.ctw + ctx + 1], 0) < need_ur) __nanosleep(100);
+    const int gy = sm.ticket;
+    if (gy >= pp.ch) return;
+    const int y0 = gy << 4;
+    __shared__ uint8_t rowflag[512];                             /* this row's intra flags (cw <= 512 covers 8K) */
+    for (int i = tid; i < cw; i += KS_INTRA_WARPS * KS_WARP) rowflag[i] = masked ? (cells[gy * cw + i].flags & KS_F_INTRA) : 1;
+    __syncthreads();
+#pragma unroll 1
+    for (int gx = 0; gx < cw; gx++) {
+        if (!rowflag[gx]) continue;
+        const int x0 = gx << 4;
+        if (tid < 4) {
+            const int ox[4] = {-1, 0, 1, -1}, oy[4] = {-1, -1, -1, 1};
+            const int nx = gx + ox[tid], ny = gy + oy[tid];
+            if (ks_avail(W, H, pp.ctw, x0, y0, nx << 4, ny << 4) && (!masked || (cells[ny * cw + nx].flags & KS_F_INTRA))) {
+                while (atomicAdd(&done[ny * cw + nx], 0) == 0) __nanosleep(64);
                 __threadfence();
             }
-            __syncthreads();
-            if (inside) ks_intra_code_cell(sm, pp, src, rec, lv, cells, modes, x0, y0, 1, tid, warp, lane);
-            if (tid == 0) { __threadfence(); atomicExch(&progress[cty * pp.ctw + ctx], z + 1); }
         }
+        __syncthreads();
+        ks_intra_code_cell(sm, pp, src, rec, lv, cells, modes, x0, y0, masked ? 0 : 1, tid, warp, lane);
+        if (tid == 0) { __threadfence(); atomicExch(&done[gy * cw + gx], 1); }
     }
 }
 
-/* P pictures: the (few) cells the CU decision flagged intra, after the inter reconstruction of everything else.  Persistent CTAs take CTUs in
- * raster order (ticket counter) and code their flagged cells in z-order; a cell waits only for the flagged cells it really reads -- left,
- * above-left, above, above-right, below-left neighbours that precede it in coding order -- through per-cell done flags in HBM.  A CTA only ever
- * waits on cells of CTUs with smaller tickets (or its own earlier cells), which are running or finished: no deadlock.  CTUs without flagged
- * cells cost one 16-cell read.  (The wavefront kernel above took 0.3 ms per P picture in this role: it walks every CTU row serially.) */
-__global__ void __launch_bounds__(KS_INTRA_WARPS * KS_WARP)
-ks_recon_intra_sparse_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells, int *sync_ws, const int *__restrict__ n_intra,
-                             const KsIntraModes *__restrict__ modes)
-{
-    __shared__ __align__(16) KsIntraSmem sm;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (*n_intra == 0) return;
-    const int W = pp.W, H = pp.H, nctu = pp.ctw * pp.cth;
-    int *ticket = sync_ws, *done = sync_ws + 1;                  /* done[cell] = 1 once an intra cell's reconstruction is in HBM */
-    ks_load_scans(sm.scan, tid, blockDim.x);
-    ks_intra_load_small_scans(sm, tid);
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) sm.ticket = atomicAdd(ticket, 1);
-        __syncthreads();
-        const int ctu = sm.ticket;
-        if (ctu >= nctu) return;
-        const int ctx = ctu % pp.ctw, cty = ctu / pp.ctw;
-        bool f = false;
-        if (tid < 16) {
-            const int cx = (tid & 1) | ((tid >> 1) & 2), cy = ((tid >> 1) & 1) | ((tid >> 2) & 2), x = (ctx << 6) + (cx << 4), y = (cty << 6) + (cy << 4);
-            f = x < W && y < H && (cells[(y >> 4) * pp.cw + (x >> 4)].flags & KS_F_INTRA);
-        }
-        const unsigned b = __ballot_sync(0xffffffffu, f);
-        if (tid == 0) sm.todo = b & 0xffffu;
-        __syncthreads();
-        const unsigned todo = sm.todo;
-        for (int z = 0; z < 16; z++) {
-            if (!((todo >> z) & 1u)) continue;
-            const int cx = (z & 1) | ((z >> 1) & 2), cy = ((z >> 1) & 1) | ((z >> 2) & 2);
-            const int x0 = (ctx << 6) + (cx << 4), y0 = (cty << 6) + (cy << 4), gx = x0 >> 4, gy = y0 >> 4;
-            if (tid < 5) {
-                const int ox[5] = {-1, -1, 0, 1, -1}, oy[5] = {0, -1, -1, -1, 1};
-                const int nx = gx + ox[tid], ny = gy + oy[tid];
-                if (ks_avail(W, H, pp.ctw, x0, y0, nx << 4, ny << 4) && (cells[ny * pp.cw + nx].flags & KS_F_INTRA)) {
-                    while (atomicAdd(&done[ny * pp.cw + nx], 0) == 0) __nanosleep(100);
-                    __threadfence();
-                }
-            }
-            __syncthreads();
-            ks_intra_code_cell(sm, pp, src, rec, lv, cells, modes, x0, y0, 0, tid, warp, lane);
-            __syncthreads();
-            if (tid == 0) { __threadfence(); atomicExch(&done[gy * pp.cw + gx], 1); }
-        }
-    }
-}
-
-/* n_intra == NULL: I picture (every cell, wavefront kernel); else P picture: only the cells flagged KS_F_INTRA, inter-slice rounding */
 void ks_launch_recon_intra(const KsPicParams &pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *cells, int *sync_ws, const int *n_intra, void *modes_ws, cudaStream_t st)
 {
     KsIntraModes *modes = reinterpret_cast<KsIntraModes *>(modes_ws);
     /* the mode search of every (flagged) cell, independent of the reconstruction; then the dependent prediction + residual pass */
     ks_intra_modes_kernel<<<pp.cw * pp.ch, KS_MODES_WARPS * KS_WARP, 0, st>>>(pp, src.p[0], cells, n_intra, modes);
-    if (n_intra) {
-        cudaMemsetAsync(sync_ws, 0, sizeof(int) * (size_t)(1 + pp.cw * pp.ch), st);
-        ks_recon_intra_sparse_kernel<<<4 * 148, KS_INTRA_WARPS * KS_WARP, 0, st>>>(pp, src, rec, lv, cells, sync_ws, n_intra, modes);
-        return;
-    }
-    cudaMemsetAsync(sync_ws, 0, sizeof(int) * (size_t)(1 + pp.ctw * pp.cth), st);
-    ks_recon_intra_kernel<<<2 * pp.cth, KS_INTRA_WARPS * KS_WARP, 0, st>>>(pp, src, rec, lv, cells, sync_ws, modes);
+    cudaMemsetAsync(sync_ws, 0, sizeof(int) * (size_t)(1 + pp.cw * pp.ch), st);
+    ks_recon_intra_rows_kernel<<<pp.ch, KS_INTRA_WARPS * KS_WARP, 0, st>>>(pp, src, rec, lv, cells, sync_ws, n_intra, modes);
 }
 size_t ks_intra_workspace_bytes(int ncell) { return (size_t)ncell * sizeof(KsIntraModes); }
