@@ -31,42 +31,54 @@ template <int N> struct KsLog2 { static const int v = N == 32 ? 5 : (N == 16 ? 4
 /* per-block statistics of ks_tb_code (the intra 16x16 vs 8x8 decision): SSE(src, rec) and the estimated level bits as coded */
 struct KsTbStat { int d1, bits; };
 
+#ifdef KS_INTRA_TIMING
+__device__ long long g_tbt[8];
+#define KS_TBT(k) do { if (N == 16 && lane == 0) { long long t_ = clock64(); atomicAdd((unsigned long long *)&g_tbt[k], (unsigned long long)(t_ - tb_t0)); tb_t0 = t_; } } while (0)
+#else
+#define KS_TBT(k) do {} while (0)
+#endif
 /* transform passes: generated partial butterflies with immediate coefficients (tools/gen_dct.py) */
 #include "ks_dct_gen.cuh"
 
 /* sign-data hiding for one coefficient group (16 scan positions starting at scan index sp) of a TB whose
- * coefficient/level/deltaU arrays are N x N row-major.  Mirrors ora_sign_hide's per-CG body.  Deliberately NOT
- * unrolled / not inlined: it runs for few groups and the kernel's instruction footprint matters more. */
+ * coefficient/level/deltaU arrays are N x N row-major.  Mirrors ora_sign_hide's per-CG body.  The group's 16 positions, levels and deltas
+ * are gathered into registers with independent (pipelined) shared loads and the decision runs on bit masks: the dependent pass of the intra
+ * kernel waits on this code, so its latency -- not its instruction count -- is what matters.  One copy per kernel (not inlined). */
 __device__ __noinline__ void ks_sbh_cg(const int16_t *C, int16_t *L, const int16_t *D, const uint16_t *scan, int sp, bool is_last_cg, int n)
 {
-#define KS_POS(i) (((int)scan[sp + (i)] >> 8) * n + ((int)scan[sp + (i)] & 255))
-    int first = 16, last = -1, sum = 0, lf = 0;
-#pragma unroll 1
-    for (int i = 0; i < 16; i++) { int l = L[KS_POS(i)]; if (l) { if (first == 16) { first = i; lf = l; } last = i; } }
-    if (last - first < 4) return;
-#pragma unroll 1
-    for (int i = first; i <= last; i++) sum += L[KS_POS(i)];
-    const int signbit = lf > 0 ? 0 : 1;
-    if (signbit == (sum & 1)) return;
-    int min_cost = 0x7fffffff, min_pos = -1, final_change = 0;
-#pragma unroll 1
-    for (int i = is_last_cg ? last : 15; i >= 0; i--) {
-        int p = KS_POS(i), lv = L[p], du = D[p], cost, change = 0;
-        if (lv != 0) {
-            if (du > 0) { cost = -du; change = 1; }
-            else if (i == first && abs(lv) == 1) cost = 0x7fffffff;
-            else { cost = du; change = -1; }
-        } else if (i < first) {
-            int this_sign = C[p] >= 0 ? 0 : 1;
-            if (this_sign != signbit) cost = 0x7fffffff;
-            else { cost = -du; change = 1; }
-        } else { cost = -du; change = 1; }
-        if (cost < min_cost) { min_cost = cost; final_change = change; min_pos = p; }
+    int pos[16], lv[16];
+    unsigned nzm = 0, negm = 0, onem = 0, par = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) { const int s = scan[sp + i]; pos[i] = (s >> 8) * n + (s & 255); }
+#pragma unroll
+    for (int i = 0; i < 16; i++) lv[i] = L[pos[i]];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        nzm |= (unsigned)(lv[i] != 0) << i; negm |= (unsigned)(lv[i] < 0) << i; onem |= (unsigned)(lv[i] == 1 || lv[i] == -1) << i; par ^= (unsigned)lv[i];
     }
-#undef KS_POS
-    int lv = L[min_pos];
-    if (lv == 32767 || lv == -32768) final_change = -1;
-    L[min_pos] = (int16_t)(C[min_pos] >= 0 ? lv + final_change : lv - final_change);
+    if (!nzm) return;
+    const int first = __ffs(nzm) - 1, last = 31 - __clz(nzm);
+    if (last - first < 4) return;
+    const unsigned signbit = (negm >> first) & 1u;
+    if (signbit == (par & 1u)) return;                     /* parity of the sum == parity of the number of odd levels */
+    const int start = is_last_cg ? last : 15;
+    int min_cost = 0x7fffffff, min_pos = 0, min_lv = 0, final_change = 0; bool min_neg = false;
+#pragma unroll
+    for (int i = 15; i >= 0; i--) {
+        const int du = D[pos[i]];
+        const bool nz = (nzm >> i) & 1u;
+        /* the coefficient's sign: the level's when it has one, the coefficient's own otherwise (only read below the first level) */
+        bool neg = (negm >> i) & 1u;
+        if (!nz && i < first) neg = C[pos[i]] < 0;
+        int cost = -du, change = 1;
+        if (nz) {
+            if (du <= 0) { change = -1; cost = (i == first && ((onem >> i) & 1u)) ? 0x7fffffff : du; }
+        } else if (i < first && (unsigned)neg != signbit) cost = 0x7fffffff;
+        if (i <= start && cost < min_cost) { min_cost = cost; final_change = change; min_pos = pos[i]; min_lv = lv[i]; min_neg = neg; }
+    }
+    if (min_lv == 32767 || min_lv == -32768) final_change = -1;
+    if (!min_lv) min_neg = C[min_pos] < 0;
+    L[min_pos] = (int16_t)(min_neg ? min_lv - final_change : min_lv + final_change);
 }
 
 /*
@@ -93,6 +105,9 @@ __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, c
     int16_t *S = sc->S + g * N * SP, *C = sc->C + g * N * N, *L = sc->L + g * N * N, *D = sc->D + g * N * N;
     int res[N];
     uint8_t pred[N];
+#ifdef KS_INTRA_TIMING
+    long long tb_t0 = clock64();
+#endif
     /* a. residual row */
 #pragma unroll
     for (int x = 0; x < N; x += 4) {
@@ -104,6 +119,7 @@ __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, c
     /* b. forward pass 1 (rows), stage shift 2*log2N-2; results stored transposed: S[u][r] */
     ks_fwd_pass<N>(res, 2 * LOG2 - 2, t0, [&](int u, int v) { S[u * SP + r] = (int16_t)v; });
     __syncwarp();
+    KS_TBT(0);
     /* c. forward pass 2 (columns): lane = horizontal frequency u = r; d. quantise each coefficient (v, u=r) as it appears */
     if constexpr (N == 4) {
         const uint2 q = *reinterpret_cast<const uint2 *>(&S[r * SP]);
@@ -129,6 +145,7 @@ __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, c
     });
     unsigned nzb = __ballot_sync(0xffffffffu, nz && valid);
     bool cbf = (nzb & gmask) != 0;
+    KS_TBT(1);
     /* e. sign-data hiding, one coefficient group per lane (uniform ballots first, then the per-CG pass) */
     if (sign_hiding && nzb) {
         constexpr int NCG = (N / 4) * (N / 4);
@@ -140,7 +157,7 @@ __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, c
             bool cgnz = false;
             if (id < G * NCG) {
                 const int16_t *Lt = sc->L + tb * N * N;
-#pragma unroll 4
+#pragma unroll
                 for (int i = 0; i < 16; i++) { int s = scan[cg * 16 + i]; cgnz |= Lt[(s >> 8) * N + (s & 255)] != 0; }
             }
             ball[rep] = __ballot_sync(0xffffffffu, cgnz);
@@ -160,6 +177,7 @@ __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, c
         }
     }
     __syncwarp();
+    KS_TBT(2);
     /* g. reconstruction */
     if (nzb) {
         const int shift = LOG2 - 1, dq = c_inv_quant_scales[qp % 6] << (qp / 6), rnd = 1 << (shift - 1);
@@ -175,6 +193,7 @@ __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, c
 #pragma unroll
         for (int x = 0; x < N; x++) pred[x] = (uint8_t)ks_clip8((int)pred[x] + t[x]);
     }
+    KS_TBT(3);
     /* h. RD zero-out and/or per-block statistics: sums over the N lanes of the group (xor butterflies stay inside the aligned group) */
     if ((rdz_lambda_q4 && nzb) || stat_out) {
         int nnz = 0, slog = 0, maxd = 0, d0 = 0, d1 = 0; unsigned cgm = 0;
@@ -193,11 +212,10 @@ __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, c
         }
         cgm |= __shfl_xor_sync(0xffffffffu, cgm, 1); cgm |= __shfl_xor_sync(0xffffffffu, cgm, 2);
         int ncg = (r & 3) == 0 ? __popc(cgm) : 0;
-#pragma unroll
-        for (int o = 1; o < N; o <<= 1) {
-            nnz += __shfl_xor_sync(0xffffffffu, nnz, o); slog += __shfl_xor_sync(0xffffffffu, slog, o); ncg += __shfl_xor_sync(0xffffffffu, ncg, o);
-            d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
-        }
+        /* nnz <= 1024, slog <= 15 * 1024, ncg <= 64: one packed sum; redux.sync over the group's lanes */
+        const unsigned pk = __reduce_add_sync(gmask, (unsigned)nnz | ((unsigned)slog << 11) | ((unsigned)ncg << 25));
+        nnz = (int)(pk & 2047u); slog = (int)((pk >> 11) & 16383u); ncg = (int)(pk >> 25);
+        d0 = (int)__reduce_add_sync(gmask, (unsigned)d0); d1 = (int)__reduce_add_sync(gmask, (unsigned)d1); maxd = (int)__reduce_max_sync(gmask, (unsigned)maxd);
         int bits = nnz ? 3 * nnz + 2 * slog + 4 * ncg + maxd : 0;
         if (rdz_lambda_q4 && nnz && (long long)d0 * 16 <= (long long)d1 * 16 + (long long)rdz_lambda_q4 * bits) {
             cbf = false; d1 = d0; bits = 0;
@@ -211,6 +229,7 @@ __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, c
         }
         if (stat_out && r == 0 && valid) { stat_out[g].d1 = d1; stat_out[g].bits = bits; }
     }
+    KS_TBT(4);
     /* f. store the level row (dense plane) and the reconstruction */
     if (valid) {
         if constexpr (N == 4) *reinterpret_cast<uint2 *>(lev_row) = *reinterpret_cast<const uint2 *>(&L[r * N]);
@@ -223,6 +242,7 @@ __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, c
             *reinterpret_cast<uint32_t *>(rec_row + x) = (uint32_t)pred[x] | ((uint32_t)pred[x + 1] << 8) | ((uint32_t)pred[x + 2] << 16) | ((uint32_t)pred[x + 3] << 24);
     }
     __syncwarp();
+    KS_TBT(5);
     return cbf;
 }
 
@@ -406,6 +426,7 @@ struct KsIntraSmem {
     long long j16, j8;
     int      cbf16, cbf8[3];
     KsIntraModes modes;
+    long long t0, acc[8];
 };
 /* working set of the mode search (one cell per CTA) */
 struct KsModesSmem {
@@ -558,6 +579,13 @@ ks_intra_modes_kernel(KsPicParams pp, const uint8_t *__restrict__ srcY, const ks
 /* one intra CU of 16x16 (LG = 4) or 8x8 (LG = 3) with a GIVEN luma mode, by a CTA of KS_INTRA_WARPS warps: reference samples (reconstruction,
  * with availability), prediction, luma + chroma (DM) residual coding with the mode-dependent scans.  Results in shared memory: cbf,
  * stat_y[0] / stat_c[0..1].  Ends with a CTA barrier.  Mirror of ora intra_block after its decision. */
+#ifdef KS_INTRA_TIMING
+#include <cstdio>
+__device__ long long g_it[8];
+#define KS_T(k) do { if (tid == 0) { long long t_ = clock64(); sm.acc[k] += t_ - sm.t0; sm.t0 = t_; } } while (0)
+#else
+#define KS_T(k) do {} while (0)
+#endif
 template <int LG>
 __device__ __forceinline__ void ks_intra_code_block(KsIntraSmem &sm, const KsPicParams &pp, const KsPlanes &src, const KsPlanes &rec, const KsLevels &lv,
                                                     int x0, int y0, int mode, int intra_slice, int tid, int warp, int lane)
@@ -578,6 +606,7 @@ __device__ __forceinline__ void ks_intra_code_block(KsIntraSmem &sm, const KsPic
     }
     if (tid == 0) sm.cbf = 0;
     __syncthreads();
+    KS_T(1);
     if (warp < 3) {
         ks_intra_substitute(sm.raw[warp], sm.av[warp], sm.nb[warp], warp ? TC : TL, warp ? NC : N, &sm.dc[warp], lane);
         if (warp == 0)
@@ -585,6 +614,7 @@ __device__ __forceinline__ void ks_intra_code_block(KsIntraSmem &sm, const KsPic
                 sm.fb[i] = (i == 0 || i == 4 * N) ? sm.nb[0][i] : (uint8_t)((sm.nb[0][i - 1] + 2 * sm.nb[0][i] + sm.nb[0][i + 1] + 2) >> 2);
     }
     __syncthreads();
+    KS_T(2);
     const int scan_idx = (mode >= 22 && mode <= 30) ? 1 : ((mode >= 6 && mode <= 14) ? 2 : 0);
     /* 2. prediction blocks: N*N luma samples, then 2 x NC*NC chroma */
     {
@@ -599,6 +629,7 @@ __device__ __forceinline__ void ks_intra_code_block(KsIntraSmem &sm, const KsPic
         }
     }
     __syncthreads();
+    KS_T(3);
     /* 3. residual coding: warp 0 luma (lanes 0..N-1), warp 1 Cb + Cr (lanes 0..2*NC-1) */
     if (warp == 0) {
         int g = lane / N, r = lane % N, y = y0 + r;
@@ -614,6 +645,7 @@ __device__ __forceinline__ void ks_intra_code_block(KsIntraSmem &sm, const KsPic
         if (r == 0 && g < 2 && cbf) atomicOr(&sm.cbf, ci ? KS_F_CBF_CR : KS_F_CBF_CB);
     }
     __syncthreads();
+    KS_T(4);
 }
 
 /* one 16x16 intra cell by a CTA: a 16x16 CU, or four 8x8 CUs coded in z-order when that is cheaper in J = 16 * SSE + lambda * bits (both
@@ -681,6 +713,10 @@ __device__ __forceinline__ void ks_intra_code_cell(KsIntraSmem &sm, const KsPicP
     __syncthreads();          /* the caller publishes the cell as finished right after this function */
 }
 
+/* flag hand-off between CTAs: release store / acquire load at gpu scope (polling with atomics + __nanosleep cost ~9 us per hand-off) */
+__device__ __forceinline__ int ks_ld_acquire(const int *p) { int v; asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ void ks_st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory"); }
+
 /* The dependent pass of the intra CUs (I pictures: every cell; P pictures: the cells the CU decision flagged KS_F_INTRA, after the inter
  * reconstruction of everything else).  Which neighbours a block may read is fixed by the normative z-scan order, but the order in which blocks
  * are PROCESSED is free as long as those neighbours are finished.  So: one CTA per 16-sample cell row (rows handed out by a ticket counter,
@@ -707,6 +743,10 @@ ks_recon_intra_rows_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels 
     const int gy = sm.ticket;
     if (gy >= pp.ch) return;
     const int y0 = gy << 4;
+#ifdef KS_INTRA_TIMING
+    unsigned long long sm_row_start = 0;
+    if (tid == 0) { for (int k = 0; k < 8; k++) sm.acc[k] = 0; sm.t0 = clock64(); asm volatile("mov.u64 %0, %globaltimer;" : "=l"(sm_row_start)); }
+#endif
     __shared__ uint8_t rowflag[512];                             /* this row's intra flags (cw <= 512 covers 8K) */
     for (int i = tid; i < cw; i += KS_INTRA_WARPS * KS_WARP) rowflag[i] = masked ? (cells[gy * cw + i].flags & KS_F_INTRA) : 1;
     __syncthreads();
@@ -718,14 +758,36 @@ ks_recon_intra_rows_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels 
             const int ox[4] = {-1, 0, 1, -1}, oy[4] = {-1, -1, -1, 1};
             const int nx = gx + ox[tid], ny = gy + oy[tid];
             if (ks_avail(W, H, pp.ctw, x0, y0, nx << 4, ny << 4) && (!masked || (cells[ny * cw + nx].flags & KS_F_INTRA))) {
-                while (atomicAdd(&done[ny * cw + nx], 0) == 0) __nanosleep(64);
-                __threadfence();
+#ifdef KS_INTRA_TIMING
+                int polls = 0, v;
+                while ((v = ks_ld_acquire(&done[ny * cw + nx])) == 0) polls++;
+                if (polls) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); atomicAdd((unsigned long long *)&g_it[7], (unsigned long long)((unsigned)gt - (unsigned)v)); atomicAdd((unsigned long long *)&g_it[6], 1ull); }
+#else
+                while (ks_ld_acquire(&done[ny * cw + nx]) == 0) { }
+#endif
             }
         }
         __syncthreads();
+        KS_T(0);
+#ifdef KS_INTRA_TIMING
+        unsigned long long t_dep = 0; if (tid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_dep));
+#endif
         ks_intra_code_cell(sm, pp, src, rec, lv, cells, modes, x0, y0, masked ? 0 : 1, tid, warp, lane);
-        if (tid == 0) { __threadfence(); atomicExch(&done[gy * cw + gx], 1); }
+        KS_T(5);
+#ifdef KS_INTRA_TIMING
+        if (0 && tid == 0 && !masked && gy < 4 && gx < 10) { unsigned long long t_end; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end)); printf("cell (%d,%d) deps-ok at %6llu ns, coded at %6llu ns (try8 %d)\n", gx, gy, t_dep - sm_row_start, t_end - sm_row_start, sm.try8); }
+#endif
+#ifdef KS_INTRA_TIMING
+        if (tid == 0) { __threadfence(); unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); ks_st_release(&done[gy * cw + gx], (int)((unsigned)gt | 1u)); }
+#else
+        if (tid == 0) { __threadfence(); ks_st_release(&done[gy * cw + gx], 1); }
+#endif
     }
+#ifdef KS_INTRA_TIMING
+    if (tid == 0 && !masked && (gy % 8 == 0 || gy == pp.ch - 1)) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); printf("row %3d blk %3d sm-clock end %lld globaltimer end %llu first-cell-start %llu\n", gy, blockIdx.x, clock64(), gt, sm_row_start); }
+    if (tid == 0 && (gy == 5 || gy == 64) && !masked) printf("intra timing row %d (cycles):", gy), printf(" wait %lld fetch %lld subst %lld pred %lld tb %lld cellrest %lld | waits that really polled: %lld, mean ns from publish to seen: %lld\n", sm.acc[0], sm.acc[1], sm.acc[2], sm.acc[3], sm.acc[4], sm.acc[5], g_it[6], g_it[6] ? g_it[7] / g_it[6] : 0),
+        printf("tb<16> cumulative cycles: fwd1 %lld fwd2q %lld sbh %lld inv %lld stat %lld store %lld\n", g_tbt[0], g_tbt[1], g_tbt[2], g_tbt[3], g_tbt[4], g_tbt[5]);
+#endif
 }
 
 void ks_launch_recon_intra(const KsPicParams &pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *cells, int *sync_ws, const int *n_intra, void *modes_ws, cudaStream_t st)
