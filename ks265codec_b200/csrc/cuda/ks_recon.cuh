@@ -67,9 +67,8 @@ __device__ __noinline__ void ks_sbh_cg(const int16_t *C, int16_t *L, const int16
     for (int i = 15; i >= 0; i--) {
         const int du = D[pos[i]];
         const bool nz = (nzm >> i) & 1u;
-        /* the coefficient's sign: the level's when it has one, the coefficient's own otherwise (only read below the first level) */
-        bool neg = (negm >> i) & 1u;
-        if (!nz && i < first) neg = C[pos[i]] < 0;
+        /* the coefficient's sign: the level's when it has one, the coefficient's own otherwise */
+        const bool neg = nz ? ((negm >> i) & 1u) != 0 : C[pos[i]] < 0;
         int cost = -du, change = 1;
         if (nz) {
             if (du <= 0) { change = -1; cost = (i == first && ((onem >> i) & 1u)) ? 0x7fffffff : du; }
@@ -77,13 +76,12 @@ __device__ __noinline__ void ks_sbh_cg(const int16_t *C, int16_t *L, const int16
         if (i <= start && cost < min_cost) { min_cost = cost; final_change = change; min_pos = pos[i]; min_lv = lv[i]; min_neg = neg; }
     }
     if (min_lv == 32767 || min_lv == -32768) final_change = -1;
-    if (!min_lv) min_neg = C[min_pos] < 0;
     L[min_pos] = (int16_t)(min_neg ? min_lv - final_change : min_lv + final_change);
 }
 
 /*
  * One warp, G = 32/N transform blocks: lane -> (g = lane / N, r = lane % N).
- *   src_row : global pointer to row r of the lane's source block      (N bytes, valid lanes only)
+ *   src_row : pointer (global or shared) to row r of the lane's source block (N bytes, 4-byte aligned, valid lanes only)
  *   pred_row: shared  pointer to row r of the lane's prediction block (N bytes)
  *   rec_row : global pointer to row r of the lane's reconstruction
  *   lev_row : global pointer to row r of the lane's level block (dense int16 plane)
@@ -95,7 +93,7 @@ __device__ __noinline__ void ks_sbh_cg(const int16_t *C, int16_t *L, const int16
  */
 template <int N>
 __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, const int *t0, bool valid,
-                                        const uint8_t *__restrict__ src_row, const uint8_t *pred_row,
+                                        const uint8_t *src_row, const uint8_t *pred_row,
                                         uint8_t *__restrict__ rec_row, int16_t *__restrict__ lev_row,
                                         int qp, int intra_slice, int sign_hiding, int lane, int rdz_lambda_q4 = 0, KsTbStat *stat_out = nullptr)
 {
@@ -105,14 +103,16 @@ __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, c
     int16_t *S = sc->S + g * N * SP, *C = sc->C + g * N * N, *L = sc->L + g * N * N, *D = sc->D + g * N * N;
     int res[N];
     uint8_t pred[N];
+    uint32_t srcw[N / 4];
 #ifdef KS_INTRA_TIMING
     long long tb_t0 = clock64();
 #endif
-    /* a. residual row */
+    /* a. residual row (the source row stays in registers for the statistics of step h) */
 #pragma unroll
     for (int x = 0; x < N; x += 4) {
         uint32_t p4 = *reinterpret_cast<const uint32_t *>(pred_row + x);
-        uint32_t s4 = valid ? __ldg(reinterpret_cast<const uint32_t *>(src_row + x)) : p4;
+        uint32_t s4 = valid ? *reinterpret_cast<const uint32_t *>(src_row + x) : p4;
+        srcw[x >> 2] = s4;
 #pragma unroll
         for (int b = 0; b < 4; b++) { pred[x + b] = (uint8_t)(p4 >> (8 * b)); res[x + b] = (int)((s4 >> (8 * b)) & 255) - (int)pred[x + b]; }
     }
@@ -201,7 +201,7 @@ __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, c
         for (int x = 0; x < N; x += 4) {
             const uint2 l4 = *reinterpret_cast<const uint2 *>(&L[r * N + x]);
             const uint32_t p4 = *reinterpret_cast<const uint32_t *>(pred_row + x);
-            const uint32_t s4 = valid ? __ldg(reinterpret_cast<const uint32_t *>(src_row + x)) : p4;
+            const uint32_t s4 = srcw[x >> 2];
 #pragma unroll
             for (int b = 0; b < 4; b++) {
                 const int l = (int)(short)(((b & 2) ? l4.y : l4.x) >> (16 * (b & 1))), a = abs(l);
@@ -212,10 +212,14 @@ __device__ __noinline__ bool ks_tb_code(KsTbScratch *sc, const uint16_t *scan, c
         }
         cgm |= __shfl_xor_sync(0xffffffffu, cgm, 1); cgm |= __shfl_xor_sync(0xffffffffu, cgm, 2);
         int ncg = (r & 3) == 0 ? __popc(cgm) : 0;
-        /* nnz <= 1024, slog <= 15 * 1024, ncg <= 64: one packed sum; redux.sync over the group's lanes */
-        const unsigned pk = __reduce_add_sync(gmask, (unsigned)nnz | ((unsigned)slog << 11) | ((unsigned)ncg << 25));
+        /* nnz <= 1024, slog <= 15 * 1024, ncg <= 64: one packed sum (redux.sync over sub-warp masks measured slower than the butterflies) */
+        unsigned pk = (unsigned)nnz | ((unsigned)slog << 11) | ((unsigned)ncg << 25);
+#pragma unroll
+        for (int o = 1; o < N; o <<= 1) {
+            pk += __shfl_xor_sync(0xffffffffu, pk, o); d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+            maxd = max(maxd, __shfl_xor_sync(0xffffffffu, maxd, o));
+        }
         nnz = (int)(pk & 2047u); slog = (int)((pk >> 11) & 16383u); ncg = (int)(pk >> 25);
-        d0 = (int)__reduce_add_sync(gmask, (unsigned)d0); d1 = (int)__reduce_add_sync(gmask, (unsigned)d1); maxd = (int)__reduce_max_sync(gmask, (unsigned)maxd);
         int bits = nnz ? 3 * nnz + 2 * slog + 4 * ncg + maxd : 0;
         if (rdz_lambda_q4 && nnz && (long long)d0 * 16 <= (long long)d1 * 16 + (long long)rdz_lambda_q4 * bits) {
             cbf = false; d1 = d0; bits = 0;
@@ -415,17 +419,18 @@ struct KsIntraSmem {
     uint8_t  av[3][72];
     uint8_t  predY[16 * 16];
     uint8_t  predC[2][8 * 8];
+    alignas(16) uint8_t srcY[16 * 16];  /* the cell's source block, prefetched while the previous cell is coded */
+    alignas(16) uint8_t srcC[2][8 * 8];
     int      dc[3];
     int      ticket;
     unsigned cbf;
-    unsigned todo;
     KsTbStat stat_y[4], stat_c[8];      /* ks_tb_code statistics of the block just coded: luma [0], Cb [0], Cr [1] */
     uint8_t  save_rec[256 + 64 + 64];   /* the 16x16 CU's result while the four 8x8 CUs are tried over it */
     int16_t  save_lev[256 + 64 + 64];
     int      try8, use8;
     long long j16, j8;
     int      cbf16, cbf8[3];
-    KsIntraModes modes;
+    alignas(8) KsIntraModes modes;
     long long t0, acc[8];
 };
 /* working set of the mode search (one cell per CTA) */
@@ -634,13 +639,13 @@ __device__ __forceinline__ void ks_intra_code_block(KsIntraSmem &sm, const KsPic
     if (warp == 0) {
         int g = lane / N, r = lane % N, y = y0 + r;
         const uint16_t *scan = LG == 4 ? sm.scan + 64 : (scan_idx == 0 ? sm.scan : sm.scan8hv[scan_idx - 1]);
-        bool cbf = ks_tb_code<N>(&sm.tb[0], scan, nullptr, g == 0, src.p[0] + (size_t)y * W + x0, &sm.predY[r * N],
+        bool cbf = ks_tb_code<N>(&sm.tb[0], scan, nullptr, g == 0, &sm.srcY[((y0 & 15) + r) * 16 + (x0 & 15)], &sm.predY[r * N],
                                  rec.p[0] + (size_t)y * W + x0, lv.p[0] + (size_t)y * W + x0, pp.qp, intra_slice, pp.sign_hiding, lane, 0, sm.stat_y);
         if (lane == 0 && cbf) atomicOr(&sm.cbf, KS_F_CBF_Y);
     } else if (warp == 1) {
         int g = lane / NC, r = lane % NC, ci = g & 1, x = x0 >> 1, y = (y0 >> 1) + r;
         const uint16_t *scan = LG == 4 ? sm.scan : sm.scan4[scan_idx];
-        bool cbf = ks_tb_code<NC>(&sm.tb[1], scan, nullptr, g < 2, src.p[1 + ci] + (size_t)y * CW + x, &sm.predC[ci][r * NC],
+        bool cbf = ks_tb_code<NC>(&sm.tb[1], scan, nullptr, g < 2, &sm.srcC[ci][((((y0 >> 1) & 7) + r) & 7) * 8 + ((x0 >> 1) & 7)], &sm.predC[ci][r * NC],
                                   rec.p[1 + ci] + (size_t)y * CW + x, lv.p[1 + ci] + (size_t)y * CW + x, pp.qpc, intra_slice, pp.sign_hiding, lane, 0, sm.stat_c);
         if (r == 0 && g < 2 && cbf) atomicOr(&sm.cbf, ci ? KS_F_CBF_CR : KS_F_CBF_CB);
     }
@@ -656,9 +661,7 @@ __device__ __forceinline__ void ks_intra_code_cell(KsIntraSmem &sm, const KsPicP
 {
     const int W = pp.W, NT = KS_INTRA_WARPS * KS_WARP;
     const long long lamq = pp.lambda_sse_q4;
-    if (tid == 0) sm.modes = modes[(y0 >> 4) * pp.cw + (x0 >> 4)];
-    __syncthreads();
-    const KsIntraModes md = sm.modes;
+    const KsIntraModes md = sm.modes;                /* staged, like the source block, by the caller */
     ks_intra_code_block<4>(sm, pp, src, rec, lv, x0, y0, md.m16, intra_slice, tid, warp, lane);
     if (tid == 0) {
         sm.cbf16 = (int)sm.cbf;
@@ -750,10 +753,25 @@ ks_recon_intra_rows_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels 
     __shared__ uint8_t rowflag[512];                             /* this row's intra flags (cw <= 512 covers 8K) */
     for (int i = tid; i < cw; i += KS_INTRA_WARPS * KS_WARP) rowflag[i] = masked ? (cells[gy * cw + i].flags & KS_F_INTRA) : 1;
     __syncthreads();
+    /* the source block and the modes of a cell do not depend on anything: every thread carries one word of the NEXT cell's
+     * (64 luma words, 2 x 16 chroma words, 2 words of modes) in a register while the current cell is coded */
+    auto next_cell = [&](int from) { while (from < cw && !rowflag[from]) from++; return from; };
+    auto prefetch = [&](int cx) -> uint32_t {
+        if (cx >= cw) return 0u;
+        if (tid < 64) return __ldg(reinterpret_cast<const uint32_t *>(src.p[0] + (size_t)(y0 + (tid >> 2)) * W + (cx << 4) + 4 * (tid & 3)));
+        if (tid < 96) { const int ci = (tid - 64) >> 4, k = (tid - 64) & 15; return __ldg(reinterpret_cast<const uint32_t *>(src.p[1 + ci] + (size_t)((y0 >> 1) + (k >> 1)) * (W >> 1) + (cx << 3) + 4 * (k & 1))); }
+        if (tid < 98) return __ldg(reinterpret_cast<const uint32_t *>(&modes[gy * cw + cx]) + (tid - 96));
+        return 0u;
+    };
+    int gx = next_cell(0);
+    uint32_t pre = prefetch(gx);
 #pragma unroll 1
-    for (int gx = 0; gx < cw; gx++) {
-        if (!rowflag[gx]) continue;
-        const int x0 = gx << 4;
+    while (gx < cw) {
+        const int x0 = gx << 4, gx_next = next_cell(gx + 1);
+        if (tid < 64) reinterpret_cast<uint32_t *>(sm.srcY)[tid] = pre;
+        else if (tid < 96) reinterpret_cast<uint32_t *>(&sm.srcC[0][0])[tid - 64] = pre;
+        else if (tid < 98) reinterpret_cast<uint32_t *>(&sm.modes)[tid - 96] = pre;
+        pre = prefetch(gx_next);
         if (tid < 4) {
             const int ox[4] = {-1, 0, 1, -1}, oy[4] = {-1, -1, -1, 1};
             const int nx = gx + ox[tid], ny = gy + oy[tid];
@@ -782,6 +800,7 @@ ks_recon_intra_rows_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels 
 #else
         if (tid == 0) { __threadfence(); ks_st_release(&done[gy * cw + gx], 1); }
 #endif
+        gx = gx_next;
     }
 #ifdef KS_INTRA_TIMING
     if (tid == 0 && !masked && (gy % 8 == 0 || gy == pp.ch - 1)) { unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); printf("row %3d blk %3d sm-clock end %lld globaltimer end %llu first-cell-start %llu\n", gy, blockIdx.x, clock64(), gt, sm_row_start); }
