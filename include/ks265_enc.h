@@ -62,6 +62,8 @@ void ks265_encoder_close(ks265_encoder *enc);
  * Returns bytes written or a negative error. */
 long ks265_encoder_encode_gop(ks265_encoder *enc, const uint8_t *frames, const void *frames_dev, int nframes,
                               uint8_t *bs, size_t bs_cap, uint8_t *recon, ks265_gop_stats *stats);
+/* VPS + SPS + PPS of the stream (Annex-B), the same bytes every GOP shard starts with (reference: QY265EncoderEncodeHeaders, qy265enc.h:202) */
+long ks265_encoder_headers(ks265_encoder *enc, uint8_t *out, size_t cap);
 /* the next encode_gop calls also fill `stats[0..cap)` with one record per coded picture (NULL / 0 turns it off) */
 void ks265_encoder_set_picture_stats(ks265_encoder *enc, ks265_pic_stat *stats, int cap);
 /* page-locked host memory for picture buffers: pictures handed to encode_gop from such a buffer are DMA-ed in place (no staging copy) */

@@ -67,7 +67,7 @@ GPU_SYMBOLS = ["ks_gpu_open", "ks_gpu_close", "ks_gpu_coded_size", "ks_gpu_uploa
                "ks_gpu_launch_count", "ks_gpu_stream", "ks_gpu_set_profiling", "ks_gpu_get_stage_times", "ks_gpu_d2h_bytes", "ks_gpu_abi_sizeof", "ks_gpu_abort", "ks_gpu_debug_fetch", "ks_gpu_debug_me", "ks_gpu_kat_sad16", "ks_gpu_kat_satd16",
                "ks_gpu_kat_interp_luma16", "ks_gpu_kat_tb"]
 ENC_SYMBOLS = ["ks265_config_default_preset", "ks265_preset_index", "ks265_encoder_open", "ks265_encoder_close",
-               "ks265_encoder_encode_gop", "ks265_encoder_run_gop_device", "ks265_encoder_set_picture_stats", "ks265_encoder_encode_gop_cb", "ks265_alloc_host", "ks265_free_host", "ks265_encoder_set_profiling", "ks265_encoder_get_stage_times"]
+               "ks265_encoder_encode_gop", "ks265_encoder_run_gop_device", "ks265_encoder_set_picture_stats", "ks265_encoder_encode_gop_cb", "ks265_alloc_host", "ks265_free_host", "ks265_encoder_set_profiling", "ks265_encoder_get_stage_times", "ks265_encoder_headers"]
 
 _lib = None
 

@@ -236,6 +236,15 @@ long ks265_encoder_run_gop_device(ks265_encoder *enc, const void *frames_dev, in
     return encode_gop_impl(enc, NULL, frames_dev, nframes, NULL, 0, NULL, stats);
 }
 
+long ks265_encoder_headers(ks265_encoder *enc, uint8_t *out, size_t cap)
+{
+    if (!enc || !out) return -22;
+    long pos = 0, n;
+    if ((n = ks_write_vps(&enc->sp, out + pos, cap - pos)) < 0) return -28; pos += n;
+    if ((n = ks_write_sps(&enc->sp, out + pos, cap - pos)) < 0) return -28; pos += n;
+    if ((n = ks_write_pps(&enc->sp, out + pos, cap - pos)) < 0) return -28; pos += n;
+    return pos;
+}
 void ks265_encoder_set_picture_stats(ks265_encoder *enc, ks265_pic_stat *stats, int cap) { if (enc) { enc->pic_stats = stats; enc->pic_stats_cap = stats ? cap : 0; } }
 
 int ks265_encoder_set_profiling(ks265_encoder *enc, int on) { return enc ? ks_gpu_set_profiling(enc->gpu, on) : -22; }
