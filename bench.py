@@ -115,6 +115,29 @@ def bind_to_gpu_numa(gpu_index, min_cpus):
     return 0, None
 
 
+def prefer_gpu_numa_memory(gpu_index):
+    """memory policy only (no CPU pinning): page-locked buffers allocated from now on come from the NUMA node the GPU hangs off, so the
+    H2D stream of each rank stays on its own socket's memory controller instead of crossing the inter-socket link (what `numactl --preferred`
+    does).  Returns the node or None."""
+    try:
+        import ctypes
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(gpu_index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus[-12:]).read())
+        if node < 0:
+            return None
+        mask = (ctypes.c_ulong * 16)()
+        mask[node // 64] = 1 << (node % 64)
+        libc = ctypes.CDLL(None, use_errno=True)
+        if libc.syscall(238, 1, mask, 16 * 64 + 1) != 0:          # set_mempolicy(MPOL_PREFERRED, mask, maxnode), x86-64 syscall 238
+            return None
+        return node
+    except Exception:
+        return None
+
+
 def run_cli(binary, c, frames, yuv_path, extra=()):
     """run an AppEncoder-compatible CLI (the reference binary or ours); returns dict(fps, wall, kbps, psnr_y) from its own summary lines"""
     out = "/dev/shm/ks265_cli_%d.265" % os.getpid()
@@ -223,11 +246,16 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     # shards in flight per GPU, measured on the 64-core/128-thread pool host at N=1 (value / e2e fps): 8 -> e2e host-bound, 16 -> 2625 / 2487,
     # 24 with sleeping waits -> 2614 / 2601 (with spinning waits 24 shards collapse to 2037 / 1813: the spinners starve the launch threads)
-    streams = a.streams or max(2, min(24 if W * H <= 3840 * 2160 else 12, cores // max(1, a.gpus)))
+    # shards in flight per GPU: the device saturates at ~12-16 (measured: 16 / 24 / 32 give the same fps at N=1) and a shard thread sleeps while its
+    # picture is on the device and needs ~1.3 ms of host time per 4K picture, so up to 4 threads per core are fine when GPUs outnumber cores / 16
+    cap = 24 if W * H <= 3840 * 2160 else 12
+    per_gpu = cores // max(1, a.gpus)
+    streams = a.streams or max(2, min(cap, max(per_gpu, min(16, 4 * per_gpu))))
     visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
     nvml_index = int(visible.split(",")[local_rank]) if visible and all(v.strip().isdigit() for v in visible.split(",")) else local_rank
     # opt-in: measured neutral on the 2-socket pool hosts (N=2: value 4403 bound vs 4414 unbound, e2e 3638 vs 3838), profiles/README.md
     numa_cpus, full_mask = bind_to_gpu_numa(nvml_index, 2 * streams) if os.environ.get("KS_NUMA_BIND") == "1" else (0, None)
+    numa_node = prefer_gpu_numa_memory(nvml_index) if os.environ.get("KS_NUMA_MEM", "1") == "1" else None
     # shard threads SLEEP while they wait for a picture (cudaEventBlockingSync).  Spinning waits are 2 % faster only for <= 16 shards of ONE
     # process; beyond that, and whenever several GPU processes share the host, the spinners slow everybody's launch threads
     # (N=2, 16 shards per GPU: 4414 / 3838 fps spinning vs 5226 / 4440 sleeping).
@@ -423,7 +451,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": workload_name(c) + " (%s)" % c["baseline"], "gop_shard": "1 IDR + %d P, closed GOP" % (IPER - 1),
-                       "streams_per_gpu": streams, "cpu_binding": ("%d CPUs local to the GPU (NVML affinity)" % numa_cpus) if numa_cpus else "none", "pictures_per_step": frames_per_step, "parallelism": "gop-shard x%d" % world,
+                       "streams_per_gpu": streams, "cpu_binding": ("%d CPUs local to the GPU (NVML affinity)" % numa_cpus) if numa_cpus else "none", "host_memory_node": numa_node, "pictures_per_step": frames_per_step, "parallelism": "gop-shard x%d" % world,
                        "l2": "inputs larger than L2: %d streams x %d distinct sequences of %.2f GB each per GPU (%s host buffers), read in place" % (streams, streams, IPER * FSZ / 1e9, "distinct pinned" if distinct_host else "one shared pinned"),
                        "value_scope": "device hot path (ME, CU/merge decision, MC+transform+quant, deblock, SAO, level pack, syntax D2H), pictures resident in HBM; host CABAC excluded",
                        "e2e_scope": "host I420 -> H2D -> device hot path -> syntax D2H -> host CABAC -> Annex-B (+NCCL NAL gather if N>1)",
