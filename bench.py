@@ -363,10 +363,9 @@ def main():
     d2h = sum(int(r[2].d2h_bytes) for r in results)
     bs_bytes = sum(int(r[2].bytes) for r in results)
     sse_y = sum(int(r[2].sse[0]) for r in results)
-    cW, cH = (W + 15) & ~15, (H + 15) & ~15
     quality = {"kbps": bs_bytes * 8.0 * FPS_NOMINAL / (streams * IPER) / 1000.0,
-               "psnr_y": 10.0 * math.log10(255.0 ** 2 * cW * cH * streams * IPER / max(1, sse_y)), "fps_nominal": FPS_NOMINAL,
-               "note": "this rank's %d shards of the e2e arm; bitrate at a nominal %g fps; PSNR from the device's SSE over the coded area" % (streams, FPS_NOMINAL)}
+               "psnr_y": 10.0 * math.log10(255.0 ** 2 * W * H * streams * IPER / max(1, sse_y)), "fps_nominal": FPS_NOMINAL,
+               "note": "this rank's %d shards of the e2e arm; bitrate at a nominal %g fps; PSNR from the device's SSE over the display area" % (streams, FPS_NOMINAL)}
 
     # ---- roofline of the dominant stage (SURVEY.md 8d per-kernel algorithmic bytes; S = 1.5*W*H per picture) ----
     S = 1.5 * W * H

@@ -36,7 +36,7 @@ typedef struct ks265_config {
 
 typedef struct ks265_gop_stats {
     int frames;
-    uint64_t sse[3];            /* summed over the shard (coded area) */
+    uint64_t sse[3];            /* summed over the shard (display area, like the reference's PSNR) */
     uint64_t bytes;
     uint64_t gpu_launches;
     uint64_t d2h_bytes;         /* syntax bytes copied device->host */

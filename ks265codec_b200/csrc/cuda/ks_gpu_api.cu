@@ -317,7 +317,7 @@ static int fill_params(const ks_gpu_ctx *c, const ks_pic_params *p, KsPicParams 
     if (p->slice_type == KS_SLICE_B && (p->ref1_slot < 0 || p->ref1_slot >= c->cfg.n_rec_slots || p->ref1_slot == p->out_slot || p->ref1_slot == p->ref_slot
                                          || p->dist_l0 <= 0 || p->dist_anchor <= p->dist_l0)) return KS_EINVAL;
     memset(pp, 0, sizeof(*pp));
-    pp->W = c->W; pp->H = c->H; pp->cw = c->cw; pp->ch = c->ch; pp->ctw = c->ctw; pp->cth = c->cth;
+    pp->W = c->W; pp->H = c->H; pp->dW = c->dw; pp->dH = c->dh; pp->cw = c->cw; pp->ch = c->ch; pp->ctw = c->ctw; pp->cth = c->cth;
     pp->slice_type = p->slice_type; pp->qp = p->qp; pp->qpc = k_chroma_qp[p->qp];
     pp->lambda_sad_q4 = k_lambda_sad_q4[p->qp]; pp->lambda_sse_q4 = k_lambda_sse_q4[p->qp];
     if (p->lambda_qp_delta < 0) return KS_EINVAL;

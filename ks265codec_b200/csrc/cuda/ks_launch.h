@@ -14,6 +14,7 @@ struct KsLevels { int16_t *p[3]; };
 /* per-picture launch parameters (passed by value to kernels) */
 struct KsPicParams {
     int W, H;               /* coded luma size */
+    int dW, dH;             /* display luma size (PSNR is taken over the display area, like the reference's) */
     int cw, ch;             /* 16x16 cells */
     int ctw, cth;           /* 64x64 CTUs */
     int slice_type, qp, qpc;

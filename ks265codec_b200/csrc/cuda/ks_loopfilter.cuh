@@ -422,6 +422,8 @@ ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_s
             const KsSaoNb n = ks_sao_load_nb(&(ci ? sm->tileC[ci - 1] : sm->tileY)[(y + 1) * pitch + KS_SAO_XOFF + x], pitch);
             const uint32_t s4 = __ldg(reinterpret_cast<const uint32_t *>(src.p[ci] + (size_t)(y0 + y) * PW + x0 + x));
             const bool top = y0 + y == 0, bot = y0 + y == PH - 1;
+            const bool in_disp_y = y0 + y < (pp.dH >> sh);
+            const int dispw = pp.dW >> sh;
             uint32_t o4 = 0;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -434,7 +436,7 @@ ks_sao_kernel(KsPicParams pp, KsPlanes src, KsPlanes deb, KsPlanes out, ks_ctu_s
                 v = ks_clip8(v);
                 o4 |= (uint32_t)v << (8 * j);
                 int e = (int)((s4 >> (8 * j)) & 255) - v;
-                sse += (unsigned)(e * e);
+                if (in_disp_y && x0 + x + j < dispw) sse += (unsigned)(e * e);
             }
             *reinterpret_cast<uint32_t *>(out.p[ci] + (size_t)(y0 + y) * PW + x0 + x) = o4;
         }

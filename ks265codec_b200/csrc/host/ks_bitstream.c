@@ -299,7 +299,8 @@ static void build_diag(uint8_t *dst, int n, int shift)
         if (i >= n * n) break;
     }
 }
-static void scans_init(void)
+/* built when the library is loaded (like the bin-coder tables): shard threads only ever read them */
+__attribute__((constructor)) static void scans_init(void)
 {
     if (g_scan_ready) return;
     build_diag(g_scan4, 4, 2);
