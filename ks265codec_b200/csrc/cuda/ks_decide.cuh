@@ -19,6 +19,7 @@
 
 #define KS_NCAND 16
 #define KS_INTRA_HDR_BITS 10
+#define KS_INTRA_FLOOR 64
 #define KS_DECIDE_WARPS 8            /* two cells per warp: 4 CTAs per SM instead of 2, so the serial stage D of one CTU idles 7 warps, not 15 */
 
 /* per-CTU result of stage E (global memory, 1.1 KB): the candidate list and every cell's distortion for every entry */
@@ -271,7 +272,8 @@ ks_decide_tree_kernel(KsPicParams pp, const ks_cell *__restrict__ mv0, const KsC
             const unsigned key = ks_decide_eval(sm, i, j, 1, lam, maxc, lane);
             /* intra 16x16 CU (about KS_INTRA_HDR_BITS of header) against the best vector */
             const int ji = sm->intra[j * 4 + i] + ((lam * KS_INTRA_HDR_BITS) >> 4);
-            if (ji < (int)(key >> 4)) {
+            /* ...and only above the quantisation-noise floor (see ora decide_block) */
+            if (ji < (int)(key >> 4) && sm->dist[j * 4 + i][key & 15u] > ((KS_INTRA_FLOOR * lam) >> 4)) {
                 if (lane == 0) { sm->smv[(j + 1) * 6 + i + 1] = 0u; sm->sok[(j + 1) * 6 + i + 1] = 0; sm->slog2[j * 4 + i] = 4; sm->sintra[j * 4 + i] = 1; }
                 __syncwarp();
                 j32 += ji;

@@ -640,13 +640,13 @@ __device__ __forceinline__ void ks_intra_code_block(KsIntraSmem &sm, const KsPic
         int g = lane / N, r = lane % N, y = y0 + r;
         const uint16_t *scan = LG == 4 ? sm.scan + 64 : (scan_idx == 0 ? sm.scan : sm.scan8hv[scan_idx - 1]);
         bool cbf = ks_tb_code<N>(&sm.tb[0], scan, nullptr, g == 0, &sm.srcY[((y0 & 15) + r) * 16 + (x0 & 15)], &sm.predY[r * N],
-                                 rec.p[0] + (size_t)y * W + x0, lv.p[0] + (size_t)y * W + x0, pp.qp, intra_slice, pp.sign_hiding, lane, 0, sm.stat_y);
+                                 rec.p[0] + (size_t)y * W + x0, lv.p[0] + (size_t)y * W + x0, pp.qp, intra_slice, pp.sign_hiding, lane, 0, intra_slice ? sm.stat_y : nullptr);
         if (lane == 0 && cbf) atomicOr(&sm.cbf, KS_F_CBF_Y);
     } else if (warp == 1) {
         int g = lane / NC, r = lane % NC, ci = g & 1, x = x0 >> 1, y = (y0 >> 1) + r;
         const uint16_t *scan = LG == 4 ? sm.scan : sm.scan4[scan_idx];
         bool cbf = ks_tb_code<NC>(&sm.tb[1], scan, nullptr, g < 2, &sm.srcC[ci][((((y0 >> 1) & 7) + r) & 7) * 8 + ((x0 >> 1) & 7)], &sm.predC[ci][r * NC],
-                                  rec.p[1 + ci] + (size_t)y * CW + x, lv.p[1 + ci] + (size_t)y * CW + x, pp.qpc, intra_slice, pp.sign_hiding, lane, 0, sm.stat_c);
+                                  rec.p[1 + ci] + (size_t)y * CW + x, lv.p[1 + ci] + (size_t)y * CW + x, pp.qpc, intra_slice, pp.sign_hiding, lane, 0, intra_slice ? sm.stat_c : nullptr);
         if (r == 0 && g < 2 && cbf) atomicOr(&sm.cbf, ci ? KS_F_CBF_CR : KS_F_CBF_CB);
     }
     __syncthreads();
@@ -663,11 +663,11 @@ __device__ __forceinline__ void ks_intra_code_cell(KsIntraSmem &sm, const KsPicP
     const long long lamq = pp.lambda_sse_q4;
     const KsIntraModes md = sm.modes;                /* staged, like the source block, by the caller */
     ks_intra_code_block<4>(sm, pp, src, rec, lv, x0, y0, md.m16, intra_slice, tid, warp, lane);
-    if (tid == 0) {
+    if (tid == 0) {                                  /* (the block statistics only exist in I pictures: P-picture intra cells stay 16x16) */
         sm.cbf16 = (int)sm.cbf;
-        sm.j16 = 16ll * sm.stat_y[0].d1 + lamq * (sm.stat_y[0].bits + 1) + 16ll * sm.stat_c[0].d1 + lamq * (sm.stat_c[0].bits + 1)
+        if (intra_slice) sm.j16 = 16ll * sm.stat_y[0].d1 + lamq * (sm.stat_y[0].bits + 1) + 16ll * sm.stat_c[0].d1 + lamq * (sm.stat_c[0].bits + 1)
                + 16ll * sm.stat_c[1].d1 + lamq * (sm.stat_c[1].bits + 1) + lamq * 8;
-        sm.try8 = intra_slice && sm.stat_y[0].bits >= KS_SPLIT8_MIN_BITS;       /* I pictures only: the intra CUs of P pictures stay 16x16 */
+        sm.try8 = intra_slice ? sm.stat_y[0].bits >= KS_SPLIT8_MIN_BITS : 0;       /* I pictures only: the intra CUs of P pictures stay 16x16 */
         sm.j8 = lamq * (8 * 4 + 2);
         sm.cbf8[0] = sm.cbf8[1] = sm.cbf8[2] = 0;
     }

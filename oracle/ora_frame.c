@@ -413,6 +413,7 @@ static void recon_inter_cu(const ora_cfg *cfg, int qp, int qpc, int rdz, const o
  *            AMVP predictors of the vectors decided so far (cells of other CTUs count with their search results). ---- */
 #define ORA_NCAND 16
 #define ORA_INTRA_HDR_BITS 10
+#define ORA_INTRA_FLOOR 64          /* x lambda (SAD domain): ~23 x Qstep per cell, i.e. a mean absolute error of ~0.09 Qstep */
 typedef struct { int n; int16_t mvx[ORA_NCAND], mvy[ORA_NCAND]; int dist[16][ORA_NCAND]; int intra[16]; } ora_ctu_cands;   /* dist[j * 4 + i][k]; intra[j * 4 + i] */
 
 static int mvd_bits_est(int d) { int a = iabs(d); if (a == 0) return 1; if (a == 1) return 3; int v = a - 2, k = 1, b = 3; while (v >= (1 << k)) { v -= 1 << k; k++; b++; } return b + k + 1; }
@@ -511,7 +512,9 @@ static int decide_block(const ora_ctu_cands *t, int ncx, int ncy, int lam, int m
     if (s > 1 && best > jsplit) return jsplit;
     if (s == 1) {       /* intra 16x16 CU (reference: intra CUs in P slices are a third of the CUs on natural clips [probe]): ~10 bits of header */
         int ji = t->intra[j * 4 + i] + ((lam * ORA_INTRA_HDR_BITS) >> 4);
-        if (ji < best) {
+        /* ...and only above the quantisation-noise floor: the estimate predicts from SOURCE neighbours while the inter distortion carries the
+         * reference picture's coding noise, so on static smooth areas intra "won" cells the reference simply skips (720p natural: -4.2 % bits, same PSNR) */
+        if (ji < best && t->dist[j * 4 + i][bk] > ((ORA_INTRA_FLOOR * lam) >> 4)) {
             st->mvx[j + 1][i + 1] = 0; st->mvy[j + 1][i + 1] = 0; st->ok[j + 1][i + 1] = 0; st->log2[j][i] = 4; st->intra[j][i] = 1;
             return ji;
         }

@@ -235,7 +235,12 @@ def test_picture_stages_match_oracle(w, h, qp, sbh, sao, subpel, satd, me):
             pool = np.ctypeslib.as_array(out.levels, (max(out.n_cg, 1) * 16,)).copy()[:out.n_cg * 16]
             first_diff(pool, o["pool"][:out.n_cg * 16], tag + "level pool")
             sse = [int(out.sse[k]) for k in range(3)]
-            osse = [int(((o["fin"][a:b].astype(np.int64) - src[a:b]) ** 2).sum()) for a, b in ((0, W * H), (W * H, W * H * 5 // 4), (W * H * 5 // 4, fsz))]
+            # the device's SSE covers the DISPLAY area (the reference's PSNR does too), not the padded coded picture
+            osse = []
+            for (a, b), (pw, ph), (dw, dh) in zip(((0, W * H), (W * H, W * H * 5 // 4), (W * H * 5 // 4, fsz)), ((W, H), (W // 2, H // 2), (W // 2, H // 2)),
+                                                  ((w, h), (w // 2, h // 2), (w // 2, h // 2))):
+                d = (o["fin"][a:b].astype(np.int64) - src[a:b]).reshape(ph, pw)[:dh, :dw]
+                osse.append(int((d ** 2).sum()))
             assert sse == osse, tag + "SSE %s vs %s" % (sse, osse)
             ref_fin = o["fin"]; prev_cells = o["cells"]
     finally:
