@@ -729,7 +729,7 @@ __device__ __forceinline__ void ks_st_release(int *p, int v) { asm volatile("st.
  * ever waits on cells of rows that are running (all rows are resident: <= 270 CTAs at 8K, 3 per SM): no deadlock.  The critical path is
  * (cells per row + 2 x rows) cell steps instead of the (CTUs per row + 2 x CTU rows) x 16 of a CTU wavefront: 510 vs 2048 steps at 4K.
  * (The CTU wavefront kernel this replaces spent 28 % of its issue slots polling for the left / upper CTU.) */
-__global__ void __launch_bounds__(KS_INTRA_WARPS * KS_WARP)
+__global__ void __launch_bounds__(KS_INTRA_WARPS * KS_WARP, 4)       /* <= 128 registers: a waiting row must not lock other shards' kernels out of the SM */
 ks_recon_intra_rows_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels lv, ks_cell *__restrict__ cells, int *sync_ws, const int *__restrict__ n_intra,
                            const KsIntraModes *__restrict__ modes)
 {
