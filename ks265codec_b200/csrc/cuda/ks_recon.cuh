@@ -793,9 +793,6 @@ ks_recon_intra_rows_kernel(KsPicParams pp, KsPlanes src, KsPlanes rec, KsLevels 
         ks_intra_code_cell(sm, pp, src, rec, lv, cells, modes, x0, y0, masked ? 0 : 1, tid, warp, lane);
         KS_T(5);
 #ifdef KS_INTRA_TIMING
-        if (0 && tid == 0 && !masked && gy < 4 && gx < 10) { unsigned long long t_end; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_end)); printf("cell (%d,%d) deps-ok at %6llu ns, coded at %6llu ns (try8 %d)\n", gx, gy, t_dep - sm_row_start, t_end - sm_row_start, sm.try8); }
-#endif
-#ifdef KS_INTRA_TIMING
         if (tid == 0) { __threadfence(); unsigned long long gt; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt)); ks_st_release(&done[gy * cw + gx], (int)((unsigned)gt | 1u)); }
 #else
         if (tid == 0) { __threadfence(); ks_st_release(&done[gy * cw + gx], 1); }
