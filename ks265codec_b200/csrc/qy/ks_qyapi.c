@@ -110,7 +110,7 @@ typedef struct qy_enc {
     int           have_pending, log_threshold;
     ks265_config  k;
     ks265_encoder *enc;
-    int           shard_len;              /* pictures per GOP shard */
+    int           shard_len, cap_len;     /* pictures per GOP shard; what the per-picture arrays are sized for */
     size_t        frame_bytes;
     uint8_t      *frames;                 /* page-locked: shard_len pictures, tightly packed I420 */
     long long    *pts_in;                 /* pts of the buffered pictures, display order */
@@ -159,7 +159,7 @@ static int open_shard(qy_enc *q)
     if (r) return r;
     q->enc = ks265_encoder_open(&q->k, &err);
     if (!q->enc) { logf_(2, q->log_threshold, "ks265qy: encoder open failed (%d)\n", err); return err == -12 ? KSQY_OUTOFMEMORY : KSQY_FAIL; }
-    q->shard_len = q->k.iper;
+    q->shard_len = q->cap_len = q->k.iper;
     q->frame_bytes = (size_t)q->k.width * q->k.height * 3 / 2;
     q->frames = (uint8_t *)ks265_alloc_host(q->frame_bytes * q->shard_len);
     q->pts_in = (long long *)malloc(sizeof(long long) * q->shard_len);
@@ -170,6 +170,31 @@ static int open_shard(qy_enc *q)
     q->nals = (ksqy_nal *)malloc(sizeof(ksqy_nal) * q->nal_cap);
     q->pstat = (ks265_pic_stat *)malloc(sizeof(ks265_pic_stat) * q->shard_len);
     if (!q->frames || !q->pts_in || !q->bs || !q->aus || !q->nals || !q->pstat) { free_shard(q); return KSQY_OUTOFMEMORY; }
+    return KSQY_OK;
+}
+
+/* a Reconfig takes effect here, between two shards (nothing buffered).  Only the encoder is re-opened: the output of the previous shard
+ * (bs / aus / nals) may still be queued and stays where it is; the per-picture arrays only ever grow. */
+static int reconfigure(qy_enc *q)
+{
+    ks265_config k; int err = 0;
+    q->have_pending = 0;
+    if (map_config(&q->pending, &k, q->log_threshold)) return KSQY_OK;                   /* (checked in Reconfig already) the old configuration stays */
+    ks265_encoder *e = ks265_encoder_open(&k, &err);
+    if (!e) { logf_(2, q->log_threshold, "ks265qy: Reconfig: encoder open failed (%d); the old configuration stays\n", err); return KSQY_OK; }
+    if (k.iper > q->cap_len) {
+        uint8_t *f = (uint8_t *)ks265_alloc_host(q->frame_bytes * k.iper);
+        long long *pi = (long long *)malloc(sizeof(long long) * k.iper);
+        ks265_pic_stat *ps = (ks265_pic_stat *)malloc(sizeof(ks265_pic_stat) * k.iper);
+        au_rec *au = f && pi && ps ? (au_rec *)realloc(q->aus, sizeof(au_rec) * k.iper) : NULL;
+        if (au) q->aus = au;
+        ksqy_nal *nl = au ? (ksqy_nal *)realloc(q->nals, sizeof(ksqy_nal) * (4 * k.iper + 8)) : NULL;
+        if (!nl) { if (f) ks265_free_host(f); free(pi); free(ps); ks265_encoder_close(e); return KSQY_OUTOFMEMORY; }
+        ks265_free_host(q->frames); free(q->pts_in); free(q->pstat);
+        q->frames = f; q->pts_in = pi; q->pstat = ps; q->nals = nl; q->nal_cap = 4 * k.iper + 8; q->cap_len = k.iper;
+    }
+    ks265_encoder_close(q->enc);
+    q->enc = e; q->k = k; q->cfg = q->pending; q->shard_len = k.iper; q->log_threshold = q->cfg.log_level;
     return KSQY_OK;
 }
 
@@ -290,10 +315,7 @@ int QY265EncoderEncodeFrame(void *h, ksqy_nal **nals, int *nal_count, ksqy_pictu
             if (queue_busy) { logf_(2, q->log_threshold, "ks265qy: output queue not drained; fetch the pending access units first\n"); return KSQY_FAIL; }
             if ((r = encode_shard(q))) return r;
         }
-        if (!q->buffered && q->have_pending && !queue_busy) {  /* shard boundary: a Reconfig takes effect here */
-            free_shard(q); q->cfg = q->pending; q->have_pending = 0; q->au_count = q->au_next = 0;
-            if ((r = open_shard(q))) return r;
-        }
+        if (!q->buffered && q->have_pending && (r = reconfigure(q))) return r;      /* shard boundary */
         if (!q->buffered) q->key_request = 0;                  /* the picture that opens a shard is the key frame */
         uint8_t *dst = q->frames + q->frame_bytes * q->buffered;
         for (int c = 0; c < 3; c++) {

@@ -5,11 +5,15 @@ reference's header (tests/qy/qy_caller.c) produces the same file and the referen
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (ROOT, os.path.join(ROOT, "tools")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
 LIB = os.path.join(ROOT, "ks265codec_b200", "libks265qy.so")
 REF_INC = "/root/reference/Android_demo/prebuilt/include"
 CALLER = os.path.join(ROOT, "ks265codec_b200", "bin", "qy_caller")
@@ -57,6 +61,7 @@ def shim():
     L.QY265EncoderEncodeHeaders.argtypes = [C.c_void_p, C.POINTER(C.POINTER(Nal)), C.POINTER(C.c_int)]
     L.QY265EncoderEncodeFrame.argtypes = [C.c_void_p, C.POINTER(C.POINTER(Nal)), C.POINTER(C.c_int), C.POINTER(Picture), C.POINTER(Picture), C.c_int]
     L.QY265EncoderKeyFrameRequest.argtypes = [C.c_void_p]
+    L.QY265EncoderReconfig.argtypes = [C.c_void_p, C.POINTER(Config)]
     L.QY265EncoderDelayedFrames.argtypes = [C.c_void_p]
     L.QY265ConfigDefaultPreset.argtypes = [C.POINTER(Config), C.c_char_p, C.c_char_p, C.c_char_p]
     L.QY265ConfigParse.argtypes = [C.POINTER(Config), C.c_char_p, C.c_char_p]
@@ -107,7 +112,7 @@ def test_open_rejects_what_the_device_path_lacks_and_fails_loudly_without_cuda()
         assert not L.QY265EncoderOpen(C.byref(cfg), C.byref(err)) and err.value != OK
 
 
-def _drive(L, yuv, w, h, n, iper, qp, key_at=()):
+def _drive(L, yuv, w, h, n, iper, qp, key_at=(), reconfig_at=None, reconfig_qp=None):
     """the demo's loop (encoderwrapper.c:366-400) through ctypes: one reused input buffer, flush while DelayedFrames"""
     cfg = Config(); err = C.c_int(0)
     assert L.QY265ConfigDefaultPreset(C.byref(cfg), b"veryfast", None, None) == OK
@@ -134,6 +139,9 @@ def _drive(L, yuv, w, h, n, iper, qp, key_at=()):
     for f in range(n):
         if f in key_at:
             L.QY265EncoderKeyFrameRequest(hnd)
+        if f == reconfig_at:
+            cfg.qp = reconfig_qp
+            L.QY265EncoderReconfig(hnd, C.byref(cfg))
         buf[:] = yuv[f * fs:(f + 1) * fs]
         pic.pts = 1000 + f
         take(L.QY265EncoderEncodeFrame(hnd, C.byref(nals), C.byref(cnt), C.byref(pic), C.byref(out), 0))
@@ -163,6 +171,13 @@ def test_shim_output_equals_the_gop_shards_of_the_encoder_api(tmp_path):
     # a key-frame request cuts the shard short: pictures 0..2 | 3..6 | 7..9
     stream2, units2 = _drive(shim(), yuv, w, h, n, iper, qp, key_at=(3,))
     assert [u[0] for u in units2] == [2, 1, 1, 2, 1, 1, 1, 2, 1, 1] and len(stream2) > 0
+    # Reconfig takes effect at the next shard boundary: pictures 0..3 at the old QP, 4..9 at the new one
+    stream3, units3 = _drive(shim(), yuv, w, h, n, iper, qp, reconfig_at=1, reconfig_qp=qp + 6)
+    want3 = bytearray()
+    for q, (a, b) in ((qp, (0, 4)), (qp + 6, (4, 8)), (qp + 6, (8, 10))):
+        with ks.Encoder(ks.default_config(w, h, preset="veryfast", qp=q, iper=iper, fps=30.0)) as e:
+            want3.extend(bytes(e.encode_gop(yuv[a * fs:b * fs])[0]))
+    assert len(units3) == n and stream3 == bytes(want3)
     # the caller compiled against the reference's own header (built where that header exists) writes the same file, and the reference decoder takes it
     if os.path.exists(CALLER):
         clip, out = tmp_path / "in.yuv", tmp_path / "out.265"
