@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "../include/ks265_syntax.h"
+#include "ora_parse.h"
 
 /* ------------------------------------------------------------------ bit reader ---------------------- */
 typedef struct { const uint8_t *b; size_t n, pos; } bitr;          /* pos in bits */
@@ -213,23 +214,9 @@ static int cd_terminate(cabd *c)
 
 /* ------------------------------------------------------------------ picture-level state ------------- */
 /* one record per coding unit, in decoding order (the P2 replay input; also the raw material of the statistics) */
-typedef struct ora_cu_rec {
-    uint16_t x, y; uint8_t log2, pred_mode /* 0 inter, 1 intra */, part_mode, skip;
-    uint8_t merge[4], merge_idx[4], inter_dir[4], ref_idx[4][2], mvp[4][2];
-    int16_t mvd[4][2][2];
-    uint8_t intra_mode[4], chroma_mode;
-    uint8_t root_cbf;
-    uint32_t first_tu, n_tu;
-} ora_cu_rec;
-typedef struct ora_tu_rec { uint16_t x, y; uint8_t log2, cbf; /* bit0 Y, 1 Cb, 2 Cr */ int8_t qp_delta; uint32_t lev_off[3]; } ora_tu_rec;   /* lev_off: index into levels (raster NxN), ~0u = none */
 
-typedef struct ora_pic_stats {
-    int poc, slice_type, qp, nal_type, num_ref[2];
-    long bits_total, bits_sao, bits_split, bits_cu_hdr, bits_mvd, bits_luma, bits_chroma, bits_intra_mode;
-    long n_cu[4] /* by log2 3..6 */, n_skip[4], n_merge[4], n_amvp[4], n_intra[4], n_intra_nxn, n_tu[4] /* by log2 2..5 */, n_cbf_luma, n_cbf_chroma;
-    long nz_luma, nz_chroma, sum_abs_luma, sum_abs_chroma, n_mvd_nonzero;
-    long sao_on_luma, sao_on_chroma, sao_merge;
-} ora_pic_stats;
+   /* per CTU and component: 0 off / 1 band (pos = first band) / 2 edge (pos = class) */
+
 
 typedef struct {
     const sps_t *sps; const pps_t *pps; cabd cd; const uint8_t *base;
@@ -246,6 +233,7 @@ typedef struct {
     int err;
     int cu_pred_mode, cu_intra_luma[4], cu_intra_chroma, cu_part;    /* of the CU being parsed */
     int is_cu_qp_delta_coded;
+    ora_sao_rec *sao; int ctw;    /* per CTU, merges resolved */
 } pctx;
 
 static uint8_t scan_diag4[16], scan_diag8[64], scan_diag2[4], scan_hor4[16], scan_ver4[16], scan_hor2[4], scan_ver2[4], scan_hor8[64], scan_ver8[64];
@@ -285,20 +273,29 @@ static void parse_sao(pctx *p, int rx, int ry)
 {
     cabd *c = &p->cd;
     long b0 = cd_pos(c, p->base);
-    int merged = 0;
-    if (rx > 0) merged = cd_bin(c, CX_SAO_MERGE);
-    if (!merged && ry > 0) merged = cd_bin(c, CX_SAO_MERGE);
-    if (merged) p->st.sao_merge++;
-    else {
+    int merge_left = 0, merge_up = 0;
+    ora_sao_rec *rec = &p->sao[ry * p->ctw + rx];
+    memset(rec, 0, sizeof(*rec));
+    if (rx > 0) merge_left = cd_bin(c, CX_SAO_MERGE);
+    if (!merge_left && ry > 0) merge_up = cd_bin(c, CX_SAO_MERGE);
+    if (merge_left || merge_up) {
+        p->st.sao_merge++;
+        *rec = merge_left ? p->sao[ry * p->ctw + rx - 1] : p->sao[(ry - 1) * p->ctw + rx];
+        /* a merge copies the candidate's parameters of the components whose SAO is on in THIS slice (7.4.9.3.2 infers the rest as off) */
+        if (!p->sao_luma) rec->type[0] = 0;
+        if (!p->sao_chroma) rec->type[1] = rec->type[2] = 0;
+    } else {
         int type = 0;
         for (int ci = 0; ci < 3; ci++) {
             if ((ci == 0 && !p->sao_luma) || (ci > 0 && !p->sao_chroma)) continue;
             if (ci < 2) { type = cd_bin(c, CX_SAO_TYPE); if (type) type = cd_bypass(c) ? 2 : 1; if (type) { if (ci == 0) p->st.sao_on_luma++; else p->st.sao_on_chroma++; } }
+            rec->type[ci] = (uint8_t)type;
             if (!type) continue;
             int off[4];
             for (int k = 0; k < 4; k++) { int a = 0; while (a < 7 && cd_bypass(c)) a++; off[k] = a; }
-            if (type == 1) { for (int k = 0; k < 4; k++) if (off[k]) cd_bypass(c); cd_bypass_bits(c, 5); }
-            else if (ci < 2) cd_bypass_bits(c, 2);
+            if (type == 1) { for (int k = 0; k < 4; k++) if (off[k] && cd_bypass(c)) off[k] = -off[k]; rec->pos[ci] = (uint8_t)cd_bypass_bits(c, 5); }
+            else { if (ci < 2) rec->pos[ci] = (uint8_t)cd_bypass_bits(c, 2); else rec->pos[2] = rec->pos[1]; off[2] = -off[2]; off[3] = -off[3]; }
+            for (int k = 0; k < 4; k++) rec->off[ci][k] = (int8_t)off[k];
         }
     }
     p->st.bits_sao += cd_pos(c, p->base) - b0;
@@ -653,20 +650,7 @@ static void parse_quadtree(pctx *p, int x0, int y0, int log2, int depth)
 }
 
 /* ------------------------------------------------------------------ stream level --------------------- */
-typedef struct ora_parsed_pic {
-    ora_pic_stats st;
-    ora_cu_rec *cus; size_t n_cus;
-    ora_tu_rec *tus; size_t n_tus;
-    int16_t *lev; size_t n_lev;
-    int ok;               /* slice ended exactly on end_of_slice_segment_flag after the last CTU */
-    int ref_poc[2][16];
-} ora_parsed_pic;
 
-typedef struct ora_parsed_stream {
-    int width, height, n_pics, log2_ctb, log2_min_cb, max_merge;
-    ora_parsed_pic *pics;
-    int error;            /* 0 = every slice parsed to its end */
-} ora_parsed_stream;
 
 static size_t unescape(const uint8_t *in, size_t n, uint8_t *out)
 {
@@ -721,10 +705,11 @@ static int parse_slice(const sps_t *sps, const pps_t *pps, int nal_type, const u
         max_merge = 5 - (int)br_ue(&r);
     }
     int qp = pps->init_qp + br_se(&r);
-    if (pps->slice_chroma_off) { br_se(&r); br_se(&r); }
+    int cb_off = pps->cb_off, cr_off = pps->cr_off, beta_off = pps->beta, tc_off = pps->tc;
+    if (pps->slice_chroma_off) { cb_off += br_se(&r); cr_off += br_se(&r); }
     int dbk_override = 0, dbk_disabled = pps->deblock_disabled;
     if (pps->deblock_override) dbk_override = br_u(&r, 1);
-    if (dbk_override) { dbk_disabled = br_u(&r, 1); if (!dbk_disabled) { br_se(&r); br_se(&r); } }
+    if (dbk_override) { dbk_disabled = br_u(&r, 1); if (!dbk_disabled) { beta_off = br_se(&r); tc_off = br_se(&r); } }
     if (pps->lf_across && (sao_l || sao_c || !dbk_disabled)) br_u(&r, 1);
     if (pps->tiles || pps->wpp) { int ne = (int)br_ue(&r); if (ne) { int ol = (int)br_ue(&r) + 1; for (int i = 0; i < ne; i++) br_u(&r, ol); if (ne) return -12; } }
     if (pps->slice_ext) { int l = (int)br_ue(&r); for (int i = 0; i < l; i++) br_u(&r, 8); }
@@ -743,6 +728,7 @@ static int parse_slice(const sps_t *sps, const pps_t *pps, int nal_type, const u
     cd_init(&p.cd, p.base, rb + n, init_type, qp);
     p.st.poc = poc; p.st.slice_type = st; p.st.qp = qp; p.st.nal_type = nal_type; p.st.num_ref[0] = nref[0]; p.st.num_ref[1] = nref[1];
     int l = sps->log2_ctb, ctw = (p.w + (1 << l) - 1) >> l, cth = (p.h + (1 << l) - 1) >> l, ok = 1;
+    p.sao = (ora_sao_rec *)calloc((size_t)ctw * cth, sizeof(ora_sao_rec)); p.ctw = ctw;
     for (int a = 0; a < ctw * cth && ok; a++) {
         int rx = a % ctw, ry = a / ctw;
         if (sao_l || sao_c) parse_sao(&p, rx, ry);
@@ -754,6 +740,9 @@ static int parse_slice(const sps_t *sps, const pps_t *pps, int nal_type, const u
     /* after end_of_slice_segment_flag = 1 the decoder must sit within the last bytes of the RBSP (9.3.2.5 reads rbsp_trailing_bits) */
     if (ok && (size_t)(p.cd.p - rb) + 4 < n) ok = 0;
     p.st.bits_total = (long)(n - (r.pos >> 3)) * 8;
+    out->sao = p.sao; out->dbk_disabled = dbk_disabled; out->beta_off_div2 = beta_off; out->tc_off_div2 = tc_off; out->cb_qp_off = cb_off; out->cr_qp_off = cr_off;
+    out->cu_qp_delta_enabled = pps->cu_qp_delta; out->any_qp_delta = 0;
+    for (size_t q = 0; q < p.n_tus; q++) if (p.tus[q].qp_delta) out->any_qp_delta = 1;
     out->st = p.st; out->cus = p.cus; out->n_cus = p.n_cus; out->tus = p.tus; out->n_tus = p.n_tus; out->lev = p.lev; out->n_lev = p.n_lev; out->ok = ok;
     for (int i = 0; i < 16; i++) { out->ref_poc[0][i] = i < rps.n_neg ? poc + rps.dpoc[i] : 0; out->ref_poc[1][i] = i < rps.n_pos ? poc + rps.dpoc[rps.n_neg + i] : 0; }
     free(p.depth); free(p.skipf); free(p.ipm); free(p.is_intra);
@@ -776,7 +765,7 @@ ora_parsed_stream *ora_parse_stream(const uint8_t *bs, size_t n)
         size_t m = unescape(bs + s + 2, e - s - 2, rb);
         while (m && rb[m - 1] == 0) m--;                          /* trailing zero bytes belong to the next start code */
         bitr r = {rb, m, 0};
-        if (nal_type == 33) { int k = parse_sps(&r, &sps); if (getenv("ORA_PARSE_DEBUG")) fprintf(stderr, "SPS %dx%d mincb %d ctb %d mintb %d maxtb %d depth inter %d intra %d amp %d sao %d nrps %d lt %d tmvp %d sis %d -> %d\n", sps.w, sps.h, sps.log2_min_cb, sps.log2_ctb, sps.log2_min_tb, sps.log2_max_tb, sps.tu_depth_inter, sps.tu_depth_intra, sps.amp, sps.sao, sps.n_rps, sps.long_term, sps.tmvp, sps.strong_intra, k); if (k) { ps->error = k; break; } have_sps = 1; ps->width = sps.w; ps->height = sps.h; ps->log2_ctb = sps.log2_ctb; ps->log2_min_cb = sps.log2_min_cb; }
+        if (nal_type == 33) { int k = parse_sps(&r, &sps); if (getenv("ORA_PARSE_DEBUG")) fprintf(stderr, "SPS %dx%d mincb %d ctb %d mintb %d maxtb %d depth inter %d intra %d amp %d sao %d nrps %d lt %d tmvp %d sis %d -> %d\n", sps.w, sps.h, sps.log2_min_cb, sps.log2_ctb, sps.log2_min_tb, sps.log2_max_tb, sps.tu_depth_inter, sps.tu_depth_intra, sps.amp, sps.sao, sps.n_rps, sps.long_term, sps.tmvp, sps.strong_intra, k); if (k) { ps->error = k; break; } have_sps = 1; ps->width = sps.w; ps->height = sps.h; ps->log2_ctb = sps.log2_ctb; ps->log2_min_cb = sps.log2_min_cb; ps->strong_intra = sps.strong_intra; }
         else if (nal_type == 34) { int k = parse_pps(&r, &pps); if (getenv("ORA_PARSE_DEBUG")) fprintf(stderr, "PPS sbh %d cabac_init %d refs %d %d tskip %d cuqpd %d/%d wpp %d dbk %d/%d/%d lists_mod %d par_mrg %d -> %d\n", pps.sign_hiding, pps.cabac_init_present, pps.ref_l0, pps.ref_l1, pps.tskip, pps.cu_qp_delta, pps.diff_cu_qp_delta_depth, pps.wpp, pps.deblock_ctrl, pps.deblock_override, pps.deblock_disabled, pps.lists_mod, pps.par_mrg, k); if (k) { ps->error = k; break; } have_pps = 1; }
         else if (nal_type <= 21 && have_sps && have_pps) {
             if (ps->n_pics == cap) { cap = cap ? cap * 2 : 64; ps->pics = (ora_parsed_pic *)realloc(ps->pics, (size_t)cap * sizeof(ora_parsed_pic)); }
@@ -793,11 +782,13 @@ ora_parsed_stream *ora_parse_stream(const uint8_t *bs, size_t n)
 void ora_parse_free(ora_parsed_stream *ps)
 {
     if (!ps) return;
-    for (int i = 0; i < ps->n_pics; i++) { free(ps->pics[i].cus); free(ps->pics[i].tus); free(ps->pics[i].lev); }
+    for (int i = 0; i < ps->n_pics; i++) { free(ps->pics[i].cus); free(ps->pics[i].tus); free(ps->pics[i].lev); free(ps->pics[i].sao); }
     free(ps->pics); free(ps);
 }
 int ora_parse_error(const ora_parsed_stream *ps) { return ps->error; }
 int ora_parse_num_pics(const ora_parsed_stream *ps) { return ps->n_pics; }
+int ora_parse_width(const ora_parsed_stream *ps) { return ps->width; }      /* coded size (the SPS's, before the conformance window) */
+int ora_parse_height(const ora_parsed_stream *ps) { return ps->height; }
 const ora_pic_stats *ora_parse_pic_stats(const ora_parsed_stream *ps, int i) { return &ps->pics[i].st; }
 size_t ora_parse_sizeof_stats(void) { return sizeof(ora_pic_stats); }
 int ora_parse_pic_ok(const ora_parsed_stream *ps, int i) { return ps->pics[i].ok; }

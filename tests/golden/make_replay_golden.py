@@ -1,0 +1,51 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/ref_intra_streams.json: I pictures coded by the REFERENCE encoder (oracle/_ref/appencoder, needs /root/reference once)
+at several presets / QPs, each with the MD5 of what the reference DECODER makes of it.  tests/test_replay.py re-creates those pictures from
+the parsed decisions with the oracle's kernels (oracle/ora_replay.c) and must hit the same MD5 -- no reference binary needed at test time."""
+import base64
+import gzip
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+import gen_yuv  # noqa: E402
+
+REF = os.path.join(ROOT, "oracle", "_ref")
+nat = np.frombuffer(gzip.open(os.path.join(HERE, "nat_320x240_6f.yuv.gz"), "rb").read(), np.uint8)
+CASES = [("nat320_veryfast_qp27", nat, 320, 240, "veryfast", 27, 0), ("nat320_slow_qp22", nat, 320, 240, "slow", 22, 0),
+         ("nat320_ultrafast_qp37", nat, 320, 240, "ultrafast", 37, 3), ("nat320_placebo_qp32", nat, 320, 240, "placebo", 32, 5),
+         ("syn200x120_medium_qp30", np.frombuffer(gen_yuv.make(200, 120, 1, seed=5), np.uint8), 200, 120, "medium", 30, 0),
+         ("syn256x128_veryslow_qp18", np.frombuffer(gen_yuv.make(256, 128, 1, seed=9), np.uint8), 256, 128, "veryslow", 18, 0)]
+# two textured crops of the reference repo's own 720p clip (read at generation time only)
+big = "/root/reference/iOS_demo/resource/1280x720_15.yuv"
+if os.path.exists(big):
+    f0 = np.fromfile(big, np.uint8, count=1280 * 720 * 3 // 2)
+    def crop(x, y, w, h):
+        Y = f0[:1280 * 720].reshape(720, 1280)[y:y + h, x:x + w]
+        U = f0[1280 * 720:1280 * 720 * 5 // 4].reshape(360, 640)[y // 2:(y + h) // 2, x // 2:(x + w) // 2]
+        V = f0[1280 * 720 * 5 // 4:].reshape(360, 640)[y // 2:(y + h) // 2, x // 2:(x + w) // 2]
+        return np.concatenate([Y.ravel(), U.ravel(), V.ravel()])
+    CASES += [("crop720_veryfast_qp27", crop(448, 232, 384, 256), 384, 256, "veryfast", 27, 0), ("crop720_slow_qp24", crop(64, 360, 320, 192), 320, 192, "slow", 24, 0)]
+out = []
+for name, yuv, w, h, preset, qp, frame in CASES:
+    fs = w * h * 3 // 2
+    with tempfile.TemporaryDirectory() as d:
+        clip, bs, dec = os.path.join(d, "i.yuv"), os.path.join(d, "o.265"), os.path.join(d, "d.yuv")
+        open(clip, "wb").write(yuv[frame * fs:(frame + 1) * fs].tobytes())
+        subprocess.run([os.path.join(REF, "appencoder"), "-i", clip, "-wdt", str(w), "-hgt", str(h), "-fr", "15", "-preset", preset, "-rc", "0", "-qp", str(qp),
+                        "-iper", "128", "-frms", "1", "-threads", "1", "-b", bs], capture_output=True, check=True)
+        subprocess.run([os.path.join(REF, "appdecoder"), "-b", bs, "-o", dec, "-threads", "1"], capture_output=True, check=True)
+        stream, decoded = open(bs, "rb").read(), open(dec, "rb").read()
+        assert len(decoded) == fs
+        out.append({"name": name, "width": w, "height": h, "preset": preset, "qp": qp, "stream_b64": base64.b64encode(stream).decode(),
+                    "decoded_md5": hashlib.md5(decoded).hexdigest()})
+        print(name, len(stream), "bytes")
+json.dump(out, open(os.path.join(HERE, "ref_intra_streams.json"), "w"), indent=0)

@@ -1,0 +1,58 @@
+"""SURVEY.md 8c tier P2 on the CPU: I pictures coded by the REFERENCE encoder are re-created from their own parsed decisions (oracle/ora_parse.c)
+with the oracle's leaf kernels (oracle/ora_replay.c) and must equal what the reference DECODER makes of them, byte for byte.  The streams and
+the decoder's MD5 are committed (tests/golden/ref_intra_streams.json, made by tests/golden/make_replay_golden.py); where the reference decoder
+is staged (oracle/_ref) the comparison is also made against a live decode."""
+import base64
+import ctypes as C
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CASES = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_intra_streams.json")))
+DEC = os.path.join(ROOT, "oracle", "_ref", "appdecoder")
+
+
+def _oracle():
+    O = C.CDLL(os.path.join(ROOT, "oracle", "libks_oracle.so"))
+    O.ora_parse_stream.restype = C.c_void_p
+    O.ora_parse_stream.argtypes = [C.c_void_p, C.c_size_t]
+    O.ora_parse_free.argtypes = [C.c_void_p]
+    for f in (O.ora_parse_error, O.ora_parse_num_pics, O.ora_parse_width, O.ora_parse_height):
+        f.argtypes = [C.c_void_p]
+    O.ora_replay_intra_picture.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    return O
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_reference_intra_picture_is_recreated_from_its_parsed_decisions(case, tmp_path):
+    O = _oracle()
+    bs = np.frombuffer(base64.b64decode(case["stream_b64"]), np.uint8).copy()
+    ps = O.ora_parse_stream(bs.ctypes.data, bs.size)
+    try:
+        assert O.ora_parse_error(ps) == 0 and O.ora_parse_num_pics(ps) == 1
+        w, h = O.ora_parse_width(ps), O.ora_parse_height(ps)
+        assert (w, h) == (case["width"], case["height"])            # sizes without a conformance window: coded == display
+        out = np.zeros(w * h * 3 // 2, np.uint8)
+        assert O.ora_replay_intra_picture(ps, 0, out.ctypes.data) == 0
+    finally:
+        O.ora_parse_free(ps)
+    assert hashlib.md5(out.tobytes()).hexdigest() == case["decoded_md5"]
+    if os.path.exists(DEC):
+        p, o = tmp_path / "s.265", tmp_path / "d.yuv"
+        p.write_bytes(bs.tobytes())
+        subprocess.run([DEC, "-b", str(p), "-o", str(o), "-threads", "1"], capture_output=True, timeout=120)
+        assert np.array_equal(np.fromfile(o, np.uint8), out)
+
+
+def test_replay_rejects_what_it_does_not_cover():
+    O = _oracle()
+    bs = np.frombuffer(base64.b64decode(CASES[0]["stream_b64"]), np.uint8).copy()
+    ps = O.ora_parse_stream(bs.ctypes.data, bs.size)
+    out = np.zeros(16, np.uint8)
+    assert O.ora_replay_intra_picture(ps, 1, out.ctypes.data) == -1          # no such picture
+    O.ora_parse_free(ps)
