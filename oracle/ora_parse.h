@@ -32,6 +32,8 @@ typedef struct ora_parsed_pic {
     int ref_poc[2][16];
     ora_sao_rec *sao;     /* per CTU (raster) */
     int dbk_disabled, beta_off_div2, tc_off_div2, cb_qp_off, cr_qp_off, cu_qp_delta_enabled, any_qp_delta;
+    int tmvp, col_ref_idx, max_merge, par_mrg_level;      /* slice_temporal_mvp_enabled_flag, collocated_ref_idx, MaxNumMergeCand, Log2ParMrgLevel */
+    int n_list0, list0_poc[16];                           /* RefPicList0 as POCs */
 } ora_parsed_pic;
 
 typedef struct ora_parsed_stream {

@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Generates tests/golden/ref_intra_streams.json: I pictures coded by the REFERENCE encoder (oracle/_ref/appencoder, needs /root/reference once)
+"""Generates tests/golden/ref_intra_streams.json and ref_p_streams.json: I pictures and P-only sequences coded by the REFERENCE encoder (oracle/_ref/appencoder, needs /root/reference once)
 at several presets / QPs, each with the MD5 of what the reference DECODER makes of it.  tests/test_replay.py re-creates those pictures from
 the parsed decisions with the oracle's kernels (oracle/ora_replay.c) and must hit the same MD5 -- no reference binary needed at test time."""
 import base64
@@ -49,3 +49,33 @@ for name, yuv, w, h, preset, qp, frame in CASES:
                     "decoded_md5": hashlib.md5(decoded).hexdigest()})
         print(name, len(stream), "bytes")
 json.dump(out, open(os.path.join(HERE, "ref_intra_streams.json"), "w"), indent=0)
+
+# P-only sequences (-bframes 0): every picture's MD5 as the reference decoder writes it
+SEQS = [("nat320_veryfast_qp27_6f", nat, 320, 240, "veryfast", 27, 6), ("nat320_slow_qp32_6f", nat, 320, 240, "slow", 32, 6), ("nat320_ultrafast_qp22_6f", nat, 320, 240, "ultrafast", 22, 6)]
+if os.path.exists(big):
+    n = 8
+    fr = np.fromfile(big, np.uint8, count=1280 * 720 * 3 // 2 * n).reshape(n, -1)
+    def crop_seq(x, y, w, h):
+        o = []
+        for f in range(n):
+            Y = fr[f][:1280 * 720].reshape(720, 1280)[y:y + h, x:x + w]
+            U = fr[f][1280 * 720:1280 * 720 * 5 // 4].reshape(360, 640)[y // 2:(y + h) // 2, x // 2:(x + w) // 2]
+            V = fr[f][1280 * 720 * 5 // 4:].reshape(360, 640)[y // 2:(y + h) // 2, x // 2:(x + w) // 2]
+            o.append(np.concatenate([Y.ravel(), U.ravel(), V.ravel()]))
+        return np.concatenate(o)
+    SEQS += [("crop720_veryfast_qp27_8f", crop_seq(448, 232, 384, 256), 384, 256, "veryfast", 27, 8), ("crop720_medium_qp30_8f", crop_seq(640, 300, 320, 192), 320, 192, "medium", 30, 8)]
+out = []
+for name, yuv, w, h, preset, qp, nf in SEQS:
+    fs = w * h * 3 // 2
+    with tempfile.TemporaryDirectory() as d:
+        clip, bs, dec = os.path.join(d, "i.yuv"), os.path.join(d, "o.265"), os.path.join(d, "d.yuv")
+        open(clip, "wb").write(yuv[:nf * fs].tobytes())
+        subprocess.run([os.path.join(REF, "appencoder"), "-i", clip, "-wdt", str(w), "-hgt", str(h), "-fr", "15", "-preset", preset, "-rc", "0", "-qp", str(qp),
+                        "-iper", "128", "-bframes", "0", "-frms", str(nf), "-threads", "1", "-b", bs], capture_output=True, check=True)
+        subprocess.run([os.path.join(REF, "appdecoder"), "-b", bs, "-o", dec, "-threads", "1"], capture_output=True, check=True)
+        stream, decoded = open(bs, "rb").read(), open(dec, "rb").read()
+        assert len(decoded) == fs * nf
+        out.append({"name": name, "width": w, "height": h, "preset": preset, "qp": qp, "frames": nf, "stream_b64": base64.b64encode(stream).decode(),
+                    "decoded_md5": [hashlib.md5(decoded[f * fs:(f + 1) * fs]).hexdigest() for f in range(nf)]})
+        print(name, len(stream), "bytes")
+json.dump(out, open(os.path.join(HERE, "ref_p_streams.json"), "w"), indent=0)

@@ -1,4 +1,4 @@
-"""SURVEY.md 8c tier P2 on the CPU: I pictures coded by the REFERENCE encoder are re-created from their own parsed decisions (oracle/ora_parse.c)
+"""SURVEY.md 8c tier P2 on the CPU: I pictures and P-only sequences coded by the REFERENCE encoder are re-created from their own parsed decisions (oracle/ora_parse.c)
 with the oracle's leaf kernels (oracle/ora_replay.c) and must equal what the reference DECODER makes of them, byte for byte.  The streams and
 the decoder's MD5 are committed (tests/golden/ref_intra_streams.json, made by tests/golden/make_replay_golden.py); where the reference decoder
 is staged (oracle/_ref) the comparison is also made against a live decode."""
@@ -14,6 +14,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CASES = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_intra_streams.json")))
+SEQS = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_p_streams.json")))
 DEC = os.path.join(ROOT, "oracle", "_ref", "appdecoder")
 
 
@@ -25,6 +26,7 @@ def _oracle():
     for f in (O.ora_parse_error, O.ora_parse_num_pics, O.ora_parse_width, O.ora_parse_height):
         f.argtypes = [C.c_void_p]
     O.ora_replay_intra_picture.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    O.ora_replay_pictures.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     return O
 
 
@@ -42,6 +44,33 @@ def test_reference_intra_picture_is_recreated_from_its_parsed_decisions(case, tm
     finally:
         O.ora_parse_free(ps)
     assert hashlib.md5(out.tobytes()).hexdigest() == case["decoded_md5"]
+    if os.path.exists(DEC):
+        p, o = tmp_path / "s.265", tmp_path / "d.yuv"
+        p.write_bytes(bs.tobytes())
+        subprocess.run([DEC, "-b", str(p), "-o", str(o), "-threads", "1"], capture_output=True, timeout=120)
+        assert np.array_equal(np.fromfile(o, np.uint8), out)
+
+
+@pytest.mark.parametrize("seq", SEQS, ids=[c["name"] for c in SEQS])
+def test_reference_p_sequence_is_recreated_from_its_parsed_decisions(seq, tmp_path):
+    """-bframes 0 streams of the reference encoder: skip / merge (spatial + temporal candidates) / AMVP with several reference pictures,
+    8x8..64x64 inter CUs, intra CUs inside P pictures, residuals, deblocking strengths from vectors and coefficients, SAO"""
+    O = _oracle()
+    bs = np.frombuffer(base64.b64decode(seq["stream_b64"]), np.uint8).copy()
+    ps = O.ora_parse_stream(bs.ctypes.data, bs.size)
+    try:
+        n = O.ora_parse_num_pics(ps)
+        assert O.ora_parse_error(ps) == 0 and n == seq["frames"]
+        w, h = O.ora_parse_width(ps), O.ora_parse_height(ps)
+        fs = w * h * 3 // 2
+        out = np.zeros(fs * n, np.uint8)
+        assert O.ora_replay_pictures(ps, 0, n, out.ctypes.data) == 0
+        # a later picture on its own: the pictures it references are replayed behind the scenes
+        one = np.zeros(fs, np.uint8)
+        assert O.ora_replay_pictures(ps, n - 1, 1, one.ctypes.data) == 0 and np.array_equal(one, out[(n - 1) * fs:])
+    finally:
+        O.ora_parse_free(ps)
+    assert [hashlib.md5(out[f * fs:(f + 1) * fs].tobytes()).hexdigest() for f in range(n)] == seq["decoded_md5"]
     if os.path.exists(DEC):
         p, o = tmp_path / "s.265", tmp_path / "d.yuv"
         p.write_bytes(bs.tobytes())
