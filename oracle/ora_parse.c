@@ -693,7 +693,7 @@ static int parse_slice(const sps_t *sps, const pps_t *pps, int nal_type, const u
     *prev_poc_tid0 = poc;
     int sao_l = 0, sao_c = 0;
     if (sps->sao) { sao_l = br_u(&r, 1); sao_c = br_u(&r, 1); }
-    int nref[2] = {0, 0}, max_merge = 5, mvd_l1_zero = 0, cabac_init = 0, col_ref_idx = 0;
+    int nref[2] = {0, 0}, max_merge = 5, mvd_l1_zero = 0, cabac_init = 0, col_ref_idx = 0, col_from_l0 = 1;
     if (st != KS_SLICE_I) {
         nref[0] = pps->ref_l0; nref[1] = st == KS_SLICE_B ? pps->ref_l1 : 0;
         if (br_u(&r, 1)) { nref[0] = (int)br_ue(&r) + 1; if (st == KS_SLICE_B) nref[1] = (int)br_ue(&r) + 1; }
@@ -701,7 +701,7 @@ static int parse_slice(const sps_t *sps, const pps_t *pps, int nal_type, const u
         if (pps->lists_mod && npt > 1) { int bits = 0; while ((1 << bits) < npt) bits++; for (int X = 0; X < (st == KS_SLICE_B ? 2 : 1); X++) if (br_u(&r, 1)) for (int i = 0; i < nref[X]; i++) br_u(&r, bits); }
         if (st == KS_SLICE_B) mvd_l1_zero = br_u(&r, 1);
         if (pps->cabac_init_present) cabac_init = br_u(&r, 1);
-        if (tmvp) { int col_l0 = 1; if (st == KS_SLICE_B) col_l0 = br_u(&r, 1); if ((col_l0 && nref[0] > 1) || (!col_l0 && nref[1] > 1)) col_ref_idx = (int)br_ue(&r); }
+        if (tmvp) { if (st == KS_SLICE_B) col_from_l0 = br_u(&r, 1); if ((col_from_l0 && nref[0] > 1) || (!col_from_l0 && nref[1] > 1)) col_ref_idx = (int)br_ue(&r); }
         max_merge = 5 - (int)br_ue(&r);
     }
     int qp = pps->init_qp + br_se(&r);
@@ -742,12 +742,18 @@ static int parse_slice(const sps_t *sps, const pps_t *pps, int nal_type, const u
     p.st.bits_total = (long)(n - (r.pos >> 3)) * 8;
     out->sao = p.sao; out->dbk_disabled = dbk_disabled; out->beta_off_div2 = beta_off; out->tc_off_div2 = tc_off; out->cb_qp_off = cb_off; out->cr_qp_off = cr_off;
     out->cu_qp_delta_enabled = pps->cu_qp_delta; out->any_qp_delta = 0;
-    out->tmvp = tmvp; out->col_ref_idx = col_ref_idx; out->max_merge = max_merge; out->par_mrg_level = pps->par_mrg; out->n_list0 = 0;
+    out->tmvp = tmvp; out->col_ref_idx = col_ref_idx; out->max_merge = max_merge; out->par_mrg_level = pps->par_mrg; out->n_list0 = 0; out->n_list1 = 0;
     if (st != KS_SLICE_I) {       /* 8.3.4 without list modification: the used short-term pictures before, then after the current one, repeated cyclically */
         int cand[32], nc = 0;
         for (int i = 0; i < rps.n_neg + rps.n_pos; i++) if (rps.used[i]) cand[nc++] = poc + rps.dpoc[i];
         for (int i = 0; i < nref[0] && i < 16 && nc; i++) out->list0_poc[out->n_list0++] = cand[i % nc];
+        /* list 1: the pictures after the current one first, then those before it */
+        int c1[32], n1 = 0;
+        for (int i = rps.n_neg; i < rps.n_neg + rps.n_pos; i++) if (rps.used[i]) c1[n1++] = poc + rps.dpoc[i];
+        for (int i = 0; i < rps.n_neg; i++) if (rps.used[i]) c1[n1++] = poc + rps.dpoc[i];
+        for (int i = 0; i < nref[1] && i < 16 && n1; i++) out->list1_poc[out->n_list1++] = c1[i % n1];
     }
+    out->col_from_l0 = col_from_l0; out->mvd_l1_zero = mvd_l1_zero; out->qg_depth = pps->diff_cu_qp_delta_depth;
     for (size_t q = 0; q < p.n_tus; q++) if (p.tus[q].qp_delta) out->any_qp_delta = 1;
     out->st = p.st; out->cus = p.cus; out->n_cus = p.n_cus; out->tus = p.tus; out->n_tus = p.n_tus; out->lev = p.lev; out->n_lev = p.n_lev; out->ok = ok;
     for (int i = 0; i < 16; i++) { out->ref_poc[0][i] = i < rps.n_neg ? poc + rps.dpoc[i] : 0; out->ref_poc[1][i] = i < rps.n_pos ? poc + rps.dpoc[rps.n_neg + i] : 0; }

@@ -34,6 +34,8 @@ typedef struct ora_parsed_pic {
     int dbk_disabled, beta_off_div2, tc_off_div2, cb_qp_off, cr_qp_off, cu_qp_delta_enabled, any_qp_delta;
     int tmvp, col_ref_idx, max_merge, par_mrg_level;      /* slice_temporal_mvp_enabled_flag, collocated_ref_idx, MaxNumMergeCand, Log2ParMrgLevel */
     int n_list0, list0_poc[16];                           /* RefPicList0 as POCs */
+    int n_list1, list1_poc[16], col_from_l0, mvd_l1_zero;
+    int qg_depth;                                         /* diff_cu_qp_delta_depth */
 } ora_parsed_pic;
 
 typedef struct ora_parsed_stream {

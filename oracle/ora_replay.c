@@ -5,10 +5,10 @@
  * luma / chroma interpolation, dequantiser, IDCT 4..32 + IDST, deblocking segments, SAO apply) plus the normative derivations a decoder
  * needs (reference-sample availability, merge list, AMVP, temporal vector prediction with POC scaling, boundary strengths).  The result must
  * equal what the reference DECODER makes of the same stream, byte for byte (tests/test_replay.py): that pins those kernels against the
- * reference at every block size and in every combination ITS encoder uses -- 4x4 NxN partitions, 32x32 intra CUs, 8x8 inter CUs, several
- * reference pictures -- not only at the sizes our own streams exercise (tier P1).  TEST INFRASTRUCTURE: nothing under ks265codec_b200/ links this.
- * Limits: I and P slices (the reference's -bframes 0 streams), 2Nx2N inter prediction blocks (presets ultrafast .. slow), one slice per
- * picture, cu_qp_delta all zero (the reference at -rc 0), Log2ParMrgLevel 2, no PCM / transform skip / scaling lists / long-term pictures.
+ * reference at every block size and in every combination ITS encoder uses -- 4x4 NxN partitions, 32x32 intra CUs, 8x8 inter CUs, bi-prediction,
+ * several reference pictures per list -- not only at the sizes our own streams exercise (tier P1).  TEST INFRASTRUCTURE: nothing under ks265codec_b200/ links this.
+ * Limits: 2Nx2N / 2NxN / Nx2N inter prediction blocks (no AMP, no NxN inter), one slice per
+ * picture, cu_qp_delta with one quantisation group per CTB (the reference's rate-controlled streams), Log2ParMrgLevel 2, no PCM / transform skip / scaling lists / long-term pictures.
  */
 #include <stdlib.h>
 #include <string.h>
@@ -52,38 +52,41 @@ static void recon_block(rpic *r, int ci, int x0, int y0, int log2, int mode, int
     } else for (int y = 0; y < n; y++) memcpy(dst + (size_t)y * pitch, pred + y * n, (size_t)n);
 }
 
-/* ------------------------------------------------------------------ inter prediction (P slices) ---- */
-typedef struct { int16_t mvx, mvy; int ref_poc; int8_t ref_idx; uint8_t inter; } minfo;      /* per 4x4 luma block */
+/* ------------------------------------------------------------------ inter prediction ---- */
+typedef struct { int16_t mv[2][2]; int ref_poc[2]; int8_t ref_idx[2]; uint8_t pf; } minfo;   /* per 4x4 luma block; pf bit X = predFlagLX, 0 = intra / not decoded */
+typedef struct { int16_t mv[2][2]; int8_t ref_idx[2]; uint8_t pf; } mcand;
 typedef struct { int poc, valid; uint8_t *pix; minfo *mv; } dpic;                             /* a decoded picture: output samples + motion field */
 #define DPB_N 32            /* ring of decoded pictures (the reference keeps at most a GOP-of-8 anchor plus its neighbours) */
 typedef struct {
     const ora_parsed_stream *ps; const ora_parsed_pic *pp;
-    rpic r; minfo *mv; uint8_t *cbfy, *intra;     /* per 4x4: motion, "in a luma TB with coefficients", intra */
-    dpic *dpb; int poc;
+    rpic r; minfo *mv; uint8_t *cbfy, *intra, *qpy; /* per 4x4: motion, "in a luma TB with coefficients", intra, QpY of the CU */
+    dpic *dpb; int poc, no_backward;
 } rctx;
 
+static int list_n(const rctx *c, int X) { return X ? c->pp->n_list1 : c->pp->n_list0; }
+static int list_poc(const rctx *c, int X, int i) { return X ? c->pp->list1_poc[i] : c->pp->list0_poc[i]; }
 static const minfo *nb_motion(const rctx *c, int x, int y)
 {   /* 6.4.2: the prediction block covering (x, y) if it is decoded already and inter */
     if (!sample_avail(&c->r, x, y)) return NULL;
     const minfo *m = &c->mv[(y >> 2) * c->r.dw + (x >> 2)];
-    return m->inter ? m : NULL;
+    return m->pf ? m : NULL;
 }
 static const dpic *find_pic(const rctx *c, int poc) { for (int i = 0; i < DPB_N; i++) if (c->dpb[i].valid && c->dpb[i].poc == poc) return &c->dpb[i]; return NULL; }
 static int clip3i(int lo, int hi, int v) { return v < lo ? lo : (v > hi ? hi : v); }
-static void scale_mv(int16_t *mx, int16_t *my, int td, int tb)
+static void scale_mv(int16_t *mv, int td, int tb)
 {   /* 8.5.3.2.7 (8-179..8-183) */
     td = clip3i(-128, 127, td); tb = clip3i(-128, 127, tb);
     const int tx = (16384 + (abs(td) >> 1)) / td, ds = clip3i(-4096, 4095, (tb * tx + 32) >> 6);
-    const int vx = ds * *mx, vy = ds * *my;
-    *mx = (int16_t)clip3i(-32768, 32767, (vx < 0 ? -1 : 1) * ((abs(vx) + 127) >> 8));
-    *my = (int16_t)clip3i(-32768, 32767, (vy < 0 ? -1 : 1) * ((abs(vy) + 127) >> 8));
+    for (int k = 0; k < 2; k++) { const int v = ds * mv[k]; mv[k] = (int16_t)clip3i(-32768, 32767, (v < 0 ? -1 : 1) * ((abs(v) + 127) >> 8)); }
 }
-/* 8.5.3.2.8 / .9: temporal candidate for reference index `ref_idx` of list 0 */
-static int temporal_mv(const rctx *c, int xp, int yp, int w, int h, int ref_idx, int16_t *mx, int16_t *my)
+/* 8.5.3.2.8 / .9: temporal candidate for reference index `ref_idx` of list X */
+static int temporal_mv(const rctx *c, int xp, int yp, int w, int h, int X, int ref_idx, int16_t *mv)
 {
     const ora_parsed_pic *pp = c->pp;
-    if (!pp->tmvp || pp->col_ref_idx >= pp->n_list0) return 0;
-    const dpic *col = find_pic(c, pp->list0_poc[pp->col_ref_idx]);
+    if (!pp->tmvp) return 0;
+    const int cl = pp->st.slice_type == 0 && !pp->col_from_l0;                   /* the list the collocated picture comes from */
+    if (pp->col_ref_idx >= list_n(c, cl) || ref_idx >= list_n(c, X)) return 0;
+    const dpic *col = find_pic(c, list_poc(c, cl, pp->col_ref_idx));
     if (!col) return 0;
     const int l = c->ps->log2_ctb;
     for (int pass = 0; pass < 2; pass++) {
@@ -91,62 +94,109 @@ static int temporal_mv(const rctx *c, int xp, int yp, int w, int h, int ref_idx,
         if (pass == 0) { x = xp + w; y = yp + h; if ((yp >> l) != (y >> l) || y >= c->r.h || x >= c->r.w) continue; }
         else { x = xp + (w >> 1); y = yp + (h >> 1); }
         const minfo *m = &col->mv[(((y >> 4) << 4) >> 2) * c->r.dw + (((x >> 4) << 4) >> 2)];
-        if (!m->inter) continue;
-        *mx = m->mvx; *my = m->mvy;
-        const int cd = col->poc - m->ref_poc, td = c->poc - pp->list0_poc[ref_idx];
-        if (cd != td) scale_mv(mx, my, cd, td);
+        if (!m->pf) continue;
+        int lc;                                                                   /* which of the collocated block's vectors */
+        if (!(m->pf & 1)) lc = 1;
+        else if (!(m->pf & 2)) lc = 0;
+        else lc = c->no_backward ? X : pp->col_from_l0;
+        mv[0] = m->mv[lc][0]; mv[1] = m->mv[lc][1];
+        const int cd = col->poc - m->ref_poc[lc], td = c->poc - list_poc(c, X, ref_idx);
+        if (cd != td) scale_mv(mv, cd, td);
         return 1;
     }
     return 0;
 }
-typedef struct { int16_t mvx, mvy; int ref_idx; } mcand;
-static int same_motion(const minfo *a, const minfo *b) { return a->mvx == b->mvx && a->mvy == b->mvy && a->ref_idx == b->ref_idx; }
-/* 8.5.3.2.2 - .5 for a 2Nx2N prediction block of a P slice (Log2ParMrgLevel 2: no merge estimation regions) */
-static mcand merge_candidate(const rctx *c, int xp, int yp, int w, int h, int idx)
+static int same_motion(const minfo *a, const minfo *b)
 {
+    if (a->pf != b->pf) return 0;
+    for (int X = 0; X < 2; X++) if ((a->pf >> X) & 1) if (a->mv[X][0] != b->mv[X][0] || a->mv[X][1] != b->mv[X][1] || a->ref_idx[X] != b->ref_idx[X]) return 0;
+    return 1;
+}
+static mcand cand_of(const minfo *m) { mcand k; memcpy(k.mv, m->mv, sizeof(k.mv)); k.ref_idx[0] = m->ref_idx[0]; k.ref_idx[1] = m->ref_idx[1]; k.pf = m->pf; return k; }
+/* 8.5.3.2.2 - .5: merge candidate `idx` of the prediction block (xp, yp, w, h), partition part_idx of a CU with part mode `part` (Log2ParMrgLevel 2) */
+static mcand merge_candidate(const rctx *c, int xp, int yp, int w, int h, int part, int part_idx, int idx)
+{
+    const ora_parsed_pic *pp = c->pp;
+    const int is_b = pp->st.slice_type == 0, maxc = pp->max_merge;
     mcand list[6]; int n = 0;
-    const minfo *a1 = nb_motion(c, xp - 1, yp + h - 1), *b1 = nb_motion(c, xp + w - 1, yp - 1), *b0 = nb_motion(c, xp + w, yp - 1),
+    const minfo *a1 = nb_motion(c, xp - 1, yp + h - 1), *b1r = nb_motion(c, xp + w - 1, yp - 1), *b0 = nb_motion(c, xp + w, yp - 1),
                 *a0 = nb_motion(c, xp - 1, yp + h), *b2 = nb_motion(c, xp - 1, yp - 1);
+    if (part_idx == 1 && (part == 2 || part == 6 || part == 7)) a1 = NULL;       /* Nx2N, nLx2N, nRx2N: the first partition would make the CU 2Nx2N */
+    if (part_idx == 1 && (part == 1 || part == 4 || part == 5)) b1r = NULL;      /* 2NxN, 2NxnU, 2NxnD */
+    const minfo *b1 = b1r;
     if (b1 && a1 && same_motion(b1, a1)) b1 = NULL;
-    if (b0 && nb_motion(c, xp + w - 1, yp - 1) && same_motion(b0, nb_motion(c, xp + w - 1, yp - 1))) b0 = NULL;
+    if (b0 && b1r && same_motion(b0, b1r)) b0 = NULL;
     if (a0 && a1 && same_motion(a0, a1)) a0 = NULL;
-    if (b2 && ((a1 && same_motion(b2, a1)) || (nb_motion(c, xp + w - 1, yp - 1) && same_motion(b2, nb_motion(c, xp + w - 1, yp - 1))))) b2 = NULL;
+    if (b2 && ((a1 && same_motion(b2, a1)) || (b1r && same_motion(b2, b1r)))) b2 = NULL;
     if (b2 && (a1 != NULL) + (b1 != NULL) + (b0 != NULL) + (a0 != NULL) == 4) b2 = NULL;
     const minfo *sp[5] = {a1, b1, b0, a0, b2};
-    for (int k = 0; k < 5; k++) if (sp[k]) { list[n].mvx = sp[k]->mvx; list[n].mvy = sp[k]->mvy; list[n].ref_idx = sp[k]->ref_idx; n++; }
-    if (n < c->pp->max_merge) { int16_t mx, my; if (temporal_mv(c, xp, yp, w, h, 0, &mx, &my)) { list[n].mvx = mx; list[n].mvy = my; list[n].ref_idx = 0; n++; } }
-    mcand z = {0, 0, 0};
-    if (idx < n && idx < c->pp->max_merge) return list[idx];
-    const int zi = idx - (n < c->pp->max_merge ? n : c->pp->max_merge);       /* zero candidates: reference index counts up, then stays 0 */
-    z.ref_idx = zi < c->pp->n_list0 ? zi : 0;
-    return z;
+    for (int k = 0; k < 5; k++) if (sp[k]) list[n++] = cand_of(sp[k]);
+    if (n < maxc) {
+        mcand t; memset(&t, 0, sizeof(t));
+        if (temporal_mv(c, xp, yp, w, h, 0, 0, t.mv[0])) t.pf |= 1;
+        if (is_b && temporal_mv(c, xp, yp, w, h, 1, 0, t.mv[1])) t.pf |= 2;
+        if (t.pf) list[n++] = t;
+    }
+    if (is_b && n > 1 && n < maxc) {                                             /* 8.5.3.2.4: combined bi-predictive candidates */
+        static const uint8_t l0i[12] = {0, 1, 0, 2, 1, 2, 0, 3, 1, 3, 2, 3}, l1i[12] = {1, 0, 2, 0, 2, 1, 3, 0, 3, 1, 3, 2};
+        const int norig = n;
+        for (int k = 0; k < norig * (norig - 1) && n < maxc; k++) {
+            const mcand *p0 = &list[l0i[k]], *p1 = &list[l1i[k]];
+            if (!(p0->pf & 1) || !(p1->pf & 2)) continue;
+            if (list_poc(c, 0, p0->ref_idx[0]) == list_poc(c, 1, p1->ref_idx[1]) && p0->mv[0][0] == p1->mv[1][0] && p0->mv[0][1] == p1->mv[1][1]) continue;
+            mcand m; m.pf = 3; m.mv[0][0] = p0->mv[0][0]; m.mv[0][1] = p0->mv[0][1]; m.ref_idx[0] = p0->ref_idx[0];
+            m.mv[1][0] = p1->mv[1][0]; m.mv[1][1] = p1->mv[1][1]; m.ref_idx[1] = p1->ref_idx[1];
+            list[n++] = m;
+        }
+    }
+    mcand out;
+    if (idx < n) out = list[idx];
+    else {                                                                       /* 8.5.3.2.5: zero candidates, the reference index counts up and then stays 0 */
+        const int nref = is_b ? (pp->n_list0 < pp->n_list1 ? pp->n_list0 : pp->n_list1) : pp->n_list0, zi = idx - n;
+        memset(&out, 0, sizeof(out));
+        out.pf = is_b ? 3 : 1; out.ref_idx[0] = (int8_t)(zi < nref ? zi : 0); out.ref_idx[1] = is_b ? out.ref_idx[0] : -1;
+    }
+    if (out.pf == 3 && w + h == 12) { out.pf = 1; out.ref_idx[1] = -1; }          /* 8x4 / 4x8 blocks are never bi-predicted */
+    return out;
 }
-/* 8.5.3.2.6 / .7: motion vector predictor of list 0 for reference index ref_idx */
-static void amvp_predictor(const rctx *c, int xp, int yp, int w, int h, int ref_idx, int mvp_idx, int16_t *px, int16_t *py)
+/* 8.5.3.2.6 / .7: motion vector predictor of list X for reference index ref_idx */
+static void amvp_predictor(const rctx *c, int xp, int yp, int w, int h, int X, int ref_idx, int mvp_idx, int16_t *pred)
 {
-    const int target = c->pp->list0_poc[ref_idx];
+    const int target = list_poc(c, X, ref_idx), Y = !X;
     const minfo *A[2] = {nb_motion(c, xp - 1, yp + h), nb_motion(c, xp - 1, yp + h - 1)};
     const minfo *B[3] = {nb_motion(c, xp + w, yp - 1), nb_motion(c, xp + w - 1, yp - 1), nb_motion(c, xp - 1, yp - 1)};
-    /* isScaledFlag looks at the AVAILABILITY of A0 / A1 (6.4.2: decoded and not intra) */
-    const int scaled_flag = A[0] != NULL || A[1] != NULL;
-    int have_a = 0, have_b = 0; int16_t ax = 0, ay = 0, bx = 0, by = 0;
-    for (int k = 0; k < 2 && !have_a; k++) if (A[k] && A[k]->ref_poc == target) { ax = A[k]->mvx; ay = A[k]->mvy; have_a = 1; }
-    for (int k = 0; k < 2 && !have_a; k++) if (A[k]) { ax = A[k]->mvx; ay = A[k]->mvy; have_a = 1; if (A[k]->ref_poc != target) scale_mv(&ax, &ay, c->poc - A[k]->ref_poc, c->poc - target); }
-    for (int k = 0; k < 3 && !have_b; k++) if (B[k] && B[k]->ref_poc == target) { bx = B[k]->mvx; by = B[k]->mvy; have_b = 1; }
-    if (!scaled_flag && have_b) { ax = bx; ay = by; have_a = 1; }
+    const int scaled_flag = A[0] != NULL || A[1] != NULL;                         /* availability of A0 / A1 (6.4.2: decoded and not intra) */
+    int have_a = 0, have_b = 0; int16_t a[2] = {0, 0}, b[2] = {0, 0};
+#define SAME(m, L) (((m)->pf >> (L)) & 1 && (m)->ref_poc[L] == target)
+#define TAKE(dst, m, L) { (dst)[0] = (m)->mv[L][0]; (dst)[1] = (m)->mv[L][1]; }
+    for (int k = 0; k < 2 && !have_a; k++) if (A[k]) { if (SAME(A[k], X)) { TAKE(a, A[k], X) have_a = 1; } else if (SAME(A[k], Y)) { TAKE(a, A[k], Y) have_a = 1; } }
+    for (int k = 0; k < 2 && !have_a; k++) if (A[k]) {
+        const int L = ((A[k]->pf >> X) & 1) ? X : Y;
+        TAKE(a, A[k], L) have_a = 1;
+        if (A[k]->ref_poc[L] != target) scale_mv(a, c->poc - A[k]->ref_poc[L], c->poc - target);
+    }
+    for (int k = 0; k < 3 && !have_b; k++) if (B[k]) { if (SAME(B[k], X)) { TAKE(b, B[k], X) have_b = 1; } else if (SAME(B[k], Y)) { TAKE(b, B[k], Y) have_b = 1; } }
+    if (!scaled_flag && have_b) { a[0] = b[0]; a[1] = b[1]; have_a = 1; }
     if (!scaled_flag) {
         have_b = 0;
-        for (int k = 0; k < 3 && !have_b; k++) if (B[k]) { bx = B[k]->mvx; by = B[k]->mvy; have_b = 1; if (B[k]->ref_poc != target) scale_mv(&bx, &by, c->poc - B[k]->ref_poc, c->poc - target); }
+        for (int k = 0; k < 3 && !have_b; k++) if (B[k]) {
+            const int L = ((B[k]->pf >> X) & 1) ? X : Y;
+            TAKE(b, B[k], L) have_b = 1;
+            if (B[k]->ref_poc[L] != target) scale_mv(b, c->poc - B[k]->ref_poc[L], c->poc - target);
+        }
     }
-    int16_t lx[3], ly[3]; int n = 0;
-    if (have_a) { lx[n] = ax; ly[n] = ay; n++; }
-    if (have_b && !(have_a && ax == bx && ay == by)) { lx[n] = bx; ly[n] = by; n++; }
-    if (n < 2) { int16_t tx, ty; if (temporal_mv(c, xp, yp, w, h, ref_idx, &tx, &ty)) { lx[n] = tx; ly[n] = ty; n++; } }
-    while (n < 2) { lx[n] = 0; ly[n] = 0; n++; }
-    *px = lx[mvp_idx]; *py = ly[mvp_idx];
+#undef SAME
+#undef TAKE
+    int16_t l[3][2]; int n = 0;
+    if (have_a) { l[n][0] = a[0]; l[n][1] = a[1]; n++; }
+    if (have_b && !(have_a && a[0] == b[0] && a[1] == b[1])) { l[n][0] = b[0]; l[n][1] = b[1]; n++; }
+    if (n < 2) { int16_t t[2]; if (temporal_mv(c, xp, yp, w, h, X, ref_idx, t)) { l[n][0] = t[0]; l[n][1] = t[1]; n++; } }
+    while (n < 2) { l[n][0] = 0; l[n][1] = 0; n++; }
+    pred[0] = l[mvp_idx][0]; pred[1] = l[mvp_idx][1];
 }
-/* motion compensation of one block from a decoded picture, reference samples clamped to the picture (8.5.3.3.3) */
-static void mc_block(const dpic *ref, int W, int H, int ci, int x0, int y0, int w, int h, int mvx, int mvy, uint8_t *dst, int ds)
+/* motion compensation of one block from a decoded picture, reference samples clamped to the picture (8.5.3.3.3); dst8 (final samples) or
+ * dst16 (14-bit intermediate for bi-prediction) */
+static void mc_block(const dpic *ref, int W, int H, int ci, int x0, int y0, int w, int h, int mvx, int mvy, uint8_t *dst8, int16_t *dst16, int ds)
 {
     const int sh = ci ? 1 : 0, pw = W >> sh, ph = H >> sh, taps = ci ? 4 : 8, before = taps / 2 - 1, fb = ci ? 3 : 2;
     const uint8_t *plane = ref->pix + (ci == 0 ? 0 : (ci == 1 ? (size_t)W * H : (size_t)W * H + (size_t)W * H / 4));
@@ -155,8 +205,51 @@ static void mc_block(const dpic *ref, int W, int H, int ci, int x0, int y0, int 
     for (int y = 0; y < th; y++) for (int x = 0; x < tw; x++)
         tmp[y * tw + x] = plane[(size_t)clip3i(0, ph - 1, iy - before + y) * pw + clip3i(0, pw - 1, ix - before + x)];
     const int mask = (1 << fb) - 1;
-    if (ci) ora_mc_chroma(dst, ds, tmp + before * tw + before, tw, w, h, mvx & mask, mvy & mask);
-    else ora_mc_luma(dst, ds, tmp + before * tw + before, tw, w, h, mvx & mask, mvy & mask);
+    const uint8_t *org = tmp + before * tw + before;
+    if (dst8) { if (ci) ora_mc_chroma(dst8, ds, org, tw, w, h, mvx & mask, mvy & mask); else ora_mc_luma(dst8, ds, org, tw, w, h, mvx & mask, mvy & mask); }
+    else { if (ci) ora_mc_chroma_16(dst16, ds, org, tw, w, h, mvx & mask, mvy & mask); else ora_mc_luma_16(dst16, ds, org, tw, w, h, mvx & mask, mvy & mask); }
+}
+/* prediction of one block into the picture being reconstructed */
+static int predict_pu(rctx *c, const mcand *m, int x, int y, int w, int h)
+{
+    const int W = c->r.w, H = c->r.h;
+    const dpic *ref[2] = {NULL, NULL};
+    for (int X = 0; X < 2; X++) if ((m->pf >> X) & 1) { if (m->ref_idx[X] < 0 || m->ref_idx[X] >= list_n(c, X)) return -7; ref[X] = find_pic(c, list_poc(c, X, m->ref_idx[X])); if (!ref[X]) return -8; }
+    for (int ci = 0; ci < 3; ci++) {
+        const int sh = ci ? 1 : 0, pw = W >> sh, bx = x >> sh, by = y >> sh, bw = w >> sh, bh = h >> sh;
+        uint8_t *dst = c->r.p[ci] + (size_t)by * pw + bx;
+        if (m->pf == 3) {
+            int16_t p0[64 * 64], p1[64 * 64];
+            mc_block(ref[0], W, H, ci, bx, by, bw, bh, m->mv[0][0], m->mv[0][1], NULL, p0, bw);
+            mc_block(ref[1], W, H, ci, bx, by, bw, bh, m->mv[1][0], m->mv[1][1], NULL, p1, bw);
+            uint8_t tmp[64 * 64];
+            ora_weighted_bi(tmp, bw, p0, p1, bw, bw, bh);
+            for (int r = 0; r < bh; r++) memcpy(dst + (size_t)r * pw, tmp + r * bw, (size_t)bw);
+        } else {
+            const int X = m->pf == 2;
+            mc_block(ref[X], W, H, ci, bx, by, bw, bh, m->mv[X][0], m->mv[X][1], dst, NULL, pw);
+        }
+    }
+    return 0;
+}
+/* 8.7.2.4, the motion part: 1 when the two blocks' motion differs enough for an edge to show */
+static int motion_bs(const minfo *p, const minfo *q)
+{
+    const int np = (p->pf & 1) + (p->pf >> 1), nq = (q->pf & 1) + (q->pf >> 1);
+    if (np != nq) return 1;
+#define FAR(a, b) (abs((a)[0] - (b)[0]) >= 4 || abs((a)[1] - (b)[1]) >= 4)
+    if (np == 1) {
+        const int lp = p->pf == 2, lq = q->pf == 2;
+        return p->ref_poc[lp] != q->ref_poc[lq] || FAR(p->mv[lp], q->mv[lq]);
+    }
+    const int p0 = p->ref_poc[0], p1 = p->ref_poc[1], q0 = q->ref_poc[0], q1 = q->ref_poc[1];
+    if (!((p0 == q0 && p1 == q1) || (p0 == q1 && p1 == q0))) return 1;           /* different reference pictures */
+    if (p0 != p1) {                                                              /* two different pictures: compare the vectors that point into the same one */
+        if (p0 == q0) return FAR(p->mv[0], q->mv[0]) || FAR(p->mv[1], q->mv[1]);
+        return FAR(p->mv[0], q->mv[1]) || FAR(p->mv[1], q->mv[0]);
+    }
+    return (FAR(p->mv[0], q->mv[0]) || FAR(p->mv[1], q->mv[1])) && (FAR(p->mv[0], q->mv[1]) || FAR(p->mv[1], q->mv[0]));
+#undef FAR
 }
 
 /* one picture (I or P slice) into c->r (pre-filter reconstruction, then deblocked in place); `out` receives the SAO output */
@@ -164,12 +257,13 @@ static int replay_picture(rctx *c, uint8_t *out)
 {
     const ora_parsed_stream *ps = c->ps; const ora_parsed_pic *pp = c->pp;
     if (!pp->ok) return -2;
-    if (pp->any_qp_delta) return -3;
-    if (pp->st.slice_type == 0) return -5;                                      /* B slices: not covered */
+    if (pp->any_qp_delta && pp->qg_depth != 0) return -3;                       /* cu_qp_delta with one quantisation group per CTB only (the reference's -rc 3) */
+    c->no_backward = 1;                                                         /* NoBackwardPredFlag: no reference picture follows the current one in output order */
+    for (int X = 0; X < 2; X++) for (int i = 0; i < list_n(c, X); i++) if (list_poc(c, X, i) > c->poc) c->no_backward = 0;
     rpic *r = &c->r;
     const int W = r->w, H = r->h, qp = pp->st.qp, dw = r->dw;
     const size_t ysz = (size_t)W * H;
-    const int qpc[3] = {qp, ora_chroma_qp[clip3i(0, 57, qp + pp->cb_qp_off)], ora_chroma_qp[clip3i(0, 57, qp + pp->cr_qp_off)]};
+    int qpc[3] = {qp, 0, 0}, qp_prev = qp, cur_ctu = -1, qg_delta = 0;
     memset(r->done, 0, (size_t)dw * ((H + 3) >> 2)); memset(c->cbfy, 0, (size_t)dw * ((H + 3) >> 2)); memset(c->intra, 0, (size_t)dw * ((H + 3) >> 2));
     memset(c->mv, 0, sizeof(minfo) * (size_t)dw * ((H + 3) >> 2));
     /* block edges on the 8x8 grid, one flag per 4-sample segment: vedge[(y/4) * ew + x/8], hedge[(y/8) * dw + x/4] */
@@ -179,26 +273,46 @@ static int replay_picture(rctx *c, uint8_t *out)
     for (size_t k = 0; k < pp->n_cus && !rc; k++) {
         const ora_cu_rec *cu = &pp->cus[k];
         const int S = 1 << cu->log2, half = S >> 1;
+        {   /* 8.6.1 with one quantisation group per CTB: the prediction is the QpY of the last CU of the previous CTB (the slice QP at first); a
+             * coded cu_qp_delta applies to its CU and to the CUs after it in the group */
+            const int l = ps->log2_ctb, ctu = (cu->y >> l) * ((W + (1 << l) - 1) >> l) + (cu->x >> l);
+            if (ctu != cur_ctu) { if (cur_ctu >= 0) qp_prev = qpc[0]; cur_ctu = ctu; qg_delta = 0; }
+            for (uint32_t q = 0; q < cu->n_tu; q++) if (pp->tus[cu->first_tu + q].qp_delta) qg_delta = pp->tus[cu->first_tu + q].qp_delta;
+            qpc[0] = (qp_prev + qg_delta + 52) % 52;
+            qpc[1] = ora_chroma_qp[clip3i(0, 57, qpc[0] + pp->cb_qp_off)]; qpc[2] = ora_chroma_qp[clip3i(0, 57, qpc[0] + pp->cr_qp_off)];
+            for (int y = cu->y >> 2; y < ((cu->y + S) >> 2) && y < ((H + 3) >> 2); y++) for (int x = cu->x >> 2; x < ((cu->x + S) >> 2) && x < dw; x++) c->qpy[y * dw + x] = (uint8_t)qpc[0];
+        }
         if (cu->pred_mode == 0) {
-            if (cu->part_mode != 0) { rc = -6; break; }                         /* only 2Nx2N inter prediction blocks */
-            mcand m;
-            if (cu->merge[0]) m = merge_candidate(c, cu->x, cu->y, S, S, cu->merge_idx[0]);
-            else {
-                int16_t px, py;
-                m.ref_idx = cu->ref_idx[0][0];
-                if (m.ref_idx >= pp->n_list0) { rc = -7; break; }
-                amvp_predictor(c, cu->x, cu->y, S, S, m.ref_idx, cu->mvp[0][0], &px, &py);
-                m.mvx = (int16_t)(px + cu->mvd[0][0][0]); m.mvy = (int16_t)(py + cu->mvd[0][0][1]);
+            if (cu->part_mode > 2) { rc = -6; break; }                          /* 2Nx2N, 2NxN, Nx2N (the reference codes no AMP / NxN inter blocks) */
+            const int npu = cu->part_mode ? 2 : 1;
+            for (int k = 0; k < npu && !rc; k++) {
+                const int pw_ = cu->part_mode == 2 ? half : S, ph_ = cu->part_mode == 1 ? half : S;
+                const int px_ = cu->x + (cu->part_mode == 2 ? k * half : 0), py_ = cu->y + (cu->part_mode == 1 ? k * half : 0);
+                mcand m;
+                if (cu->merge[k]) m = merge_candidate(c, px_, py_, pw_, ph_, cu->part_mode, k, cu->merge_idx[k]);
+                else {
+                    memset(&m, 0, sizeof(m));
+                    m.pf = pp->st.slice_type == 0 ? cu->inter_dir[k] : 1; m.ref_idx[0] = m.ref_idx[1] = -1;
+                    for (int X = 0; X < 2 && !rc; X++) if ((m.pf >> X) & 1) {
+                        int16_t pred[2];
+                        m.ref_idx[X] = (int8_t)cu->ref_idx[k][X];
+                        if (m.ref_idx[X] >= list_n(c, X)) { rc = -7; break; }
+                        amvp_predictor(c, px_, py_, pw_, ph_, X, m.ref_idx[X], cu->mvp[k][X], pred);
+                        m.mv[X][0] = (int16_t)(pred[0] + cu->mvd[k][X][0]); m.mv[X][1] = (int16_t)(pred[1] + cu->mvd[k][X][1]);
+                    }
+                }
+                if (!rc) rc = predict_pu(c, &m, px_, py_, pw_, ph_);
+                if (rc) break;
+                for (int y = py_ >> 2; y < ((py_ + ph_) >> 2) && y < ((H + 3) >> 2); y++) for (int x = px_ >> 2; x < ((px_ + pw_) >> 2) && x < dw; x++) {
+                    minfo *mi = &c->mv[y * dw + x]; memset(mi, 0, sizeof(*mi)); mi->pf = m.pf;
+                    for (int X = 0; X < 2; X++) if ((m.pf >> X) & 1) { mi->mv[X][0] = m.mv[X][0]; mi->mv[X][1] = m.mv[X][1]; mi->ref_idx[X] = m.ref_idx[X]; mi->ref_poc[X] = list_poc(c, X, m.ref_idx[X]); }
+                    r->done[y * dw + x] = 1;
+                }
+                /* the boundary between the two prediction blocks of a CU is a prediction edge */
+                if (k == 1 && cu->part_mode == 2 && (px_ & 7) == 0) for (int y = py_ >> 2; y < ((py_ + ph_) >> 2); y++) vedge[y * ew + (px_ >> 3)] |= 1;
+                if (k == 1 && cu->part_mode == 1 && (py_ & 7) == 0) for (int x = px_ >> 2; x < ((px_ + pw_) >> 2); x++) hedge[(py_ >> 3) * dw + x] |= 1;
             }
-            if (m.ref_idx >= pp->n_list0) { rc = -7; break; }
-            const dpic *ref = find_pic(c, pp->list0_poc[m.ref_idx]);
-            if (!ref) { rc = -8; break; }
-            mc_block(ref, W, H, 0, cu->x, cu->y, S, S, m.mvx, m.mvy, r->p[0] + (size_t)cu->y * W + cu->x, W);
-            for (int ci = 1; ci < 3; ci++) mc_block(ref, W, H, ci, cu->x >> 1, cu->y >> 1, half, half, m.mvx, m.mvy, r->p[ci] + (size_t)(cu->y >> 1) * (W >> 1) + (cu->x >> 1), W >> 1);
-            for (int y = cu->y >> 2; y < ((cu->y + S) >> 2) && y < ((H + 3) >> 2); y++) for (int x = cu->x >> 2; x < ((cu->x + S) >> 2) && x < dw; x++) {
-                minfo *mi = &c->mv[y * dw + x]; mi->mvx = m.mvx; mi->mvy = m.mvy; mi->ref_idx = (int8_t)m.ref_idx; mi->ref_poc = pp->list0_poc[m.ref_idx]; mi->inter = 1;
-                r->done[y * dw + x] = 1;
-            }
+            if (rc) break;
         } else
             for (int y = cu->y >> 2; y < ((cu->y + S) >> 2) && y < ((H + 3) >> 2); y++) for (int x = cu->x >> 2; x < ((cu->x + S) >> 2) && x < dw; x++) c->intra[y * dw + x] = 1;
         /* the CU boundary is a prediction-block edge AND a transform-block edge whatever its transform tree looks like (8.7.2.3 starts from the coding block) */
@@ -239,10 +353,6 @@ static int replay_picture(rctx *c, uint8_t *out)
     }
     /* 8.7.2: all vertical edges of the picture, then all horizontal ones */
     if (!rc && !pp->dbk_disabled) {
-        const int beta = ora_beta_table[clip3i(0, 51, qp + 2 * pp->beta_off_div2)];
-        int tcc[3] = {0, 0, 0};
-        for (int ci = 1; ci < 3; ci++)             /* 8.7.2.5.5: QpC from the luma QP + the chroma offset, Bs 2 */
-            tcc[ci] = ora_tc_table[clip3i(0, 53, ora_chroma_qp[clip3i(0, 57, qp + (ci == 1 ? pp->cb_qp_off : pp->cr_qp_off))] + 2 + 2 * pp->tc_off_div2)];
         for (int dir = 0; dir < 2; dir++)
             for (int e = 8; e < (dir ? H : W); e += 8)
                 for (int s = 0; s < (dir ? W : H); s += 4) {
@@ -253,15 +363,16 @@ static int replay_picture(rctx *c, uint8_t *out)
                     int bs = 0;
                     if (c->intra[iq] || c->intra[ip]) bs = 2;                   /* 8.7.2.4 */
                     else if ((fl & 2) && (c->cbfy[iq] || c->cbfy[ip])) bs = 1;
-                    else {
-                        const minfo *mq = &c->mv[iq], *mp = &c->mv[ip];
-                        if (mq->ref_poc != mp->ref_poc || abs(mq->mvx - mp->mvx) >= 4 || abs(mq->mvy - mp->mvy) >= 4) bs = 1;
-                    }
+                    else bs = motion_bs(&c->mv[ip], &c->mv[iq]);
                     if (!bs) continue;
-                    const int tc = ora_tc_table[clip3i(0, 53, qp + 2 * (bs - 1) + 2 * pp->tc_off_div2)];
+                    const int ql = (c->qpy[ip] + c->qpy[iq] + 1) >> 1;           /* 8.7.2.5.3: the edge's QP is the mean of the two CUs' */
+                    const int beta = ora_beta_table[clip3i(0, 51, ql + 2 * pp->beta_off_div2)];
+                    const int tc = ora_tc_table[clip3i(0, 53, ql + 2 * (bs - 1) + 2 * pp->tc_off_div2)];
                     ora_deblock_luma_seg(r->p[0] + (size_t)yq * W + xq, dir ? W : 1, dir ? 1 : W, beta, tc);
-                    if (bs == 2 && !(e & 8)) for (int ci = 1; ci < 3; ci++)
-                        ora_deblock_chroma_seg(r->p[ci] + (size_t)(yq >> 1) * (W >> 1) + (xq >> 1), dir ? (W >> 1) : 1, dir ? 1 : (W >> 1), tcc[ci], 2);
+                    if (bs == 2 && !(e & 8)) for (int ci = 1; ci < 3; ci++) {    /* 8.7.2.5.5: QpC from that mean + the chroma offset */
+                        const int tcc = ora_tc_table[clip3i(0, 53, ora_chroma_qp[clip3i(0, 57, ql + (ci == 1 ? pp->cb_qp_off : pp->cr_qp_off))] + 2 + 2 * pp->tc_off_div2)];
+                        ora_deblock_chroma_seg(r->p[ci] + (size_t)(yq >> 1) * (W >> 1) + (xq >> 1), dir ? (W >> 1) : 1, dir ? 1 : (W >> 1), tcc, 2);
+                    }
                 }
     }
     /* 8.7.3: SAO reads the deblocked picture and writes the output picture */
@@ -294,7 +405,7 @@ int ora_replay_pictures(const ora_parsed_stream *ps, int first, int count, uint8
     c.ps = ps; c.r.w = W; c.r.h = H; c.r.dw = dw;
     uint8_t *pre = (uint8_t *)calloc(fsz, 1);
     c.r.p[0] = pre; c.r.p[1] = pre + ysz; c.r.p[2] = pre + ysz + ysz / 4;
-    c.r.done = (uint8_t *)calloc((size_t)nb, 1); c.cbfy = (uint8_t *)calloc((size_t)nb, 1); c.intra = (uint8_t *)calloc((size_t)nb, 1);
+    c.r.done = (uint8_t *)calloc((size_t)nb, 1); c.cbfy = (uint8_t *)calloc((size_t)nb, 1); c.intra = (uint8_t *)calloc((size_t)nb, 1); c.qpy = (uint8_t *)calloc((size_t)nb, 1);
     c.mv = (minfo *)calloc((size_t)nb, sizeof(minfo));
     dpic dpb[DPB_N]; memset(dpb, 0, sizeof(dpb)); c.dpb = dpb;
     int rc = 0, slot = 0;
@@ -312,7 +423,7 @@ int ora_replay_pictures(const ora_parsed_stream *ps, int first, int count, uint8
         memcpy(d->pix, dst, fsz); memcpy(d->mv, c.mv, sizeof(minfo) * (size_t)nb); d->poc = c.poc; d->valid = 1;
     }
     for (int k = 0; k < DPB_N; k++) { free(dpb[k].pix); free(dpb[k].mv); }
-    free(scratch); free(pre); free(c.r.done); free(c.cbfy); free(c.intra); free(c.mv);
+    free(scratch); free(pre); free(c.r.done); free(c.cbfy); free(c.intra); free(c.qpy); free(c.mv);
     return rc;
 }
 

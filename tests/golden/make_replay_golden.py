@@ -50,7 +50,7 @@ for name, yuv, w, h, preset, qp, frame in CASES:
         print(name, len(stream), "bytes")
 json.dump(out, open(os.path.join(HERE, "ref_intra_streams.json"), "w"), indent=0)
 
-# P-only sequences (-bframes 0): every picture's MD5 as the reference decoder writes it
+# P-only sequences (-bframes 0): every picture's MD5 as the reference decoder writes it (display order)
 SEQS = [("nat320_veryfast_qp27_6f", nat, 320, 240, "veryfast", 27, 6), ("nat320_slow_qp32_6f", nat, 320, 240, "slow", 32, 6), ("nat320_ultrafast_qp22_6f", nat, 320, 240, "ultrafast", 22, 6)]
 if os.path.exists(big):
     n = 8
@@ -65,13 +65,20 @@ if os.path.exists(big):
         return np.concatenate(o)
     SEQS += [("crop720_veryfast_qp27_8f", crop_seq(448, 232, 384, 256), 384, 256, "veryfast", 27, 8), ("crop720_medium_qp30_8f", crop_seq(640, 300, 320, 192), 320, 192, "medium", 30, 8)]
 out = []
-for name, yuv, w, h, preset, qp, nf in SEQS:
+# ... and sequences with the reference's DEFAULT picture structure (hierarchical B pictures, decoding order != display order)
+SEQS = [(a, b, c, d, e, f, g, ("-bframes", "0")) for a, b, c, d, e, f, g in SEQS]
+SEQS += [("nat320_veryfast_qp27_6f_B", nat, 320, 240, "veryfast", 27, 6, ()), ("nat320_placebo_qp30_6f_B", nat, 320, 240, "placebo", 30, 6, ()),
+         # rate-controlled: cu_qp_delta per CTB (the -rc 0 -qp arguments that follow are overridden by these)
+         ("nat320_fast_crf26_6f_B", nat, 320, 240, "fast", 27, 6, ("-rc", "3", "-crf", "26")), ("nat320_veryfast_abr200_6f_B", nat, 320, 240, "veryfast", 27, 6, ("-rc", "2", "-br", "200"))]
+if os.path.exists(big):
+    SEQS += [("crop720_medium_qp27_8f_B", crop_seq(448, 232, 384, 256), 384, 256, "medium", 27, 8, ()), ("crop720_veryslow_qp32_8f_B", crop_seq(640, 300, 320, 192), 320, 192, "veryslow", 32, 8, ())]
+for name, yuv, w, h, preset, qp, nf, extra in SEQS:
     fs = w * h * 3 // 2
     with tempfile.TemporaryDirectory() as d:
         clip, bs, dec = os.path.join(d, "i.yuv"), os.path.join(d, "o.265"), os.path.join(d, "d.yuv")
         open(clip, "wb").write(yuv[:nf * fs].tobytes())
-        subprocess.run([os.path.join(REF, "appencoder"), "-i", clip, "-wdt", str(w), "-hgt", str(h), "-fr", "15", "-preset", preset, "-rc", "0", "-qp", str(qp),
-                        "-iper", "128", "-bframes", "0", "-frms", str(nf), "-threads", "1", "-b", bs], capture_output=True, check=True)
+        subprocess.run([os.path.join(REF, "appencoder"), "-i", clip, "-wdt", str(w), "-hgt", str(h), "-fr", "15", "-preset", preset, *(("-rc", "0", "-qp", str(qp)) if "-rc" not in extra else ()),
+                        "-iper", "128", *extra, "-frms", str(nf), "-threads", "1", "-b", bs], capture_output=True, check=True)
         subprocess.run([os.path.join(REF, "appdecoder"), "-b", bs, "-o", dec, "-threads", "1"], capture_output=True, check=True)
         stream, decoded = open(bs, "rb").read(), open(dec, "rb").read()
         assert len(decoded) == fs * nf

@@ -9,6 +9,8 @@ import json
 import os
 import subprocess
 
+import sys
+
 import numpy as np
 import pytest
 
@@ -16,6 +18,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CASES = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_intra_streams.json")))
 SEQS = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_p_streams.json")))
 DEC = os.path.join(ROOT, "oracle", "_ref", "appdecoder")
+if os.path.join(ROOT, "tools") not in sys.path:
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+import stream_stats  # noqa: E402  (the ctypes mirror of the parser's per-picture record)
 
 
 def _oracle():
@@ -27,6 +32,8 @@ def _oracle():
         f.argtypes = [C.c_void_p]
     O.ora_replay_intra_picture.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     O.ora_replay_pictures.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    O.ora_parse_pic_stats.restype = C.POINTER(stream_stats.PicStats)
+    O.ora_parse_pic_stats.argtypes = [C.c_void_p, C.c_int]
     return O
 
 
@@ -53,8 +60,10 @@ def test_reference_intra_picture_is_recreated_from_its_parsed_decisions(case, tm
 
 @pytest.mark.parametrize("seq", SEQS, ids=[c["name"] for c in SEQS])
 def test_reference_p_sequence_is_recreated_from_its_parsed_decisions(seq, tmp_path):
-    """-bframes 0 streams of the reference encoder: skip / merge (spatial + temporal candidates) / AMVP with several reference pictures,
-    8x8..64x64 inter CUs, intra CUs inside P pictures, residuals, deblocking strengths from vectors and coefficients, SAO"""
+    """-bframes 0 and default-GOP (hierarchical B) streams of the reference encoder: skip / merge (spatial, temporal, combined bi-predictive
+    candidates) / AMVP over several reference pictures in both lists, 8x8..64x64 inter CUs incl. 2NxN / Nx2N partitions, bi-prediction, intra
+    CUs inside inter pictures, residuals, deblocking strengths from vectors and coefficients, SAO.  The replay runs in decoding order; the
+    decoder writes display order."""
     O = _oracle()
     bs = np.frombuffer(base64.b64decode(seq["stream_b64"]), np.uint8).copy()
     ps = O.ora_parse_stream(bs.ctypes.data, bs.size)
@@ -68,8 +77,10 @@ def test_reference_p_sequence_is_recreated_from_its_parsed_decisions(seq, tmp_pa
         # a later picture on its own: the pictures it references are replayed behind the scenes
         one = np.zeros(fs, np.uint8)
         assert O.ora_replay_pictures(ps, n - 1, 1, one.ctypes.data) == 0 and np.array_equal(one, out[(n - 1) * fs:])
+        pocs = [O.ora_parse_pic_stats(ps, i).contents.poc for i in range(n)]
     finally:
         O.ora_parse_free(ps)
+    out = np.concatenate([out[i * fs:(i + 1) * fs] for i in sorted(range(n), key=lambda i: pocs[i])])          # display order
     assert [hashlib.md5(out[f * fs:(f + 1) * fs].tobytes()).hexdigest() for f in range(n)] == seq["decoded_md5"]
     if os.path.exists(DEC):
         p, o = tmp_path / "s.265", tmp_path / "d.yuv"
