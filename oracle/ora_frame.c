@@ -161,6 +161,21 @@ static int code_tb(const ora_cfg *cfg, int qp, int intra_slice, int log2, int is
     return nnz != 0;
 }
 
+/* The levels OUR transform-block coder makes of (src, pred): forward transform, quantiser, sign-data hiding -- no RD zero-out.  ora_replay.c
+ * holds them against the levels the reference encoder coded for the same block (its prediction re-created from its own stream).
+ * intra_mode < 0: inter block (diagonal scan, DCT). */
+int ora_tb_levels(int qp, int intra_slice, int log2, int is_luma, int intra_mode, int sign_hiding, const uint8_t *src, int ss, const uint8_t *pred, int ps, int16_t *lev)
+{
+    int n = 1 << log2;
+    int16_t res[1024], coef[1024], du[1024];
+    build_scans();
+    ora_residual(res, src, pred, ss, ps, n);
+    ora_fdct(res, coef, n, n, log2, intra_mode >= 0 && is_luma && log2 == 2);
+    int nnz = ora_quant(coef, lev, n, qp, log2, intra_slice, du);
+    if (nnz && sign_hiding) nnz = ora_sign_hide(coef, lev, du, n, log2, intra_mode >= 0 ? intra_scan(log2, is_luma, intra_mode) : scan_tb[log2 - 2]);
+    return nnz;
+}
+
 /* ------------------------------------------------------------------ intra picture ---------------- */
 static void build_nb(const ora_cfg *cfg, const ora_plane *rec, int comp, int x0, int y0, int n, uint8_t *nb)
 {   /* 8.4.4.2.2 reference sample availability + substitution; (x0,y0) in component samples */

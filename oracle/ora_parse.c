@@ -753,7 +753,7 @@ static int parse_slice(const sps_t *sps, const pps_t *pps, int nal_type, const u
         for (int i = 0; i < rps.n_neg; i++) if (rps.used[i]) c1[n1++] = poc + rps.dpoc[i];
         for (int i = 0; i < nref[1] && i < 16 && n1; i++) out->list1_poc[out->n_list1++] = c1[i % n1];
     }
-    out->col_from_l0 = col_from_l0; out->mvd_l1_zero = mvd_l1_zero; out->qg_depth = pps->diff_cu_qp_delta_depth;
+    out->col_from_l0 = col_from_l0; out->mvd_l1_zero = mvd_l1_zero; out->qg_depth = pps->diff_cu_qp_delta_depth; out->sign_hiding = pps->sign_hiding;
     for (size_t q = 0; q < p.n_tus; q++) if (p.tus[q].qp_delta) out->any_qp_delta = 1;
     out->st = p.st; out->cus = p.cus; out->n_cus = p.n_cus; out->tus = p.tus; out->n_tus = p.n_tus; out->lev = p.lev; out->n_lev = p.n_lev; out->ok = ok;
     for (int i = 0; i < 16; i++) { out->ref_poc[0][i] = i < rps.n_neg ? poc + rps.dpoc[i] : 0; out->ref_poc[1][i] = i < rps.n_pos ? poc + rps.dpoc[rps.n_neg + i] : 0; }

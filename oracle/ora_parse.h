@@ -36,6 +36,7 @@ typedef struct ora_parsed_pic {
     int n_list0, list0_poc[16];                           /* RefPicList0 as POCs */
     int n_list1, list1_poc[16], col_from_l0, mvd_l1_zero;
     int qg_depth;                                         /* diff_cu_qp_delta_depth */
+    int sign_hiding;                                      /* pps sign_data_hiding_enabled_flag */
 } ora_parsed_pic;
 
 typedef struct ora_parsed_stream {

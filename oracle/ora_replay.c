@@ -15,7 +15,12 @@
 #include "ks_oracle.h"
 #include "ora_parse.h"
 
-typedef struct { uint8_t *p[3]; int w, h; uint8_t *done; int dw; } rpic;       /* planes (pitch w, w/2); done: per 4x4 luma block, decoded */
+int ora_tb_levels(int qp, int intra_slice, int log2, int is_luma, int intra_mode, int sign_hiding, const uint8_t *src, int ss, const uint8_t *pred, int ps, int16_t *lev);   /* ora_frame.c */
+
+/* a transform block with coefficients, seen just before its residual is added: component, position and size in component samples, the
+ * prediction, the block's QP, the intra mode (-1: inter block) and the levels the stream carries (raster n x n) */
+typedef void (*tb_tap)(void *user, int ci, int x, int y, int log2, const uint8_t *pred, int pred_stride, int qp, int intra_mode, const int16_t *lev);
+typedef struct { uint8_t *p[3]; int w, h; uint8_t *done; int dw; tb_tap tap; void *tap_user; } rpic;       /* planes (pitch w, w/2); done: per 4x4 luma block, decoded */
 
 /* 6.4.1 for one sample position in LUMA coordinates: inside the picture and already decoded (decoding order == z-scan order) */
 static int sample_avail(const rpic *r, int x, int y) { return x >= 0 && y >= 0 && x < r->w && y < r->h && r->done[(y >> 2) * r->dw + (x >> 2)]; }
@@ -47,6 +52,7 @@ static void recon_block(rpic *r, int ci, int x0, int y0, int log2, int mode, int
     ora_intra_pred(pred, n, nb, log2, mode, ci == 0, strong);
     uint8_t *dst = r->p[ci] + (size_t)y0 * pitch + x0;
     if (lev) {
+        if (r->tap) r->tap(r->tap_user, ci, x0, y0, log2, pred, n, qp, mode, lev);
         ora_dequant(lev, coef, n, qp, log2);
         ora_idct_add(coef, dst, pred, n, pitch, n, log2, ci == 0 && log2 == 2);           /* 4x4 intra luma: DST */
     } else for (int y = 0; y < n; y++) memcpy(dst + (size_t)y * pitch, pred + y * n, (size_t)n);
@@ -327,6 +333,7 @@ static int replay_picture(rctx *c, uint8_t *out)
             } else if (t->cbf & 1) {
                 int16_t coef[32 * 32];
                 uint8_t *dst = r->p[0] + (size_t)t->y * W + t->x;
+                if (r->tap) r->tap(r->tap_user, 0, t->x, t->y, t->log2, dst, W, qpc[0], -1, pp->lev + t->lev_off[0]);
                 ora_dequant(pp->lev + t->lev_off[0], coef, n, qpc[0], t->log2);
                 ora_idct_add(coef, dst, dst, n, W, W, t->log2, 0);
             }
@@ -344,6 +351,7 @@ static int replay_picture(rctx *c, uint8_t *out)
                 else if (lev) {
                     int16_t coef[32 * 32];
                     uint8_t *dst = r->p[ci] + (size_t)yc * (W >> 1) + xc;
+                    if (r->tap) r->tap(r->tap_user, ci, xc, yc, l2c, dst, W >> 1, qpc[ci], -1, lev);
                     ora_dequant(lev, coef, 1 << l2c, qpc[ci], l2c);
                     ora_idct_add(coef, dst, dst, 1 << l2c, W >> 1, W >> 1, l2c, 0);
                 }
@@ -396,7 +404,8 @@ static int replay_picture(rctx *c, uint8_t *out)
 
 /* Replays pictures first .. first + count - 1 of the stream (decoding order; I and P slices, P-only streams come out in display order) into
  * `out` (count coded-size I420 pictures).  Returns 0, or a negative code at the first picture outside the limits in the header. */
-int ora_replay_pictures(const ora_parsed_stream *ps, int first, int count, uint8_t *out)
+typedef struct { tb_tap fn; void *user; int *cur_pic; } tap_cfg;
+static int replay_run(const ora_parsed_stream *ps, int first, int count, uint8_t *out, const tap_cfg *tap)
 {
     if (!ps || first < 0 || count < 1 || first + count > ps->n_pics) return -1;
     const int W = ps->width, H = ps->height, dw = (W + 3) >> 2, nb = dw * ((H + 3) >> 2);
@@ -414,6 +423,8 @@ int ora_replay_pictures(const ora_parsed_stream *ps, int first, int count, uint8
     uint8_t *scratch = (uint8_t *)malloc(fsz);
     for (int i = start; i < first + count && !rc; i++) {
         c.pp = &ps->pics[i]; c.poc = c.pp->st.poc;
+        c.r.tap = tap && i >= first ? tap->fn : NULL; c.r.tap_user = tap ? tap->user : NULL;
+        if (tap && tap->cur_pic) *tap->cur_pic = i;
         if (c.pp->st.nal_type == 19 || c.pp->st.nal_type == 20) for (int k = 0; k < DPB_N; k++) dpb[k].valid = 0;
         uint8_t *dst = i >= first ? out + fsz * (size_t)(i - first) : scratch;
         rc = replay_picture(&c, dst);
@@ -424,6 +435,44 @@ int ora_replay_pictures(const ora_parsed_stream *ps, int first, int count, uint8
     }
     for (int k = 0; k < DPB_N; k++) { free(dpb[k].pix); free(dpb[k].mv); }
     free(scratch); free(pre); free(c.r.done); free(c.cbfy); free(c.intra); free(c.qpy); free(c.mv);
+    return rc;
+}
+
+int ora_replay_pictures(const ora_parsed_stream *ps, int first, int count, uint8_t *out) { return replay_run(ps, first, count, out, NULL); }
+
+/* ---- the reference's LEVELS against our transform-block coder ----
+ * For every transform block with coefficients of the reference's stream: residual = source - the reference's own prediction (re-created above),
+ * through OUR forward transform + quantiser + sign-data hiding (ora_tb_levels), compared with the levels the reference coded.  `src` holds the
+ * source pictures in DISPLAY order (coded size, I420), valid for one IDR period.  counts[cat][0..3] = blocks compared, blocks with identical
+ * levels, coefficients that are non-zero on either side, coefficients that differ; cat = 0 I-slice luma, 1 I-slice chroma, 2 inter-slice intra
+ * blocks, 3 inter blocks luma, 4 inter blocks chroma.  Tells how much of the reference's quantiser (rounding offsets, sign hiding, any RD
+ * quantisation) our restatement reproduces; the reference's decisions to drop whole blocks do not enter (those blocks carry no levels). */
+typedef struct { const ora_parsed_stream *ps; const uint8_t *src; int cur; long (*counts)[4]; } lev_cmp;
+static void compare_tap(void *user, int ci, int x, int y, int log2, const uint8_t *pred, int ps_, int qp, int intra_mode, const int16_t *lev)
+{
+    lev_cmp *u = (lev_cmp *)user;
+    const ora_parsed_pic *pp = &u->ps->pics[u->cur];
+    const int W = u->ps->width, H = u->ps->height, n = 1 << log2, islice = pp->st.slice_type == 2;
+    const size_t fsz = (size_t)W * H * 3 / 2;
+    const uint8_t *plane = u->src + fsz * (size_t)pp->st.poc + (ci == 0 ? 0 : (ci == 1 ? (size_t)W * H : (size_t)W * H * 5 / 4));
+    const int pitch = ci ? W >> 1 : W;
+    int16_t ours[1024];
+    ora_tb_levels(qp, islice, log2, ci == 0, intra_mode, pp->sign_hiding, plane + (size_t)y * pitch + x, pitch, pred, ps_, ours);
+    const int cat = islice ? (ci ? 1 : 0) : (intra_mode >= 0 ? 2 : (ci ? 4 : 3));
+    long nz = 0, diff = 0;
+    for (int i = 0; i < n * n; i++) { if (ours[i] || lev[i]) nz++; if (ours[i] != lev[i]) diff++; }
+    u->counts[cat][0]++; u->counts[cat][1] += diff == 0; u->counts[cat][2] += nz; u->counts[cat][3] += diff;
+}
+int ora_replay_compare_levels(const ora_parsed_stream *ps, int first, int count, const uint8_t *src, long counts[5][4])
+{
+    if (!ps || !src || !counts) return -1;
+    const size_t fsz = (size_t)ps->width * ps->height * 3 / 2;
+    uint8_t *out = (uint8_t *)malloc(fsz * (size_t)(count > 0 ? count : 1));
+    lev_cmp u; u.ps = ps; u.src = src; u.cur = 0; u.counts = counts;
+    memset(counts, 0, sizeof(long) * 20);
+    tap_cfg t; t.fn = compare_tap; t.user = &u; t.cur_pic = &u.cur;
+    const int rc = replay_run(ps, first, count, out, &t);
+    free(out);
     return rc;
 }
 

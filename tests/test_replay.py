@@ -89,6 +89,31 @@ def test_reference_p_sequence_is_recreated_from_its_parsed_decisions(seq, tmp_pa
         assert np.array_equal(np.fromfile(o, np.uint8), out)
 
 
+@pytest.mark.parametrize("seq", [c for c in SEQS if c["name"].startswith("nat320_")], ids=[c["name"] for c in SEQS if c["name"].startswith("nat320_")])
+def test_reference_levels_against_our_transform_block_coder(seq):
+    """Every transform block with coefficients in the reference's stream: source minus the reference's own prediction (re-created by the replay),
+    through OUR forward transform + quantiser + sign-data hiding, against the levels the reference coded.  At the presets without RD
+    quantisation (ultrafast .. veryfast, the north star's) every level must be identical; from `fast` up the reference switches its RDOQ on
+    (SURVEY: rdoQuant E@0x4a3040), which this repo does not have, and a large share differs -- asserted too, so the check cannot pass vacuously."""
+    import gzip
+    O = _oracle()
+    O.ora_replay_compare_levels.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    src = np.frombuffer(gzip.open(os.path.join(ROOT, "tests", "golden", "nat_320x240_6f.yuv.gz"), "rb").read(), np.uint8).copy()
+    bs = np.frombuffer(base64.b64decode(seq["stream_b64"]), np.uint8).copy()
+    ps = O.ora_parse_stream(bs.ctypes.data, bs.size)
+    cnt = (C.c_long * 20)()
+    try:
+        assert O.ora_replay_compare_levels(ps, 0, O.ora_parse_num_pics(ps), src.ctypes.data, cnt) == 0
+    finally:
+        O.ora_parse_free(ps)
+    blocks, same = sum(cnt[4 * k] for k in range(5)), sum(cnt[4 * k + 1] for k in range(5))
+    assert blocks > 300
+    if seq["preset"] in ("ultrafast", "superfast", "veryfast"):
+        assert same == blocks and sum(cnt[4 * k + 3] for k in range(5)) == 0
+    else:
+        assert same < 0.9 * blocks
+
+
 def test_replay_rejects_what_it_does_not_cover():
     O = _oracle()
     bs = np.frombuffer(base64.b64decode(CASES[0]["stream_b64"]), np.uint8).copy()
