@@ -176,6 +176,17 @@ int ora_tb_levels(int qp, int intra_slice, int log2, int is_luma, int intra_mode
     return nnz;
 }
 
+/* Would OUR inter transform-block coder keep levels for (src, pred)?  Returns 1 / 0 after the RD zero-out at lambda_qp; *plain_nnz = non-zero
+ * levels of the plain quantiser + sign hiding before that decision.  ora_replay.c holds this against the reference's coded-block flags. */
+int ora_tb_decision(int qp, int lambda_qp, int log2, int sign_hiding, const uint8_t *src, int ss, const uint8_t *pred, int ps, int *plain_nnz)
+{
+    ora_cfg cfg; memset(&cfg, 0, sizeof(cfg)); cfg.sign_hiding = sign_hiding;
+    uint8_t rec[32 * 32]; int16_t lev[32 * 32];
+    build_scans();
+    if (plain_nnz) { *plain_nnz = 0; code_tb(&cfg, qp, 0, log2, 0, src, ss, pred, ps, rec, 32, lev, 32, 0, NULL); for (int y = 0; y < (1 << log2); y++) for (int x = 0; x < (1 << log2); x++) *plain_nnz += lev[y * 32 + x] != 0; }
+    return code_tb(&cfg, qp, 0, log2, 0, src, ss, pred, ps, rec, 32, lev, 32, ora_lambda_sse_q4[clip3(0, 51, lambda_qp)], NULL);
+}
+
 /* ------------------------------------------------------------------ intra picture ---------------- */
 static void build_nb(const ora_cfg *cfg, const ora_plane *rec, int comp, int x0, int y0, int n, uint8_t *nb)
 {   /* 8.4.4.2.2 reference sample availability + substitution; (x0,y0) in component samples */

@@ -20,7 +20,9 @@ int ora_tb_levels(int qp, int intra_slice, int log2, int is_luma, int intra_mode
 /* a transform block with coefficients, seen just before its residual is added: component, position and size in component samples, the
  * prediction, the block's QP, the intra mode (-1: inter block) and the levels the stream carries (raster n x n) */
 typedef void (*tb_tap)(void *user, int ci, int x, int y, int log2, const uint8_t *pred, int pred_stride, int qp, int intra_mode, const int16_t *lev);
-typedef struct { uint8_t *p[3]; int w, h; uint8_t *done; int dw; tb_tap tap; void *tap_user; } rpic;       /* planes (pitch w, w/2); done: per 4x4 luma block, decoded */
+/* an inter CU seen right after its prediction: position, size, and per luma transform block (raster of min(size,32)-blocks) the stream's cbf */
+typedef void (*cu_tap)(void *user, int x, int y, int log2, const uint8_t *pred, int pred_stride, int qp, const uint8_t *cbf_luma);
+typedef struct { uint8_t *p[3]; int w, h; uint8_t *done; int dw; tb_tap tap; void *tap_user; cu_tap cutap; } rpic;       /* planes (pitch w, w/2); done: per 4x4 luma block, decoded */
 
 /* 6.4.1 for one sample position in LUMA coordinates: inside the picture and already decoded (decoding order == z-scan order) */
 static int sample_avail(const rpic *r, int x, int y) { return x >= 0 && y >= 0 && x < r->w && y < r->h && r->done[(y >> 2) * r->dw + (x >> 2)]; }
@@ -319,6 +321,11 @@ static int replay_picture(rctx *c, uint8_t *out)
                 if (k == 1 && cu->part_mode == 1 && (py_ & 7) == 0) for (int x = px_ >> 2; x < ((px_ + pw_) >> 2); x++) hedge[(py_ >> 3) * dw + x] |= 1;
             }
             if (rc) break;
+            if (r->cutap) {
+                const int tl = cu->log2 > 5 ? 5 : cu->log2, nt = S >> tl; uint8_t cbf[4] = {0, 0, 0, 0};
+                for (uint32_t q = 0; q < cu->n_tu; q++) { const ora_tu_rec *t = &pp->tus[cu->first_tu + q]; if (t->log2 == tl && (t->cbf & 1)) cbf[((t->y - cu->y) >> tl) * nt + ((t->x - cu->x) >> tl)] = 1; else if (t->log2 != tl) cbf[0] |= 2; }
+                if (!(cbf[0] & 2)) r->cutap(r->tap_user, cu->x, cu->y, cu->log2, r->p[0] + (size_t)cu->y * W + cu->x, W, qpc[0], cbf);
+            }
         } else
             for (int y = cu->y >> 2; y < ((cu->y + S) >> 2) && y < ((H + 3) >> 2); y++) for (int x = cu->x >> 2; x < ((cu->x + S) >> 2) && x < dw; x++) c->intra[y * dw + x] = 1;
         /* the CU boundary is a prediction-block edge AND a transform-block edge whatever its transform tree looks like (8.7.2.3 starts from the coding block) */
@@ -404,7 +411,7 @@ static int replay_picture(rctx *c, uint8_t *out)
 
 /* Replays pictures first .. first + count - 1 of the stream (decoding order; I and P slices, P-only streams come out in display order) into
  * `out` (count coded-size I420 pictures).  Returns 0, or a negative code at the first picture outside the limits in the header. */
-typedef struct { tb_tap fn; void *user; int *cur_pic; } tap_cfg;
+typedef struct { tb_tap fn; void *user; int *cur_pic; cu_tap cufn; } tap_cfg;
 static int replay_run(const ora_parsed_stream *ps, int first, int count, uint8_t *out, const tap_cfg *tap)
 {
     if (!ps || first < 0 || count < 1 || first + count > ps->n_pics) return -1;
@@ -423,7 +430,7 @@ static int replay_run(const ora_parsed_stream *ps, int first, int count, uint8_t
     uint8_t *scratch = (uint8_t *)malloc(fsz);
     for (int i = start; i < first + count && !rc; i++) {
         c.pp = &ps->pics[i]; c.poc = c.pp->st.poc;
-        c.r.tap = tap && i >= first ? tap->fn : NULL; c.r.tap_user = tap ? tap->user : NULL;
+        c.r.tap = tap && i >= first ? tap->fn : NULL; c.r.tap_user = tap ? tap->user : NULL; c.r.cutap = tap && i >= first ? tap->cufn : NULL;
         if (tap && tap->cur_pic) *tap->cur_pic = i;
         if (c.pp->st.nal_type == 19 || c.pp->st.nal_type == 20) for (int k = 0; k < DPB_N; k++) dpb[k].valid = 0;
         uint8_t *dst = i >= first ? out + fsz * (size_t)(i - first) : scratch;
@@ -470,7 +477,42 @@ int ora_replay_compare_levels(const ora_parsed_stream *ps, int first, int count,
     uint8_t *out = (uint8_t *)malloc(fsz * (size_t)(count > 0 ? count : 1));
     lev_cmp u; u.ps = ps; u.src = src; u.cur = 0; u.counts = counts;
     memset(counts, 0, sizeof(long) * 20);
-    tap_cfg t; t.fn = compare_tap; t.user = &u; t.cur_pic = &u.cur;
+    tap_cfg t; t.fn = compare_tap; t.user = &u; t.cur_pic = &u.cur; t.cufn = NULL;
+    const int rc = replay_run(ps, first, count, out, &t);
+    free(out);
+    return rc;
+}
+
+/* ---- the reference's zero-block decisions against ours ----
+ * For every luma transform block of every 2Nx2N-transform inter CU of the P pictures: does the reference code levels (its cbf), would the plain
+ * quantiser produce any, and does OUR coder keep them after its RD zero-out (lambda of QP + lambda_delta on the pictures with poc % 4 != 0,
+ * as ks_rc_lambda_qp does for -bframes 0 streams)?  counts[0..5] = blocks, reference codes, plain quantiser non-zero, ours codes, both code,
+ * neither codes. */
+typedef struct { const ora_parsed_stream *ps; const uint8_t *src; int cur, lambda_delta; long *counts; } zb_cmp;
+int ora_tb_decision(int qp, int lambda_qp, int log2, int sign_hiding, const uint8_t *src, int ss, const uint8_t *pred, int ps, int *plain_nnz);   /* ora_frame.c */
+static void zero_tap(void *user, int x, int y, int log2, const uint8_t *pred, int ps_, int qp, const uint8_t *cbf)
+{
+    zb_cmp *u = (zb_cmp *)user;
+    const ora_parsed_pic *pp = &u->ps->pics[u->cur];
+    if (pp->st.slice_type != 1) return;
+    const int W = u->ps->width, H = u->ps->height, tl = log2 > 5 ? 5 : log2, nt = (1 << log2) >> tl, n = 1 << tl;
+    const uint8_t *plane = u->src + (size_t)W * H * 3 / 2 * (size_t)pp->st.poc;
+    const int lq = qp + ((pp->st.poc & 3) ? (u->lambda_delta & 255) : (u->lambda_delta >> 8));     /* low byte: non-key pictures, next byte: key pictures */
+    for (int j = 0; j < nt; j++) for (int i = 0; i < nt; i++) {
+        int plain = 0;
+        const int ours = ora_tb_decision(qp, lq, tl, pp->sign_hiding, plane + (size_t)(y + j * n) * W + x + i * n, W, pred + (size_t)(j * n) * ps_ + i * n, ps_, &plain);
+        const int ref = cbf[j * nt + i] & 1;
+        u->counts[0]++; u->counts[1] += ref; u->counts[2] += plain != 0; u->counts[3] += ours; u->counts[4] += ref && ours; u->counts[5] += !ref && !ours;
+    }
+}
+int ora_replay_compare_zero_blocks(const ora_parsed_stream *ps, int first, int count, const uint8_t *src, int lambda_delta, long counts[6])
+{
+    if (!ps || !src || !counts) return -1;
+    const size_t fsz = (size_t)ps->width * ps->height * 3 / 2;
+    uint8_t *out = (uint8_t *)malloc(fsz * (size_t)(count > 0 ? count : 1));
+    zb_cmp u; u.ps = ps; u.src = src; u.cur = 0; u.lambda_delta = lambda_delta; u.counts = counts;
+    memset(counts, 0, sizeof(long) * 6);
+    tap_cfg t; t.fn = NULL; t.user = &u; t.cur_pic = &u.cur; t.cufn = zero_tap;
     const int rc = replay_run(ps, first, count, out, &t);
     free(out);
     return rc;

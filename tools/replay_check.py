@@ -2,7 +2,8 @@
 """SURVEY.md 8c tier P2, by hand: encode a clip with the REFERENCE encoder (oracle/_ref/appencoder, any options), then
   1. re-create its reconstruction from the parsed stream with the oracle's kernels (oracle/ora_replay.c) and compare every picture with what
      the reference DECODER writes, and
-  2. hold the levels it coded against OUR forward transform + quantiser + sign-data hiding on the same residuals.
+  2. hold the levels it coded against OUR forward transform + quantiser + sign-data hiding on the same residuals, and
+  3. (-bframes 0 streams) hold its zero-block decisions against our RD zero-out on its own predictions.
 usage: replay_check.py clip.yuv width height qp preset frames [extra appencoder options, e.g. -bframes 0 / -rc 3 -crf 26]"""
 import ctypes as C
 import os
@@ -54,6 +55,16 @@ def main():
         a, b, c, e = cnt[4 * k:4 * k + 4]
         if a:
             print("  %-28s %7d blocks, %7d identical (%.1f %%); %8d coefficient positions, %7d differ (%.2f %%)" % (name, a, b, 100.0 * b / a, c, e, 100.0 * e / max(c, 1)))
+    if "-bframes" in extra and extra[extra.index("-bframes") + 1] == "0":
+        O.ora_replay_compare_zero_blocks.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        print("zero-block decisions on the reference's own predictions (luma blocks of its inter CUs, P pictures):")
+        for delta in (0, 3):
+            z = (C.c_long * 6)()
+            O.ora_replay_compare_zero_blocks(ps, 0, npic, src.ctypes.data, delta, z)
+            b, ref, plain, ours, both, neither = list(z)
+            if b:
+                print("  lambda of QP+%d on non-key pictures: %d blocks; reference codes %.1f %%, plain quantiser %.1f %%, ours %.1f %%; same decision on %.1f %%"
+                      % (delta, b, 100.0 * ref / b, 100.0 * plain / b, 100.0 * ours / b, 100.0 * (both + neither) / b))
     return 1 if rc or bad else 0
 
 
