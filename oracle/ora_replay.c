@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "ks_oracle.h"
+#include "ora_frame.h"
 #include "ora_parse.h"
 
 int ora_tb_levels(int qp, int intra_slice, int log2, int is_luma, int intra_mode, int sign_hiding, const uint8_t *src, int ss, const uint8_t *pred, int ps, int16_t *lev);   /* ora_frame.c */
@@ -69,6 +70,7 @@ typedef struct {
     const ora_parsed_stream *ps; const ora_parsed_pic *pp;
     rpic r; minfo *mv; uint8_t *cbfy, *intra, *qpy; /* per 4x4: motion, "in a luma TB with coefficients", intra, QpY of the CU */
     dpic *dpb; int poc, no_backward;
+    const uint8_t *sao_src; int sao_level; long *sao_counts;     /* ora_replay_compare_sao */
 } rctx;
 
 static int list_n(const rctx *c, int X) { return X ? c->pp->n_list1 : c->pp->n_list0; }
@@ -390,6 +392,28 @@ static int replay_picture(rctx *c, uint8_t *out)
                     }
                 }
     }
+    if (!rc && c->sao_counts) {         /* OUR SAO decision on the reference's deblocked picture, against the parameters it coded */
+        ora_cfg cfg; memset(&cfg, 0, sizeof(cfg)); cfg.width = W; cfg.height = H; cfg.sao = c->sao_level;
+        ora_pic src, deb, tmp;
+        const int l = ps->log2_ctb, ctw = (W + (1 << l) - 1) >> l, cth = (H + (1 << l) - 1) >> l;
+        ks_ctu_syn *ctus = (ks_ctu_syn *)calloc((size_t)ctw * cth, sizeof(ks_ctu_syn));
+        if (l == 6 && ctus && !ora_pic_alloc(&src, W, H) && !ora_pic_alloc(&deb, W, H) && !ora_pic_alloc(&tmp, W, H)) {
+            ora_pic_load(&src, c->sao_src + ysz * 3 / 2 * (size_t)c->poc, W, H); ora_pic_load(&deb, r->p[0], W, H);
+            ora_sao_picture(&cfg, qp, &src, &deb, &tmp, ctus);
+            for (int i = 0; i < ctw * cth; i++) for (int grp = 0; grp < 2; grp++) {
+                const int ci = grp ? 1 : 0, rt = pp->sao[i].type[ci], ot = ctus[i].sao[ci].type;
+                long *k = c->sao_counts + grp * 8;
+                k[0]++; k[1] += rt != 0; k[2] += ot != 0; k[3] += rt == ot;
+                if (rt && rt == ot) {
+                    int same_pos = pp->sao[i].pos[ci] == ctus[i].sao[ci].band_or_class && (!grp || rt == 2 || pp->sao[i].pos[2] == ctus[i].sao[2].band_or_class);
+                    int same_off = same_pos && !memcmp(pp->sao[i].off[ci], ctus[i].sao[ci].off, 4) && (!grp || !memcmp(pp->sao[i].off[2], ctus[i].sao[2].off, 4));
+                    k[4]++; k[5] += same_pos; k[6] += same_off;
+                }
+            }
+            ora_pic_free(&src); ora_pic_free(&deb); ora_pic_free(&tmp);
+        }
+        free(ctus);
+    }
     /* 8.7.3: SAO reads the deblocked picture and writes the output picture */
     if (!rc) {
         memcpy(out, r->p[0], ysz * 3 / 2);
@@ -411,7 +435,7 @@ static int replay_picture(rctx *c, uint8_t *out)
 
 /* Replays pictures first .. first + count - 1 of the stream (decoding order; I and P slices, P-only streams come out in display order) into
  * `out` (count coded-size I420 pictures).  Returns 0, or a negative code at the first picture outside the limits in the header. */
-typedef struct { tb_tap fn; void *user; int *cur_pic; cu_tap cufn; } tap_cfg;
+typedef struct { tb_tap fn; void *user; int *cur_pic; cu_tap cufn; const uint8_t *sao_src; int sao_level; long *sao_counts; } tap_cfg;
 static int replay_run(const ora_parsed_stream *ps, int first, int count, uint8_t *out, const tap_cfg *tap)
 {
     if (!ps || first < 0 || count < 1 || first + count > ps->n_pics) return -1;
@@ -432,6 +456,7 @@ static int replay_run(const ora_parsed_stream *ps, int first, int count, uint8_t
         c.pp = &ps->pics[i]; c.poc = c.pp->st.poc;
         c.r.tap = tap && i >= first ? tap->fn : NULL; c.r.tap_user = tap ? tap->user : NULL; c.r.cutap = tap && i >= first ? tap->cufn : NULL;
         if (tap && tap->cur_pic) *tap->cur_pic = i;
+        c.sao_counts = tap && i >= first ? tap->sao_counts : NULL; c.sao_src = tap ? tap->sao_src : NULL; c.sao_level = tap ? tap->sao_level : 0;
         if (c.pp->st.nal_type == 19 || c.pp->st.nal_type == 20) for (int k = 0; k < DPB_N; k++) dpb[k].valid = 0;
         uint8_t *dst = i >= first ? out + fsz * (size_t)(i - first) : scratch;
         rc = replay_picture(&c, dst);
@@ -477,7 +502,7 @@ int ora_replay_compare_levels(const ora_parsed_stream *ps, int first, int count,
     uint8_t *out = (uint8_t *)malloc(fsz * (size_t)(count > 0 ? count : 1));
     lev_cmp u; u.ps = ps; u.src = src; u.cur = 0; u.counts = counts;
     memset(counts, 0, sizeof(long) * 20);
-    tap_cfg t; t.fn = compare_tap; t.user = &u; t.cur_pic = &u.cur; t.cufn = NULL;
+    tap_cfg t; memset(&t, 0, sizeof(t)); t.fn = compare_tap; t.user = &u; t.cur_pic = &u.cur;
     const int rc = replay_run(ps, first, count, out, &t);
     free(out);
     return rc;
@@ -512,7 +537,23 @@ int ora_replay_compare_zero_blocks(const ora_parsed_stream *ps, int first, int c
     uint8_t *out = (uint8_t *)malloc(fsz * (size_t)(count > 0 ? count : 1));
     zb_cmp u; u.ps = ps; u.src = src; u.cur = 0; u.lambda_delta = lambda_delta; u.counts = counts;
     memset(counts, 0, sizeof(long) * 6);
-    tap_cfg t; t.fn = NULL; t.user = &u; t.cur_pic = &u.cur; t.cufn = zero_tap;
+    tap_cfg t; memset(&t, 0, sizeof(t)); t.user = &u; t.cur_pic = &u.cur; t.cufn = zero_tap;
+    const int rc = replay_run(ps, first, count, out, &t);
+    free(out);
+    return rc;
+}
+
+/* ---- the reference's SAO parameters against our decision (row a18) ----
+ * OUR SAO decision (ora_sao_picture at `sao_level`, the model the device kernel equals) runs on the reference's own deblocked pictures and
+ * source; per CTU and component group (0 luma, 1 chroma) counts[grp * 8 + 0..6] = CTUs, reference has SAO on, ours has it on, same type,
+ * both on with the same type, of those the same band position / edge class, of those identical offsets.  `src` in display order (one IDR period). */
+int ora_replay_compare_sao(const ora_parsed_stream *ps, int first, int count, const uint8_t *src, int sao_level, long counts[16])
+{
+    if (!ps || !src || !counts) return -1;
+    const size_t fsz = (size_t)ps->width * ps->height * 3 / 2;
+    uint8_t *out = (uint8_t *)malloc(fsz * (size_t)(count > 0 ? count : 1));
+    memset(counts, 0, sizeof(long) * 16);
+    tap_cfg t; memset(&t, 0, sizeof(t)); t.sao_src = src; t.sao_level = sao_level; t.sao_counts = counts;
     const int rc = replay_run(ps, first, count, out, &t);
     free(out);
     return rc;

@@ -141,6 +141,27 @@ def test_reference_zero_block_decisions_against_our_rd_zero_out():
     assert res[0][3] > 1.3 * ref and res[0][4] + res[0][5] < both + neither      # without the raised lambda: far more coded blocks, less agreement
 
 
+def test_reference_sao_parameters_against_our_decision():
+    """Row a18 (the SAO offset decision, closed in the reference; ours is our own): run OUR decision on the reference's deblocked pictures and
+    compare with the parameters it coded.  The statistics and the apply stage are pinned elsewhere (KAT, replay); this only MEASURES how far the
+    decision is from the reference's -- it switches SAO on for about twice as many CTUs as ours (720p x 16 pictures: 48 % vs 20 % of the luma
+    CTUs) -- and keeps the comparison from rotting."""
+    import gzip
+    O = _oracle()
+    O.ora_replay_compare_sao.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    src = np.frombuffer(gzip.open(os.path.join(ROOT, "tests", "golden", "nat_320x240_6f.yuv.gz"), "rb").read(), np.uint8).copy()
+    seq = [c for c in SEQS if c["name"] == "nat320_veryfast_qp27_6f"][0]
+    bs = np.frombuffer(base64.b64decode(seq["stream_b64"]), np.uint8).copy()
+    ps = O.ora_parse_stream(bs.ctypes.data, bs.size)
+    cnt = (C.c_long * 16)()
+    try:
+        assert O.ora_replay_compare_sao(ps, 0, O.ora_parse_num_pics(ps), src.ctypes.data, 3, cnt) == 0
+    finally:
+        O.ora_parse_free(ps)
+    ctus, ref_on, ours_on, same_type = cnt[0], cnt[1], cnt[2], cnt[3]
+    assert ctus == 6 * 5 * 4 and ref_on > 0 and 0 < ours_on <= ref_on and same_type >= 0.25 * ctus
+
+
 def test_replay_rejects_what_it_does_not_cover():
     O = _oracle()
     bs = np.frombuffer(base64.b64decode(CASES[0]["stream_b64"]), np.uint8).copy()
