@@ -475,6 +475,13 @@ static void decide_candidates(const ora_cfg *cfg, const ora_plane *src, const or
     }
 }
 
+/* OUR search for one 16x16 cell against an arbitrary reference picture (ora_replay.c runs it on the reference encoder's own reference pictures and
+ * compares vector and distortion with what the reference chose): returns the winner's cost, *dist its distortion in the search metric */
+int ora_me_probe(const ora_cfg *cfg, int qp, const ora_pic *src, const ora_pic *ref, int x0, int y0, int tpx, int tpy, int *mx, int *my, int *dist)
+{
+    return me_cell(cfg, ora_lambda_sad_q4[qp], &src->c[0], &ref->c[0], x0, y0, tpx, tpy, mx, my, dist);
+}
+
 /* stage D state of one CTU: vectors of the 4x4 cells plus a one-cell border (row -1: above CTUs incl. above-left / above-right,
  * column -1: left CTU); index [j + 1][i + 1], i = -1..4, j = -1..4 */
 typedef struct {

@@ -16,6 +16,7 @@
 #include "ora_frame.h"
 #include "ora_parse.h"
 
+int ora_me_probe(const ora_cfg *cfg, int qp, const ora_pic *src, const ora_pic *ref, int x0, int y0, int tpx, int tpy, int *mx, int *my, int *dist);   /* ora_frame.c */
 int ora_tb_levels(int qp, int intra_slice, int log2, int is_luma, int intra_mode, int sign_hiding, const uint8_t *src, int ss, const uint8_t *pred, int ps, int16_t *lev);   /* ora_frame.c */
 
 /* a transform block with coefficients, seen just before its residual is added: component, position and size in component samples, the
@@ -71,6 +72,8 @@ typedef struct {
     rpic r; minfo *mv; uint8_t *cbfy, *intra, *qpy; /* per 4x4: motion, "in a luma TB with coefficients", intra, QpY of the CU */
     dpic *dpb; int poc, no_backward;
     const uint8_t *sao_src; int sao_level; long *sao_counts;     /* ora_replay_compare_sao */
+    const uint8_t *me_src; int me_method; long *me_counts;       /* ora_replay_compare_me */
+    ora_pic me_cur, me_ref; int me_ref_poc, me_cur_poc, me_ready;
 } rctx;
 
 static int list_n(const rctx *c, int X) { return X ? c->pp->n_list1 : c->pp->n_list0; }
@@ -323,6 +326,36 @@ static int replay_picture(rctx *c, uint8_t *out)
                 if (k == 1 && cu->part_mode == 1 && (py_ & 7) == 0) for (int x = px_ >> 2; x < ((px_ + pw_) >> 2); x++) hedge[(py_ >> 3) * dw + x] |= 1;
             }
             if (rc) break;
+            if (c->me_counts && pp->st.slice_type == 1 && cu->part_mode == 0 && cu->log2 >= 4) {
+                /* OUR search, cell by cell, on the picture the reference predicted this CU from (only CUs that use the previous picture: what our
+                 * encoder's single reference would be) */
+                const minfo *mi = &c->mv[(cu->y >> 2) * dw + (cu->x >> 2)];
+                const dpic *rp = find_pic(c, mi->ref_poc[0]);
+                if (rp && mi->ref_poc[0] == c->poc - 1) {
+                    if (!c->me_ready) { ora_pic_alloc(&c->me_cur, W, H); ora_pic_alloc(&c->me_ref, W, H); c->me_ready = 1; c->me_cur_poc = c->me_ref_poc = -1000000; }
+                    if (c->me_cur_poc != c->poc) { ora_pic_load(&c->me_cur, c->me_src + ysz * 3 / 2 * (size_t)c->poc, W, H); c->me_cur_poc = c->poc; }
+                    if (c->me_ref_poc != rp->poc) { ora_pic_load(&c->me_ref, rp->pix, W, H); c->me_ref_poc = rp->poc; }
+                    ora_cfg cfg; memset(&cfg, 0, sizeof(cfg)); cfg.width = W; cfg.height = H; cfg.me_range = 64; cfg.me_iters = 16; cfg.subpel = 2; cfg.me_method = c->me_method;
+                    for (int cy = cu->y; cy < cu->y + S && cy + 16 <= H; cy += 16) for (int cx = cu->x; cx < cu->x + S && cx + 16 <= W; cx += 16) {
+                        const minfo *col = &rp->mv[(cy >> 2) * dw + (cx >> 2)];                 /* the co-located vector of the previous picture seeds the search */
+                        int mx, my, dist;
+                        int tpx = 0, tpy = 0;
+                        if (col->pf & 1) { const int d = rp->poc - col->ref_poc[0]; tpx = d > 0 ? col->mv[0][0] / d : 0; tpy = d > 0 ? col->mv[0][1] / d : 0; }   /* per picture of distance */
+                        ora_me_probe(&cfg, qp, &c->me_cur, &c->me_ref, cx, cy, tpx, tpy, &mx, &my, &dist);
+                        uint8_t pr[256];
+                        ora_mc_luma(pr, 16, c->me_ref.c[0].p + (size_t)cy * c->me_ref.c[0].stride + cx, c->me_ref.c[0].stride, 16, 16, mi->mv[0][0], mi->mv[0][1]);
+                        const int rd = (int)ora_sad(c->me_cur.c[0].p + (size_t)cy * c->me_cur.c[0].stride + cx, pr, c->me_cur.c[0].stride, 16, 16, 16);
+                        long *k = c->me_counts;
+                        k[0]++; k[1] += mx == mi->mv[0][0] && my == mi->mv[0][1]; k[2] += abs(mx - mi->mv[0][0]) <= 1 && abs(my - mi->mv[0][1]) <= 1;
+                        k[3] += dist <= rd; k[4] += dist; k[5] += rd; k[6] += dist < rd; k[7] += dist > rd;
+                        {   /* the same by the size of the reference's vector (whole samples): < 2, < 8, < 16, < 32, >= 32 -> cells, our SAD sum, its SAD sum */
+                            const int mag = (abs(mi->mv[0][0]) > abs(mi->mv[0][1]) ? abs(mi->mv[0][0]) : abs(mi->mv[0][1])) >> 2;
+                            const int b = mag < 2 ? 0 : (mag < 8 ? 1 : (mag < 16 ? 2 : (mag < 32 ? 3 : 4)));
+                            k[8 + 3 * b]++; k[9 + 3 * b] += dist; k[10 + 3 * b] += rd;
+                        }
+                    }
+                }
+            }
             if (r->cutap) {
                 const int tl = cu->log2 > 5 ? 5 : cu->log2, nt = S >> tl; uint8_t cbf[4] = {0, 0, 0, 0};
                 for (uint32_t q = 0; q < cu->n_tu; q++) { const ora_tu_rec *t = &pp->tus[cu->first_tu + q]; if (t->log2 == tl && (t->cbf & 1)) cbf[((t->y - cu->y) >> tl) * nt + ((t->x - cu->x) >> tl)] = 1; else if (t->log2 != tl) cbf[0] |= 2; }
@@ -435,7 +468,7 @@ static int replay_picture(rctx *c, uint8_t *out)
 
 /* Replays pictures first .. first + count - 1 of the stream (decoding order; I and P slices, P-only streams come out in display order) into
  * `out` (count coded-size I420 pictures).  Returns 0, or a negative code at the first picture outside the limits in the header. */
-typedef struct { tb_tap fn; void *user; int *cur_pic; cu_tap cufn; const uint8_t *sao_src; int sao_level; long *sao_counts; } tap_cfg;
+typedef struct { tb_tap fn; void *user; int *cur_pic; cu_tap cufn; const uint8_t *sao_src; int sao_level; long *sao_counts; const uint8_t *me_src; int me_method; long *me_counts; } tap_cfg;
 static int replay_run(const ora_parsed_stream *ps, int first, int count, uint8_t *out, const tap_cfg *tap)
 {
     if (!ps || first < 0 || count < 1 || first + count > ps->n_pics) return -1;
@@ -456,6 +489,7 @@ static int replay_run(const ora_parsed_stream *ps, int first, int count, uint8_t
         c.pp = &ps->pics[i]; c.poc = c.pp->st.poc;
         c.r.tap = tap && i >= first ? tap->fn : NULL; c.r.tap_user = tap ? tap->user : NULL; c.r.cutap = tap && i >= first ? tap->cufn : NULL;
         if (tap && tap->cur_pic) *tap->cur_pic = i;
+        c.me_counts = tap && i >= first ? tap->me_counts : NULL; c.me_src = tap ? tap->me_src : NULL; c.me_method = tap ? tap->me_method : 0;
         c.sao_counts = tap && i >= first ? tap->sao_counts : NULL; c.sao_src = tap ? tap->sao_src : NULL; c.sao_level = tap ? tap->sao_level : 0;
         if (c.pp->st.nal_type == 19 || c.pp->st.nal_type == 20) for (int k = 0; k < DPB_N; k++) dpb[k].valid = 0;
         uint8_t *dst = i >= first ? out + fsz * (size_t)(i - first) : scratch;
@@ -466,6 +500,7 @@ static int replay_run(const ora_parsed_stream *ps, int first, int count, uint8_t
         memcpy(d->pix, dst, fsz); memcpy(d->mv, c.mv, sizeof(minfo) * (size_t)nb); d->poc = c.poc; d->valid = 1;
     }
     for (int k = 0; k < DPB_N; k++) { free(dpb[k].pix); free(dpb[k].mv); }
+    if (c.me_ready) { ora_pic_free(&c.me_cur); ora_pic_free(&c.me_ref); }
     free(scratch); free(pre); free(c.r.done); free(c.cbfy); free(c.intra); free(c.qpy); free(c.mv);
     return rc;
 }
@@ -554,6 +589,25 @@ int ora_replay_compare_sao(const ora_parsed_stream *ps, int first, int count, co
     uint8_t *out = (uint8_t *)malloc(fsz * (size_t)(count > 0 ? count : 1));
     memset(counts, 0, sizeof(long) * 16);
     tap_cfg t; memset(&t, 0, sizeof(t)); t.sao_src = src; t.sao_level = sao_level; t.sao_counts = counts;
+    const int rc = replay_run(ps, first, count, out, &t);
+    free(out);
+    return rc;
+}
+
+/* ---- the reference's vectors against our search (rows a3-a6) ----
+ * For every 16x16 cell of the 2Nx2N inter CUs (>= 16x16, P pictures, predicted from the previous picture) of a -bframes 0 stream: OUR search
+ * (small diamond / hexagon + half + quarter refinement, SAD) on the reference's own reference picture, seeded like our encoder seeds it (the
+ * co-located vector of the previous picture).  counts[0..7] = cells, identical vector, within one quarter sample, our SAD <= the SAD at the
+ * reference's vector, sum of our SADs, sum of the reference's, ours strictly lower, ours strictly higher; counts[8 + 3 b ..] = cells, our SAD sum, the reference's SAD sum for the cells whose
+ * reference vector is < 2, < 8, < 16, < 32, >= 32 whole samples long (b = 0..4). */
+int ora_me_probe(const ora_cfg *cfg, int qp, const ora_pic *src, const ora_pic *ref, int x0, int y0, int tpx, int tpy, int *mx, int *my, int *dist);   /* ora_frame.c */
+int ora_replay_compare_me(const ora_parsed_stream *ps, int first, int count, const uint8_t *src, int me_method, long counts[23])
+{
+    if (!ps || !src || !counts) return -1;
+    const size_t fsz = (size_t)ps->width * ps->height * 3 / 2;
+    uint8_t *out = (uint8_t *)malloc(fsz * (size_t)(count > 0 ? count : 1));
+    memset(counts, 0, sizeof(long) * 23);
+    tap_cfg t; memset(&t, 0, sizeof(t)); t.me_src = src; t.me_method = me_method; t.me_counts = counts;
     const int rc = replay_run(ps, first, count, out, &t);
     free(out);
     return rc;
