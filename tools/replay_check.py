@@ -3,7 +3,8 @@
   1. re-create its reconstruction from the parsed stream with the oracle's kernels (oracle/ora_replay.c) and compare every picture with what
      the reference DECODER writes, and
   2. hold the levels it coded against OUR forward transform + quantiser + sign-data hiding on the same residuals, and
-  3. (-bframes 0 streams) hold its zero-block decisions against our RD zero-out on its own predictions.
+  3. (-bframes 0 streams) hold its zero-block decisions against our RD zero-out on its own predictions, its vectors against our search on its
+     own reference pictures, and its SAO parameters against our SAO decision on its own deblocked pictures.
 usage: replay_check.py clip.yuv width height qp preset frames [extra appencoder options, e.g. -bframes 0 / -rc 3 -crf 26]"""
 import ctypes as C
 import os
@@ -65,6 +66,24 @@ def main():
             if b:
                 print("  lambda of QP+%d on non-key pictures: %d blocks; reference codes %.1f %%, plain quantiser %.1f %%, ours %.1f %%; same decision on %.1f %%"
                       % (delta, b, 100.0 * ref / b, 100.0 * plain / b, 100.0 * ours / b, 100.0 * (both + neither) / b))
+        O.ora_replay_compare_me.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        for method, name in ((0, "small diamond"), (1, "hexagon")):
+            k = (C.c_long * 23)()
+            O.ora_replay_compare_me(ps, 0, npic, src.ctypes.data, method, k)
+            if k[0]:
+                print("our search (%s) on the reference's own reference pictures: %d cells; same vector %.1f %%, within 1/4 sample %.1f %%, our SAD <= the SAD at its "
+                      "vector %.1f %%; mean SAD ours %.1f, reference %.1f" % (name, k[0], 100.0 * k[1] / k[0], 100.0 * k[2] / k[0], 100.0 * k[3] / k[0], k[4] / k[0], k[5] / k[0]))
+                for b, rng in enumerate(("< 2", "2-8", "8-16", "16-32", ">= 32")):
+                    if k[8 + 3 * b]:
+                        print("    reference vector %5s samples: %6d cells, mean SAD ours %.0f, reference %.0f" % (rng, k[8 + 3 * b], k[9 + 3 * b] / k[8 + 3 * b], k[10 + 3 * b] / k[8 + 3 * b]))
+        O.ora_replay_compare_sao.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        z = (C.c_long * 16)()
+        O.ora_replay_compare_sao(ps, 0, npic, src.ctypes.data, 3 if preset in ("ultrafast", "superfast", "veryfast", "fast") else 4, z)
+        for g, name in ((0, "luma"), (1, "chroma")):
+            k = z[8 * g:8 * g + 7]
+            if k[0]:
+                print("SAO %s: %d CTUs; reference on %.1f %%, ours on %.1f %%, same type %.1f %%; both on with the same type %d: same class/band %.1f %%, same offsets %.1f %%"
+                      % (name, k[0], 100.0 * k[1] / k[0], 100.0 * k[2] / k[0], 100.0 * k[3] / k[0], k[4], 100.0 * k[5] / max(k[4], 1), 100.0 * k[6] / max(k[4], 1)))
     return 1 if rc or bad else 0
 
 
